@@ -1,0 +1,178 @@
+/*
+ * zsv_b200.h -- C ABI of libzsv_b200.so, the B200 (sm_100a) arithmetic under the reference's
+ * nn.Module protocol for the R(2+1)D-18 / C3D training hot path and the zero-shot nearest-class search.
+ *
+ * The reference (damien911224/ZeroShotVideoClassification) has no FFI of its own: its seam is
+ * PyTorch's nn.Module.forward / Tensor.backward (main.py:174, main.py:195).  Each entry point below
+ * names the reference call site whose arithmetic it replaces.  Conventions:
+ *   - every pointer is a CUDA device pointer owned by the caller (PyTorch); the library never
+ *     allocates, frees or retains device memory and writes only through its out-parameters;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it, no
+ *     host synchronisation, CUDA-graph capturable;
+ *   - return value 0 = success, otherwise a zsv_status code; zsv_last_error() returns a
+ *     thread-local message.  There is no CPU fallback: without a sm_100 device every compute
+ *     entry point fails with ZSV_ERR_CUDA.
+ *   - activations are bf16, channels-last NDHWC, channel pitch padded to a multiple of 8
+ *     (zsv_cpad); pad lanes are written as zero by the producers.
+ */
+#ifndef ZSV_B200_H_
+#define ZSV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum zsv_status {
+    ZSV_OK = 0,
+    ZSV_ERR_BAD_ARG = 1,     /* shape / stride / alignment not supported */
+    ZSV_ERR_CUDA = 2,        /* CUDA runtime or driver call failed (message has the CUDA error) */
+    ZSV_ERR_WORKSPACE = 3,   /* caller-provided workspace too small */
+    ZSV_ERR_UNSUPPORTED = 4  /* configuration outside what the kernels implement */
+} zsv_status;
+
+/* Thread-local description of the last non-zero status returned on this thread. */
+const char* zsv_last_error(void);
+/* ABI version (bumped on any signature change). */
+int zsv_abi_version(void);
+/* Channel pitch used for a tensor with c channels: c rounded up to a multiple of 8. */
+int zsv_cpad(int c);
+
+/* ------------------------------------------------------------------------------------------------
+ * Convolution descriptor.  Describes one nn.Conv3d of the reference:
+ *   resnet.py:40-52 (Conv2Plus1D spatial 1x3x3 / temporal 3x1x1), resnet.py:181-184 (R2Plus1dStem),
+ *   resnet.py:271 (1x1x1 stride-2 downsample), network.py:102-117 (C3D 3x3x3 + bias).
+ * Strides must be 1 or 2 per dimension.
+ * ---------------------------------------------------------------------------------------------- */
+#define ZSV_CONV_X_NDHWC 0   /* input activation: bf16 [N][T][H][W][cpad(Cin)] */
+#define ZSV_CONV_X_WFOLD 1   /* first-layer input: bf16 [N][T][H][W+8][8], 3..pw zero columns on the left
+                                (produced by zsv_repack_input with layout=1); requires cpad(Cin)*kw <= 64 */
+typedef struct zsv_conv_desc {
+    int32_t N, T, H, W;      /* input extents (logical, unpadded) */
+    int32_t Cin, Cout;       /* true channel counts */
+    int32_t kt, kh, kw;      /* filter extents */
+    int32_t st, sh, sw;      /* strides (1 or 2) */
+    int32_t pt, ph, pw;      /* zero padding */
+    int32_t x_layout;        /* ZSV_CONV_X_* */
+} zsv_conv_desc;
+
+/* Output extents of the convolution: out[0..2] = To, Ho, Wo. */
+int zsv_conv3d_out_shape(const zsv_conv_desc* d, int32_t out[3]);
+
+/* Bytes of the packed bf16 weight images.  which = 0: fprop image [tap][Cout][cpad(K)];
+ * which = 1: dgrad image [tap][Cin][cpad(Cout)]. */
+size_t zsv_conv3d_packed_weight_bytes(const zsv_conv_desc* d, int which);
+
+/* fp32 [Cout][Cin][kt][kh][kw] (the state_dict layout, resnet.py:40) -> packed bf16 images.
+ * Either output may be NULL. */
+int zsv_conv3d_pack_weight(const zsv_conv_desc* d, const float* w, void* w_fprop, void* w_dgrad, void* stream);
+
+/* Number of rows of the per-tile BatchNorm partial-statistics buffers written by fprop. */
+int zsv_conv3d_stat_rows(const zsv_conv_desc* d);
+
+/* Forward convolution (aten::conv3d reached from resnet.py:40-52,181-184,271; network.py:102-117).
+ *   x       : bf16 input in d->x_layout
+ *   w_fprop : packed weights (which = 0)
+ *   y       : bf16 [N][To][Ho][Wo][cpad(Cout)]
+ *   part_sum, part_sq : optional fp32 [stat_rows][cpad(Cout)] per-tile sum / sum of squares of the
+ *             bf16-rounded outputs (BatchNorm3d batch statistics, resnet.py:48); NULL to skip
+ *   bias    : optional fp32 [Cout] (C3D); relu != 0 applies max(.,0) in the epilogue (network.py:147) */
+int zsv_conv3d_fprop(const zsv_conv_desc* d, const void* x, const void* w_fprop, void* y, float* part_sum,
+                     float* part_sq, const float* bias, int relu, void* stream);
+
+/* Data gradient (autograd of conv3d w.r.t. its input, triggered at main.py:195).
+ *   dy : bf16 [N][To][Ho][Wo][cpad(Cout)];  w_dgrad : packed weights (which = 1)
+ *   dx : bf16 [N][T][H][W][cpad(Cin)];  addend: optional bf16 tensor shaped like dx added in the
+ *        epilogue (residual-branch gradient, resnet.py:103-111). */
+int zsv_conv3d_dgrad(const zsv_conv_desc* d, const void* dy, const void* w_dgrad, void* dx, const void* addend,
+                     void* stream);
+
+/* Weight gradient (autograd of conv3d w.r.t. its weight).  dw is fp32 in the state_dict layout
+ * [Cout][Cin][kt][kh][kw]; db (optional, fp32 [Cout]) receives the bias gradient.  The workspace holds
+ * split-K partial tiles; zsv_conv3d_wgrad_workspace gives the required size. */
+size_t zsv_conv3d_wgrad_workspace(const zsv_conv_desc* d);
+int zsv_conv3d_wgrad(const zsv_conv_desc* d, const void* x, const void* dy, float* dw, float* db, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout conversion at the PyTorch boundary.
+ * ---------------------------------------------------------------------------------------------- */
+/* fp32 NCDHW clip batch (main.py:167, network.py:534-535) -> bf16 channels-last.
+ * layout 0: [N][T][H][W][cpad(C)]; layout 1 (ZSV_CONV_X_WFOLD): [N][T][H][W+8][8] with `wpad_left`
+ * zero columns on the left. */
+int zsv_repack_input(const float* x, void* out, int N, int C, int T, int H, int W, int layout, int wpad_left,
+                     void* stream);
+/* bf16 NDHWC (pitch cpad(C)) <-> fp32 NCDHW, used by the per-module autograd shims and tests. */
+int zsv_ndhwc_to_ncdhw(const void* x, float* out, int N, int C, int T, int H, int W, void* stream);
+int zsv_ncdhw_to_ndhwc(const float* x, void* out, int N, int C, int T, int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm3d (+ReLU, +residual), training mode (resnet.py:48,95,97,182,185,272; BasicBlock.forward
+ * resnet.py:102-113).  rows = N*T*H*W positions, C true channels, pitch = cpad(C).
+ * ---------------------------------------------------------------------------------------------- */
+/* Reduce per-tile partials to batch mean / biased variance; emit scale = gamma*invstd,
+ * shift = beta - mean*scale, mean, invstd (all fp32 [cpad(C)]); update running_mean / running_var
+ * (momentum, unbiased variance) in place when they are non-NULL. */
+int zsv_bn_finalize(const float* part_sum, const float* part_sq, int part_rows, int C, long long count,
+                    const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum,
+                    float eps, float* scale, float* shift, float* mean, float* invstd, void* stream);
+/* Eval mode: scale/shift from running statistics (main.py:229). */
+int zsv_bn_eval_scale_shift(int C, const float* gamma, const float* beta, const float* running_mean,
+                            const float* running_var, float eps, float* scale, float* shift, void* stream);
+/* out = act( y*scale + shift  [+ y2*scale2 + shift2]  [+ residual] ), act = ReLU when relu != 0.
+ * y2/scale2/shift2 (BatchNorm'd downsample branch, resnet.py:107-108) and residual (identity branch)
+ * are optional. */
+int zsv_bn_apply(const void* y, const float* scale, const float* shift, const void* y2, const float* scale2,
+                 const float* shift2, const void* residual, void* out, long long rows, int C, int relu,
+                 void* stream);
+/* Backward of out = relu?(bn(y) [+ bn2(y2)] [+ residual]):
+ *   g    : bf16 gradient w.r.t. out;  out: bf16 forward output (ReLU mask), may be NULL when relu == 0
+ *   pass 1 (reduce): per-block partial sums of dz and dz*xhat for y (and y2) -> workspace
+ *   pass 2 (apply) : dy = scale*(dz - mean(dz) - xhat*mean(dz*xhat)); optional dy2; optional dz
+ *                    written out (gradient flowing into the identity residual).
+ *   dgamma/dbeta are fp32 [C].  Workspace size from zsv_bn_bwd_workspace. */
+size_t zsv_bn_bwd_workspace(int C);
+int zsv_bn_bwd(const void* g, const void* out, int relu, const void* y, const float* mean, const float* invstd,
+               const float* gamma, const void* y2, const float* mean2, const float* invstd2, const float* gamma2,
+               void* dy, void* dy2, void* dz, float* dgamma, float* dbeta, float* dgamma2, float* dbeta2,
+               long long rows, int C, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Embedding head: mean over (T,H,W) -> Linear(512,512) -> ReLU -> Linear(512,300) -> L2 normalise
+ * (network.py:595-596, MLP network.py:603-618, F.normalize).  All fp32 except the bf16 feature map.
+ * ---------------------------------------------------------------------------------------------- */
+/* feat: bf16 [B][P][cpad(C)] (P = T*H*W positions).  Saves pooled [B][C], hidden [B][Hd], o-norm [B]. */
+int zsv_head_fwd(const void* feat, int B, int P, int C, const float* w1, const float* b1, int Hd, const float* w2,
+                 const float* b2, int E, float eps, float* pooled, float* hidden, float* onorm, float* emb,
+                 void* stream);
+/* Backward given demb [B][E]; grads for w1,b1,w2,b2 (fp32, overwritten) and dfeat (bf16 [B][P][cpad(C)]). */
+int zsv_head_bwd(const float* demb, const float* emb, const float* onorm, const float* pooled, const float* hidden,
+                 int B, int P, int C, const float* w1, int Hd, const float* w2, int E, float eps, float* dw1,
+                 float* db1, float* dw2, float* db2, void* dfeat, float* scratch, void* stream);
+/* MSELoss(mean) forward + gradient (main.py:130,179): loss[0] = mean((emb-target)^2),
+ * demb = 2*(emb-target)/(B*E) * grad_scale. */
+int zsv_mse_fwd_bwd(const float* emb, const float* target, int B, int E, float grad_scale, float* loss, float* demb,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Zero-shot nearest-class search (main.py:183, main.py:321-322: scipy cdist(...,'cosine') then
+ * argmin / argsort[:, :k]).  fp32 inputs promoted to fp64 exactly like scipy; ties resolved towards
+ * the lowest class index.  idx_out: int64 [N][k], k <= 8; dist_out (optional): fp64 [N][k].
+ * ---------------------------------------------------------------------------------------------- */
+int zsv_nearest_class(const float* emb, const float* cls, int N, int C, int D, int k, int64_t* idx_out,
+                      double* dist_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * MaxPool3d for C3D (network.py:103-118): kernel == stride, optional H/W padding with -inf.
+ * ---------------------------------------------------------------------------------------------- */
+int zsv_maxpool3d_fwd(const void* x, void* y, int32_t* argmax, int N, int T, int H, int W, int C, int kt, int kh,
+                      int kw, int pt, int ph, int pw, void* stream);
+int zsv_maxpool3d_bwd(const void* dy, const int32_t* argmax, void* dx, int N, int T, int H, int W, int C, int kt,
+                      int kh, int kw, int pt, int ph, int pw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZSV_B200_H_ */

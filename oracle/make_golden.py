@@ -1,0 +1,124 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/* from the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference, scipy):
+
+    python -m oracle.make_golden
+
+It imports the reference's own ``resnet.py`` / ``network.py`` (with ``sys.modules`` stubs for the unused
+top-level imports ``gensim`` and ``clip``, network.py:8,19), runs its forward/backward on CPU fp32 through
+stock PyTorch, and restates ``compute_accuracy`` (main.py:316-325) with scipy exactly as written there
+(main.py itself cannot be imported: it parses argv and builds datasets at import time, main.py:55-137).
+The reference cannot travel to the GPU box, so the outputs are committed as small fixtures.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import types
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def import_reference():
+    gensim = types.ModuleType("gensim")
+    gm = types.ModuleType("gensim.models")
+    gm.KeyedVectors = type("KeyedVectors", (), {})
+    gensim.models = gm
+    sys.modules.setdefault("gensim", gensim)
+    sys.modules.setdefault("gensim.models", gm)
+    sys.modules.setdefault("clip", types.ModuleType("clip"))
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import network  # noqa: E402  (the reference's network.py)
+    return network
+
+
+def checksum(t: torch.Tensor):
+    t = t.detach().double().flatten()
+    idx = torch.linspace(0, t.numel() - 1, steps=min(8, t.numel())).long()
+    return {"sum": float(t.sum()), "abs": float(t.abs().sum()), "sq": float((t * t).sum()),
+            "samples": [float(v) for v in t[idx]]}
+
+
+def synthetic_batch(B, T, H, W, seed, n_classes=101):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 1, 3, T, H, W, generator=g)
+    cls = F.normalize(torch.randn(n_classes, 300, generator=g))
+    labels = torch.randint(0, n_classes, (B,), generator=g)
+    return x, cls[labels], labels
+
+
+def reference_step(network, B, T, H, W, seed):
+    """main.py:170-195 on the reference modules (fp32 CPU, no optimizer step), with forward hooks recording
+    every conv / block output."""
+    torch.manual_seed(seed)
+    opt = SimpleNamespace(network="r2plus1d_18", fixconvs=False, nopretrained=False)
+    model = network.get_network(opt).train()
+    init = {k: checksum(v) for k, v in model.state_dict().items() if v.is_floating_point()}
+    keys = {k: list(v.shape) for k, v in model.state_dict().items()}
+    x, z, _ = synthetic_batch(B, T, H, W, seed + 100)
+    acts = {}
+
+    def hook(name):
+        def fn(_m, _i, o):
+            acts[name] = checksum(o)
+        return fn
+
+    for name, m in model.model.named_modules():
+        if isinstance(m, torch.nn.Conv3d) or (name.startswith("layer") and name.count(".") == 1):
+            m.register_forward_hook(hook(name))
+    emb, none = model(x)
+    assert none is None
+    loss = torch.nn.MSELoss()(emb, z)
+    loss.backward()
+    grads = {k: checksum(p.grad) for k, p in model.named_parameters() if p.grad is not None}
+    dead = sorted(k for k, p in model.named_parameters() if p.grad is None)
+    bn_after = {k: checksum(v) for k, v in model.state_dict().items()
+                if k.endswith(("running_mean", "running_var")) and k.startswith("model.")}
+    return dict(config=dict(B=B, T=T, H=H, W=W, seed=seed), emb=emb.detach().numpy().tolist(), loss=float(loss),
+                acts=acts, grads=grads, dead=dead, bn_after=bn_after), init, keys
+
+
+def nearest_fixture():
+    """main.py:321-322 restated with scipy exactly as the reference calls it."""
+    from scipy.spatial.distance import cdist
+    rng = np.random.default_rng(2026)
+    out = {}
+    for C in (51, 101, 200):
+        emb = rng.standard_normal((400, 300)).astype(np.float32)
+        emb /= np.linalg.norm(emb, axis=1, keepdims=True)
+        cls = rng.standard_normal((C, 300)).astype(np.float32)
+        cls /= np.linalg.norm(cls, axis=1, keepdims=True)
+        emb[:10] = cls[:10]                                  # exact hits: distance 0
+        emb[10:20] = cls[:10] + 1e-4 * emb[10:20]            # near ties
+        d = cdist(emb, cls, "cosine")
+        out[f"emb_{C}"] = emb
+        out[f"cls_{C}"] = cls
+        out[f"dist_{C}"] = d
+        out[f"argmin_{C}"] = d.argmin(1)
+        out[f"top5_{C}"] = d.argsort(1)[:, :5]
+    np.savez_compressed(os.path.join(OUT, "nearest_scipy.npz"), **out)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    network = import_reference()
+    small, init, keys = reference_step(network, 2, 8, 32, 32, seed=0)
+    json.dump(keys, open(os.path.join(OUT, "r2plus1d_state_dict_keys.json"), "w"), indent=0)
+    json.dump(init, open(os.path.join(OUT, "r2plus1d_init_seed0.json"), "w"))
+    json.dump(small, open(os.path.join(OUT, "r2plus1d_step_small.json"), "w"))
+    full, _, _ = reference_step(network, 2, 16, 112, 112, seed=0)   # BASELINE.json config 1
+    json.dump(full, open(os.path.join(OUT, "r2plus1d_step_bs2_16x112.json"), "w"))
+    nearest_fixture()
+    print("golden fixtures written to", OUT)
+
+
+if __name__ == "__main__":
+    main()

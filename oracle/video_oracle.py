@@ -1,0 +1,243 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the R(2+1)D-18 / C3D embedding networks.
+
+A functional, state-dict driven restatement (plain PyTorch CPU, fp32 or fp64) of the arithmetic the
+reference reaches through its nn.Module tree.  Every function cites the reference lines it follows.
+It is deliberately slow and simple; parity tests compare the CUDA path against it.
+
+Pinned against the reference itself by ``oracle/make_golden.py`` -> ``tests/golden/`` (the reference has
+no tests of its own; see oracle/__init__.py).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+BN_EPS = 1e-5        # nn.BatchNorm3d default (resnet.py:48)
+BN_MOMENTUM = 0.1    # nn.BatchNorm3d default
+
+
+def midplanes(inplanes: int, planes: int) -> int:
+    """Width of the factorised (2+1)D convolution -- resnet.py:91."""
+    return (inplanes * planes * 3 * 3 * 3) // (inplanes * 3 * 3 + 3 * planes)
+
+
+def batchnorm_train(x: Tensor, sd: Dict[str, Tensor], prefix: str, trace: Optional[dict] = None,
+                    update_running: bool = True) -> Tensor:
+    """nn.BatchNorm3d in training mode (resnet.py:48,95,97,182,185,272): batch mean / biased variance over
+    (N,T,H,W); running stats updated with momentum 0.1 and the unbiased variance."""
+    dims = (0, 2, 3, 4)
+    mean = x.mean(dims)
+    var = x.var(dims, unbiased=False)
+    n = x.numel() // x.shape[1]
+    if update_running:
+        with torch.no_grad():
+            sd[prefix + ".running_mean"].mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * mean.detach())
+            sd[prefix + ".running_var"].mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * var.detach() * n / max(n - 1, 1))
+            sd[prefix + ".num_batches_tracked"].add_(1)
+    shape = (1, -1, 1, 1, 1)
+    xhat = (x - mean.view(shape)) / torch.sqrt(var.view(shape) + BN_EPS)
+    y = xhat * sd[prefix + ".weight"].view(shape) + sd[prefix + ".bias"].view(shape)
+    if trace is not None:
+        trace[prefix + ":mean"] = mean.detach()
+        trace[prefix + ":var"] = var.detach()
+    return y
+
+
+def batchnorm_eval(x: Tensor, sd: Dict[str, Tensor], prefix: str) -> Tensor:
+    """nn.BatchNorm3d in eval mode (main.py:229): running statistics."""
+    shape = (1, -1, 1, 1, 1)
+    inv = torch.rsqrt(sd[prefix + ".running_var"].view(shape) + BN_EPS)
+    return (x - sd[prefix + ".running_mean"].view(shape)) * inv * sd[prefix + ".weight"].view(shape) + \
+        sd[prefix + ".bias"].view(shape)
+
+
+class _Net:
+    """Shared plumbing: conv / bn helpers that record per-layer tensors when tracing."""
+
+    def __init__(self, sd: Dict[str, Tensor], train: bool, trace: Optional[dict]):
+        self.sd, self.train, self.trace = sd, train, trace
+
+    def conv(self, x: Tensor, name: str, stride, padding) -> Tensor:
+        y = F.conv3d(x, self.sd[name + ".weight"], self.sd.get(name + ".bias"), stride=stride, padding=padding)
+        if self.trace is not None:
+            if y.requires_grad:
+                y.retain_grad()
+            self.trace[name] = y
+        return y
+
+    def bn(self, x: Tensor, name: str) -> Tensor:
+        y = batchnorm_train(x, self.sd, name, self.trace) if self.train else batchnorm_eval(x, self.sd, name)
+        if self.trace is not None:
+            if y.requires_grad:
+                y.retain_grad()
+            self.trace[name] = y
+        return y
+
+
+def _conv2plus1d(net: _Net, x: Tensor, prefix: str, stride: int) -> Tensor:
+    """Conv2Plus1D (resnet.py:37-57): spatial 1x3x3 (stride (1,s,s)) -> BN(mid) -> ReLU -> temporal 3x1x1
+    (stride (s,1,1)); no bias."""
+    x = net.conv(x, prefix + ".0", (1, stride, stride), (0, 1, 1))
+    x = F.relu(net.bn(x, prefix + ".1"))
+    return net.conv(x, prefix + ".3", (stride, 1, 1), (1, 0, 0))
+
+
+def _basic_block(net: _Net, x: Tensor, prefix: str, stride: int, has_ds: bool) -> Tensor:
+    """BasicBlock.forward (resnet.py:102-113)."""
+    residual = x
+    out = _conv2plus1d(net, x, prefix + ".conv1.0", stride)
+    out = F.relu(net.bn(out, prefix + ".conv1.1"))
+    out = _conv2plus1d(net, out, prefix + ".conv2.0", 1)
+    out = net.bn(out, prefix + ".conv2.1")
+    if has_ds:  # resnet.py:268-273: 1x1x1 conv, stride (s,s,s), then BN
+        residual = net.conv(x, prefix + ".downsample.0", (stride, stride, stride), (0, 0, 0))
+        residual = net.bn(residual, prefix + ".downsample.1")
+    out = F.relu(out + residual)
+    if net.trace is not None:
+        if out.requires_grad:
+            out.retain_grad()
+        net.trace[prefix] = out
+    return out
+
+
+def r2plus1d_18_features(sd: Dict[str, Tensor], x: Tensor, train: bool = True, trace: Optional[dict] = None,
+                         prefix: str = "model.") -> Tensor:
+    """VideoResNet.forward up to layer4 (resnet.py:243-249) for r2plus1d_18 (resnet.py:342-362):
+    x [B,3,T,H,W] -> f [B,512,T/8,H/16,W/16]."""
+    net = _Net({k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}, train, trace)
+    # R2Plus1dStem (resnet.py:176-187)
+    x = net.conv(x, "stem.0", (1, 2, 2), (0, 3, 3))
+    x = F.relu(net.bn(x, "stem.1"))
+    x = net.conv(x, "stem.3", (1, 1, 1), (1, 0, 0))
+    x = F.relu(net.bn(x, "stem.4"))
+    if trace is not None:
+        trace["stem"] = x
+    for li, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):  # _make_layer (resnet.py:258-281), layers=[2,2,2,2]
+        x = _basic_block(net, x, f"layer{li}.0", stride, has_ds=(li != 1))
+        x = _basic_block(net, x, f"layer{li}.1", 1, has_ds=False)
+    return x
+
+
+def embedding_head(sd: Dict[str, Tensor], feats: Tensor) -> Tensor:
+    """network.py:595-596 with MLP network.py:613-618: mean over (T,H,W), Linear-ReLU-Linear, F.normalize."""
+    f = feats.mean(dim=(2, 3, 4))
+    h = F.relu(F.linear(f, sd["output2emb_proj.layers.0.weight"], sd["output2emb_proj.layers.0.bias"]))
+    o = F.linear(h, sd["output2emb_proj.layers.1.weight"], sd["output2emb_proj.layers.1.bias"])
+    return F.normalize(o)
+
+
+def model_forward(sd: Dict[str, Tensor], x: Tensor, train: bool = True, trace: Optional[dict] = None) -> Tensor:
+    """network.Model.forward (network.py:533-600), live lines only: x [B,nc,3,T,H,W] -> emb [B*nc,300]."""
+    bs, nc = x.shape[:2]
+    x = x.reshape(bs * nc, *x.shape[2:])
+    feats = r2plus1d_18_features(sd, x, train, trace)
+    if trace is not None:
+        trace["feats"] = feats
+    return embedding_head(sd, feats)
+
+
+def c3d_forward(sd: Dict[str, Tensor], x: Tensor, train: bool = False) -> Tensor:
+    """network.C3D.forward (network.py:143-180).  Dropout(p=0.1) (network.py:167) is only applied in train
+    mode; parity tests run with train=False (or p=0) because the mask is not reproducible across devices."""
+    bs, nc = x.shape[:2]
+    h = x.reshape(bs * nc, *x.shape[2:])
+
+    def conv(name, t):
+        return F.relu(F.conv3d(t, sd[name + ".weight"], sd[name + ".bias"], padding=1))
+
+    h = F.max_pool3d(conv("conv1", h), (1, 2, 2), (1, 2, 2))
+    h = F.max_pool3d(conv("conv2", h), (2, 2, 2), (2, 2, 2))
+    h = F.max_pool3d(conv("conv3b", conv("conv3a", h)), (2, 2, 2), (2, 2, 2))
+    h = F.max_pool3d(conv("conv4b", conv("conv4a", h)), (2, 2, 2), (2, 2, 2))
+    h = F.max_pool3d(conv("conv5b", conv("conv5a", h)), (2, 2, 2), (2, 2, 2), padding=(0, 1, 1))
+    h = h.reshape(-1, 8192)
+    h = F.relu(F.linear(h, sd["fc6.weight"], sd["fc6.bias"]))
+    if train:
+        h = F.dropout(h, p=0.10, training=True)
+    h = h.reshape(bs, nc, -1).mean(1).reshape(bs, -1)
+    h = F.linear(h, sd["regressor.weight"], sd["regressor.bias"])
+    return F.normalize(h, dim=-1)
+
+
+def mse_loss(emb: Tensor, target: Tensor) -> Tensor:
+    """nn.MSELoss() with mean reduction (main.py:130,179)."""
+    return ((emb - target) ** 2).mean()
+
+
+def train_step_grads(sd: Dict[str, Tensor], x: Tensor, target: Tensor, trace: Optional[dict] = None,
+                     loss_scale: float = 1.0) -> Tuple[Tensor, Tensor, Dict[str, Tensor]]:
+    """One forward + backward of main.py:170-195 (no optimizer): returns (emb, loss, grads by state-dict key)."""
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()
+              and not k.endswith(("running_mean", "running_var"))}
+    work = dict(sd)
+    work.update(params)
+    emb = model_forward(work, x, train=True, trace=trace)
+    loss = mse_loss(emb, target)
+    (loss * loss_scale).backward()
+    grads = {k: p.grad for k, p in params.items() if p.grad is not None}
+    return emb.detach(), loss.detach(), grads
+
+
+# ----------------------------------------------------------------------------------------------------
+# single ops in channels-first fp32, used by per-kernel parity tests
+# ----------------------------------------------------------------------------------------------------
+def conv3d(x: Tensor, w: Tensor, bias: Optional[Tensor], stride, padding) -> Tensor:
+    return F.conv3d(x, w, bias, stride=stride, padding=padding)
+
+
+def conv3d_grads(x: Tensor, w: Tensor, dy: Tensor, stride, padding) -> Tuple[Tensor, Tensor]:
+    """(dx, dw) of conv3d by autograd."""
+    x = x.detach().clone().requires_grad_(True)
+    w = w.detach().clone().requires_grad_(True)
+    F.conv3d(x, w, None, stride=stride, padding=padding).backward(dy)
+    return x.grad, w.grad
+
+
+def synthetic_state_dict_r2plus1d(seed: int = 0, dtype=torch.float32) -> Dict[str, Tensor]:
+    """Random-init state dict with the reference's key names, shapes and init scheme (resnet.py:226-236:
+    Kaiming-normal fan_out for convs, BN weight 1 / bias 0; nn.Linear default init for the MLP).  Only the
+    live parameters of network.Model are created (the dead Transformer branch, network.py:500-514, never
+    reaches the output).  NOT bit-identical to constructing the reference modules (different RNG order); use
+    the golden fixtures for that."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+
+    def conv(name, cout, cin, k):
+        fan_out = cout * k[0] * k[1] * k[2]
+        sd[name + ".weight"] = torch.randn(cout, cin, *k, generator=g, dtype=dtype) * (2.0 / fan_out) ** 0.5
+
+    def bn(name, c):
+        sd[name + ".weight"] = torch.ones(c, dtype=dtype)
+        sd[name + ".bias"] = torch.zeros(c, dtype=dtype)
+        sd[name + ".running_mean"] = torch.zeros(c, dtype=dtype)
+        sd[name + ".running_var"] = torch.ones(c, dtype=dtype)
+        sd[name + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+
+    def linear(name, cout, cin):
+        bound = 1.0 / cin ** 0.5
+        sd[name + ".weight"] = (torch.rand(cout, cin, generator=g, dtype=dtype) * 2 - 1) * bound
+        sd[name + ".bias"] = (torch.rand(cout, generator=g, dtype=dtype) * 2 - 1) * bound
+
+    conv("model.stem.0", 45, 3, (1, 7, 7)); bn("model.stem.1", 45)
+    conv("model.stem.3", 64, 45, (3, 1, 1)); bn("model.stem.4", 64)
+    inplanes = 64
+    for li, planes in ((1, 64), (2, 128), (3, 256), (4, 512)):
+        for bi in range(2):
+            p = f"model.layer{li}.{bi}"
+            cin = inplanes if bi == 0 else planes
+            mid1 = midplanes(cin, planes)
+            conv(p + ".conv1.0.0", mid1, cin, (1, 3, 3)); bn(p + ".conv1.0.1", mid1)
+            conv(p + ".conv1.0.3", planes, mid1, (3, 1, 1)); bn(p + ".conv1.1", planes)
+            # resnet.py:91,97: conv2 reuses the block's midplanes (computed from the block's inplanes)
+            conv(p + ".conv2.0.0", mid1, planes, (1, 3, 3)); bn(p + ".conv2.0.1", mid1)
+            conv(p + ".conv2.0.3", planes, mid1, (3, 1, 1)); bn(p + ".conv2.1", planes)
+            if bi == 0 and li != 1:
+                conv(p + ".downsample.0", planes, cin, (1, 1, 1)); bn(p + ".downsample.1", planes)
+        inplanes = planes
+    linear("output2emb_proj.layers.0", 512, 512)
+    linear("output2emb_proj.layers.1", 300, 512)
+    return sd

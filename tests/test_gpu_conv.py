@@ -1,0 +1,157 @@
+"""GPU parity of the implicit-GEMM convolution kernels (fprop / dgrad / wgrad) against the CPU oracle.
+
+Tolerances: operands are bf16-rounded identically on both sides, accumulation is fp32, outputs are rounded to
+bf16 (fprop/dgrad) -> 1e-2 relative to the tensor scale (north_star), wgrad fp32 -> 2e-3.
+"""
+import pytest
+import torch
+
+from oracle import video_oracle as vo
+from tests.helpers import bf16_round, cpad, from_ndhwc, rel_err, to_ndhwc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-2
+
+# (name, N, T, H, W, Cin, Cout, kernel, stride, padding)
+CASES = [
+    ("spatial_64_64", 2, 2, 16, 16, 64, 64, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("spatial_64_144", 2, 4, 24, 24, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("temporal_144_64", 2, 6, 12, 12, 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0)),
+    ("temporal_45_64", 2, 4, 10, 10, 45, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0)),
+    ("spatial_s2_64_230", 2, 2, 20, 20, 64, 230, (1, 3, 3), (1, 2, 2), (0, 1, 1)),
+    ("temporal_s2_230_128", 1, 8, 6, 6, 230, 128, (3, 1, 1), (2, 1, 1), (1, 0, 0)),
+    ("downsample_64_128", 2, 4, 12, 12, 64, 128, (1, 1, 1), (2, 2, 2), (0, 0, 0)),
+    ("spatial_256_460", 1, 2, 14, 14, 256, 460, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("spatial_odd_hw", 3, 3, 7, 7, 128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("spatial_s2_odd", 1, 2, 15, 13, 64, 96, (1, 3, 3), (1, 2, 2), (0, 1, 1)),
+    ("c3d_27tap", 1, 4, 8, 8, 64, 128, (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+]
+
+
+def _make(case, seed=0):
+    name, N, T, H, W, cin, cout, k, s, p = case
+    g = torch.Generator().manual_seed(seed)
+    x = bf16_round(torch.randn(N, cin, T, H, W, generator=g))
+    w = bf16_round(torch.randn(cout, cin, *k, generator=g) * (2.0 / (cin * k[0] * k[1] * k[2])) ** 0.5)
+    return x, w
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_fprop_matches_oracle(case):
+    from zeroshotvideoclassification_b200 import ops
+    name, N, T, H, W, cin, cout, k, s, p = case
+    x, w = _make(case)
+    ref = vo.conv3d(x, w, None, s, p)
+    op = ops.Conv3d(N, T, H, W, cin, cout, k, s, p)
+    wf, _ = op.pack(w.cuda(), need_dgrad=False)
+    y, ps, pq = op.fprop(to_ndhwc(x), wf, stats=True)
+    torch.cuda.synchronize()
+    got = from_ndhwc(y, cout)
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < TOL, name
+    # pad lanes are written as exact zeros
+    if cpad(cout) != cout:
+        assert float(y[..., cout:].float().abs().max()) == 0.0
+    # BatchNorm partial statistics: sums of the bf16-rounded outputs
+    yb = y[..., :cout].float().reshape(-1, cout).double()
+    s1 = ps.double().sum(0)[:cout].cpu()
+    s2 = pq.double().sum(0)[:cout].cpu()
+    assert torch.allclose(s1, yb.sum(0).cpu(), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(s2, (yb * yb).sum(0).cpu(), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_dgrad_matches_oracle(case):
+    from zeroshotvideoclassification_b200 import ops
+    name, N, T, H, W, cin, cout, k, s, p = case
+    x, w = _make(case)
+    y = vo.conv3d(x, w, None, s, p)
+    g = torch.Generator().manual_seed(1)
+    dy = bf16_round(torch.randn(y.shape, generator=g))
+    dx_ref, _ = vo.conv3d_grads(x, w, dy, s, p)
+    op = ops.Conv3d(N, T, H, W, cin, cout, k, s, p)
+    _, wd = op.pack(w.cuda(), need_dgrad=True)
+    dx = op.dgrad(to_ndhwc(dy), wd)
+    torch.cuda.synchronize()
+    assert rel_err(from_ndhwc(dx, cin), dx_ref) < TOL, name
+    # fused residual-gradient add
+    add = bf16_round(torch.randn(x.shape, generator=g))
+    dx2 = op.dgrad(to_ndhwc(dy), wd, addend=to_ndhwc(add))
+    torch.cuda.synchronize()
+    assert rel_err(from_ndhwc(dx2, cin), dx_ref + add) < TOL, name
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_wgrad_matches_oracle(case):
+    from zeroshotvideoclassification_b200 import ops
+    name, N, T, H, W, cin, cout, k, s, p = case
+    x, w = _make(case)
+    y = vo.conv3d(x, w, None, s, p)
+    g = torch.Generator().manual_seed(2)
+    dy = bf16_round(torch.randn(y.shape, generator=g))
+    _, dw_ref = vo.conv3d_grads(x, w, dy, s, p)
+    op = ops.Conv3d(N, T, H, W, cin, cout, k, s, p)
+    dw, _ = op.wgrad(to_ndhwc(x), to_ndhwc(dy))
+    torch.cuda.synchronize()
+    assert dw.shape == dw_ref.shape
+    assert rel_err(dw.cpu(), dw_ref) < 2e-3, name
+
+
+def test_stem_wfold_fprop_and_wgrad():
+    """First layer (resnet.py:181): Cin=3, 1x7x7, stride (1,2,2) through the W-folded input layout."""
+    from zeroshotvideoclassification_b200 import _lib, ops
+    N, T, H, W, cin, cout = 2, 3, 32, 32, 3, 45
+    k, s, p = (1, 7, 7), (1, 2, 2), (0, 3, 3)
+    g = torch.Generator().manual_seed(3)
+    x = bf16_round(torch.randn(N, cin, T, H, W, generator=g))
+    w = bf16_round(torch.randn(cout, cin, *k, generator=g) * 0.1)
+    ref = vo.conv3d(x, w, None, s, p)
+    op = ops.Conv3d(N, T, H, W, cin, cout, k, s, p, x_layout=_lib.X_WFOLD)
+    xin = ops.repack_input(x.cuda(), _lib.X_WFOLD, p[2])
+    wf, wd = op.pack(w.cuda(), need_dgrad=False)
+    assert wd is None
+    y, _, _ = op.fprop(xin, wf, stats=True)
+    torch.cuda.synchronize()
+    assert rel_err(from_ndhwc(y, cout), ref) < TOL
+    dy = bf16_round(torch.randn(ref.shape, generator=g))
+    _, dw_ref = vo.conv3d_grads(x, w, dy, s, p)
+    dw, _ = op.wgrad(xin, to_ndhwc(dy))
+    torch.cuda.synchronize()
+    assert rel_err(dw.cpu(), dw_ref) < 2e-3
+
+
+def test_bias_relu_epilogue():
+    """C3D convolutions carry a bias and a ReLU (network.py:102-117,147-162)."""
+    from zeroshotvideoclassification_b200 import ops
+    N, T, H, W, cin, cout = 1, 4, 8, 8, 64, 64
+    k, s, p = (3, 3, 3), (1, 1, 1), (1, 1, 1)
+    g = torch.Generator().manual_seed(4)
+    x = bf16_round(torch.randn(N, cin, T, H, W, generator=g))
+    w = bf16_round(torch.randn(cout, cin, *k, generator=g) * 0.03)
+    b = torch.randn(cout, generator=g)
+    ref = torch.relu(vo.conv3d(x, w, b, s, p))
+    op = ops.Conv3d(N, T, H, W, cin, cout, k, s, p)
+    wf, _ = op.pack(w.cuda(), need_dgrad=False)
+    y, _, _ = op.fprop(to_ndhwc(x), wf, stats=False, bias=b.cuda(), relu=True)
+    torch.cuda.synchronize()
+    assert rel_err(from_ndhwc(y, cout), ref) < TOL
+
+
+def test_fprop_full_size_layer1_linearity():
+    """BASELINE-size layer1 spatial conv (bs=22, 64->144, 16x56x56): too large for the CPU oracle in seconds,
+    so check against torch's fp32 conv on the same device and the size-independent linearity property."""
+    from zeroshotvideoclassification_b200 import ops
+    N, T, H, W, cin, cout = 22, 16, 56, 56, 64, 144
+    k, s, p = (1, 3, 3), (1, 1, 1), (0, 1, 1)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    xa = torch.randn(N, T, H, W, cin, generator=g, device="cuda").to(torch.bfloat16)
+    w = bf16_round(torch.randn(cout, cin, *k, generator=g, device="cuda") * 0.05)
+    op = ops.Conv3d(N, T, H, W, cin, cout, k, s, p)
+    wf, _ = op.pack(w, need_dgrad=False)
+    ya, _, _ = op.fprop(xa, wf, stats=False)
+    ref = torch.nn.functional.conv3d(xa.float().permute(0, 4, 1, 2, 3), w, None, s, p).permute(0, 2, 3, 4, 1)
+    assert rel_err(ya.float().cpu(), ref.cpu()) < TOL
+    # linearity: conv(2x) == 2 conv(x) exactly in bf16 (power-of-two scaling commutes with rounding)
+    yb, _, _ = op.fprop((xa.float() * 2).to(torch.bfloat16), wf, stats=False)
+    assert torch.equal(yb.float(), ya.float() * 2)

@@ -1,0 +1,53 @@
+"""GPU nearest-class search vs the CPU oracle: indices must be bit-identical (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nearest_oracle as no
+
+pytestmark = pytest.mark.gpu
+
+
+def _unit(rng, n, d=300):
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    return x / np.linalg.norm(x, axis=1, keepdims=True)
+
+
+@pytest.mark.parametrize("C", [51, 101, 200, 664])
+def test_indices_and_distances_bit_exact(C):
+    from zeroshotvideoclassification_b200 import ops
+    rng = np.random.default_rng(C)
+    n = 10000 if C != 664 else 22
+    emb, cls = _unit(rng, n), _unit(rng, C)
+    dist = no.cosine_distance_table(emb, cls)
+    ref = no.topk_lowest_index(dist, 5)
+    idx, d = ops.nearest_class(torch.from_numpy(emb).cuda(), torch.from_numpy(cls).cuda(), k=5, return_dist=True)
+    idx, d = idx.cpu().numpy(), d.cpu().numpy()
+    assert np.array_equal(idx, ref)
+    assert np.array_equal(d, np.take_along_axis(dist, ref, axis=1))      # fp64 distances, bit for bit
+    top1 = ops.nearest_class(torch.from_numpy(emb).cuda(), torch.from_numpy(cls).cuda(), k=1).cpu().numpy()[:, 0]
+    assert np.array_equal(top1, dist.argmin(1))
+
+
+def test_edge_cases():
+    """duplicates of class rows (distance exactly 0), duplicated class rows (lowest index wins), near-ties,
+    zero-norm embedding (all-NaN row -> indices 0..k-1 like numpy argsort), odd D, ragged N."""
+    from zeroshotvideoclassification_b200 import ops
+    rng = np.random.default_rng(7)
+    cls = _unit(rng, 101)
+    cls[57] = cls[12]                      # duplicated class vector
+    emb = np.concatenate([cls[:30], cls[:30] + 1e-4 * _unit(rng, 30), np.zeros((1, 300), np.float32), _unit(rng, 3)])
+    dist = no.cosine_distance_table(emb, cls)
+    ref = no.topk_lowest_index(dist, 5)
+    idx = ops.nearest_class(torch.from_numpy(emb).cuda(), torch.from_numpy(cls).cuda(), k=5).cpu().numpy()
+    assert np.array_equal(idx, ref)
+    assert idx[12, 0] == 12 and idx[12, 1] == 57
+    assert list(idx[60]) == [0, 1, 2, 3, 4]
+    # odd embedding width exercises the tail term of the even/odd accumulation
+    e2, c2 = rng.standard_normal((17, 301)).astype(np.float32), rng.standard_normal((9, 301)).astype(np.float32)
+    got = ops.nearest_class(torch.from_numpy(e2).cuda(), torch.from_numpy(c2).cuda(), k=3, return_dist=True)
+    d2 = no.cosine_distance_table(e2, c2)
+    assert np.array_equal(got[0].cpu().numpy(), no.topk_lowest_index(d2, 3))
+    assert np.array_equal(got[1].cpu().numpy(), np.sort(d2, axis=1)[:, :3])
+    # empty batch
+    assert ops.nearest_class(torch.zeros((0, 300)).cuda(), torch.from_numpy(cls).cuda(), k=1).shape == (0, 1)

@@ -1,0 +1,34 @@
+"""GPU replacement for the reference's scipy-based accuracy code (main.py:182-185, main.py:316-325)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def _as_cuda(x, device=None) -> torch.Tensor:
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    if not x.is_cuda:
+        x = x.to(device if device is not None else "cuda")
+    return x
+
+
+def nearest_class(emb, class_embed, k: int = 1) -> torch.Tensor:
+    """``cdist(emb, class_embed, 'cosine').argsort(1)[:, :k]`` (argmin for k=1), int64 [N,k] on the GPU."""
+    emb = _as_cuda(emb)
+    return ops.nearest_class(emb, _as_cuda(class_embed, emb.device), k)
+
+
+def compute_accuracy(predicted_embed, class_embed, true_embed):
+    """main.py:316-325: returns (top-1 %, top-5 %); labels are recovered from the true embeddings."""
+    assert len(predicted_embed) == len(true_embed), "True and predicted labels must have the same number of samples"
+    pred = _as_cuda(predicted_embed)
+    cls = _as_cuda(class_embed, pred.device)
+    k = min(5, cls.shape[0])
+    y_pred = ops.nearest_class(pred, cls, k)
+    y = ops.nearest_class(_as_cuda(true_embed, pred.device), cls, 1)
+    top1 = (y_pred[:, :1] == y).float().mean() * 100
+    top5 = (y_pred == y).any(dim=1).float().mean() * 100
+    return float(top1), float(top5)

@@ -1,0 +1,1124 @@
+// Implicit-GEMM 3-D convolution for sm_100a: fprop, dgrad (K-major operands) and wgrad (MN-major operands).
+//
+// Replaces the arithmetic PyTorch reaches from the reference's nn.Conv3d call sites
+// (resnet.py:40-52 Conv2Plus1D, resnet.py:181-184 R2Plus1dStem, resnet.py:271 downsample,
+// network.py:102-117 C3D) and their autograd (main.py:195).
+//
+// Design:
+//   * activations are bf16 NDHWC; a GEMM-M tile is a (bw x bh x bt x bn) box of output positions, so one
+//     5-D TMA box load at tap-shifted coordinates *is* the im2col tile: padding comes from TMA
+//     out-of-bounds zero fill, stride-2 convolutions read parity-plane views of the same tensor
+//     (a separate tensor map per parity, doubled strides) so every load is a plain tiled load;
+//   * the TMA writes SWIZZLE_128B tiles that tcgen05.mma consumes directly from shared memory,
+//     accumulating fp32 in TMEM; one elected thread issues the MMAs, one drives the TMA ring;
+//   * the epilogue reads TMEM with tcgen05.ld, rounds to bf16, stores channels-last and emits
+//     per-tile BatchNorm partial statistics (sum, sum of squares of the rounded values);
+//   * dgrad is the same kernel on dy with the transposed weight image, decomposed into output parity
+//     classes for stride 2; wgrad contracts over positions with both operands MN-major
+//     (channels contiguous), split over CTAs along the position axis with deterministic partials.
+#include <algorithm>
+#include <mutex>
+#include <string.h>
+#include <vector>
+
+#include "zsv_internal.h"
+#include "zsv_ptx.cuh"
+
+namespace zsv {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// tensor maps
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// bf16 tensor map with SWIZZLE_128B; dims/box innermost first; strides in bytes for dims 1..rank-1.
+int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+             const uint32_t* box) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(ZSV_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    cuuint64_t gd[5];
+    cuuint64_t gs[4];
+    cuuint32_t bx[5];
+    cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) {
+        gd[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+    }
+    for (int i = 0; i + 1 < rank; ++i) gs[i] = strides[i];
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        return fail(ZSV_ERR_CUDA,
+                    "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] strides [%llu %llu "
+                    "%llu %llu] box [%u %u %u %u %u] base %p",
+                    (int)r, rank, (unsigned long long)gd[0], (unsigned long long)(rank > 1 ? gd[1] : 0),
+                    (unsigned long long)(rank > 2 ? gd[2] : 0), (unsigned long long)(rank > 3 ? gd[3] : 0),
+                    (unsigned long long)(rank > 4 ? gd[4] : 0), (unsigned long long)(rank > 1 ? gs[0] : 0),
+                    (unsigned long long)(rank > 2 ? gs[1] : 0), (unsigned long long)(rank > 3 ? gs[2] : 0),
+                    (unsigned long long)(rank > 4 ? gs[3] : 0), bx[0], rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0,
+                    rank > 3 ? bx[3] : 0, rank > 4 ? bx[4] : 0, base);
+    }
+    return ZSV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel argument blocks
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxTaps = 32;
+constexpr int kMaxMaps = 4;
+constexpr uint32_t kPanelBytes = 128 * 128;  // 128 rows x 128 B
+constexpr int kWfoldWpad = 8;                // extra W columns of the ZSV_CONV_X_WFOLD layout
+
+struct Tap {
+    int16_t map, dw, dh, dt;  // which activation map, coordinate offsets of the box origin
+    int16_t btap, r0, r1, r2; // weight tap index
+};
+
+struct IgemmArgs {
+    int32_t bw, bh, bt, bn;  // box of positions forming one M tile (bw*bh*bt*bn <= 128 rows)
+    int32_t tw, th, tt, tn;  // tile counts per dimension
+    int32_t OW, OH, OT, ON;  // extents of the output position space
+    int32_t kdim;            // reduction channels per tap (true count)
+    int32_t ntaps;
+    int32_t ncols;           // output columns to store (channel pitch, multiple of 8)
+    int32_t nbias;           // valid entries of bias
+    int32_t bn_tile;         // UMMA N
+    int32_t stages;
+    int32_t relu;
+    int32_t tmem_cols;
+    int32_t part_pitch;
+    long long o_sN, o_sT, o_sH, o_sW;  // element strides of the output tensor
+    __nv_bfloat16* out;
+    const __nv_bfloat16* addend;
+    float* part_sum;
+    float* part_sq;
+    const float* bias;
+    Tap taps[kMaxTaps];
+};
+
+struct WgradArgs {
+    int32_t bw, bh, bt, bn;  // box of positions forming one K block (rows multiple of 16, <= 128)
+    int32_t tw, th, tt, tn;
+    int32_t kchunks;         // 64-channel panels per tap on the x side
+    int32_t npanels;         // ntaps * kchunks
+    int32_t ntaps;
+    int32_t ci_store;        // rows (x channels) to store per tap
+    int32_t ci_pitch;        // workspace pitch (x channels)
+    int32_t co_pitch;        // workspace pitch (dy channels) = n_tiles * bn_tile
+    int32_t bn_tile, nbp;    // UMMA N, 64-wide dy panels per stage
+    int32_t stages, tmem_cols;
+    int32_t num_kb, kb_per_split;
+    float* ws;               // [split][tap][ci_pitch][co_pitch]
+    Tap taps[kMaxTaps];
+};
+
+// Transposing butterfly: every lane enters with 16 column values of its own row; on exit lane l holds in
+// v[0] the sum over all 32 lanes of column  8*b4 + 4*b3 + 2*b2 + b1  (bK = bit K of l).
+__device__ __forceinline__ void warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const bool up = lane & 16;
+        const float send = up ? v[i] : v[i + 8];
+        const float keep = up ? v[i + 8] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool up = lane & 8;
+        const float send = up ? v[i] : v[i + 4];
+        const float keep = up ? v[i + 4] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const bool up = lane & 4;
+        const float send = up ? v[i] : v[i + 2];
+        const float keep = up ? v[i + 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+        const bool up = lane & 2;
+        const float send = up ? v[0] : v[1];
+        const float keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-major implicit GEMM: out[pos][co] = sum_{tap, ci} act[pos + tap][ci] * w[tap][co][ci]
+// grid = (M tiles, N tiles); 192 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
+// warps 2..5 epilogue (TMEM lane quadrant = warp % 4).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192, 2)
+igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                    const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+                    const __grid_constant__ CUtensorMap mapB, const __grid_constant__ IgemmArgs P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int stages = P.stages;
+    const uint32_t stageB = static_cast<uint32_t>(P.bn_tile) * 128u;
+    const uint32_t stageBytes = kPanelBytes + stageB;
+    const uint32_t ringBytes = stages * stageBytes;
+    const uint32_t barFull = base + ringBytes;
+    const uint32_t barEmpty = barFull + 8u * stages;
+    const uint32_t barTmem = barEmpty + 8u * stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ringBytes + 16u * stages + 8u);
+    float* stat = reinterpret_cast<float*>(smem + ringBytes + 16u * stages + 16u);  // [2][4][bn_tile]
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(barFull + 8u * s, 1);
+            mbar_init(barEmpty + 8u * s, 1);
+        }
+        mbar_init(barTmem, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), P.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile coordinates
+    int m = blockIdx.x;
+    const int iw = m % P.tw;
+    m /= P.tw;
+    const int ih = m % P.th;
+    m /= P.th;
+    const int it = m % P.tt;
+    const int in_ = m / P.tt;
+    const int w0 = iw * P.bw, h0 = ih * P.bh, t0 = it * P.bt, n0 = in_ * P.bn;
+    const int n_tile = blockIdx.y;
+    const int rows = P.bw * P.bh * P.bt * P.bn;
+    const int kchunks = (P.kdim + 63) >> 6;
+    const int num_kb = P.ntaps * kchunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const CUtensorMap* maps[kMaxMaps] = {&mapA0, &mapA1, &mapA2, &mapA3};
+            const uint32_t tx = static_cast<uint32_t>(rows) * 128u + stageB;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % stages;
+                const uint32_t ph = (kb / stages) & 1;
+                mbar_wait(barEmpty + 8u * s, ph ^ 1u);
+                const int tp = kb / kchunks;
+                const int c0 = (kb - tp * kchunks) << 6;
+                const Tap tap = P.taps[tp];
+                const uint32_t full = barFull + 8u * s;
+                const uint32_t sa = base + s * stageBytes;
+                mbar_expect_tx(full, tx);
+                tma_load_5d(sa, maps[tap.map], full, c0, w0 + tap.dw, h0 + tap.dh, t0 + tap.dt, n0);
+                tma_load_3d(sa + kPanelBytes, &mapB, full, c0, n_tile * P.bn_tile, tap.btap);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, P.bn_tile, 0, 0);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % stages;
+                const uint32_t ph = (kb / stages) & 1;
+                mbar_wait(barFull + 8u * s, ph);
+                tc_fence_after();
+                const int tp = kb / kchunks;
+                const int c0 = (kb - tp * kchunks) << 6;
+                const int ksteps = min(4, (P.kdim - c0 + 15) >> 4);
+                const uint32_t sa = base + s * stageBytes;
+                const uint64_t da = umma_smem_desc(sa, 16, 1024);
+                const uint64_t db = umma_smem_desc(sa + kPanelBytes, 16, 1024);
+                for (int k = 0; k < ksteps; ++k)
+                    umma_bf16(tmem_base, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+                umma_commit(barEmpty + 8u * s);
+            }
+            umma_commit(barTmem);
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int r = row;
+        const int w = r % P.bw;
+        r /= P.bw;
+        const int h = r % P.bh;
+        r /= P.bh;
+        const int t = r % P.bt;
+        const int n = r / P.bt;
+        const bool valid = row < rows && (w0 + w) < P.OW && (h0 + h) < P.OH && (t0 + t) < P.OT && (n0 + n) < P.ON;
+        const long long off = (long long)(n0 + n) * P.o_sN + (long long)(t0 + t) * P.o_sT +
+                              (long long)(h0 + h) * P.o_sH + (long long)(w0 + w) * P.o_sW;
+        const bool do_stats = P.part_sum != nullptr;
+        mbar_wait(barTmem, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        for (int c = 0; c < P.bn_tile; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + c, v);
+            tmem_ld_wait();
+            const int col = n_tile * P.bn_tile + c;
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            if (P.bias != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (col + j < P.nbias) f[j] += __ldg(P.bias + col + j);
+            }
+            if (P.addend != nullptr && valid) {
+#pragma unroll
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                    if (col + 8 * hlf < P.ncols) {
+                        const uint4 a = *reinterpret_cast<const uint4*>(P.addend + off + col + 8 * hlf);
+                        const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            f[8 * hlf + 2 * j] += bf16_lo(aw[j]);
+                            f[8 * hlf + 2 * j + 1] += bf16_hi(aw[j]);
+                        }
+                    }
+                }
+            }
+            if (P.relu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+            if (valid) {
+                if (col < P.ncols)
+                    *reinterpret_cast<uint4*>(P.out + off + col) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                if (col + 8 < P.ncols)
+                    *reinterpret_cast<uint4*>(P.out + off + col + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+            if (do_stats) {
+                float s1[16], s2[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float lo = valid ? bf16_lo(pk[j]) : 0.f;
+                    const float hi = valid ? bf16_hi(pk[j]) : 0.f;
+                    s1[2 * j] = lo;
+                    s1[2 * j + 1] = hi;
+                    s2[2 * j] = lo * lo;
+                    s2[2 * j + 1] = hi * hi;
+                }
+                warp_colsum16(s1, lane);
+                warp_colsum16(s2, lane);
+                if ((lane & 1) == 0) {
+                    const int cj = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
+                                   ((lane >> 1) & 1);
+                    stat[(0 * 4 + q) * P.bn_tile + c + cj] = s1[0];
+                    stat[(1 * 4 + q) * P.bn_tile + c + cj] = s2[0];
+                }
+            }
+        }
+        if (do_stats) {
+            named_bar_sync(1, 128);
+            const int et = threadIdx.x - 64;
+            for (int i = et; i < P.bn_tile; i += 128) {
+                const int col = n_tile * P.bn_tile + i;
+                if (col < P.ncols) {
+                    const float a = ((stat[(0 * 4 + 0) * P.bn_tile + i] + stat[(0 * 4 + 1) * P.bn_tile + i]) +
+                                     stat[(0 * 4 + 2) * P.bn_tile + i]) +
+                                    stat[(0 * 4 + 3) * P.bn_tile + i];
+                    const float b = ((stat[(1 * 4 + 0) * P.bn_tile + i] + stat[(1 * 4 + 1) * P.bn_tile + i]) +
+                                     stat[(1 * 4 + 2) * P.bn_tile + i]) +
+                                    stat[(1 * 4 + 3) * P.bn_tile + i];
+                    P.part_sum[(long long)blockIdx.x * P.part_pitch + col] = a;
+                    P.part_sq[(long long)blockIdx.x * P.part_pitch + col] = b;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, P.tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MN-major weight-gradient GEMM: ws[split][tap][ci][co] = sum_{pos in split} x[pos + tap][ci] * dy[pos][co]
+// A = x panels ([pos rows][64 ci], M = 128 = two panels), B = dy panels ([pos rows][64 co]).
+// grid = (panel pairs, N tiles, splits).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192, 1)
+wgrad_mnmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+                     const __grid_constant__ CUtensorMap mapB, const __grid_constant__ WgradArgs P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int stages = P.stages;
+    const uint32_t stageBytes = (2u + P.nbp) * kPanelBytes;
+    const uint32_t ringBytes = stages * stageBytes;
+    const uint32_t barFull = base + ringBytes;
+    const uint32_t barEmpty = barFull + 8u * stages;
+    const uint32_t barTmem = barEmpty + 8u * stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ringBytes + 16u * stages + 8u);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(barFull + 8u * s, 1);
+            mbar_init(barEmpty + 8u * s, 1);
+        }
+        mbar_init(barTmem, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), P.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int m_tile = blockIdx.x;
+    const int n_tile = blockIdx.y;
+    const int split = blockIdx.z;
+    const int rows = P.bw * P.bh * P.bt * P.bn;
+    const int kb0 = split * P.kb_per_split;
+    const int kb1 = min(P.num_kb, kb0 + P.kb_per_split);
+    const int p0 = 2 * m_tile;
+    const int npan = min(2, P.npanels - p0);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const CUtensorMap* maps[kMaxMaps] = {&mapA0, &mapA1, &mapA2, &mapA3};
+            const uint32_t tx = static_cast<uint32_t>(rows) * 128u * (npan + P.nbp);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const int i = kb - kb0;
+                const int s = i % stages;
+                const uint32_t ph = (i / stages) & 1;
+                mbar_wait(barEmpty + 8u * s, ph ^ 1u);
+                int m = kb;
+                const int iw = m % P.tw;
+                m /= P.tw;
+                const int ih = m % P.th;
+                m /= P.th;
+                const int it = m % P.tt;
+                const int in_ = m / P.tt;
+                const int w0 = iw * P.bw, h0 = ih * P.bh, t0 = it * P.bt, n0 = in_ * P.bn;
+                const uint32_t full = barFull + 8u * s;
+                const uint32_t sa = base + s * stageBytes;
+                mbar_expect_tx(full, tx);
+                for (int j = 0; j < npan; ++j) {
+                    const int p = p0 + j;
+                    const int tp = p / P.kchunks;
+                    const int c0 = (p - tp * P.kchunks) << 6;
+                    const Tap tap = P.taps[tp];
+                    tma_load_5d(sa + j * kPanelBytes, maps[tap.map], full, c0, w0 + tap.dw, h0 + tap.dh, t0 + tap.dt,
+                                n0);
+                }
+                for (int j = 0; j < P.nbp; ++j)
+                    tma_load_5d(sa + (2 + j) * kPanelBytes, &mapB, full, n_tile * P.bn_tile + 64 * j, w0, h0, t0, n0);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, P.bn_tile, 1, 1);
+            const int ksteps = rows >> 4;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const int i = kb - kb0;
+                const int s = i % stages;
+                const uint32_t ph = (i / stages) & 1;
+                mbar_wait(barFull + 8u * s, ph);
+                tc_fence_after();
+                const uint32_t sa = base + s * stageBytes;
+                const uint64_t da = umma_smem_desc(sa, kPanelBytes, 1024);
+                const uint64_t db = umma_smem_desc(sa + 2 * kPanelBytes, kPanelBytes, 1024);
+                for (int k = 0; k < ksteps; ++k)  // 16 position rows = 2048 B per step
+                    umma_bf16(tmem_base, da + 128u * k, db + 128u * k, idesc, (i | k) != 0);
+                umma_commit(barEmpty + 8u * s);
+            }
+            umma_commit(barTmem);
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int p = p0 + (row >> 6);
+        const int tp = p / P.kchunks;
+        const int ci = ((p - tp * P.kchunks) << 6) + (row & 63);
+        const bool valid = p < P.npanels && ci < P.ci_store;
+        float* dst = P.ws + (((long long)split * P.ntaps + tp) * P.ci_pitch + ci) * P.co_pitch + n_tile * P.bn_tile;
+        mbar_wait(barTmem, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        for (int c = 0; c < P.bn_tile; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + c, v);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(dst + c + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, P.tmem_cols);
+    }
+}
+
+// dw[co][ci][tap] = sum_split ws[split][tap][ci][co]   (wfold: tap=(dt,dh), ci = dw*8 + c)
+__global__ void wgrad_finalize_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int ntaps,
+                                      int ci_pitch, int co_pitch, int Cin, int Cout, int wfold_kw, int wfold_taps) {
+    const long long total = (long long)ntaps * ci_pitch * co_pitch;
+    const long long split_stride = total;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int co = static_cast<int>(i % co_pitch);
+        long long r = i / co_pitch;
+        const int ci = static_cast<int>(r % ci_pitch);
+        const int tap = static_cast<int>(r / ci_pitch);
+        if (co >= Cout) continue;
+        int c_true, tap_true, ntaps_true;
+        if (wfold_kw > 0) {
+            const int dwi = ci >> 3;
+            c_true = ci & 7;
+            if (dwi >= wfold_kw || c_true >= Cin) continue;
+            tap_true = tap * wfold_kw + dwi;
+            ntaps_true = wfold_taps;
+        } else {
+            if (ci >= Cin) continue;
+            c_true = ci;
+            tap_true = tap;
+            ntaps_true = ntaps;
+        }
+        float acc = 0.f;
+        for (int s = 0; s < splits; ++s) acc += ws[s * split_stride + i];
+        dw[((long long)co * Cin + c_true) * ntaps_true + tap_true] = acc;
+    }
+}
+
+// weight packing: fp32 [Cout][Cin][taps] -> bf16 fprop image [tap][Cout][kpitch] and dgrad image [tap][Cin][cpad(Cout)]
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                   __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int ntaps, int kpitch,
+                                   int copitch, int wfold_kw) {
+    const int ftaps = wfold_kw > 0 ? ntaps / wfold_kw : ntaps;
+    const long long nf = wf ? (long long)ftaps * Cout * kpitch : 0;
+    const long long nd = wd ? (long long)ntaps * Cin * copitch : 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nf + nd;
+         i += (long long)gridDim.x * blockDim.x) {
+        if (i < nf) {
+            const int k = static_cast<int>(i % kpitch);
+            long long r = i / kpitch;
+            const int co = static_cast<int>(r % Cout);
+            const int tap = static_cast<int>(r / Cout);
+            float v = 0.f;
+            if (wfold_kw > 0) {
+                const int dwi = k >> 3, c = k & 7;
+                if (dwi < wfold_kw && c < Cin) v = w[((long long)co * Cin + c) * ntaps + tap * wfold_kw + dwi];
+            } else if (k < Cin) {
+                v = w[((long long)co * Cin + k) * ntaps + tap];
+            }
+            wf[i] = __float2bfloat16(v);
+        } else {
+            const long long j = i - nf;
+            const int co = static_cast<int>(j % copitch);
+            long long r = j / copitch;
+            const int ci = static_cast<int>(r % Cin);
+            const int tap = static_cast<int>(r / Cin);
+            const float v = co < Cout ? w[((long long)co * Cin + ci) * ntaps + tap] : 0.f;
+            wd[j] = __float2bfloat16(v);
+        }
+    }
+}
+
+// db[co] = sum over rows of dy[row][co]  (C3D bias gradient)
+__global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db, long long rows,
+                                 int pitch, int Cout) {
+    const int co = blockIdx.x;
+    float acc = 0.f;
+    for (long long r = threadIdx.x; r < rows; r += blockDim.x) acc += __bfloat162float(dy[r * pitch + co]);
+    __shared__ float sh[256];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && co < Cout) db[co] = sh[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side geometry
+// ------------------------------------------------------------------------------------------------
+struct Shape {
+    int To, Ho, Wo;
+    int cinp, coutp;
+    bool wfold;
+    int keff;    // reduction channels per tap on the x side (Cin, or 64 for wfold)
+    int kpitch;  // channel pitch of the fprop weight image
+    int ntaps;   // kt*kh*kw
+    int ftaps;   // taps seen by fprop/wgrad kernels (kw folded away for wfold)
+};
+
+int check_desc(const zsv_conv_desc* d, Shape* s) {
+    if (!d) return fail(ZSV_ERR_BAD_ARG, "null conv descriptor");
+    if (d->N < 1 || d->T < 1 || d->H < 1 || d->W < 1 || d->Cin < 1 || d->Cout < 1)
+        return fail(ZSV_ERR_BAD_ARG, "conv desc: non-positive extent");
+    if (d->kt < 1 || d->kh < 1 || d->kw < 1 || d->kt > 7 || d->kh > 7 || d->kw > 7)
+        return fail(ZSV_ERR_BAD_ARG, "conv desc: filter extents must be in 1..7");
+    const int st[3] = {d->st, d->sh, d->sw};
+    for (int i = 0; i < 3; ++i)
+        if (st[i] != 1 && st[i] != 2) return fail(ZSV_ERR_UNSUPPORTED, "conv desc: stride must be 1 or 2");
+    if (d->pt < 0 || d->ph < 0 || d->pw < 0) return fail(ZSV_ERR_BAD_ARG, "conv desc: negative padding");
+    s->To = (d->T + 2 * d->pt - d->kt) / d->st + 1;
+    s->Ho = (d->H + 2 * d->ph - d->kh) / d->sh + 1;
+    s->Wo = (d->W + 2 * d->pw - d->kw) / d->sw + 1;
+    if (s->To < 1 || s->Ho < 1 || s->Wo < 1) return fail(ZSV_ERR_BAD_ARG, "conv desc: empty output");
+    s->cinp = cpad(d->Cin);
+    s->coutp = cpad(d->Cout);
+    s->ntaps = d->kt * d->kh * d->kw;
+    s->wfold = d->x_layout == ZSV_CONV_X_WFOLD;
+    if (s->wfold) {
+        if (s->cinp != 8 || d->kw > 8) return fail(ZSV_ERR_UNSUPPORTED, "wfold layout needs Cin <= 8 and kw <= 8");
+        if ((s->Wo - 1) * d->sw + 8 > d->W + kWfoldWpad || d->pw > kWfoldWpad)
+            return fail(ZSV_ERR_UNSUPPORTED, "wfold layout: window exceeds padded row");
+        s->keff = 64;
+        s->kpitch = 64;
+        s->ftaps = d->kt * d->kh;
+    } else if (d->x_layout == ZSV_CONV_X_NDHWC) {
+        s->keff = d->Cin;
+        s->kpitch = s->cinp;
+        s->ftaps = s->ntaps;
+    } else {
+        return fail(ZSV_ERR_BAD_ARG, "conv desc: unknown x_layout %d", d->x_layout);
+    }
+    if (s->ftaps > kMaxTaps) return fail(ZSV_ERR_UNSUPPORTED, "conv desc: more than %d taps", kMaxTaps);
+    return ZSV_OK;
+}
+
+struct Box {
+    int bw, bh, bt, bn;
+    int rows() const { return bw * bh * bt * bn; }
+};
+
+// Pick the box of positions (<= 128 rows) covering (OW,OH,OT,ON) with the least wasted MMA rows.
+// rows16: rows must be a multiple of 16 (wgrad consumes rows as the K dimension).
+Box choose_box(int OW, int OH, int OT, int ON, bool rows16) {
+    Box best{1, 1, 1, 1};
+    double best_score = -1.0;
+    const double total = (double)OW * OH * OT * ON;
+    for (int bw = 1; bw <= std::min(OW, 128); ++bw)
+        for (int bh = 1; bh <= std::min(OH, 128 / bw); ++bh)
+            for (int bt = 1; bt <= std::min(OT, 128 / (bw * bh)); ++bt)
+                for (int bn = 1; bn <= std::min(ON, 128 / (bw * bh * bt)); ++bn) {
+                    const int rows = bw * bh * bt * bn;
+                    if (rows16 && (rows & 15)) continue;
+                    const double tiles = (double)ceil_div(OW, bw) * ceil_div(OH, bh) * ceil_div(OT, bt) *
+                                         ceil_div(ON, bn);
+                    const double cost = rows16 ? tiles * (rows + 16) : tiles * 128.0;
+                    // tiny bias towards wide-in-w, then tall boxes (longer contiguous runs in memory)
+                    const double score = total / cost + 1e-6 * bw + 1e-8 * bh;
+                    if (score > best_score) {
+                        best_score = score;
+                        best = Box{bw, bh, bt, bn};
+                    }
+                }
+    if (rows16 && best_score < 0) {
+        // tensor smaller than 16 positions in every factorisation: over-cover with a padded box (OOB rows read zero)
+        best = Box{std::min(128, 16 * ceil_div(OW, 16)), 1, 1, 1};
+        if (best.bw > 128) best.bw = 128;
+    }
+    return best;
+}
+
+// N tile (multiple of 16, <= 256) for `cols` output channels given the number of M tiles.
+void choose_ntile(int cols, long long m_tiles, int* bn_tile, int* n_tiles) {
+    const int cols16 = (cols + 15) & ~15;
+    const int sms = std::max(1, sm_count());
+    double best = 1e300;
+    int best_bn = std::min(cols16, 256), best_n = ceil_div(cols16, std::min(cols16, 256));
+    for (int nt = ceil_div(cols16, 256); nt <= ceil_div(cols16, 256) + 6 && nt <= ceil_div(cols16, 16); ++nt) {
+        int bn = ((ceil_div(cols16, nt) + 15) & ~15);
+        if (bn > 256) continue;
+        if (bn < 64 && cols16 >= 64) continue;
+        const long long ctas = m_tiles * nt;
+        const long long slots = 2LL * sms;
+        const long long waves = ceil_div_ll(ctas, slots);
+        // per-CTA cost ~ A-tile handling (fixed) + MMA/B/epilogue work proportional to bn
+        const double cost = (double)waves * (bn + 48.0);
+        if (cost < best) {
+            best = cost;
+            best_bn = bn;
+            best_n = nt;
+        }
+    }
+    *bn_tile = best_bn;
+    *n_tiles = best_n;
+}
+
+int pow2_cols(int n) {
+    int c = 32;
+    while (c < n) c <<= 1;
+    return c;
+}
+
+struct DimTap {
+    int j;       // filter index along this dimension
+    int parity;  // parity plane of the source coordinate (0 when stride 1)
+    int off;     // coordinate offset in the (plane) index space
+};
+
+// forward taps along one dimension: source i = s*o + j - p
+std::vector<DimTap> fwd_dim_taps(int k, int s, int p) {
+    std::vector<DimTap> v;
+    for (int j = 0; j < k; ++j) {
+        const int e = j - p;
+        if (s == 1) {
+            v.push_back({j, 0, e});
+        } else {
+            const int par = ((e % 2) + 2) % 2;
+            v.push_back({j, par, (e - par) / 2});
+        }
+    }
+    return v;
+}
+// dgrad taps along one dimension for dx positions i = s*q + cls: source o = (i + p - j)/s when divisible
+std::vector<DimTap> bwd_dim_taps(int k, int s, int p, int cls) {
+    std::vector<DimTap> v;
+    for (int j = 0; j < k; ++j) {
+        const int e = cls + p - j;
+        if (s == 1) {
+            v.push_back({j, 0, e});
+        } else if (((e % 2) + 2) % 2 == 0) {
+            v.push_back({j, 0, e / 2});
+        }
+    }
+    return v;
+}
+
+// Activation tensor map for parity plane (pt_, ph_, pw_) of x with box (64, bw, bh, bt, bn).
+int make_x_map(CUtensorMap* m, const zsv_conv_desc* d, const Shape& s, const void* x, int pt_, int ph_, int pw_,
+               const Box& b) {
+    uint64_t dims[5], strides[4];
+    uint32_t box[5] = {64, (uint32_t)b.bw, (uint32_t)b.bh, (uint32_t)b.bt, (uint32_t)b.bn};
+    const char* p = static_cast<const char*>(x);
+    if (s.wfold) {
+        const long long Wp = d->W + kWfoldWpad;
+        const long long rowB = Wp * 8 * 2;
+        // column (pw - d->pw .. ) : repack placed exactly d->pw zero columns on the left, so window start = sw*wo
+        dims[0] = 64;
+        dims[1] = s.Wo;
+        dims[2] = (d->H - ph_ + d->sh - 1) / d->sh;
+        dims[3] = (d->T - pt_ + d->st - 1) / d->st;
+        dims[4] = d->N;
+        strides[0] = (uint64_t)d->sw * 8 * 2;
+        strides[1] = (uint64_t)rowB * d->sh;
+        strides[2] = (uint64_t)rowB * d->H * d->st;
+        strides[3] = (uint64_t)rowB * d->H * d->T;
+        p += ((long long)pt_ * d->H + ph_) * rowB;
+    } else {
+        const long long cB = (long long)s.cinp * 2;
+        dims[0] = d->Cin;
+        dims[1] = (d->W - pw_ + d->sw - 1) / d->sw;
+        dims[2] = (d->H - ph_ + d->sh - 1) / d->sh;
+        dims[3] = (d->T - pt_ + d->st - 1) / d->st;
+        dims[4] = d->N;
+        strides[0] = (uint64_t)cB * d->sw;
+        strides[1] = (uint64_t)cB * d->W * d->sh;
+        strides[2] = (uint64_t)cB * d->W * d->H * d->st;
+        strides[3] = (uint64_t)cB * d->W * d->H * d->T;
+        p += (((long long)pt_ * d->H + ph_) * d->W + pw_) * cB;
+    }
+    for (int i = 1; i < 4; ++i)
+        if (dims[i] == 0) dims[i] = 1;
+    return make_map(m, p, 5, dims, strides, box);
+}
+
+// Plain NDHWC map of an activation-shaped tensor [N][T][H][W][pitch] with C valid channels.
+int make_plain_map(CUtensorMap* m, const void* base, int N, int T, int H, int W, int C, int pitch, const Box& b) {
+    uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)T, (uint64_t)N};
+    const uint64_t cB = (uint64_t)pitch * 2;
+    uint64_t strides[4] = {cB, cB * W, cB * W * H, cB * W * H * T};
+    uint32_t box[5] = {64, (uint32_t)b.bw, (uint32_t)b.bh, (uint32_t)b.bt, (uint32_t)b.bn};
+    return make_map(m, base, 5, dims, strides, box);
+}
+
+// Forward-style tap table (used by fprop and wgrad): fills taps + the parity maps they reference.
+int build_fwd_taps(const zsv_conv_desc* d, const Shape& s, const void* x, const Box& b, Tap* taps, CUtensorMap* maps,
+                   int* nmaps) {
+    const int kw_eff = s.wfold ? 1 : d->kw;
+    std::vector<DimTap> tt = fwd_dim_taps(d->kt, d->st, d->pt);
+    std::vector<DimTap> th = fwd_dim_taps(d->kh, d->sh, d->ph);
+    std::vector<DimTap> tw = s.wfold ? std::vector<DimTap>{{0, 0, 0}} : fwd_dim_taps(d->kw, d->sw, d->pw);
+    int keys[kMaxMaps];
+    *nmaps = 0;
+    for (const DimTap& a : tt)
+        for (const DimTap& bq : th)
+            for (const DimTap& c : tw) {
+                const int key = (a.parity << 2) | (bq.parity << 1) | c.parity;
+                int id = -1;
+                for (int i = 0; i < *nmaps; ++i)
+                    if (keys[i] == key) id = i;
+                if (id < 0) {
+                    if (*nmaps == kMaxMaps) return fail(ZSV_ERR_UNSUPPORTED, "conv needs more than %d parity maps", kMaxMaps);
+                    id = (*nmaps)++;
+                    keys[id] = key;
+                    int rc = make_x_map(&maps[id], d, s, x, a.parity, bq.parity, c.parity, b);
+                    if (rc) return rc;
+                }
+                const int ti = (a.j * d->kh + bq.j) * kw_eff + c.j;
+                taps[ti].map = (int16_t)id;
+                taps[ti].dt = (int16_t)a.off;
+                taps[ti].dh = (int16_t)bq.off;
+                taps[ti].dw = (int16_t)c.off;
+                taps[ti].btap = (int16_t)ti;
+            }
+    for (int i = *nmaps; i < kMaxMaps; ++i) maps[i] = maps[0];
+    return ZSV_OK;
+}
+
+int igemm_smem_bytes(int bn_tile, int stages) {
+    return 1024 + stages * (kPanelBytes + bn_tile * 128) + 16 * stages + 16 + 8 * bn_tile * 4 + 64;
+}
+
+int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, IgemmArgs& a, long long m_tiles, int n_tiles,
+                 cudaStream_t stream) {
+    // stages: aim for two CTAs per SM (<= ~110 KB each), at least 2 and at most 6 stages
+    int stages = 6;
+    while (stages > 2 && igemm_smem_bytes(a.bn_tile, stages) > 112 * 1024) --stages;
+    const int kchunks = (a.kdim + 63) / 64;
+    stages = std::max(2, std::min(stages, a.ntaps * kchunks));
+    if (a.ntaps * kchunks == 1) stages = 1;
+    a.stages = stages;
+    a.tmem_cols = pow2_cols(a.bn_tile);
+    const int smem = igemm_smem_bytes(a.bn_tile, stages);
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(igemm_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    if (attr_err != cudaSuccess)
+        return fail(ZSV_ERR_CUDA, "cudaFuncSetAttribute(igemm) failed: %s", cudaGetErrorString(attr_err));
+    if (m_tiles > 0x7fffffffLL) return fail(ZSV_ERR_UNSUPPORTED, "too many M tiles");
+    dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, 1);
+    igemm_kmajor_kernel<<<grid, 192, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], mapB, a);
+    ZSV_LAUNCH_CHECK("igemm_kmajor_kernel");
+    return ZSV_OK;
+}
+
+}  // namespace
+}  // namespace zsv
+
+using namespace zsv;
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" int zsv_conv3d_out_shape(const zsv_conv_desc* d, int32_t out[3]) {
+    Shape s;
+    int rc = check_desc(d, &s);
+    if (rc) return rc;
+    out[0] = s.To;
+    out[1] = s.Ho;
+    out[2] = s.Wo;
+    return ZSV_OK;
+}
+
+extern "C" size_t zsv_conv3d_packed_weight_bytes(const zsv_conv_desc* d, int which) {
+    Shape s;
+    if (check_desc(d, &s)) return 0;
+    if (which == 0) return (size_t)s.ftaps * d->Cout * s.kpitch * 2;
+    if (s.wfold) return 0;
+    return (size_t)s.ntaps * d->Cin * s.coutp * 2;
+}
+
+extern "C" int zsv_conv3d_pack_weight(const zsv_conv_desc* d, const float* w, void* w_fprop, void* w_dgrad,
+                                      void* stream) {
+    Shape s;
+    int rc = check_desc(d, &s);
+    if (rc) return rc;
+    if (!w) return fail(ZSV_ERR_BAD_ARG, "pack_weight: null weight");
+    if (s.wfold && w_dgrad) return fail(ZSV_ERR_UNSUPPORTED, "pack_weight: no dgrad image for the wfold layout");
+    if (!w_fprop && !w_dgrad) return ZSV_OK;
+    const long long n = (w_fprop ? (long long)s.ftaps * d->Cout * s.kpitch : 0) +
+                        (w_dgrad ? (long long)s.ntaps * d->Cin * s.coutp : 0);
+    const int blocks = (int)std::min<long long>(ceil_div_ll(n, 256), 148 * 16);
+    pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        w, (__nv_bfloat16*)w_fprop, (__nv_bfloat16*)w_dgrad, d->Cout, d->Cin, s.ntaps, s.kpitch, s.coutp,
+        s.wfold ? d->kw : 0);
+    ZSV_LAUNCH_CHECK("pack_weight_kernel");
+    return ZSV_OK;
+}
+
+extern "C" int zsv_conv3d_stat_rows(const zsv_conv_desc* d) {
+    Shape s;
+    if (check_desc(d, &s)) return -1;
+    const Box b = choose_box(s.Wo, s.Ho, s.To, d->N, false);
+    return ceil_div(s.Wo, b.bw) * ceil_div(s.Ho, b.bh) * ceil_div(s.To, b.bt) * ceil_div(d->N, b.bn);
+}
+
+extern "C" int zsv_conv3d_fprop(const zsv_conv_desc* d, const void* x, const void* w_fprop, void* y, float* part_sum,
+                                float* part_sq, const float* bias, int relu, void* stream) {
+    Shape s;
+    int rc = check_desc(d, &s);
+    if (rc) return rc;
+    if (!x || !w_fprop || !y) return fail(ZSV_ERR_BAD_ARG, "fprop: null pointer");
+    if ((part_sum == nullptr) != (part_sq == nullptr)) return fail(ZSV_ERR_BAD_ARG, "fprop: need both stat buffers");
+
+    IgemmArgs a;
+    memset(&a, 0, sizeof(a));
+    const Box b = choose_box(s.Wo, s.Ho, s.To, d->N, false);
+    a.bw = b.bw, a.bh = b.bh, a.bt = b.bt, a.bn = b.bn;
+    a.tw = ceil_div(s.Wo, b.bw), a.th = ceil_div(s.Ho, b.bh), a.tt = ceil_div(s.To, b.bt), a.tn = ceil_div(d->N, b.bn);
+    a.OW = s.Wo, a.OH = s.Ho, a.OT = s.To, a.ON = d->N;
+    a.kdim = s.keff;
+    a.ntaps = s.ftaps;
+    a.ncols = s.coutp;
+    a.nbias = bias ? d->Cout : 0;
+    a.relu = relu;
+    a.part_pitch = s.coutp;
+    a.o_sW = s.coutp;
+    a.o_sH = (long long)s.coutp * s.Wo;
+    a.o_sT = a.o_sH * s.Ho;
+    a.o_sN = a.o_sT * s.To;
+    a.out = (__nv_bfloat16*)y;
+    a.part_sum = part_sum;
+    a.part_sq = part_sq;
+    a.bias = bias;
+    const long long m_tiles = (long long)a.tw * a.th * a.tt * a.tn;
+    int n_tiles;
+    choose_ntile(d->Cout, m_tiles, &a.bn_tile, &n_tiles);
+
+    CUtensorMap maps[kMaxMaps];
+    int nmaps;
+    rc = build_fwd_taps(d, s, x, b, a.taps, maps, &nmaps);
+    if (rc) return rc;
+    CUtensorMap mapB;
+    {
+        uint64_t dims[3] = {(uint64_t)s.keff, (uint64_t)d->Cout, (uint64_t)s.ftaps};
+        uint64_t strides[2] = {(uint64_t)s.kpitch * 2, (uint64_t)s.kpitch * 2 * d->Cout};
+        uint32_t box[3] = {64, (uint32_t)a.bn_tile, 1};
+        rc = make_map(&mapB, w_fprop, 3, dims, strides, box);
+        if (rc) return rc;
+    }
+    return launch_igemm(maps, mapB, a, m_tiles, n_tiles, (cudaStream_t)stream);
+}
+
+extern "C" int zsv_conv3d_dgrad(const zsv_conv_desc* d, const void* dy, const void* w_dgrad, void* dx,
+                                const void* addend, void* stream) {
+    Shape s;
+    int rc = check_desc(d, &s);
+    if (rc) return rc;
+    if (s.wfold) return fail(ZSV_ERR_UNSUPPORTED, "dgrad: not available for the wfold (first-layer) layout");
+    if (!dy || !w_dgrad || !dx) return fail(ZSV_ERR_BAD_ARG, "dgrad: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+
+    // weight image [tap][Cin][coutp]: K = Cout
+    const int classes_t = d->st, classes_h = d->sh, classes_w = d->sw;
+    bool any_empty = false;
+    for (int ct = 0; ct < classes_t; ++ct)
+        for (int ch = 0; ch < classes_h; ++ch)
+            for (int cw = 0; cw < classes_w; ++cw)
+                if (bwd_dim_taps(d->kt, d->st, d->pt, ct).empty() || bwd_dim_taps(d->kh, d->sh, d->ph, ch).empty() ||
+                    bwd_dim_taps(d->kw, d->sw, d->pw, cw).empty())
+                    any_empty = true;
+    const size_t dx_bytes = (size_t)d->N * d->T * d->H * d->W * s.cinp * 2;
+    if (any_empty) {
+        if (addend) {
+            if (addend != dx) ZSV_CUDA_CHECK(cudaMemcpyAsync(dx, addend, dx_bytes, cudaMemcpyDeviceToDevice, st));
+        } else {
+            ZSV_CUDA_CHECK(cudaMemsetAsync(dx, 0, dx_bytes, st));
+        }
+    }
+
+    for (int ct = 0; ct < classes_t; ++ct)
+        for (int ch = 0; ch < classes_h; ++ch)
+            for (int cw = 0; cw < classes_w; ++cw) {
+                std::vector<DimTap> tt = bwd_dim_taps(d->kt, d->st, d->pt, ct);
+                std::vector<DimTap> th = bwd_dim_taps(d->kh, d->sh, d->ph, ch);
+                std::vector<DimTap> tw = bwd_dim_taps(d->kw, d->sw, d->pw, cw);
+                if (tt.empty() || th.empty() || tw.empty()) continue;
+                const int QT = (d->T - ct + d->st - 1) / d->st;
+                const int QH = (d->H - ch + d->sh - 1) / d->sh;
+                const int QW = (d->W - cw + d->sw - 1) / d->sw;
+                if (QT < 1 || QH < 1 || QW < 1) continue;
+                IgemmArgs a;
+                memset(&a, 0, sizeof(a));
+                const Box b = choose_box(QW, QH, QT, d->N, false);
+                a.bw = b.bw, a.bh = b.bh, a.bt = b.bt, a.bn = b.bn;
+                a.tw = ceil_div(QW, b.bw), a.th = ceil_div(QH, b.bh), a.tt = ceil_div(QT, b.bt),
+                a.tn = ceil_div(d->N, b.bn);
+                a.OW = QW, a.OH = QH, a.OT = QT, a.ON = d->N;
+                a.kdim = d->Cout;
+                a.ntaps = (int)(tt.size() * th.size() * tw.size());
+                a.ncols = s.cinp;
+                a.o_sW = (long long)s.cinp * d->sw;
+                a.o_sH = (long long)s.cinp * d->W * d->sh;
+                a.o_sT = (long long)s.cinp * d->W * d->H * d->st;
+                a.o_sN = (long long)s.cinp * d->W * d->H * d->T;
+                const long long class_off = (((long long)ct * d->H + ch) * d->W + cw) * s.cinp;
+                a.out = (__nv_bfloat16*)dx + class_off;
+                // when the tensor was pre-filled with the addend (empty classes), it is still added here for
+                // the non-empty classes because their positions are overwritten
+                a.addend = addend ? (const __nv_bfloat16*)addend + class_off : nullptr;
+                int ti = 0;
+                for (const DimTap& x1 : tt)
+                    for (const DimTap& x2 : th)
+                        for (const DimTap& x3 : tw) {
+                            a.taps[ti].map = 0;
+                            a.taps[ti].dt = (int16_t)x1.off;
+                            a.taps[ti].dh = (int16_t)x2.off;
+                            a.taps[ti].dw = (int16_t)x3.off;
+                            a.taps[ti].btap = (int16_t)((x1.j * d->kh + x2.j) * d->kw + x3.j);
+                            ++ti;
+                        }
+                const long long m_tiles = (long long)a.tw * a.th * a.tt * a.tn;
+                int n_tiles;
+                choose_ntile(d->Cin, m_tiles, &a.bn_tile, &n_tiles);
+                CUtensorMap maps[kMaxMaps];
+                rc = make_plain_map(&maps[0], dy, d->N, s.To, s.Ho, s.Wo, d->Cout, s.coutp, b);
+                if (rc) return rc;
+                maps[1] = maps[2] = maps[3] = maps[0];
+                CUtensorMap mapB;
+                uint64_t dims[3] = {(uint64_t)d->Cout, (uint64_t)d->Cin, (uint64_t)s.ntaps};
+                uint64_t strides[2] = {(uint64_t)s.coutp * 2, (uint64_t)s.coutp * 2 * d->Cin};
+                uint32_t box[3] = {64, (uint32_t)a.bn_tile, 1};
+                rc = make_map(&mapB, w_dgrad, 3, dims, strides, box);
+                if (rc) return rc;
+                rc = launch_igemm(maps, mapB, a, m_tiles, n_tiles, st);
+                if (rc) return rc;
+            }
+    return ZSV_OK;
+}
+
+namespace {
+struct WgradPlan {
+    Box box;
+    int num_kb, kchunks, npanels, m_tiles, bn_tile, n_tiles, nbp, splits, kb_per_split, stages, ci_pitch, co_pitch;
+    size_t ws_bytes;
+};
+int plan_wgrad(const zsv_conv_desc* d, const Shape& s, WgradPlan* p) {
+    p->box = choose_box(s.Wo, s.Ho, s.To, d->N, true);
+    const Box& b = p->box;
+    p->num_kb = ceil_div(s.Wo, b.bw) * ceil_div(s.Ho, b.bh) * ceil_div(s.To, b.bt) * ceil_div(d->N, b.bn);
+    p->kchunks = ceil_div(s.keff, 64);
+    p->npanels = s.ftaps * p->kchunks;
+    p->m_tiles = ceil_div(p->npanels, 2);
+    // N tiles are whole 64-wide dy panels except the last
+    const int cols16 = (d->Cout + 15) & ~15;
+    p->n_tiles = ceil_div(cols16, 256);
+    p->bn_tile = (ceil_div(cols16, p->n_tiles) + 15) & ~15;
+    if (p->n_tiles > 1) p->bn_tile = (p->bn_tile + 63) & ~63;  // keep panel-aligned tile origins
+    p->n_tiles = ceil_div(cols16, p->bn_tile);
+    p->nbp = ceil_div(p->bn_tile, 64);
+    const int tiles = p->m_tiles * p->n_tiles;
+    const int sms = std::max(1, sm_count());
+    int splits = std::max(1, (2 * sms) / tiles);
+    splits = std::min(splits, p->num_kb);
+    p->kb_per_split = ceil_div(p->num_kb, splits);
+    p->splits = ceil_div(p->num_kb, p->kb_per_split);
+    const int stage = (2 + p->nbp) * kPanelBytes;
+    p->stages = std::max(1, std::min(4, (227 * 1024 - 2048) / stage));
+    p->ci_pitch = s.wfold ? 64 : s.cinp;
+    p->co_pitch = p->n_tiles * p->bn_tile;
+    p->ws_bytes = (size_t)p->splits * s.ftaps * p->ci_pitch * p->co_pitch * 4;
+    return ZSV_OK;
+}
+}  // namespace
+
+extern "C" size_t zsv_conv3d_wgrad_workspace(const zsv_conv_desc* d) {
+    Shape s;
+    if (check_desc(d, &s)) return 0;
+    WgradPlan p;
+    plan_wgrad(d, s, &p);
+    return p.ws_bytes;
+}
+
+extern "C" int zsv_conv3d_wgrad(const zsv_conv_desc* d, const void* x, const void* dy, float* dw, float* db,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    Shape s;
+    int rc = check_desc(d, &s);
+    if (rc) return rc;
+    if (!x || !dy || !dw || !workspace) return fail(ZSV_ERR_BAD_ARG, "wgrad: null pointer");
+    WgradPlan p;
+    plan_wgrad(d, s, &p);
+    if (workspace_bytes < p.ws_bytes)
+        return fail(ZSV_ERR_WORKSPACE, "wgrad: workspace %zu < required %zu bytes", workspace_bytes, p.ws_bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+
+    WgradArgs a;
+    memset(&a, 0, sizeof(a));
+    const Box& b = p.box;
+    a.bw = b.bw, a.bh = b.bh, a.bt = b.bt, a.bn = b.bn;
+    a.tw = ceil_div(s.Wo, b.bw), a.th = ceil_div(s.Ho, b.bh), a.tt = ceil_div(s.To, b.bt), a.tn = ceil_div(d->N, b.bn);
+    a.kchunks = p.kchunks;
+    a.npanels = p.npanels;
+    a.ntaps = s.ftaps;
+    a.ci_store = p.ci_pitch;
+    a.ci_pitch = p.ci_pitch;
+    a.co_pitch = p.co_pitch;
+    a.bn_tile = p.bn_tile;
+    a.nbp = p.nbp;
+    a.stages = p.stages;
+    a.tmem_cols = pow2_cols(p.bn_tile);
+    a.num_kb = p.num_kb;
+    a.kb_per_split = p.kb_per_split;
+    a.ws = (float*)workspace;
+
+    CUtensorMap maps[kMaxMaps];
+    int nmaps;
+    rc = build_fwd_taps(d, s, x, b, a.taps, maps, &nmaps);
+    if (rc) return rc;
+    CUtensorMap mapB;
+    rc = make_plain_map(&mapB, dy, d->N, s.To, s.Ho, s.Wo, d->Cout, s.coutp, b);
+    if (rc) return rc;
+
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(wgrad_mnmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    if (attr_err != cudaSuccess)
+        return fail(ZSV_ERR_CUDA, "cudaFuncSetAttribute(wgrad) failed: %s", cudaGetErrorString(attr_err));
+    const int smem = 1024 + p.stages * (2 + p.nbp) * kPanelBytes + 16 * p.stages + 64;
+    dim3 grid(p.m_tiles, p.n_tiles, p.splits);
+    wgrad_mnmajor_kernel<<<grid, 192, smem, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, a);
+    ZSV_LAUNCH_CHECK("wgrad_mnmajor_kernel");
+
+    const long long total = (long long)s.ftaps * p.ci_pitch * p.co_pitch;
+    const int blocks = (int)std::min<long long>(ceil_div_ll(total, 256), 148 * 8);
+    wgrad_finalize_kernel<<<blocks, 256, 0, st>>>((const float*)workspace, dw, p.splits, s.ftaps, p.ci_pitch,
+                                                  p.co_pitch, d->Cin, d->Cout, s.wfold ? d->kw : 0, s.ntaps);
+    ZSV_LAUNCH_CHECK("wgrad_finalize_kernel");
+    if (db) {
+        const long long rows = (long long)d->N * s.To * s.Ho * s.Wo;
+        bias_grad_kernel<<<d->Cout, 256, 0, st>>>((const __nv_bfloat16*)dy, db, rows, s.coutp, d->Cout);
+        ZSV_LAUNCH_CHECK("bias_grad_kernel");
+    }
+    return ZSV_OK;
+}

@@ -1,0 +1,618 @@
+// HBM-bound kernels of the hot path: layout conversion at the PyTorch boundary, BatchNorm3d finalize /
+// apply (+ReLU, +residual) / backward, MaxPool3d.  All activations are bf16 NDHWC with channel pitch cpad(C);
+// every thread moves 16-byte vectors (8 channels) so that warps read and write full 128-byte lines.
+//
+// Reference call sites: nn.BatchNorm3d resnet.py:48,95,97,182,185,272; nn.ReLU resnet.py:49,95,98;
+// residual add resnet.py:110-111; nn.MaxPool3d network.py:103-118; input reshape network.py:534-535.
+#include <algorithm>
+
+#include "zsv_internal.h"
+#include "zsv_ptx.cuh"
+
+namespace zsv {
+namespace {
+
+constexpr int kMaxC = 2048;  // largest channel pitch staged in shared memory by the BN kernels
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    f[0] = bf16_lo(v.x), f[1] = bf16_hi(v.x), f[2] = bf16_lo(v.y), f[3] = bf16_hi(v.y);
+    f[4] = bf16_lo(v.z), f[5] = bf16_hi(v.z), f[6] = bf16_lo(v.w), f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                      pack_bf16x2(f[6], f[7]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout conversion
+// ------------------------------------------------------------------------------------------------
+// fp32 NCDHW -> bf16 [N][T][H][Wp][Cp]; column w of the source lands at column w + wl; pad columns/lanes are zero.
+__global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int C,
+                                      int T, int H, int W, int Cp, int Wp, int wl) {
+    const int V = Cp >> 3;
+    const long long thw = (long long)T * H * W;
+    const long long total = (long long)N * T * H * Wp * V;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        // position fastest so that the strided fp32 reads of one channel are coalesced across the warp
+        long long r = i;
+        const int wp = static_cast<int>(r % Wp);
+        r /= Wp;
+        const int h = static_cast<int>(r % H);
+        r /= H;
+        const int t = static_cast<int>(r % T);
+        r /= T;
+        const int n = static_cast<int>(r % N);
+        const int g = static_cast<int>(r / N);
+        const int w = wp - wl;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = g * 8 + j;
+            f[j] = (c < C && w >= 0 && w < W) ? x[((long long)n * C + c) * thw + ((long long)t * H + h) * W + w] : 0.f;
+        }
+        const long long pos = (((long long)n * T + t) * H + h) * Wp + wp;
+        *reinterpret_cast<uint4*>(out + pos * Cp + g * 8) = pack8(f);
+    }
+}
+
+__global__ void ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int N, int C,
+                                      int T, int H, int W, int Cp) {
+    const int V = Cp >> 3;
+    const long long thw = (long long)T * H * W;
+    const long long total = (long long)N * thw * V;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        const long long p = r % thw;
+        r /= thw;
+        const int n = static_cast<int>(r % N);
+        const int g = static_cast<int>(r / N);
+        const uint4 v = *reinterpret_cast<const uint4*>(x + ((long long)n * thw + p) * Cp + g * 8);
+        float f[8];
+        unpack8(v, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = g * 8 + j;
+            if (c < C) out[((long long)n * C + c) * thw + p] = f[j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm finalize: per-tile partials -> batch statistics, affine scale/shift, running stats
+// block = 32 channels x 32 row lanes
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* __restrict__ part_sum, const float* __restrict__ part_sq,
+                                   int part_rows, int C, int Cp, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float momentum, float eps,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out) {
+    __shared__ double sh1[32][33];
+    __shared__ double sh2[32][33];
+    const int cl = threadIdx.x & 31;
+    const int rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    double a = 0.0, b = 0.0;
+    if (c < Cp) {
+        for (int r = rl; r < part_rows; r += 32) {
+            a += (double)part_sum[(long long)r * Cp + c];
+            b += (double)part_sq[(long long)r * Cp + c];
+        }
+    }
+    sh1[rl][cl] = a;
+    sh2[rl][cl] = b;
+    __syncthreads();
+    if (rl == 0 && c < Cp) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int r = 0; r < 32; ++r) {
+            s1 += sh1[r][cl];
+            s2 += sh2[r][cl];
+        }
+        if (c < C) {
+            const double mean = s1 / count;
+            double var = s2 / count - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const double invstd = 1.0 / sqrt(var + (double)eps);
+            const float g = gamma ? gamma[c] : 1.f;
+            const float bt = beta ? beta[c] : 0.f;
+            const float sc = (float)((double)g * invstd);
+            scale[c] = sc;
+            shift[c] = (float)((double)bt - mean * (double)g * invstd);
+            mean_out[c] = (float)mean;
+            invstd_out[c] = (float)invstd;
+            if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+            if (running_var) {
+                const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+                running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+            }
+        } else {  // pad lanes stay exactly zero downstream
+            scale[c] = 0.f;
+            shift[c] = 0.f;
+            mean_out[c] = 0.f;
+            invstd_out[c] = 0.f;
+        }
+    }
+}
+
+__global__ void bn_eval_kernel(int C, int Cp, const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                               float* __restrict__ scale, float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cp) return;
+    if (c < C) {
+        const float invstd = rsqrtf(rv[c] + eps);
+        const float g = gamma ? gamma[c] : 1.f;
+        const float b = beta ? beta[c] : 0.f;
+        scale[c] = g * invstd;
+        shift[c] = b - rm[c] * g * invstd;
+    } else {
+        scale[c] = 0.f;
+        shift[c] = 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm apply (+ second normalised branch, + residual, + ReLU)
+// ------------------------------------------------------------------------------------------------
+template <bool kHasY2, bool kHasRes>
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                const __nv_bfloat16* __restrict__ y2, const float* __restrict__ scale2,
+                const float* __restrict__ shift2, const __nv_bfloat16* __restrict__ res,
+                __nv_bfloat16* __restrict__ out, long long nvec, int Cp, int relu) {
+    extern __shared__ float sm[];
+    float* s_scale = sm;
+    float* s_shift = sm + Cp;
+    float* s_scale2 = sm + 2 * Cp;
+    float* s_shift2 = sm + 3 * Cp;
+    for (int i = threadIdx.x; i < Cp; i += blockDim.x) {
+        s_scale[i] = scale[i];
+        s_shift[i] = shift[i];
+        if (kHasY2) {
+            s_scale2[i] = scale2[i];
+            s_shift2[i] = shift2[i];
+        }
+    }
+    __syncthreads();
+    const int V = Cp >> 3;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = static_cast<int>(i % V) << 3;
+        float f[8], o[8];
+        unpack8(*reinterpret_cast<const uint4*>(y + i * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(f[j], s_scale[c0 + j], s_shift[c0 + j]);
+        if (kHasY2) {
+            unpack8(*reinterpret_cast<const uint4*>(y2 + i * 8), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += fmaf(f[j], s_scale2[c0 + j], s_shift2[c0 + j]);
+        }
+        if (kHasRes) {
+            unpack8(*reinterpret_cast<const uint4*>(res + i * 8), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += f[j];
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+        }
+        *reinterpret_cast<uint4*>(out + i * 8) = pack8(o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm backward.  dz = g * [out > 0];  s1 = sum dz, s2 = sum dz * xhat (per channel, per branch)
+//   reduce : block = V channel groups x R row lanes, register accumulation, fixed-order smem reduction,
+//            per-block partials [block][4][Cp]
+//   final  : sums the block partials in fp64 -> sums[4][Cp] (+ dgamma/dbeta outputs)
+//   apply  : dy = gamma*invstd*(dz - s1/M - xhat*s2/M)
+// ------------------------------------------------------------------------------------------------
+template <bool kHasY2>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ out, int relu,
+                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                     const float* __restrict__ invstd, const __nv_bfloat16* __restrict__ y2,
+                     const float* __restrict__ mean2, const float* __restrict__ invstd2, long long rows, int Cp, int R,
+                     float* __restrict__ partial) {
+    extern __shared__ float sm[];  // [R][4][Cp] reduction scratch (only lanes r > 0 write)
+    const int V = Cp >> 3;
+    const int vl = threadIdx.x % V;
+    const int rl = threadIdx.x / V;
+    const bool active = rl < R;
+    const int c0 = vl << 3;
+    float a1[8], a2[8], b1[8], b2[8];
+    float mu[8], is[8], mu2[8], is2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        a1[j] = a2[j] = b1[j] = b2[j] = 0.f;
+        mu[j] = mean[c0 + j];
+        is[j] = invstd[c0 + j];
+        mu2[j] = kHasY2 ? mean2[c0 + j] : 0.f;
+        is2[j] = kHasY2 ? invstd2[c0 + j] : 0.f;
+    }
+    if (active) {
+        for (long long r = (long long)blockIdx.x * R + rl; r < rows; r += (long long)gridDim.x * R) {
+            const long long e = r * Cp + c0;
+            float gz[8], f[8];
+            unpack8(*reinterpret_cast<const uint4*>(g + e), gz);
+            if (relu) {
+                unpack8(*reinterpret_cast<const uint4*>(out + e), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) gz[j] = f[j] > 0.f ? gz[j] : 0.f;
+            }
+            unpack8(*reinterpret_cast<const uint4*>(y + e), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                a1[j] += gz[j];
+                a2[j] = fmaf(gz[j], (f[j] - mu[j]) * is[j], a2[j]);
+            }
+            if (kHasY2) {
+                unpack8(*reinterpret_cast<const uint4*>(y2 + e), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) b2[j] = fmaf(gz[j], (f[j] - mu2[j]) * is2[j], b2[j]);
+            }
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sm[(rl * 4 + 0) * Cp + c0 + j] = a1[j];
+            sm[(rl * 4 + 1) * Cp + c0 + j] = a2[j];
+            if (kHasY2) sm[(rl * 4 + 3) * Cp + c0 + j] = b2[j];
+        }
+    }
+    __syncthreads();
+    const int nq = kHasY2 ? 4 : 2;
+    for (int i = threadIdx.x; i < nq * Cp; i += blockDim.x) {
+        const int qi = i / Cp, c = i - qi * Cp;
+        float s = 0.f;
+        if (qi == 2) {
+            for (int r = 0; r < R; ++r) s += sm[(r * 4 + 0) * Cp + c];  // s1 of branch 2 equals s1 of branch 1
+        } else {
+            for (int r = 0; r < R; ++r) s += sm[(r * 4 + qi) * Cp + c];
+        }
+        partial[((long long)blockIdx.x * 4 + qi) * Cp + c] = s;
+    }
+    (void)b1;
+}
+
+__global__ void bn_bwd_final_kernel(const float* __restrict__ partial, int nblocks, int nq, int C, int Cp,
+                                    float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                    float* __restrict__ dgamma2, float* __restrict__ dbeta2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq * Cp) return;
+    const int qi = i / Cp, c = i - qi * Cp;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += (double)partial[((long long)b * 4 + qi) * Cp + c];
+    sums[qi * Cp + c] = (float)s;
+    if (c < C) {
+        if (qi == 0 && dbeta) dbeta[c] = (float)s;
+        if (qi == 1 && dgamma) dgamma[c] = (float)s;
+        if (qi == 2 && dbeta2) dbeta2[c] = (float)s;
+        if (qi == 3 && dgamma2) dgamma2[c] = (float)s;
+    }
+}
+
+template <bool kHasY2>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ out, int relu,
+                    const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                    const __nv_bfloat16* __restrict__ y2, const float* __restrict__ mean2,
+                    const float* __restrict__ invstd2, const float* __restrict__ gamma2,
+                    const float* __restrict__ sums, __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dy2,
+                    __nv_bfloat16* __restrict__ dz, long long nvec, int C, int Cp, float inv_count) {
+    extern __shared__ float sm[];  // per channel: mean, k = gamma*invstd, invstd, c1 = s1/M, c2 = s2/M  (x2 branches)
+    float* p_mu = sm;
+    float* p_k = sm + Cp;
+    float* p_is = sm + 2 * Cp;
+    float* p_c1 = sm + 3 * Cp;
+    float* p_c2 = sm + 4 * Cp;
+    float* q_mu = sm + 5 * Cp;
+    float* q_k = sm + 6 * Cp;
+    float* q_is = sm + 7 * Cp;
+    float* q_c2 = sm + 8 * Cp;
+    for (int i = threadIdx.x; i < Cp; i += blockDim.x) {
+        const float gm = (i < C) ? (gamma ? gamma[i] : 1.f) : 0.f;
+        p_mu[i] = mean[i];
+        p_is[i] = invstd[i];
+        p_k[i] = gm * invstd[i];
+        p_c1[i] = sums[i] * inv_count;
+        p_c2[i] = sums[Cp + i] * inv_count;
+        if (kHasY2) {
+            const float gm2 = (i < C) ? (gamma2 ? gamma2[i] : 1.f) : 0.f;
+            q_mu[i] = mean2[i];
+            q_is[i] = invstd2[i];
+            q_k[i] = gm2 * invstd2[i];
+            q_c2[i] = sums[3 * Cp + i] * inv_count;
+        }
+    }
+    __syncthreads();
+    const int V = Cp >> 3;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = static_cast<int>(i % V) << 3;
+        float gz[8], f[8], o[8];
+        unpack8(*reinterpret_cast<const uint4*>(g + i * 8), gz);
+        if (relu) {
+            unpack8(*reinterpret_cast<const uint4*>(out + i * 8), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gz[j] = f[j] > 0.f ? gz[j] : 0.f;
+        }
+        unpack8(*reinterpret_cast<const uint4*>(y + i * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float xh = (f[j] - p_mu[c0 + j]) * p_is[c0 + j];
+            o[j] = p_k[c0 + j] * (gz[j] - p_c1[c0 + j] - xh * p_c2[c0 + j]);
+        }
+        *reinterpret_cast<uint4*>(dy + i * 8) = pack8(o);
+        if (kHasY2) {
+            unpack8(*reinterpret_cast<const uint4*>(y2 + i * 8), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = (f[j] - q_mu[c0 + j]) * q_is[c0 + j];
+                o[j] = q_k[c0 + j] * (gz[j] - p_c1[c0 + j] - xh * q_c2[c0 + j]);
+            }
+            *reinterpret_cast<uint4*>(dy2 + i * 8) = pack8(o);
+        }
+        if (dz != nullptr) *reinterpret_cast<uint4*>(dz + i * 8) = pack8(gz);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MaxPool3d (kernel == stride), NDHWC, 8 channels per thread, argmax = flat window index (int8 range)
+// ------------------------------------------------------------------------------------------------
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                   int32_t* __restrict__ argmax, int N, int T, int H, int W, int Cp, int kt, int kh,
+                                   int kw, int pt, int ph, int pw, int To, int Ho, int Wo) {
+    const int V = Cp >> 3;
+    const long long total = (long long)N * To * Ho * Wo * V;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        const int g = static_cast<int>(r % V);
+        r /= V;
+        const int wo = static_cast<int>(r % Wo);
+        r /= Wo;
+        const int ho = static_cast<int>(r % Ho);
+        r /= Ho;
+        const int to = static_cast<int>(r % To);
+        const int n = static_cast<int>(r / To);
+        float best[8];
+        int bi[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) best[j] = -INFINITY, bi[j] = -1;
+        for (int a = 0; a < kt; ++a)
+            for (int b = 0; b < kh; ++b)
+                for (int c = 0; c < kw; ++c) {
+                    const int t = to * kt + a - pt, h = ho * kh + b - ph, w = wo * kw + c - pw;
+                    if (t < 0 || t >= T || h < 0 || h >= H || w < 0 || w >= W) continue;
+                    float f[8];
+                    unpack8(*reinterpret_cast<const uint4*>(x + ((((long long)n * T + t) * H + h) * W + w) * Cp + g * 8),
+                            f);
+                    const int code = (a * kh + b) * kw + c;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (f[j] > best[j] || bi[j] < 0) best[j] = f[j], bi[j] = code;
+                }
+        *reinterpret_cast<uint4*>(y + i * 8) = pack8(best);
+        int32_t* am = argmax + i * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) am[j] = bi[j];
+    }
+}
+
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const int32_t* __restrict__ argmax,
+                                   __nv_bfloat16* __restrict__ dx, int N, int T, int H, int W, int Cp, int kt, int kh,
+                                   int kw, int pt, int ph, int pw, int To, int Ho, int Wo) {
+    // one thread per input vector: windows do not overlap (kernel == stride), so each input element belongs to
+    // exactly one window and the gradient is a gather
+    const int V = Cp >> 3;
+    const long long total = (long long)N * T * H * W * V;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        const int g = static_cast<int>(r % V);
+        r /= V;
+        const int w = static_cast<int>(r % W);
+        r /= W;
+        const int h = static_cast<int>(r % H);
+        r /= H;
+        const int t = static_cast<int>(r % T);
+        const int n = static_cast<int>(r / T);
+        const int to = (t + pt) / kt, ho = (h + ph) / kh, wo = (w + pw) / kw;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.f;
+        if (to < To && ho < Ho && wo < Wo) {
+            const int code = (((t + pt) - to * kt) * kh + ((h + ph) - ho * kh)) * kw + ((w + pw) - wo * kw);
+            const long long oi = ((((long long)n * To + to) * Ho + ho) * Wo + wo) * V + g;
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>(dy + oi * 8), f);
+            const int32_t* am = argmax + oi * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = am[j] == code ? f[j] : 0.f;
+        }
+        *reinterpret_cast<uint4*>(dx + i * 8) = pack8(o);
+    }
+}
+
+int ew_blocks(long long work_items, int threads) {
+    const long long want = ceil_div_ll(work_items, threads);
+    return (int)std::max<long long>(1, std::min<long long>(want, (long long)sm_count() * 8));
+}
+
+constexpr int kBwdMaxBlocks = 592;
+
+}  // namespace
+}  // namespace zsv
+
+using namespace zsv;
+
+extern "C" int zsv_repack_input(const float* x, void* out, int N, int C, int T, int H, int W, int layout,
+                                int wpad_left, void* stream) {
+    if (!x || !out) return fail(ZSV_ERR_BAD_ARG, "repack_input: null pointer");
+    if (N < 1 || C < 1 || T < 1 || H < 1 || W < 1) return fail(ZSV_ERR_BAD_ARG, "repack_input: bad extents");
+    int Cp = cpad(C), Wp = W, wl = 0;
+    if (layout == ZSV_CONV_X_WFOLD) {
+        if (Cp != 8) return fail(ZSV_ERR_UNSUPPORTED, "repack_input: wfold layout needs C <= 8");
+        if (wpad_left < 0 || wpad_left > 8) return fail(ZSV_ERR_BAD_ARG, "repack_input: wpad_left out of range");
+        Wp = W + 8;
+        wl = wpad_left;
+    } else if (layout != ZSV_CONV_X_NDHWC) {
+        return fail(ZSV_ERR_BAD_ARG, "repack_input: unknown layout %d", layout);
+    }
+    const long long total = (long long)N * T * H * Wp * (Cp >> 3);
+    ncdhw_to_ndhwc_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, N, C, T, H,
+                                                                                   W, Cp, Wp, wl);
+    ZSV_LAUNCH_CHECK("ncdhw_to_ndhwc_kernel");
+    return ZSV_OK;
+}
+
+extern "C" int zsv_ncdhw_to_ndhwc(const float* x, void* out, int N, int C, int T, int H, int W, void* stream) {
+    return zsv_repack_input(x, out, N, C, T, H, W, ZSV_CONV_X_NDHWC, 0, stream);
+}
+
+extern "C" int zsv_ndhwc_to_ncdhw(const void* x, float* out, int N, int C, int T, int H, int W, void* stream) {
+    if (!x || !out) return fail(ZSV_ERR_BAD_ARG, "ndhwc_to_ncdhw: null pointer");
+    const int Cp = cpad(C);
+    const long long total = (long long)N * T * H * W * (Cp >> 3);
+    ndhwc_to_ncdhw_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, N, C,
+                                                                                   T, H, W, Cp);
+    ZSV_LAUNCH_CHECK("ndhwc_to_ncdhw_kernel");
+    return ZSV_OK;
+}
+
+extern "C" int zsv_bn_finalize(const float* part_sum, const float* part_sq, int part_rows, int C, long long count,
+                               const float* gamma, const float* beta, float* running_mean, float* running_var,
+                               float momentum, float eps, float* scale, float* shift, float* mean, float* invstd,
+                               void* stream) {
+    if (!part_sum || !part_sq || !scale || !shift || !mean || !invstd)
+        return fail(ZSV_ERR_BAD_ARG, "bn_finalize: null pointer");
+    if (part_rows < 1 || C < 1 || count < 1) return fail(ZSV_ERR_BAD_ARG, "bn_finalize: bad sizes");
+    const int Cp = cpad(C);
+    bn_finalize_kernel<<<ceil_div(Cp, 32), 1024, 0, (cudaStream_t)stream>>>(
+        part_sum, part_sq, part_rows, C, Cp, (double)count, gamma, beta, running_mean, running_var, momentum, eps,
+        scale, shift, mean, invstd);
+    ZSV_LAUNCH_CHECK("bn_finalize_kernel");
+    return ZSV_OK;
+}
+
+extern "C" int zsv_bn_eval_scale_shift(int C, const float* gamma, const float* beta, const float* running_mean,
+                                       const float* running_var, float eps, float* scale, float* shift, void* stream) {
+    if (!running_mean || !running_var || !scale || !shift) return fail(ZSV_ERR_BAD_ARG, "bn_eval: null pointer");
+    const int Cp = cpad(C);
+    bn_eval_kernel<<<ceil_div(Cp, 128), 128, 0, (cudaStream_t)stream>>>(C, Cp, gamma, beta, running_mean, running_var,
+                                                                        eps, scale, shift);
+    ZSV_LAUNCH_CHECK("bn_eval_kernel");
+    return ZSV_OK;
+}
+
+extern "C" int zsv_bn_apply(const void* y, const float* scale, const float* shift, const void* y2, const float* scale2,
+                            const float* shift2, const void* residual, void* out, long long rows, int C, int relu,
+                            void* stream) {
+    if (!y || !scale || !shift || !out) return fail(ZSV_ERR_BAD_ARG, "bn_apply: null pointer");
+    if (y2 && (!scale2 || !shift2)) return fail(ZSV_ERR_BAD_ARG, "bn_apply: second branch needs scale2/shift2");
+    const int Cp = cpad(C);
+    if (Cp > kMaxC) return fail(ZSV_ERR_UNSUPPORTED, "bn_apply: more than %d channels", kMaxC);
+    if (rows < 1) return ZSV_OK;
+    const long long nvec = rows * (Cp >> 3);
+    const int blocks = ew_blocks(nvec, 256 * 4);
+    const size_t smem = (size_t)4 * Cp * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+    const __nv_bfloat16* yb = (const __nv_bfloat16*)y;
+    const __nv_bfloat16* y2b = (const __nv_bfloat16*)y2;
+    const __nv_bfloat16* rb = (const __nv_bfloat16*)residual;
+    __nv_bfloat16* ob = (__nv_bfloat16*)out;
+    if (y2 && residual)
+        bn_apply_kernel<true, true><<<blocks, 256, smem, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, nvec, Cp, relu);
+    else if (y2)
+        bn_apply_kernel<true, false><<<blocks, 256, smem, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, nvec, Cp, relu);
+    else if (residual)
+        bn_apply_kernel<false, true><<<blocks, 256, smem, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, nvec, Cp, relu);
+    else
+        bn_apply_kernel<false, false><<<blocks, 256, smem, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, nvec, Cp, relu);
+    ZSV_LAUNCH_CHECK("bn_apply_kernel");
+    return ZSV_OK;
+}
+
+extern "C" size_t zsv_bn_bwd_workspace(int C) {
+    const int Cp = cpad(C);
+    return ((size_t)kBwdMaxBlocks * 4 * Cp + 4 * Cp) * sizeof(float);
+}
+
+extern "C" int zsv_bn_bwd(const void* g, const void* out, int relu, const void* y, const float* mean,
+                          const float* invstd, const float* gamma, const void* y2, const float* mean2,
+                          const float* invstd2, const float* gamma2, void* dy, void* dy2, void* dz, float* dgamma,
+                          float* dbeta, float* dgamma2, float* dbeta2, long long rows, int C, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    if (!g || !y || !mean || !invstd || !dy || !workspace) return fail(ZSV_ERR_BAD_ARG, "bn_bwd: null pointer");
+    if (relu && !out) return fail(ZSV_ERR_BAD_ARG, "bn_bwd: relu mask needs the forward output");
+    if (y2 && (!mean2 || !invstd2 || !dy2)) return fail(ZSV_ERR_BAD_ARG, "bn_bwd: second branch incomplete");
+    const int Cp = cpad(C);
+    if (Cp > kMaxC) return fail(ZSV_ERR_UNSUPPORTED, "bn_bwd: more than %d channels", kMaxC);
+    if (workspace_bytes < zsv_bn_bwd_workspace(C)) return fail(ZSV_ERR_WORKSPACE, "bn_bwd: workspace too small");
+    if (rows < 1) return fail(ZSV_ERR_BAD_ARG, "bn_bwd: rows < 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int V = Cp >> 3;
+    const int R = std::max(1, 256 / V);
+    if (V > 256) return fail(ZSV_ERR_UNSUPPORTED, "bn_bwd: channel pitch too large");
+    const int nblocks = (int)std::max<long long>(1, std::min<long long>(kBwdMaxBlocks, ceil_div_ll(rows, (long long)R * 4)));
+    float* partial = (float*)workspace;
+    float* sums = partial + (size_t)kBwdMaxBlocks * 4 * Cp;
+    const size_t smem_r = (size_t)R * 4 * Cp * sizeof(float);
+    const __nv_bfloat16 *gb = (const __nv_bfloat16*)g, *ob = (const __nv_bfloat16*)out, *yb = (const __nv_bfloat16*)y,
+                        *y2b = (const __nv_bfloat16*)y2;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(bn_bwd_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(bn_bwd_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr_done = true;
+    }
+    if (smem_r > 160 * 1024) return fail(ZSV_ERR_UNSUPPORTED, "bn_bwd: reduction scratch too large");
+    if (y2)
+        bn_bwd_reduce_kernel<true><<<nblocks, 256, smem_r, st>>>(gb, ob, relu, yb, mean, invstd, y2b, mean2, invstd2, rows, Cp, R, partial);
+    else
+        bn_bwd_reduce_kernel<false><<<nblocks, 256, smem_r, st>>>(gb, ob, relu, yb, mean, invstd, y2b, mean2, invstd2, rows, Cp, R, partial);
+    ZSV_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+    const int nq = y2 ? 4 : 2;
+    bn_bwd_final_kernel<<<ceil_div(nq * Cp, 128), 128, 0, st>>>(partial, nblocks, nq, C, Cp, sums, dgamma, dbeta, dgamma2, dbeta2);
+    ZSV_LAUNCH_CHECK("bn_bwd_final_kernel");
+    const long long nvec = rows * V;
+    const int blocks = ew_blocks(nvec, 256 * 4);
+    const size_t smem_a = (size_t)9 * Cp * sizeof(float);
+    const float inv_count = (float)(1.0 / (double)rows);
+    if (y2)
+        bn_bwd_apply_kernel<true><<<blocks, 256, smem_a, st>>>(gb, ob, relu, yb, mean, invstd, gamma, y2b, mean2, invstd2, gamma2, sums, (__nv_bfloat16*)dy, (__nv_bfloat16*)dy2, (__nv_bfloat16*)dz, nvec, C, Cp, inv_count);
+    else
+        bn_bwd_apply_kernel<false><<<blocks, 256, smem_a, st>>>(gb, ob, relu, yb, mean, invstd, gamma, y2b, mean2, invstd2, gamma2, sums, (__nv_bfloat16*)dy, (__nv_bfloat16*)dy2, (__nv_bfloat16*)dz, nvec, C, Cp, inv_count);
+    ZSV_LAUNCH_CHECK("bn_bwd_apply_kernel");
+    return ZSV_OK;
+}
+
+extern "C" int zsv_maxpool3d_fwd(const void* x, void* y, int32_t* argmax, int N, int T, int H, int W, int C, int kt,
+                                 int kh, int kw, int pt, int ph, int pw, void* stream) {
+    if (!x || !y || !argmax) return fail(ZSV_ERR_BAD_ARG, "maxpool_fwd: null pointer");
+    const int Cp = cpad(C);
+    const int To = (T + 2 * pt - kt) / kt + 1, Ho = (H + 2 * ph - kh) / kh + 1, Wo = (W + 2 * pw - kw) / kw + 1;
+    if (To < 1 || Ho < 1 || Wo < 1) return fail(ZSV_ERR_BAD_ARG, "maxpool_fwd: empty output");
+    const long long total = (long long)N * To * Ho * Wo * (Cp >> 3);
+    maxpool_fwd_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, argmax, N, T, H, W, Cp, kt, kh, kw, pt, ph, pw, To, Ho, Wo);
+    ZSV_LAUNCH_CHECK("maxpool_fwd_kernel");
+    return ZSV_OK;
+}
+
+extern "C" int zsv_maxpool3d_bwd(const void* dy, const int32_t* argmax, void* dx, int N, int T, int H, int W, int C,
+                                 int kt, int kh, int kw, int pt, int ph, int pw, void* stream) {
+    if (!dy || !dx || !argmax) return fail(ZSV_ERR_BAD_ARG, "maxpool_bwd: null pointer");
+    const int Cp = cpad(C);
+    const int To = (T + 2 * pt - kt) / kt + 1, Ho = (H + 2 * ph - kh) / kh + 1, Wo = (W + 2 * pw - kw) / kw + 1;
+    const long long total = (long long)N * T * H * W * (Cp >> 3);
+    maxpool_bwd_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dy, argmax, (__nv_bfloat16*)dx, N, T, H, W, Cp, kt, kh, kw, pt, ph, pw, To, Ho, Wo);
+    ZSV_LAUNCH_CHECK("maxpool_bwd_kernel");
+    return ZSV_OK;
+}

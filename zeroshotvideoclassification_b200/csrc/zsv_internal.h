@@ -1,0 +1,36 @@
+// Host-side helpers shared by the translation units of libzsv_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../include/zsv_b200.h"
+
+namespace zsv {
+
+// Record a message for zsv_last_error() and return the status (printf-style).
+int fail(int status, const char* fmt, ...);
+
+inline int cpad(int c) { return (c + 7) & ~7; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// Number of SMs of the current device (cached).
+int sm_count();
+
+#define ZSV_CUDA_CHECK(expr)                                                                            \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return ::zsv::fail(ZSV_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),    \
+                               __FILE__, __LINE__);                                                     \
+    } while (0)
+
+#define ZSV_LAUNCH_CHECK(name)                                                                          \
+    do {                                                                                                \
+        cudaError_t _e = cudaGetLastError();                                                            \
+        if (_e != cudaSuccess)                                                                          \
+            return ::zsv::fail(ZSV_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e));  \
+    } while (0)
+
+}  // namespace zsv

@@ -1,0 +1,333 @@
+"""Whole-network execution of the R(2+1)D-18 hot path on libzsv_b200.so.
+
+One ``torch.autograd.Function`` spans the backbone (resnet.py:243-249) and one the embedding head
+(network.py:595-596); inside them the step is a fixed sequence of C-ABI kernel launches on the current
+stream over channels-last bf16 buffers:
+
+  forward : repack -> [conv fprop (+BN partial stats in the epilogue) -> BN finalize -> BN apply(+ReLU,+residual)]*
+  backward: [BN backward (reduce, apply) -> wgrad -> dgrad(+residual gradient)]* in reverse order
+
+``Tensor.backward()`` at main.py:195 therefore reaches exactly these kernels; parameter gradients come back
+as fp32 tensors in the state-dict layout so GradScaler/Adam (main.py:195-203) work unchanged.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib, ops
+from ._lib import cpad
+
+
+# ----------------------------------------------------------------------------------------------------
+# static description of the network (parameter names relative to the VideoResNet module)
+# ----------------------------------------------------------------------------------------------------
+@dataclass
+class ConvSpec:
+    name: str            # state-dict prefix of the nn.Conv3d, e.g. "layer1.0.conv1.0.0"
+    bn: str              # prefix of the BatchNorm3d that follows it
+    cin: int
+    cout: int
+    kernel: Tuple[int, int, int]
+    stride: Tuple[int, int, int]
+    padding: Tuple[int, int, int]
+
+
+@dataclass
+class BlockSpec:
+    prefix: str
+    convs: List[ConvSpec]                 # spatial1, temporal1, spatial2, temporal2
+    downsample: Optional[ConvSpec]
+
+
+def _r2plus1d_specs():
+    stem = [ConvSpec("stem.0", "stem.1", 3, 45, (1, 7, 7), (1, 2, 2), (0, 3, 3)),
+            ConvSpec("stem.3", "stem.4", 45, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0))]
+    blocks = []
+    cin = 64
+    for li, cout in ((1, 64), (2, 128), (3, 256), (4, 512)):
+        for bi in range(2):
+            s = 2 if (li > 1 and bi == 0) else 1
+            mid = (cin * cout * 27) // (cin * 9 + 3 * cout)       # resnet.py:91
+            p = f"layer{li}.{bi}"
+            convs = [ConvSpec(p + ".conv1.0.0", p + ".conv1.0.1", cin, mid, (1, 3, 3), (1, s, s), (0, 1, 1)),
+                     ConvSpec(p + ".conv1.0.3", p + ".conv1.1", mid, cout, (3, 1, 1), (s, 1, 1), (1, 0, 0)),
+                     ConvSpec(p + ".conv2.0.0", p + ".conv2.0.1", cout, mid, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+                     ConvSpec(p + ".conv2.0.3", p + ".conv2.1", mid, cout, (3, 1, 1), (1, 1, 1), (1, 0, 0))]
+            ds = None
+            if s != 1 or cin != cout:
+                ds = ConvSpec(p + ".downsample.0", p + ".downsample.1", cin, cout, (1, 1, 1), (s, s, s), (0, 0, 0))
+            blocks.append(BlockSpec(p, convs, ds))
+            cin = cout
+    return stem, blocks
+
+
+STEM_SPECS, BLOCK_SPECS = _r2plus1d_specs()
+
+
+def all_conv_specs() -> List[ConvSpec]:
+    out = list(STEM_SPECS)
+    for b in BLOCK_SPECS:
+        out.extend(b.convs)
+        if b.downsample is not None:
+            out.append(b.downsample)
+    return out
+
+
+def param_names() -> List[str]:
+    """Differentiable parameters of the backbone in the order they are passed to the autograd Function."""
+    names = []
+    for c in all_conv_specs():
+        names += [c.name + ".weight", c.bn + ".weight", c.bn + ".bias"]
+    return names
+
+
+# ----------------------------------------------------------------------------------------------------
+# geometry cache
+# ----------------------------------------------------------------------------------------------------
+_conv_cache: Dict[tuple, ops.Conv3d] = {}
+
+
+def _conv_for(spec: ConvSpec, N, T, H, W, layout=_lib.X_NDHWC) -> ops.Conv3d:
+    key = (N, T, H, W, spec.cin, spec.cout, spec.kernel, spec.stride, spec.padding, layout)
+    op = _conv_cache.get(key)
+    if op is None:
+        op = ops.Conv3d(N, T, H, W, spec.cin, spec.cout, spec.kernel, spec.stride, spec.padding, layout)
+        _conv_cache[key] = op
+    return op
+
+
+# ----------------------------------------------------------------------------------------------------
+# tape records
+# ----------------------------------------------------------------------------------------------------
+@dataclass
+class UnitRec:
+    """conv -> BN(train) [-> ReLU] with everything backward needs."""
+    spec: ConvSpec
+    op: ops.Conv3d
+    x: torch.Tensor                 # conv input (bf16)
+    wd: Optional[torch.Tensor]      # packed dgrad weights
+    y: torch.Tensor                 # raw conv output (bf16)
+    mean: torch.Tensor
+    invstd: torch.Tensor
+    out: Optional[torch.Tensor]     # post-activation output (ReLU mask); None for a bare BN feeding a block tail
+    relu: bool
+
+
+@dataclass
+class BlockRec:
+    units: List[UnitRec]            # spatial1, temporal1, spatial2, temporal2(tail, out=None)
+    ds: Optional[UnitRec]
+    out: torch.Tensor               # block output after add + ReLU
+    x: torch.Tensor                 # block input
+
+
+class BackboneRunner:
+    """Executes the backbone given a flat dict of parameter / buffer tensors (names relative to VideoResNet)."""
+
+    def __init__(self, tensors: Dict[str, torch.Tensor], train: bool, need_grad: bool):
+        self.t = tensors
+        self.train = train
+        self.need_grad = need_grad
+        self.stem_recs: List[UnitRec] = []
+        self.block_recs: List[BlockRec] = []
+
+    # -- forward building blocks -------------------------------------------------------------------
+    def _unit(self, spec: ConvSpec, x: torch.Tensor, dims, relu: bool, apply_now: bool = True, layout=_lib.X_NDHWC,
+              need_dgrad: bool = True):
+        N, T, H, W = dims
+        op = _conv_for(spec, N, T, H, W, layout)
+        w = self.t[spec.name + ".weight"]
+        wf, wd = op.pack(w, need_dgrad=self.need_grad and need_dgrad)
+        gamma, beta = self.t[spec.bn + ".weight"], self.t[spec.bn + ".bias"]
+        rm, rv = self.t[spec.bn + ".running_mean"], self.t[spec.bn + ".running_var"]
+        if self.train:
+            y, ps, pq = op.fprop(x, wf, stats=True)
+            scale, shift, mean, invstd = ops.bn_finalize(ps, pq, spec.cout, op.out_positions, gamma, beta, rm, rv)
+            nbt = self.t.get(spec.bn + ".num_batches_tracked")
+            if nbt is not None:
+                nbt.add_(1)
+        else:
+            y, _, _ = op.fprop(x, wf, stats=False)
+            scale, shift = ops.bn_eval_scale_shift(spec.cout, gamma, beta, rm, rv)
+            mean = invstd = None
+        out = ops.bn_apply(y, scale, shift, spec.cout, relu) if apply_now else None
+        rec = UnitRec(spec, op, x, wd, y, mean, invstd, out, relu) if self.need_grad else None
+        return out, y, (scale, shift), rec, (op.To, op.Ho, op.Wo)
+
+    def forward(self, x_ncdhw: torch.Tensor) -> torch.Tensor:
+        N, _, T, H, W = x_ncdhw.shape
+        s0 = STEM_SPECS[0]
+        a = ops.repack_input(x_ncdhw, _lib.X_WFOLD, s0.padding[2])
+        a, _, _, rec, (T1, H1, W1) = self._unit(s0, a, (N, T, H, W), True, layout=_lib.X_WFOLD, need_dgrad=False)
+        self.stem_recs.append(rec)
+        a, _, _, rec, (T1, H1, W1) = self._unit(STEM_SPECS[1], a, (N, T1, H1, W1), True)
+        self.stem_recs.append(rec)
+        dims = (N, T1, H1, W1)
+        for b in BLOCK_SPECS:
+            a, dims = self._block(b, a, dims)
+        return a
+
+    def _block(self, b: BlockSpec, x: torch.Tensor, dims):
+        N = dims[0]
+        recs = []
+        a, _, _, r, d1 = self._unit(b.convs[0], x, dims, True)
+        recs.append(r)
+        a, _, _, r, d2 = self._unit(b.convs[1], a, (N, *d1), True)
+        recs.append(r)
+        a, _, _, r, d3 = self._unit(b.convs[2], a, (N, *d2), True)
+        recs.append(r)
+        _, y_t, (sc, sh), r, d4 = self._unit(b.convs[3], a, (N, *d3), False, apply_now=False)
+        recs.append(r)
+        ds_rec = None
+        if b.downsample is not None:
+            _, y_d, (sc_d, sh_d), ds_rec, _ = self._unit(b.downsample, x, dims, False, apply_now=False)
+            out = ops.bn_apply(y_t, sc, sh, b.convs[3].cout, True, y2=y_d, scale2=sc_d, shift2=sh_d)
+        else:
+            out = ops.bn_apply(y_t, sc, sh, b.convs[3].cout, True, residual=x)
+        if self.need_grad:
+            self.block_recs.append(BlockRec(recs, ds_rec, out, x))
+        return out, (N, *d4)
+
+    # -- backward ----------------------------------------------------------------------------------
+    def backward(self, g: torch.Tensor, want: Dict[str, bool]) -> Dict[str, torch.Tensor]:
+        """g: gradient w.r.t. the backbone output (bf16 NDHWC).  Returns grads keyed by parameter name."""
+        grads: Dict[str, torch.Tensor] = {}
+        g = g.contiguous()
+
+        def unit_bwd(rec: UnitRec, gin: torch.Tensor, addend=None, need_dx: bool = True):
+            """gin: gradient w.r.t. rec.out (post BN/ReLU).  Returns gradient w.r.t. rec.x."""
+            dy, _, _, dgamma, dbeta, _, _ = ops.bn_bwd(gin, rec.out, rec.relu, rec.y, rec.mean, rec.invstd,
+                                                       self.t[rec.spec.bn + ".weight"], rec.spec.cout)
+            grads[rec.spec.bn + ".weight"] = dgamma
+            grads[rec.spec.bn + ".bias"] = dbeta
+            return conv_bwd(rec, dy, addend, need_dx)
+
+        def conv_bwd(rec: UnitRec, dy: torch.Tensor, addend=None, need_dx: bool = True):
+            if want.get(rec.spec.name + ".weight", True):
+                grads[rec.spec.name + ".weight"], _ = rec.op.wgrad(rec.x, dy)
+            return rec.op.dgrad(dy, rec.wd, addend) if need_dx else None
+
+        for brec in reversed(self.block_recs):
+            tail = brec.units[3]
+            ds = brec.ds
+            if ds is not None:
+                dy_t, dy_d, _, dg, db, dg2, db2 = ops.bn_bwd(
+                    g, brec.out, True, tail.y, tail.mean, tail.invstd, self.t[tail.spec.bn + ".weight"],
+                    tail.spec.cout, y2=ds.y, mean2=ds.mean, invstd2=ds.invstd, gamma2=self.t[ds.spec.bn + ".weight"])
+                grads[ds.spec.bn + ".weight"], grads[ds.spec.bn + ".bias"] = dg2, db2
+                dz = None
+            else:
+                dy_t, _, dz, dg, db, _, _ = ops.bn_bwd(
+                    g, brec.out, True, tail.y, tail.mean, tail.invstd, self.t[tail.spec.bn + ".weight"],
+                    tail.spec.cout, want_dz=True)
+            grads[tail.spec.bn + ".weight"], grads[tail.spec.bn + ".bias"] = dg, db
+            ga = conv_bwd(tail, dy_t)                       # grad w.r.t. spatial2 output
+            ga = unit_bwd(brec.units[2], ga)                # -> grad w.r.t. block conv1 output
+            ga = unit_bwd(brec.units[1], ga)                # -> grad w.r.t. spatial1 output
+            if ds is not None:
+                gx = unit_bwd(brec.units[0], ga)            # main branch
+                g = conv_bwd(ds, dy_d, addend=gx)           # + projected shortcut
+            else:
+                g = unit_bwd(brec.units[0], ga, addend=dz)  # + identity shortcut
+        ga = unit_bwd(self.stem_recs[1], g)
+        unit_bwd(self.stem_recs[0], ga, need_dx=False)
+        return grads
+
+
+# ----------------------------------------------------------------------------------------------------
+# autograd glue
+# ----------------------------------------------------------------------------------------------------
+_BUFFER_SUFFIXES = (".running_mean", ".running_var", ".num_batches_tracked")
+
+
+def _module_tensors(module: torch.nn.Module) -> Dict[str, torch.Tensor]:
+    t = {k: v for k, v in module.named_parameters()}
+    t.update({k: v for k, v in module.named_buffers()})
+    return t
+
+
+class _BackboneFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        names = param_names()
+        tensors = {k: v.detach() for k, v in _module_tensors(module).items()}
+        for n, p in zip(names, params):
+            tensors[n] = p.detach()
+        need_grad = any(ctx.needs_input_grad[2:])
+        runner = BackboneRunner(tensors, train=module.training, need_grad=need_grad)
+        feats = runner.forward(x)
+        ctx.runner = runner if need_grad else None
+        ctx.names = names
+        ctx.want = {n: ctx.needs_input_grad[2 + i] for i, n in enumerate(names)}
+        ctx.param_meta = [(p.dtype, p.shape) for p in params]
+        return feats
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.runner is None:
+            return (None, None) + tuple(None for _ in ctx.names)
+        grads = ctx.runner.backward(g, ctx.want)
+        ctx.runner = None
+        out = []
+        for n, (dt, shape) in zip(ctx.names, ctx.param_meta):
+            gr = grads.get(n) if ctx.want[n] else None
+            if gr is not None:
+                gr = gr.reshape(shape)
+                if gr.dtype != dt:
+                    gr = gr.to(dt)
+            out.append(gr)
+        return (None, None) + tuple(out)
+
+
+def backbone_forward(module: torch.nn.Module, x: torch.Tensor) -> torch.Tensor:
+    """R(2+1)D-18 trunk on a ``VideoResNet18``-shaped module: x [B,3,T,H,W] fp32 CUDA -> bf16 [B,T',H',W',512]."""
+    ops._require_cuda(x, "backbone_forward")
+    _lib.load()
+    lookup = dict(module.named_parameters())
+    params = [lookup[n] for n in param_names()]
+    if not torch.is_grad_enabled():
+        params = [p.detach() for p in params]
+    return _BackboneFn.apply(module, x, *params)
+
+
+class _HeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, w1, b1, w2, b2):
+        channels = w1.shape[1]
+        w1c, b1c, w2c, b2c = (t.detach().float().contiguous() for t in (w1, b1, w2, b2))
+        emb, saved = ops.head_fwd(feats.detach().contiguous(), channels, w1c, b1c, w2c, b2c)
+        ctx.save_for_backward(emb, *saved, w1c, w2c)
+        ctx.feat_shape = tuple(feats.shape)
+        ctx.channels = channels
+        return emb
+
+    @staticmethod
+    def backward(ctx, demb):
+        emb, pooled, hidden, onorm, w1c, w2c = ctx.saved_tensors
+        need_w = any(ctx.needs_input_grad[1:])
+        dw1, db1, dw2, db2, dfeat = ops.head_bwd(demb, emb, (pooled, hidden, onorm), ctx.feat_shape, ctx.channels,
+                                                 w1c, w2c, need_wgrad=need_w, need_dfeat=ctx.needs_input_grad[0])
+        return dfeat, dw1, db1, dw2, db2
+
+
+def head_forward(feats, w1, b1, w2, b2) -> torch.Tensor:
+    """mean-pool -> Linear -> ReLU -> Linear -> L2 normalise (network.py:595-596) -> fp32 [B,300]."""
+    return _HeadFn.apply(feats, w1, b1, w2, b2)
+
+
+class _ToNCDHW(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, channels):
+        ctx.shape = tuple(feats.shape)
+        return ops.ndhwc_to_ncdhw(feats.contiguous(), channels)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.ncdhw_to_ndhwc(g.contiguous()), None
+
+
+def features_to_ncdhw(feats: torch.Tensor, channels: int = 512) -> torch.Tensor:
+    return _ToNCDHW.apply(feats, channels)

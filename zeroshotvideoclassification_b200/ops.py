@@ -1,0 +1,272 @@
+"""Tensor-level wrappers over the C ABI (one Python function per entry point of include/zsv_b200.h).
+
+Tensors are torch CUDA tensors used purely as typed device buffers: activations are bf16 ``[N,T,H,W,cpad(C)]``
+(channels-last, pitch padded to 8), statistics and parameters fp32.  Every call enqueues on the current
+torch CUDA stream and never synchronises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, check, cpad, ptr
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: expected a CUDA tensor -- this package has no CPU path "
+                           "(the CPU oracle lives under oracle/ and is test infrastructure only)")
+
+
+_workspace = {}
+
+
+def workspace(nbytes: int, device, tag: str = "default") -> torch.Tensor:
+    """Grow-only scratch buffer per (device, tag); stream-ordered reuse on the current stream."""
+    key = (str(device), tag)
+    buf = _workspace.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspace[key] = buf
+    return buf
+
+
+class Conv3d:
+    """One convolution of fixed geometry: descriptor + derived sizes.  Mirrors an ``nn.Conv3d`` of the
+    reference (resnet.py:40-52,181-184,271; network.py:102-117)."""
+
+    def __init__(self, N, T, H, W, cin, cout, kernel, stride, padding, x_layout=_lib.X_NDHWC):
+        self.lib = _lib.load()
+        self.desc = ConvDesc(N, T, H, W, cin, cout, *kernel, *stride, *padding, x_layout)
+        out = (C.c_int32 * 3)()
+        check(self.lib.zsv_conv3d_out_shape(C.byref(self.desc), out), "zsv_conv3d_out_shape")
+        self.N, self.T, self.H, self.W, self.cin, self.cout = N, T, H, W, cin, cout
+        self.To, self.Ho, self.Wo = int(out[0]), int(out[1]), int(out[2])
+        self.kernel, self.stride, self.padding = tuple(kernel), tuple(stride), tuple(padding)
+        self.x_layout = x_layout
+        self.stat_rows = self.lib.zsv_conv3d_stat_rows(C.byref(self.desc))
+        self.wf_bytes = self.lib.zsv_conv3d_packed_weight_bytes(C.byref(self.desc), 0)
+        self.wd_bytes = self.lib.zsv_conv3d_packed_weight_bytes(C.byref(self.desc), 1)
+        self.wgrad_ws = self.lib.zsv_conv3d_wgrad_workspace(C.byref(self.desc))
+        self.out_positions = N * self.To * self.Ho * self.Wo
+
+    # -- weights ---------------------------------------------------------------------------------
+    def pack(self, w: torch.Tensor, need_dgrad: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        _require_cuda(w, "Conv3d.pack")
+        w = w.detach()
+        if w.dtype != torch.float32 or not w.is_contiguous():
+            w = w.float().contiguous()
+        wf = torch.empty(self.wf_bytes // 2, dtype=torch.bfloat16, device=w.device)
+        wd = None
+        if need_dgrad and self.wd_bytes:
+            wd = torch.empty(self.wd_bytes // 2, dtype=torch.bfloat16, device=w.device)
+        check(self.lib.zsv_conv3d_pack_weight(C.byref(self.desc), ptr(w), ptr(wf), ptr(wd), _stream()),
+              "zsv_conv3d_pack_weight")
+        return wf, wd
+
+    # -- forward ---------------------------------------------------------------------------------
+    def fprop(self, x, wf, stats: bool = True, bias=None, relu: bool = False):
+        y = torch.empty((self.N, self.To, self.Ho, self.Wo, cpad(self.cout)), dtype=torch.bfloat16, device=x.device)
+        ps = pq = None
+        if stats:
+            ps = torch.empty((self.stat_rows, cpad(self.cout)), dtype=torch.float32, device=x.device)
+            pq = torch.empty_like(ps)
+        check(self.lib.zsv_conv3d_fprop(C.byref(self.desc), ptr(x), ptr(wf), ptr(y), ptr(ps), ptr(pq), ptr(bias),
+                                        int(relu), _stream()), "zsv_conv3d_fprop")
+        return y, ps, pq
+
+    # -- backward --------------------------------------------------------------------------------
+    def dgrad(self, dy, wd, addend=None):
+        dx = torch.empty((self.N, self.T, self.H, self.W, cpad(self.cin)), dtype=torch.bfloat16, device=dy.device)
+        check(self.lib.zsv_conv3d_dgrad(C.byref(self.desc), ptr(dy), ptr(wd), ptr(dx), ptr(addend), _stream()),
+              "zsv_conv3d_dgrad")
+        return dx
+
+    def wgrad(self, x, dy, want_bias: bool = False):
+        dw = torch.empty((self.cout, self.cin, *self.kernel), dtype=torch.float32, device=dy.device)
+        db = torch.empty(self.cout, dtype=torch.float32, device=dy.device) if want_bias else None
+        ws = workspace(self.wgrad_ws, dy.device, "wgrad")
+        check(self.lib.zsv_conv3d_wgrad(C.byref(self.desc), ptr(x), ptr(dy), ptr(dw), ptr(db), ptr(ws), ws.numel(),
+                                        _stream()), "zsv_conv3d_wgrad")
+        return dw, db
+
+
+# ------------------------------------------------------------------------------------------------
+# layout
+# ------------------------------------------------------------------------------------------------
+def repack_input(x: torch.Tensor, layout: int = _lib.X_NDHWC, wpad_left: int = 0) -> torch.Tensor:
+    """fp32 NCDHW -> bf16 channels-last (network.py:534-535 reshapes, main.py:167 uploads)."""
+    _require_cuda(x, "repack_input")
+    lib = _lib.load()
+    x = x.detach()
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        x = x.float().contiguous()
+    N, Cc, T, H, W = x.shape
+    Wp = W + 8 if layout == _lib.X_WFOLD else W
+    out = torch.empty((N, T, H, Wp, cpad(Cc)), dtype=torch.bfloat16, device=x.device)
+    check(lib.zsv_repack_input(ptr(x), ptr(out), N, Cc, T, H, W, layout, wpad_left, _stream()), "zsv_repack_input")
+    return out
+
+
+def ndhwc_to_ncdhw(x: torch.Tensor, channels: int) -> torch.Tensor:
+    lib = _lib.load()
+    N, T, H, W, _ = x.shape
+    out = torch.empty((N, channels, T, H, W), dtype=torch.float32, device=x.device)
+    check(lib.zsv_ndhwc_to_ncdhw(ptr(x), ptr(out), N, channels, T, H, W, _stream()), "zsv_ndhwc_to_ncdhw")
+    return out
+
+
+def ncdhw_to_ndhwc(x: torch.Tensor) -> torch.Tensor:
+    return repack_input(x, _lib.X_NDHWC, 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# batch norm
+# ------------------------------------------------------------------------------------------------
+def bn_finalize(ps, pq, channels: int, count: int, gamma, beta, running_mean, running_var,
+                momentum: float = BN_MOMENTUM, eps: float = BN_EPS):
+    lib = _lib.load()
+    cp = cpad(channels)
+    out = torch.empty((4, cp), dtype=torch.float32, device=ps.device)
+    scale, shift, mean, invstd = out[0], out[1], out[2], out[3]
+    check(lib.zsv_bn_finalize(ptr(ps), ptr(pq), ps.shape[0], channels, count, ptr(gamma), ptr(beta),
+                              ptr(running_mean), ptr(running_var), momentum, eps, ptr(scale), ptr(shift), ptr(mean),
+                              ptr(invstd), _stream()), "zsv_bn_finalize")
+    return scale, shift, mean, invstd
+
+
+def bn_eval_scale_shift(channels: int, gamma, beta, running_mean, running_var, eps: float = BN_EPS):
+    lib = _lib.load()
+    cp = cpad(channels)
+    out = torch.empty((2, cp), dtype=torch.float32, device=running_mean.device)
+    check(lib.zsv_bn_eval_scale_shift(channels, ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), eps,
+                                      ptr(out[0]), ptr(out[1]), _stream()), "zsv_bn_eval_scale_shift")
+    return out[0], out[1]
+
+
+def bn_apply(y, scale, shift, channels: int, relu: bool, y2=None, scale2=None, shift2=None, residual=None):
+    lib = _lib.load()
+    out = torch.empty_like(y)
+    rows = y.numel() // y.shape[-1]
+    check(lib.zsv_bn_apply(ptr(y), ptr(scale), ptr(shift), ptr(y2), ptr(scale2), ptr(shift2), ptr(residual), ptr(out),
+                           rows, channels, int(relu), _stream()), "zsv_bn_apply")
+    return out
+
+
+def bn_bwd(g, out, relu: bool, y, mean, invstd, gamma, channels: int, y2=None, mean2=None, invstd2=None, gamma2=None,
+           want_dz: bool = False):
+    """Returns (dy, dy2, dz, dgamma, dbeta, dgamma2, dbeta2)."""
+    lib = _lib.load()
+    rows = y.numel() // y.shape[-1]
+    dy = torch.empty_like(y)
+    dy2 = torch.empty_like(y2) if y2 is not None else None
+    dz = torch.empty_like(y) if want_dz else None
+    dgb = torch.empty((4, channels), dtype=torch.float32, device=y.device)
+    ws_bytes = lib.zsv_bn_bwd_workspace(channels)
+    ws = workspace(ws_bytes, y.device, "bn_bwd")
+    has2 = y2 is not None
+    check(lib.zsv_bn_bwd(ptr(g), ptr(out) if relu else None, int(relu), ptr(y), ptr(mean), ptr(invstd), ptr(gamma),
+                         ptr(y2), ptr(mean2), ptr(invstd2), ptr(gamma2), ptr(dy), ptr(dy2), ptr(dz), ptr(dgb[0]),
+                         ptr(dgb[1]), ptr(dgb[2]) if has2 else None, ptr(dgb[3]) if has2 else None, rows, channels,
+                         ptr(ws), ws.numel(), _stream()), "zsv_bn_bwd")
+    return dy, dy2, dz, dgb[0], dgb[1], (dgb[2] if has2 else None), (dgb[3] if has2 else None)
+
+
+# ------------------------------------------------------------------------------------------------
+# head / loss / nearest class / pooling
+# ------------------------------------------------------------------------------------------------
+def head_fwd(feat, channels: int, w1, b1, w2, b2, eps: float = 1e-12):
+    lib = _lib.load()
+    B = feat.shape[0]
+    P = feat.numel() // (B * feat.shape[-1])
+    Hd, E = w1.shape[0], w2.shape[0]
+    dev = feat.device
+    pooled = torch.empty((B, channels), dtype=torch.float32, device=dev)
+    hidden = torch.empty((B, Hd), dtype=torch.float32, device=dev)
+    onorm = torch.empty((B,), dtype=torch.float32, device=dev)
+    emb = torch.empty((B, E), dtype=torch.float32, device=dev)
+    check(lib.zsv_head_fwd(ptr(feat), B, P, channels, ptr(w1), ptr(b1), Hd, ptr(w2), ptr(b2), E, eps, ptr(pooled),
+                           ptr(hidden), ptr(onorm), ptr(emb), _stream()), "zsv_head_fwd")
+    return emb, (pooled, hidden, onorm)
+
+
+def head_bwd(demb, emb, saved, feat_shape, channels: int, w1, w2, need_wgrad: bool = True, need_dfeat: bool = True,
+             eps: float = 1e-12):
+    lib = _lib.load()
+    pooled, hidden, onorm = saved
+    B, E = emb.shape
+    Hd = w1.shape[0]
+    P = 1
+    for s in feat_shape[1:-1]:
+        P *= s
+    dev = emb.device
+    dw1 = torch.empty_like(w1) if need_wgrad else None
+    db1 = torch.empty(Hd, dtype=torch.float32, device=dev) if need_wgrad else None
+    dw2 = torch.empty_like(w2) if need_wgrad else None
+    db2 = torch.empty(E, dtype=torch.float32, device=dev) if need_wgrad else None
+    dfeat = torch.empty(feat_shape, dtype=torch.bfloat16, device=dev) if need_dfeat else None
+    scratch = torch.empty(B * (E + Hd + channels), dtype=torch.float32, device=dev)
+    demb = demb.float().contiguous()
+    check(lib.zsv_head_bwd(ptr(demb), ptr(emb), ptr(onorm), ptr(pooled), ptr(hidden), B, P, channels, ptr(w1), Hd,
+                           ptr(w2), E, eps, ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(dfeat), ptr(scratch),
+                           _stream()), "zsv_head_bwd")
+    return dw1, db1, dw2, db2, dfeat
+
+
+def mse_fwd_bwd(emb, target, grad_scale: float = 1.0, want_grad: bool = True):
+    lib = _lib.load()
+    B, E = emb.shape
+    loss = torch.empty(1, dtype=torch.float32, device=emb.device)
+    demb = torch.empty_like(emb) if want_grad else None
+    check(lib.zsv_mse_fwd_bwd(ptr(emb), ptr(target), B, E, grad_scale, ptr(loss), ptr(demb), _stream()),
+          "zsv_mse_fwd_bwd")
+    return loss, demb
+
+
+def nearest_class(emb: torch.Tensor, cls: torch.Tensor, k: int = 1, return_dist: bool = False):
+    """int64 [N,k] indices of the k nearest class vectors by cosine distance (main.py:183, 321-322)."""
+    _require_cuda(emb, "nearest_class")
+    lib = _lib.load()
+    emb = emb.detach().float().contiguous()
+    cls = cls.detach().float().contiguous().to(emb.device)
+    N, D = emb.shape
+    Cn = cls.shape[0]
+    idx = torch.empty((N, k), dtype=torch.int64, device=emb.device)
+    dist = torch.empty((N, k), dtype=torch.float64, device=emb.device) if return_dist else None
+    check(lib.zsv_nearest_class(ptr(emb), ptr(cls), N, Cn, D, k, ptr(idx), ptr(dist), _stream()),
+          "zsv_nearest_class")
+    return (idx, dist) if return_dist else idx
+
+
+def maxpool3d_fwd(x, channels: int, kernel, padding=(0, 0, 0)):
+    lib = _lib.load()
+    N, T, H, W, cp = x.shape
+    kt, kh, kw = kernel
+    pt, ph, pw = padding
+    To, Ho, Wo = (T + 2 * pt - kt) // kt + 1, (H + 2 * ph - kh) // kh + 1, (W + 2 * pw - kw) // kw + 1
+    y = torch.empty((N, To, Ho, Wo, cp), dtype=torch.bfloat16, device=x.device)
+    am = torch.empty((N, To, Ho, Wo, cp), dtype=torch.int32, device=x.device)
+    check(lib.zsv_maxpool3d_fwd(ptr(x), ptr(y), ptr(am), N, T, H, W, channels, kt, kh, kw, pt, ph, pw, _stream()),
+          "zsv_maxpool3d_fwd")
+    return y, am
+
+
+def maxpool3d_bwd(dy, argmax, in_shape, channels: int, kernel, padding=(0, 0, 0)):
+    lib = _lib.load()
+    N, T, H, W, cp = in_shape
+    kt, kh, kw = kernel
+    pt, ph, pw = padding
+    dx = torch.empty(in_shape, dtype=torch.bfloat16, device=dy.device)
+    check(lib.zsv_maxpool3d_bwd(ptr(dy), ptr(argmax), ptr(dx), N, T, H, W, channels, kt, kh, kw, pt, ph, pw,
+                                _stream()), "zsv_maxpool3d_bwd")
+    return dx
