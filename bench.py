@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""Headline benchmark: R(2+1)D-18 training clips/s (16x112x112 clips, bf16 compute) on N x B200.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --gpus 1 --steps 4 --warmup 1      # CPU arm (oracle port of the reference)
+
+A step is exactly the reference's training iteration (main.py:170-207) on one synthetic batch of 22 clips per
+GPU: zero_grad -> model(X) -> MSELoss -> train-time nearest-class accuracy (main.py:182-185, here on the GPU) ->
+backward -> Adam step.  `value` is timed with the batch already resident in HBM; `e2e` repeats the measurement
+through the same public API with pinned HOST buffers (H2D of the clip batch and targets and D2H of the loss
+inside the timed region).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "R(2+1)D-18 train clips/s (16x112^2, bf16)"
+FLOP_PER_CLIP = 242.449e9          # fwd + dgrad + wgrad, SURVEY.md section 8(d) (no dgrad for stem.0)
+N_TRAIN_CLASSES = 664              # train-time class table (Kinetics after the tau-filter, any C <= 700)
+
+
+# ----------------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------------
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(tflops_sustained=p.get("bf16_tflops_sustained", 1400.0), tflops_burst=p.get("bf16_tflops", 1590.0),
+                    hbm_gbs=p.get("hbm_gbs", 6650.0), source="MEASURED_PEAKS.json (of measured)")
+    return dict(tflops_sustained=1400.0, tflops_burst=1590.0, hbm_gbs=6650.0,
+                source="B200_PROFILING.md fallback (of fallback)")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while a timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def conv_flops(op) -> float:
+    """Algorithmic FLOPs of one convolution pass (fprop, dgrad or wgrad): 2*M*N*K with unpadded channel counts."""
+    k = op.kernel[0] * op.kernel[1] * op.kernel[2]
+    return 2.0 * op.out_positions * op.cout * op.cin * k
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's training step on the host cores
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps: int, warmup: int, bs: int = 2):
+    """main.py:170-207 restated on the CPU oracle (fp32, torch CPU kernels on all host threads): forward,
+    MSELoss, nearest-class accuracy, backward, Adam.  Returns (clips_per_s, seconds_per_step list, threads)."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from oracle import nearest_oracle, video_oracle as vo
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = vo.synthetic_state_dict_r2plus1d(0)
+    params = {k: v.requires_grad_(True) for k, v in sd.items()
+              if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))}
+    optimizer = torch.optim.Adam(list(params.values()), lr=1e-3)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(bs, 1, 3, 16, 112, 112, generator=g)
+    cls = F.normalize(torch.randn(N_TRAIN_CLASSES, 300, generator=g))
+    labels = torch.randint(0, N_TRAIN_CLASSES, (bs,), generator=g)
+    z = cls[labels]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        optimizer.zero_grad()
+        emb = vo.model_forward(sd, x, train=True)
+        loss = vo.mse_loss(emb, z)
+        pred = nearest_oracle.nearest_class(emb.detach().numpy(), cls.numpy(), 1)[:, 0]
+        _acc = float(np.mean(pred == labels.numpy()))
+        loss.backward()
+        optimizer.step()
+        float(loss.detach())
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return bs * len(times) / total, times, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    bs = 2
+    cps, times, threads = cpu_reference_steps(args.steps, args.warmup, bs)
+    ms = 1e3 * sum(times) / len(times)
+    sample = (f"{len(times)} steps x {bs} clips (BASELINE.json config 1: bs=2x3x16x112x112, fp32) of the same training "
+              f"step on the host cores")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cps, "unit": "clips/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "R(2+1)D-18 training step, 16x112x112 clips, bs=22/GPU (CPU arm: bounded sample, bs=2 per step)",
+                   "network": "r2plus1d_18", "per_gpu_batch": 22, "cpu_step_batch": bs},
+        "cpu_baseline": {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": cps, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "oracle/ port of the reference path (the Python reference cannot travel to the GPU box); "
+                "torch CPU kernels, all host threads",
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+
+    from zeroshotvideoclassification_b200 import _lib, build, default_opt, get_network, ops
+    from zeroshotvideoclassification_b200 import dist as zdist
+    from zeroshotvideoclassification_b200.accuracy import nearest_class
+
+    build.build()
+    _lib.load()
+    rank, local_rank, world = zdist.init_from_env("nccl")
+    if world != args.gpus:
+        if rank == 0:
+            sys.stderr.write(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE\n")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    B = args.batch
+    torch.manual_seed(0)
+    model = get_network(default_opt(args.network)).to(dev).train()
+    zdist.broadcast_module(model)
+    criterion = torch.nn.MSELoss().to(dev)
+    optimizer = torch.optim.Adam(model.parameters(), lr=1e-3)
+    sync = zdist.GradSync() if world > 1 else None
+    zdist.set_grad_sync(sync)
+    head_params = list(model.output2emb_proj.parameters())
+
+    g = torch.Generator().manual_seed(1 + rank)
+    x_host = torch.randn(B, 1, 3, 16, 112, 112, generator=g).pin_memory()
+    cls = F.normalize(torch.randn(N_TRAIN_CLASSES, 300, generator=torch.Generator().manual_seed(7)))
+    labels = torch.randint(0, N_TRAIN_CLASSES, (B,), generator=g)
+    z_host = cls[labels].contiguous().pin_memory()
+    x_dev = x_host.to(dev)
+    z_dev = z_host.to(dev)
+    cls_dev = cls.to(dev)
+    labels_dev = labels.to(dev)
+    acc_sum = torch.zeros((), device=dev)
+
+    def step(X, Z):
+        optimizer.zero_grad(set_to_none=True)
+        out = model(X)
+        emb = out[0] if isinstance(out, tuple) else out
+        loss = criterion(emb, Z)
+        pred = nearest_class(emb.detach(), cls_dev, 1)[:, 0]          # main.py:182-185, without the host round trip
+        acc_sum.add_((pred == labels_dev).float().mean())
+        loss.backward()
+        if world > 1:
+            zdist.sync_head_grads(head_params)
+        optimizer.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    n_warm = args.warmup if args.quick else max(args.warmup, 3)
+    for _ in range(n_warm):
+        step(x_dev, z_dev)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM ----
+    prof = []
+    ops.set_profile(prof)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        loss = step(x_dev, z_dev)
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ops.set_profile(None)
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total / 1e3)
+    final_loss = float(loss.detach())
+
+    # per-kernel accounting from the CUDA events recorded around every convolution call in the timed region
+    kinds = {}
+    for kind, op, e0, e1 in prof:
+        d = kinds.setdefault(kind, {"ms": 0.0, "flops": 0.0, "calls": 0})
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += conv_flops(op)
+        d["calls"] += 1
+    peaks = load_peaks()
+    km = {k: {"ms_per_step": v["ms"] / args.steps, "calls_per_step": v["calls"] / args.steps,
+              "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 else None,
+              "share_of_step": v["ms"] / ms_total} for k, v in kinds.items()}
+    dom_ms = sum(kinds[k]["ms"] for k in ("fprop", "dgrad") if k in kinds)
+    dom_fl = sum(kinds[k]["flops"] for k in ("fprop", "dgrad") if k in kinds)
+    dom_calls = sum(kinds[k]["calls"] for k in ("fprop", "dgrad") if k in kinds)
+    achieved = dom_fl / (dom_ms / 1e3) / 1e12 if dom_ms > 0 else None
+    roofline = {
+        "bound": "tensor", "kernel": "igemm_kmajor_kernel (conv fprop + dgrad, tcgen05/TMA implicit GEMM)",
+        "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+        "frac": (achieved / peaks["tflops_sustained"]) if achieved else None, "traffic": None,
+        "peak_source": peaks["source"] + ", bf16_tflops_sustained (kernel timed inside a long step)",
+        "avg_launch_ms": dom_ms / dom_calls if dom_calls else None,
+        "flops_per_launch": dom_fl / dom_calls if dom_calls else None,
+        "share_of_step": dom_ms / ms_total if ms_total else None,
+        "by_kernel": km,
+        "whole_step_frac_of_tensor_peak": (value / world) * FLOP_PER_CLIP / (peaks["tflops_sustained"] * 1e12),
+    }
+
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world,
+                              "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_per_step, "quick": True,
+                              "roofline": roofline, "gpu_launches": launches, "clocks": clocks}))
+        return
+
+    # ---- timed region 2: end to end with host buffers ----
+    x_stage = torch.empty_like(x_dev)
+    z_stage = torch.empty_like(z_dev)
+
+    def e2e_step():
+        x_stage.copy_(x_host, non_blocking=True)
+        z_stage.copy_(z_host, non_blocking=True)
+        l = step(x_stage, z_stage)
+        return float(l.detach())            # D2H read of the step's loss (main.py:207)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t.item()) / 1e3)
+    h2d = x_host.numel() * 4 + z_host.numel() * 4
+    e2e = {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+           "ms_per_step": float(t.item()) / args.steps}
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cps, times, threads = cpu_reference_steps(4, 1, 2)
+        cpu = {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port",
+               "sample": f"{len(times)} steps x 2 clips (bs=2x3x16x112x112 fp32, BASELINE.json config 1) of the same "
+                         f"training step; {sum(times):.1f} s of CPU work"}
+    line = {
+        "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+        "warmup": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"R(2+1)D-18 end-to-end training step bs={B}/GPU, 16x112x112 synthetic clips, "
+                               f"Word2Vec-300 MSE regression, Adam (BASELINE.json configs[{1 if world == 1 else 2}])",
+                   "network": args.network, "per_gpu_batch": B, "global_batch": B * world, "clip": "3x16x112x112",
+                   "parallelism": f"dp{world}" if world > 1 else "single",
+                   "l2": "per-step working set (~6 GB of activations) is far larger than the 126 MB L2; no flush needed",
+                   "loss_scaling": "none (bf16)", "weights": "random init (resnet.py:226-236)"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "final_loss": final_loss,
+    }
+    if sync is not None:
+        line["allreduce_bytes_per_step"] = sync.bytes_reduced / (n_warm + 2 * args.steps + 2)
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=22, help="clips per GPU (README.md:45)")
+    ap.add_argument("--network", default="r2plus1d_18")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true",
+                    help="profiling aid (ncu): honour --warmup below 3, skip the e2e and CPU-baseline legs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

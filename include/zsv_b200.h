@@ -39,6 +39,8 @@ const char* zsv_last_error(void);
 int zsv_abi_version(void);
 /* Channel pitch used for a tensor with c channels: c rounded up to a multiple of 8. */
 int zsv_cpad(int c);
+/* Number of CUDA kernels this library has launched in the calling process so far (monotonic). */
+unsigned long long zsv_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Convolution descriptor.  Describes one nn.Conv3d of the reference:

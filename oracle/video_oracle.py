@@ -27,23 +27,20 @@ def midplanes(inplanes: int, planes: int) -> int:
 
 def batchnorm_train(x: Tensor, sd: Dict[str, Tensor], prefix: str, trace: Optional[dict] = None,
                     update_running: bool = True) -> Tensor:
-    """nn.BatchNorm3d in training mode (resnet.py:48,95,97,182,185,272): batch mean / biased variance over
-    (N,T,H,W); running stats updated with momentum 0.1 and the unbiased variance."""
-    dims = (0, 2, 3, 4)
-    mean = x.mean(dims)
-    var = x.var(dims, unbiased=False)
-    n = x.numel() // x.shape[1]
+    """nn.BatchNorm3d in training mode (resnet.py:48,95,97,182,185,272) through the same ATen op the module
+    calls (F.batch_norm): batch mean / biased variance over (N,T,H,W); running stats updated with momentum 0.1
+    and the unbiased variance; num_batches_tracked += 1."""
+    rm = sd[prefix + ".running_mean"] if update_running else None
+    rv = sd[prefix + ".running_var"] if update_running else None
+    y = F.batch_norm(x, rm, rv, sd[prefix + ".weight"], sd[prefix + ".bias"], training=True,
+                     momentum=BN_MOMENTUM, eps=BN_EPS)
     if update_running:
         with torch.no_grad():
-            sd[prefix + ".running_mean"].mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * mean.detach())
-            sd[prefix + ".running_var"].mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * var.detach() * n / max(n - 1, 1))
             sd[prefix + ".num_batches_tracked"].add_(1)
-    shape = (1, -1, 1, 1, 1)
-    xhat = (x - mean.view(shape)) / torch.sqrt(var.view(shape) + BN_EPS)
-    y = xhat * sd[prefix + ".weight"].view(shape) + sd[prefix + ".bias"].view(shape)
     if trace is not None:
-        trace[prefix + ":mean"] = mean.detach()
-        trace[prefix + ":var"] = var.detach()
+        with torch.no_grad():
+            trace[prefix + ":mean"] = x.mean((0, 2, 3, 4))
+            trace[prefix + ":var"] = x.var((0, 2, 3, 4), unbiased=False)
     return y
 
 
@@ -55,14 +52,57 @@ def batchnorm_eval(x: Tensor, sd: Dict[str, Tensor], prefix: str) -> Tensor:
         sd[prefix + ".bias"].view(shape)
 
 
-class _Net:
-    """Shared plumbing: conv / bn helpers that record per-layer tensors when tracing."""
+class _RoundBf16Both(torch.autograd.Function):
+    """bf16 storage point of an activation: rounds the value in forward and the gradient in backward."""
 
-    def __init__(self, sd: Dict[str, Tensor], train: bool, trace: Optional[dict]):
-        self.sd, self.train, self.trace = sd, train, trace
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+class _RoundBf16Fwd(torch.autograd.Function):
+    """bf16 copy of an fp32 master value (weights, input clip): rounds in forward, gradient passes in fp32."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _Net:
+    """Shared plumbing: conv / bn helpers that record per-layer tensors when tracing.
+
+    ``emulate_bf16`` places bf16 rounding at exactly the points where the B200 path stores bf16 (conv outputs,
+    post-activation tensors, their gradients, bf16 weight copies) while all arithmetic stays fp32 -- the same
+    mixed-precision contract as north_star ("bf16 compute, fp32 accumulate").  A randomly initialised 37-BN-deep
+    network amplifies any perturbation ~1e2-1e3x (numerics), so plain fp32 vs bf16 comparisons
+    only bound the error loosely; this mode checks the composition of the kernels tightly."""
+
+    def __init__(self, sd: Dict[str, Tensor], train: bool, trace: Optional[dict], emulate_bf16: bool = False):
+        self.sd, self.train, self.trace, self.emu = sd, train, trace, emulate_bf16
+
+    def act(self, x: Tensor, name: Optional[str] = None) -> Tensor:
+        """Storage point of a post-activation tensor (bf16 on the B200 path)."""
+        x = _RoundBf16Both.apply(x) if self.emu else x
+        if self.trace is not None and name is not None:
+            if x.requires_grad:
+                x.retain_grad()
+            self.trace[name + ":out"] = x
+        return x
 
     def conv(self, x: Tensor, name: str, stride, padding) -> Tensor:
-        y = F.conv3d(x, self.sd[name + ".weight"], self.sd.get(name + ".bias"), stride=stride, padding=padding)
+        w = self.sd[name + ".weight"]
+        if self.emu:
+            w = _RoundBf16Fwd.apply(w)
+        y = F.conv3d(x, w, self.sd.get(name + ".bias"), stride=stride, padding=padding)
+        y = _RoundBf16Both.apply(y) if self.emu else y
         if self.trace is not None:
             if y.requires_grad:
                 y.retain_grad()
@@ -82,7 +122,7 @@ def _conv2plus1d(net: _Net, x: Tensor, prefix: str, stride: int) -> Tensor:
     """Conv2Plus1D (resnet.py:37-57): spatial 1x3x3 (stride (1,s,s)) -> BN(mid) -> ReLU -> temporal 3x1x1
     (stride (s,1,1)); no bias."""
     x = net.conv(x, prefix + ".0", (1, stride, stride), (0, 1, 1))
-    x = F.relu(net.bn(x, prefix + ".1"))
+    x = net.act(F.relu(net.bn(x, prefix + ".1")), prefix + ".1")
     return net.conv(x, prefix + ".3", (stride, 1, 1), (1, 0, 0))
 
 
@@ -90,13 +130,13 @@ def _basic_block(net: _Net, x: Tensor, prefix: str, stride: int, has_ds: bool) -
     """BasicBlock.forward (resnet.py:102-113)."""
     residual = x
     out = _conv2plus1d(net, x, prefix + ".conv1.0", stride)
-    out = F.relu(net.bn(out, prefix + ".conv1.1"))
+    out = net.act(F.relu(net.bn(out, prefix + ".conv1.1")), prefix + ".conv1.1")
     out = _conv2plus1d(net, out, prefix + ".conv2.0", 1)
     out = net.bn(out, prefix + ".conv2.1")
     if has_ds:  # resnet.py:268-273: 1x1x1 conv, stride (s,s,s), then BN
         residual = net.conv(x, prefix + ".downsample.0", (stride, stride, stride), (0, 0, 0))
         residual = net.bn(residual, prefix + ".downsample.1")
-    out = F.relu(out + residual)
+    out = net.act(F.relu(out + residual))
     if net.trace is not None:
         if out.requires_grad:
             out.retain_grad()
@@ -105,15 +145,17 @@ def _basic_block(net: _Net, x: Tensor, prefix: str, stride: int, has_ds: bool) -
 
 
 def r2plus1d_18_features(sd: Dict[str, Tensor], x: Tensor, train: bool = True, trace: Optional[dict] = None,
-                         prefix: str = "model.") -> Tensor:
+                         prefix: str = "model.", emulate_bf16: bool = False) -> Tensor:
     """VideoResNet.forward up to layer4 (resnet.py:243-249) for r2plus1d_18 (resnet.py:342-362):
     x [B,3,T,H,W] -> f [B,512,T/8,H/16,W/16]."""
-    net = _Net({k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}, train, trace)
+    net = _Net({k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}, train, trace, emulate_bf16)
+    if emulate_bf16:
+        x = _RoundBf16Fwd.apply(x)
     # R2Plus1dStem (resnet.py:176-187)
     x = net.conv(x, "stem.0", (1, 2, 2), (0, 3, 3))
-    x = F.relu(net.bn(x, "stem.1"))
+    x = net.act(F.relu(net.bn(x, "stem.1")))
     x = net.conv(x, "stem.3", (1, 1, 1), (1, 0, 0))
-    x = F.relu(net.bn(x, "stem.4"))
+    x = net.act(F.relu(net.bn(x, "stem.4")))
     if trace is not None:
         trace["stem"] = x
     for li, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):  # _make_layer (resnet.py:258-281), layers=[2,2,2,2]
@@ -130,11 +172,12 @@ def embedding_head(sd: Dict[str, Tensor], feats: Tensor) -> Tensor:
     return F.normalize(o)
 
 
-def model_forward(sd: Dict[str, Tensor], x: Tensor, train: bool = True, trace: Optional[dict] = None) -> Tensor:
+def model_forward(sd: Dict[str, Tensor], x: Tensor, train: bool = True, trace: Optional[dict] = None,
+                  emulate_bf16: bool = False) -> Tensor:
     """network.Model.forward (network.py:533-600), live lines only: x [B,nc,3,T,H,W] -> emb [B*nc,300]."""
     bs, nc = x.shape[:2]
     x = x.reshape(bs * nc, *x.shape[2:])
-    feats = r2plus1d_18_features(sd, x, train, trace)
+    feats = r2plus1d_18_features(sd, x, train, trace, emulate_bf16=emulate_bf16)
     if trace is not None:
         trace["feats"] = feats
     return embedding_head(sd, feats)
@@ -169,13 +212,13 @@ def mse_loss(emb: Tensor, target: Tensor) -> Tensor:
 
 
 def train_step_grads(sd: Dict[str, Tensor], x: Tensor, target: Tensor, trace: Optional[dict] = None,
-                     loss_scale: float = 1.0) -> Tuple[Tensor, Tensor, Dict[str, Tensor]]:
+                     loss_scale: float = 1.0, emulate_bf16: bool = False) -> Tuple[Tensor, Tensor, Dict[str, Tensor]]:
     """One forward + backward of main.py:170-195 (no optimizer): returns (emb, loss, grads by state-dict key)."""
     params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()
               and not k.endswith(("running_mean", "running_var"))}
     work = dict(sd)
     work.update(params)
-    emb = model_forward(work, x, train=True, trace=trace)
+    emb = model_forward(work, x, train=True, trace=trace, emulate_bf16=emulate_bf16)
     loss = mse_loss(emb, target)
     (loss * loss_scale).backward()
     grads = {k: p.grad for k, p in params.items() if p.grad is not None}

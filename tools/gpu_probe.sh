@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,driver_version,memory.total --format=csv > gpurun_ou
 for f in "$@"; do
   name=$(basename "$f" .py)
   echo "=== $f ===" | tee -a gpurun_out/probe_summary.txt
-  timeout 600 python -m pytest "$f" -m gpu -q -x --timeout 300 -p no:cacheprovider -s > "gpurun_out/$name.log" 2>&1
+  timeout 600 python -m pytest "$f" -m gpu -q --timeout 300 -p no:cacheprovider -s > "gpurun_out/$name.log" 2>&1
   rc=$?
   echo "rc=$rc" | tee -a gpurun_out/probe_summary.txt
   tail -n 25 "gpurun_out/$name.log" | tee -a gpurun_out/probe_summary.txt

@@ -39,6 +39,7 @@ SIGNATURES = {
     "zsv_last_error": (C.c_char_p, []),
     "zsv_abi_version": (_I, []),
     "zsv_cpad": (_I, [_I]),
+    "zsv_launch_count": (C.c_ulonglong, []),
     "zsv_conv3d_out_shape": (_I, [_DP, C.POINTER(C.c_int32)]),
     "zsv_conv3d_packed_weight_bytes": (_SZ, [_DP, _I]),
     "zsv_conv3d_pack_weight": (_I, [_DP, _P, _P, _P, _P]),
@@ -98,6 +99,11 @@ def check(status: int, what: str) -> None:
 def ptr(t) -> int | None:
     """Device pointer of a torch tensor (None passes NULL)."""
     return None if t is None else t.data_ptr()
+
+
+def launch_count() -> int:
+    """Kernels launched by the library in this process so far."""
+    return int(load().zsv_launch_count())
 
 
 def cpad(c: int) -> int:

@@ -1,4 +1,5 @@
 // Error reporting and device queries shared by all entry points of libzsv_b200.so.
+#include <atomic>
 #include <mutex>
 #include <string.h>
 
@@ -15,6 +16,9 @@ int fail(int status, const char* fmt, ...) {
     va_end(ap);
     return status;
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int sm_count() {
     static int n = 0;
@@ -33,3 +37,4 @@ int sm_count() {
 extern "C" const char* zsv_last_error(void) { return zsv::g_err; }
 extern "C" int zsv_abi_version(void) { return 1; }
 extern "C" int zsv_cpad(int c) { return zsv::cpad(c); }
+extern "C" unsigned long long zsv_launch_count(void) { return zsv::g_launches.load(std::memory_order_relaxed); }

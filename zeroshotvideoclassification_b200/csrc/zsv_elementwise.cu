@@ -81,22 +81,22 @@ __global__ void ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ x, float
 
 // ------------------------------------------------------------------------------------------------
 // BatchNorm finalize: per-tile partials -> batch statistics, affine scale/shift, running stats
-// block = 32 channels x 32 row lanes
+// block = 32 channels x 16 row lanes
 // ------------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(const float* __restrict__ part_sum, const float* __restrict__ part_sq,
+__global__ void __launch_bounds__(512) bn_finalize_kernel(const float* __restrict__ part_sum, const float* __restrict__ part_sq,
                                    int part_rows, int C, int Cp, double count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float momentum, float eps,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                                    float* __restrict__ invstd_out) {
-    __shared__ double sh1[32][33];
-    __shared__ double sh2[32][33];
+    __shared__ double sh1[16][33];
+    __shared__ double sh2[16][33];
     const int cl = threadIdx.x & 31;
     const int rl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
     double a = 0.0, b = 0.0;
     if (c < Cp) {
-        for (int r = rl; r < part_rows; r += 32) {
+        for (int r = rl; r < part_rows; r += 16) {
             a += (double)part_sum[(long long)r * Cp + c];
             b += (double)part_sq[(long long)r * Cp + c];
         }
@@ -106,7 +106,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ part_sum, const flo
     __syncthreads();
     if (rl == 0 && c < Cp) {
         double s1 = 0.0, s2 = 0.0;
-        for (int r = 0; r < 32; ++r) {
+        for (int r = 0; r < 16; ++r) {
             s1 += sh1[r][cl];
             s2 += sh2[r][cl];
         }
@@ -493,7 +493,7 @@ extern "C" int zsv_bn_finalize(const float* part_sum, const float* part_sq, int 
         return fail(ZSV_ERR_BAD_ARG, "bn_finalize: null pointer");
     if (part_rows < 1 || C < 1 || count < 1) return fail(ZSV_ERR_BAD_ARG, "bn_finalize: bad sizes");
     const int Cp = cpad(C);
-    bn_finalize_kernel<<<ceil_div(Cp, 32), 1024, 0, (cudaStream_t)stream>>>(
+    bn_finalize_kernel<<<ceil_div(Cp, 32), 512, 0, (cudaStream_t)stream>>>(
         part_sum, part_sq, part_rows, C, Cp, (double)count, gamma, beta, running_mean, running_var, momentum, eps,
         scale, shift, mean, invstd);
     ZSV_LAUNCH_CHECK("bn_finalize_kernel");

@@ -18,6 +18,9 @@ inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b;
 // Number of SMs of the current device (cached).
 int sm_count();
 
+// Count one kernel launch issued by this library (read back through zsv_launch_count()).
+void count_launch();
+
 #define ZSV_CUDA_CHECK(expr)                                                                            \
     do {                                                                                                \
         cudaError_t _e = (expr);                                                                        \
@@ -31,6 +34,7 @@ int sm_count();
         cudaError_t _e = cudaGetLastError();                                                            \
         if (_e != cudaSuccess)                                                                          \
             return ::zsv::fail(ZSV_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(_e));  \
+        ::zsv::count_launch();                                                                          \
     } while (0)
 
 }  // namespace zsv

@@ -192,48 +192,65 @@ class BackboneRunner:
         return out, (N, *d4)
 
     # -- backward ----------------------------------------------------------------------------------
+    def _conv_bwd(self, rec: UnitRec, dy, grads, want, addend=None, need_dx: bool = True):
+        if want.get(rec.spec.name + ".weight", True):
+            grads[rec.spec.name + ".weight"], _ = rec.op.wgrad(rec.x, dy)
+        return rec.op.dgrad(dy, rec.wd, addend) if need_dx else None
+
+    def _unit_bwd(self, rec: UnitRec, gin, grads, want, addend=None, need_dx: bool = True):
+        """gin: gradient w.r.t. rec.out (post BN/ReLU).  Returns the gradient w.r.t. rec.x."""
+        dy, _, _, dgamma, dbeta, _, _ = ops.bn_bwd(gin, rec.out, rec.relu, rec.y, rec.mean, rec.invstd,
+                                                   self.t[rec.spec.bn + ".weight"], rec.spec.cout)
+        grads[rec.spec.bn + ".weight"] = dgamma
+        grads[rec.spec.bn + ".bias"] = dbeta
+        return self._conv_bwd(rec, dy, grads, want, addend, need_dx)
+
+    def block_backward(self, brec: BlockRec, g, grads, want):
+        """g: gradient w.r.t. the block output -> gradient w.r.t. the block input (resnet.py:102-113 reversed)."""
+        tail, ds = brec.units[3], brec.ds
+        if ds is not None:
+            dy_t, dy_d, _, dg, db, dg2, db2 = ops.bn_bwd(
+                g, brec.out, True, tail.y, tail.mean, tail.invstd, self.t[tail.spec.bn + ".weight"],
+                tail.spec.cout, y2=ds.y, mean2=ds.mean, invstd2=ds.invstd, gamma2=self.t[ds.spec.bn + ".weight"])
+            grads[ds.spec.bn + ".weight"], grads[ds.spec.bn + ".bias"] = dg2, db2
+            dz = None
+        else:
+            dy_t, _, dz, dg, db, _, _ = ops.bn_bwd(
+                g, brec.out, True, tail.y, tail.mean, tail.invstd, self.t[tail.spec.bn + ".weight"],
+                tail.spec.cout, want_dz=True)
+        grads[tail.spec.bn + ".weight"], grads[tail.spec.bn + ".bias"] = dg, db
+        ga = self._conv_bwd(tail, dy_t, grads, want)              # grad w.r.t. spatial2 output
+        ga = self._unit_bwd(brec.units[2], ga, grads, want)       # -> grad w.r.t. block conv1 output
+        ga = self._unit_bwd(brec.units[1], ga, grads, want)       # -> grad w.r.t. spatial1 output
+        if ds is not None:
+            gx = self._unit_bwd(brec.units[0], ga, grads, want)   # main branch
+            return self._conv_bwd(ds, dy_d, grads, want, addend=gx)   # + projected shortcut
+        return self._unit_bwd(brec.units[0], ga, grads, want, addend=dz)  # + identity shortcut
+
     def backward(self, g: torch.Tensor, want: Dict[str, bool]) -> Dict[str, torch.Tensor]:
         """g: gradient w.r.t. the backbone output (bf16 NDHWC).  Returns grads keyed by parameter name."""
+        if not self.train:
+            raise NotImplementedError("backward through eval-mode BatchNorm is not part of the hot path "
+                                      "(the reference only back-propagates in train mode, main.py:143,195)")
+        from . import dist as zdist
+        sync = zdist.active_grad_sync()
         grads: Dict[str, torch.Tensor] = {}
         g = g.contiguous()
-
-        def unit_bwd(rec: UnitRec, gin: torch.Tensor, addend=None, need_dx: bool = True):
-            """gin: gradient w.r.t. rec.out (post BN/ReLU).  Returns gradient w.r.t. rec.x."""
-            dy, _, _, dgamma, dbeta, _, _ = ops.bn_bwd(gin, rec.out, rec.relu, rec.y, rec.mean, rec.invstd,
-                                                       self.t[rec.spec.bn + ".weight"], rec.spec.cout)
-            grads[rec.spec.bn + ".weight"] = dgamma
-            grads[rec.spec.bn + ".bias"] = dbeta
-            return conv_bwd(rec, dy, addend, need_dx)
-
-        def conv_bwd(rec: UnitRec, dy: torch.Tensor, addend=None, need_dx: bool = True):
-            if want.get(rec.spec.name + ".weight", True):
-                grads[rec.spec.name + ".weight"], _ = rec.op.wgrad(rec.x, dy)
-            return rec.op.dgrad(dy, rec.wd, addend) if need_dx else None
-
         for brec in reversed(self.block_recs):
-            tail = brec.units[3]
-            ds = brec.ds
-            if ds is not None:
-                dy_t, dy_d, _, dg, db, dg2, db2 = ops.bn_bwd(
-                    g, brec.out, True, tail.y, tail.mean, tail.invstd, self.t[tail.spec.bn + ".weight"],
-                    tail.spec.cout, y2=ds.y, mean2=ds.mean, invstd2=ds.invstd, gamma2=self.t[ds.spec.bn + ".weight"])
-                grads[ds.spec.bn + ".weight"], grads[ds.spec.bn + ".bias"] = dg2, db2
-                dz = None
-            else:
-                dy_t, _, dz, dg, db, _, _ = ops.bn_bwd(
-                    g, brec.out, True, tail.y, tail.mean, tail.invstd, self.t[tail.spec.bn + ".weight"],
-                    tail.spec.cout, want_dz=True)
-            grads[tail.spec.bn + ".weight"], grads[tail.spec.bn + ".bias"] = dg, db
-            ga = conv_bwd(tail, dy_t)                       # grad w.r.t. spatial2 output
-            ga = unit_bwd(brec.units[2], ga)                # -> grad w.r.t. block conv1 output
-            ga = unit_bwd(brec.units[1], ga)                # -> grad w.r.t. spatial1 output
-            if ds is not None:
-                gx = unit_bwd(brec.units[0], ga)            # main branch
-                g = conv_bwd(ds, dy_d, addend=gx)           # + projected shortcut
-            else:
-                g = unit_bwd(brec.units[0], ga, addend=dz)  # + identity shortcut
-        ga = unit_bwd(self.stem_recs[1], g)
-        unit_bwd(self.stem_recs[0], ga, need_dx=False)
+            blk: Dict[str, torch.Tensor] = {}
+            g = self.block_backward(brec, g, blk, want)
+            if sync is not None:
+                sync.submit(blk)          # all-reduce of this block overlaps the next block's backward
+            grads.update(blk)
+        blk = {}
+        ga = self._unit_bwd(self.stem_recs[1], g, blk, want)
+        self._unit_bwd(self.stem_recs[0], ga, blk, want, need_dx=False)
+        if sync is not None:
+            sync.submit(blk)
+            grads.update(blk)
+            grads.update(sync.finish())   # averaged gradients replace the local ones
+        else:
+            grads.update(blk)
         return grads
 
 

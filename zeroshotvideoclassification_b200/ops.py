@@ -29,6 +29,30 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
 
 
 _workspace = {}
+_profile = None   # when a list: (kind, conv, start_event, end_event) appended around every convolution call
+
+
+def set_profile(sink) -> None:
+    """bench.py: record CUDA events (on the launching stream) around each convolution call into ``sink``."""
+    global _profile
+    _profile = sink
+
+
+class _Timed:
+    def __init__(self, kind, conv):
+        self.kind, self.conv = kind, conv
+
+    def __enter__(self):
+        if _profile is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _profile is not None and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _profile.append((self.kind, self.conv, self.e0, e1))
+        return False
 
 
 def workspace(nbytes: int, device, tag: str = "default") -> torch.Tensor:
@@ -81,23 +105,26 @@ class Conv3d:
         if stats:
             ps = torch.empty((self.stat_rows, cpad(self.cout)), dtype=torch.float32, device=x.device)
             pq = torch.empty_like(ps)
-        check(self.lib.zsv_conv3d_fprop(C.byref(self.desc), ptr(x), ptr(wf), ptr(y), ptr(ps), ptr(pq), ptr(bias),
-                                        int(relu), _stream()), "zsv_conv3d_fprop")
+        with _Timed("fprop", self):
+            check(self.lib.zsv_conv3d_fprop(C.byref(self.desc), ptr(x), ptr(wf), ptr(y), ptr(ps), ptr(pq), ptr(bias),
+                                            int(relu), _stream()), "zsv_conv3d_fprop")
         return y, ps, pq
 
     # -- backward --------------------------------------------------------------------------------
     def dgrad(self, dy, wd, addend=None):
         dx = torch.empty((self.N, self.T, self.H, self.W, cpad(self.cin)), dtype=torch.bfloat16, device=dy.device)
-        check(self.lib.zsv_conv3d_dgrad(C.byref(self.desc), ptr(dy), ptr(wd), ptr(dx), ptr(addend), _stream()),
-              "zsv_conv3d_dgrad")
+        with _Timed("dgrad", self):
+            check(self.lib.zsv_conv3d_dgrad(C.byref(self.desc), ptr(dy), ptr(wd), ptr(dx), ptr(addend), _stream()),
+                  "zsv_conv3d_dgrad")
         return dx
 
     def wgrad(self, x, dy, want_bias: bool = False):
         dw = torch.empty((self.cout, self.cin, *self.kernel), dtype=torch.float32, device=dy.device)
         db = torch.empty(self.cout, dtype=torch.float32, device=dy.device) if want_bias else None
         ws = workspace(self.wgrad_ws, dy.device, "wgrad")
-        check(self.lib.zsv_conv3d_wgrad(C.byref(self.desc), ptr(x), ptr(dy), ptr(dw), ptr(db), ptr(ws), ws.numel(),
-                                        _stream()), "zsv_conv3d_wgrad")
+        with _Timed("wgrad", self):
+            check(self.lib.zsv_conv3d_wgrad(C.byref(self.desc), ptr(x), ptr(dy), ptr(dw), ptr(db), ptr(ws),
+                                            ws.numel(), _stream()), "zsv_conv3d_wgrad")
         return dw, db
 
 
@@ -243,6 +270,8 @@ def nearest_class(emb: torch.Tensor, cls: torch.Tensor, k: int = 1, return_dist:
     Cn = cls.shape[0]
     idx = torch.empty((N, k), dtype=torch.int64, device=emb.device)
     dist = torch.empty((N, k), dtype=torch.float64, device=emb.device) if return_dist else None
+    if N == 0:   # empty batch (every sample of a batch was filtered, main.py:157-158)
+        return (idx, dist) if return_dist else idx
     check(lib.zsv_nearest_class(ptr(emb), ptr(cls), N, Cn, D, k, ptr(idx), ptr(dist), _stream()),
           "zsv_nearest_class")
     return (idx, dist) if return_dist else idx
