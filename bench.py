@@ -266,6 +266,21 @@ def run_b200(args):
         d["ms"] += e0.elapsed_time(e1)
         d["flops"] += conv_flops(op)
         d["calls"] += 1
+    if args.layer_table:
+        # per-layer table (stderr): which convolutions run far from the tensor roofline
+        tab = {}
+        for kind, op, e0, e1 in prof:
+            key = (kind, op.cin, op.cout, op.kernel, op.stride, op.T, op.H)
+            d = tab.setdefault(key, [0.0, 0.0, 0])
+            d[0] += e0.elapsed_time(e1)
+            d[1] += conv_flops(op)
+            d[2] += 1
+        if rank == 0:
+            sys.stderr.write("kind  cin->cout kernel stride TxH : calls/step  us/call  TFLOP/s  ms/step\n")
+            for key, (ms, fl, n) in sorted(tab.items(), key=lambda kv: -kv[1][0]):
+                sys.stderr.write(f"{key[0]:5s} {key[1]:4d}->{key[2]:4d} {key[3]} {key[4]} {key[5]}x{key[6]} : "
+                                 f"{n / args.steps:4.0f} {1e3 * ms / n:9.1f} {fl / (ms / 1e3) / 1e12:8.1f} "
+                                 f"{ms / args.steps:7.3f}\n")
     peaks = load_peaks()
     km = {k: {"ms_per_step": v["ms"] / args.steps, "calls_per_step": v["calls"] / args.steps,
               "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 else None,
@@ -355,6 +370,7 @@ def main():
     ap.add_argument("--batch", type=int, default=22, help="clips per GPU (README.md:45)")
     ap.add_argument("--network", default="r2plus1d_18")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layer-table", action="store_true", help="print a per-layer conv timing table to stderr")
     ap.add_argument("--quick", action="store_true",
                     help="profiling aid (ncu): honour --warmup below 3, skip the e2e and CPU-baseline legs")
     args = ap.parse_args()

@@ -116,10 +116,13 @@ int zsv_ncdhw_to_ndhwc(const float* x, void* out, int N, int C, int T, int H, in
  * ---------------------------------------------------------------------------------------------- */
 /* Reduce per-tile partials to batch mean / biased variance; emit scale = gamma*invstd,
  * shift = beta - mean*scale, mean, invstd (all fp32 [cpad(C)]); update running_mean / running_var
- * (momentum, unbiased variance) in place when they are non-NULL. */
+ * (momentum, unbiased variance) in place when they are non-NULL.  Two-stage fp64 reduction through a
+ * caller-provided workspace (zsv_bn_finalize_workspace bytes). */
+size_t zsv_bn_finalize_workspace(int C);
 int zsv_bn_finalize(const float* part_sum, const float* part_sq, int part_rows, int C, long long count,
                     const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum,
-                    float eps, float* scale, float* shift, float* mean, float* invstd, void* stream);
+                    float eps, float* scale, float* shift, float* mean, float* invstd, void* workspace,
+                    size_t workspace_bytes, void* stream);
 /* Eval mode: scale/shift from running statistics (main.py:229). */
 int zsv_bn_eval_scale_shift(int C, const float* gamma, const float* beta, const float* running_mean,
                             const float* running_var, float eps, float* scale, float* shift, void* stream);

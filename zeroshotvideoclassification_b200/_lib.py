@@ -12,7 +12,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libzsv_b200.so"
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 X_NDHWC = 0
 X_WFOLD = 1
 
@@ -51,7 +51,8 @@ SIGNATURES = {
     "zsv_repack_input": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "zsv_ndhwc_to_ncdhw": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "zsv_ncdhw_to_ndhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
-    "zsv_bn_finalize": (_I, [_P, _P, _I, _I, _LL, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P]),
+    "zsv_bn_finalize_workspace": (_SZ, [_I]),
+    "zsv_bn_finalize": (_I, [_P, _P, _I, _I, _LL, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _SZ, _P]),
     "zsv_bn_eval_scale_shift": (_I, [_I, _P, _P, _P, _P, _F, _P, _P, _P]),
     "zsv_bn_apply": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _P]),
     "zsv_bn_bwd_workspace": (_SZ, [_I]),

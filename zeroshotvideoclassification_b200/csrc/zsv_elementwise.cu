@@ -80,15 +80,46 @@ __global__ void ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ x, float
 }
 
 // ------------------------------------------------------------------------------------------------
-// BatchNorm finalize: per-tile partials -> batch statistics, affine scale/shift, running stats
-// block = 32 channels x 16 row lanes
+// BatchNorm finalize: per-tile partials -> batch statistics, affine scale/shift, running stats.
+//   stage 1 (grid = 32-channel groups x row chunks, block = 32 channels x 32 row lanes): fp64 chunk sums
+//   stage 2 (block = 32 channels x 16 chunk lanes): total, mean / var / invstd, scale / shift, running stats
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) bn_finalize_kernel(const float* __restrict__ part_sum, const float* __restrict__ part_sq,
-                                   int part_rows, int C, int Cp, double count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, float momentum, float eps,
-                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
-                                   float* __restrict__ invstd_out) {
+__global__ void __launch_bounds__(1024)
+bn_finalize_stage1_kernel(const float* __restrict__ part_sum, const float* __restrict__ part_sq, int part_rows,
+                          int Cp, int rows_per_chunk, double* __restrict__ chunk) {
+    __shared__ double sh1[32][33];
+    __shared__ double sh2[32][33];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    const int r0 = blockIdx.y * rows_per_chunk;
+    const int r1 = min(part_rows, r0 + rows_per_chunk);
+    double a = 0.0, b = 0.0;
+    if (c < Cp) {
+        for (int r = r0 + rl; r < r1; r += 32) {
+            a += (double)part_sum[(long long)r * Cp + c];
+            b += (double)part_sq[(long long)r * Cp + c];
+        }
+    }
+    sh1[rl][cl] = a;
+    sh2[rl][cl] = b;
+    __syncthreads();
+    if (rl == 0 && c < Cp) {
+        a = b = 0.0;
+        for (int r = 0; r < 32; ++r) {
+            a += sh1[r][cl];
+            b += sh2[r][cl];
+        }
+        chunk[((long long)blockIdx.y * 2 + 0) * Cp + c] = a;
+        chunk[((long long)blockIdx.y * 2 + 1) * Cp + c] = b;
+    }
+}
+
+__global__ void __launch_bounds__(512)
+bn_finalize_stage2_kernel(const double* __restrict__ chunk, int nchunks, int C, int Cp, double count,
+                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                          float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
+                          float eps, float* __restrict__ scale, float* __restrict__ shift,
+                          float* __restrict__ mean_out, float* __restrict__ invstd_out) {
     __shared__ double sh1[16][33];
     __shared__ double sh2[16][33];
     const int cl = threadIdx.x & 31;
@@ -96,9 +127,9 @@ __global__ void __launch_bounds__(512) bn_finalize_kernel(const float* __restric
     const int c = blockIdx.x * 32 + cl;
     double a = 0.0, b = 0.0;
     if (c < Cp) {
-        for (int r = rl; r < part_rows; r += 16) {
-            a += (double)part_sum[(long long)r * Cp + c];
-            b += (double)part_sq[(long long)r * Cp + c];
+        for (int r = rl; r < nchunks; r += 16) {
+            a += chunk[((long long)r * 2 + 0) * Cp + c];
+            b += chunk[((long long)r * 2 + 1) * Cp + c];
         }
     }
     sh1[rl][cl] = a;
@@ -177,28 +208,44 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
     }
     __syncthreads();
     const int V = Cp >> 3;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = static_cast<int>(i % V) << 3;
-        float f[8], o[8];
-        unpack8(*reinterpret_cast<const uint4*>(y + i * 8), f);
+    constexpr int U = 4;  // independent 16-byte vectors in flight per thread
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < nvec; i0 += U * stride) {
+        uint4 vy[U], vy2[U], vr[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf(f[j], s_scale[c0 + j], s_shift[c0 + j]);
-        if (kHasY2) {
-            unpack8(*reinterpret_cast<const uint4*>(y2 + i * 8), f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] += fmaf(f[j], s_scale2[c0 + j], s_shift2[c0 + j]);
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < nvec) {
+                vy[u] = *reinterpret_cast<const uint4*>(y + i * 8);
+                if (kHasY2) vy2[u] = *reinterpret_cast<const uint4*>(y2 + i * 8);
+                if (kHasRes) vr[u] = *reinterpret_cast<const uint4*>(res + i * 8);
+            }
         }
-        if (kHasRes) {
-            unpack8(*reinterpret_cast<const uint4*>(res + i * 8), f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] += f[j];
-        }
-        if (relu) {
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i >= nvec) break;
+            const int c0 = static_cast<int>(i % V) << 3;
+            float f[8], o[8];
+            unpack8(vy[u], f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(f[j], s_scale[c0 + j], s_shift[c0 + j]);
+            if (kHasY2) {
+                unpack8(vy2[u], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] += fmaf(f[j], s_scale2[c0 + j], s_shift2[c0 + j]);
+            }
+            if (kHasRes) {
+                unpack8(vr[u], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] += f[j];
+            }
+            if (relu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+            }
+            *reinterpret_cast<uint4*>(out + i * 8) = pack8(o);
         }
-        *reinterpret_cast<uint4*>(out + i * 8) = pack8(o);
     }
 }
 
@@ -278,14 +325,23 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* _
     (void)b1;
 }
 
-__global__ void bn_bwd_final_kernel(const float* __restrict__ partial, int nblocks, int nq, int C, int Cp,
-                                    float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                    float* __restrict__ dgamma2, float* __restrict__ dbeta2) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq * Cp) return;
-    const int qi = i / Cp, c = i - qi * Cp;
+__global__ void __launch_bounds__(1024)
+bn_bwd_final_kernel(const float* __restrict__ partial, int nblocks, int nq, int C, int Cp,
+                    float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                    float* __restrict__ dgamma2, float* __restrict__ dbeta2) {
+    // block = 32 columns (q*Cp + c) x 32 row lanes over the per-block partials
+    __shared__ double sh[32][33];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + cl;
     double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += (double)partial[((long long)b * 4 + qi) * Cp + c];
+    if (i < nq * Cp)
+        for (int b = rl; b < nblocks; b += 32) s += (double)partial[(long long)b * 4 * Cp + i];
+    sh[rl][cl] = s;
+    __syncthreads();
+    if (rl != 0 || i >= nq * Cp) return;
+    s = 0.0;
+    for (int r = 0; r < 32; ++r) s += sh[r][cl];
+    const int qi = i / Cp, c = i - qi * Cp;
     sums[qi * Cp + c] = (float)s;
     if (c < C) {
         if (qi == 0 && dbeta) dbeta[c] = (float)s;
@@ -331,33 +387,50 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __
     }
     __syncthreads();
     const int V = Cp >> 3;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int c0 = static_cast<int>(i % V) << 3;
-        float gz[8], f[8], o[8];
-        unpack8(*reinterpret_cast<const uint4*>(g + i * 8), gz);
-        if (relu) {
-            unpack8(*reinterpret_cast<const uint4*>(out + i * 8), f);
+    constexpr int U = 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < nvec; i0 += U * stride) {
+        uint4 vg[U], vo[U], vy[U], vy2[U];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) gz[j] = f[j] > 0.f ? gz[j] : 0.f;
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < nvec) {
+                vg[u] = *reinterpret_cast<const uint4*>(g + i * 8);
+                if (relu) vo[u] = *reinterpret_cast<const uint4*>(out + i * 8);
+                vy[u] = *reinterpret_cast<const uint4*>(y + i * 8);
+                if (kHasY2) vy2[u] = *reinterpret_cast<const uint4*>(y2 + i * 8);
+            }
         }
-        unpack8(*reinterpret_cast<const uint4*>(y + i * 8), f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float xh = (f[j] - p_mu[c0 + j]) * p_is[c0 + j];
-            o[j] = p_k[c0 + j] * (gz[j] - p_c1[c0 + j] - xh * p_c2[c0 + j]);
-        }
-        *reinterpret_cast<uint4*>(dy + i * 8) = pack8(o);
-        if (kHasY2) {
-            unpack8(*reinterpret_cast<const uint4*>(y2 + i * 8), f);
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i >= nvec) break;
+            const int c0 = static_cast<int>(i % V) << 3;
+            float gz[8], f[8], o[8];
+            unpack8(vg[u], gz);
+            if (relu) {
+                unpack8(vo[u], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) gz[j] = f[j] > 0.f ? gz[j] : 0.f;
+            }
+            unpack8(vy[u], f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float xh = (f[j] - q_mu[c0 + j]) * q_is[c0 + j];
-                o[j] = q_k[c0 + j] * (gz[j] - p_c1[c0 + j] - xh * q_c2[c0 + j]);
+                const float xh = (f[j] - p_mu[c0 + j]) * p_is[c0 + j];
+                o[j] = p_k[c0 + j] * (gz[j] - p_c1[c0 + j] - xh * p_c2[c0 + j]);
             }
-            *reinterpret_cast<uint4*>(dy2 + i * 8) = pack8(o);
+            *reinterpret_cast<uint4*>(dy + i * 8) = pack8(o);
+            if (kHasY2) {
+                unpack8(vy2[u], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float xh = (f[j] - q_mu[c0 + j]) * q_is[c0 + j];
+                    o[j] = q_k[c0 + j] * (gz[j] - p_c1[c0 + j] - xh * q_c2[c0 + j]);
+                }
+                *reinterpret_cast<uint4*>(dy2 + i * 8) = pack8(o);
+            }
+            if (dz != nullptr) *reinterpret_cast<uint4*>(dz + i * 8) = pack8(gz);
         }
-        if (dz != nullptr) *reinterpret_cast<uint4*>(dz + i * 8) = pack8(gz);
     }
 }
 
@@ -485,18 +558,36 @@ extern "C" int zsv_ndhwc_to_ncdhw(const void* x, float* out, int N, int C, int T
     return ZSV_OK;
 }
 
+namespace {
+constexpr int kFinalizeMaxChunks = 64;
+}
+
+extern "C" size_t zsv_bn_finalize_workspace(int C) {
+    return (size_t)kFinalizeMaxChunks * 2 * cpad(C) * sizeof(double);
+}
+
 extern "C" int zsv_bn_finalize(const float* part_sum, const float* part_sq, int part_rows, int C, long long count,
                                const float* gamma, const float* beta, float* running_mean, float* running_var,
                                float momentum, float eps, float* scale, float* shift, float* mean, float* invstd,
-                               void* stream) {
-    if (!part_sum || !part_sq || !scale || !shift || !mean || !invstd)
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    if (!part_sum || !part_sq || !scale || !shift || !mean || !invstd || !workspace)
         return fail(ZSV_ERR_BAD_ARG, "bn_finalize: null pointer");
     if (part_rows < 1 || C < 1 || count < 1) return fail(ZSV_ERR_BAD_ARG, "bn_finalize: bad sizes");
+    if (workspace_bytes < zsv_bn_finalize_workspace(C)) return fail(ZSV_ERR_WORKSPACE, "bn_finalize: workspace too small");
     const int Cp = cpad(C);
-    bn_finalize_kernel<<<ceil_div(Cp, 32), 512, 0, (cudaStream_t)stream>>>(
-        part_sum, part_sq, part_rows, C, Cp, (double)count, gamma, beta, running_mean, running_var, momentum, eps,
-        scale, shift, mean, invstd);
-    ZSV_LAUNCH_CHECK("bn_finalize_kernel");
+    cudaStream_t st = (cudaStream_t)stream;
+    // ~128 partial rows per chunk keeps every stage-1 block busy while spreading large layers over many SMs
+    int nchunks = std::max(1, std::min(kFinalizeMaxChunks, ceil_div(part_rows, 128)));
+    const int rows_per_chunk = ceil_div(part_rows, nchunks);
+    nchunks = ceil_div(part_rows, rows_per_chunk);
+    double* chunk = (double*)workspace;
+    bn_finalize_stage1_kernel<<<dim3(ceil_div(Cp, 32), nchunks), 1024, 0, st>>>(part_sum, part_sq, part_rows, Cp,
+                                                                                 rows_per_chunk, chunk);
+    ZSV_LAUNCH_CHECK("bn_finalize_stage1_kernel");
+    bn_finalize_stage2_kernel<<<ceil_div(Cp, 32), 512, 0, st>>>(chunk, nchunks, C, Cp, (double)count, gamma, beta,
+                                                                running_mean, running_var, momentum, eps, scale, shift,
+                                                                mean, invstd);
+    ZSV_LAUNCH_CHECK("bn_finalize_stage2_kernel");
     return ZSV_OK;
 }
 
@@ -578,7 +669,7 @@ extern "C" int zsv_bn_bwd(const void* g, const void* out, int relu, const void* 
         bn_bwd_reduce_kernel<false><<<nblocks, 256, smem_r, st>>>(gb, ob, relu, yb, mean, invstd, y2b, mean2, invstd2, rows, Cp, R, partial);
     ZSV_LAUNCH_CHECK("bn_bwd_reduce_kernel");
     const int nq = y2 ? 4 : 2;
-    bn_bwd_final_kernel<<<ceil_div(nq * Cp, 128), 128, 0, st>>>(partial, nblocks, nq, C, Cp, sums, dgamma, dbeta, dgamma2, dbeta2);
+    bn_bwd_final_kernel<<<ceil_div(nq * Cp, 32), 1024, 0, st>>>(partial, nblocks, nq, C, Cp, sums, dgamma, dbeta, dgamma2, dbeta2);
     ZSV_LAUNCH_CHECK("bn_bwd_final_kernel");
     const long long nvec = rows * V;
     const int blocks = ew_blocks(nvec, 256 * 4);

@@ -166,26 +166,26 @@ __global__ void mse_kernel(const float* __restrict__ emb, const float* __restric
 // block = 128 threads (one class each per tile) x kRows embedding rows; distances staged in shared memory,
 // then one warp per row extracts the k smallest (lowest index wins ties, NaN sorts last).
 // ------------------------------------------------------------------------------------------------
-constexpr int kRows = 8;
 constexpr int kKC = 32;  // k-chunk of the class tile staged in shared memory
 
+template <int R>
 __global__ void __launch_bounds__(128)
 nearest_kernel(const float* __restrict__ emb, const float* __restrict__ cls, int N, int C, int D, int k,
                int64_t* __restrict__ idx_out, double* __restrict__ dist_out) {
     extern __shared__ double smd[];
-    double* dist = smd;                                               // [kRows][C]
-    double* nrm_e = dist + (size_t)kRows * C;                         // [kRows]
-    float* s_e = reinterpret_cast<float*>(nrm_e + kRows);             // [kRows][D]
-    float* s_c = s_e + (size_t)kRows * D;                             // [128][kKC+1]
-    const int i0 = blockIdx.x * kRows;
+    double* dist = smd;                                               // [R][C]
+    double* nrm_e = dist + (size_t)R * C;                         // [R]
+    float* s_e = reinterpret_cast<float*>(nrm_e + R);             // [R][D]
+    float* s_c = s_e + (size_t)R * D;                             // [128][kKC+1]
+    const int i0 = blockIdx.x * R;
     const int tid = threadIdx.x;
-    for (int i = tid; i < kRows * D; i += 128) {
+    for (int i = tid; i < R * D; i += 128) {
         const int r = i / D, kk = i - r * D;
         s_e[i] = (i0 + r < N) ? emb[(long long)(i0 + r) * D + kk] : 0.f;
     }
     __syncthreads();
     const int Deven = D & ~1;
-    if (tid < kRows) {  // scipy _row_norms, same even/odd order as the dot products
+    if (tid < R) {  // scipy _row_norms, same even/odd order as the dot products
         double s0 = 0.0, s1 = 0.0;
         for (int kk = 0; kk < Deven; kk += 2) {
             const double v0 = (double)s_e[tid * D + kk], v1 = (double)s_e[tid * D + kk + 1];
@@ -202,10 +202,10 @@ nearest_kernel(const float* __restrict__ emb, const float* __restrict__ cls, int
     __syncthreads();
     for (int j0 = 0; j0 < C; j0 += 128) {
         const int j = j0 + tid;
-        double acc0[kRows], acc1[kRows];  // even-k / odd-k accumulators
+        double acc0[R], acc1[R];  // even-k / odd-k accumulators
         double cc0 = 0.0, cc1 = 0.0;      // squared norm of this thread's class row, same order
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) acc0[r] = acc1[r] = 0.0;
+        for (int r = 0; r < R; ++r) acc0[r] = acc1[r] = 0.0;
         for (int k0 = 0; k0 < D; k0 += kKC) {
             __syncthreads();
             for (int i = tid; i < 128 * kKC; i += 128) {
@@ -219,7 +219,7 @@ nearest_kernel(const float* __restrict__ emb, const float* __restrict__ cls, int
                 cc0 = __dadd_rn(cc0, __dmul_rn(c0, c0));
                 cc1 = __dadd_rn(cc1, __dmul_rn(c1, c1));
 #pragma unroll
-                for (int r = 0; r < kRows; ++r) {
+                for (int r = 0; r < R; ++r) {
                     acc0[r] = __dadd_rn(acc0[r], __dmul_rn((double)s_e[r * D + k0 + kk], c0));
                     acc1[r] = __dadd_rn(acc1[r], __dmul_rn((double)s_e[r * D + k0 + kk + 1], c1));
                 }
@@ -229,7 +229,7 @@ nearest_kernel(const float* __restrict__ emb, const float* __restrict__ cls, int
                 cc0 = __dadd_rn(__dadd_rn(cc0, cc1), __dmul_rn(ct, ct));
                 cc1 = 0.0;
 #pragma unroll
-                for (int r = 0; r < kRows; ++r) {
+                for (int r = 0; r < R; ++r) {
                     acc0[r] = __dadd_rn(__dadd_rn(acc0[r], acc1[r]), __dmul_rn((double)s_e[r * D + Deven], ct));
                     acc1[r] = 0.0;
                 }
@@ -239,7 +239,7 @@ nearest_kernel(const float* __restrict__ emb, const float* __restrict__ cls, int
             // when D is odd the tail step above already folded the lanes (and zeroed the odd one: x + 0.0 == x)
             const double nv = sqrt(__dadd_rn(cc0, cc1));
 #pragma unroll
-            for (int r = 0; r < kRows; ++r) {
+            for (int r = 0; r < R; ++r) {
                 double cosine = __dadd_rn(acc0[r], acc1[r]) / (nrm_e[r] * nv);
                 if (fabs(cosine) > 1.0) cosine = copysign(1.0, cosine);
                 dist[(size_t)r * C + j] = 1.0 - cosine;
@@ -249,7 +249,7 @@ nearest_kernel(const float* __restrict__ emb, const float* __restrict__ cls, int
     __syncthreads();
     // selection: warp w handles rows w, w+4
     const int warp = tid >> 5, lane = tid & 31;
-    for (int r = warp; r < kRows; r += 4) {
+    for (int r = warp; r < R; r += 4) {
         if (i0 + r >= N) continue;
         double* dr = dist + (size_t)r * C;
         for (int sel = 0; sel < k; ++sel) {
@@ -362,15 +362,22 @@ extern "C" int zsv_nearest_class(const float* emb, const float* cls, int N, int 
     if (N < 0 || C < 1 || D < 1 || k < 1 || k > 8 || k > C) return fail(ZSV_ERR_BAD_ARG, "nearest_class: bad sizes");
     if (N == 0) return ZSV_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = sizeof(double) * ((size_t)kRows * C + kRows) + sizeof(float) * ((size_t)kRows * D + 128 * (kKC + 1));
+    // few rows (train-time batch, main.py:183): one row per block so the grid still covers the SMs;
+    // many rows (evaluation, main.py:321): 8 rows per block amortise the class-table traffic
+    const int R = N <= 2048 ? 1 : 8;
+    const size_t smem = sizeof(double) * ((size_t)R * C + R) + sizeof(float) * ((size_t)R * D + 128 * (kKC + 1));
     if (smem > 200 * 1024)
         return fail(ZSV_ERR_UNSUPPORTED, "nearest_class: class table too large for shared memory (%zu bytes)", smem);
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(nearest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(nearest_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(nearest_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_done = true;
     }
-    nearest_kernel<<<ceil_div(N, kRows), 128, smem, st>>>(emb, cls, N, C, D, k, idx_out, dist_out);
+    if (R == 1)
+        nearest_kernel<1><<<N, 128, smem, st>>>(emb, cls, N, C, D, k, idx_out, dist_out);
+    else
+        nearest_kernel<8><<<ceil_div(N, 8), 128, smem, st>>>(emb, cls, N, C, D, k, idx_out, dist_out);
     ZSV_LAUNCH_CHECK("nearest_kernel");
     return ZSV_OK;
 }

@@ -166,9 +166,10 @@ def bn_finalize(ps, pq, channels: int, count: int, gamma, beta, running_mean, ru
     cp = cpad(channels)
     out = torch.empty((4, cp), dtype=torch.float32, device=ps.device)
     scale, shift, mean, invstd = out[0], out[1], out[2], out[3]
+    ws = workspace(lib.zsv_bn_finalize_workspace(channels), ps.device, "bn_finalize")
     check(lib.zsv_bn_finalize(ptr(ps), ptr(pq), ps.shape[0], channels, count, ptr(gamma), ptr(beta),
                               ptr(running_mean), ptr(running_var), momentum, eps, ptr(scale), ptr(shift), ptr(mean),
-                              ptr(invstd), _stream()), "zsv_bn_finalize")
+                              ptr(invstd), ptr(ws), ws.numel(), _stream()), "zsv_bn_finalize")
     return scale, shift, mean, invstd
 
 
