@@ -92,11 +92,18 @@ int zsv_conv3d_dgrad(const zsv_conv_desc* d, const void* dy, const void* w_dgrad
                      void* stream);
 
 /* Weight gradient (autograd of conv3d w.r.t. its weight).  dw is fp32 in the state_dict layout
- * [Cout][Cin][kt][kh][kw]; db (optional, fp32 [Cout]) receives the bias gradient.  The workspace holds
- * split-K partial tiles; zsv_conv3d_wgrad_workspace gives the required size. */
+ * [Cout][Cin][kt][kh][kw].  The workspace holds split-K partial tiles; zsv_conv3d_wgrad_workspace gives the
+ * required size. */
 size_t zsv_conv3d_wgrad_workspace(const zsv_conv_desc* d);
-int zsv_conv3d_wgrad(const zsv_conv_desc* d, const void* x, const void* dy, float* dw, float* db, void* workspace,
+int zsv_conv3d_wgrad(const zsv_conv_desc* d, const void* x, const void* dy, float* dw, void* workspace,
                      size_t workspace_bytes, void* stream);
+/* Bias gradient of a convolution (C3D, network.py:102-117): db[c] = sum over the rows of dy (bf16 [rows][cpad(C)]),
+ * deterministic two-stage reduction through the workspace. */
+size_t zsv_bias_grad_workspace(int C);
+int zsv_bias_grad(const void* dy, float* db, long long rows, int C, void* workspace, size_t workspace_bytes,
+                  void* stream);
+/* ReLU backward on channels-last bf16: dz = g * [out > 0] (C3D conv+bias+ReLU, network.py:147-162). */
+int zsv_relu_bwd(const void* g, const void* out, void* dz, long long rows, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Layout conversion at the PyTorch boundary.
@@ -156,6 +163,16 @@ int zsv_head_fwd(const void* feat, int B, int P, int C, const float* w1, const f
 int zsv_head_bwd(const float* demb, const float* emb, const float* onorm, const float* pooled, const float* hidden,
                  int B, int P, int C, const float* w1, int Hd, const float* w2, int E, float eps, float* dw1,
                  float* db1, float* dw2, float* db2, void* dfeat, float* scratch, void* stream);
+/* Plain fp32 Linear (C3D fc6 / regressor, network.py:120,132,166,178): out = act(x W^T + b), weight-streaming.
+ * Backward: optional ReLU mask from the forward output `act` (needs scratch [B][J]); dx, dw, db optional. */
+int zsv_linear_fwd(const float* x, const float* w, const float* bias, float* out, int B, int K, int J, int relu,
+                   void* stream);
+int zsv_linear_bwd(const float* dy, const float* x, const float* w, const float* act, int B, int K, int J, float* dx,
+                   float* dw, float* db, float* scratch, void* stream);
+/* F.normalize(dim=-1) forward / backward (network.py:179, network.py:596). */
+int zsv_l2norm_fwd(const float* o, float* emb, float* onorm, int B, int E, float eps, void* stream);
+int zsv_l2norm_bwd(const float* demb, const float* emb, const float* onorm, float* dout, int B, int E, float eps,
+                   void* stream);
 /* MSELoss(mean) forward + gradient (main.py:130,179): loss[0] = mean((emb-target)^2),
  * demb = 2*(emb-target)/(B*E) * grad_scale. */
 int zsv_mse_fwd_bwd(const float* emb, const float* target, int B, int E, float grad_scale, float* loss, float* demb,
@@ -174,8 +191,10 @@ int zsv_nearest_class(const float* emb, const float* cls, int N, int C, int D, i
  * ---------------------------------------------------------------------------------------------- */
 int zsv_maxpool3d_fwd(const void* x, void* y, int32_t* argmax, int N, int T, int H, int W, int C, int kt, int kh,
                       int kw, int pt, int ph, int pw, void* stream);
-int zsv_maxpool3d_bwd(const void* dy, const int32_t* argmax, void* dx, int N, int T, int H, int W, int C, int kt,
-                      int kh, int kw, int pt, int ph, int pw, void* stream);
+/* relu_mask_src (optional): the pooled tensor itself (a ReLU output); positions where it is <= 0 get no gradient,
+ * which fuses the ReLU backward of network.py:147-162 into the pooling backward. */
+int zsv_maxpool3d_bwd(const void* dy, const int32_t* argmax, const void* relu_mask_src, void* dx, int N, int T, int H,
+                      int W, int C, int kt, int kh, int kw, int pt, int ph, int pw, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,76 @@
+"""CPU (gloo, world_size 2): the data-parallel gradient synchronisation used at N > 1 GPUs.
+
+GradSync is backend-agnostic (SUM + scale), so the bucketing / ordering / averaging logic is exercised here with
+gloo; on the GPU box the same code runs over NCCL (bench.py --gpus N)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, bucket_bytes, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from zeroshotvideoclassification_b200 import dist as zdist
+    r, lr, w = zdist.init_from_env("gloo")
+    assert (r, w) == (rank, world)
+    sync = zdist.GradSync(bucket_bytes=bucket_bytes)
+    g = torch.Generator().manual_seed(1234)            # same "true" gradients on both ranks ...
+    shapes = {"layer4.w": (64, 32, 3), "layer4.gamma": (64,), "layer3.w": (16, 8, 3, 3), "stem.w": (5, 3, 7)}
+    base = {k: torch.randn(*s, generator=g) for k, s in shapes.items()}
+    local = {k: v * (rank + 1) for k, v in base.items()}          # ... scaled per rank: mean factor is 1.5
+    # submitted in backward order, in two groups like two residual blocks
+    sync.submit({k: local[k].clone() for k in ("layer4.w", "layer4.gamma")})
+    sync.submit({k: local[k].clone() for k in ("layer3.w", "stem.w")})
+    out = sync.finish()
+    ok = set(out) == set(shapes)
+    for k in shapes:
+        ok &= bool(torch.allclose(out[k], base[k] * 1.5, rtol=1e-6, atol=1e-7)) and out[k].shape == base[k].shape
+    # head-gradient helper and parameter broadcast
+    lin = torch.nn.Linear(4, 3)
+    with torch.no_grad():
+        for p in lin.parameters():
+            p.fill_(float(rank + 1))
+    zdist.broadcast_module(lin, 0)
+    ok &= all(bool((p == 1.0).all()) for p in lin.parameters())
+    for p in lin.parameters():
+        p.grad = torch.full_like(p, float(rank))
+    zdist.sync_head_grads(list(lin.parameters()))
+    ok &= all(bool(torch.allclose(p.grad, torch.full_like(p, 0.5))) for p in lin.parameters())
+    q.put((rank, ok, sync.bytes_reduced))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bucket_bytes", [1, 1 << 20])
+def test_gradsync_world2_gloo(bucket_bytes):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, bucket_bytes, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res), res
+    nbytes = 4 * (64 * 32 * 3 + 64 + 16 * 8 * 3 * 3 + 5 * 3 * 7)
+    assert all(b == nbytes for _, _, b in res)
+
+
+def test_gradsync_single_process_is_a_noop():
+    from zeroshotvideoclassification_b200 import dist as zdist
+    sync = zdist.GradSync()
+    sync.submit({"w": torch.ones(3)})
+    assert sync.finish() == {} and sync.world == 1

@@ -12,7 +12,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libzsv_b200.so"
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 X_NDHWC = 0
 X_WFOLD = 1
 
@@ -47,7 +47,14 @@ SIGNATURES = {
     "zsv_conv3d_fprop": (_I, [_DP, _P, _P, _P, _P, _P, _P, _I, _P]),
     "zsv_conv3d_dgrad": (_I, [_DP, _P, _P, _P, _P, _P]),
     "zsv_conv3d_wgrad_workspace": (_SZ, [_DP]),
-    "zsv_conv3d_wgrad": (_I, [_DP, _P, _P, _P, _P, _P, _SZ, _P]),
+    "zsv_conv3d_wgrad": (_I, [_DP, _P, _P, _P, _P, _SZ, _P]),
+    "zsv_bias_grad_workspace": (_SZ, [_I]),
+    "zsv_bias_grad": (_I, [_P, _P, _LL, _I, _P, _SZ, _P]),
+    "zsv_relu_bwd": (_I, [_P, _P, _P, _LL, _I, _P]),
+    "zsv_linear_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "zsv_linear_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "zsv_l2norm_fwd": (_I, [_P, _P, _P, _I, _I, _F, _P]),
+    "zsv_l2norm_bwd": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "zsv_repack_input": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "zsv_ndhwc_to_ncdhw": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "zsv_ncdhw_to_ndhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
@@ -62,7 +69,7 @@ SIGNATURES = {
     "zsv_mse_fwd_bwd": (_I, [_P, _P, _I, _I, _F, _P, _P, _P]),
     "zsv_nearest_class": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "zsv_maxpool3d_fwd": (_I, [_P, _P, _P] + [_I] * 11 + [_P]),
-    "zsv_maxpool3d_bwd": (_I, [_P, _P, _P] + [_I] * 11 + [_P]),
+    "zsv_maxpool3d_bwd": (_I, [_P, _P, _P, _P] + [_I] * 11 + [_P]),
 }
 
 _lib = None

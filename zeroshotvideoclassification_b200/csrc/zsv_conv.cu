@@ -556,22 +556,6 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
     }
 }
 
-// db[co] = sum over rows of dy[row][co]  (C3D bias gradient)
-__global__ void bias_grad_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db, long long rows,
-                                 int pitch, int Cout) {
-    const int co = blockIdx.x;
-    float acc = 0.f;
-    for (long long r = threadIdx.x; r < rows; r += blockDim.x) acc += __bfloat162float(dy[r * pitch + co]);
-    __shared__ float sh[256];
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0 && co < Cout) db[co] = sh[0];
-}
-
 // ------------------------------------------------------------------------------------------------
 // host-side geometry
 // ------------------------------------------------------------------------------------------------
@@ -1059,8 +1043,8 @@ extern "C" size_t zsv_conv3d_wgrad_workspace(const zsv_conv_desc* d) {
     return p.ws_bytes;
 }
 
-extern "C" int zsv_conv3d_wgrad(const zsv_conv_desc* d, const void* x, const void* dy, float* dw, float* db,
-                                void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int zsv_conv3d_wgrad(const zsv_conv_desc* d, const void* x, const void* dy, float* dw, void* workspace,
+                                size_t workspace_bytes, void* stream) {
     Shape s;
     int rc = check_desc(d, &s);
     if (rc) return rc;
@@ -1115,10 +1099,5 @@ extern "C" int zsv_conv3d_wgrad(const zsv_conv_desc* d, const void* x, const voi
     wgrad_finalize_kernel<<<blocks, 256, 0, st>>>((const float*)workspace, dw, p.splits, s.ftaps, p.ci_pitch,
                                                   p.co_pitch, d->Cin, d->Cout, s.wfold ? d->kw : 0, s.ntaps);
     ZSV_LAUNCH_CHECK("wgrad_finalize_kernel");
-    if (db) {
-        const long long rows = (long long)d->N * s.To * s.Ho * s.Wo;
-        bias_grad_kernel<<<d->Cout, 256, 0, st>>>((const __nv_bfloat16*)dy, db, rows, s.coutp, d->Cout);
-        ZSV_LAUNCH_CHECK("bias_grad_kernel");
-    }
     return ZSV_OK;
 }

@@ -477,8 +477,67 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
     }
 }
 
+// dz = g * [out > 0]  (C3D: ReLU after conv+bias, network.py:147-162)
+__global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ out,
+                                __nv_bfloat16* __restrict__ dz, long long nvec) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+         i += (long long)gridDim.x * blockDim.x) {
+        float a[8], b[8];
+        unpack8(*reinterpret_cast<const uint4*>(g + i * 8), a);
+        unpack8(*reinterpret_cast<const uint4*>(out + i * 8), b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = b[j] > 0.f ? a[j] : 0.f;
+        *reinterpret_cast<uint4*>(dz + i * 8) = pack8(a);
+    }
+}
+
+// per-block column sums of a bf16 [rows][Cp] tensor -> partial[block][Cp] (fp32); block = V groups x R row lanes
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int Cp, int R, float* __restrict__ partial) {
+    extern __shared__ float sm[];  // [R][Cp]
+    const int V = Cp >> 3;
+    const int vl = threadIdx.x % V, rl = threadIdx.x / V;
+    const int c0 = vl << 3;
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.f;
+    if (rl < R) {
+        for (long long r = (long long)blockIdx.x * R + rl; r < rows; r += (long long)gridDim.x * R) {
+            float f[8];
+            unpack8(*reinterpret_cast<const uint4*>(x + r * Cp + c0), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] += f[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sm[rl * Cp + c0 + j] = a[j];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < R; ++r) s += sm[r * Cp + c];
+        partial[(long long)blockIdx.x * Cp + c] = s;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+colsum_final_kernel(const float* __restrict__ partial, int nblocks, int C, int Cp, float* __restrict__ out) {
+    __shared__ double sh[32][33];
+    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    double s = 0.0;
+    if (c < Cp)
+        for (int b = rl; b < nblocks; b += 32) s += (double)partial[(long long)b * Cp + c];
+    sh[rl][cl] = s;
+    __syncthreads();
+    if (rl == 0 && c < C) {
+        s = 0.0;
+        for (int r = 0; r < 32; ++r) s += sh[r][cl];
+        out[c] = (float)s;
+    }
+}
+
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const int32_t* __restrict__ argmax,
-                                   __nv_bfloat16* __restrict__ dx, int N, int T, int H, int W, int Cp, int kt, int kh,
+                                   const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ dx, int N, int T, int H, int W, int Cp, int kt, int kh,
                                    int kw, int pt, int ph, int pw, int To, int Ho, int Wo) {
     // one thread per input vector: windows do not overlap (kernel == stride), so each input element belongs to
     // exactly one window and the gradient is a gather
@@ -507,6 +566,12 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const i
             const int32_t* am = argmax + oi * 8;
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = am[j] == code ? f[j] : 0.f;
+            if (mask_src != nullptr) {  // fused ReLU backward of the tensor that was pooled
+                float m[8];
+                unpack8(*reinterpret_cast<const uint4*>(mask_src + i * 8), m);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = m[j] > 0.f ? o[j] : 0.f;
+            }
         }
         *reinterpret_cast<uint4*>(dx + i * 8) = pack8(o);
     }
@@ -696,14 +761,44 @@ extern "C" int zsv_maxpool3d_fwd(const void* x, void* y, int32_t* argmax, int N,
     return ZSV_OK;
 }
 
-extern "C" int zsv_maxpool3d_bwd(const void* dy, const int32_t* argmax, void* dx, int N, int T, int H, int W, int C,
-                                 int kt, int kh, int kw, int pt, int ph, int pw, void* stream) {
+extern "C" int zsv_relu_bwd(const void* g, const void* out, void* dz, long long rows, int C, void* stream) {
+    if (!g || !out || !dz) return fail(ZSV_ERR_BAD_ARG, "relu_bwd: null pointer");
+    const long long nvec = rows * (cpad(C) >> 3);
+    relu_bwd_kernel<<<ew_blocks(nvec, 1024), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)g, (const __nv_bfloat16*)out, (__nv_bfloat16*)dz, nvec);
+    ZSV_LAUNCH_CHECK("relu_bwd_kernel");
+    return ZSV_OK;
+}
+
+extern "C" size_t zsv_bias_grad_workspace(int C) { return (size_t)kBwdMaxBlocks * cpad(C) * sizeof(float); }
+
+extern "C" int zsv_bias_grad(const void* dy, float* db, long long rows, int C, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+    if (!dy || !db || !workspace) return fail(ZSV_ERR_BAD_ARG, "bias_grad: null pointer");
+    if (workspace_bytes < zsv_bias_grad_workspace(C)) return fail(ZSV_ERR_WORKSPACE, "bias_grad: workspace too small");
+    const int Cp = cpad(C), V = Cp >> 3;
+    if (V > 256) return fail(ZSV_ERR_UNSUPPORTED, "bias_grad: channel pitch too large");
+    const int R = std::max(1, 256 / V);
+    const int nblocks = (int)std::max<long long>(1, std::min<long long>(kBwdMaxBlocks, ceil_div_ll(rows, (long long)R * 4)));
+    cudaStream_t st = (cudaStream_t)stream;
+    colsum_partial_kernel<<<nblocks, 256, (size_t)R * Cp * sizeof(float), st>>>((const __nv_bfloat16*)dy, rows, Cp, R,
+                                                                                 (float*)workspace);
+    ZSV_LAUNCH_CHECK("colsum_partial_kernel");
+    colsum_final_kernel<<<ceil_div(Cp, 32), 1024, 0, st>>>((const float*)workspace, nblocks, C, Cp, db);
+    ZSV_LAUNCH_CHECK("colsum_final_kernel");
+    return ZSV_OK;
+}
+
+extern "C" int zsv_maxpool3d_bwd(const void* dy, const int32_t* argmax, const void* relu_mask_src, void* dx, int N,
+                                 int T, int H, int W, int C, int kt, int kh, int kw, int pt, int ph, int pw,
+                                 void* stream) {
     if (!dy || !dx || !argmax) return fail(ZSV_ERR_BAD_ARG, "maxpool_bwd: null pointer");
     const int Cp = cpad(C);
     const int To = (T + 2 * pt - kt) / kt + 1, Ho = (H + 2 * ph - kh) / kh + 1, Wo = (W + 2 * pw - kw) / kw + 1;
     const long long total = (long long)N * T * H * W * (Cp >> 3);
     maxpool_bwd_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)dy, argmax, (__nv_bfloat16*)dx, N, T, H, W, Cp, kt, kh, kw, pt, ph, pw, To, Ho, Wo);
+        (const __nv_bfloat16*)dy, argmax, (const __nv_bfloat16*)relu_mask_src, (__nv_bfloat16*)dx, N, T, H, W, Cp, kt, kh,
+        kw, pt, ph, pw, To, Ho, Wo);
     ZSV_LAUNCH_CHECK("maxpool_bwd_kernel");
     return ZSV_OK;
 }

@@ -112,16 +112,36 @@ __global__ void linear_wgrad_kernel(const float* __restrict__ dy, const float* _
     if (k == 0 && db) db[j] = accb;
 }
 
-// dx[b][k] = (sum_j dy[b][j] * w[j][k]) * (mask ? [act[b][k] > 0] : 1)
+// dx[b][k] = (sum_j dy[b][j] * w[j][k]) * (mask ? [act[b][k] > 0] : 1); one thread per k, 8 batch rows per pass,
+// so the weight matrix is streamed ceil(B/8) times with coalesced rows
 __global__ void linear_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                     const float* __restrict__ act, float* __restrict__ dx, int B, int K, int J) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    for (int b0 = 0; b0 < B; b0 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int j = 0; j < J; ++j) {
+            const float wv = w[(long long)j * K + k];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (b0 + i < B) acc[i] = fmaf(dy[(long long)(b0 + i) * J + j], wv, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (b0 + i < B) {
+                const long long o = (long long)(b0 + i) * K + k;
+                dx[o] = (act && !(act[o] > 0.f)) ? 0.f : acc[i];
+            }
+        }
+    }
+}
+
+__global__ void relu_mask_kernel(const float* __restrict__ dy, const float* __restrict__ act, float* __restrict__ out,
+                                 long long n) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= (long long)B * K) return;
-    const int b = static_cast<int>(i / K), k = static_cast<int>(i - (long long)b * K);
-    float acc = 0.f;
-    for (int j = 0; j < J; ++j) acc = fmaf(dy[(long long)b * J + j], w[(long long)j * K + k], acc);
-    if (act && !(act[i] > 0.f)) acc = 0.f;
-    dx[i] = acc;
+    if (i < n) out[i] = act[i] > 0.f ? dy[i] : 0.f;
 }
 
 // dfeat[b][p][c] = dpooled[b][c] / P
@@ -331,20 +351,67 @@ extern "C" int zsv_head_bwd(const float* demb, const float* emb, const float* on
         linear_wgrad_kernel<<<ceil_div(E * Hd, 256), 256, 0, st>>>(dout, hidden, dw2, db2, B, Hd, E);
         ZSV_LAUNCH_CHECK("linear_wgrad_kernel(2)");
     }
-    linear_dgrad_kernel<<<ceil_div(B * Hd, 128), 128, 0, st>>>(dout, w2, hidden, dh, B, Hd, E);
+    linear_dgrad_kernel<<<ceil_div(Hd, 128), 128, 0, st>>>(dout, w2, hidden, dh, B, Hd, E);
     ZSV_LAUNCH_CHECK("linear_dgrad_kernel(2)");
     if (dw1) {
         linear_wgrad_kernel<<<ceil_div(Hd * C, 256), 256, 0, st>>>(dh, pooled, dw1, db1, B, C, Hd);
         ZSV_LAUNCH_CHECK("linear_wgrad_kernel(1)");
     }
     if (dfeat) {
-        linear_dgrad_kernel<<<ceil_div(B * C, 128), 128, 0, st>>>(dh, w1, nullptr, dpooled, B, C, Hd);
+        linear_dgrad_kernel<<<ceil_div(C, 128), 128, 0, st>>>(dh, w1, nullptr, dpooled, B, C, Hd);
         ZSV_LAUNCH_CHECK("linear_dgrad_kernel(1)");
         const long long total = (long long)B * P * cpad(C);
         pool_bwd_kernel<<<(int)std::min<long long>(ceil_div_ll(total, 256), 148 * 8), 256, 0, st>>>(
             dpooled, (__nv_bfloat16*)dfeat, B, P, C, cpad(C));
         ZSV_LAUNCH_CHECK("pool_bwd_kernel");
     }
+    return ZSV_OK;
+}
+
+extern "C" int zsv_linear_fwd(const float* x, const float* w, const float* bias, float* out, int B, int K, int J,
+                              int relu, void* stream) {
+    if (!x || !w || !out) return fail(ZSV_ERR_BAD_ARG, "linear_fwd: null pointer");
+    if (B < 1 || K < 1 || J < 1) return fail(ZSV_ERR_BAD_ARG, "linear_fwd: bad sizes");
+    linear_fwd_kernel<<<ceil_div(J * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, w, bias, out, B, K, J, relu);
+    ZSV_LAUNCH_CHECK("linear_fwd_kernel");
+    return ZSV_OK;
+}
+
+extern "C" int zsv_linear_bwd(const float* dy, const float* x, const float* w, const float* act, int B, int K, int J,
+                              float* dx, float* dw, float* db, float* scratch, void* stream) {
+    if (!dy || !x || !w) return fail(ZSV_ERR_BAD_ARG, "linear_bwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* g = dy;
+    if (act) {  // ReLU on the forward output: mask dy first (scratch [B][J])
+        if (!scratch) return fail(ZSV_ERR_BAD_ARG, "linear_bwd: relu mask needs scratch");
+        const long long n = (long long)B * J;
+        relu_mask_kernel<<<(int)ceil_div_ll(n, 256), 256, 0, st>>>(dy, act, scratch, n);
+        ZSV_LAUNCH_CHECK("relu_mask_kernel");
+        g = scratch;
+    }
+    if (dw) {
+        linear_wgrad_kernel<<<(int)ceil_div_ll((long long)J * K, 256), 256, 0, st>>>(g, x, dw, db, B, K, J);
+        ZSV_LAUNCH_CHECK("linear_wgrad_kernel");
+    }
+    if (dx) {
+        linear_dgrad_kernel<<<ceil_div(K, 128), 128, 0, st>>>(g, w, nullptr, dx, B, K, J);
+        ZSV_LAUNCH_CHECK("linear_dgrad_kernel");
+    }
+    return ZSV_OK;
+}
+
+extern "C" int zsv_l2norm_fwd(const float* o, float* emb, float* onorm, int B, int E, float eps, void* stream) {
+    if (!o || !emb || !onorm) return fail(ZSV_ERR_BAD_ARG, "l2norm_fwd: null pointer");
+    normalize_fwd_kernel<<<ceil_div(B * 32, 128), 128, 0, (cudaStream_t)stream>>>(o, emb, onorm, B, E, eps);
+    ZSV_LAUNCH_CHECK("normalize_fwd_kernel");
+    return ZSV_OK;
+}
+
+extern "C" int zsv_l2norm_bwd(const float* demb, const float* emb, const float* onorm, float* dout, int B, int E,
+                              float eps, void* stream) {
+    if (!demb || !emb || !onorm || !dout) return fail(ZSV_ERR_BAD_ARG, "l2norm_bwd: null pointer");
+    normalize_bwd_kernel<<<ceil_div(B * 32, 128), 128, 0, (cudaStream_t)stream>>>(demb, emb, onorm, dout, B, E, eps);
+    ZSV_LAUNCH_CHECK("normalize_bwd_kernel");
     return ZSV_OK;
 }
 

@@ -120,11 +120,11 @@ class Conv3d:
 
     def wgrad(self, x, dy, want_bias: bool = False):
         dw = torch.empty((self.cout, self.cin, *self.kernel), dtype=torch.float32, device=dy.device)
-        db = torch.empty(self.cout, dtype=torch.float32, device=dy.device) if want_bias else None
         ws = workspace(self.wgrad_ws, dy.device, "wgrad")
         with _Timed("wgrad", self):
-            check(self.lib.zsv_conv3d_wgrad(C.byref(self.desc), ptr(x), ptr(dy), ptr(dw), ptr(db), ptr(ws),
-                                            ws.numel(), _stream()), "zsv_conv3d_wgrad")
+            check(self.lib.zsv_conv3d_wgrad(C.byref(self.desc), ptr(x), ptr(dy), ptr(dw), ptr(ws), ws.numel(),
+                                            _stream()), "zsv_conv3d_wgrad")
+        db = bias_grad(dy, self.cout) if want_bias else None
         return dw, db
 
 
@@ -291,12 +291,69 @@ def maxpool3d_fwd(x, channels: int, kernel, padding=(0, 0, 0)):
     return y, am
 
 
-def maxpool3d_bwd(dy, argmax, in_shape, channels: int, kernel, padding=(0, 0, 0)):
+def maxpool3d_bwd(dy, argmax, in_shape, channels: int, kernel, padding=(0, 0, 0), relu_mask_src=None):
     lib = _lib.load()
     N, T, H, W, cp = in_shape
     kt, kh, kw = kernel
     pt, ph, pw = padding
     dx = torch.empty(in_shape, dtype=torch.bfloat16, device=dy.device)
-    check(lib.zsv_maxpool3d_bwd(ptr(dy), ptr(argmax), ptr(dx), N, T, H, W, channels, kt, kh, kw, pt, ph, pw,
-                                _stream()), "zsv_maxpool3d_bwd")
+    check(lib.zsv_maxpool3d_bwd(ptr(dy), ptr(argmax), ptr(relu_mask_src), ptr(dx), N, T, H, W, channels, kt, kh, kw,
+                                pt, ph, pw, _stream()), "zsv_maxpool3d_bwd")
     return dx
+
+
+def relu_bwd(g, out, channels: int):
+    lib = _lib.load()
+    dz = torch.empty_like(g)
+    rows = g.numel() // g.shape[-1]
+    check(lib.zsv_relu_bwd(ptr(g), ptr(out), ptr(dz), rows, channels, _stream()), "zsv_relu_bwd")
+    return dz
+
+
+def bias_grad(dy, channels: int):
+    lib = _lib.load()
+    rows = dy.numel() // dy.shape[-1]
+    db = torch.empty(channels, dtype=torch.float32, device=dy.device)
+    ws = workspace(lib.zsv_bias_grad_workspace(channels), dy.device, "bias_grad")
+    check(lib.zsv_bias_grad(ptr(dy), ptr(db), rows, channels, ptr(ws), ws.numel(), _stream()), "zsv_bias_grad")
+    return db
+
+
+def linear_fwd(x, w, b, relu: bool):
+    lib = _lib.load()
+    B, K = x.shape
+    J = w.shape[0]
+    out = torch.empty((B, J), dtype=torch.float32, device=x.device)
+    check(lib.zsv_linear_fwd(ptr(x), ptr(w), ptr(b), ptr(out), B, K, J, int(relu), _stream()), "zsv_linear_fwd")
+    return out
+
+
+def linear_bwd(dy, x, w, act=None, need_dx=True, need_dw=True):
+    lib = _lib.load()
+    B, K = x.shape
+    J = w.shape[0]
+    dev = x.device
+    dx = torch.empty((B, K), dtype=torch.float32, device=dev) if need_dx else None
+    dw = torch.empty((J, K), dtype=torch.float32, device=dev) if need_dw else None
+    db = torch.empty((J,), dtype=torch.float32, device=dev) if need_dw else None
+    scratch = torch.empty((B, J), dtype=torch.float32, device=dev) if act is not None else None
+    check(lib.zsv_linear_bwd(ptr(dy), ptr(x), ptr(w), ptr(act), B, K, J, ptr(dx), ptr(dw), ptr(db), ptr(scratch),
+                             _stream()), "zsv_linear_bwd")
+    return dx, dw, db
+
+
+def l2norm_fwd(o, eps: float = 1e-12):
+    lib = _lib.load()
+    B, E = o.shape
+    emb = torch.empty_like(o)
+    onorm = torch.empty((B,), dtype=torch.float32, device=o.device)
+    check(lib.zsv_l2norm_fwd(ptr(o), ptr(emb), ptr(onorm), B, E, eps, _stream()), "zsv_l2norm_fwd")
+    return emb, onorm
+
+
+def l2norm_bwd(demb, emb, onorm, eps: float = 1e-12):
+    lib = _lib.load()
+    B, E = emb.shape
+    dout = torch.empty_like(emb)
+    check(lib.zsv_l2norm_bwd(ptr(demb), ptr(emb), ptr(onorm), ptr(dout), B, E, eps, _stream()), "zsv_l2norm_bwd")
+    return dout
