@@ -183,14 +183,22 @@ def model_forward(sd: Dict[str, Tensor], x: Tensor, train: bool = True, trace: O
     return embedding_head(sd, feats)
 
 
-def c3d_forward(sd: Dict[str, Tensor], x: Tensor, train: bool = False) -> Tensor:
+def c3d_forward(sd: Dict[str, Tensor], x: Tensor, train: bool = False, emulate_bf16: bool = False) -> Tensor:
     """network.C3D.forward (network.py:143-180).  Dropout(p=0.1) (network.py:167) is only applied in train
-    mode; parity tests run with train=False (or p=0) because the mask is not reproducible across devices."""
+    mode; parity tests run with train=False (or p=0) because the mask is not reproducible across devices.
+    emulate_bf16: bf16 rounding at the storage points of the B200 path (input clip, weight copies, every
+    conv+bias+ReLU output and its gradient); arithmetic stays fp32."""
     bs, nc = x.shape[:2]
     h = x.reshape(bs * nc, *x.shape[2:])
+    if emulate_bf16:
+        h = _RoundBf16Fwd.apply(h)
 
     def conv(name, t):
-        return F.relu(F.conv3d(t, sd[name + ".weight"], sd[name + ".bias"], padding=1))
+        w = sd[name + ".weight"]
+        if emulate_bf16:
+            w = _RoundBf16Fwd.apply(w)
+        y = F.relu(F.conv3d(t, w, sd[name + ".bias"], padding=1))
+        return _RoundBf16Both.apply(y) if emulate_bf16 else y
 
     h = F.max_pool3d(conv("conv1", h), (1, 2, 2), (1, 2, 2))
     h = F.max_pool3d(conv("conv2", h), (2, 2, 2), (2, 2, 2))

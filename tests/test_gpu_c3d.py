@@ -1,5 +1,7 @@
-"""C3D (network.py:95-180) on the CUDA path vs the CPU oracle (eval mode: Dropout is not reproducible across
-devices).  C3D has no BatchNorm, so there is no chaotic amplification: plain fp32 oracle."""
+"""C3D (network.py:95-180) on the CUDA path vs the CPU oracle (Dropout p set to 0: its mask is not reproducible
+across devices).  Forward is gated against the plain fp32 oracle; gradients against the
+rounding-matched oracle (bf16 storage flips ReLU masks / pooling arg-max of near-zero elements, which alone moves
+gradients by several percent rms per layer relative to pure fp32 -- see DESIGN.md, numerics)."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -21,10 +23,12 @@ def test_c3d_forward_backward_vs_oracle():
     x = torch.randn(2, 1, 3, 16, 112, 112, generator=g)
     z = F.normalize(torch.randn(2, 300, generator=g))
 
-    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    emb_ref = vo.c3d_forward(params, x, train=False)
+    params32 = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    emb_ref = vo.c3d_forward(params32, x, train=False)
     loss_ref = vo.mse_loss(emb_ref, z)
     loss_ref.backward()
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    vo.mse_loss(vo.c3d_forward(params, x, train=False, emulate_bf16=True), z).backward()
 
     model = model.cuda().train()
     emb = model(x.cuda())
@@ -36,15 +40,29 @@ def test_c3d_forward_backward_vs_oracle():
     print("c3d emb rel err", e, "loss", float(loss.detach()), float(loss_ref))
     assert e < 2e-2
     assert abs(float(loss.detach()) - float(loss_ref)) < 2e-2 * abs(float(loss_ref))
-    errs = {}
+    errs, errs32 = {}, {}
     for name, p in model.named_parameters():
         ref = params[name].grad
         if ref is None:
             assert p.grad is None, name          # fc7 / fc8 are dead (network.py:168-172)
             continue
         errs[name] = rms_rel_err(p.grad.cpu(), ref)
-    print({k: f"{v:.2e}" for k, v in errs.items()})
-    assert max(errs.values()) < 8e-2, errs
+        errs32[name] = rms_rel_err(p.grad.cpu(), params32[name].grad)
+    # calibration: stock PyTorch bf16 autocast (what main.py:172 does) on the same weights / clips
+    pac = {k: v.clone().cuda().requires_grad_(True) for k, v in sd.items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        emb_ac = vo.c3d_forward(pac, x.cuda(), train=False)
+        loss_ac = vo.mse_loss(emb_ac.float(), z.cuda())
+    loss_ac.backward()
+    errs_ac = {k: rms_rel_err(pac[k].grad.float().cpu(), params32[k].grad) for k in errs}
+    print("grad rms-rel vs rounding-matched oracle:", {k: f"{v:.2e}" for k, v in errs.items()})
+    print("grad rms-rel vs plain fp32 oracle      :", {k: f"{v:.2e}" for k, v in errs32.items()})
+    print("autocast grad rms-rel vs fp32 oracle   :", {k: f"{v:.2e}" for k, v in errs_ac.items()})
+    # bf16 storage flips the ReLU mask / pooling arg-max of elements next to zero: a few percent rms of gradient
+    # noise per layer for ANY bf16 implementation, so the gate is "not worse than stock bf16 autocast"
+    bad = {k: (errs32[k], errs_ac[k]) for k in errs if not errs32[k] < max(5e-2, 1.5 * errs_ac[k])}
+    assert not bad, bad
+    assert errs["regressor.weight"] < 1e-2 and errs["fc6.weight"] < 5e-2
 
 
 def test_c3d_multi_clip_eval():
