@@ -18,6 +18,7 @@
 //     (channels contiguous), split over CTAs along the position axis with deterministic partials.
 #include <algorithm>
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -105,6 +106,7 @@ struct IgemmArgs {
     int32_t relu;
     int32_t tmem_cols;
     int32_t part_pitch;
+    int32_t m_tiles, n_tiles;
     long long o_sN, o_sT, o_sH, o_sW;  // element strides of the output tensor
     __nv_bfloat16* out;
     const __nv_bfloat16* addend;
@@ -165,13 +167,23 @@ __device__ __forceinline__ void warp_colsum16(float (&v)[16], int lane) {
 
 // ------------------------------------------------------------------------------------------------
 // K-major implicit GEMM: out[pos][co] = sum_{tap, ci} act[pos + tap][ci] * w[tap][co][ci]
-// grid = (M tiles, N tiles); 192 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner,
-// warps 2..5 epilogue (TMEM lane quadrant = warp % 4).
+//
+// Persistent, warp-specialised: grid = min(#tiles, #SMs), one CTA per SM looping over (M tile, N tile) pairs.
+//   warp 0      : TMA producer -- runs ahead across tile boundaries through a `stages`-deep smem ring
+//   warp 1      : MMA issuer + TMEM owner -- two accumulator buffers in TMEM, so the epilogue of tile i overlaps
+//                 the mainloop of tile i+1
+//   warps 2..9  : epilogue (TMEM lane quadrant = warp % 4; the two warps of a quadrant split the 16-column
+//                 chunks even/odd): tcgen05.ld -> bias/addend/ReLU -> bf16 -> 16-byte channels-last stores, plus
+//                 per-tile BatchNorm partial sums
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(192, 2)
+constexpr int kIgemmThreads = 320;
+constexpr int kEpiWarps = 8;
+
+__global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
-                    const __grid_constant__ CUtensorMap mapB, const __grid_constant__ IgemmArgs P) {
+                    const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
+                    const __grid_constant__ IgemmArgs P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -183,18 +195,25 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     const uint32_t stageB = static_cast<uint32_t>(P.bn_tile) * 128u;
     const uint32_t stageBytes = kPanelBytes + stageB;
     const uint32_t ringBytes = stages * stageBytes;
-    const uint32_t barFull = base + ringBytes;
+    const int out_panels = (P.bn_tile + 63) >> 6;                    // 64-channel output panels of one tile
+    const uint32_t stagingOff = ringBytes;                           // [out_panels][128 rows][128 B], SWIZZLE_128B
+    const uint32_t stagingBytes = out_panels * kPanelBytes;
+    const uint32_t barOff = stagingOff + stagingBytes;
+    const uint32_t barFull = base + barOff;
     const uint32_t barEmpty = barFull + 8u * stages;
-    const uint32_t barTmem = barEmpty + 8u * stages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ringBytes + 16u * stages + 8u);
-    float* stat = reinterpret_cast<float*>(smem + ringBytes + 16u * stages + 16u);  // [2][4][bn_tile]
+    const uint32_t barTmemFull = barEmpty + 8u * stages;   // [2]
+    const uint32_t barTmemEmpty = barTmemFull + 16u;       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + barOff + 16u * stages + 32u);
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(barFull + 8u * s, 1);
             mbar_init(barEmpty + 8u * s, 1);
         }
-        mbar_init(barTmem, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(barTmemFull + 8u * b, 1);
+            mbar_init(barTmemEmpty + 8u * b, kEpiWarps);
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), P.tmem_cols);
@@ -202,63 +221,75 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t acc_stride = static_cast<uint32_t>(P.tmem_cols) >> 1;
 
-    // tile coordinates
-    int m = blockIdx.x;
-    const int iw = m % P.tw;
-    m /= P.tw;
-    const int ih = m % P.th;
-    m /= P.th;
-    const int it = m % P.tt;
-    const int in_ = m / P.tt;
-    const int w0 = iw * P.bw, h0 = ih * P.bh, t0 = it * P.bt, n0 = in_ * P.bn;
-    const int n_tile = blockIdx.y;
     const int rows = P.bw * P.bh * P.bt * P.bn;
     const int kchunks = (P.kdim + 63) >> 6;
     const int num_kb = P.ntaps * kchunks;
+    const int num_tiles = P.m_tiles * P.n_tiles;
 
     if (warp == 0) {
         if (lane == 0) {
             const CUtensorMap* maps[kMaxMaps] = {&mapA0, &mapA1, &mapA2, &mapA3};
             const uint32_t tx = static_cast<uint32_t>(rows) * 128u + stageB;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % stages;
-                const uint32_t ph = (kb / stages) & 1;
-                mbar_wait(barEmpty + 8u * s, ph ^ 1u);
-                const int tp = kb / kchunks;
-                const int c0 = (kb - tp * kchunks) << 6;
-                const Tap tap = P.taps[tp];
-                const uint32_t full = barFull + 8u * s;
-                const uint32_t sa = base + s * stageBytes;
-                mbar_expect_tx(full, tx);
-                tma_load_5d(sa, maps[tap.map], full, c0, w0 + tap.dw, h0 + tap.dh, t0 + tap.dt, n0);
-                tma_load_3d(sa + kPanelBytes, &mapB, full, c0, n_tile * P.bn_tile, tap.btap);
+            uint32_t it = 0;  // global k-block counter: ring position and phase continue across tiles
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int m = tile / P.n_tiles;
+                const int n_tile = tile - m * P.n_tiles;
+                const int iw = m % P.tw;
+                m /= P.tw;
+                const int ih = m % P.th;
+                m /= P.th;
+                const int itt = m % P.tt;
+                const int in_ = m / P.tt;
+                const int w0 = iw * P.bw, h0 = ih * P.bh, t0 = itt * P.bt, n0 = in_ * P.bn;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % stages;
+                    const uint32_t ph = (it / stages) & 1u;
+                    mbar_wait(barEmpty + 8u * s, ph ^ 1u);
+                    const int tp = kb / kchunks;
+                    const int c0 = (kb - tp * kchunks) << 6;
+                    const Tap tap = P.taps[tp];
+                    const uint32_t full = barFull + 8u * s;
+                    const uint32_t sa = base + s * stageBytes;
+                    mbar_expect_tx(full, tx);
+                    tma_load_5d(sa, maps[tap.map], full, c0, w0 + tap.dw, h0 + tap.dh, t0 + tap.dt, n0);
+                    tma_load_3d(sa + kPanelBytes, &mapB, full, c0, n_tile * P.bn_tile, tap.btap);
+                }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_bf16(128, P.bn_tile, 0, 0);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % stages;
-                const uint32_t ph = (kb / stages) & 1;
-                mbar_wait(barFull + 8u * s, ph);
+            uint32_t it = 0;
+            int local = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+                const uint32_t buf = local & 1;
+                mbar_wait(barTmemEmpty + 8u * buf, ((local >> 1) & 1u) ^ 1u);   // epilogue drained this buffer
                 tc_fence_after();
-                const int tp = kb / kchunks;
-                const int c0 = (kb - tp * kchunks) << 6;
-                const int ksteps = min(4, (P.kdim - c0 + 15) >> 4);
-                const uint32_t sa = base + s * stageBytes;
-                const uint64_t da = umma_smem_desc(sa, 16, 1024);
-                const uint64_t db = umma_smem_desc(sa + kPanelBytes, 16, 1024);
-                for (int k = 0; k < ksteps; ++k)
-                    umma_bf16(tmem_base, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
-                umma_commit(barEmpty + 8u * s);
+                const uint32_t tacc = tmem_base + buf * acc_stride;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % stages;
+                    const uint32_t ph = (it / stages) & 1u;
+                    mbar_wait(barFull + 8u * s, ph);
+                    tc_fence_after();
+                    const int tp = kb / kchunks;
+                    const int c0 = (kb - tp * kchunks) << 6;
+                    const int ksteps = min(4, (P.kdim - c0 + 15) >> 4);
+                    const uint32_t sa = base + s * stageBytes;
+                    const uint64_t da = umma_smem_desc(sa, 16, 1024);
+                    const uint64_t db = umma_smem_desc(sa + kPanelBytes, 16, 1024);
+                    for (int k = 0; k < ksteps; ++k) umma_bf16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
+                    umma_commit(barEmpty + 8u * s);
+                }
+                umma_commit(barTmemFull + 8u * buf);
             }
-            umma_commit(barTmem);
         }
         __syncwarp();
     } else {
-        const int q = warp & 3;
+        const int q = warp & 3;               // TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;     // which of the two warps of the quadrant (even / odd column chunks)
         const int row = q * 32 + lane;
         int r = row;
         const int w = r % P.bw;
@@ -267,92 +298,122 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         r /= P.bh;
         const int t = r % P.bt;
         const int n = r / P.bt;
-        const bool valid = row < rows && (w0 + w) < P.OW && (h0 + h) < P.OH && (t0 + t) < P.OT && (n0 + n) < P.ON;
-        const long long off = (long long)(n0 + n) * P.o_sN + (long long)(t0 + t) * P.o_sT +
-                              (long long)(h0 + h) * P.o_sH + (long long)(w0 + w) * P.o_sW;
         const bool do_stats = P.part_sum != nullptr;
-        mbar_wait(barTmem, 0);
-        tc_fence_after();
-        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        for (int c = 0; c < P.bn_tile; c += 16) {
-            uint32_t v[16];
-            tmem_ld16(trow + c, v);
-            tmem_ld_wait();
-            const int col = n_tile * P.bn_tile + c;
-            float f[16];
+        const int et = threadIdx.x - 64;      // 0..255 within the epilogue group
+        uint8_t* staging = smem + stagingOff;
+        const uint32_t staging_u32 = base + stagingOff;
+        const uint32_t srow = static_cast<uint32_t>(row) * 128u;
+        const uint32_t sxor = static_cast<uint32_t>(row & 7);
+        int local = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+            int m = tile / P.n_tiles;
+            const int n_tile = tile - m * P.n_tiles;
+            const int m_tile = m;
+            const int iw = m % P.tw;
+            m /= P.tw;
+            const int ih = m % P.th;
+            m /= P.th;
+            const int itt = m % P.tt;
+            const int in_ = m / P.tt;
+            const int w0 = iw * P.bw, h0 = ih * P.bh, t0 = itt * P.bt, n0 = in_ * P.bn;
+            const bool valid =
+                row < rows && (w0 + w) < P.OW && (h0 + h) < P.OH && (t0 + t) < P.OT && (n0 + n) < P.ON;
+            const long long off = (long long)(n0 + n) * P.o_sN + (long long)(t0 + t) * P.o_sT +
+                                  (long long)(h0 + h) * P.o_sH + (long long)(w0 + w) * P.o_sW;
+            const uint32_t buf = local & 1;
+            mbar_wait(barTmemFull + 8u * buf, (local >> 1) & 1u);
+            tc_fence_after();
+            // staging buffer free again: the thread that issued the previous tile's TMA store has waited for the
+            // bulk group to finish reading it, and every thread has finished its statistics pass over it
+            if (et == 0) tma_store_wait_read();
+            named_bar_sync(1, kEpiWarps * 32);
+            const uint32_t trow = tmem_base + buf * acc_stride + (static_cast<uint32_t>(q * 32) << 16);
+            for (int c = half * 16; c < P.bn_tile; c += 32) {
+                uint32_t v[16];
+                tmem_ld16(trow + c, v);
+                tmem_ld_wait();
+                const int col = n_tile * P.bn_tile + c;
+                float f[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-            if (P.bias != nullptr) {
+                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                if (P.bias != nullptr) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (col + j < P.nbias) f[j] += __ldg(P.bias + col + j);
-            }
-            if (P.addend != nullptr && valid) {
+                    for (int j = 0; j < 16; ++j)
+                        if (col + j < P.nbias) f[j] += __ldg(P.bias + col + j);
+                }
+                if (P.addend != nullptr && valid) {
 #pragma unroll
-                for (int hlf = 0; hlf < 2; ++hlf) {
-                    if (col + 8 * hlf < P.ncols) {
-                        const uint4 a = *reinterpret_cast<const uint4*>(P.addend + off + col + 8 * hlf);
-                        const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+                    for (int hlf = 0; hlf < 2; ++hlf) {
+                        if (col + 8 * hlf < P.ncols) {
+                            const uint4 a = *reinterpret_cast<const uint4*>(P.addend + off + col + 8 * hlf);
+                            const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            f[8 * hlf + 2 * j] += bf16_lo(aw[j]);
-                            f[8 * hlf + 2 * j + 1] += bf16_hi(aw[j]);
+                            for (int j = 0; j < 4; ++j) {
+                                f[8 * hlf + 2 * j] += bf16_lo(aw[j]);
+                                f[8 * hlf + 2 * j + 1] += bf16_hi(aw[j]);
+                            }
                         }
                     }
                 }
-            }
-            if (P.relu) {
+                if (P.relu) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-            }
-            uint32_t pk[8];
+                    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                }
+                uint32_t pk[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-            if (valid) {
-                if (col < P.ncols)
-                    *reinterpret_cast<uint4*>(P.out + off + col) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                if (col + 8 < P.ncols)
-                    *reinterpret_cast<uint4*>(P.out + off + col + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                for (int j = 0; j < 8; ++j) pk[j] = valid ? pack_bf16x2(f[2 * j], f[2 * j + 1]) : 0u;
+                // SWIZZLE_128B staging: 16-byte chunk index XOR (row & 7) inside the 64-channel panel
+                uint8_t* prow = staging + static_cast<uint32_t>(c >> 6) * kPanelBytes + srow;
+                const uint32_t ch = static_cast<uint32_t>(c & 63) >> 3;   // first of the two 16-byte chunks
+                *reinterpret_cast<uint4*>(prow + ((ch ^ sxor) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(prow + (((ch + 1) ^ sxor) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+            // accumulator buffer fully read: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(barTmemEmpty + 8u * buf);
+            fence_proxy_async_smem();                 // generic-proxy smem writes -> visible to the TMA store
+            named_bar_sync(2, kEpiWarps * 32);
+            if (et == 0) {
+                for (int p = 0; p < out_panels; ++p) {
+                    const int ccol = n_tile * P.bn_tile + 64 * p;
+                    if (ccol < P.ncols) tma_store_5d(&mapOut, staging_u32 + p * kPanelBytes, ccol, w0, h0, t0, n0);
+                }
+                tma_store_commit();
             }
             if (do_stats) {
-                float s1[16], s2[16];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float lo = valid ? bf16_lo(pk[j]) : 0.f;
-                    const float hi = valid ? bf16_hi(pk[j]) : 0.f;
-                    s1[2 * j] = lo;
-                    s1[2 * j + 1] = hi;
-                    s2[2 * j] = lo * lo;
-                    s2[2 * j + 1] = hi * hi;
-                }
-                warp_colsum16(s1, lane);
-                warp_colsum16(s2, lane);
-                if ((lane & 1) == 0) {
-                    const int cj = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
-                                   ((lane >> 1) & 1);
-                    stat[(0 * 4 + q) * P.bn_tile + c + cj] = s1[0];
-                    stat[(1 * 4 + q) * P.bn_tile + c + cj] = s2[0];
-                }
-            }
-        }
-        if (do_stats) {
-            named_bar_sync(1, 128);
-            const int et = threadIdx.x - 64;
-            for (int i = et; i < P.bn_tile; i += 128) {
-                const int col = n_tile * P.bn_tile + i;
-                if (col < P.ncols) {
-                    const float a = ((stat[(0 * 4 + 0) * P.bn_tile + i] + stat[(0 * 4 + 1) * P.bn_tile + i]) +
-                                     stat[(0 * 4 + 2) * P.bn_tile + i]) +
-                                    stat[(0 * 4 + 3) * P.bn_tile + i];
-                    const float b = ((stat[(1 * 4 + 0) * P.bn_tile + i] + stat[(1 * 4 + 1) * P.bn_tile + i]) +
-                                     stat[(1 * 4 + 2) * P.bn_tile + i]) +
-                                    stat[(1 * 4 + 3) * P.bn_tile + i];
-                    P.part_sum[(long long)blockIdx.x * P.part_pitch + col] = a;
-                    P.part_sq[(long long)blockIdx.x * P.part_pitch + col] = b;
+                // column sums of the bf16 tile from shared memory: thread = (column pair, row half); invalid rows
+                // were staged as zeros.  Each half writes its own partial row (2*m_tile + half).
+                const int npairs = P.bn_tile >> 1;
+                for (int i = et; i < 2 * npairs; i += kEpiWarps * 32) {
+                    const int hh = i / npairs;
+                    const int cp2 = i - hh * npairs;            // column pair
+                    const int cc = cp2 * 2;
+                    const uint8_t* pb = staging + static_cast<uint32_t>(cc >> 6) * kPanelBytes;
+                    const uint32_t chunk = static_cast<uint32_t>(cc & 63) >> 3;
+                    const uint32_t inner = static_cast<uint32_t>(cc & 7) * 2u;
+                    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+                    const int r0 = hh * 64;
+#pragma unroll 8
+                    for (int rr = r0; rr < r0 + 64; ++rr) {
+                        const uint32_t v2 = *reinterpret_cast<const uint32_t*>(
+                            pb + rr * 128 + ((chunk ^ static_cast<uint32_t>(rr & 7)) << 4) + inner);
+                        const float lo = bf16_lo(v2), hi = bf16_hi(v2);
+                        s1a += lo;
+                        s1b += hi;
+                        s2a = fmaf(lo, lo, s2a);
+                        s2b = fmaf(hi, hi, s2b);
+                    }
+                    const int col = n_tile * P.bn_tile + cc;
+                    if (col < P.ncols) {   // ncols is even
+                        const long long o = (long long)(2 * m_tile + hh) * P.part_pitch + col;
+                        *reinterpret_cast<float2*>(P.part_sum + o) = make_float2(s1a, s1b);
+                        *reinterpret_cast<float2*>(P.part_sq + o) = make_float2(s2a, s2b);
+                    }
                 }
             }
         }
-        tc_fence_before();
+        if (et == 0) tma_store_wait_all();   // global writes of the last tile complete before the CTA exits
     }
     __syncthreads();
     if (warp == 1) {
@@ -613,6 +674,11 @@ struct Box {
 // Pick the box of positions (<= 128 rows) covering (OW,OH,OT,ON) with the least wasted MMA rows.
 // rows16: rows must be a multiple of 16 (wgrad consumes rows as the K dimension).
 Box choose_box(int OW, int OH, int OT, int ON, bool rows16) {
+    if (const char* e = getenv("ZSV_DEBUG_BOX")) {   // tuning aid: force the position box "bw,bh,bt,bn"
+        Box b{1, 1, 1, 1};
+        if (sscanf(e, "%d,%d,%d,%d", &b.bw, &b.bh, &b.bt, &b.bn) == 4 && b.rows() <= 128 && (!rows16 || b.rows() % 16 == 0))
+            return b;
+    }
     Box best{1, 1, 1, 1};
     double best_score = -1.0;
     const double total = (double)OW * OH * OT * ON;
@@ -648,10 +714,12 @@ void choose_ntile(int cols, long long m_tiles, int* bn_tile, int* n_tiles) {
     int best_bn = std::min(cols16, 256), best_n = ceil_div(cols16, std::min(cols16, 256));
     for (int nt = ceil_div(cols16, 256); nt <= ceil_div(cols16, 256) + 6 && nt <= ceil_div(cols16, 16); ++nt) {
         int bn = ((ceil_div(cols16, nt) + 15) & ~15);
+        if (nt > 1) bn = (bn + 63) & ~63;   // the output is stored in 64-channel panels: tile origins stay panel-aligned
         if (bn > 256) continue;
+        if (nt > 1 && (long long)bn * (nt - 1) >= cols16) continue;   // last tile would be empty
         if (bn < 64 && cols16 >= 64) continue;
         const long long ctas = m_tiles * nt;
-        const long long slots = 2LL * sms;
+        const long long slots = sms;
         const long long waves = ceil_div_ll(ctas, slots);
         // per-CTA cost ~ A-tile handling (fixed) + MMA/B/epilogue work proportional to bn
         const double cost = (double)waves * (bn + 48.0);
@@ -787,19 +855,17 @@ int build_fwd_taps(const zsv_conv_desc* d, const Shape& s, const void* x, const 
 }
 
 int igemm_smem_bytes(int bn_tile, int stages) {
-    return 1024 + stages * (kPanelBytes + bn_tile * 128) + 16 * stages + 16 + 8 * bn_tile * 4 + 64;
+    return 1024 + stages * (kPanelBytes + bn_tile * 128) + ((bn_tile + 63) / 64) * kPanelBytes + 16 * stages + 48 + 64;
 }
 
-int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, IgemmArgs& a, long long m_tiles, int n_tiles,
-                 cudaStream_t stream) {
-    // stages: aim for two CTAs per SM (<= ~110 KB each), at least 2 and at most 6 stages
-    int stages = 6;
-    while (stages > 2 && igemm_smem_bytes(a.bn_tile, stages) > 112 * 1024) --stages;
-    const int kchunks = (a.kdim + 63) / 64;
-    stages = std::max(2, std::min(stages, a.ntaps * kchunks));
-    if (a.ntaps * kchunks == 1) stages = 1;
+int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtensorMap& mapOut, IgemmArgs& a,
+                 long long m_tiles, int n_tiles, cudaStream_t stream) {
+    // one persistent CTA per SM owns (almost) all shared memory: as many ring stages as fit, at most 8
+    int stages = 8;
+    while (stages > 2 && igemm_smem_bytes(a.bn_tile, stages) > 226 * 1024) --stages;
     a.stages = stages;
-    a.tmem_cols = pow2_cols(a.bn_tile);
+    a.tmem_cols = 2 * pow2_cols(a.bn_tile);   // two accumulator buffers
+    if (a.tmem_cols > 512) return fail(ZSV_ERR_UNSUPPORTED, "igemm: N tile %d too wide for two TMEM buffers", a.bn_tile);
     const int smem = igemm_smem_bytes(a.bn_tile, stages);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
@@ -808,9 +874,12 @@ int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, IgemmArgs& a,
     });
     if (attr_err != cudaSuccess)
         return fail(ZSV_ERR_CUDA, "cudaFuncSetAttribute(igemm) failed: %s", cudaGetErrorString(attr_err));
-    if (m_tiles > 0x7fffffffLL) return fail(ZSV_ERR_UNSUPPORTED, "too many M tiles");
-    dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, 1);
-    igemm_kmajor_kernel<<<grid, 192, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], mapB, a);
+    if (m_tiles * n_tiles > 0x7fffffffLL) return fail(ZSV_ERR_UNSUPPORTED, "too many tiles");
+    a.m_tiles = (int)m_tiles;
+    a.n_tiles = n_tiles;
+    const long long tiles = m_tiles * n_tiles;
+    const int grid = (int)std::min<long long>(tiles, sm_count());
+    igemm_kmajor_kernel<<<grid, kIgemmThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], mapB, mapOut, a);
     ZSV_LAUNCH_CHECK("igemm_kmajor_kernel");
     return ZSV_OK;
 }
@@ -863,7 +932,8 @@ extern "C" int zsv_conv3d_stat_rows(const zsv_conv_desc* d) {
     Shape s;
     if (check_desc(d, &s)) return -1;
     const Box b = choose_box(s.Wo, s.Ho, s.To, d->N, false);
-    return ceil_div(s.Wo, b.bw) * ceil_div(s.Ho, b.bh) * ceil_div(s.To, b.bt) * ceil_div(d->N, b.bn);
+    // two partial rows per M tile (one per 64-row half of the tile)
+    return 2 * ceil_div(s.Wo, b.bw) * ceil_div(s.Ho, b.bh) * ceil_div(s.To, b.bt) * ceil_div(d->N, b.bn);
 }
 
 extern "C" int zsv_conv3d_fprop(const zsv_conv_desc* d, const void* x, const void* w_fprop, void* y, float* part_sum,
@@ -910,7 +980,10 @@ extern "C" int zsv_conv3d_fprop(const zsv_conv_desc* d, const void* x, const voi
         rc = make_map(&mapB, w_fprop, 3, dims, strides, box);
         if (rc) return rc;
     }
-    return launch_igemm(maps, mapB, a, m_tiles, n_tiles, (cudaStream_t)stream);
+    CUtensorMap mapOut;
+    rc = make_plain_map(&mapOut, y, d->N, s.To, s.Ho, s.Wo, s.coutp, s.coutp, b);
+    if (rc) return rc;
+    return launch_igemm(maps, mapB, mapOut, a, m_tiles, n_tiles, (cudaStream_t)stream);
 }
 
 extern "C" int zsv_conv3d_dgrad(const zsv_conv_desc* d, const void* dy, const void* w_dgrad, void* dx,
@@ -994,7 +1067,17 @@ extern "C" int zsv_conv3d_dgrad(const zsv_conv_desc* d, const void* dy, const vo
                 uint32_t box[3] = {64, (uint32_t)a.bn_tile, 1};
                 rc = make_map(&mapB, w_dgrad, 3, dims, strides, box);
                 if (rc) return rc;
-                rc = launch_igemm(maps, mapB, a, m_tiles, n_tiles, st);
+                CUtensorMap mapOut;
+                {
+                    const uint64_t cB = (uint64_t)s.cinp * 2;
+                    uint64_t odims[5] = {(uint64_t)s.cinp, (uint64_t)QW, (uint64_t)QH, (uint64_t)QT, (uint64_t)d->N};
+                    uint64_t ostr[4] = {cB * d->sw, cB * d->W * d->sh, cB * d->W * d->H * d->st,
+                                        cB * d->W * d->H * d->T};
+                    uint32_t obox[5] = {64, (uint32_t)b.bw, (uint32_t)b.bh, (uint32_t)b.bt, (uint32_t)b.bn};
+                    rc = make_map(&mapOut, (const char*)dx + class_off * 2, 5, odims, ostr, obox);
+                    if (rc) return rc;
+                }
+                rc = launch_igemm(maps, mapB, mapOut, a, m_tiles, n_tiles, st);
                 if (rc) return rc;
             }
     return ZSV_OK;
