@@ -9,5 +9,6 @@ Public surface (mirrors the reference's own names):
 """
 from .video_models import MLP, Model, default_opt, get_network, r2plus1d_18  # noqa: F401
 from .accuracy import compute_accuracy, nearest_class  # noqa: F401
+from . import dist  # noqa: F401
 
 __all__ = ["get_network", "Model", "MLP", "r2plus1d_18", "default_opt", "compute_accuracy", "nearest_class"]
