@@ -35,7 +35,8 @@ for spec in sys.argv[1:]:
     dy = torch.randn_like(y)
     flops = 2.0 * op.out_positions * cout * cin * k[0] * k[1] * k[2]
     t_f = bench(lambda: op.fprop(x, wf, stats=True))
+    t_fn = bench(lambda: op.fprop(x, wf, stats=False))
     t_d = bench(lambda: op.dgrad(dy, wd))
     t_w = bench(lambda: op.wgrad(x, dy))
-    print(f"{spec:48s} fprop {t_f:8.1f} us {flops / t_f / 1e6:7.1f} TF/s | dgrad {t_d:8.1f} us {flops / t_d / 1e6:7.1f} TF/s"
+    print(f"{spec:48s} fprop {t_f:8.1f} us {flops / t_f / 1e6:7.1f} TF/s (no stats {t_fn:8.1f} us) | dgrad {t_d:8.1f} us {flops / t_d / 1e6:7.1f} TF/s"
           f" | wgrad {t_w:8.1f} us {flops / t_w / 1e6:7.1f} TF/s")

@@ -50,7 +50,7 @@ EncodeTiledFn encode_fn() {
 
 // bf16 tensor map with SWIZZLE_128B; dims/box innermost first; strides in bytes for dims 1..rank-1.
 int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-             const uint32_t* box) {
+             const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(ZSV_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     cuuint64_t gd[5];
@@ -64,7 +64,7 @@ int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, c
     }
     for (int i = 0; i + 1 < rank; ++i) gs[i] = strides[i];
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         return fail(ZSV_ERR_CUDA,
@@ -132,39 +132,6 @@ struct WgradArgs {
     Tap taps[kMaxTaps];
 };
 
-// Transposing butterfly: every lane enters with 16 column values of its own row; on exit lane l holds in
-// v[0] the sum over all 32 lanes of column  8*b4 + 4*b3 + 2*b2 + b1  (bK = bit K of l).
-__device__ __forceinline__ void warp_colsum16(float (&v)[16], int lane) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const bool up = lane & 16;
-        const float send = up ? v[i] : v[i + 8];
-        const float keep = up ? v[i + 8] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const bool up = lane & 8;
-        const float send = up ? v[i] : v[i + 4];
-        const float keep = up ? v[i + 4] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const bool up = lane & 4;
-        const float send = up ? v[i] : v[i + 2];
-        const float keep = up ? v[i + 2] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    {
-        const bool up = lane & 2;
-        const float send = up ? v[0] : v[1];
-        const float keep = up ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-
 // ------------------------------------------------------------------------------------------------
 // K-major implicit GEMM: out[pos][co] = sum_{tap, ci} act[pos + tap][ci] * w[tap][co][ci]
 //
@@ -228,65 +195,84 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     const int num_kb = P.ntaps * kchunks;
     const int num_tiles = P.m_tiles * P.n_tiles;
 
+    // Producer and MMA warps run their loops with all 32 lanes (warp-uniform control flow and addresses); only the
+    // TMA / MMA / commit instructions themselves are issued by one elected lane.  The issuing thread is a scalar
+    // bottleneck (one MMA every N/2 cycles must be fed), so the loops avoid divisions, 64-bit descriptor arithmetic
+    // and dynamic parameter indexing.
     if (warp == 0) {
-        if (lane == 0) {
-            const CUtensorMap* maps[kMaxMaps] = {&mapA0, &mapA1, &mapA2, &mapA3};
-            const uint32_t tx = static_cast<uint32_t>(rows) * 128u + stageB;
-            uint32_t it = 0;  // global k-block counter: ring position and phase continue across tiles
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                int m = tile / P.n_tiles;
-                const int n_tile = tile - m * P.n_tiles;
-                const int iw = m % P.tw;
-                m /= P.tw;
-                const int ih = m % P.th;
-                m /= P.th;
-                const int itt = m % P.tt;
-                const int in_ = m / P.tt;
-                const int w0 = iw * P.bw, h0 = ih * P.bh, t0 = itt * P.bt, n0 = in_ * P.bn;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const uint32_t s = it % stages;
-                    const uint32_t ph = (it / stages) & 1u;
-                    mbar_wait(barEmpty + 8u * s, ph ^ 1u);
-                    const int tp = kb / kchunks;
-                    const int c0 = (kb - tp * kchunks) << 6;
-                    const Tap tap = P.taps[tp];
-                    const uint32_t full = barFull + 8u * s;
-                    const uint32_t sa = base + s * stageBytes;
-                    mbar_expect_tx(full, tx);
-                    tma_load_5d(sa, maps[tap.map], full, c0, w0 + tap.dw, h0 + tap.dh, t0 + tap.dt, n0);
-                    tma_load_3d(sa + kPanelBytes, &mapB, full, c0, n_tile * P.bn_tile, tap.btap);
+        const uint32_t leader = elect_one();
+        const uint32_t tx = static_cast<uint32_t>(rows) * 128u + stageB;
+        uint32_t stage = 0, phase = 0;   // ring position and phase continue across tiles
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int m = tile / P.n_tiles;
+            const int n_tile = tile - m * P.n_tiles;
+            const int iw = m % P.tw;
+            m /= P.tw;
+            const int ih = m % P.th;
+            m /= P.th;
+            const int itt = m % P.tt;
+            const int in_ = m / P.tt;
+            const int w0 = iw * P.bw, h0 = ih * P.bh, t0 = itt * P.bt, n0 = in_ * P.bn;
+            for (int tp = 0; tp < P.ntaps; ++tp) {
+                const Tap tap = P.taps[tp];
+                const CUtensorMap* mp = tap.map == 0 ? &mapA0 : (tap.map == 1 ? &mapA1 : (tap.map == 2 ? &mapA2 : &mapA3));
+                for (int c0 = 0; c0 < P.kdim; c0 += 64) {
+                    mbar_wait(barEmpty + 8u * stage, phase ^ 1u);
+                    if (leader) {
+                        const uint32_t full = barFull + 8u * stage;
+                        const uint32_t sa = base + stage * stageBytes;
+                        mbar_expect_tx(full, tx);
+                        tma_load_5d(sa, mp, full, c0, w0 + tap.dw, h0 + tap.dh, t0 + tap.dt, n0);
+                        tma_load_3d(sa + kPanelBytes, &mapB, full, c0, n_tile * P.bn_tile, tap.btap);
+                    }
+                    __syncwarp();
+                    if (++stage == static_cast<uint32_t>(stages)) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
                 }
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(128, P.bn_tile, 0, 0);
-            uint32_t it = 0;
-            int local = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-                const uint32_t buf = local & 1;
-                mbar_wait(barTmemEmpty + 8u * buf, ((local >> 1) & 1u) ^ 1u);   // epilogue drained this buffer
-                tc_fence_after();
-                const uint32_t tacc = tmem_base + buf * acc_stride;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const uint32_t s = it % stages;
-                    const uint32_t ph = (it / stages) & 1u;
-                    mbar_wait(barFull + 8u * s, ph);
+        const uint32_t leader = elect_one();
+        const uint32_t idesc = umma_idesc_bf16(128, P.bn_tile, 0, 0);
+        const uint32_t dhi = umma_desc_hi(1024, 2);
+        const int tail_steps = ((P.kdim - ((kchunks - 1) << 6)) + 15) >> 4;
+        uint32_t stage = 0, phase = 0;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+            const uint32_t buf = local & 1;
+            mbar_wait(barTmemEmpty + 8u * buf, ((local >> 1) & 1u) ^ 1u);   // epilogue drained this buffer
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + buf * acc_stride;
+            uint32_t acc = 0;
+            for (int tp = 0; tp < P.ntaps; ++tp) {
+                for (int c = 0; c < kchunks; ++c) {
+                    const int ksteps = (c + 1 < kchunks) ? 4 : tail_steps;
+                    mbar_wait(barFull + 8u * stage, phase);
                     tc_fence_after();
-                    const int tp = kb / kchunks;
-                    const int c0 = (kb - tp * kchunks) << 6;
-                    const int ksteps = min(4, (P.kdim - c0 + 15) >> 4);
-                    const uint32_t sa = base + s * stageBytes;
-                    const uint64_t da = umma_smem_desc(sa, 16, 1024);
-                    const uint64_t db = umma_smem_desc(sa + kPanelBytes, 16, 1024);
-                    for (int k = 0; k < ksteps; ++k) umma_bf16(tacc, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0);
-                    umma_commit(barEmpty + 8u * s);
+                    if (leader) {
+                        const uint32_t sa = base + stage * stageBytes;
+                        const uint32_t a_lo = umma_desc_lo(sa), b_lo = umma_desc_lo(sa + kPanelBytes);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (k < ksteps) {
+                                umma_bf16_lohi(tacc, a_lo + 2u * k, dhi, b_lo + 2u * k, dhi, idesc, acc);
+                                acc = 1;
+                            }
+                        }
+                        umma_commit(barEmpty + 8u * stage);
+                    }
+                    __syncwarp();
+                    if (++stage == static_cast<uint32_t>(stages)) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
                 }
-                umma_commit(barTmemFull + 8u * buf);
             }
+            if (leader) umma_commit(barTmemFull + 8u * buf);
+            __syncwarp();
         }
-        __syncwarp();
     } else {
         const int q = warp & 3;               // TMEM lane quadrant this warp may read
         const int half = (warp - 2) >> 2;     // which of the two warps of the quadrant (even / odd column chunks)
@@ -414,6 +400,321 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             }
         }
         if (et == 0) tma_store_wait_all();   // global writes of the last tile complete before the CTA exits
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, P.tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Halo implicit GEMM for stride-1 convolutions whose weight image fits in shared memory
+// (spatial 1x3x3 and temporal 3x1x1 of the stem / layer 1; fprop and dgrad).
+//
+// TMA ingest per SM (~40 B/clk) is what bounds the generic kernel: one load per tap brings ~34 MAC per byte.  Here
+//   * the weight tile of this CTA (all taps, all channel chunks) is loaded ONCE and stays resident, and
+//   * the activation box is ordered with the tap ("shift") dimension OUTERMOST in shared memory and carries a halo of
+//     S-1 extra slices, so the S taps along that dimension are the same staged tile read at descriptor offsets of
+//     whole swizzle atoms (inner_rows % 8 == 0); taps along W (spatial convs) are separate, W-shifted copies.
+// One staged (chunk, copy) tile therefore feeds S x ksteps MMAs: 177 MAC per ingested byte for the 64->144 conv.
+// Channel tails of 16 / 32 use SWIZZLE_32B / SWIZZLE_64B tiles so they cost 1/4 / 1/2 of a full chunk.
+// Same persistent warp-specialised structure and epilogue as igemm_kmajor_kernel; a CTA keeps one N tile.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxCopies = 8;
+
+struct HaloArgs {
+    int32_t b[4];        // box extents in smem row order: inner dims 0..2, then the shift dim (output extent)
+    int32_t tl[4];       // tile counts per box dim
+    int32_t O[4];        // output extents per box dim
+    long long os[4];     // output element strides per box dim (addend addressing)
+    int32_t S;           // taps along the shift dimension
+    int32_t ncopies;     // W-shifted copies per channel chunk
+    int32_t copy_off[kMaxCopies];   // coordinate offset along box dim 0 for each copy
+    int32_t shift_org;   // coordinate of the halo origin relative to the tile origin along the shift dim
+    int32_t tap0, tap_dcp, tap_dsh; // weight tap index for (copy cp, shift tap sh) = tap0 + cp*tap_dcp + sh*tap_dsh
+    int32_t kdim, nchunks, tail_box; // reduction channels, 64-wide chunks (incl. tail), box width of the tail chunk
+    int32_t ntaps;
+    int32_t ncols, nbias, bn_tile, n_step, n_tiles, m_tiles, stages, relu, tmem_cols, part_pitch;
+    uint32_t a_stage_bytes, b_main_bytes, b_tail_bytes, b_total_bytes;
+    const __nv_bfloat16* addend;
+    float* part_sum;
+    float* part_sq;
+    const float* bias;
+};
+
+__global__ void __launch_bounds__(kIgemmThreads, 1)
+igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAtail,
+                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBtail,
+                  const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ HaloArgs P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int stages = P.stages;
+    const uint32_t ringOff = P.b_total_bytes;
+    const uint32_t ringBytes = stages * P.a_stage_bytes;
+    const int out_panels = (P.bn_tile + 63) >> 6;
+    const uint32_t stagingOff = ringOff + ringBytes;
+    const uint32_t barOff = stagingOff + out_panels * kPanelBytes;
+    const uint32_t barFull = base + barOff;
+    const uint32_t barEmpty = barFull + 8u * stages;
+    const uint32_t barTmemFull = barEmpty + 8u * stages;
+    const uint32_t barTmemEmpty = barTmemFull + 16u;
+    const uint32_t barB = barTmemEmpty + 16u;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + barOff + 16u * stages + 40u);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(barFull + 8u * s, 1);
+            mbar_init(barEmpty + 8u * s, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(barTmemFull + 8u * i, 1);
+            mbar_init(barTmemEmpty + 8u * i, kEpiWarps);
+        }
+        mbar_init(barB, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), P.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t acc_stride = static_cast<uint32_t>(P.tmem_cols) >> 1;
+
+    const int inner_rows = P.b[0] * P.b[1] * P.b[2];
+    const int rows = inner_rows * P.b[3];
+    const int halo_rows = inner_rows * (P.b[3] + P.S - 1);
+    const int nmain = (P.tail_box == 64) ? P.nchunks : P.nchunks - 1;   // chunks that use the 128-byte-row maps
+    const uint32_t tail_row_bytes = static_cast<uint32_t>(P.tail_box) * 2u;
+    const uint32_t per_tap_bytes = nmain * P.b_main_bytes + (nmain < P.nchunks ? P.b_tail_bytes : 0u);
+    // this CTA's N tile is fixed (its weight tile is resident); M tiles are strided over the CTAs that share it
+    const int n_tile = blockIdx.x % P.n_tiles;
+    const int m_first = blockIdx.x / P.n_tiles;
+    const int m_stride = gridDim.x / P.n_tiles;
+    const int n_origin = n_tile * P.n_step;
+
+    if (warp == 0) {
+        const uint32_t leader = elect_one();
+        if (leader) {
+            // resident weights: [tap][chunk] tiles
+            uint32_t btx = 0;
+            for (int c = 0; c < P.nchunks; ++c) btx += static_cast<uint32_t>(P.bn_tile) * (c < nmain ? 128u : tail_row_bytes);
+            mbar_expect_tx(barB, btx * P.ntaps);
+            for (int tp = 0; tp < P.ntaps; ++tp)
+                for (int c = 0; c < P.nchunks; ++c) {
+                    const uint32_t dst = base + tp * per_tap_bytes + (c < nmain ? c * P.b_main_bytes : nmain * P.b_main_bytes);
+                    tma_load_3d(dst, c < nmain ? &mapB : &mapBtail, barB, c << 6, n_origin, tp);
+                }
+        }
+        __syncwarp();
+        uint32_t stage = 0, phase = 0;
+        for (int mt = m_first; mt < P.m_tiles; mt += m_stride) {
+            int m = mt;
+            const int o0 = (m % P.tl[0]) * P.b[0];
+            m /= P.tl[0];
+            const int o1 = (m % P.tl[1]) * P.b[1];
+            m /= P.tl[1];
+            const int o2 = (m % P.tl[2]) * P.b[2];
+            const int o3 = (m / P.tl[2]) * P.b[3];
+            for (int c = 0; c < P.nchunks; ++c) {
+                const bool main_chunk = c < nmain;
+                const uint32_t tx = static_cast<uint32_t>(halo_rows) * (main_chunk ? 128u : tail_row_bytes);
+                const CUtensorMap* mp = main_chunk ? &mapA : &mapAtail;
+                for (int cp = 0; cp < P.ncopies; ++cp) {
+                    mbar_wait(barEmpty + 8u * stage, phase ^ 1u);
+                    if (leader) {
+                        const uint32_t full = barFull + 8u * stage;
+                        mbar_expect_tx(full, tx);
+                        tma_load_5d(base + ringOff + stage * P.a_stage_bytes, mp, full, c << 6, o0 + P.copy_off[cp], o1, o2,
+                                    o3 + P.shift_org);
+                    }
+                    __syncwarp();
+                    if (++stage == static_cast<uint32_t>(stages)) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t leader = elect_one();
+        const uint32_t idesc = umma_idesc_bf16(128, P.bn_tile, 0, 0);
+        const uint32_t tail_layout = P.tail_box == 16 ? 6u : (P.tail_box == 32 ? 4u : 2u);
+        const uint32_t hi_main = umma_desc_hi(1024, 2);
+        const uint32_t hi_tail = umma_desc_hi(tail_row_bytes * 8u, tail_layout);
+        const int tail_steps = ((P.kdim - ((P.nchunks - 1) << 6)) + 15) >> 4;
+        const uint32_t tap_bytes16 = per_tap_bytes >> 4;   // descriptor start addresses count 16-byte units
+        mbar_wait(barB, 0);
+        tc_fence_after();
+        uint32_t stage = 0, phase = 0;
+        int local = 0;
+        for (int mt = m_first; mt < P.m_tiles; mt += m_stride, ++local) {
+            const uint32_t buf = local & 1;
+            mbar_wait(barTmemEmpty + 8u * buf, ((local >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + buf * acc_stride;
+            uint32_t acc = 0;   // 0 only for the very first MMA of the tile
+            for (int c = 0; c < P.nchunks; ++c) {
+                const bool main_chunk = c < nmain;
+                const uint32_t row_bytes = main_chunk ? 128u : tail_row_bytes;
+                const uint32_t dhi = main_chunk ? hi_main : hi_tail;
+                const int ksteps = (c + 1 < P.nchunks) ? 4 : tail_steps;
+                const uint32_t shift16 = (static_cast<uint32_t>(inner_rows) * row_bytes) >> 4;
+                const uint32_t b_chunk_lo = umma_desc_lo(base + (main_chunk ? c * P.b_main_bytes : nmain * P.b_main_bytes));
+                for (int cp = 0; cp < P.ncopies; ++cp) {
+                    mbar_wait(barFull + 8u * stage, phase);
+                    tc_fence_after();
+                    if (leader) {
+                        uint32_t a_lo = umma_desc_lo(base + ringOff + stage * P.a_stage_bytes);
+                        uint32_t b_lo = b_chunk_lo + static_cast<uint32_t>(P.tap0 + cp * P.tap_dcp) * tap_bytes16;
+                        const uint32_t b_step = static_cast<uint32_t>(P.tap_dsh) * tap_bytes16;   // may wrap (negative step)
+                        for (int sh = 0; sh < P.S; ++sh) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                if (k < ksteps) {
+                                    umma_bf16_lohi(tacc, a_lo + 2u * k, dhi, b_lo + 2u * k, dhi, idesc, acc);
+                                    acc = 1;
+                                }
+                            }
+                            a_lo += shift16;
+                            b_lo += b_step;
+                        }
+                        umma_commit(barEmpty + 8u * stage);
+                    }
+                    __syncwarp();
+                    if (++stage == static_cast<uint32_t>(stages)) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+            if (leader) umma_commit(barTmemFull + 8u * buf);
+            __syncwarp();
+        }
+    } else {
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        int r = row;
+        const int i0 = r % P.b[0];
+        r /= P.b[0];
+        const int i1 = r % P.b[1];
+        r /= P.b[1];
+        const int i2 = r % P.b[2];
+        const int i3 = r / P.b[2];
+        const bool do_stats = P.part_sum != nullptr;
+        const int et = threadIdx.x - 64;
+        uint8_t* staging = smem + stagingOff;
+        const uint32_t staging_u32 = base + stagingOff;
+        const uint32_t srow = static_cast<uint32_t>(row) * 128u;
+        const uint32_t sxor = static_cast<uint32_t>(row & 7);
+        // columns this tile owns: a non-last N tile only owns n_step of its bn_tile computed columns
+        const int width = (n_tile + 1 < P.n_tiles) ? P.n_step : P.bn_tile;
+        int local = 0;
+        for (int mt = m_first; mt < P.m_tiles; mt += m_stride, ++local) {
+            int m = mt;
+            const int o0 = (m % P.tl[0]) * P.b[0];
+            m /= P.tl[0];
+            const int o1 = (m % P.tl[1]) * P.b[1];
+            m /= P.tl[1];
+            const int o2 = (m % P.tl[2]) * P.b[2];
+            const int o3 = (m / P.tl[2]) * P.b[3];
+            const bool valid = row < rows && (o0 + i0) < P.O[0] && (o1 + i1) < P.O[1] && (o2 + i2) < P.O[2] &&
+                               (o3 + i3) < P.O[3];
+            const long long off = (long long)(o0 + i0) * P.os[0] + (long long)(o1 + i1) * P.os[1] +
+                                  (long long)(o2 + i2) * P.os[2] + (long long)(o3 + i3) * P.os[3];
+            const uint32_t buf = local & 1;
+            mbar_wait(barTmemFull + 8u * buf, (local >> 1) & 1u);
+            tc_fence_after();
+            if (et == 0) tma_store_wait_read();
+            named_bar_sync(1, kEpiWarps * 32);
+            const uint32_t trow = tmem_base + buf * acc_stride + (static_cast<uint32_t>(q * 32) << 16);
+            for (int c = half * 16; c < width; c += 32) {
+                uint32_t v[16];
+                tmem_ld16(trow + c, v);
+                tmem_ld_wait();
+                const int col = n_origin + c;
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                if (P.bias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (col + j < P.nbias) f[j] += __ldg(P.bias + col + j);
+                }
+                if (P.addend != nullptr && valid) {
+#pragma unroll
+                    for (int hlf = 0; hlf < 2; ++hlf) {
+                        if (col + 8 * hlf < P.ncols) {
+                            const uint4 a = *reinterpret_cast<const uint4*>(P.addend + off + col + 8 * hlf);
+                            const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                f[8 * hlf + 2 * j] += bf16_lo(aw[j]);
+                                f[8 * hlf + 2 * j + 1] += bf16_hi(aw[j]);
+                            }
+                        }
+                    }
+                }
+                if (P.relu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                }
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pk[j] = valid ? pack_bf16x2(f[2 * j], f[2 * j + 1]) : 0u;
+                uint8_t* prow = staging + static_cast<uint32_t>(c >> 6) * kPanelBytes + srow;
+                const uint32_t ch = static_cast<uint32_t>(c & 63) >> 3;
+                *reinterpret_cast<uint4*>(prow + ((ch ^ sxor) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(prow + (((ch + 1) ^ sxor) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(barTmemEmpty + 8u * buf);
+            fence_proxy_async_smem();
+            named_bar_sync(2, kEpiWarps * 32);
+            if (et == 0) {
+                for (int p = 0; p * 64 < width; ++p) {
+                    const int ccol = n_origin + 64 * p;
+                    if (ccol < P.ncols) tma_store_5d(&mapOut, staging_u32 + p * kPanelBytes, ccol, o0, o1, o2, o3);
+                }
+                tma_store_commit();
+            }
+            if (do_stats) {
+                const int npairs = width >> 1;
+                for (int i = et; i < 2 * npairs; i += kEpiWarps * 32) {
+                    const int hh = i / npairs;
+                    const int cc = (i - hh * npairs) * 2;
+                    const uint8_t* pb = staging + static_cast<uint32_t>(cc >> 6) * kPanelBytes;
+                    const uint32_t chunk = static_cast<uint32_t>(cc & 63) >> 3;
+                    const uint32_t inner = static_cast<uint32_t>(cc & 7) * 2u;
+                    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+                    const int r0 = hh * 64;
+#pragma unroll 8
+                    for (int rr = r0; rr < r0 + 64; ++rr) {
+                        const uint32_t v2 = *reinterpret_cast<const uint32_t*>(
+                            pb + rr * 128 + ((chunk ^ static_cast<uint32_t>(rr & 7)) << 4) + inner);
+                        const float lo = bf16_lo(v2), hi = bf16_hi(v2);
+                        s1a += lo;
+                        s1b += hi;
+                        s2a = fmaf(lo, lo, s2a);
+                        s2b = fmaf(hi, hi, s2b);
+                    }
+                    const int col = n_origin + cc;
+                    if (col < P.ncols) {
+                        const long long o = (long long)(2 * mt + hh) * P.part_pitch + col;
+                        *reinterpret_cast<float2*>(P.part_sum + o) = make_float2(s1a, s1b);
+                        *reinterpret_cast<float2*>(P.part_sq + o) = make_float2(s2a, s2b);
+                    }
+                }
+            }
+        }
+        if (et == 0) tma_store_wait_all();
     }
     __syncthreads();
     if (warp == 1) {
@@ -884,6 +1185,185 @@ int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtenso
     return ZSV_OK;
 }
 
+// ---- halo kernel planning -------------------------------------------------------------------------
+struct HaloPlan {
+    bool ok;
+    bool spatial;       // shift dim = H (taps along W are copies) ; otherwise shift dim = T
+    int b[4], tl[4], O[4];
+    int S, ncopies, stages, bn_tile, n_step, n_tiles, nchunks, tail_box;
+    long long m_tiles;
+    uint32_t a_stage_bytes, b_main_bytes, b_tail_bytes, b_total_bytes;
+    int smem;
+};
+
+inline uint32_t align1k(uint32_t v) { return (v + 1023u) & ~1023u; }
+
+// act extents (W,H,T,N) of the GEMM-M space (stride-1 conv: output extents == input extents), reduction channels
+// kdim, output columns `cols`, filter (kt,kh,kw).  Only spatial 1xkhxkw (kh==3) and temporal ktx1x1 (kt==3).
+HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int kh, int kw) {
+    HaloPlan p;
+    memset(&p, 0, sizeof(p));
+    if (getenv("ZSV_DEBUG_NO_HALO")) return p;
+    if (kt == 1 && kh == 3 && kw >= 1 && kw <= kMaxCopies) {
+        p.spatial = true;
+        p.S = kh;
+        p.ncopies = kw;
+    } else if (kt == 3 && kh == 1 && kw == 1) {
+        p.spatial = false;
+        p.S = kt;
+        p.ncopies = 1;
+    } else {
+        return p;
+    }
+    // box order: spatial (W, T, N | H), temporal (W, H, N | T)
+    const int E[4] = {W, p.spatial ? T : H, N, p.spatial ? H : T};
+    double best = -1;
+    for (int b0 = 1; b0 <= std::min(E[0], 128); ++b0)
+        for (int b1 = 1; b1 <= std::min(E[1], 128 / b0); ++b1)
+            for (int b2 = 1; b2 <= std::min(E[2], 128 / (b0 * b1)); ++b2) {
+                const int inner = b0 * b1 * b2;
+                if (inner % 8) continue;
+                for (int b3 = 1; b3 <= std::min(E[3], 128 / inner); ++b3) {
+                    if (b3 + p.S - 1 > 256) continue;
+                    const double tiles = (double)ceil_div(E[0], b0) * ceil_div(E[1], b1) * ceil_div(E[2], b2) *
+                                         ceil_div(E[3], b3);
+                    const double eff = ((double)E[0] * E[1] * E[2] * E[3]) / (tiles * 128.0);
+                    const double halo = (double)(b3 + p.S - 1) / b3;
+                    const double score = eff / (0.5 + 0.5 * halo) + 1e-6 * b0;   // MMA rows wasted vs bytes re-read
+                    if (score > best) {
+                        best = score;
+                        p.b[0] = b0, p.b[1] = b1, p.b[2] = b2, p.b[3] = b3;
+                    }
+                }
+            }
+    if (best < 0) return p;
+    for (int i = 0; i < 4; ++i) {
+        p.O[i] = E[i];
+        p.tl[i] = ceil_div(E[i], p.b[i]);
+    }
+    p.m_tiles = (long long)p.tl[0] * p.tl[1] * p.tl[2] * p.tl[3];
+    const int inner = p.b[0] * p.b[1] * p.b[2];
+    const int halo_rows = inner * (p.b[3] + p.S - 1);
+    p.a_stage_bytes = align1k((uint32_t)halo_rows * 128u);
+    p.nchunks = ceil_div(kdim, 64);
+    const int tail = kdim - 64 * (p.nchunks - 1);
+    p.tail_box = tail <= 16 ? 16 : (tail <= 32 ? 32 : 64);
+    const int nmain = p.tail_box == 64 ? p.nchunks : p.nchunks - 1;
+    const int ntaps = kt * kh * kw;
+    const int cols16 = (cols + 15) & ~15;
+    // N tiling: origins step by multiples of 64 (output panels), the last tile takes the remainder
+    for (int nt = 1; nt <= 4; ++nt) {
+        int n_step, bn;
+        if (nt == 1) {
+            n_step = bn = cols16;
+        } else {
+            n_step = ((cols16 / nt) / 64) * 64;
+            if (n_step < 64) break;
+            bn = cols16 - n_step * (nt - 1);
+            if (bn < n_step) bn = n_step;
+        }
+        if (bn > 256) continue;
+        p.b_main_bytes = align1k((uint32_t)bn * 128u);
+        p.b_tail_bytes = align1k((uint32_t)bn * (uint32_t)p.tail_box * 2u);
+        p.b_total_bytes = (uint32_t)ntaps * (nmain * p.b_main_bytes + (nmain < p.nchunks ? p.b_tail_bytes : 0u));
+        const int staging = ((bn + 63) / 64) * (int)kPanelBytes;
+        const int fixed = 1024 + (int)p.b_total_bytes + staging + 256;
+        const int avail = 226 * 1024 - fixed;
+        int stages = avail > 0 ? avail / (int)p.a_stage_bytes : 0;
+        if (stages < 2) continue;
+        stages = std::min(stages, 8);
+        p.stages = stages;
+        p.bn_tile = bn;
+        p.n_step = n_step;
+        p.n_tiles = nt;
+        p.smem = fixed + stages * (int)p.a_stage_bytes + 16 * stages + 64;
+        p.ok = true;
+        return p;
+    }
+    return p;
+}
+
+// act: tensor [N][T][H][W][pitch] providing the reduction channels (x for fprop, dy for dgrad); wimg: packed weight
+// image [tap][rows = output channels][kpitch]; out: [N][T][H][W][opitch].  org / btap describe the tap geometry.
+int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, const void* wimg, int wRows, int wKpitch,
+                int ntaps, void* out, int outPitch, int W, int H, int T, int N, const int* copy_off, int shift_org,
+                int tap0, int tap_dcp, int tap_dsh, const void* addend, float* part_sum, float* part_sq, const float* bias,
+                int nbias, int relu, cudaStream_t st) {
+    HaloArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < 4; ++i) a.b[i] = p.b[i], a.tl[i] = p.tl[i], a.O[i] = p.O[i];
+    // strides (elements of the OUTPUT tensor) in box order
+    const long long sW = outPitch, sH = (long long)outPitch * W, sT = sH * H, sN = sT * T;
+    if (p.spatial) a.os[0] = sW, a.os[1] = sT, a.os[2] = sN, a.os[3] = sH;
+    else a.os[0] = sW, a.os[1] = sH, a.os[2] = sN, a.os[3] = sT;
+    a.S = p.S, a.ncopies = p.ncopies, a.shift_org = shift_org;
+    for (int c = 0; c < p.ncopies; ++c) a.copy_off[c] = copy_off[c];
+    a.tap0 = tap0, a.tap_dcp = tap_dcp, a.tap_dsh = tap_dsh;
+    a.kdim = actC, a.nchunks = p.nchunks, a.tail_box = p.tail_box, a.ntaps = ntaps;
+    a.ncols = outPitch, a.nbias = nbias, a.bn_tile = p.bn_tile, a.n_step = p.n_step, a.n_tiles = p.n_tiles;
+    a.m_tiles = (int)p.m_tiles, a.stages = p.stages, a.relu = relu, a.tmem_cols = 2 * pow2_cols(p.bn_tile);
+    a.part_pitch = outPitch;
+    a.a_stage_bytes = p.a_stage_bytes, a.b_main_bytes = p.b_main_bytes, a.b_tail_bytes = p.b_tail_bytes;
+    a.b_total_bytes = p.b_total_bytes;
+    a.addend = (const __nv_bfloat16*)addend, a.part_sum = part_sum, a.part_sq = part_sq, a.bias = bias;
+    if (a.tmem_cols > 512) return fail(ZSV_ERR_UNSUPPORTED, "halo igemm: N tile too wide");
+
+    // activation maps in box order
+    auto act_map = [&](CUtensorMap* m, const void* basep, int C, int pitch, int boxc, int shift_ext,
+                       CUtensorMapSwizzle sw) {
+        const uint64_t cB = (uint64_t)pitch * 2;
+        const uint64_t bW = cB, bH = cB * W, bT = bH * H, bN = bT * T;
+        uint64_t dims[5], str[4];
+        dims[0] = C;
+        dims[1] = W, str[0] = bW;
+        if (p.spatial) {
+            dims[2] = T, str[1] = bT;
+            dims[3] = N, str[2] = bN;
+            dims[4] = H, str[3] = bH;
+        } else {
+            dims[2] = H, str[1] = bH;
+            dims[3] = N, str[2] = bN;
+            dims[4] = T, str[3] = bT;
+        }
+        uint32_t box[5] = {(uint32_t)boxc, (uint32_t)p.b[0], (uint32_t)p.b[1], (uint32_t)p.b[2], (uint32_t)shift_ext};
+        return make_map(m, basep, 5, dims, str, box, sw);
+    };
+    const CUtensorMapSwizzle tail_sw = p.tail_box == 16 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                     : (p.tail_box == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+    CUtensorMap mA, mAt, mB, mBt, mO;
+    int rc = act_map(&mA, act, actC, actPitch, 64, p.b[3] + p.S - 1, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    rc = act_map(&mAt, act, actC, actPitch, p.tail_box, p.b[3] + p.S - 1, tail_sw);
+    if (rc) return rc;
+    {
+        uint64_t dims[3] = {(uint64_t)actC, (uint64_t)wRows, (uint64_t)ntaps};
+        uint64_t str[2] = {(uint64_t)wKpitch * 2, (uint64_t)wKpitch * 2 * wRows};
+        uint32_t box[3] = {64, (uint32_t)p.bn_tile, 1};
+        rc = make_map(&mB, wimg, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        box[0] = (uint32_t)p.tail_box;
+        rc = make_map(&mBt, wimg, 3, dims, str, box, tail_sw);
+        if (rc) return rc;
+    }
+    rc = act_map(&mO, out, outPitch, outPitch, 64, p.b[3], CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(igemm_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    if (attr_err != cudaSuccess)
+        return fail(ZSV_ERR_CUDA, "cudaFuncSetAttribute(halo igemm) failed: %s", cudaGetErrorString(attr_err));
+    // grid: a multiple of n_tiles so that every CTA keeps one N tile
+    const long long want = p.m_tiles * p.n_tiles;
+    int grid = (int)std::min<long long>(want, (long long)(sm_count() / p.n_tiles) * p.n_tiles);
+    if (grid < p.n_tiles) grid = p.n_tiles;
+    igemm_halo_kernel<<<grid, kIgemmThreads, p.smem, st>>>(mA, mAt, mB, mBt, mO, a);
+    ZSV_LAUNCH_CHECK("igemm_halo_kernel");
+    return ZSV_OK;
+}
+
 }  // namespace
 }  // namespace zsv
 
@@ -931,8 +1411,12 @@ extern "C" int zsv_conv3d_pack_weight(const zsv_conv_desc* d, const float* w, vo
 extern "C" int zsv_conv3d_stat_rows(const zsv_conv_desc* d) {
     Shape s;
     if (check_desc(d, &s)) return -1;
+    // two partial rows per M tile (one per 64-row half of the tile); the tiling depends on which kernel fprop uses
+    if (!s.wfold && d->st == 1 && d->sh == 1 && d->sw == 1 && s.To == d->T && s.Ho == d->H && s.Wo == d->W) {
+        const HaloPlan hp = plan_halo(d->W, d->H, d->T, d->N, d->Cin, d->Cout, d->kt, d->kh, d->kw);
+        if (hp.ok) return (int)(2 * hp.m_tiles);
+    }
     const Box b = choose_box(s.Wo, s.Ho, s.To, d->N, false);
-    // two partial rows per M tile (one per 64-row half of the tile)
     return 2 * ceil_div(s.Wo, b.bw) * ceil_div(s.Ho, b.bh) * ceil_div(s.To, b.bt) * ceil_div(d->N, b.bn);
 }
 
@@ -943,6 +1427,19 @@ extern "C" int zsv_conv3d_fprop(const zsv_conv_desc* d, const void* x, const voi
     if (rc) return rc;
     if (!x || !w_fprop || !y) return fail(ZSV_ERR_BAD_ARG, "fprop: null pointer");
     if ((part_sum == nullptr) != (part_sq == nullptr)) return fail(ZSV_ERR_BAD_ARG, "fprop: need both stat buffers");
+
+    if (!s.wfold && d->st == 1 && d->sh == 1 && d->sw == 1 && s.To == d->T && s.Ho == d->H && s.Wo == d->W) {
+        const HaloPlan hp = plan_halo(d->W, d->H, d->T, d->N, d->Cin, d->Cout, d->kt, d->kh, d->kw);
+        if (hp.ok) {
+            // tap(cp, sh) = sh*kw + cp (spatial) or sh (temporal)
+            int copy_off[kMaxCopies];
+            for (int c = 0; c < hp.ncopies; ++c) copy_off[c] = hp.spatial ? c - d->pw : 0;
+            const int shift_org = hp.spatial ? -d->ph : -d->pt;
+            return launch_halo(hp, x, d->Cin, s.cinp, w_fprop, d->Cout, s.kpitch, s.ntaps, y, s.coutp, d->W, d->H, d->T,
+                               d->N, copy_off, shift_org, 0, 1, hp.spatial ? d->kw : 1, nullptr, part_sum, part_sq, bias,
+                               bias ? d->Cout : 0, relu, (cudaStream_t)stream);
+        }
+    }
 
     IgemmArgs a;
     memset(&a, 0, sizeof(a));
@@ -994,6 +1491,22 @@ extern "C" int zsv_conv3d_dgrad(const zsv_conv_desc* d, const void* dy, const vo
     if (s.wfold) return fail(ZSV_ERR_UNSUPPORTED, "dgrad: not available for the wfold (first-layer) layout");
     if (!dy || !w_dgrad || !dx) return fail(ZSV_ERR_BAD_ARG, "dgrad: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+
+    if (d->st == 1 && d->sh == 1 && d->sw == 1 && s.To == d->T && s.Ho == d->H && s.Wo == d->W) {
+        const HaloPlan hp = plan_halo(d->W, d->H, d->T, d->N, d->Cout, d->Cin, d->kt, d->kh, d->kw);
+        if (hp.ok) {
+            // dx[i] = sum_j dy[i + p - j] w[j]: copy j reads dy at W offset p - j; along the shift dim the halo starts
+            // at i0 + p - (S-1) and filter index j sits at halo slice S-1-j
+            // (tap = (S-1-sh)*kw + cp for spatial, S-1-sh for temporal)
+            int copy_off[kMaxCopies];
+            for (int c = 0; c < hp.ncopies; ++c) copy_off[c] = hp.spatial ? d->pw - c : 0;
+            const int shift_org = (hp.spatial ? d->ph : d->pt) - (hp.S - 1);
+            const int kwm = hp.spatial ? d->kw : 1;
+            return launch_halo(hp, dy, d->Cout, s.coutp, w_dgrad, d->Cin, s.coutp, s.ntaps, dx, s.cinp, d->W, d->H, d->T,
+                               d->N, copy_off, shift_org, (hp.S - 1) * kwm, 1, -kwm, addend, nullptr, nullptr, nullptr, 0, 0,
+                               st);
+        }
+    }
 
     // weight image [tap][Cin][coutp]: K = Cout
     const int classes_t = d->st, classes_h = d->sh, classes_w = d->sw;

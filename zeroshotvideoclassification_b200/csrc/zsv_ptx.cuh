@@ -116,6 +116,41 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same MMA with the two 64-bit shared-memory descriptors passed as 32-bit halves: the high word (SBO, version, layout)
+// is loop invariant and the low word (start address, LBO) advances by small constants, so the single issuing thread
+// spends a couple of 32-bit adds per MMA instead of 64-bit descriptor arithmetic.
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                               uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// halves of a K-major shared-memory descriptor: lo = start address | LBO(=16 B), hi = SBO | version | layout type
+__host__ __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__host__ __device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo_bytes, uint32_t layout) {
+    return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((layout & 7u) << 29);
+}
+// one lane of the (converged) warp
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .b32 r;\n"
+        ".reg .pred p;\n"
+        "elect.sync r|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred;
+}
 // Arrive on an mbarrier once all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -147,6 +182,17 @@ __host__ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint
     d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;   // stride byte offset  [32,46)
     d |= 1ull << 46;                                               // descriptor version (Blackwell)
     d |= 2ull << 61;                                               // layout type: SWIZZLE_128B
+    return d;
+}
+// Same descriptor with an explicit layout type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+// (K-major tiles whose rows are 128 / 64 / 32 bytes wide; SBO = 8 rows).
+__host__ __device__ __forceinline__ uint64_t umma_smem_desc_layout(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= 1ull << 46;
+    d |= static_cast<uint64_t>(layout & 7u) << 61;
     return d;
 }
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
