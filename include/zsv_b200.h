@@ -140,13 +140,16 @@ int zsv_bn_apply(const void* y, const float* scale, const float* shift, const vo
                  const float* shift2, const void* residual, void* out, long long rows, int C, int relu,
                  void* stream);
 /* Backward of out = relu?(bn(y) [+ bn2(y2)] [+ residual]):
- *   g    : bf16 gradient w.r.t. out;  out: bf16 forward output (ReLU mask), may be NULL when relu == 0
+ *   g    : bf16 gradient w.r.t. out
+ *   relu : 0 = no activation; 1 = ReLU, mask taken from the forward output `out`; 2 = ReLU of a single-branch unit,
+ *          mask recomputed as y*mask_scale + mask_shift > 0 (the forward's scale/shift) so `out` is not re-read
  *   pass 1 (reduce): per-block partial sums of dz and dz*xhat for y (and y2) -> workspace
  *   pass 2 (apply) : dy = scale*(dz - mean(dz) - xhat*mean(dz*xhat)); optional dy2; optional dz
  *                    written out (gradient flowing into the identity residual).
  *   dgamma/dbeta are fp32 [C].  Workspace size from zsv_bn_bwd_workspace. */
 size_t zsv_bn_bwd_workspace(int C);
-int zsv_bn_bwd(const void* g, const void* out, int relu, const void* y, const float* mean, const float* invstd,
+int zsv_bn_bwd(const void* g, const void* out, int relu, const float* mask_scale, const float* mask_shift,
+               const void* y, const float* mean, const float* invstd,
                const float* gamma, const void* y2, const float* mean2, const float* invstd2, const float* gamma2,
                void* dy, void* dy2, void* dz, float* dgamma, float* dbeta, float* dgamma2, float* dbeta2,
                long long rows, int C, void* workspace, size_t workspace_bytes, void* stream);

@@ -123,6 +123,11 @@ def test_bn_forward_backward(C, relu, mode):
         assert rel_err(db2.cpu(), extra[2].grad) < 5e-3
     if res is not None:
         assert rel_err(from_ndhwc(dz, C), extra[0].grad) < 1e-2
+    if mode == "plain" and relu:
+        # relu=2: the mask is recomputed from y with the forward's scale/shift instead of re-reading `out`
+        r2 = ops.bn_bwd(gd, None, 2, yd, mean, invstd, gamma.to(dev), C, mask_scale=scale, mask_shift=shift)
+        torch.cuda.synchronize()
+        assert torch.equal(r2[0], dy) and torch.equal(r2[3], dg) and torch.equal(r2[4], db)
 
 
 def test_bn_eval_scale_shift():

@@ -12,7 +12,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libzsv_b200.so"
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 X_NDHWC = 0
 X_WFOLD = 1
 
@@ -63,7 +63,8 @@ SIGNATURES = {
     "zsv_bn_eval_scale_shift": (_I, [_I, _P, _P, _P, _P, _F, _P, _P, _P]),
     "zsv_bn_apply": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _P]),
     "zsv_bn_bwd_workspace": (_SZ, [_I]),
-    "zsv_bn_bwd": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _P, _SZ, _P]),
+    "zsv_bn_bwd": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _P, _SZ,
+                        _P]),
     "zsv_head_fwd": (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _F, _P, _P, _P, _P, _P]),
     "zsv_head_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "zsv_mse_fwd_bwd": (_I, [_P, _P, _I, _I, _F, _P, _P, _P]),

@@ -35,6 +35,6 @@ int sm_count() {
 }  // namespace zsv
 
 extern "C" const char* zsv_last_error(void) { return zsv::g_err; }
-extern "C" int zsv_abi_version(void) { return 3; }
+extern "C" int zsv_abi_version(void) { return 4; }
 extern "C" int zsv_cpad(int c) { return zsv::cpad(c); }
 extern "C" unsigned long long zsv_launch_count(void) { return zsv::g_launches.load(std::memory_order_relaxed); }

@@ -107,6 +107,7 @@ struct IgemmArgs {
     int32_t tmem_cols;
     int32_t part_pitch;
     int32_t m_tiles, n_tiles;
+    int32_t nstg;            // output staging buffers (2 = the TMA store of tile i overlaps the epilogue of tile i+1)
     long long o_sN, o_sT, o_sH, o_sW;  // element strides of the output tensor
     __nv_bfloat16* out;
     const __nv_bfloat16* addend;
@@ -132,6 +133,138 @@ struct WgradArgs {
     Tap taps[kMaxTaps];
 };
 
+constexpr int kIgemmThreads = 320;
+constexpr int kEpiWarps = 8;
+
+// ------------------------------------------------------------------------------------------------
+// Shared epilogue of the igemm kernels (8 warps = 256 threads, `et` = thread index within them).
+// One call handles one output tile: TMEM -> registers -> (+bias, +addend, ReLU) -> bf16 -> SWIZZLE_128B staging in
+// shared memory -> one TMA store per 64-channel panel, plus BatchNorm partial sums read back from the staging tile.
+// ------------------------------------------------------------------------------------------------
+struct EpiArgs {
+    const __nv_bfloat16* addend;
+    const float* bias;
+    float* part_sum;
+    float* part_sq;
+    int ncols, nbias, relu, part_pitch;
+};
+
+__device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMap* mapOut, uint8_t* staging,
+                                              uint32_t staging_u32, float* statbuf, uint32_t trow,
+                                              uint32_t bar_tmem_empty, int width, int n_origin, bool valid,
+                                              long long off, int o0, int o1, int o2, int o3, int m_tile,
+                                              bool keep_one_store_in_flight, int q, int half, int row, int lane,
+                                              int et) {
+    (void)q;
+    // the staging buffer about to be written must have been read by the TMA store that used it last
+    if (et == 0) {
+        if (keep_one_store_in_flight) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else tma_store_wait_read();
+    }
+    named_bar_sync(1, kEpiWarps * 32);
+    const uint32_t srow = static_cast<uint32_t>(row) * 128u;
+    const uint32_t sxor = static_cast<uint32_t>(row & 7);
+    for (int c = half * 16; c < width; c += 32) {
+        uint32_t v[16];
+        tmem_ld16(trow + c, v);
+        tmem_ld_wait();
+        const int col = n_origin + c;
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        if (E.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (col + j < E.nbias) f[j] += __ldg(E.bias + col + j);
+        }
+        if (E.addend != nullptr && valid) {
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                if (col + 8 * hlf < E.ncols) {
+                    const uint4 a = *reinterpret_cast<const uint4*>(E.addend + off + col + 8 * hlf);
+                    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        f[8 * hlf + 2 * j] += bf16_lo(aw[j]);
+                        f[8 * hlf + 2 * j + 1] += bf16_hi(aw[j]);
+                    }
+                }
+            }
+        }
+        if (E.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk[j] = valid ? pack_bf16x2(f[2 * j], f[2 * j + 1]) : 0u;
+        // SWIZZLE_128B staging: 16-byte chunk index XOR (row & 7) inside the 64-channel panel
+        uint8_t* prow = staging + static_cast<uint32_t>(c >> 6) * kPanelBytes + srow;
+        const uint32_t ch = static_cast<uint32_t>(c & 63) >> 3;
+        *reinterpret_cast<uint4*>(prow + ((ch ^ sxor) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(prow + (((ch + 1) ^ sxor) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+    // accumulator buffer fully read: hand it back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_tmem_empty);
+    fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA store
+    named_bar_sync(2, kEpiWarps * 32);
+    if (et == 0) {
+        for (int p = 0; p * 64 < width; ++p) {
+            const int ccol = n_origin + 64 * p;
+            if (ccol < E.ncols) tma_store_5d(mapOut, staging_u32 + p * kPanelBytes, ccol, o0, o1, o2, o3);
+        }
+        tma_store_commit();
+    }
+    if (E.part_sum != nullptr) {
+        // column sums of the staged bf16 tile (invalid rows were staged as zeros): thread = (column pair, row segment),
+        // segments combined in fixed order through shared memory -> one deterministic partial row per M tile
+        const int npairs = width >> 1;
+        int nseg = (kEpiWarps * 32) / npairs;
+        nseg = nseg > 8 ? 8 : (nseg < 1 ? 1 : nseg);
+        const int rows_per = (128 + nseg - 1) / nseg;
+        if (et < npairs * nseg) {
+            const int seg = et / npairs;
+            const int cc = (et - seg * npairs) * 2;
+            const uint8_t* pb = staging + static_cast<uint32_t>(cc >> 6) * kPanelBytes;
+            const uint32_t chunk = static_cast<uint32_t>(cc & 63) >> 3;
+            const uint32_t inner = static_cast<uint32_t>(cc & 7) * 2u;
+            float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+            const int r0 = seg * rows_per;
+            const int r1 = min(128, r0 + rows_per);
+#pragma unroll 4
+            for (int rr = r0; rr < r1; ++rr) {
+                const uint32_t v2 = *reinterpret_cast<const uint32_t*>(
+                    pb + rr * 128 + ((chunk ^ static_cast<uint32_t>(rr & 7)) << 4) + inner);
+                const float lo = bf16_lo(v2), hi = bf16_hi(v2);
+                s1a += lo;
+                s1b += hi;
+                s2a = fmaf(lo, lo, s2a);
+                s2b = fmaf(hi, hi, s2b);
+            }
+            *reinterpret_cast<float2*>(statbuf + (seg * 2 + 0) * width + cc) = make_float2(s1a, s1b);
+            *reinterpret_cast<float2*>(statbuf + (seg * 2 + 1) * width + cc) = make_float2(s2a, s2b);
+        }
+        named_bar_sync(3, kEpiWarps * 32);
+        if (et < npairs) {
+            const int cc = et * 2;
+            float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+            for (int sg = 0; sg < nseg; ++sg) {
+                const float2 x = *reinterpret_cast<const float2*>(statbuf + (sg * 2 + 0) * width + cc);
+                const float2 y = *reinterpret_cast<const float2*>(statbuf + (sg * 2 + 1) * width + cc);
+                a.x += x.x, a.y += x.y, b.x += y.x, b.y += y.y;
+            }
+            const int col = n_origin + cc;
+            if (col < E.ncols) {   // ncols is even
+                const long long o = (long long)m_tile * E.part_pitch + col;
+                *reinterpret_cast<float2*>(E.part_sum + o) = a;
+                *reinterpret_cast<float2*>(E.part_sq + o) = b;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K-major implicit GEMM: out[pos][co] = sum_{tap, ci} act[pos + tap][ci] * w[tap][co][ci]
 //
@@ -143,9 +276,6 @@ struct WgradArgs {
 //                 chunks even/odd): tcgen05.ld -> bias/addend/ReLU -> bf16 -> 16-byte channels-last stores, plus
 //                 per-tile BatchNorm partial sums
 // ------------------------------------------------------------------------------------------------
-constexpr int kIgemmThreads = 320;
-constexpr int kEpiWarps = 8;
-
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
@@ -163,9 +293,10 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     const uint32_t stageBytes = kPanelBytes + stageB;
     const uint32_t ringBytes = stages * stageBytes;
     const int out_panels = (P.bn_tile + 63) >> 6;                    // 64-channel output panels of one tile
-    const uint32_t stagingOff = ringBytes;                           // [out_panels][128 rows][128 B], SWIZZLE_128B
+    const uint32_t stagingOff = ringBytes;                           // [nstg][out_panels][128 rows][128 B], SWIZZLE_128B
     const uint32_t stagingBytes = out_panels * kPanelBytes;
-    const uint32_t barOff = stagingOff + stagingBytes;
+    const uint32_t statOff = stagingOff + P.nstg * stagingBytes;     // 4 KB of fp32 scratch for the BN column sums
+    const uint32_t barOff = statOff + 4096u;
     const uint32_t barFull = base + barOff;
     const uint32_t barEmpty = barFull + 8u * stages;
     const uint32_t barTmemFull = barEmpty + 8u * stages;   // [2]
@@ -192,7 +323,6 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
 
     const int rows = P.bw * P.bh * P.bt * P.bn;
     const int kchunks = (P.kdim + 63) >> 6;
-    const int num_kb = P.ntaps * kchunks;
     const int num_tiles = P.m_tiles * P.n_tiles;
 
     // Producer and MMA warps run their loops with all 32 lanes (warp-uniform control flow and addresses); only the
@@ -284,12 +414,11 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         r /= P.bh;
         const int t = r % P.bt;
         const int n = r / P.bt;
-        const bool do_stats = P.part_sum != nullptr;
         const int et = threadIdx.x - 64;      // 0..255 within the epilogue group
-        uint8_t* staging = smem + stagingOff;
-        const uint32_t staging_u32 = base + stagingOff;
-        const uint32_t srow = static_cast<uint32_t>(row) * 128u;
-        const uint32_t sxor = static_cast<uint32_t>(row & 7);
+        EpiArgs E;
+        E.addend = P.addend, E.bias = P.bias, E.part_sum = P.part_sum, E.part_sq = P.part_sq;
+        E.ncols = P.ncols, E.nbias = P.nbias, E.relu = P.relu, E.part_pitch = P.part_pitch;
+        float* statbuf = reinterpret_cast<float*>(smem + statOff);
         int local = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
             int m = tile / P.n_tiles;
@@ -309,95 +438,11 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             const uint32_t buf = local & 1;
             mbar_wait(barTmemFull + 8u * buf, (local >> 1) & 1u);
             tc_fence_after();
-            // staging buffer free again: the thread that issued the previous tile's TMA store has waited for the
-            // bulk group to finish reading it, and every thread has finished its statistics pass over it
-            if (et == 0) tma_store_wait_read();
-            named_bar_sync(1, kEpiWarps * 32);
+            const uint32_t sb = (P.nstg == 2 ? (local & 1) : 0) * stagingBytes;
             const uint32_t trow = tmem_base + buf * acc_stride + (static_cast<uint32_t>(q * 32) << 16);
-            for (int c = half * 16; c < P.bn_tile; c += 32) {
-                uint32_t v[16];
-                tmem_ld16(trow + c, v);
-                tmem_ld_wait();
-                const int col = n_tile * P.bn_tile + c;
-                float f[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-                if (P.bias != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (col + j < P.nbias) f[j] += __ldg(P.bias + col + j);
-                }
-                if (P.addend != nullptr && valid) {
-#pragma unroll
-                    for (int hlf = 0; hlf < 2; ++hlf) {
-                        if (col + 8 * hlf < P.ncols) {
-                            const uint4 a = *reinterpret_cast<const uint4*>(P.addend + off + col + 8 * hlf);
-                            const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                f[8 * hlf + 2 * j] += bf16_lo(aw[j]);
-                                f[8 * hlf + 2 * j + 1] += bf16_hi(aw[j]);
-                            }
-                        }
-                    }
-                }
-                if (P.relu) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-                }
-                uint32_t pk[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) pk[j] = valid ? pack_bf16x2(f[2 * j], f[2 * j + 1]) : 0u;
-                // SWIZZLE_128B staging: 16-byte chunk index XOR (row & 7) inside the 64-channel panel
-                uint8_t* prow = staging + static_cast<uint32_t>(c >> 6) * kPanelBytes + srow;
-                const uint32_t ch = static_cast<uint32_t>(c & 63) >> 3;   // first of the two 16-byte chunks
-                *reinterpret_cast<uint4*>(prow + ((ch ^ sxor) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                *reinterpret_cast<uint4*>(prow + (((ch + 1) ^ sxor) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            }
-            // accumulator buffer fully read: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(barTmemEmpty + 8u * buf);
-            fence_proxy_async_smem();                 // generic-proxy smem writes -> visible to the TMA store
-            named_bar_sync(2, kEpiWarps * 32);
-            if (et == 0) {
-                for (int p = 0; p < out_panels; ++p) {
-                    const int ccol = n_tile * P.bn_tile + 64 * p;
-                    if (ccol < P.ncols) tma_store_5d(&mapOut, staging_u32 + p * kPanelBytes, ccol, w0, h0, t0, n0);
-                }
-                tma_store_commit();
-            }
-            if (do_stats) {
-                // column sums of the bf16 tile from shared memory: thread = (column pair, row half); invalid rows
-                // were staged as zeros.  Each half writes its own partial row (2*m_tile + half).
-                const int npairs = P.bn_tile >> 1;
-                for (int i = et; i < 2 * npairs; i += kEpiWarps * 32) {
-                    const int hh = i / npairs;
-                    const int cp2 = i - hh * npairs;            // column pair
-                    const int cc = cp2 * 2;
-                    const uint8_t* pb = staging + static_cast<uint32_t>(cc >> 6) * kPanelBytes;
-                    const uint32_t chunk = static_cast<uint32_t>(cc & 63) >> 3;
-                    const uint32_t inner = static_cast<uint32_t>(cc & 7) * 2u;
-                    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-                    const int r0 = hh * 64;
-#pragma unroll 8
-                    for (int rr = r0; rr < r0 + 64; ++rr) {
-                        const uint32_t v2 = *reinterpret_cast<const uint32_t*>(
-                            pb + rr * 128 + ((chunk ^ static_cast<uint32_t>(rr & 7)) << 4) + inner);
-                        const float lo = bf16_lo(v2), hi = bf16_hi(v2);
-                        s1a += lo;
-                        s1b += hi;
-                        s2a = fmaf(lo, lo, s2a);
-                        s2b = fmaf(hi, hi, s2b);
-                    }
-                    const int col = n_tile * P.bn_tile + cc;
-                    if (col < P.ncols) {   // ncols is even
-                        const long long o = (long long)(2 * m_tile + hh) * P.part_pitch + col;
-                        *reinterpret_cast<float2*>(P.part_sum + o) = make_float2(s1a, s1b);
-                        *reinterpret_cast<float2*>(P.part_sq + o) = make_float2(s2a, s2b);
-                    }
-                }
-            }
+            epilogue_tile(E, &mapOut, smem + stagingOff + sb, base + stagingOff + sb, statbuf, trow,
+                          barTmemEmpty + 8u * buf, P.bn_tile, n_tile * P.bn_tile, valid, off, w0, h0, t0, n0, m_tile,
+                          P.nstg == 2, q, half, row, lane, et);
         }
         if (et == 0) tma_store_wait_all();   // global writes of the last tile complete before the CTA exits
     }
@@ -435,7 +480,7 @@ struct HaloArgs {
     int32_t tap0, tap_dcp, tap_dsh; // weight tap index for (copy cp, shift tap sh) = tap0 + cp*tap_dcp + sh*tap_dsh
     int32_t kdim, nchunks, tail_box; // reduction channels, 64-wide chunks (incl. tail), box width of the tail chunk
     int32_t ntaps;
-    int32_t ncols, nbias, bn_tile, n_step, n_tiles, m_tiles, stages, relu, tmem_cols, part_pitch;
+    int32_t ncols, nbias, bn_tile, n_step, n_tiles, m_tiles, stages, relu, tmem_cols, part_pitch, nstg;
     uint32_t a_stage_bytes, b_main_bytes, b_tail_bytes, b_total_bytes;
     const __nv_bfloat16* addend;
     float* part_sum;
@@ -459,7 +504,9 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const uint32_t ringBytes = stages * P.a_stage_bytes;
     const int out_panels = (P.bn_tile + 63) >> 6;
     const uint32_t stagingOff = ringOff + ringBytes;
-    const uint32_t barOff = stagingOff + out_panels * kPanelBytes;
+    const uint32_t stagingBytes = out_panels * kPanelBytes;
+    const uint32_t statOff = stagingOff + P.nstg * stagingBytes;
+    const uint32_t barOff = statOff + 4096u;
     const uint32_t barFull = base + barOff;
     const uint32_t barEmpty = barFull + 8u * stages;
     const uint32_t barTmemFull = barEmpty + 8u * stages;
@@ -607,12 +654,11 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         r /= P.b[1];
         const int i2 = r % P.b[2];
         const int i3 = r / P.b[2];
-        const bool do_stats = P.part_sum != nullptr;
         const int et = threadIdx.x - 64;
-        uint8_t* staging = smem + stagingOff;
-        const uint32_t staging_u32 = base + stagingOff;
-        const uint32_t srow = static_cast<uint32_t>(row) * 128u;
-        const uint32_t sxor = static_cast<uint32_t>(row & 7);
+        EpiArgs E;
+        E.addend = P.addend, E.bias = P.bias, E.part_sum = P.part_sum, E.part_sq = P.part_sq;
+        E.ncols = P.ncols, E.nbias = P.nbias, E.relu = P.relu, E.part_pitch = P.part_pitch;
+        float* statbuf = reinterpret_cast<float*>(smem + statOff);
         // columns this tile owns: a non-last N tile only owns n_step of its bn_tile computed columns
         const int width = (n_tile + 1 < P.n_tiles) ? P.n_step : P.bn_tile;
         int local = 0;
@@ -631,88 +677,11 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             const uint32_t buf = local & 1;
             mbar_wait(barTmemFull + 8u * buf, (local >> 1) & 1u);
             tc_fence_after();
-            if (et == 0) tma_store_wait_read();
-            named_bar_sync(1, kEpiWarps * 32);
+            const uint32_t sb = (P.nstg == 2 ? (local & 1) : 0) * stagingBytes;
             const uint32_t trow = tmem_base + buf * acc_stride + (static_cast<uint32_t>(q * 32) << 16);
-            for (int c = half * 16; c < width; c += 32) {
-                uint32_t v[16];
-                tmem_ld16(trow + c, v);
-                tmem_ld_wait();
-                const int col = n_origin + c;
-                float f[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-                if (P.bias != nullptr) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (col + j < P.nbias) f[j] += __ldg(P.bias + col + j);
-                }
-                if (P.addend != nullptr && valid) {
-#pragma unroll
-                    for (int hlf = 0; hlf < 2; ++hlf) {
-                        if (col + 8 * hlf < P.ncols) {
-                            const uint4 a = *reinterpret_cast<const uint4*>(P.addend + off + col + 8 * hlf);
-                            const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                f[8 * hlf + 2 * j] += bf16_lo(aw[j]);
-                                f[8 * hlf + 2 * j + 1] += bf16_hi(aw[j]);
-                            }
-                        }
-                    }
-                }
-                if (P.relu) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-                }
-                uint32_t pk[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) pk[j] = valid ? pack_bf16x2(f[2 * j], f[2 * j + 1]) : 0u;
-                uint8_t* prow = staging + static_cast<uint32_t>(c >> 6) * kPanelBytes + srow;
-                const uint32_t ch = static_cast<uint32_t>(c & 63) >> 3;
-                *reinterpret_cast<uint4*>(prow + ((ch ^ sxor) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                *reinterpret_cast<uint4*>(prow + (((ch + 1) ^ sxor) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(barTmemEmpty + 8u * buf);
-            fence_proxy_async_smem();
-            named_bar_sync(2, kEpiWarps * 32);
-            if (et == 0) {
-                for (int p = 0; p * 64 < width; ++p) {
-                    const int ccol = n_origin + 64 * p;
-                    if (ccol < P.ncols) tma_store_5d(&mapOut, staging_u32 + p * kPanelBytes, ccol, o0, o1, o2, o3);
-                }
-                tma_store_commit();
-            }
-            if (do_stats) {
-                const int npairs = width >> 1;
-                for (int i = et; i < 2 * npairs; i += kEpiWarps * 32) {
-                    const int hh = i / npairs;
-                    const int cc = (i - hh * npairs) * 2;
-                    const uint8_t* pb = staging + static_cast<uint32_t>(cc >> 6) * kPanelBytes;
-                    const uint32_t chunk = static_cast<uint32_t>(cc & 63) >> 3;
-                    const uint32_t inner = static_cast<uint32_t>(cc & 7) * 2u;
-                    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-                    const int r0 = hh * 64;
-#pragma unroll 8
-                    for (int rr = r0; rr < r0 + 64; ++rr) {
-                        const uint32_t v2 = *reinterpret_cast<const uint32_t*>(
-                            pb + rr * 128 + ((chunk ^ static_cast<uint32_t>(rr & 7)) << 4) + inner);
-                        const float lo = bf16_lo(v2), hi = bf16_hi(v2);
-                        s1a += lo;
-                        s1b += hi;
-                        s2a = fmaf(lo, lo, s2a);
-                        s2b = fmaf(hi, hi, s2b);
-                    }
-                    const int col = n_origin + cc;
-                    if (col < P.ncols) {
-                        const long long o = (long long)(2 * mt + hh) * P.part_pitch + col;
-                        *reinterpret_cast<float2*>(P.part_sum + o) = make_float2(s1a, s1b);
-                        *reinterpret_cast<float2*>(P.part_sq + o) = make_float2(s2a, s2b);
-                    }
-                }
-            }
+            epilogue_tile(E, &mapOut, smem + stagingOff + sb, base + stagingOff + sb, statbuf, trow,
+                          barTmemEmpty + 8u * buf, width, n_origin, valid, off, o0, o1, o2, o3, mt, P.nstg == 2, q, half,
+                          row, lane, et);
         }
         if (et == 0) tma_store_wait_all();
     }
@@ -770,58 +739,92 @@ wgrad_mnmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
     const int p0 = 2 * m_tile;
     const int npan = min(2, P.npanels - p0);
 
+    // warp-uniform loops, one elected lane issues (see igemm_kmajor_kernel)
     if (warp == 0) {
-        if (lane == 0) {
-            const CUtensorMap* maps[kMaxMaps] = {&mapA0, &mapA1, &mapA2, &mapA3};
-            const uint32_t tx = static_cast<uint32_t>(rows) * 128u * (npan + P.nbp);
-            for (int kb = kb0; kb < kb1; ++kb) {
-                const int i = kb - kb0;
-                const int s = i % stages;
-                const uint32_t ph = (i / stages) & 1;
-                mbar_wait(barEmpty + 8u * s, ph ^ 1u);
-                int m = kb;
-                const int iw = m % P.tw;
-                m /= P.tw;
-                const int ih = m % P.th;
-                m /= P.th;
-                const int it = m % P.tt;
-                const int in_ = m / P.tt;
+        const uint32_t leader = elect_one();
+        const uint32_t tx = static_cast<uint32_t>(rows) * 128u * (npan + P.nbp);
+        // the (at most two) x panels of this M tile: tap geometry and channel offset are loop invariant
+        Tap tapj[2];
+        int c0j[2];
+        const CUtensorMap* mpj[2];
+        for (int j = 0; j < 2; ++j) {
+            const int p = min(p0 + j, P.npanels - 1);
+            const int tp = p / P.kchunks;
+            c0j[j] = (p - tp * P.kchunks) << 6;
+            tapj[j] = P.taps[tp];
+            mpj[j] = tapj[j].map == 0 ? &mapA0 : (tapj[j].map == 1 ? &mapA1 : (tapj[j].map == 2 ? &mapA2 : &mapA3));
+        }
+        // position-tile coordinates advance incrementally with the k-block index
+        int m = kb0;
+        int iw = m % P.tw;
+        m /= P.tw;
+        int ih = m % P.th;
+        m /= P.th;
+        int it = m % P.tt;
+        int in_ = m / P.tt;
+        uint32_t stage = 0, phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(barEmpty + 8u * stage, phase ^ 1u);
+            if (leader) {
                 const int w0 = iw * P.bw, h0 = ih * P.bh, t0 = it * P.bt, n0 = in_ * P.bn;
-                const uint32_t full = barFull + 8u * s;
-                const uint32_t sa = base + s * stageBytes;
+                const uint32_t full = barFull + 8u * stage;
+                const uint32_t sa = base + stage * stageBytes;
                 mbar_expect_tx(full, tx);
-                for (int j = 0; j < npan; ++j) {
-                    const int p = p0 + j;
-                    const int tp = p / P.kchunks;
-                    const int c0 = (p - tp * P.kchunks) << 6;
-                    const Tap tap = P.taps[tp];
-                    tma_load_5d(sa + j * kPanelBytes, maps[tap.map], full, c0, w0 + tap.dw, h0 + tap.dh, t0 + tap.dt,
-                                n0);
-                }
+                tma_load_5d(sa, mpj[0], full, c0j[0], w0 + tapj[0].dw, h0 + tapj[0].dh, t0 + tapj[0].dt, n0);
+                if (npan > 1)
+                    tma_load_5d(sa + kPanelBytes, mpj[1], full, c0j[1], w0 + tapj[1].dw, h0 + tapj[1].dh,
+                                t0 + tapj[1].dt, n0);
                 for (int j = 0; j < P.nbp; ++j)
                     tma_load_5d(sa + (2 + j) * kPanelBytes, &mapB, full, n_tile * P.bn_tile + 64 * j, w0, h0, t0, n0);
             }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(128, P.bn_tile, 1, 1);
-            const int ksteps = rows >> 4;
-            for (int kb = kb0; kb < kb1; ++kb) {
-                const int i = kb - kb0;
-                const int s = i % stages;
-                const uint32_t ph = (i / stages) & 1;
-                mbar_wait(barFull + 8u * s, ph);
-                tc_fence_after();
-                const uint32_t sa = base + s * stageBytes;
-                const uint64_t da = umma_smem_desc(sa, kPanelBytes, 1024);
-                const uint64_t db = umma_smem_desc(sa + 2 * kPanelBytes, kPanelBytes, 1024);
-                for (int k = 0; k < ksteps; ++k)  // 16 position rows = 2048 B per step
-                    umma_bf16(tmem_base, da + 128u * k, db + 128u * k, idesc, (i | k) != 0);
-                umma_commit(barEmpty + 8u * s);
+            __syncwarp();
+            if (++stage == static_cast<uint32_t>(stages)) {
+                stage = 0;
+                phase ^= 1u;
             }
-            umma_commit(barTmem);
+            if (++iw == P.tw) {
+                iw = 0;
+                if (++ih == P.th) {
+                    ih = 0;
+                    if (++it == P.tt) {
+                        it = 0;
+                        ++in_;
+                    }
+                }
+            }
         }
+    } else if (warp == 1) {
+        const uint32_t leader = elect_one();
+        const uint32_t idesc = umma_idesc_bf16(128, P.bn_tile, 1, 1);
+        const int ksteps = rows >> 4;
+        // MN-major SWIZZLE_128B descriptors: LBO = panel stride (next 64 channels), SBO = 1024 B (next 8 positions)
+        const uint32_t dhi = umma_desc_hi(1024, 2);
+        const uint32_t lbo = (kPanelBytes >> 4) << 16;
+        uint32_t stage = 0, phase = 0;
+        uint32_t acc = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(barFull + 8u * stage, phase);
+            tc_fence_after();
+            if (leader) {
+                const uint32_t sa = base + stage * stageBytes;
+                const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | lbo;
+                const uint32_t b_lo = (((sa + 2 * kPanelBytes) >> 4) & 0x3FFFu) | lbo;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {   // 16 position rows = 2048 B per step
+                    if (k < ksteps) {
+                        umma_bf16_lohi(tmem_base, a_lo + 128u * k, dhi, b_lo + 128u * k, dhi, idesc, acc);
+                        acc = 1;
+                    }
+                }
+                umma_commit(barEmpty + 8u * stage);
+            }
+            __syncwarp();
+            if (++stage == static_cast<uint32_t>(stages)) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        }
+        if (leader) umma_commit(barTmem);
         __syncwarp();
     } else {
         const int q = warp & 3;
@@ -1155,19 +1158,28 @@ int build_fwd_taps(const zsv_conv_desc* d, const Shape& s, const void* x, const 
     return ZSV_OK;
 }
 
-int igemm_smem_bytes(int bn_tile, int stages) {
-    return 1024 + stages * (kPanelBytes + bn_tile * 128) + ((bn_tile + 63) / 64) * kPanelBytes + 16 * stages + 48 + 64;
+int igemm_smem_bytes(int bn_tile, int stages, int nstg) {
+    return 1024 + stages * (kPanelBytes + bn_tile * 128) + nstg * ((bn_tile + 63) / 64) * kPanelBytes + 4096 +
+           16 * stages + 48 + 64;
 }
 
 int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtensorMap& mapOut, IgemmArgs& a,
                  long long m_tiles, int n_tiles, cudaStream_t stream) {
     // one persistent CTA per SM owns (almost) all shared memory: as many ring stages as fit, at most 8
+    // two output staging buffers when at least 3 ring stages still fit beside them
+    int nstg = 2;
     int stages = 8;
-    while (stages > 2 && igemm_smem_bytes(a.bn_tile, stages) > 226 * 1024) --stages;
+    while (stages > 2 && igemm_smem_bytes(a.bn_tile, stages, nstg) > 226 * 1024) --stages;
+    if (stages < 3 || igemm_smem_bytes(a.bn_tile, stages, nstg) > 226 * 1024) {
+        nstg = 1;
+        stages = 8;
+        while (stages > 2 && igemm_smem_bytes(a.bn_tile, stages, nstg) > 226 * 1024) --stages;
+    }
+    a.nstg = nstg;
     a.stages = stages;
     a.tmem_cols = 2 * pow2_cols(a.bn_tile);   // two accumulator buffers
     if (a.tmem_cols > 512) return fail(ZSV_ERR_UNSUPPORTED, "igemm: N tile %d too wide for two TMEM buffers", a.bn_tile);
-    const int smem = igemm_smem_bytes(a.bn_tile, stages);
+    const int smem = igemm_smem_bytes(a.bn_tile, stages, nstg);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
@@ -1190,7 +1202,7 @@ struct HaloPlan {
     bool ok;
     bool spatial;       // shift dim = H (taps along W are copies) ; otherwise shift dim = T
     int b[4], tl[4], O[4];
-    int S, ncopies, stages, bn_tile, n_step, n_tiles, nchunks, tail_box;
+    int S, ncopies, stages, nstg, bn_tile, n_step, n_tiles, nchunks, tail_box;
     long long m_tiles;
     uint32_t a_stage_bytes, b_main_bytes, b_tail_bytes, b_total_bytes;
     int smem;
@@ -1266,13 +1278,18 @@ HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int k
         p.b_main_bytes = align1k((uint32_t)bn * 128u);
         p.b_tail_bytes = align1k((uint32_t)bn * (uint32_t)p.tail_box * 2u);
         p.b_total_bytes = (uint32_t)ntaps * (nmain * p.b_main_bytes + (nmain < p.nchunks ? p.b_tail_bytes : 0u));
-        const int staging = ((bn + 63) / 64) * (int)kPanelBytes;
-        const int fixed = 1024 + (int)p.b_total_bytes + staging + 256;
-        const int avail = 226 * 1024 - fixed;
-        int stages = avail > 0 ? avail / (int)p.a_stage_bytes : 0;
-        if (stages < 2) continue;
+        const int staging1 = ((bn + 63) / 64) * (int)kPanelBytes;
+        int nstg = 2, stages = 0, fixed = 0;
+        for (; nstg >= 1; --nstg) {   // prefer two staging buffers if >= 3 activation stages still fit
+            fixed = 1024 + (int)p.b_total_bytes + nstg * staging1 + 4096 + 256;
+            const int avail = 226 * 1024 - fixed;
+            stages = avail > 0 ? avail / (int)p.a_stage_bytes : 0;
+            if (stages >= (nstg == 2 ? 3 : 2)) break;
+        }
+        if (nstg < 1) continue;
         stages = std::min(stages, 8);
         p.stages = stages;
+        p.nstg = nstg;
         p.bn_tile = bn;
         p.n_step = n_step;
         p.n_tiles = nt;
@@ -1303,6 +1320,7 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
     a.ncols = outPitch, a.nbias = nbias, a.bn_tile = p.bn_tile, a.n_step = p.n_step, a.n_tiles = p.n_tiles;
     a.m_tiles = (int)p.m_tiles, a.stages = p.stages, a.relu = relu, a.tmem_cols = 2 * pow2_cols(p.bn_tile);
     a.part_pitch = outPitch;
+    a.nstg = p.nstg;
     a.a_stage_bytes = p.a_stage_bytes, a.b_main_bytes = p.b_main_bytes, a.b_tail_bytes = p.b_tail_bytes;
     a.b_total_bytes = p.b_total_bytes;
     a.addend = (const __nv_bfloat16*)addend, a.part_sum = part_sum, a.part_sq = part_sq, a.bias = bias;
@@ -1411,13 +1429,13 @@ extern "C" int zsv_conv3d_pack_weight(const zsv_conv_desc* d, const float* w, vo
 extern "C" int zsv_conv3d_stat_rows(const zsv_conv_desc* d) {
     Shape s;
     if (check_desc(d, &s)) return -1;
-    // two partial rows per M tile (one per 64-row half of the tile); the tiling depends on which kernel fprop uses
+    // one partial row per M tile; the tiling depends on which kernel fprop uses
     if (!s.wfold && d->st == 1 && d->sh == 1 && d->sw == 1 && s.To == d->T && s.Ho == d->H && s.Wo == d->W) {
         const HaloPlan hp = plan_halo(d->W, d->H, d->T, d->N, d->Cin, d->Cout, d->kt, d->kh, d->kw);
-        if (hp.ok) return (int)(2 * hp.m_tiles);
+        if (hp.ok) return (int)hp.m_tiles;
     }
     const Box b = choose_box(s.Wo, s.Ho, s.To, d->N, false);
-    return 2 * ceil_div(s.Wo, b.bw) * ceil_div(s.Ho, b.bh) * ceil_div(s.To, b.bt) * ceil_div(d->N, b.bn);
+    return ceil_div(s.Wo, b.bw) * ceil_div(s.Ho, b.bh) * ceil_div(s.To, b.bt) * ceil_div(d->N, b.bn);
 }
 
 extern "C" int zsv_conv3d_fprop(const zsv_conv_desc* d, const void* x, const void* w_fprop, void* y, float* part_sum,

@@ -187,53 +187,54 @@ __global__ void bn_eval_kernel(int C, int Cp, const float* __restrict__ gamma, c
 // ------------------------------------------------------------------------------------------------
 // BatchNorm apply (+ second normalised branch, + residual, + ReLU)
 // ------------------------------------------------------------------------------------------------
+// Thread layout shared by the BN streaming kernels: a block is V = Cp/8 channel groups x R = 256/V rows.  Every thread
+// keeps ONE channel group for its whole life, so the per-channel constants live in registers (no shared-memory
+// lookups, no index arithmetic per element) while a block still reads/writes R whole rows = one contiguous span.
 template <bool kHasY2, bool kHasRes>
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                 const __nv_bfloat16* __restrict__ y2, const float* __restrict__ scale2,
                 const float* __restrict__ shift2, const __nv_bfloat16* __restrict__ res,
-                __nv_bfloat16* __restrict__ out, long long nvec, int Cp, int relu) {
-    extern __shared__ float sm[];
-    float* s_scale = sm;
-    float* s_shift = sm + Cp;
-    float* s_scale2 = sm + 2 * Cp;
-    float* s_shift2 = sm + 3 * Cp;
-    for (int i = threadIdx.x; i < Cp; i += blockDim.x) {
-        s_scale[i] = scale[i];
-        s_shift[i] = shift[i];
-        if (kHasY2) {
-            s_scale2[i] = scale2[i];
-            s_shift2[i] = shift2[i];
-        }
-    }
-    __syncthreads();
+                __nv_bfloat16* __restrict__ out, long long rows, int Cp, int R, int relu) {
     const int V = Cp >> 3;
-    constexpr int U = 4;  // independent 16-byte vectors in flight per thread
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < nvec; i0 += U * stride) {
+    const int vl = threadIdx.x % V;
+    const int rl = threadIdx.x / V;
+    if (rl >= R) return;
+    const int c0 = vl << 3;
+    float sc[8], sh[8], sc2[8], sh2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = scale[c0 + j];
+        sh[j] = shift[c0 + j];
+        sc2[j] = kHasY2 ? scale2[c0 + j] : 0.f;
+        sh2[j] = kHasY2 ? shift2[c0 + j] : 0.f;
+    }
+    constexpr int U = 2;   // rows in flight per thread
+    const long long rstride = (long long)gridDim.x * R;
+    for (long long r0 = (long long)blockIdx.x * R + rl; r0 < rows; r0 += U * rstride) {
         uint4 vy[U], vy2[U], vr[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long i = i0 + u * stride;
-            if (i < nvec) {
-                vy[u] = *reinterpret_cast<const uint4*>(y + i * 8);
-                if (kHasY2) vy2[u] = *reinterpret_cast<const uint4*>(y2 + i * 8);
-                if (kHasRes) vr[u] = *reinterpret_cast<const uint4*>(res + i * 8);
+            const long long r = r0 + u * rstride;
+            if (r < rows) {
+                const long long e = r * Cp + c0;
+                vy[u] = *reinterpret_cast<const uint4*>(y + e);
+                if (kHasY2) vy2[u] = *reinterpret_cast<const uint4*>(y2 + e);
+                if (kHasRes) vr[u] = *reinterpret_cast<const uint4*>(res + e);
             }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long i = i0 + u * stride;
-            if (i >= nvec) break;
-            const int c0 = static_cast<int>(i % V) << 3;
+            const long long r = r0 + u * rstride;
+            if (r >= rows) break;
             float f[8], o[8];
             unpack8(vy[u], f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = fmaf(f[j], s_scale[c0 + j], s_shift[c0 + j]);
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(f[j], sc[j], sh[j]);
             if (kHasY2) {
                 unpack8(vy2[u], f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] += fmaf(f[j], s_scale2[c0 + j], s_shift2[c0 + j]);
+                for (int j = 0; j < 8; ++j) o[j] += fmaf(f[j], sc2[j], sh2[j]);
             }
             if (kHasRes) {
                 unpack8(vr[u], f);
@@ -244,7 +245,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
             }
-            *reinterpret_cast<uint4*>(out + i * 8) = pack8(o);
+            *reinterpret_cast<uint4*>(out + r * Cp + c0) = pack8(o);
         }
     }
 }
@@ -259,6 +260,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
 template <bool kHasY2>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ out, int relu,
+                     const float* __restrict__ mask_scale, const float* __restrict__ mask_shift,
                      const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
                      const float* __restrict__ invstd, const __nv_bfloat16* __restrict__ y2,
                      const float* __restrict__ mean2, const float* __restrict__ invstd2, long long rows, int Cp, int R,
@@ -270,12 +272,14 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* _
     const bool active = rl < R;
     const int c0 = vl << 3;
     float a1[8], a2[8], b1[8], b2[8];
-    float mu[8], is[8], mu2[8], is2[8];
+    float mu[8], is[8], mu2[8], is2[8], msc[8], msh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         a1[j] = a2[j] = b1[j] = b2[j] = 0.f;
         mu[j] = mean[c0 + j];
         is[j] = invstd[c0 + j];
+        msc[j] = relu == 2 ? mask_scale[c0 + j] : 0.f;
+        msh[j] = relu == 2 ? mask_shift[c0 + j] : 0.f;
         mu2[j] = kHasY2 ? mean2[c0 + j] : 0.f;
         is2[j] = kHasY2 ? invstd2[c0 + j] : 0.f;
     }
@@ -284,12 +288,16 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* _
             const long long e = r * Cp + c0;
             float gz[8], f[8];
             unpack8(*reinterpret_cast<const uint4*>(g + e), gz);
-            if (relu) {
+            if (relu == 1) {
                 unpack8(*reinterpret_cast<const uint4*>(out + e), f);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) gz[j] = f[j] > 0.f ? gz[j] : 0.f;
             }
             unpack8(*reinterpret_cast<const uint4*>(y + e), f);
+            if (relu == 2) {   // ReLU mask recomputed from the pre-activation: saves re-reading the forward output
+#pragma unroll
+                for (int j = 0; j < 8; ++j) gz[j] = fmaf(f[j], msc[j], msh[j]) > 0.f ? gz[j] : 0.f;
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 a1[j] += gz[j];
@@ -351,85 +359,90 @@ bn_bwd_final_kernel(const float* __restrict__ partial, int nblocks, int nq, int 
     }
 }
 
+// dy = k*(dz - c1 - xhat*c2) with k = gamma*invstd, c1 = mean(dz), c2 = mean(dz*xhat), xhat = (y-mu)*invstd, folded
+// per channel into  dy = A*dz + B*y + D  (A = k, B = -k*c2*invstd, D = k*(c2*invstd*mu - c1)).
 template <bool kHasY2>
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ out, int relu,
+                    const float* __restrict__ mask_scale, const float* __restrict__ mask_shift,
                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
                     const float* __restrict__ invstd, const float* __restrict__ gamma,
                     const __nv_bfloat16* __restrict__ y2, const float* __restrict__ mean2,
                     const float* __restrict__ invstd2, const float* __restrict__ gamma2,
                     const float* __restrict__ sums, __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dy2,
-                    __nv_bfloat16* __restrict__ dz, long long nvec, int C, int Cp, float inv_count) {
-    extern __shared__ float sm[];  // per channel: mean, k = gamma*invstd, invstd, c1 = s1/M, c2 = s2/M  (x2 branches)
-    float* p_mu = sm;
-    float* p_k = sm + Cp;
-    float* p_is = sm + 2 * Cp;
-    float* p_c1 = sm + 3 * Cp;
-    float* p_c2 = sm + 4 * Cp;
-    float* q_mu = sm + 5 * Cp;
-    float* q_k = sm + 6 * Cp;
-    float* q_is = sm + 7 * Cp;
-    float* q_c2 = sm + 8 * Cp;
-    for (int i = threadIdx.x; i < Cp; i += blockDim.x) {
-        const float gm = (i < C) ? (gamma ? gamma[i] : 1.f) : 0.f;
-        p_mu[i] = mean[i];
-        p_is[i] = invstd[i];
-        p_k[i] = gm * invstd[i];
-        p_c1[i] = sums[i] * inv_count;
-        p_c2[i] = sums[Cp + i] * inv_count;
-        if (kHasY2) {
-            const float gm2 = (i < C) ? (gamma2 ? gamma2[i] : 1.f) : 0.f;
-            q_mu[i] = mean2[i];
-            q_is[i] = invstd2[i];
-            q_k[i] = gm2 * invstd2[i];
-            q_c2[i] = sums[3 * Cp + i] * inv_count;
-        }
-    }
-    __syncthreads();
+                    __nv_bfloat16* __restrict__ dz, long long rows, int C, int Cp, int R, float inv_count) {
     const int V = Cp >> 3;
+    const int vl = threadIdx.x % V;
+    const int rl = threadIdx.x / V;
+    if (rl >= R) return;
+    const int c0 = vl << 3;
+    float A[8], Bc[8], D[8], A2[8], B2[8], D2[8], msc[8], msh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        const float gm = (c < C) ? (gamma ? gamma[c] : 1.f) : 0.f;
+        const float is = invstd[c], mu = mean[c];
+        const float k = gm * is;
+        const float c1 = sums[c] * inv_count, c2 = sums[Cp + c] * inv_count;
+        A[j] = k;
+        Bc[j] = -k * c2 * is;
+        D[j] = k * (c2 * is * mu - c1);
+        if (kHasY2) {
+            const float gm2 = (c < C) ? (gamma2 ? gamma2[c] : 1.f) : 0.f;
+            const float is2 = invstd2[c], mu2 = mean2[c];
+            const float k2 = gm2 * is2;
+            const float c22 = sums[3 * Cp + c] * inv_count;
+            A2[j] = k2;
+            B2[j] = -k2 * c22 * is2;
+            D2[j] = k2 * (c22 * is2 * mu2 - c1);
+        } else {
+            A2[j] = B2[j] = D2[j] = 0.f;
+        }
+        msc[j] = relu == 2 ? mask_scale[c] : 0.f;
+        msh[j] = relu == 2 ? mask_shift[c] : 0.f;
+    }
     constexpr int U = 2;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < nvec; i0 += U * stride) {
+    const long long rstride = (long long)gridDim.x * R;
+    for (long long r0 = (long long)blockIdx.x * R + rl; r0 < rows; r0 += U * rstride) {
         uint4 vg[U], vo[U], vy[U], vy2[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long i = i0 + u * stride;
-            if (i < nvec) {
-                vg[u] = *reinterpret_cast<const uint4*>(g + i * 8);
-                if (relu) vo[u] = *reinterpret_cast<const uint4*>(out + i * 8);
-                vy[u] = *reinterpret_cast<const uint4*>(y + i * 8);
-                if (kHasY2) vy2[u] = *reinterpret_cast<const uint4*>(y2 + i * 8);
+            const long long r = r0 + u * rstride;
+            if (r < rows) {
+                const long long e = r * Cp + c0;
+                vg[u] = *reinterpret_cast<const uint4*>(g + e);
+                if (relu == 1) vo[u] = *reinterpret_cast<const uint4*>(out + e);
+                vy[u] = *reinterpret_cast<const uint4*>(y + e);
+                if (kHasY2) vy2[u] = *reinterpret_cast<const uint4*>(y2 + e);
             }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long i = i0 + u * stride;
-            if (i >= nvec) break;
-            const int c0 = static_cast<int>(i % V) << 3;
+            const long long r = r0 + u * rstride;
+            if (r >= rows) break;
+            const long long e = r * Cp + c0;
             float gz[8], f[8], o[8];
             unpack8(vg[u], gz);
-            if (relu) {
+            if (relu == 1) {
                 unpack8(vo[u], f);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) gz[j] = f[j] > 0.f ? gz[j] : 0.f;
             }
             unpack8(vy[u], f);
+            if (relu == 2) {   // ReLU mask recomputed from the pre-activation
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float xh = (f[j] - p_mu[c0 + j]) * p_is[c0 + j];
-                o[j] = p_k[c0 + j] * (gz[j] - p_c1[c0 + j] - xh * p_c2[c0 + j]);
+                for (int j = 0; j < 8; ++j) gz[j] = fmaf(f[j], msc[j], msh[j]) > 0.f ? gz[j] : 0.f;
             }
-            *reinterpret_cast<uint4*>(dy + i * 8) = pack8(o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], gz[j], fmaf(Bc[j], f[j], D[j]));
+            *reinterpret_cast<uint4*>(dy + e) = pack8(o);
             if (kHasY2) {
                 unpack8(vy2[u], f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float xh = (f[j] - q_mu[c0 + j]) * q_is[c0 + j];
-                    o[j] = q_k[c0 + j] * (gz[j] - p_c1[c0 + j] - xh * q_c2[c0 + j]);
-                }
-                *reinterpret_cast<uint4*>(dy2 + i * 8) = pack8(o);
+                for (int j = 0; j < 8; ++j) o[j] = fmaf(A2[j], gz[j], fmaf(B2[j], f[j], D2[j]));
+                *reinterpret_cast<uint4*>(dy2 + e) = pack8(o);
             }
-            if (dz != nullptr) *reinterpret_cast<uint4*>(dz + i * 8) = pack8(gz);
+            if (dz != nullptr) *reinterpret_cast<uint4*>(dz + e) = pack8(gz);
         }
     }
 }
@@ -674,22 +687,23 @@ extern "C" int zsv_bn_apply(const void* y, const float* scale, const float* shif
     const int Cp = cpad(C);
     if (Cp > kMaxC) return fail(ZSV_ERR_UNSUPPORTED, "bn_apply: more than %d channels", kMaxC);
     if (rows < 1) return ZSV_OK;
-    const long long nvec = rows * (Cp >> 3);
-    const int blocks = ew_blocks(nvec, 256 * 4);
-    const size_t smem = (size_t)4 * Cp * sizeof(float);
+    const int V = Cp >> 3;
+    if (V > 256) return fail(ZSV_ERR_UNSUPPORTED, "bn_apply: channel pitch too large");
+    const int R = std::max(1, 256 / V);
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((long long)sm_count() * 8, ceil_div_ll(rows, (long long)R * 2)));
     cudaStream_t st = (cudaStream_t)stream;
     const __nv_bfloat16* yb = (const __nv_bfloat16*)y;
     const __nv_bfloat16* y2b = (const __nv_bfloat16*)y2;
     const __nv_bfloat16* rb = (const __nv_bfloat16*)residual;
     __nv_bfloat16* ob = (__nv_bfloat16*)out;
     if (y2 && residual)
-        bn_apply_kernel<true, true><<<blocks, 256, smem, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, nvec, Cp, relu);
+        bn_apply_kernel<true, true><<<blocks, 256, 0, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, rows, Cp, R, relu);
     else if (y2)
-        bn_apply_kernel<true, false><<<blocks, 256, smem, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, nvec, Cp, relu);
+        bn_apply_kernel<true, false><<<blocks, 256, 0, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, rows, Cp, R, relu);
     else if (residual)
-        bn_apply_kernel<false, true><<<blocks, 256, smem, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, nvec, Cp, relu);
+        bn_apply_kernel<false, true><<<blocks, 256, 0, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, rows, Cp, R, relu);
     else
-        bn_apply_kernel<false, false><<<blocks, 256, smem, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, nvec, Cp, relu);
+        bn_apply_kernel<false, false><<<blocks, 256, 0, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, rows, Cp, R, relu);
     ZSV_LAUNCH_CHECK("bn_apply_kernel");
     return ZSV_OK;
 }
@@ -699,13 +713,17 @@ extern "C" size_t zsv_bn_bwd_workspace(int C) {
     return ((size_t)kBwdMaxBlocks * 4 * Cp + 4 * Cp) * sizeof(float);
 }
 
-extern "C" int zsv_bn_bwd(const void* g, const void* out, int relu, const void* y, const float* mean,
+extern "C" int zsv_bn_bwd(const void* g, const void* out, int relu, const float* mask_scale, const float* mask_shift,
+                          const void* y, const float* mean,
                           const float* invstd, const float* gamma, const void* y2, const float* mean2,
                           const float* invstd2, const float* gamma2, void* dy, void* dy2, void* dz, float* dgamma,
                           float* dbeta, float* dgamma2, float* dbeta2, long long rows, int C, void* workspace,
                           size_t workspace_bytes, void* stream) {
     if (!g || !y || !mean || !invstd || !dy || !workspace) return fail(ZSV_ERR_BAD_ARG, "bn_bwd: null pointer");
-    if (relu && !out) return fail(ZSV_ERR_BAD_ARG, "bn_bwd: relu mask needs the forward output");
+    if (relu == 1 && !out) return fail(ZSV_ERR_BAD_ARG, "bn_bwd: relu mask needs the forward output");
+    if (relu == 2 && (!mask_scale || !mask_shift)) return fail(ZSV_ERR_BAD_ARG, "bn_bwd: relu=2 needs scale/shift");
+    if (relu < 0 || relu > 2) return fail(ZSV_ERR_BAD_ARG, "bn_bwd: relu must be 0, 1 or 2");
+    if (relu == 2 && y2) return fail(ZSV_ERR_BAD_ARG, "bn_bwd: mask recomputation is for single-branch units");
     if (y2 && (!mean2 || !invstd2 || !dy2)) return fail(ZSV_ERR_BAD_ARG, "bn_bwd: second branch incomplete");
     const int Cp = cpad(C);
     if (Cp > kMaxC) return fail(ZSV_ERR_UNSUPPORTED, "bn_bwd: more than %d channels", kMaxC);
@@ -729,21 +747,19 @@ extern "C" int zsv_bn_bwd(const void* g, const void* out, int relu, const void* 
     }
     if (smem_r > 160 * 1024) return fail(ZSV_ERR_UNSUPPORTED, "bn_bwd: reduction scratch too large");
     if (y2)
-        bn_bwd_reduce_kernel<true><<<nblocks, 256, smem_r, st>>>(gb, ob, relu, yb, mean, invstd, y2b, mean2, invstd2, rows, Cp, R, partial);
+        bn_bwd_reduce_kernel<true><<<nblocks, 256, smem_r, st>>>(gb, ob, relu, mask_scale, mask_shift, yb, mean, invstd, y2b, mean2, invstd2, rows, Cp, R, partial);
     else
-        bn_bwd_reduce_kernel<false><<<nblocks, 256, smem_r, st>>>(gb, ob, relu, yb, mean, invstd, y2b, mean2, invstd2, rows, Cp, R, partial);
+        bn_bwd_reduce_kernel<false><<<nblocks, 256, smem_r, st>>>(gb, ob, relu, mask_scale, mask_shift, yb, mean, invstd, y2b, mean2, invstd2, rows, Cp, R, partial);
     ZSV_LAUNCH_CHECK("bn_bwd_reduce_kernel");
     const int nq = y2 ? 4 : 2;
     bn_bwd_final_kernel<<<ceil_div(nq * Cp, 32), 1024, 0, st>>>(partial, nblocks, nq, C, Cp, sums, dgamma, dbeta, dgamma2, dbeta2);
     ZSV_LAUNCH_CHECK("bn_bwd_final_kernel");
-    const long long nvec = rows * V;
-    const int blocks = ew_blocks(nvec, 256 * 4);
-    const size_t smem_a = (size_t)9 * Cp * sizeof(float);
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((long long)sm_count() * 8, ceil_div_ll(rows, (long long)R * 2)));
     const float inv_count = (float)(1.0 / (double)rows);
     if (y2)
-        bn_bwd_apply_kernel<true><<<blocks, 256, smem_a, st>>>(gb, ob, relu, yb, mean, invstd, gamma, y2b, mean2, invstd2, gamma2, sums, (__nv_bfloat16*)dy, (__nv_bfloat16*)dy2, (__nv_bfloat16*)dz, nvec, C, Cp, inv_count);
+        bn_bwd_apply_kernel<true><<<blocks, 256, 0, st>>>(gb, ob, relu, mask_scale, mask_shift, yb, mean, invstd, gamma, y2b, mean2, invstd2, gamma2, sums, (__nv_bfloat16*)dy, (__nv_bfloat16*)dy2, (__nv_bfloat16*)dz, rows, C, Cp, R, inv_count);
     else
-        bn_bwd_apply_kernel<false><<<blocks, 256, smem_a, st>>>(gb, ob, relu, yb, mean, invstd, gamma, y2b, mean2, invstd2, gamma2, sums, (__nv_bfloat16*)dy, (__nv_bfloat16*)dy2, (__nv_bfloat16*)dz, nvec, C, Cp, inv_count);
+        bn_bwd_apply_kernel<false><<<blocks, 256, 0, st>>>(gb, ob, relu, mask_scale, mask_shift, yb, mean, invstd, gamma, y2b, mean2, invstd2, gamma2, sums, (__nv_bfloat16*)dy, (__nv_bfloat16*)dy2, (__nv_bfloat16*)dz, rows, C, Cp, R, inv_count);
     ZSV_LAUNCH_CHECK("bn_bwd_apply_kernel");
     return ZSV_OK;
 }

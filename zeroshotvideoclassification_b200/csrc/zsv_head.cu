@@ -138,6 +138,18 @@ __global__ void linear_dgrad_kernel(const float* __restrict__ dy, const float* _
     }
 }
 
+// small problems (the R(2+1)D head): one thread per (b, k) keeps thousands of threads busy; W is re-read per batch row
+__global__ void linear_dgrad_small_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                          const float* __restrict__ act, float* __restrict__ dx, int B, int K, int J) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)B * K) return;
+    const int b = static_cast<int>(i / K), k = static_cast<int>(i - (long long)b * K);
+    float acc = 0.f;
+    for (int j = 0; j < J; ++j) acc = fmaf(dy[(long long)b * J + j], w[(long long)j * K + k], acc);
+    if (act && !(act[i] > 0.f)) acc = 0.f;
+    dx[i] = acc;
+}
+
 __global__ void relu_mask_kernel(const float* __restrict__ dy, const float* __restrict__ act, float* __restrict__ out,
                                  long long n) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -351,14 +363,14 @@ extern "C" int zsv_head_bwd(const float* demb, const float* emb, const float* on
         linear_wgrad_kernel<<<ceil_div(E * Hd, 256), 256, 0, st>>>(dout, hidden, dw2, db2, B, Hd, E);
         ZSV_LAUNCH_CHECK("linear_wgrad_kernel(2)");
     }
-    linear_dgrad_kernel<<<ceil_div(Hd, 128), 128, 0, st>>>(dout, w2, hidden, dh, B, Hd, E);
+    linear_dgrad_small_kernel<<<ceil_div(B * Hd, 128), 128, 0, st>>>(dout, w2, hidden, dh, B, Hd, E);
     ZSV_LAUNCH_CHECK("linear_dgrad_kernel(2)");
     if (dw1) {
         linear_wgrad_kernel<<<ceil_div(Hd * C, 256), 256, 0, st>>>(dh, pooled, dw1, db1, B, C, Hd);
         ZSV_LAUNCH_CHECK("linear_wgrad_kernel(1)");
     }
     if (dfeat) {
-        linear_dgrad_kernel<<<ceil_div(C, 128), 128, 0, st>>>(dh, w1, nullptr, dpooled, B, C, Hd);
+        linear_dgrad_small_kernel<<<ceil_div(B * C, 128), 128, 0, st>>>(dh, w1, nullptr, dpooled, B, C, Hd);
         ZSV_LAUNCH_CHECK("linear_dgrad_kernel(1)");
         const long long total = (long long)B * P * cpad(C);
         pool_bwd_kernel<<<(int)std::min<long long>(ceil_div_ll(total, 256), 148 * 8), 256, 0, st>>>(
@@ -394,7 +406,10 @@ extern "C" int zsv_linear_bwd(const float* dy, const float* x, const float* w, c
         ZSV_LAUNCH_CHECK("linear_wgrad_kernel");
     }
     if (dx) {
-        linear_dgrad_kernel<<<ceil_div(K, 128), 128, 0, st>>>(g, w, nullptr, dx, B, K, J);
+        if ((long long)K * J <= (1LL << 20))   // small weight matrix: parallelise over (b, k)
+            linear_dgrad_small_kernel<<<ceil_div(B * K, 128), 128, 0, st>>>(g, w, nullptr, dx, B, K, J);
+        else                                   // large (C3D fc6): stream W ceil(B/8) times
+            linear_dgrad_kernel<<<ceil_div(K, 128), 128, 0, st>>>(g, w, nullptr, dx, B, K, J);
         ZSV_LAUNCH_CHECK("linear_dgrad_kernel");
     }
     return ZSV_OK;

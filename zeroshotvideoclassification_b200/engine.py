@@ -112,8 +112,10 @@ class UnitRec:
     y: torch.Tensor                 # raw conv output (bf16)
     mean: torch.Tensor
     invstd: torch.Tensor
-    out: Optional[torch.Tensor]     # post-activation output (ReLU mask); None for a bare BN feeding a block tail
+    out: Optional[torch.Tensor]     # post-activation output; None for a bare BN feeding a block tail
     relu: bool
+    scale: Optional[torch.Tensor] = None   # forward scale / shift: backward recomputes the ReLU mask from y with them
+    shift: Optional[torch.Tensor] = None
 
 
 @dataclass
@@ -154,7 +156,7 @@ class BackboneRunner:
             scale, shift = ops.bn_eval_scale_shift(spec.cout, gamma, beta, rm, rv)
             mean = invstd = None
         out = ops.bn_apply(y, scale, shift, spec.cout, relu) if apply_now else None
-        rec = UnitRec(spec, op, x, wd, y, mean, invstd, out, relu) if self.need_grad else None
+        rec = UnitRec(spec, op, x, wd, y, mean, invstd, out, relu, scale, shift) if self.need_grad else None
         return out, y, (scale, shift), rec, (op.To, op.Ho, op.Wo)
 
     def forward(self, x_ncdhw: torch.Tensor) -> torch.Tensor:
@@ -199,8 +201,9 @@ class BackboneRunner:
 
     def _unit_bwd(self, rec: UnitRec, gin, grads, want, addend=None, need_dx: bool = True):
         """gin: gradient w.r.t. rec.out (post BN/ReLU).  Returns the gradient w.r.t. rec.x."""
-        dy, _, _, dgamma, dbeta, _, _ = ops.bn_bwd(gin, rec.out, rec.relu, rec.y, rec.mean, rec.invstd,
-                                                   self.t[rec.spec.bn + ".weight"], rec.spec.cout)
+        dy, _, _, dgamma, dbeta, _, _ = ops.bn_bwd(gin, None, 2 if rec.relu else 0, rec.y, rec.mean, rec.invstd,
+                                                   self.t[rec.spec.bn + ".weight"], rec.spec.cout,
+                                                   mask_scale=rec.scale, mask_shift=rec.shift)
         grads[rec.spec.bn + ".weight"] = dgamma
         grads[rec.spec.bn + ".bias"] = dbeta
         return self._conv_bwd(rec, dy, grads, want, addend, need_dx)

@@ -191,9 +191,11 @@ def bn_apply(y, scale, shift, channels: int, relu: bool, y2=None, scale2=None, s
     return out
 
 
-def bn_bwd(g, out, relu: bool, y, mean, invstd, gamma, channels: int, y2=None, mean2=None, invstd2=None, gamma2=None,
-           want_dz: bool = False):
-    """Returns (dy, dy2, dz, dgamma, dbeta, dgamma2, dbeta2)."""
+def bn_bwd(g, out, relu, y, mean, invstd, gamma, channels: int, y2=None, mean2=None, invstd2=None, gamma2=None,
+           want_dz: bool = False, mask_scale=None, mask_shift=None):
+    """Returns (dy, dy2, dz, dgamma, dbeta, dgamma2, dbeta2).  relu: False/0, True/1 (mask from `out`) or 2 (mask
+    recomputed from y with the forward's scale/shift)."""
+    relu = int(relu)
     lib = _lib.load()
     rows = y.numel() // y.shape[-1]
     dy = torch.empty_like(y)
@@ -203,7 +205,8 @@ def bn_bwd(g, out, relu: bool, y, mean, invstd, gamma, channels: int, y2=None, m
     ws_bytes = lib.zsv_bn_bwd_workspace(channels)
     ws = workspace(ws_bytes, y.device, "bn_bwd")
     has2 = y2 is not None
-    check(lib.zsv_bn_bwd(ptr(g), ptr(out) if relu else None, int(relu), ptr(y), ptr(mean), ptr(invstd), ptr(gamma),
+    check(lib.zsv_bn_bwd(ptr(g), ptr(out) if relu == 1 else None, relu, ptr(mask_scale), ptr(mask_shift), ptr(y),
+                         ptr(mean), ptr(invstd), ptr(gamma),
                          ptr(y2), ptr(mean2), ptr(invstd2), ptr(gamma2), ptr(dy), ptr(dy2), ptr(dz), ptr(dgb[0]),
                          ptr(dgb[1]), ptr(dgb[2]) if has2 else None, ptr(dgb[3]) if has2 else None, rows, channels,
                          ptr(ws), ws.numel(), _stream()), "zsv_bn_bwd")
