@@ -384,12 +384,15 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                     if (leader) {
                         const uint32_t sa = base + stage * stageBytes;
                         const uint32_t a_lo = umma_desc_lo(sa), b_lo = umma_desc_lo(sa + kPanelBytes);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (k < ksteps) {
-                                umma_bf16_lohi(tacc, a_lo + 2u * k, dhi, b_lo + 2u * k, dhi, idesc, acc);
-                                acc = 1;
-                            }
+                        umma_bf16_lohi(tacc, a_lo, dhi, b_lo, dhi, idesc, acc);
+                        acc = 1;
+                        if (ksteps == 4) {   // common case: straight-line, constant accumulate flag
+                            umma_bf16_lohi(tacc, a_lo + 2u, dhi, b_lo + 2u, dhi, idesc, 1u);
+                            umma_bf16_lohi(tacc, a_lo + 4u, dhi, b_lo + 4u, dhi, idesc, 1u);
+                            umma_bf16_lohi(tacc, a_lo + 6u, dhi, b_lo + 6u, dhi, idesc, 1u);
+                        } else {
+                            for (int k = 1; k < ksteps; ++k)
+                                umma_bf16_lohi(tacc, a_lo + 2u * k, dhi, b_lo + 2u * k, dhi, idesc, 1u);
                         }
                         umma_commit(barEmpty + 8u * stage);
                     }
@@ -621,12 +624,15 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                         uint32_t b_lo = b_chunk_lo + static_cast<uint32_t>(P.tap0 + cp * P.tap_dcp) * tap_bytes16;
                         const uint32_t b_step = static_cast<uint32_t>(P.tap_dsh) * tap_bytes16;   // may wrap (negative step)
                         for (int sh = 0; sh < P.S; ++sh) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                if (k < ksteps) {
-                                    umma_bf16_lohi(tacc, a_lo + 2u * k, dhi, b_lo + 2u * k, dhi, idesc, acc);
-                                    acc = 1;
-                                }
+                            umma_bf16_lohi(tacc, a_lo, dhi, b_lo, dhi, idesc, acc);
+                            acc = 1;
+                            if (ksteps == 4) {   // common case: straight-line, constant accumulate flag
+                                umma_bf16_lohi(tacc, a_lo + 2u, dhi, b_lo + 2u, dhi, idesc, 1u);
+                                umma_bf16_lohi(tacc, a_lo + 4u, dhi, b_lo + 4u, dhi, idesc, 1u);
+                                umma_bf16_lohi(tacc, a_lo + 6u, dhi, b_lo + 6u, dhi, idesc, 1u);
+                            } else {
+                                for (int k = 1; k < ksteps; ++k)
+                                    umma_bf16_lohi(tacc, a_lo + 2u * k, dhi, b_lo + 2u * k, dhi, idesc, 1u);
                             }
                             a_lo += shift16;
                             b_lo += b_step;
@@ -1175,6 +1181,7 @@ int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtenso
         stages = 8;
         while (stages > 2 && igemm_smem_bytes(a.bn_tile, stages, nstg) > 226 * 1024) --stages;
     }
+    if (const char* e = getenv("ZSV_DEBUG_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));
     a.nstg = nstg;
     a.stages = stages;
     a.tmem_cols = 2 * pow2_cols(a.bn_tile);   // two accumulator buffers
@@ -1264,7 +1271,8 @@ HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int k
     const int ntaps = kt * kh * kw;
     const int cols16 = (cols + 15) & ~15;
     // N tiling: origins step by multiples of 64 (output panels), the last tile takes the remainder
-    for (int nt = 1; nt <= 4; ++nt) {
+    const int max_nt = getenv("ZSV_DEBUG_HALO_NSPLIT") ? 4 : 1;
+    for (int nt = 1; nt <= max_nt; ++nt) {
         int n_step, bn;
         if (nt == 1) {
             n_step = bn = cols16;
@@ -1288,6 +1296,10 @@ HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int k
         }
         if (nstg < 1) continue;
         stages = std::min(stages, 8);
+        if (const char* e = getenv("ZSV_DEBUG_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));
+        if (const char* e = getenv("ZSV_DEBUG_NSTG")) {
+            if (atoi(e) == 1 && nstg == 2) nstg = 1;
+        }
         p.stages = stages;
         p.nstg = nstg;
         p.bn_tile = bn;

@@ -284,29 +284,47 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* _
         is2[j] = kHasY2 ? invstd2[c0 + j] : 0.f;
     }
     if (active) {
-        for (long long r = (long long)blockIdx.x * R + rl; r < rows; r += (long long)gridDim.x * R) {
-            const long long e = r * Cp + c0;
-            float gz[8], f[8];
-            unpack8(*reinterpret_cast<const uint4*>(g + e), gz);
-            if (relu == 1) {
-                unpack8(*reinterpret_cast<const uint4*>(out + e), f);
+        constexpr int U = 2;   // rows in flight per thread
+        const long long rstride = (long long)gridDim.x * R;
+        for (long long r0 = (long long)blockIdx.x * R + rl; r0 < rows; r0 += U * rstride) {
+            uint4 vg[U], vo[U], vy[U], vy2[U];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) gz[j] = f[j] > 0.f ? gz[j] : 0.f;
+            for (int u = 0; u < U; ++u) {
+                const long long r = r0 + u * rstride;
+                if (r < rows) {
+                    const long long e = r * Cp + c0;
+                    vg[u] = *reinterpret_cast<const uint4*>(g + e);
+                    if (relu == 1) vo[u] = *reinterpret_cast<const uint4*>(out + e);
+                    vy[u] = *reinterpret_cast<const uint4*>(y + e);
+                    if (kHasY2) vy2[u] = *reinterpret_cast<const uint4*>(y2 + e);
+                }
             }
-            unpack8(*reinterpret_cast<const uint4*>(y + e), f);
-            if (relu == 2) {   // ReLU mask recomputed from the pre-activation: saves re-reading the forward output
 #pragma unroll
-                for (int j = 0; j < 8; ++j) gz[j] = fmaf(f[j], msc[j], msh[j]) > 0.f ? gz[j] : 0.f;
-            }
+            for (int u = 0; u < U; ++u) {
+                const long long r = r0 + u * rstride;
+                if (r >= rows) break;
+                float gz[8], f[8];
+                unpack8(vg[u], gz);
+                if (relu == 1) {
+                    unpack8(vo[u], f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                a1[j] += gz[j];
-                a2[j] = fmaf(gz[j], (f[j] - mu[j]) * is[j], a2[j]);
-            }
-            if (kHasY2) {
-                unpack8(*reinterpret_cast<const uint4*>(y2 + e), f);
+                    for (int j = 0; j < 8; ++j) gz[j] = f[j] > 0.f ? gz[j] : 0.f;
+                }
+                unpack8(vy[u], f);
+                if (relu == 2) {   // ReLU mask recomputed from the pre-activation: saves re-reading the forward output
 #pragma unroll
-                for (int j = 0; j < 8; ++j) b2[j] = fmaf(gz[j], (f[j] - mu2[j]) * is2[j], b2[j]);
+                    for (int j = 0; j < 8; ++j) gz[j] = fmaf(f[j], msc[j], msh[j]) > 0.f ? gz[j] : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    a1[j] += gz[j];
+                    a2[j] = fmaf(gz[j], (f[j] - mu[j]) * is[j], a2[j]);
+                }
+                if (kHasY2) {
+                    unpack8(vy2[u], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) b2[j] = fmaf(gz[j], (f[j] - mu2[j]) * is2[j], b2[j]);
+                }
             }
         }
     }
