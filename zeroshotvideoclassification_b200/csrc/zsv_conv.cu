@@ -863,8 +863,44 @@ wgrad_mnmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
 }
 
 // dw[co][ci][tap] = sum_split ws[split][tap][ci][co]   (wfold: tap=(dt,dh), ci = dw*8 + c)
-__global__ void wgrad_finalize_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int ntaps,
-                                      int ci_pitch, int co_pitch, int Cin, int Cout, int wfold_kw, int wfold_taps) {
+// Transposing reduction through shared memory: a block owns 32 output channels x CI_T input channels x all taps; the
+// split partials are read coalesced along co, the state-dict layout is written in contiguous (ci, tap) runs per co.
+__global__ void __launch_bounds__(256)
+wgrad_finalize_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int ntaps, int ci_pitch,
+                      int co_pitch, int Cin, int Cout, int ci_tile) {
+    extern __shared__ float tile[];   // [ntaps][ci_tile][33]
+    const int co0 = blockIdx.x * 32;
+    const int ci0 = blockIdx.y * ci_tile;
+    const long long split_stride = (long long)ntaps * ci_pitch * co_pitch;
+    const int lane_co = threadIdx.x & 31;
+    const int row0 = threadIdx.x >> 5;    // 8 (tap, ci) rows per pass
+    const int nrows = ntaps * ci_tile;
+    for (int r = row0; r < nrows; r += 8) {
+        const int tap = r / ci_tile, ci = r - tap * ci_tile;
+        float acc = 0.f;
+        if (ci0 + ci < ci_pitch && co0 + lane_co < co_pitch) {
+            const float* p = ws + ((long long)tap * ci_pitch + ci0 + ci) * co_pitch + co0 + lane_co;
+            for (int sp = 0; sp < splits; ++sp) acc += p[sp * split_stride];
+        }
+        tile[(tap * ci_tile + ci) * 33 + lane_co] = acc;
+    }
+    __syncthreads();
+    const int run = ci_tile * ntaps;      // contiguous floats per output channel
+    for (int i = threadIdx.x; i < 32 * run; i += 256) {
+        const int co = i / run;
+        const int j = i - co * run;       // j = ci * ntaps + tap
+        const int ci = j / ntaps, tap = j - ci * ntaps;
+        if (co0 + co < Cout && ci0 + ci < Cin)
+            dw[((long long)(co0 + co) * Cin + ci0 + ci) * ntaps + tap] = tile[(tap * ci_tile + ci) * 33 + co];
+    }
+}
+
+// Element-wise variant for small weight tensors reduced over MANY splits (layer 1, stem: one thread per element
+// keeps the whole GPU busy where the tiled kernel would only have a handful of blocks) and for the first-layer
+// W-folded layout (tap = (dt,dh), ci = dw*8 + c).
+__global__ void wgrad_finalize_small_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int ntaps,
+                                            int ci_pitch, int co_pitch, int Cin, int Cout, int wfold_kw,
+                                            int wfold_taps) {
     const long long total = (long long)ntaps * ci_pitch * co_pitch;
     const long long split_stride = total;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -1720,10 +1756,18 @@ extern "C" int zsv_conv3d_wgrad(const zsv_conv_desc* d, const void* x, const voi
     wgrad_mnmajor_kernel<<<grid, 192, smem, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, a);
     ZSV_LAUNCH_CHECK("wgrad_mnmajor_kernel");
 
-    const long long total = (long long)s.ftaps * p.ci_pitch * p.co_pitch;
-    const int blocks = (int)std::min<long long>(ceil_div_ll(total, 256), 148 * 8);
-    wgrad_finalize_kernel<<<blocks, 256, 0, st>>>((const float*)workspace, dw, p.splits, s.ftaps, p.ci_pitch,
-                                                  p.co_pitch, d->Cin, d->Cout, s.wfold ? d->kw : 0, s.ntaps);
+    const long long wtotal = (long long)s.ftaps * p.ci_pitch * p.co_pitch;
+    if (s.wfold || wtotal < (1LL << 22)) {
+        const int blocks = (int)std::min<long long>(ceil_div_ll(wtotal, 256), 148 * 8);
+        wgrad_finalize_small_kernel<<<blocks, 256, 0, st>>>((const float*)workspace, dw, p.splits, s.ftaps, p.ci_pitch,
+                                                            p.co_pitch, d->Cin, d->Cout, s.wfold ? d->kw : 0, s.ntaps);
+    } else {
+        const int ci_tile = s.ftaps <= 9 ? 32 : 8;
+        const size_t fsm = (size_t)s.ftaps * ci_tile * 33 * sizeof(float);
+        dim3 fgrid(ceil_div(d->Cout, 32), ceil_div(d->Cin, ci_tile));
+        wgrad_finalize_kernel<<<fgrid, 256, fsm, st>>>((const float*)workspace, dw, p.splits, s.ftaps, p.ci_pitch,
+                                                       p.co_pitch, d->Cin, d->Cout, ci_tile);
+    }
     ZSV_LAUNCH_CHECK("wgrad_finalize_kernel");
     return ZSV_OK;
 }
