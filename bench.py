@@ -26,6 +26,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION/INFO; stdout must carry exactly one JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("ZSV_KEEP_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "R(2+1)D-18 train clips/s (16x112^2, bf16)"
 FLOP_PER_CLIP = 242.449e9          # fwd + dgrad + wgrad, SURVEY.md section 8(d) (no dgrad for stem.0)
