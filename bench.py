@@ -30,6 +30,28 @@ if ROOT not in sys.path:
 if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("ZSV_KEEP_NCCL_DEBUG"):
     os.environ["NCCL_DEBUG"] = "WARN"
 
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    """Route fd 1 to stderr while libraries (NCCL banners, warnings) may print; the JSON line goes to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    line = json.dumps(obj) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line)
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, line.encode())
+
+
 METRIC = "R(2+1)D-18 train clips/s (16x112^2, bf16)"
 FLOP_PER_CLIP = 242.449e9          # fwd + dgrad + wgrad, SURVEY.md section 8(d) (no dgrad for stem.0)
 N_TRAIN_CLASSES = 664              # train-time class table (Kinetics after the tau-filter, any C <= 700)
@@ -167,7 +189,7 @@ def run_reference(args):
         "note": "oracle/ port of the reference path (the Python reference cannot travel to the GPU box); "
                 "torch CPU kernels, all host threads",
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -306,9 +328,9 @@ def run_b200(args):
 
     if args.quick:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world,
-                              "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_per_step, "quick": True,
-                              "roofline": roofline, "gpu_launches": launches, "clocks": clocks}))
+            emit({"metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world,
+                  "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_per_step, "quick": True,
+                  "roofline": roofline, "gpu_launches": launches, "clocks": clocks})
         return
 
     # ---- timed region 2: end to end with host buffers ----
@@ -361,7 +383,7 @@ def run_b200(args):
     }
     if sync is not None:
         line["allreduce_bytes_per_step"] = sync.bytes_reduced / (n_warm + 2 * args.steps + 2)
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -377,6 +399,7 @@ def main():
     ap.add_argument("--quick", action="store_true",
                     help="profiling aid (ncu): honour --warmup below 3, skip the e2e and CPU-baseline legs")
     args = ap.parse_args()
+    _capture_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
