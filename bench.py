@@ -268,8 +268,10 @@ def run_b200(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         loss = step(x_dev, z_dev)
+    host_ms_per_step = 1e3 * (time.perf_counter() - t_host0) / args.steps    # enqueue time, no synchronisation
     ev1.record()
     barrier()
     launches = _lib.launch_count() - launches0
@@ -330,7 +332,8 @@ def run_b200(args):
         if rank == 0:
             emit({"metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world,
                   "steps": args.steps, "warmup": n_warm, "ms_per_step": ms_per_step, "quick": True,
-                  "roofline": roofline, "gpu_launches": launches, "clocks": clocks})
+                  "roofline": roofline, "gpu_launches": launches, "clocks": clocks,
+                  "host_enqueue_ms_per_step": host_ms_per_step})
         return
 
     # ---- timed region 2: end to end with host buffers ----
@@ -379,7 +382,7 @@ def run_b200(args):
                    "l2": "per-step working set (~6 GB of activations) is far larger than the 126 MB L2; no flush needed",
                    "loss_scaling": "none (bf16)", "weights": "random init (resnet.py:226-236)"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "final_loss": final_loss,
+        "final_loss": final_loss, "host_enqueue_ms_per_step": host_ms_per_step,
     }
     if sync is not None:
         line["allreduce_bytes_per_step"] = sync.bytes_reduced / (n_warm + 2 * args.steps + 2)
