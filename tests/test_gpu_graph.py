@@ -1,0 +1,74 @@
+"""GraphedStep: the training iteration replayed as one CUDA graph must be the same arithmetic as the iteration
+enqueued kernel by kernel (main.py:170-207), must not advance training while capturing, and must fall back to the
+eager step for ragged batches (main.py:156-158 filters broken samples)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(seed=0):
+    from zeroshotvideoclassification_b200 import video_models as vm
+    torch.manual_seed(seed)
+    model = vm.get_network(vm.default_opt("r2plus1d_18")).cuda().train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
+    crit = torch.nn.MSELoss()
+
+    def step(X, Z):
+        opt.zero_grad(set_to_none=True)
+        emb, _ = model(X)
+        loss = crit(emb, Z)
+        loss.backward()
+        opt.step()
+        return loss
+
+    return model, opt, step
+
+
+def _data(B, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    xs = [torch.randn(B, 1, 3, 8, 64, 64, generator=g) for _ in range(3)]
+    cls = F.normalize(torch.randn(51, 300, generator=g))
+    zs = [cls[torch.randint(0, 51, (B,), generator=g)] for _ in range(3)]
+    return xs, zs
+
+
+def test_graphed_step_matches_eager_and_keeps_state():
+    from zeroshotvideoclassification_b200.graph import GraphedStep
+    xs, zs = _data(2)
+
+    model_e, _, step_e = _make()
+    eager_losses = [float(step_e(x.cuda(), z.cuda())) for x, z in zip(xs, zs)]
+
+    model_g, opt_g, step_g = _make()
+    before = {k: v.detach().clone() for k, v in model_g.state_dict().items()}
+    gstep = GraphedStep(step_g, (xs[0], zs[0]), model=model_g, optimizer=opt_g)
+    # capturing (warm-up iterations included) left parameters, BN running statistics and Adam state untouched
+    for k, v in model_g.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    for st in opt_g.state.values():
+        assert float(st["step"]) == 0.0 and float(st["exp_avg"].abs().max()) == 0.0
+    assert gstep.launches_per_replay > 300
+
+    graph_losses = []
+    for x, z in zip(xs, zs):
+        loss = gstep(x.pin_memory(), z.pin_memory())      # host batches: H2D into the captured buffers
+        graph_losses.append(float(loss))
+    # deterministic kernels (no atomics): the replay is bit-identical to the eager iteration
+    assert graph_losses == eager_losses
+    sd_e, sd_g = model_e.state_dict(), model_g.state_dict()
+    for k in sd_e:
+        assert torch.equal(sd_e[k], sd_g[k]), k
+    assert gstep.replays == 3
+
+
+def test_graphed_step_ragged_batch_runs_eagerly():
+    from zeroshotvideoclassification_b200.graph import GraphedStep
+    xs, zs = _data(3)
+    model, opt, step = _make()
+    gstep = GraphedStep(step, (xs[0], zs[0]), model=model, optimizer=opt)
+    l_full = float(gstep(xs[0], zs[0]))
+    l_ragged = float(gstep(xs[1][:2], zs[1][:2]))        # one sample filtered out
+    assert gstep.replays == 1
+    assert l_full > 0 and l_ragged > 0 and l_ragged == l_ragged

@@ -195,23 +195,24 @@ __global__ void mse_kernel(const float* __restrict__ emb, const float* __restric
 // order scipy 1.18.1 compiles them (2-lane reduction: even-k and odd-k accumulators over the first D - D%2
 // terms, total = even + odd, then the odd tail term; see oracle/nearest_oracle.py).  Products of two fp32
 // values are exact in fp64, so fma == mul+add here.  cosine = dot / (nu*nv), clipped to +-1, d = 1 - cosine.
-// block = 128 threads (one class each per tile) x kRows embedding rows; distances staged in shared memory,
+// block = nt threads (one class each per tile) x R embedding rows; distances staged in shared memory,
 // then one warp per row extracts the k smallest (lowest index wins ties, NaN sorts last).
 // ------------------------------------------------------------------------------------------------
 constexpr int kKC = 32;  // k-chunk of the class tile staged in shared memory
 
 template <int R>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(R == 1 ? 1024 : 128)
 nearest_kernel(const float* __restrict__ emb, const float* __restrict__ cls, int N, int C, int D, int k,
                int64_t* __restrict__ idx_out, double* __restrict__ dist_out) {
     extern __shared__ double smd[];
     double* dist = smd;                                               // [R][C]
     double* nrm_e = dist + (size_t)R * C;                         // [R]
     float* s_e = reinterpret_cast<float*>(nrm_e + R);             // [R][D]
-    float* s_c = s_e + (size_t)R * D;                             // [128][kKC+1]
+    float* s_c = s_e + (size_t)R * D;                             // [nt][kKC+1]
+    const int nt = blockDim.x;                                    // classes per tile = threads per block
     const int i0 = blockIdx.x * R;
     const int tid = threadIdx.x;
-    for (int i = tid; i < R * D; i += 128) {
+    for (int i = tid; i < R * D; i += nt) {
         const int r = i / D, kk = i - r * D;
         s_e[i] = (i0 + r < N) ? emb[(long long)(i0 + r) * D + kk] : 0.f;
     }
@@ -232,7 +233,7 @@ nearest_kernel(const float* __restrict__ emb, const float* __restrict__ cls, int
         nrm_e[tid] = sqrt(s);
     }
     __syncthreads();
-    for (int j0 = 0; j0 < C; j0 += 128) {
+    for (int j0 = 0; j0 < C; j0 += nt) {
         const int j = j0 + tid;
         double acc0[R], acc1[R];  // even-k / odd-k accumulators
         double cc0 = 0.0, cc1 = 0.0;      // squared norm of this thread's class row, same order
@@ -240,7 +241,7 @@ nearest_kernel(const float* __restrict__ emb, const float* __restrict__ cls, int
         for (int r = 0; r < R; ++r) acc0[r] = acc1[r] = 0.0;
         for (int k0 = 0; k0 < D; k0 += kKC) {
             __syncthreads();
-            for (int i = tid; i < 128 * kKC; i += 128) {
+            for (int i = tid; i < nt * kKC; i += nt) {
                 const int jj = i / kKC, kk = i - jj * kKC;
                 s_c[jj * (kKC + 1) + kk] = (j0 + jj < C && k0 + kk < D) ? cls[(long long)(j0 + jj) * D + k0 + kk] : 0.f;
             }
@@ -279,9 +280,9 @@ nearest_kernel(const float* __restrict__ emb, const float* __restrict__ cls, int
         }
     }
     __syncthreads();
-    // selection: warp w handles rows w, w+4
+    // selection: warp w handles rows w, w + #warps, ...
     const int warp = tid >> 5, lane = tid & 31;
-    for (int r = warp; r < R; r += 4) {
+    for (int r = warp; r < R; r += (nt >> 5)) {
         if (i0 + r >= N) continue;
         double* dr = dist + (size_t)r * C;
         for (int sel = 0; sel < k; ++sel) {
@@ -447,7 +448,10 @@ extern "C" int zsv_nearest_class(const float* emb, const float* cls, int N, int 
     // few rows (train-time batch, main.py:183): one row per block so the grid still covers the SMs;
     // many rows (evaluation, main.py:321): 8 rows per block amortise the class-table traffic
     const int R = N <= 2048 ? 1 : 8;
-    const size_t smem = sizeof(double) * ((size_t)R * C + R) + sizeof(float) * ((size_t)R * D + 128 * (kKC + 1));
+    // R == 1: the fp64 chain of one (row, class) pair is sequential by construction (scipy's order), so the block is made
+    // as wide as the class table (up to 1024 threads) instead of walking 128-class tiles one after the other
+    const int nt = R == 1 ? std::min(1024, ceil_div(C, 128) * 128) : 128;
+    const size_t smem = sizeof(double) * ((size_t)R * C + R) + sizeof(float) * ((size_t)R * D + (size_t)nt * (kKC + 1));
     if (smem > 200 * 1024)
         return fail(ZSV_ERR_UNSUPPORTED, "nearest_class: class table too large for shared memory (%zu bytes)", smem);
     static bool attr_done = false;
@@ -457,7 +461,7 @@ extern "C" int zsv_nearest_class(const float* emb, const float* cls, int N, int 
         attr_done = true;
     }
     if (R == 1)
-        nearest_kernel<1><<<N, 128, smem, st>>>(emb, cls, N, C, D, k, idx_out, dist_out);
+        nearest_kernel<1><<<N, nt, smem, st>>>(emb, cls, N, C, D, k, idx_out, dist_out);
     else
         nearest_kernel<8><<<ceil_div(N, 8), 128, smem, st>>>(emb, cls, N, C, D, k, idx_out, dist_out);
     ZSV_LAUNCH_CHECK("nearest_kernel");

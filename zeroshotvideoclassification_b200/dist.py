@@ -30,6 +30,8 @@ class GradSync:
         self._cur: List[tuple] = []
         self._cur_bytes = 0
         self.bytes_reduced = 0
+        self.bytes_per_step = 0           # bytes all-reduced by the most recent backward pass
+        self._step_bytes = 0
 
     # called from the backward pass with fresh fp32 gradients
     def submit(self, grads: Dict[str, torch.Tensor]) -> None:
@@ -49,6 +51,7 @@ class GradSync:
         self._cur, self._cur_bytes = [], 0
         flat = torch.cat([g.reshape(-1) for _, g in items])
         self.bytes_reduced += flat.numel() * flat.element_size()
+        self._step_bytes += flat.numel() * flat.element_size()
         # SUM + scale keeps gloo (CPU tests) and NCCL on the same code path
         work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         self._pending.append((work, flat, items))
@@ -66,6 +69,7 @@ class GradSync:
                 out[name] = flat[off:off + n].view(g.shape)
                 off += n
         self._pending = []
+        self.bytes_per_step, self._step_bytes = self._step_bytes, 0
         return out
 
 
