@@ -71,6 +71,12 @@ size_t zsv_conv3d_packed_weight_bytes(const zsv_conv_desc* d, int which);
  * Either output may be NULL. */
 int zsv_conv3d_pack_weight(const zsv_conv_desc* d, const float* w, void* w_fprop, void* w_dgrad, void* stream);
 
+/* The same for n convolutions in one launch (all weights of a network are re-packed after every optimizer step,
+ * main.py:203): descs[n], w[n], w_fprop[n], w_dgrad[n] are HOST arrays of descriptors / device pointers; an output
+ * pointer may be NULL. */
+int zsv_conv3d_pack_weights(int n, const zsv_conv_desc* descs, const float* const* w, void* const* w_fprop,
+                            void* const* w_dgrad, void* stream);
+
 /* Number of rows of the per-tile BatchNorm partial-statistics buffers written by fprop. */
 int zsv_conv3d_stat_rows(const zsv_conv_desc* d);
 

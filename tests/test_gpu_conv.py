@@ -155,3 +155,32 @@ def test_fprop_full_size_layer1_linearity():
     # linearity: conv(2x) == 2 conv(x) exactly in bf16 (power-of-two scaling commutes with rounding)
     yb, _, _ = op.fprop((xa.float() * 2).to(torch.bfloat16), wf, stats=False)
     assert torch.equal(yb.float(), ya.float() * 2)
+
+
+def test_batched_weight_pack_matches_per_conv_pack():
+    """zsv_conv3d_pack_weights (one launch for a list of convolutions) writes the same bf16 images as
+    zsv_conv3d_pack_weight per convolution, including the W-folded first-layer image and a conv without dgrad image."""
+    import torch
+    from zeroshotvideoclassification_b200 import _lib, ops
+    g = torch.Generator().manual_seed(3)
+    geoms = [(3, 45, (1, 7, 7), (1, 2, 2), (0, 3, 3), _lib.X_WFOLD, False),
+             (45, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), _lib.X_NDHWC, True),
+             (64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), _lib.X_NDHWC, True),
+             (64, 230, (1, 3, 3), (1, 2, 2), (0, 1, 1), _lib.X_NDHWC, False),
+             (64, 128, (1, 1, 1), (2, 2, 2), (0, 0, 0), _lib.X_NDHWC, True)]
+    convs, ws, nd = [], [], []
+    for cin, cout, k, s, p, layout, need in geoms:
+        convs.append(ops.Conv3d(2, 8, 32, 32, cin, cout, k, s, p, layout))
+        ws.append(torch.randn(cout, cin, *k, generator=g).cuda())
+        nd.append(need)
+    plan = ops.PackPlan(convs, nd)
+    n0 = _lib.launch_count()
+    wfs, wds = plan.pack(ws)
+    assert _lib.launch_count() - n0 == 1
+    for c, w, need, wf, wd in zip(convs, ws, nd, wfs, wds):
+        wf1, wd1 = c.pack(w, need_dgrad=need)
+        assert torch.equal(wf.view(torch.int16), wf1.view(torch.int16))
+        if need:
+            assert torch.equal(wd.view(torch.int16), wd1.view(torch.int16))
+        else:
+            assert wd is None

@@ -10,17 +10,29 @@ sys.path.insert(0, ".")
 from zeroshotvideoclassification_b200 import ops
 
 
-def bench(fn, iters=20):
-    for _ in range(3):
+def bench(fn, iters=10):
+    """us per call, timed as a CUDA-graph replay of `iters` back-to-back calls (no host launch overhead in the number)."""
+    for _ in range(2):
         fn()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        fn()
+    for _ in range(3):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters * 1e3  # us
+    return e0.elapsed_time(e1) / (3 * iters) * 1e3  # us
 
 
 for spec in sys.argv[1:]:

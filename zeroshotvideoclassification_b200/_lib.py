@@ -43,6 +43,7 @@ SIGNATURES = {
     "zsv_conv3d_out_shape": (_I, [_DP, C.POINTER(C.c_int32)]),
     "zsv_conv3d_packed_weight_bytes": (_SZ, [_DP, _I]),
     "zsv_conv3d_pack_weight": (_I, [_DP, _P, _P, _P, _P]),
+    "zsv_conv3d_pack_weights": (_I, [_I, _P, _P, _P, _P, _P]),
     "zsv_conv3d_stat_rows": (_I, [_DP]),
     "zsv_conv3d_fprop": (_I, [_DP, _P, _P, _P, _P, _P, _P, _I, _P]),
     "zsv_conv3d_dgrad": (_I, [_DP, _P, _P, _P, _P, _P]),

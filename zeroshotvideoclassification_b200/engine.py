@@ -99,6 +99,37 @@ def _conv_for(spec: ConvSpec, N, T, H, W, layout=_lib.X_NDHWC) -> ops.Conv3d:
     return op
 
 
+_plan_cache: Dict[tuple, tuple] = {}
+
+
+def _network_plan(N, T, H, W, need_grad: bool):
+    """Geometry of every convolution for a clip batch of this shape (in all_conv_specs() order) and the one-launch
+    weight re-pack for them."""
+    key = (N, T, H, W, need_grad)
+    hit = _plan_cache.get(key)
+    if hit is not None:
+        return hit
+    convs, nd = {}, {}
+
+    def add(spec, dims, layout=_lib.X_NDHWC, need_dgrad=True):
+        op = _conv_for(spec, dims[0], dims[1], dims[2], dims[3], layout)
+        convs[spec.name], nd[spec.name] = op, need_grad and need_dgrad
+        return (dims[0], op.To, op.Ho, op.Wo)
+
+    d = add(STEM_SPECS[0], (N, T, H, W), _lib.X_WFOLD, need_dgrad=False)
+    d = add(STEM_SPECS[1], d)
+    for b in BLOCK_SPECS:
+        d_in = d
+        for c in b.convs:
+            d = add(c, d)
+        if b.downsample is not None:
+            add(b.downsample, d_in)
+    names = [c.name for c in all_conv_specs()]
+    plan = ops.PackPlan([convs[n] for n in names], [nd[n] for n in names])
+    _plan_cache[key] = (names, plan)
+    return names, plan
+
+
 # ----------------------------------------------------------------------------------------------------
 # tape records
 # ----------------------------------------------------------------------------------------------------
@@ -135,14 +166,18 @@ class BackboneRunner:
         self.need_grad = need_grad
         self.stem_recs: List[UnitRec] = []
         self.block_recs: List[BlockRec] = []
+        self.packed: Dict[str, tuple] = {}      # bf16 weight images of the whole network, packed in one launch
+        self.nbt: List[torch.Tensor] = []       # num_batches_tracked counters, bumped once per forward in one launch
 
     # -- forward building blocks -------------------------------------------------------------------
     def _unit(self, spec: ConvSpec, x: torch.Tensor, dims, relu: bool, apply_now: bool = True, layout=_lib.X_NDHWC,
               need_dgrad: bool = True):
         N, T, H, W = dims
         op = _conv_for(spec, N, T, H, W, layout)
-        w = self.t[spec.name + ".weight"]
-        wf, wd = op.pack(w, need_dgrad=self.need_grad and need_dgrad)
+        pk = self.packed.get(spec.name)
+        if pk is None:       # a unit driven on its own (block-level tests): pack just this convolution
+            pk = op.pack(self.t[spec.name + ".weight"], need_dgrad=self.need_grad and need_dgrad)
+        wf, wd = pk
         gamma, beta = self.t[spec.bn + ".weight"], self.t[spec.bn + ".bias"]
         rm, rv = self.t[spec.bn + ".running_mean"], self.t[spec.bn + ".running_var"]
         if self.train:
@@ -150,7 +185,7 @@ class BackboneRunner:
             scale, shift, mean, invstd = ops.bn_finalize(ps, pq, spec.cout, op.out_positions, gamma, beta, rm, rv)
             nbt = self.t.get(spec.bn + ".num_batches_tracked")
             if nbt is not None:
-                nbt.add_(1)
+                self.nbt.append(nbt)
         else:
             y, _, _ = op.fprop(x, wf, stats=False)
             scale, shift = ops.bn_eval_scale_shift(spec.cout, gamma, beta, rm, rv)
@@ -161,6 +196,9 @@ class BackboneRunner:
 
     def forward(self, x_ncdhw: torch.Tensor) -> torch.Tensor:
         N, _, T, H, W = x_ncdhw.shape
+        names, plan = _network_plan(N, T, H, W, self.need_grad)
+        wfs, wds = plan.pack([self.t[n + ".weight"] for n in names])
+        self.packed = {n: (wf, wd) for n, wf, wd in zip(names, wfs, wds)}
         s0 = STEM_SPECS[0]
         a = ops.repack_input(x_ncdhw, _lib.X_WFOLD, s0.padding[2])
         a, _, _, rec, (T1, H1, W1) = self._unit(s0, a, (N, T, H, W), True, layout=_lib.X_WFOLD, need_dgrad=False)
@@ -170,6 +208,8 @@ class BackboneRunner:
         dims = (N, T1, H1, W1)
         for b in BLOCK_SPECS:
             a, dims = self._block(b, a, dims)
+        if self.nbt:
+            torch._foreach_add_(self.nbt, 1)
         return a
 
     def _block(self, b: BlockSpec, x: torch.Tensor, dims):

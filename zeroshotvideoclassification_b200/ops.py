@@ -128,6 +128,51 @@ class Conv3d:
         return dw, db
 
 
+class PackPlan:
+    """Re-packs the weights of a fixed list of convolutions in ONE kernel launch (zsv_conv3d_pack_weights): after
+    every optimizer step (main.py:203) all 37 fp32 master weights of R(2+1)D-18 need fresh bf16 images."""
+
+    def __init__(self, convs, need_dgrad):
+        self.lib = _lib.load()
+        self.convs = list(convs)
+        n = self.n = len(self.convs)
+        self.descs = (ConvDesc * n)()
+        for i, c in enumerate(self.convs):
+            C.memmove(C.byref(self.descs[i]), C.byref(c.desc), C.sizeof(ConvDesc))
+        self.wf_off, self.wd_off, off = [], [], 0
+        for c, nd in zip(self.convs, need_dgrad):
+            self.wf_off.append(off)
+            off += (c.wf_bytes // 2 + 7) & ~7                 # 16-byte aligned images (TMA global address alignment)
+            if nd and c.wd_bytes:
+                self.wd_off.append(off)
+                off += (c.wd_bytes // 2 + 7) & ~7
+            else:
+                self.wd_off.append(None)
+        self.total = off
+        self.w_arr, self.wf_arr, self.wd_arr = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_void_p * n)()
+
+    def pack(self, weights):
+        """weights: fp32 CUDA tensors in conv order -> ([wf...], [wd or None...]) views of one bf16 buffer."""
+        dev = weights[0].device
+        buf = torch.empty(self.total, dtype=torch.bfloat16, device=dev)
+        base = buf.data_ptr()
+        keep = []
+        for i, w in enumerate(weights):
+            _require_cuda(w, "PackPlan.pack")
+            w = w.detach()
+            if w.dtype != torch.float32 or not w.is_contiguous():
+                w = w.float().contiguous()
+                keep.append(w)
+            self.w_arr[i] = w.data_ptr()
+            self.wf_arr[i] = base + 2 * self.wf_off[i]
+            self.wd_arr[i] = None if self.wd_off[i] is None else base + 2 * self.wd_off[i]
+        check(self.lib.zsv_conv3d_pack_weights(self.n, self.descs, self.w_arr, self.wf_arr, self.wd_arr, _stream()),
+              "zsv_conv3d_pack_weights")
+        wfs = [buf[o:o + c.wf_bytes // 2] for o, c in zip(self.wf_off, self.convs)]
+        wds = [None if o is None else buf[o:o + c.wd_bytes // 2] for o, c in zip(self.wd_off, self.convs)]
+        return wfs, wds
+
+
 # ------------------------------------------------------------------------------------------------
 # layout
 # ------------------------------------------------------------------------------------------------
