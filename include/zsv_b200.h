@@ -129,8 +129,10 @@ int zsv_ncdhw_to_ndhwc(const float* x, void* out, int N, int C, int T, int H, in
  * ---------------------------------------------------------------------------------------------- */
 /* Reduce per-tile partials to batch mean / biased variance; emit scale = gamma*invstd,
  * shift = beta - mean*scale, mean, invstd (all fp32 [cpad(C)]); update running_mean / running_var
- * (momentum, unbiased variance) in place when they are non-NULL.  Two-stage fp64 reduction through a
- * caller-provided workspace (zsv_bn_finalize_workspace bytes). */
+ * (momentum, unbiased variance) in place when they are non-NULL.  One launch: fp64 chunk sums, then the last block
+ * of each 32-channel group (ticket counter) finishes.  The caller-provided workspace (zsv_bn_finalize_workspace
+ * bytes) must have its first 1024 bytes ZERO before the first call; every call leaves them zero again, so calls
+ * that follow each other on one stream may share the workspace. */
 size_t zsv_bn_finalize_workspace(int C);
 int zsv_bn_finalize(const float* part_sum, const float* part_sq, int part_rows, int C, long long count,
                     const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum,

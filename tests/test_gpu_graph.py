@@ -72,3 +72,25 @@ def test_graphed_step_ragged_batch_runs_eagerly():
     l_ragged = float(gstep(xs[1][:2], zs[1][:2]))        # one sample filtered out
     assert gstep.replays == 1
     assert l_full > 0 and l_ragged > 0 and l_ragged == l_ragged
+
+
+def test_prefetch_pipeline_matches_direct_calls():
+    """prefetch() + step() (next batch uploaded on a copy stream during the current replay) gives the same training
+    trajectory as passing each batch to the step directly."""
+    from zeroshotvideoclassification_b200.graph import GraphedStep
+    xs, zs = _data(2)
+    model_a, opt_a, step_a = _make()
+    ga = GraphedStep(step_a, (xs[0], zs[0]), model=model_a, optimizer=opt_a)
+    direct = [float(ga(x, z)) for x, z in zip(xs, zs)]
+
+    model_b, opt_b, step_b = _make()
+    gb = GraphedStep(step_b, (xs[0], zs[0]), model=model_b, optimizer=opt_b)
+    pinned = [(x.pin_memory(), z.pin_memory()) for x, z in zip(xs, zs)]
+    gb.prefetch(*pinned[0])
+    piped = []
+    for i in range(3):
+        loss = gb()
+        if i + 1 < 3:
+            gb.prefetch(*pinned[i + 1])
+        piped.append(float(loss))
+    assert piped == direct

@@ -1,6 +1,5 @@
-{
-echo "== N=4 (L2 resident) EPI=7"; ZSV_DEBUG_EPI=7 python tools/bench_conv.py 4,16,56,56,45,64,3,1,1,1,1,1,1,0,0 4,16,56,56,144,64,3,1,1,1,1,1,1,0,0 4,16,56,56,64,64,3,1,1,1,1,1,1,0,0
-echo "== N=4 (L2 resident) EPI=0"; python tools/bench_conv.py 4,16,56,56,45,64,3,1,1,1,1,1,1,0,0 4,16,56,56,144,64,3,1,1,1,1,1,1,0,0 4,16,56,56,64,64,3,1,1,1,1,1,1,0,0
-echo "== N=22 EPI=0"; python tools/bench_conv.py 22,16,56,56,45,64,3,1,1,1,1,1,1,0,0 22,16,56,56,144,64,3,1,1,1,1,1,1,0,0  22,16,56,56,64,144,1,3,3,1,1,1,0,1,1
-} > gpurun_out/conv_exp5.log 2>&1
-cat gpurun_out/conv_exp5.log
+set -x
+python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/pytest_gpu.log
+python bench.py --steps 20 --warmup 5 --layer-table --no-cpu-baseline > gpurun_out/bench4.json 2> gpurun_out/bench4.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv python bench.py --quick --no-graph --steps 1 --warmup 1 > gpurun_out/ncu.log 2>&1
+tail -4 gpurun_out/pytest_gpu.log; cat gpurun_out/bench4.json

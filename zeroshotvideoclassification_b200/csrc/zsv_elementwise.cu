@@ -84,13 +84,22 @@ __global__ void ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ x, float
 //   stage 1 (grid = 32-channel groups x row chunks, block = 32 channels x 32 row lanes): fp64 chunk sums
 //   stage 2 (block = 32 channels x 16 chunk lanes): total, mean / var / invstd, scale / shift, running stats
 // ------------------------------------------------------------------------------------------------
+// One kernel: every block reduces its chunk of partial rows for 32 channels (fp64), publishes the chunk sums and takes
+// a ticket; the LAST block of a channel group (all chunks published) turns them into batch statistics.  The ticket
+// counters live in the caller's workspace, start at zero and are reset by the finishing block, so back-to-back calls
+// on one stream can share them.  The order of the additions is fixed, so the result is deterministic.
 __global__ void __launch_bounds__(1024)
-bn_finalize_stage1_kernel(const float* __restrict__ part_sum, const float* __restrict__ part_sq, int part_rows,
-                          int Cp, int rows_per_chunk, double* __restrict__ chunk) {
+bn_finalize_kernel(const float* __restrict__ part_sum, const float* __restrict__ part_sq, int part_rows, int C, int Cp,
+                   int rows_per_chunk, double* __restrict__ chunk, unsigned int* __restrict__ tickets, double count,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ running_mean,
+                   float* __restrict__ running_var, float momentum, float eps, float* __restrict__ scale,
+                   float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ invstd_out) {
     __shared__ double sh1[32][33];
     __shared__ double sh2[32][33];
+    __shared__ int last;
     const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
+    const int nchunks = gridDim.y;
     const int r0 = blockIdx.y * rows_per_chunk;
     const int r1 = min(part_rows, r0 + rows_per_chunk);
     double a = 0.0, b = 0.0;
@@ -111,33 +120,27 @@ bn_finalize_stage1_kernel(const float* __restrict__ part_sum, const float* __res
         }
         chunk[((long long)blockIdx.y * 2 + 0) * Cp + c] = a;
         chunk[((long long)blockIdx.y * 2 + 1) * Cp + c] = b;
+        __threadfence();   // publish before the ticket
     }
-}
-
-__global__ void __launch_bounds__(512)
-bn_finalize_stage2_kernel(const double* __restrict__ chunk, int nchunks, int C, int Cp, double count,
-                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                          float* __restrict__ running_mean, float* __restrict__ running_var, float momentum,
-                          float eps, float* __restrict__ scale, float* __restrict__ shift,
-                          float* __restrict__ mean_out, float* __restrict__ invstd_out) {
-    __shared__ double sh1[16][33];
-    __shared__ double sh2[16][33];
-    const int cl = threadIdx.x & 31;
-    const int rl = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cl;
-    double a = 0.0, b = 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(&tickets[blockIdx.x], 1u) == (unsigned)(nchunks - 1));
+    __syncthreads();
+    if (!last) return;
+    __threadfence();       // the other blocks' chunk sums are visible from here on
+    a = b = 0.0;
     if (c < Cp) {
-        for (int r = rl; r < nchunks; r += 16) {
-            a += chunk[((long long)r * 2 + 0) * Cp + c];
-            b += chunk[((long long)r * 2 + 1) * Cp + c];
+        for (int r = rl; r < nchunks; r += 32) {
+            a += __ldcg(chunk + ((long long)r * 2 + 0) * Cp + c);
+            b += __ldcg(chunk + ((long long)r * 2 + 1) * Cp + c);
         }
     }
     sh1[rl][cl] = a;
     sh2[rl][cl] = b;
     __syncthreads();
+    if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;
     if (rl == 0 && c < Cp) {
         double s1 = 0.0, s2 = 0.0;
-        for (int r = 0; r < 16; ++r) {
+        for (int r = 0; r < 32; ++r) {
             s1 += sh1[r][cl];
             s2 += sh2[r][cl];
         }
@@ -148,8 +151,7 @@ bn_finalize_stage2_kernel(const double* __restrict__ chunk, int nchunks, int C, 
             const double invstd = 1.0 / sqrt(var + (double)eps);
             const float g = gamma ? gamma[c] : 1.f;
             const float bt = beta ? beta[c] : 0.f;
-            const float sc = (float)((double)g * invstd);
-            scale[c] = sc;
+            scale[c] = (float)((double)g * invstd);
             shift[c] = (float)((double)bt - mean * (double)g * invstd);
             mean_out[c] = (float)mean;
             invstd_out[c] = (float)invstd;
@@ -658,8 +660,10 @@ namespace {
 constexpr int kFinalizeMaxChunks = 64;
 }
 
+constexpr size_t kTicketBytes = 1024;   // ticket counters at the start of the workspace (one per 32-channel group)
+
 extern "C" size_t zsv_bn_finalize_workspace(int C) {
-    return (size_t)kFinalizeMaxChunks * 2 * cpad(C) * sizeof(double);
+    return kTicketBytes + (size_t)kFinalizeMaxChunks * 2 * cpad(C) * sizeof(double);
 }
 
 extern "C" int zsv_bn_finalize(const float* part_sum, const float* part_sq, int part_rows, int C, long long count,
@@ -676,14 +680,13 @@ extern "C" int zsv_bn_finalize(const float* part_sum, const float* part_sq, int 
     int nchunks = std::max(1, std::min(kFinalizeMaxChunks, ceil_div(part_rows, 128)));
     const int rows_per_chunk = ceil_div(part_rows, nchunks);
     nchunks = ceil_div(part_rows, rows_per_chunk);
-    double* chunk = (double*)workspace;
-    bn_finalize_stage1_kernel<<<dim3(ceil_div(Cp, 32), nchunks), 1024, 0, st>>>(part_sum, part_sq, part_rows, Cp,
-                                                                                 rows_per_chunk, chunk);
-    ZSV_LAUNCH_CHECK("bn_finalize_stage1_kernel");
-    bn_finalize_stage2_kernel<<<ceil_div(Cp, 32), 512, 0, st>>>(chunk, nchunks, C, Cp, (double)count, gamma, beta,
-                                                                running_mean, running_var, momentum, eps, scale, shift,
-                                                                mean, invstd);
-    ZSV_LAUNCH_CHECK("bn_finalize_stage2_kernel");
+    if (ceil_div(Cp, 32) * sizeof(unsigned int) > kTicketBytes) return fail(ZSV_ERR_UNSUPPORTED, "bn_finalize: too many channels");
+    unsigned int* tickets = (unsigned int*)workspace;
+    double* chunk = (double*)((char*)workspace + kTicketBytes);
+    bn_finalize_kernel<<<dim3(ceil_div(Cp, 32), nchunks), 1024, 0, st>>>(
+        part_sum, part_sq, part_rows, C, Cp, rows_per_chunk, chunk, tickets, (double)count, gamma, beta, running_mean,
+        running_var, momentum, eps, scale, shift, mean, invstd);
+    ZSV_LAUNCH_CHECK("bn_finalize_kernel");
     return ZSV_OK;
 }
 

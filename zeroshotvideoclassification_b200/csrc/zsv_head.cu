@@ -31,7 +31,8 @@ __global__ void pool_kernel(const __nv_bfloat16* __restrict__ feat, float* __res
     pooled[(long long)b * C + c] = acc / (float)P;
 }
 
-// out[b][j] = act(sum_k x[b][k] * w[j][k] + bias[j]); one warp per output feature j, 8 batch rows per pass
+// out[b][j] = act(sum_k x[b][k] * w[j][k] + bias[j]); one warp per output feature j, 8 batch rows per pass.
+// gridDim.y > 1 spreads the 8-row groups over blocks (small weight matrices: more warps instead of fewer weight reads).
 __global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                   const float* __restrict__ bias, float* __restrict__ out, int B, int K, int J,
                                   int relu) {
@@ -39,7 +40,7 @@ __global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __re
     const int lane = threadIdx.x & 31;
     if (warp >= J) return;
     const float* wr = w + (long long)warp * K;
-    for (int b0 = 0; b0 < B; b0 += 8) {
+    for (int b0 = blockIdx.y * 8; b0 < B; b0 += 8 * gridDim.y) {
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -138,16 +139,38 @@ __global__ void linear_dgrad_kernel(const float* __restrict__ dy, const float* _
     }
 }
 
-// small problems (the R(2+1)D head): one thread per (b, k) keeps thousands of threads busy; W is re-read per batch row
-__global__ void linear_dgrad_small_kernel(const float* __restrict__ dy, const float* __restrict__ w,
-                                          const float* __restrict__ act, float* __restrict__ dx, int B, int K, int J) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= (long long)B * K) return;
-    const int b = static_cast<int>(i / K), k = static_cast<int>(i - (long long)b * K);
-    float acc = 0.f;
-    for (int j = 0; j < J; ++j) acc = fmaf(dy[(long long)b * J + j], w[(long long)j * K + k], acc);
-    if (act && !(act[i] > 0.f)) acc = 0.f;
-    dx[i] = acc;
+// dx for small weight matrices: block = 32 k lanes x 8 slices of the J reduction, 8 batch rows; the slices are combined
+// in fixed order through shared memory.  grid = (ceil(K/32), ceil(B/8)).
+__global__ void __launch_bounds__(256)
+linear_dgrad_tile_kernel(const float* __restrict__ dy, const float* __restrict__ w, const float* __restrict__ act,
+                         float* __restrict__ dx, int B, int K, int J) {
+    __shared__ float red[8][8][33];
+    const int kl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int k = blockIdx.x * 32 + kl;
+    const int b0 = blockIdx.y * 8;
+    const int jper = (J + 7) >> 3;
+    const int j0 = sl * jper, j1 = min(J, j0 + jper);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 4
+    for (int j = j0; j < j1; ++j) {
+        const float wv = k < K ? w[(long long)j * K + k] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (b0 + i < B) acc[i] = fmaf(dy[(long long)(b0 + i) * J + j], wv, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[sl][i][kl] = acc[i];
+    __syncthreads();
+    const int i = sl;   // 8 warps -> 8 batch rows
+    if (b0 + i < B && k < K) {
+        float s2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) s2 += red[t][i][kl];
+        const long long o = (long long)(b0 + i) * K + k;
+        dx[o] = (act && !(act[o] > 0.f)) ? 0.f : s2;
+    }
 }
 
 __global__ void relu_mask_kernel(const float* __restrict__ dy, const float* __restrict__ act, float* __restrict__ out,
@@ -337,10 +360,11 @@ extern "C" int zsv_head_fwd(const void* feat, int B, int P, int C, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     pool_kernel<<<dim3(ceil_div(C, 128), B), 128, 0, st>>>((const __nv_bfloat16*)feat, pooled, B, P, C, cpad(C));
     ZSV_LAUNCH_CHECK("pool_kernel");
-    linear_fwd_kernel<<<ceil_div(Hd * 32, 256), 256, 0, st>>>(pooled, w1, b1, hidden, B, C, Hd, 1);
+    const int bgroups = ceil_div(B, 8);
+    linear_fwd_kernel<<<dim3(ceil_div(Hd * 32, 256), bgroups), 256, 0, st>>>(pooled, w1, b1, hidden, B, C, Hd, 1);
     ZSV_LAUNCH_CHECK("linear_fwd_kernel(1)");
     // raw projection goes to emb, then normalised in place
-    linear_fwd_kernel<<<ceil_div(E * 32, 256), 256, 0, st>>>(hidden, w2, b2, emb, B, Hd, E, 0);
+    linear_fwd_kernel<<<dim3(ceil_div(E * 32, 256), bgroups), 256, 0, st>>>(hidden, w2, b2, emb, B, Hd, E, 0);
     ZSV_LAUNCH_CHECK("linear_fwd_kernel(2)");
     normalize_fwd_kernel<<<ceil_div(B * 32, 128), 128, 0, st>>>(emb, emb, onorm, B, E, eps);
     ZSV_LAUNCH_CHECK("normalize_fwd_kernel");
@@ -364,14 +388,14 @@ extern "C" int zsv_head_bwd(const float* demb, const float* emb, const float* on
         linear_wgrad_kernel<<<ceil_div(E * Hd, 256), 256, 0, st>>>(dout, hidden, dw2, db2, B, Hd, E);
         ZSV_LAUNCH_CHECK("linear_wgrad_kernel(2)");
     }
-    linear_dgrad_small_kernel<<<ceil_div(B * Hd, 128), 128, 0, st>>>(dout, w2, hidden, dh, B, Hd, E);
+    linear_dgrad_tile_kernel<<<dim3(ceil_div(Hd, 32), ceil_div(B, 8)), 256, 0, st>>>(dout, w2, hidden, dh, B, Hd, E);
     ZSV_LAUNCH_CHECK("linear_dgrad_kernel(2)");
     if (dw1) {
         linear_wgrad_kernel<<<ceil_div(Hd * C, 256), 256, 0, st>>>(dh, pooled, dw1, db1, B, C, Hd);
         ZSV_LAUNCH_CHECK("linear_wgrad_kernel(1)");
     }
     if (dfeat) {
-        linear_dgrad_small_kernel<<<ceil_div(B * C, 128), 128, 0, st>>>(dh, w1, nullptr, dpooled, B, C, Hd);
+        linear_dgrad_tile_kernel<<<dim3(ceil_div(C, 32), ceil_div(B, 8)), 256, 0, st>>>(dh, w1, nullptr, dpooled, B, C, Hd);
         ZSV_LAUNCH_CHECK("linear_dgrad_kernel(1)");
         const long long total = (long long)B * P * cpad(C);
         pool_bwd_kernel<<<(int)std::min<long long>(ceil_div_ll(total, 256), 148 * 8), 256, 0, st>>>(
@@ -385,7 +409,9 @@ extern "C" int zsv_linear_fwd(const float* x, const float* w, const float* bias,
                               int relu, void* stream) {
     if (!x || !w || !out) return fail(ZSV_ERR_BAD_ARG, "linear_fwd: null pointer");
     if (B < 1 || K < 1 || J < 1) return fail(ZSV_ERR_BAD_ARG, "linear_fwd: bad sizes");
-    linear_fwd_kernel<<<ceil_div(J * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, w, bias, out, B, K, J, relu);
+    // small weight matrix: one block row per 8 batch rows; large (C3D fc6): stream W once per pass over all rows
+    const int gy = (long long)K * J <= (1LL << 20) ? ceil_div(B, 8) : 1;
+    linear_fwd_kernel<<<dim3(ceil_div(J * 32, 256), gy), 256, 0, (cudaStream_t)stream>>>(x, w, bias, out, B, K, J, relu);
     ZSV_LAUNCH_CHECK("linear_fwd_kernel");
     return ZSV_OK;
 }
@@ -408,7 +434,7 @@ extern "C" int zsv_linear_bwd(const float* dy, const float* x, const float* w, c
     }
     if (dx) {
         if ((long long)K * J <= (1LL << 20))   // small weight matrix: parallelise over (b, k)
-            linear_dgrad_small_kernel<<<ceil_div(B * K, 128), 128, 0, st>>>(g, w, nullptr, dx, B, K, J);
+            linear_dgrad_tile_kernel<<<dim3(ceil_div(K, 32), ceil_div(B, 8)), 256, 0, st>>>(g, w, nullptr, dx, B, K, J);
         else                                   // large (C3D fc6): stream W ceil(B/8) times
             linear_dgrad_kernel<<<ceil_div(K, 128), 128, 0, st>>>(g, w, nullptr, dx, B, K, J);
         ZSV_LAUNCH_CHECK("linear_dgrad_kernel");

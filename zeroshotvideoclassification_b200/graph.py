@@ -59,6 +59,12 @@ class GraphedStep:
         self.launches_per_replay = _lib.launch_count() - n0
         self._restore(saved, model, optimizer)
         self.replays = 0
+        # double buffering of the inputs: prefetch() uploads the NEXT batch on a copy stream while the current replay runs
+        self._staging = None
+        self._copy_stream = None
+        self._staged = None          # event: staging buffers hold a complete batch
+        self._staging_free = None    # event: the replay that consumed the staging buffers has copied them out
+        self._has_prefetch = False
 
     # -- state kept out of the capture's side effects ------------------------------------------------------------
     @staticmethod
@@ -90,8 +96,44 @@ class GraphedStep:
                     else:
                         t.zero_()      # state created lazily by the warm-up iterations (Adam: step, exp_avg, exp_avg_sq)
 
+    # -- input prefetch ------------------------------------------------------------------------------------------
+    def prefetch(self, *inputs: torch.Tensor) -> None:
+        """Start copying the next batch (pinned host or device tensors of the captured shapes) into staging buffers on
+        a side stream; the next ``step()`` call without arguments consumes it.  This is the loader-side overlap the
+        reference gets from DataLoader workers + ``.cuda()`` (main.py:166-167): the H2D copy of batch i+1 runs while
+        the graph of batch i executes."""
+        if len(inputs) != len(self.static_inputs):
+            raise RuntimeError(f"GraphedStep.prefetch: expected {len(self.static_inputs)} inputs, got {len(inputs)}")
+        for s, t in zip(self.static_inputs, inputs):
+            if tuple(t.shape) != tuple(s.shape) or t.dtype != s.dtype:
+                raise RuntimeError("GraphedStep.prefetch: shape/dtype differs from the captured batch; pass ragged "
+                                   "batches to __call__ directly")
+        dev = self.static_inputs[0].device
+        if self._staging is None:
+            self._staging = [torch.empty_like(s) for s in self.static_inputs]
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._staged = torch.cuda.Event()
+            self._staging_free = torch.cuda.Event()
+            self._staging_free.record(torch.cuda.current_stream(dev))
+        self._copy_stream.wait_event(self._staging_free)
+        with torch.cuda.stream(self._copy_stream):
+            for st, t in zip(self._staging, inputs):
+                st.copy_(t, non_blocking=True)
+            self._staged.record(self._copy_stream)
+        self._has_prefetch = True
+
     # -- one iteration -------------------------------------------------------------------------------------------
     def __call__(self, *inputs: torch.Tensor):
+        if not inputs and self._has_prefetch:
+            cur = torch.cuda.current_stream(self.static_inputs[0].device)
+            cur.wait_event(self._staged)
+            for s, st in zip(self.static_inputs, self._staging):
+                s.copy_(st, non_blocking=True)
+            self._staging_free.record(cur)
+            self._has_prefetch = False
+            self.graph.replay()
+            self.replays += 1
+            return self.static_outputs
         if len(inputs) != len(self.static_inputs):
             raise RuntimeError(f"GraphedStep: expected {len(self.static_inputs)} inputs, got {len(inputs)}")
         if any(tuple(t.shape) != tuple(s.shape) or t.dtype != s.dtype for s, t in zip(self.static_inputs, inputs)):

@@ -56,11 +56,12 @@ class _Timed:
 
 
 def workspace(nbytes: int, device, tag: str = "default") -> torch.Tensor:
-    """Grow-only scratch buffer per (device, tag); stream-ordered reuse on the current stream."""
+    """Grow-only scratch buffer per (device, tag); stream-ordered reuse on the current stream.  Buffers start zeroed:
+    kernels that keep self-resetting ticket counters in their workspace (zsv_bn_finalize) rely on it."""
     key = (str(device), tag)
     buf = _workspace.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        buf = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _workspace[key] = buf
     return buf
 
