@@ -39,6 +39,8 @@ const char* zsv_last_error(void);
 int zsv_abi_version(void);
 /* Channel pitch used for a tensor with c channels: c rounded up to a multiple of 8. */
 int zsv_cpad(int c);
+/* Streaming multiprocessors of the current device (the persistent kernels launch one CTA per SM). */
+int zsv_sm_count(void);
 /* Number of CUDA kernels this library has launched in the calling process so far (monotonic). */
 unsigned long long zsv_launch_count(void);
 
@@ -90,12 +92,26 @@ int zsv_conv3d_stat_rows(const zsv_conv_desc* d);
 int zsv_conv3d_fprop(const zsv_conv_desc* d, const void* x, const void* w_fprop, void* y, float* part_sum,
                      float* part_sq, const float* bias, int relu, void* stream);
 
+/* Optional fusion of the first pass of BatchNorm3d backward into the data gradient.  The input of a convolution
+ * is out = relu?(bn(y)) of the previous layer (resnet.py:48-49,95,182-186), so its data gradient g is exactly what
+ * BatchNorm backward reduces over.  With this request dgrad writes dz = g * [y*scale+shift > 0] (or g when relu == 0)
+ * instead of g, and every CTA leaves its per-channel sums of dz and dz*xhat in `partial`, so zsv_bn_bwd_finish can
+ * go straight to the second pass; the separate reduction pass over g and y is gone. */
+typedef struct zsv_bn_bwd_fuse {
+    const void* y;          /* bf16 [N][T][H][W][cpad(Cin)]: pre-BatchNorm output of the layer that produced the input */
+    const float* table;     /* fp32 [cpad(Cin)][4] = (scale, shift, invstd, -mean*invstd), from zsv_bn_finalize */
+    int32_t relu;           /* != 0: that BatchNorm is followed by ReLU */
+    float* partial;         /* out: fp32 [partial_rows][4][cpad(Cin)] (row r: [0] = sum dz, [1] = sum dz*xhat) */
+    int32_t partial_rows;   /* capacity in rows; 8 * #SMs always suffices */
+    int32_t rows_written;   /* out (host side): rows filled by this call */
+} zsv_bn_bwd_fuse;
+
 /* Data gradient (autograd of conv3d w.r.t. its input, triggered at main.py:195).
  *   dy : bf16 [N][To][Ho][Wo][cpad(Cout)];  w_dgrad : packed weights (which = 1)
  *   dx : bf16 [N][T][H][W][cpad(Cin)];  addend: optional bf16 tensor shaped like dx added in the
- *        epilogue (residual-branch gradient, resnet.py:103-111). */
+ *        epilogue (residual-branch gradient, resnet.py:103-111); bn_fuse: optional, see above (NULL = plain dgrad). */
 int zsv_conv3d_dgrad(const zsv_conv_desc* d, const void* dy, const void* w_dgrad, void* dx, const void* addend,
-                     void* stream);
+                     zsv_bn_bwd_fuse* bn_fuse, void* stream);
 
 /* Weight gradient (autograd of conv3d w.r.t. its weight).  dw is fp32 in the state_dict layout
  * [Cout][Cin][kt][kh][kw].  The workspace holds split-K partial tiles; zsv_conv3d_wgrad_workspace gives the
@@ -132,12 +148,13 @@ int zsv_ncdhw_to_ndhwc(const float* x, void* out, int N, int C, int T, int H, in
  * (momentum, unbiased variance) in place when they are non-NULL.  One launch: fp64 chunk sums, then the last block
  * of each 32-channel group (ticket counter) finishes.  The caller-provided workspace (zsv_bn_finalize_workspace
  * bytes) must have its first 1024 bytes ZERO before the first call; every call leaves them zero again, so calls
- * that follow each other on one stream may share the workspace. */
+ * that follow each other on one stream may share the workspace.  bwd_table (optional): fp32 [cpad(C)][4] =
+ * (scale, shift, invstd, -mean*invstd) per channel, the constants zsv_bn_bwd_fuse needs. */
 size_t zsv_bn_finalize_workspace(int C);
 int zsv_bn_finalize(const float* part_sum, const float* part_sq, int part_rows, int C, long long count,
                     const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum,
-                    float eps, float* scale, float* shift, float* mean, float* invstd, void* workspace,
-                    size_t workspace_bytes, void* stream);
+                    float eps, float* scale, float* shift, float* mean, float* invstd, float* bwd_table,
+                    void* workspace, size_t workspace_bytes, void* stream);
 /* Eval mode: scale/shift from running statistics (main.py:229). */
 int zsv_bn_eval_scale_shift(int C, const float* gamma, const float* beta, const float* running_mean,
                             const float* running_var, float eps, float* scale, float* shift, void* stream);
@@ -161,6 +178,13 @@ int zsv_bn_bwd(const void* g, const void* out, int relu, const float* mask_scale
                const float* gamma, const void* y2, const float* mean2, const float* invstd2, const float* gamma2,
                void* dy, void* dy2, void* dz, float* dgamma, float* dbeta, float* dgamma2, float* dbeta2,
                long long rows, int C, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Second pass of BatchNorm backward when the sums came out of zsv_conv3d_dgrad (zsv_bn_bwd_fuse): reduces the
+ * partial rows (fixed order, fp64) to dgamma / dbeta and writes dy = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)).
+ * workspace: 4*cpad(C) floats. */
+int zsv_bn_bwd_finish(const void* dz, const void* y, const float* mean, const float* invstd, const float* gamma,
+                      const float* partial, int partial_rows, void* dy, float* dgamma, float* dbeta, long long rows,
+                      int C, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Embedding head: mean over (T,H,W) -> Linear(512,512) -> ReLU -> Linear(512,300) -> L2 normalise

@@ -184,3 +184,65 @@ def test_batched_weight_pack_matches_per_conv_pack():
             assert torch.equal(wd.view(torch.int16), wd1.view(torch.int16))
         else:
             assert wd is None
+
+
+@pytest.mark.parametrize("geom", [
+    # cin, cout, kernel, stride, padding, T, H, W, relu, addend
+    (48, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), 8, 16, 16, True, False),     # temporal halo kernel
+    (64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), 4, 24, 24, True, True),     # spatial halo kernel + shortcut gradient
+    (230, 128, (3, 1, 1), (2, 1, 1), (1, 0, 0), 8, 12, 12, True, False),   # temporal stride 2: parity-class launches
+    (144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), 4, 12, 12, False, False),   # BatchNorm without ReLU
+    (300, 520, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, 10, 10, True, False),   # wide layers: several N tiles
+], ids=["temporal", "spatial+addend", "temporal-s2", "norelu", "wide"])
+def test_dgrad_with_fused_bn_backward_matches_two_pass(geom):
+    """dgrad with zsv_bn_bwd_fuse + zsv_bn_bwd_finish == plain dgrad followed by the two-pass zsv_bn_bwd
+    (same masks, same rounding points; only the order of the fp32 partial sums differs)."""
+    import torch
+    from zeroshotvideoclassification_b200 import ops
+    cin, cout, k, s, p, T, H, W, relu, use_add = geom
+    N = 3
+    g = torch.Generator().manual_seed(11)
+    op = ops.Conv3d(N, T, H, W, cin, cout, k, s, p)
+    cp_in = ops.cpad(cin)
+    w = (torch.randn(cout, cin, *k, generator=g) * 0.05).cuda()
+    _, wd = op.pack(w)
+    dyo = torch.zeros(N, op.To, op.Ho, op.Wo, ops.cpad(cout), dtype=torch.bfloat16)
+    dyo[..., :cout] = torch.randn(N, op.To, op.Ho, op.Wo, cout, generator=g).to(torch.bfloat16)
+    dyo = dyo.cuda()
+    # the BatchNorm that produced this conv's input: raw y, batch statistics, affine parameters
+    y = torch.zeros(N, T, H, W, cp_in, dtype=torch.bfloat16)
+    y[..., :cin] = (torch.randn(N, T, H, W, cin, generator=g) * 1.5 + 0.3).to(torch.bfloat16)
+    y = y.cuda()
+    yf = y[..., :cin].float().reshape(-1, cin)
+    mean = torch.zeros(cp_in, device="cuda")
+    invstd = torch.zeros(cp_in, device="cuda")
+    mean[:cin] = yf.mean(0)
+    invstd[:cin] = 1.0 / torch.sqrt(yf.var(0, unbiased=False) + 1e-5)
+    gamma = (0.5 + torch.rand(cin, generator=g)).cuda()
+    beta = (0.2 * torch.randn(cin, generator=g)).cuda()
+    scale = torch.zeros(cp_in, device="cuda")
+    shift = torch.zeros(cp_in, device="cuda")
+    scale[:cin] = gamma * invstd[:cin]
+    shift[:cin] = beta - mean[:cin] * scale[:cin]
+    table = torch.stack([scale, shift, invstd, -mean * invstd], dim=1).contiguous()
+    addend = None
+    if use_add:
+        addend = torch.zeros_like(y)
+        addend[..., :cin] = torch.randn(N, T, H, W, cin, generator=g).to(torch.bfloat16).cuda()
+
+    gin = op.dgrad(dyo, wd, addend)
+    ref_dy, _, _, ref_dg, ref_db, _, _ = ops.bn_bwd(gin, None, 2 if relu else 0, y, mean, invstd, gamma, cin,
+                                                    mask_scale=scale, mask_shift=shift)
+    dz, partial, rows = op.dgrad_bn_fused(dyo, wd, addend, y, table, relu)
+    assert rows >= 1
+    got_dy, got_dg, got_db = ops.bn_bwd_finish(dz, y, mean, invstd, gamma, partial, rows, cin)
+    torch.cuda.synchronize()
+    # dz is the masked plain gradient, bit for bit
+    mask = (y.float() * scale + shift) > 0 if relu else torch.ones_like(y, dtype=torch.bool)
+    want_dz = torch.where(mask, gin, torch.zeros_like(gin))
+    # (an element whose pre-activation rounds differently with / without FMA may flip its mask: allow a handful)
+    assert float((dz.view(torch.int16) != want_dz.view(torch.int16)).float().mean()) < 1e-4
+    assert rel_err(got_db.cpu(), ref_db.cpu()) < 1e-4
+    assert rel_err(got_dg.cpu(), ref_dg.cpu()) < 1e-4
+    assert rel_err(got_dy[..., :cin].float().cpu(), ref_dy[..., :cin].float().cpu()) < 1e-2
+    assert float(got_dy[..., cin:].abs().max()) == 0.0 if cp_in > cin else True

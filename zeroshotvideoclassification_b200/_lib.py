@@ -12,7 +12,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libzsv_b200.so"
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 X_NDHWC = 0
 X_WFOLD = 1
 
@@ -25,6 +25,13 @@ class ConvDesc(C.Structure):
 
     def key(self):
         return tuple(getattr(self, n) for n, _ in self._fields_)
+
+
+class BnBwdFuse(C.Structure):
+    """Mirror of ``zsv_bn_bwd_fuse`` (include/zsv_b200.h)."""
+
+    _fields_ = [("y", C.c_void_p), ("table", C.c_void_p), ("relu", C.c_int32), ("partial", C.c_void_p),
+                ("partial_rows", C.c_int32), ("rows_written", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -40,13 +47,14 @@ SIGNATURES = {
     "zsv_abi_version": (_I, []),
     "zsv_cpad": (_I, [_I]),
     "zsv_launch_count": (C.c_ulonglong, []),
+    "zsv_sm_count": (_I, []),
     "zsv_conv3d_out_shape": (_I, [_DP, C.POINTER(C.c_int32)]),
     "zsv_conv3d_packed_weight_bytes": (_SZ, [_DP, _I]),
     "zsv_conv3d_pack_weight": (_I, [_DP, _P, _P, _P, _P]),
     "zsv_conv3d_pack_weights": (_I, [_I, _P, _P, _P, _P, _P]),
     "zsv_conv3d_stat_rows": (_I, [_DP]),
     "zsv_conv3d_fprop": (_I, [_DP, _P, _P, _P, _P, _P, _P, _I, _P]),
-    "zsv_conv3d_dgrad": (_I, [_DP, _P, _P, _P, _P, _P]),
+    "zsv_conv3d_dgrad": (_I, [_DP, _P, _P, _P, _P, C.POINTER(BnBwdFuse), _P]),
     "zsv_conv3d_wgrad_workspace": (_SZ, [_DP]),
     "zsv_conv3d_wgrad": (_I, [_DP, _P, _P, _P, _P, _SZ, _P]),
     "zsv_bias_grad_workspace": (_SZ, [_I]),
@@ -60,7 +68,8 @@ SIGNATURES = {
     "zsv_ndhwc_to_ncdhw": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "zsv_ncdhw_to_ndhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "zsv_bn_finalize_workspace": (_SZ, [_I]),
-    "zsv_bn_finalize": (_I, [_P, _P, _I, _I, _LL, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _SZ, _P]),
+    "zsv_bn_finalize": (_I, [_P, _P, _I, _I, _LL, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "zsv_bn_bwd_finish": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _LL, _I, _P, _SZ, _P]),
     "zsv_bn_eval_scale_shift": (_I, [_I, _P, _P, _P, _P, _F, _P, _P, _P]),
     "zsv_bn_apply": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _I, _P]),
     "zsv_bn_bwd_workspace": (_SZ, [_I]),

@@ -139,6 +139,11 @@ struct IgemmArgs {
     int32_t nstg;            // output staging buffers (2 = the TMA store of tile i overlaps the epilogue of tile i+1)
     FastDiv fd_ntiles, fd_tw, fd_th, fd_tt;
     int32_t debug;
+    int32_t scratch_bytes;   // epilogue scratch in shared memory (BN-backward fusion sums), multiple of 1 KB
+    int32_t bn_relu;
+    const __nv_bfloat16* bn_y;
+    const float4* bn_tab;
+    float* bn_partial;       // [gridDim.x][4][ncols]: rows 0/1 = sum dz, sum dz*xhat of this CTA
     long long o_sN, o_sT, o_sH, o_sW;  // element strides of the output tensor
     __nv_bfloat16* out;
     const __nv_bfloat16* addend;
@@ -164,8 +169,8 @@ struct WgradArgs {
     Tap taps[kMaxTaps];
 };
 
-constexpr int kIgemmThreads = 320;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 8;                        // 2 per TMEM lane quadrant, each takes every 2nd 16-column chunk
+constexpr int kIgemmThreads = 64 + kEpiWarps * 32;
 
 // ------------------------------------------------------------------------------------------------
 // Shared epilogue of the igemm kernels (8 warps = 256 threads, `et` = thread index within them).
@@ -178,6 +183,13 @@ struct EpiArgs {
     float* part_sum;
     float* part_sq;
     int ncols, nbias, relu, part_pitch;
+    // BatchNorm-backward fusion (dgrad): the tile written is dz = g * [ReLU mask of the BatchNorm that produced this
+    // conv's input], and the CTA accumulates sum(dz) and sum(dz * xhat) per channel (see zsv_bn_bwd_fuse)
+    const __nv_bfloat16* bn_y;   // pre-BatchNorm tensor, same layout as the output
+    const float4* bn_tab;        // per channel (scale, shift, invstd, -mean*invstd); scale/shift give the ReLU mask
+    int bn_relu;
+    float* bn_acc;               // smem [2][ncols] running sums of this CTA
+    float* bn_scratch;           // smem [4 quadrants][2][width] per-tile sums
     int debug;   // tuning aid (ZSV_DEBUG_EPI bit mask): 1 = skip the TMA store, 2 = skip TMEM read + staging, 4 = skip stats
 };
 
@@ -203,6 +215,23 @@ __device__ __forceinline__ void xreduce_stage(float (&v)[16], int lane, int m) {
         const float send = upper ? v[i] : v[i + n / 2];
         const float keep = upper ? v[i + n / 2] : v[i];
         v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+    }
+}
+
+// 32 values per lane -> after 5 exchange stages lane L holds the sum over all 32 lanes of value index L
+__device__ __forceinline__ void xreduce32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int st = 0; st < 5; ++st) {
+        const int m = 16 >> st;       // lane bit exchanged in this stage == live values after it
+        const bool upper = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (i < m) {
+                const float send = upper ? v[i] : v[i + m];
+                const float keep = upper ? v[i + m] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+            }
+        }
     }
 }
 
@@ -313,25 +342,58 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMa
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
         }
+        float xh[16];   // xhat of the BatchNorm input at this row (BN-backward fusion only)
+        if (E.bn_y != nullptr) {
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                const bool in = valid && (col + 8 * hlf < E.ncols);
+                uint4 a = make_uint4(0u, 0u, 0u, 0u);
+                if (in) a = *reinterpret_cast<const uint4*>(E.bn_y + off + col + 8 * hlf);
+                const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float yv = (j & 1) ? bf16_hi(aw[j >> 1]) : bf16_lo(aw[j >> 1]);
+                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (col + 8 * hlf < E.ncols) t = __ldg(E.bn_tab + col + 8 * hlf + j);
+                    if (E.bn_relu && !(fmaf(yv, t.x, t.y) > 0.f)) f[8 * hlf + j] = 0.f;
+                    xh[8 * hlf + j] = in ? fmaf(yv, t.z, t.w) : 0.f;
+                }
+            }
+        }
         uint32_t pk[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) pk[j] = valid ? pack_bf16x2(f[2 * j], f[2 * j + 1]) : 0u;
+        if (E.bn_y != nullptr) {
+            // sums over the 32 rows of this warp for 16 columns x {dz, dz*xhat}, of the bf16-rounded dz that is stored
+            float red[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                red[2 * j] = bf16_lo(pk[j]);
+                red[2 * j + 1] = bf16_hi(pk[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) red[16 + j] = red[j] * xh[j];
+            xreduce32(red, lane);
+            // lane = quantity * 16 + column
+            E.bn_scratch[((q << 1) + (lane >> 4)) * width + c + (lane & 15)] = red[0];
+        }
         // SWIZZLE_128B staging: 16-byte chunk index XOR (row & 7) inside the 64-channel panel
         uint8_t* prow = staging + static_cast<uint32_t>(c >> 6) * kPanelBytes + srow;
         const uint32_t ch = static_cast<uint32_t>(c & 63) >> 3;
         *reinterpret_cast<uint4*>(prow + ((ch ^ sxor) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *reinterpret_cast<uint4*>(prow + (((ch + 1) ^ sxor) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     };
-    // two TMEM loads in flight per wait: the thread's chunks are 32 columns apart (the other warp of the quadrant
-    // takes the chunks in between)
-    for (int c = half * 16; c < width && !(E.debug & 2); c += 64) {
+    // two TMEM loads in flight per wait: the thread's chunks are 16*kEpiWarps/4 columns apart (the other warps of the
+    // quadrant take the chunks in between)
+    constexpr int kChunkStride = 4 * kEpiWarps;
+    for (int c = half * 16; c < width && !(E.debug & 2); c += 2 * kChunkStride) {
         uint32_t v0[16], v1[16];
-        const bool two = c + 32 < width;
+        const bool two = c + kChunkStride < width;
         tmem_ld16(trow + c, v0);
-        if (two) tmem_ld16(trow + c + 32, v1);
+        if (two) tmem_ld16(trow + c + kChunkStride, v1);
         tmem_ld_wait();
         emit_chunk(c, v0);
-        if (two) emit_chunk(c + 32, v1);
+        if (two) emit_chunk(c + kChunkStride, v1);
     }
     // accumulator buffer fully read: hand it back to the MMA warp
     tc_fence_before();
@@ -346,6 +408,18 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMa
         }
         tma_store_commit();
     }
+    for (int e = et; E.bn_y != nullptr && e < 2 * width; e += kEpiWarps * 32) {
+        // column owner: quadrants in fixed order, then into the CTA's running sum (one owner per column: deterministic)
+        const int qn = e >= width ? 1 : 0;
+        const int cc = e - qn * width;
+        const int col = n_origin + cc;
+        if (col < E.ncols) {
+            float sum = 0.f;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) sum += E.bn_scratch[((qq << 1) + qn) * width + cc];
+            E.bn_acc[qn * E.ncols + col] += sum;
+        }
+    }
     if (E.part_sum != nullptr && !(E.debug & 4)) tile_column_stats(E, staging_u32, width, n_origin, m_tile, et, lane);
 }
 
@@ -356,9 +430,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMa
 //   warp 0      : TMA producer -- runs ahead across tile boundaries through a `stages`-deep smem ring
 //   warp 1      : MMA issuer + TMEM owner -- two accumulator buffers in TMEM, so the epilogue of tile i overlaps
 //                 the mainloop of tile i+1
-//   warps 2..9  : epilogue (TMEM lane quadrant = warp % 4; the two warps of a quadrant split the 16-column
-//                 chunks even/odd): tcgen05.ld -> bias/addend/ReLU -> bf16 -> 16-byte channels-last stores, plus
-//                 per-tile BatchNorm partial sums
+//   warps 2..   : epilogue, kEpiWarps warps (TMEM lane quadrant = warp % 4; the warps of a quadrant take the 16-column
+//                 chunks round-robin; 16 warps were measured and are not faster than 8): tcgen05.ld -> bias/addend/ReLU -> bf16 -> swizzled staging -> TMA store, plus per-tile
+//                 BatchNorm partial sums.  The epilogue of a small-K tile is a latency chain (TMEM load, fences,
+//                 barriers) that bounds the whole kernel, hence the wide group.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -380,7 +455,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     const uint32_t stagingOff = ringBytes;                           // [nstg][out_panels][128 rows][128 B], SWIZZLE_128B
     const uint32_t stagingBytes = out_panels * kPanelBytes;
     const uint32_t statOff = stagingOff + P.nstg * stagingBytes;     // 4 KB of fp32 scratch for the BN column sums
-    const uint32_t barOff = statOff + 4096u;
+    const uint32_t barOff = statOff + static_cast<uint32_t>(P.scratch_bytes);
     const uint32_t barFull = base + barOff;
     const uint32_t barEmpty = barFull + 8u * stages;
     const uint32_t barTmemFull = barEmpty + 8u * stages;   // [2]
@@ -489,7 +564,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         }
     } else {
         const int q = warp & 3;               // TMEM lane quadrant this warp may read
-        const int half = (warp - 2) >> 2;     // which of the two warps of the quadrant (even / odd column chunks)
+        const int half = (warp - 2) >> 2;     // which of the warps of the quadrant (chunk index mod kEpiWarps/4)
         const int row = q * 32 + lane;
         int r = row;
         const int w = r % P.bw;
@@ -504,6 +579,11 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         E.ncols = P.ncols, E.nbias = P.nbias, E.relu = P.relu, E.part_pitch = P.part_pitch;
         E.debug = P.debug;
         float* statbuf = reinterpret_cast<float*>(smem + statOff);
+        E.bn_y = P.bn_y, E.bn_tab = P.bn_tab, E.bn_relu = P.bn_relu;
+        E.bn_acc = statbuf;
+        E.bn_scratch = statbuf + 2 * P.ncols;
+        if (P.bn_y != nullptr)   // running sums start at zero; the first tile's barrier orders this before any use
+            for (int i = et; i < 2 * P.ncols; i += kEpiWarps * 32) statbuf[i] = 0.f;
         int local = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
             int m, in_;
@@ -527,6 +607,13 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                           P.nstg == 2, q, half, row, lane, et);
         }
         if (et == 0) tma_store_wait_all();   // global writes of the last tile complete before the CTA exits
+        if (P.bn_y != nullptr) {
+            named_bar_sync(1, kEpiWarps * 32);   // every column owner has added its last tile
+            for (int i = et; i < 2 * P.ncols; i += kEpiWarps * 32) {
+                const int qn = i >= P.ncols ? 1 : 0;
+                P.bn_partial[((long long)blockIdx.x * 4 + qn) * P.ncols + (i - qn * P.ncols)] = statbuf[i];
+            }
+        }
     }
     __syncthreads();
     if (warp == 1) {
@@ -567,6 +654,11 @@ struct HaloArgs {
     FastDiv fd_tl0, fd_tl1, fd_tl2;
     int32_t debug;
     int32_t pf_dist;     // L2 prefetch distance in tiles (0 = off)
+    int32_t scratch_bytes;   // epilogue scratch in shared memory (BN-backward fusion sums), multiple of 1 KB
+    int32_t bn_relu;
+    const __nv_bfloat16* bn_y;
+    const float4* bn_tab;
+    float* bn_partial;       // [gridDim.x][4][ncols]
     const __nv_bfloat16* addend;
     float* part_sum;
     float* part_sq;
@@ -591,7 +683,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const uint32_t stagingOff = ringOff + ringBytes;
     const uint32_t stagingBytes = out_panels * kPanelBytes;
     const uint32_t statOff = stagingOff + P.nstg * stagingBytes;
-    const uint32_t barOff = statOff + 4096u;
+    const uint32_t barOff = statOff + static_cast<uint32_t>(P.scratch_bytes);
     const uint32_t barFull = base + barOff;
     const uint32_t barEmpty = barFull + 8u * stages;
     const uint32_t barTmemFull = barEmpty + 8u * stages;
@@ -712,7 +804,9 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 for (int cp = 0; cp < P.ncopies; ++cp) {
                     mbar_wait(barFull + 8u * stage, phase);
                     tc_fence_after();
-                    if (leader) {
+                    if (P.debug & 8) {   // tuning aid: consume the stage without issuing MMAs
+                        if (leader) mbar_arrive(barEmpty + 8u * stage);
+                    } else if (leader) {
                         uint32_t a_lo = umma_desc_lo(base + ringOff + stage * P.a_stage_bytes);
                         uint32_t b_lo = b_chunk_lo + static_cast<uint32_t>(P.tap0 + cp * P.tap_dcp) * tap_bytes16;
                         const uint32_t b_step = static_cast<uint32_t>(P.tap_dsh) * tap_bytes16;   // may wrap (negative step)
@@ -739,7 +833,10 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                     }
                 }
             }
-            if (leader) umma_commit(barTmemFull + 8u * buf);
+            if (leader) {
+                if (P.debug & 8) mbar_arrive(barTmemFull + 8u * buf);
+                else umma_commit(barTmemFull + 8u * buf);
+            }
             __syncwarp();
         }
     } else {
@@ -759,6 +856,11 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         E.ncols = P.ncols, E.nbias = P.nbias, E.relu = P.relu, E.part_pitch = P.part_pitch;
         E.debug = P.debug;
         float* statbuf = reinterpret_cast<float*>(smem + statOff);
+        E.bn_y = P.bn_y, E.bn_tab = P.bn_tab, E.bn_relu = P.bn_relu;
+        E.bn_acc = statbuf;
+        E.bn_scratch = statbuf + 2 * P.ncols;
+        if (P.bn_y != nullptr)   // running sums start at zero; the first tile's barrier orders this before any use
+            for (int i = et; i < 2 * P.ncols; i += kEpiWarps * 32) statbuf[i] = 0.f;
         // columns this tile owns: a non-last N tile only owns n_step of its bn_tile computed columns
         const int width = (n_tile + 1 < P.n_tiles) ? P.n_step : P.bn_tile;
         int local = 0;
@@ -782,6 +884,13 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                           row, lane, et);
         }
         if (et == 0) tma_store_wait_all();
+        if (P.bn_y != nullptr) {
+            named_bar_sync(1, kEpiWarps * 32);
+            for (int i = et; i < 2 * P.ncols; i += kEpiWarps * 32) {
+                const int qn = i >= P.ncols ? 1 : 0;
+                P.bn_partial[((long long)blockIdx.x * 4 + qn) * P.ncols + (i - qn * P.ncols)] = statbuf[i];
+            }
+        }
     }
     __syncthreads();
     if (warp == 1) {
@@ -1345,29 +1454,45 @@ int build_fwd_taps(const zsv_conv_desc* d, const Shape& s, const void* x, const 
     return ZSV_OK;
 }
 
-int igemm_smem_bytes(int bn_tile, int stages, int nstg) {
-    return 1024 + stages * (kPanelBytes + bn_tile * 128) + nstg * ((bn_tile + 63) / 64) * kPanelBytes + 4096 +
+// host-side view of a zsv_bn_bwd_fuse request while the (one or more) launches of a dgrad call are issued
+struct BnFuseLaunch {
+    const __nv_bfloat16* y;   // already offset to the parity class of the launch
+    const float4* tab;
+    int relu;
+    float* partial;
+    int capacity;             // rows
+    int rows_used;
+};
+
+// shared-memory scratch of the fused BatchNorm-backward sums: [2][ncols] running + [4][2][bn_tile] per tile
+int bn_scratch_bytes(int ncols, int bn_tile) { return (((2 * ncols + 8 * bn_tile) * 4) + 1023) & ~1023; }
+
+int igemm_smem_bytes(int bn_tile, int stages, int nstg, int scratch = 0) {
+    return 1024 + stages * (kPanelBytes + bn_tile * 128) + nstg * ((bn_tile + 63) / 64) * kPanelBytes + scratch +
            16 * stages + 48 + 64;
 }
 
 int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtensorMap& mapOut, IgemmArgs& a,
-                 long long m_tiles, int n_tiles, cudaStream_t stream) {
+                 long long m_tiles, int n_tiles, cudaStream_t stream, BnFuseLaunch* fuse = nullptr) {
     // one persistent CTA per SM owns (almost) all shared memory: as many ring stages as fit, at most 8
     // two output staging buffers when at least 3 ring stages still fit beside them
+    const int scratch = fuse ? bn_scratch_bytes(a.ncols, a.bn_tile) : 0;
     int nstg = 2;
     int stages = 8;
-    while (stages > 2 && igemm_smem_bytes(a.bn_tile, stages, nstg) > 226 * 1024) --stages;
-    if (stages < 3 || igemm_smem_bytes(a.bn_tile, stages, nstg) > 226 * 1024) {
+    while (stages > 2 && igemm_smem_bytes(a.bn_tile, stages, nstg, scratch) > 226 * 1024) --stages;
+    if (stages < 3 || igemm_smem_bytes(a.bn_tile, stages, nstg, scratch) > 226 * 1024) {
         nstg = 1;
         stages = 8;
-        while (stages > 2 && igemm_smem_bytes(a.bn_tile, stages, nstg) > 226 * 1024) --stages;
+        while (stages > 2 && igemm_smem_bytes(a.bn_tile, stages, nstg, scratch) > 226 * 1024) --stages;
     }
     if (const char* e = getenv("ZSV_DEBUG_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));
     a.nstg = nstg;
     a.stages = stages;
     a.tmem_cols = 2 * pow2_cols(a.bn_tile);   // two accumulator buffers
     if (a.tmem_cols > 512) return fail(ZSV_ERR_UNSUPPORTED, "igemm: N tile %d too wide for two TMEM buffers", a.bn_tile);
-    const int smem = igemm_smem_bytes(a.bn_tile, stages, nstg);
+    const int smem = igemm_smem_bytes(a.bn_tile, stages, nstg, scratch);
+    if (smem > 227 * 1024) return fail(ZSV_ERR_UNSUPPORTED, "igemm: shared memory budget exceeded (%d bytes)", smem);
+    a.scratch_bytes = scratch;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
@@ -1383,6 +1508,14 @@ int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtenso
     if (const char* e = getenv("ZSV_DEBUG_EPI")) a.debug = atoi(e);
     const long long tiles = m_tiles * n_tiles;
     const int grid = (int)std::min<long long>(tiles, sm_count());
+    if (fuse) {
+        if (fuse->rows_used + grid > fuse->capacity)
+            return fail(ZSV_ERR_WORKSPACE, "dgrad: BN-fusion partial buffer holds %d rows, need %d", fuse->capacity,
+                        fuse->rows_used + grid);
+        a.bn_y = fuse->y, a.bn_tab = fuse->tab, a.bn_relu = fuse->relu;
+        a.bn_partial = fuse->partial + (size_t)fuse->rows_used * 4 * a.ncols;
+        fuse->rows_used += grid;
+    }
     igemm_kmajor_kernel<<<grid, kIgemmThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], mapB, mapOut, a);
     ZSV_LAUNCH_CHECK("igemm_kmajor_kernel");
     return ZSV_OK;
@@ -1397,13 +1530,14 @@ struct HaloPlan {
     long long m_tiles;
     uint32_t a_stage_bytes, b_main_bytes, b_tail_bytes, b_total_bytes;
     int smem;
+    int scratch;
 };
 
 inline uint32_t align1k(uint32_t v) { return (v + 1023u) & ~1023u; }
 
 // act extents (W,H,T,N) of the GEMM-M space (stride-1 conv: output extents == input extents), reduction channels
 // kdim, output columns `cols`, filter (kt,kh,kw).  Only spatial 1xkhxkw (kh==3) and temporal ktx1x1 (kt==3).
-HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int kh, int kw) {
+HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int kh, int kw, bool bn_fuse = false) {
     HaloPlan p;
     memset(&p, 0, sizeof(p));
     if (getenv("ZSV_DEBUG_NO_HALO")) return p;
@@ -1439,6 +1573,13 @@ HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int k
                     }
                 }
             }
+    if (const char* e = getenv("ZSV_DEBUG_HALO_BOX")) {   // tuning aid: force the box "b0,b1,b2,b3"
+        int q[4];
+        if (sscanf(e, "%d,%d,%d,%d", &q[0], &q[1], &q[2], &q[3]) == 4 && (q[0] * q[1] * q[2]) % 8 == 0 &&
+            q[0] * q[1] * q[2] * q[3] <= 128)
+            for (int i = 0; i < 4; ++i) p.b[i] = q[i];
+        best = 1;
+    }
     if (best < 0) return p;
     for (int i = 0; i < 4; ++i) {
         p.O[i] = E[i];
@@ -1473,7 +1614,8 @@ HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int k
         const int staging1 = ((bn + 63) / 64) * (int)kPanelBytes;
         int nstg = 2, stages = 0, fixed = 0;
         for (; nstg >= 1; --nstg) {   // prefer two staging buffers if >= 3 activation stages still fit
-            fixed = 1024 + (int)p.b_total_bytes + nstg * staging1 + 4096 + 256;
+            p.scratch = bn_fuse ? bn_scratch_bytes(cpad(cols), bn) : 0;
+            fixed = 1024 + (int)p.b_total_bytes + nstg * staging1 + p.scratch + 256;
             const int avail = 226 * 1024 - fixed;
             stages = avail > 0 ? avail / (int)p.a_stage_bytes : 0;
             if (stages >= (nstg == 2 ? 3 : 2)) break;
@@ -1501,7 +1643,7 @@ HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int k
 int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, const void* wimg, int wRows, int wKpitch,
                 int ntaps, void* out, int outPitch, int W, int H, int T, int N, const int* copy_off, int shift_org,
                 int tap0, int tap_dcp, int tap_dsh, const void* addend, float* part_sum, float* part_sq, const float* bias,
-                int nbias, int relu, cudaStream_t st) {
+                int nbias, int relu, cudaStream_t st, BnFuseLaunch* fuse = nullptr) {
     HaloArgs a;
     memset(&a, 0, sizeof(a));
     for (int i = 0; i < 4; ++i) a.b[i] = p.b[i], a.tl[i] = p.tl[i], a.O[i] = p.O[i];
@@ -1577,6 +1719,16 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
     const long long want = p.m_tiles * p.n_tiles;
     int grid = (int)std::min<long long>(want, (long long)(sm_count() / p.n_tiles) * p.n_tiles);
     if (grid < p.n_tiles) grid = p.n_tiles;
+    a.scratch_bytes = p.scratch;
+    if (fuse) {
+        if (p.scratch < bn_scratch_bytes(a.ncols, p.bn_tile)) return fail(ZSV_ERR_UNSUPPORTED, "halo plan without BN-fusion scratch");
+        if (fuse->rows_used + grid > fuse->capacity)
+            return fail(ZSV_ERR_WORKSPACE, "dgrad: BN-fusion partial buffer holds %d rows, need %d", fuse->capacity,
+                        fuse->rows_used + grid);
+        a.bn_y = fuse->y, a.bn_tab = fuse->tab, a.bn_relu = fuse->relu;
+        a.bn_partial = fuse->partial + (size_t)fuse->rows_used * 4 * a.ncols;
+        fuse->rows_used += grid;
+    }
     igemm_halo_kernel<<<grid, kIgemmThreads, p.smem, st>>>(mA, mAt, mB, mBt, mO, a);
     ZSV_LAUNCH_CHECK("igemm_halo_kernel");
     return ZSV_OK;
@@ -1744,16 +1896,30 @@ extern "C" int zsv_conv3d_fprop(const zsv_conv_desc* d, const void* x, const voi
 }
 
 extern "C" int zsv_conv3d_dgrad(const zsv_conv_desc* d, const void* dy, const void* w_dgrad, void* dx,
-                                const void* addend, void* stream) {
+                                const void* addend, zsv_bn_bwd_fuse* bnf, void* stream) {
     Shape s;
     int rc = check_desc(d, &s);
     if (rc) return rc;
     if (s.wfold) return fail(ZSV_ERR_UNSUPPORTED, "dgrad: not available for the wfold (first-layer) layout");
     if (!dy || !w_dgrad || !dx) return fail(ZSV_ERR_BAD_ARG, "dgrad: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    BnFuseLaunch fuse_state;
+    BnFuseLaunch* fuse = nullptr;
+    if (bnf) {
+        if (!bnf->y || !bnf->table || !bnf->partial || bnf->partial_rows < 1)
+            return fail(ZSV_ERR_BAD_ARG, "dgrad: incomplete zsv_bn_bwd_fuse");
+        fuse_state.y = (const __nv_bfloat16*)bnf->y;
+        fuse_state.tab = (const float4*)bnf->table;
+        fuse_state.relu = bnf->relu;
+        fuse_state.partial = bnf->partial;
+        fuse_state.capacity = bnf->partial_rows;
+        fuse_state.rows_used = 0;
+        fuse = &fuse_state;
+        bnf->rows_written = 0;
+    }
 
     if (d->st == 1 && d->sh == 1 && d->sw == 1 && s.To == d->T && s.Ho == d->H && s.Wo == d->W) {
-        const HaloPlan hp = plan_halo(d->W, d->H, d->T, d->N, d->Cout, d->Cin, d->kt, d->kh, d->kw);
+        const HaloPlan hp = plan_halo(d->W, d->H, d->T, d->N, d->Cout, d->Cin, d->kt, d->kh, d->kw, fuse != nullptr);
         if (hp.ok) {
             // dx[i] = sum_j dy[i + p - j] w[j]: copy j reads dy at W offset p - j; along the shift dim the halo starts
             // at i0 + p - (S-1) and filter index j sits at halo slice S-1-j
@@ -1762,9 +1928,11 @@ extern "C" int zsv_conv3d_dgrad(const zsv_conv_desc* d, const void* dy, const vo
             for (int c = 0; c < hp.ncopies; ++c) copy_off[c] = hp.spatial ? d->pw - c : 0;
             const int shift_org = (hp.spatial ? d->ph : d->pt) - (hp.S - 1);
             const int kwm = hp.spatial ? d->kw : 1;
-            return launch_halo(hp, dy, d->Cout, s.coutp, w_dgrad, d->Cin, s.coutp, s.ntaps, dx, s.cinp, d->W, d->H, d->T,
-                               d->N, copy_off, shift_org, (hp.S - 1) * kwm, 1, -kwm, addend, nullptr, nullptr, nullptr, 0, 0,
-                               st);
+            rc = launch_halo(hp, dy, d->Cout, s.coutp, w_dgrad, d->Cin, s.coutp, s.ntaps, dx, s.cinp, d->W, d->H, d->T,
+                             d->N, copy_off, shift_org, (hp.S - 1) * kwm, 1, -kwm, addend, nullptr, nullptr, nullptr, 0, 0,
+                             st, fuse);
+            if (fuse) bnf->rows_written = fuse->rows_used;
+            return rc;
         }
     }
 
@@ -1778,6 +1946,8 @@ extern "C" int zsv_conv3d_dgrad(const zsv_conv_desc* d, const void* dy, const vo
                     bwd_dim_taps(d->kw, d->sw, d->pw, cw).empty())
                     any_empty = true;
     const size_t dx_bytes = (size_t)d->N * d->T * d->H * d->W * s.cinp * 2;
+    if (any_empty && fuse)
+        return fail(ZSV_ERR_UNSUPPORTED, "dgrad: BN-backward fusion needs every output parity class to have a filter tap");
     if (any_empty) {
         if (addend) {
             if (addend != dx) ZSV_CUDA_CHECK(cudaMemcpyAsync(dx, addend, dx_bytes, cudaMemcpyDeviceToDevice, st));
@@ -1816,6 +1986,7 @@ extern "C" int zsv_conv3d_dgrad(const zsv_conv_desc* d, const void* dy, const vo
                 // when the tensor was pre-filled with the addend (empty classes), it is still added here for
                 // the non-empty classes because their positions are overwritten
                 a.addend = addend ? (const __nv_bfloat16*)addend + class_off : nullptr;
+                if (fuse) fuse->y = (const __nv_bfloat16*)bnf->y + class_off;
                 int ti = 0;
                 for (const DimTap& x1 : tt)
                     for (const DimTap& x2 : th)
@@ -1850,9 +2021,10 @@ extern "C" int zsv_conv3d_dgrad(const zsv_conv_desc* d, const void* dy, const vo
                     rc = make_map(&mapOut, (const char*)dx + class_off * 2, 5, odims, ostr, obox);
                     if (rc) return rc;
                 }
-                rc = launch_igemm(maps, mapB, mapOut, a, m_tiles, n_tiles, st);
+                rc = launch_igemm(maps, mapB, mapOut, a, m_tiles, n_tiles, st, fuse);
                 if (rc) return rc;
             }
+    if (fuse) bnf->rows_written = fuse->rows_used;
     return ZSV_OK;
 }
 

@@ -93,7 +93,8 @@ bn_finalize_kernel(const float* __restrict__ part_sum, const float* __restrict__
                    int rows_per_chunk, double* __restrict__ chunk, unsigned int* __restrict__ tickets, double count,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ running_mean,
                    float* __restrict__ running_var, float momentum, float eps, float* __restrict__ scale,
-                   float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+                   float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                   float4* __restrict__ bwd_table) {
     __shared__ double sh1[32][33];
     __shared__ double sh2[32][33];
     __shared__ int last;
@@ -155,6 +156,9 @@ bn_finalize_kernel(const float* __restrict__ part_sum, const float* __restrict__
             shift[c] = (float)((double)bt - mean * (double)g * invstd);
             mean_out[c] = (float)mean;
             invstd_out[c] = (float)invstd;
+            if (bwd_table)
+                bwd_table[c] = make_float4((float)((double)g * invstd), (float)((double)bt - mean * (double)g * invstd),
+                                           (float)invstd, (float)(-mean * invstd));
             if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
             if (running_var) {
                 const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
@@ -165,6 +169,7 @@ bn_finalize_kernel(const float* __restrict__ part_sum, const float* __restrict__
             shift[c] = 0.f;
             mean_out[c] = 0.f;
             invstd_out[c] = 0.f;
+            if (bwd_table) bwd_table[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
 }
@@ -192,6 +197,23 @@ __global__ void bn_eval_kernel(int C, int Cp, const float* __restrict__ gamma, c
 // Thread layout shared by the BN streaming kernels: a block is V = Cp/8 channel groups x R = 256/V rows.  Every thread
 // keeps ONE channel group for its whole life, so the per-channel constants live in registers (no shared-memory
 // lookups, no index arithmetic per element) while a block still reads/writes R whole rows = one contiguous span.
+// ReLU mask of a packed bf16 pair: 0xFFFF in each half that is > 0
+__device__ __forceinline__ uint32_t relu_mask2(uint32_t bf16pair) {
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&bf16pair);
+    return __hgt2_mask(v, __float2bfloat162_rn(0.f));
+}
+__device__ __forceinline__ uint32_t relu2(uint32_t bf16pair) {
+    __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&bf16pair);
+    v = __hmax2(v, __float2bfloat162_rn(0.f));
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void load_pairs(const float* __restrict__ p, int c0, f32x2 (&out)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = f2_make(p[c0 + 2 * j], p[c0 + 2 * j + 1]);
+}
+
+// The arithmetic runs on packed fp32 pairs (one FFMA2 per two channels) and the ReLU on the packed bf16 result:
+// rounding and max(., 0) commute, so the result is bit-identical to the scalar form with half the instructions.
 template <bool kHasY2, bool kHasRes>
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -203,15 +225,14 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
     const int rl = threadIdx.x / V;
     if (rl >= R) return;
     const int c0 = vl << 3;
-    float sc[8], sh[8], sc2[8], sh2[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        sc[j] = scale[c0 + j];
-        sh[j] = shift[c0 + j];
-        sc2[j] = kHasY2 ? scale2[c0 + j] : 0.f;
-        sh2[j] = kHasY2 ? shift2[c0 + j] : 0.f;
+    f32x2 sc[4], sh[4], sc2[4], sh2[4];
+    load_pairs(scale, c0, sc);
+    load_pairs(shift, c0, sh);
+    if (kHasY2) {
+        load_pairs(scale2, c0, sc2);
+        load_pairs(shift2, c0, sh2);
     }
-    constexpr int U = 2;   // rows in flight per thread
+    constexpr int U = 2;   // rows in flight per thread (4 was measured: not faster)
     const long long rstride = (long long)gridDim.x * R;
     for (long long r0 = (long long)blockIdx.x * R + rl; r0 < rows; r0 += U * rstride) {
         uint4 vy[U], vy2[U], vr[U];
@@ -229,25 +250,19 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
         for (int u = 0; u < U; ++u) {
             const long long r = r0 + u * rstride;
             if (r >= rows) break;
-            float f[8], o[8];
-            unpack8(vy[u], f);
+            const uint32_t wy[4] = {vy[u].x, vy[u].y, vy[u].z, vy[u].w};
+            const uint32_t wy2[4] = {vy2[u].x, vy2[u].y, vy2[u].z, vy2[u].w};
+            const uint32_t wr[4] = {vr[u].x, vr[u].y, vr[u].z, vr[u].w};
+            uint32_t o[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = fmaf(f[j], sc[j], sh[j]);
-            if (kHasY2) {
-                unpack8(vy2[u], f);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] += fmaf(f[j], sc2[j], sh2[j]);
+            for (int j = 0; j < 4; ++j) {
+                f32x2 v = f2_fma(f2_from_bf16x2(wy[j]), sc[j], sh[j]);
+                if (kHasY2) v = f2_add(v, f2_fma(f2_from_bf16x2(wy2[j]), sc2[j], sh2[j]));
+                if (kHasRes) v = f2_add(v, f2_from_bf16x2(wr[j]));
+                o[j] = f2_to_bf16x2(v);
+                if (relu) o[j] = relu2(o[j]);
             }
-            if (kHasRes) {
-                unpack8(vr[u], f);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] += f[j];
-            }
-            if (relu) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
-            }
-            *reinterpret_cast<uint4*>(out + r * Cp + c0) = pack8(o);
+            *reinterpret_cast<uint4*>(out + r * Cp + c0) = make_uint4(o[0], o[1], o[2], o[3]);
         }
     }
 }
@@ -259,34 +274,30 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
 //   final  : sums the block partials in fp64 -> sums[4][Cp] (+ dgamma/dbeta outputs)
 //   apply  : dy = gamma*invstd*(dz - s1/M - xhat*s2/M)
 // ------------------------------------------------------------------------------------------------
+// Sums are taken against the RAW pre-activation (s2raw = sum dz*y); the final kernel turns them into
+// sum dz*xhat = invstd*(s2raw - mean*s1) in fp64.  Per pair of channels: mask (FFMA2 + bf16x2 compare), two unpacks,
+// one FADD2 and one FFMA2.
 template <bool kHasY2>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ out, int relu,
                      const float* __restrict__ mask_scale, const float* __restrict__ mask_shift,
-                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
-                     const float* __restrict__ invstd, const __nv_bfloat16* __restrict__ y2,
-                     const float* __restrict__ mean2, const float* __restrict__ invstd2, long long rows, int Cp, int R,
-                     float* __restrict__ partial) {
-    extern __shared__ float sm[];  // [R][4][Cp] reduction scratch (only lanes r > 0 write)
+                     const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ y2, long long rows, int Cp,
+                     int R, float* __restrict__ partial) {
+    extern __shared__ float sm[];  // [R][4][Cp] reduction scratch
     const int V = Cp >> 3;
     const int vl = threadIdx.x % V;
     const int rl = threadIdx.x / V;
     const bool active = rl < R;
     const int c0 = vl << 3;
-    float a1[8], a2[8], b1[8], b2[8];
-    float mu[8], is[8], mu2[8], is2[8], msc[8], msh[8];
+    f32x2 a1[4], a2[4], b2[4], msc[4], msh[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        a1[j] = a2[j] = b1[j] = b2[j] = 0.f;
-        mu[j] = mean[c0 + j];
-        is[j] = invstd[c0 + j];
-        msc[j] = relu == 2 ? mask_scale[c0 + j] : 0.f;
-        msh[j] = relu == 2 ? mask_shift[c0 + j] : 0.f;
-        mu2[j] = kHasY2 ? mean2[c0 + j] : 0.f;
-        is2[j] = kHasY2 ? invstd2[c0 + j] : 0.f;
+    for (int j = 0; j < 4; ++j) a1[j] = a2[j] = b2[j] = msc[j] = msh[j] = 0ull;
+    if (relu == 2) {
+        load_pairs(mask_scale, c0, msc);
+        load_pairs(mask_shift, c0, msh);
     }
     if (active) {
-        constexpr int U = 2;   // rows in flight per thread
+        constexpr int U = 2;   // rows in flight per thread (4 was measured: not faster)
         const long long rstride = (long long)gridDim.x * R;
         for (long long r0 = (long long)blockIdx.x * R + rl; r0 < rows; r0 += U * rstride) {
             uint4 vg[U], vo[U], vy[U], vy2[U];
@@ -305,37 +316,36 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* _
             for (int u = 0; u < U; ++u) {
                 const long long r = r0 + u * rstride;
                 if (r >= rows) break;
-                float gz[8], f[8];
-                unpack8(vg[u], gz);
-                if (relu == 1) {
-                    unpack8(vo[u], f);
+                const uint32_t wg[4] = {vg[u].x, vg[u].y, vg[u].z, vg[u].w};
+                const uint32_t wo[4] = {vo[u].x, vo[u].y, vo[u].z, vo[u].w};
+                const uint32_t wy[4] = {vy[u].x, vy[u].y, vy[u].z, vy[u].w};
+                const uint32_t wy2[4] = {vy2[u].x, vy2[u].y, vy2[u].z, vy2[u].w};
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) gz[j] = f[j] > 0.f ? gz[j] : 0.f;
-                }
-                unpack8(vy[u], f);
-                if (relu == 2) {   // ReLU mask recomputed from the pre-activation: saves re-reading the forward output
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) gz[j] = fmaf(f[j], msc[j], msh[j]) > 0.f ? gz[j] : 0.f;
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    a1[j] += gz[j];
-                    a2[j] = fmaf(gz[j], (f[j] - mu[j]) * is[j], a2[j]);
-                }
-                if (kHasY2) {
-                    unpack8(vy2[u], f);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) b2[j] = fmaf(gz[j], (f[j] - mu2[j]) * is2[j], b2[j]);
+                for (int j = 0; j < 4; ++j) {
+                    const f32x2 yv = f2_from_bf16x2(wy[j]);
+                    uint32_t gw = wg[j];
+                    if (relu == 1) gw &= relu_mask2(wo[j]);
+                    if (relu == 2) gw &= relu_mask2(f2_to_bf16x2(f2_fma(yv, msc[j], msh[j])));
+                    const f32x2 gz = f2_from_bf16x2(gw);
+                    a1[j] = f2_add(a1[j], gz);
+                    a2[j] = f2_fma(gz, yv, a2[j]);
+                    if (kHasY2) b2[j] = f2_fma(gz, f2_from_bf16x2(wy2[j]), b2[j]);
                 }
             }
         }
     }
     if (active) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            sm[(rl * 4 + 0) * Cp + c0 + j] = a1[j];
-            sm[(rl * 4 + 1) * Cp + c0 + j] = a2[j];
-            if (kHasY2) sm[(rl * 4 + 3) * Cp + c0 + j] = b2[j];
+        for (int j = 0; j < 4; ++j) {
+            float lo, hi;
+            f2_split(a1[j], lo, hi);
+            sm[(rl * 4 + 0) * Cp + c0 + 2 * j] = lo, sm[(rl * 4 + 0) * Cp + c0 + 2 * j + 1] = hi;
+            f2_split(a2[j], lo, hi);
+            sm[(rl * 4 + 1) * Cp + c0 + 2 * j] = lo, sm[(rl * 4 + 1) * Cp + c0 + 2 * j + 1] = hi;
+            if (kHasY2) {
+                f2_split(b2[j], lo, hi);
+                sm[(rl * 4 + 3) * Cp + c0 + 2 * j] = lo, sm[(rl * 4 + 3) * Cp + c0 + 2 * j + 1] = hi;
+            }
         }
     }
     __syncthreads();
@@ -350,39 +360,58 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* _
         }
         partial[((long long)blockIdx.x * 4 + qi) * Cp + c] = s;
     }
-    (void)b1;
 }
 
+// raw != 0: rows 1 / 3 of the partials are sums against the raw pre-activation and are converted here:
+// sum dz*xhat = invstd * (s2raw - mean * s1).  Block = one group of 32 channels, all quantities of that group.
 __global__ void __launch_bounds__(1024)
-bn_bwd_final_kernel(const float* __restrict__ partial, int nblocks, int nq, int C, int Cp,
-                    float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                    float* __restrict__ dgamma2, float* __restrict__ dbeta2) {
-    // block = 32 columns (q*Cp + c) x 32 row lanes over the per-block partials
+bn_bwd_final_kernel(const float* __restrict__ partial, int nblocks, int nq, int C, int Cp, int raw,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ mean2,
+                    const float* __restrict__ invstd2, float* __restrict__ sums, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, float* __restrict__ dgamma2, float* __restrict__ dbeta2) {
     __shared__ double sh[32][33];
+    __shared__ double tot[4][32];
     const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
-    const int i = blockIdx.x * 32 + cl;
-    double s = 0.0;
-    if (i < nq * Cp)
-        for (int b = rl; b < nblocks; b += 32) s += (double)partial[(long long)b * 4 * Cp + i];
-    sh[rl][cl] = s;
-    __syncthreads();
-    if (rl != 0 || i >= nq * Cp) return;
-    s = 0.0;
-    for (int r = 0; r < 32; ++r) s += sh[r][cl];
-    const int qi = i / Cp, c = i - qi * Cp;
-    sums[qi * Cp + c] = (float)s;
+    const int c = blockIdx.x * 32 + cl;
+    for (int qi = 0; qi < nq; ++qi) {
+        double s = 0.0;
+        if (c < Cp)
+            for (int b = rl; b < nblocks; b += 32) s += (double)partial[((long long)b * 4 + qi) * Cp + c];
+        sh[rl][cl] = s;
+        __syncthreads();
+        if (rl == 0) {
+            s = 0.0;
+            for (int r = 0; r < 32; ++r) s += sh[r][cl];
+            tot[qi][cl] = s;
+        }
+        __syncthreads();
+    }
+    if (rl != 0 || c >= Cp) return;
+    const double s1 = tot[0][cl];
+    double s2 = tot[1][cl];
+    if (raw) s2 = (double)invstd[c] * (s2 - (double)mean[c] * s1);
+    sums[0 * Cp + c] = (float)s1;
+    sums[1 * Cp + c] = (float)s2;
     if (c < C) {
-        if (qi == 0 && dbeta) dbeta[c] = (float)s;
-        if (qi == 1 && dgamma) dgamma[c] = (float)s;
-        if (qi == 2 && dbeta2) dbeta2[c] = (float)s;
-        if (qi == 3 && dgamma2) dgamma2[c] = (float)s;
+        if (dbeta) dbeta[c] = (float)s1;
+        if (dgamma) dgamma[c] = (float)s2;
+    }
+    if (nq == 4) {
+        double s4 = tot[3][cl];
+        if (raw) s4 = (double)invstd2[c] * (s4 - (double)mean2[c] * s1);
+        sums[2 * Cp + c] = (float)s1;
+        sums[3 * Cp + c] = (float)s4;
+        if (c < C) {
+            if (dbeta2) dbeta2[c] = (float)s1;
+            if (dgamma2) dgamma2[c] = (float)s4;
+        }
     }
 }
 
 // dy = k*(dz - c1 - xhat*c2) with k = gamma*invstd, c1 = mean(dz), c2 = mean(dz*xhat), xhat = (y-mu)*invstd, folded
 // per channel into  dy = A*dz + B*y + D  (A = k, B = -k*c2*invstd, D = k*(c2*invstd*mu - c1)).
 template <bool kHasY2>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, kHasY2 ? 1 : 3)
 bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ out, int relu,
                     const float* __restrict__ mask_scale, const float* __restrict__ mask_shift,
                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean,
@@ -396,30 +425,37 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __
     const int rl = threadIdx.x / V;
     if (rl >= R) return;
     const int c0 = vl << 3;
-    float A[8], Bc[8], D[8], A2[8], B2[8], D2[8], msc[8], msh[8];
+    f32x2 A[4], Bc[4], D[4], A2[4], B2[4], D2[4], msc[4], msh[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = c0 + j;
-        const float gm = (c < C) ? (gamma ? gamma[c] : 1.f) : 0.f;
-        const float is = invstd[c], mu = mean[c];
-        const float k = gm * is;
-        const float c1 = sums[c] * inv_count, c2 = sums[Cp + c] * inv_count;
-        A[j] = k;
-        Bc[j] = -k * c2 * is;
-        D[j] = k * (c2 * is * mu - c1);
-        if (kHasY2) {
-            const float gm2 = (c < C) ? (gamma2 ? gamma2[c] : 1.f) : 0.f;
-            const float is2 = invstd2[c], mu2 = mean2[c];
-            const float k2 = gm2 * is2;
-            const float c22 = sums[3 * Cp + c] * inv_count;
-            A2[j] = k2;
-            B2[j] = -k2 * c22 * is2;
-            D2[j] = k2 * (c22 * is2 * mu2 - c1);
-        } else {
-            A2[j] = B2[j] = D2[j] = 0.f;
+    for (int j = 0; j < 4; ++j) {
+        float a[2], b[2], d[2], a2[2] = {0.f, 0.f}, b2[2] = {0.f, 0.f}, d2[2] = {0.f, 0.f};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = c0 + 2 * j + h;
+            const float gm = (c < C) ? (gamma ? gamma[c] : 1.f) : 0.f;
+            const float is = invstd[c], mu = mean[c];
+            const float k = gm * is;
+            const float c1 = sums[c] * inv_count, c2 = sums[Cp + c] * inv_count;
+            a[h] = k;
+            b[h] = -k * c2 * is;
+            d[h] = k * (c2 * is * mu - c1);
+            if (kHasY2) {
+                const float gm2 = (c < C) ? (gamma2 ? gamma2[c] : 1.f) : 0.f;
+                const float is2 = invstd2[c], mu2 = mean2[c];
+                const float k2 = gm2 * is2;
+                const float c22 = sums[3 * Cp + c] * inv_count;
+                a2[h] = k2;
+                b2[h] = -k2 * c22 * is2;
+                d2[h] = k2 * (c22 * is2 * mu2 - c1);
+            }
         }
-        msc[j] = relu == 2 ? mask_scale[c] : 0.f;
-        msh[j] = relu == 2 ? mask_shift[c] : 0.f;
+        A[j] = f2_make(a[0], a[1]), Bc[j] = f2_make(b[0], b[1]), D[j] = f2_make(d[0], d[1]);
+        A2[j] = f2_make(a2[0], a2[1]), B2[j] = f2_make(b2[0], b2[1]), D2[j] = f2_make(d2[0], d2[1]);
+        msc[j] = msh[j] = 0ull;
+    }
+    if (relu == 2) {
+        load_pairs(mask_scale, c0, msc);
+        load_pairs(mask_shift, c0, msh);
     }
     constexpr int U = 2;
     const long long rstride = (long long)gridDim.x * R;
@@ -441,28 +477,25 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __
             const long long r = r0 + u * rstride;
             if (r >= rows) break;
             const long long e = r * Cp + c0;
-            float gz[8], f[8], o[8];
-            unpack8(vg[u], gz);
-            if (relu == 1) {
-                unpack8(vo[u], f);
+            const uint32_t wg[4] = {vg[u].x, vg[u].y, vg[u].z, vg[u].w};
+            const uint32_t wo[4] = {vo[u].x, vo[u].y, vo[u].z, vo[u].w};
+            const uint32_t wy[4] = {vy[u].x, vy[u].y, vy[u].z, vy[u].w};
+            const uint32_t wy2[4] = {vy2[u].x, vy2[u].y, vy2[u].z, vy2[u].w};
+            uint32_t o[4], o2[4], z[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) gz[j] = f[j] > 0.f ? gz[j] : 0.f;
+            for (int j = 0; j < 4; ++j) {
+                const f32x2 yv = f2_from_bf16x2(wy[j]);
+                uint32_t gw = wg[j];
+                if (relu == 1) gw &= relu_mask2(wo[j]);
+                if (relu == 2) gw &= relu_mask2(f2_to_bf16x2(f2_fma(yv, msc[j], msh[j])));   // mask from the pre-activation
+                z[j] = gw;
+                const f32x2 gz = f2_from_bf16x2(gw);
+                o[j] = f2_to_bf16x2(f2_fma(A[j], gz, f2_fma(Bc[j], yv, D[j])));
+                if (kHasY2) o2[j] = f2_to_bf16x2(f2_fma(A2[j], gz, f2_fma(B2[j], f2_from_bf16x2(wy2[j]), D2[j])));
             }
-            unpack8(vy[u], f);
-            if (relu == 2) {   // ReLU mask recomputed from the pre-activation
-#pragma unroll
-                for (int j = 0; j < 8; ++j) gz[j] = fmaf(f[j], msc[j], msh[j]) > 0.f ? gz[j] : 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], gz[j], fmaf(Bc[j], f[j], D[j]));
-            *reinterpret_cast<uint4*>(dy + e) = pack8(o);
-            if (kHasY2) {
-                unpack8(vy2[u], f);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = fmaf(A2[j], gz[j], fmaf(B2[j], f[j], D2[j]));
-                *reinterpret_cast<uint4*>(dy2 + e) = pack8(o);
-            }
-            if (dz != nullptr) *reinterpret_cast<uint4*>(dz + e) = pack8(gz);
+            *reinterpret_cast<uint4*>(dy + e) = make_uint4(o[0], o[1], o[2], o[3]);
+            if (kHasY2) *reinterpret_cast<uint4*>(dy2 + e) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+            if (dz != nullptr) *reinterpret_cast<uint4*>(dz + e) = make_uint4(z[0], z[1], z[2], z[3]);
         }
     }
 }
@@ -669,7 +702,7 @@ extern "C" size_t zsv_bn_finalize_workspace(int C) {
 extern "C" int zsv_bn_finalize(const float* part_sum, const float* part_sq, int part_rows, int C, long long count,
                                const float* gamma, const float* beta, float* running_mean, float* running_var,
                                float momentum, float eps, float* scale, float* shift, float* mean, float* invstd,
-                               void* workspace, size_t workspace_bytes, void* stream) {
+                               float* bwd_table, void* workspace, size_t workspace_bytes, void* stream) {
     if (!part_sum || !part_sq || !scale || !shift || !mean || !invstd || !workspace)
         return fail(ZSV_ERR_BAD_ARG, "bn_finalize: null pointer");
     if (part_rows < 1 || C < 1 || count < 1) return fail(ZSV_ERR_BAD_ARG, "bn_finalize: bad sizes");
@@ -685,7 +718,7 @@ extern "C" int zsv_bn_finalize(const float* part_sum, const float* part_sq, int 
     double* chunk = (double*)((char*)workspace + kTicketBytes);
     bn_finalize_kernel<<<dim3(ceil_div(Cp, 32), nchunks), 1024, 0, st>>>(
         part_sum, part_sq, part_rows, C, Cp, rows_per_chunk, chunk, tickets, (double)count, gamma, beta, running_mean,
-        running_var, momentum, eps, scale, shift, mean, invstd);
+        running_var, momentum, eps, scale, shift, mean, invstd, (float4*)bwd_table);
     ZSV_LAUNCH_CHECK("bn_finalize_kernel");
     return ZSV_OK;
 }
@@ -768,12 +801,12 @@ extern "C" int zsv_bn_bwd(const void* g, const void* out, int relu, const float*
     }
     if (smem_r > 160 * 1024) return fail(ZSV_ERR_UNSUPPORTED, "bn_bwd: reduction scratch too large");
     if (y2)
-        bn_bwd_reduce_kernel<true><<<nblocks, 256, smem_r, st>>>(gb, ob, relu, mask_scale, mask_shift, yb, mean, invstd, y2b, mean2, invstd2, rows, Cp, R, partial);
+        bn_bwd_reduce_kernel<true><<<nblocks, 256, smem_r, st>>>(gb, ob, relu, mask_scale, mask_shift, yb, y2b, rows, Cp, R, partial);
     else
-        bn_bwd_reduce_kernel<false><<<nblocks, 256, smem_r, st>>>(gb, ob, relu, mask_scale, mask_shift, yb, mean, invstd, y2b, mean2, invstd2, rows, Cp, R, partial);
+        bn_bwd_reduce_kernel<false><<<nblocks, 256, smem_r, st>>>(gb, ob, relu, mask_scale, mask_shift, yb, y2b, rows, Cp, R, partial);
     ZSV_LAUNCH_CHECK("bn_bwd_reduce_kernel");
     const int nq = y2 ? 4 : 2;
-    bn_bwd_final_kernel<<<ceil_div(nq * Cp, 32), 1024, 0, st>>>(partial, nblocks, nq, C, Cp, sums, dgamma, dbeta, dgamma2, dbeta2);
+    bn_bwd_final_kernel<<<ceil_div(Cp, 32), 1024, 0, st>>>(partial, nblocks, nq, C, Cp, 1, mean, invstd, mean2, invstd2, sums, dgamma, dbeta, dgamma2, dbeta2);
     ZSV_LAUNCH_CHECK("bn_bwd_final_kernel");
     const int blocks = (int)std::max<long long>(1, std::min<long long>((long long)sm_count() * 8, ceil_div_ll(rows, (long long)R * 2)));
     const float inv_count = (float)(1.0 / (double)rows);
@@ -781,6 +814,33 @@ extern "C" int zsv_bn_bwd(const void* g, const void* out, int relu, const float*
         bn_bwd_apply_kernel<true><<<blocks, 256, 0, st>>>(gb, ob, relu, mask_scale, mask_shift, yb, mean, invstd, gamma, y2b, mean2, invstd2, gamma2, sums, (__nv_bfloat16*)dy, (__nv_bfloat16*)dy2, (__nv_bfloat16*)dz, rows, C, Cp, R, inv_count);
     else
         bn_bwd_apply_kernel<false><<<blocks, 256, 0, st>>>(gb, ob, relu, mask_scale, mask_shift, yb, mean, invstd, gamma, y2b, mean2, invstd2, gamma2, sums, (__nv_bfloat16*)dy, (__nv_bfloat16*)dy2, (__nv_bfloat16*)dz, rows, C, Cp, R, inv_count);
+    ZSV_LAUNCH_CHECK("bn_bwd_apply_kernel");
+    return ZSV_OK;
+}
+
+extern "C" int zsv_bn_bwd_finish(const void* dz, const void* y, const float* mean, const float* invstd,
+                                 const float* gamma, const float* partial, int partial_rows, void* dy, float* dgamma,
+                                 float* dbeta, long long rows, int C, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+    if (!dz || !y || !mean || !invstd || !partial || !dy || !workspace)
+        return fail(ZSV_ERR_BAD_ARG, "bn_bwd_finish: null pointer");
+    if (partial_rows < 1 || rows < 1) return fail(ZSV_ERR_BAD_ARG, "bn_bwd_finish: bad sizes");
+    const int Cp = cpad(C);
+    if (Cp > kMaxC) return fail(ZSV_ERR_UNSUPPORTED, "bn_bwd_finish: more than %d channels", kMaxC);
+    if (workspace_bytes < 4 * (size_t)Cp * sizeof(float)) return fail(ZSV_ERR_WORKSPACE, "bn_bwd_finish: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* sums = (float*)workspace;
+    bn_bwd_final_kernel<<<ceil_div(Cp, 32), 1024, 0, st>>>(partial, partial_rows, 2, C, Cp, 0, mean, invstd, nullptr, nullptr,
+                                                          sums, dgamma, dbeta, nullptr, nullptr);
+    ZSV_LAUNCH_CHECK("bn_bwd_final_kernel");
+    const int V = Cp >> 3;
+    if (V > 256) return fail(ZSV_ERR_UNSUPPORTED, "bn_bwd_finish: channel pitch too large");
+    const int R = std::max(1, 256 / V);
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((long long)sm_count() * 8, ceil_div_ll(rows, (long long)R * 2)));
+    const float inv_count = (float)(1.0 / (double)rows);
+    bn_bwd_apply_kernel<false><<<blocks, 256, 0, st>>>(
+        (const __nv_bfloat16*)dz, nullptr, 0, nullptr, nullptr, (const __nv_bfloat16*)y, mean, invstd, gamma, nullptr,
+        nullptr, nullptr, nullptr, sums, (__nv_bfloat16*)dy, nullptr, nullptr, rows, C, Cp, R, inv_count);
     ZSV_LAUNCH_CHECK("bn_bwd_apply_kernel");
     return ZSV_OK;
 }

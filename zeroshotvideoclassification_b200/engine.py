@@ -99,6 +99,25 @@ def _conv_for(spec: ConvSpec, N, T, H, W, layout=_lib.X_NDHWC) -> ops.Conv3d:
     return op
 
 
+import os
+
+# fuse the reduction pass of BatchNorm backward into the epilogue of the dgrad that produces its input gradient
+FUSE_BN_BWD = os.environ.get("ZSV_FUSE_BN_BWD", "1") != "0"
+
+# run the weight-gradient GEMMs on a second stream: they only depend on dy, nothing in the backward chain depends on
+# them, and being tensor / L2 bound they overlap with the HBM-bound BatchNorm-backward kernels of the next layer
+OVERLAP_WGRAD = os.environ.get("ZSV_OVERLAP_WGRAD", "1") != "0"
+_side_streams: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _side_streams.get(idx)
+    if st is None:
+        st = _side_streams[idx] = torch.cuda.Stream(device=device)
+    return st
+
+
 _plan_cache: Dict[tuple, tuple] = {}
 
 
@@ -147,6 +166,7 @@ class UnitRec:
     relu: bool
     scale: Optional[torch.Tensor] = None   # forward scale / shift: backward recomputes the ReLU mask from y with them
     shift: Optional[torch.Tensor] = None
+    table: Optional[torch.Tensor] = None   # (scale, shift, invstd, -mean*invstd) per channel for the fused BN backward
 
 
 @dataclass
@@ -166,6 +186,7 @@ class BackboneRunner:
         self.need_grad = need_grad
         self.stem_recs: List[UnitRec] = []
         self.block_recs: List[BlockRec] = []
+        self._side_keep: List[tuple] = []       # tensors in use by weight gradients running on the side stream
         self.packed: Dict[str, tuple] = {}      # bf16 weight images of the whole network, packed in one launch
         self.nbt: List[torch.Tensor] = []       # num_batches_tracked counters, bumped once per forward in one launch
 
@@ -180,9 +201,11 @@ class BackboneRunner:
         wf, wd = pk
         gamma, beta = self.t[spec.bn + ".weight"], self.t[spec.bn + ".bias"]
         rm, rv = self.t[spec.bn + ".running_mean"], self.t[spec.bn + ".running_var"]
+        table = None
         if self.train:
             y, ps, pq = op.fprop(x, wf, stats=True)
-            scale, shift, mean, invstd = ops.bn_finalize(ps, pq, spec.cout, op.out_positions, gamma, beta, rm, rv)
+            scale, shift, mean, invstd, table = ops.bn_finalize(ps, pq, spec.cout, op.out_positions, gamma, beta, rm, rv,
+                                                                want_table=True)
             nbt = self.t.get(spec.bn + ".num_batches_tracked")
             if nbt is not None:
                 self.nbt.append(nbt)
@@ -191,7 +214,7 @@ class BackboneRunner:
             scale, shift = ops.bn_eval_scale_shift(spec.cout, gamma, beta, rm, rv)
             mean = invstd = None
         out = ops.bn_apply(y, scale, shift, spec.cout, relu) if apply_now else None
-        rec = UnitRec(spec, op, x, wd, y, mean, invstd, out, relu, scale, shift) if self.need_grad else None
+        rec = UnitRec(spec, op, x, wd, y, mean, invstd, out, relu, scale, shift, table) if self.need_grad else None
         return out, y, (scale, shift), rec, (op.To, op.Ho, op.Wo)
 
     def forward(self, x_ncdhw: torch.Tensor) -> torch.Tensor:
@@ -234,23 +257,60 @@ class BackboneRunner:
         return out, (N, *d4)
 
     # -- backward ----------------------------------------------------------------------------------
-    def _conv_bwd(self, rec: UnitRec, dy, grads, want, addend=None, need_dx: bool = True):
+    def _conv_bwd(self, rec: UnitRec, dy, grads, want, addend=None, need_dx: bool = True,
+                  producer: Optional[UnitRec] = None):
+        """wgrad + dgrad of rec's convolution.  `producer` is the conv->BN(->ReLU) unit whose output is this
+        convolution's input: when given, the dgrad epilogue also does the reduction pass of that BatchNorm's backward
+        and the return value is (dz, partial, rows) for ``_unit_bwd`` instead of the plain gradient."""
         if want.get(rec.spec.name + ".weight", True):
-            grads[rec.spec.name + ".weight"], _ = rec.op.wgrad(rec.x, dy)
-        return rec.op.dgrad(dy, rec.wd, addend) if need_dx else None
+            if OVERLAP_WGRAD:
+                main = torch.cuda.current_stream(dy.device)
+                side = _side_stream(dy.device)
+                side.wait_stream(main)                     # dy (and x) are complete on the main stream
+                with torch.cuda.stream(side):
+                    dw, _ = rec.op.wgrad(rec.x, dy)
+                # x / dy were allocated on the main stream: keep them referenced until the main stream has joined
+                # the side stream (join_side), so the caching allocator cannot hand their memory out early
+                self._side_keep.append((rec.x, dy, dw))
+                grads[rec.spec.name + ".weight"] = dw
+            else:
+                grads[rec.spec.name + ".weight"], _ = rec.op.wgrad(rec.x, dy)
+        if not need_dx:
+            return None
+        # Fusing pays when the tile's main loop is long compared with its epilogue (few output channels, deep reduction:
+        # the spatial 1x3x3 convolutions); measured on the wide, shallow temporal dgrads it triples their time.
+        op = rec.op
+        deep = op.cout * op.kernel[0] * op.kernel[1] * op.kernel[2] >= 8 * op.cin and op.stride == (1, 1, 1)
+        if producer is not None and FUSE_BN_BWD and deep:
+            return rec.op.dgrad_bn_fused(dy, rec.wd, addend, producer.y, producer.table, producer.relu)
+        return rec.op.dgrad(dy, rec.wd, addend)
 
-    def _unit_bwd(self, rec: UnitRec, gin, grads, want, addend=None, need_dx: bool = True):
-        """gin: gradient w.r.t. rec.out (post BN/ReLU).  Returns the gradient w.r.t. rec.x."""
-        dy, _, _, dgamma, dbeta, _, _ = ops.bn_bwd(gin, None, 2 if rec.relu else 0, rec.y, rec.mean, rec.invstd,
-                                                   self.t[rec.spec.bn + ".weight"], rec.spec.cout,
-                                                   mask_scale=rec.scale, mask_shift=rec.shift)
+    def join_side(self, device) -> None:
+        """Main stream waits for the weight gradients issued so far on the side stream."""
+        if self._side_keep:
+            torch.cuda.current_stream(device).wait_stream(_side_stream(device))
+            self._side_keep = []
+
+    def _unit_bwd(self, rec: UnitRec, gin, grads, want, addend=None, need_dx: bool = True,
+                  producer: Optional[UnitRec] = None):
+        """gin: gradient w.r.t. rec.out (post BN/ReLU), or the (dz, partial, rows) triple of a fused dgrad.
+        Returns the gradient w.r.t. rec.x (same convention, depending on `producer`)."""
+        gamma = self.t[rec.spec.bn + ".weight"]
+        if isinstance(gin, tuple):
+            dz, partial, nrows = gin
+            dy, dgamma, dbeta = ops.bn_bwd_finish(dz, rec.y, rec.mean, rec.invstd, gamma, partial, nrows, rec.spec.cout)
+        else:
+            dy, _, _, dgamma, dbeta, _, _ = ops.bn_bwd(gin, None, 2 if rec.relu else 0, rec.y, rec.mean, rec.invstd,
+                                                       gamma, rec.spec.cout, mask_scale=rec.scale, mask_shift=rec.shift)
         grads[rec.spec.bn + ".weight"] = dgamma
         grads[rec.spec.bn + ".bias"] = dbeta
-        return self._conv_bwd(rec, dy, grads, want, addend, need_dx)
+        return self._conv_bwd(rec, dy, grads, want, addend, need_dx, producer)
 
-    def block_backward(self, brec: BlockRec, g, grads, want):
-        """g: gradient w.r.t. the block output -> gradient w.r.t. the block input (resnet.py:102-113 reversed)."""
+    def block_backward(self, brec: BlockRec, g, grads, want, producer: Optional[UnitRec] = None):
+        """g: gradient w.r.t. the block output -> gradient w.r.t. the block input (resnet.py:102-113 reversed).
+        `producer`: the unit that produced the block input when it is a plain conv->BN->ReLU (the stem)."""
         tail, ds = brec.units[3], brec.ds
+        u = brec.units
         if ds is not None:
             dy_t, dy_d, _, dg, db, dg2, db2 = ops.bn_bwd(
                 g, brec.out, True, tail.y, tail.mean, tail.invstd, self.t[tail.spec.bn + ".weight"],
@@ -262,13 +322,13 @@ class BackboneRunner:
                 g, brec.out, True, tail.y, tail.mean, tail.invstd, self.t[tail.spec.bn + ".weight"],
                 tail.spec.cout, want_dz=True)
         grads[tail.spec.bn + ".weight"], grads[tail.spec.bn + ".bias"] = dg, db
-        ga = self._conv_bwd(tail, dy_t, grads, want)              # grad w.r.t. spatial2 output
-        ga = self._unit_bwd(brec.units[2], ga, grads, want)       # -> grad w.r.t. block conv1 output
-        ga = self._unit_bwd(brec.units[1], ga, grads, want)       # -> grad w.r.t. spatial1 output
+        ga = self._conv_bwd(tail, dy_t, grads, want, producer=u[2])          # grad w.r.t. spatial2 output
+        ga = self._unit_bwd(u[2], ga, grads, want, producer=u[1])            # -> grad w.r.t. block conv1 output
+        ga = self._unit_bwd(u[1], ga, grads, want, producer=u[0])            # -> grad w.r.t. spatial1 output
         if ds is not None:
-            gx = self._unit_bwd(brec.units[0], ga, grads, want)   # main branch
-            return self._conv_bwd(ds, dy_d, grads, want, addend=gx)   # + projected shortcut
-        return self._unit_bwd(brec.units[0], ga, grads, want, addend=dz)  # + identity shortcut
+            gx = self._unit_bwd(u[0], ga, grads, want)                       # main branch
+            return self._conv_bwd(ds, dy_d, grads, want, addend=gx)          # + projected shortcut
+        return self._unit_bwd(u[0], ga, grads, want, addend=dz, producer=producer)   # + identity shortcut
 
     def backward(self, g: torch.Tensor, want: Dict[str, bool]) -> Dict[str, torch.Tensor]:
         """g: gradient w.r.t. the backbone output (bf16 NDHWC).  Returns grads keyed by parameter name."""
@@ -279,15 +339,19 @@ class BackboneRunner:
         sync = zdist.active_grad_sync()
         grads: Dict[str, torch.Tensor] = {}
         g = g.contiguous()
-        for brec in reversed(self.block_recs):
+        for bi in range(len(self.block_recs) - 1, -1, -1):
+            brec = self.block_recs[bi]
             blk: Dict[str, torch.Tensor] = {}
-            g = self.block_backward(brec, g, blk, want)
+            # the first block's input is the stem's conv->BN->ReLU output: its BatchNorm backward is fused as well
+            g = self.block_backward(brec, g, blk, want, producer=self.stem_recs[1] if bi == 0 else None)
             if sync is not None:
+                self.join_side(g[0].device if isinstance(g, tuple) else g.device)
                 sync.submit(blk)          # all-reduce of this block overlaps the next block's backward
             grads.update(blk)
         blk = {}
-        ga = self._unit_bwd(self.stem_recs[1], g, blk, want)
+        ga = self._unit_bwd(self.stem_recs[1], g, blk, want, producer=self.stem_recs[0])
         self._unit_bwd(self.stem_recs[0], ga, blk, want, need_dx=False)
+        self.join_side(self.stem_recs[0].y.device)
         if sync is not None:
             sync.submit(blk)
             grads.update(blk)

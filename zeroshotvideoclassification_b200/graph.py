@@ -43,7 +43,10 @@ class GraphedStep:
 
         saved = self._snapshot(model, optimizer)
         cur = torch.cuda.current_stream(dev)
-        side = torch.cuda.Stream(device=dev)
+        # Warm up and capture on a HIGH-priority stream: streams the step forks internally (the weight-gradient stream
+        # of engine.py) keep the default, lower priority, so the block scheduler serves the dependent chain first and
+        # fills the gaps with the independent weight-gradient CTAs.
+        side = torch.cuda.Stream(device=dev, priority=-1)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):
@@ -53,7 +56,7 @@ class GraphedStep:
 
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
-        with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
+        with torch.cuda.graph(self.graph, stream=side, capture_error_mode=capture_error_mode):
             self.static_outputs = fn(*self.static_inputs)
         #: kernels of libzsv_b200.so inside one replay (the host-side launch counter does not see replays)
         self.launches_per_replay = _lib.launch_count() - n0

@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import ConvDesc, check, cpad, ptr
+from ._lib import BnBwdFuse, ConvDesc, check, cpad, ptr
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
@@ -115,9 +115,22 @@ class Conv3d:
     def dgrad(self, dy, wd, addend=None):
         dx = torch.empty((self.N, self.T, self.H, self.W, cpad(self.cin)), dtype=torch.bfloat16, device=dy.device)
         with _Timed("dgrad", self):
-            check(self.lib.zsv_conv3d_dgrad(C.byref(self.desc), ptr(dy), ptr(wd), ptr(dx), ptr(addend), _stream()),
+            check(self.lib.zsv_conv3d_dgrad(C.byref(self.desc), ptr(dy), ptr(wd), ptr(dx), ptr(addend), None, _stream()),
                   "zsv_conv3d_dgrad")
         return dx
+
+    def dgrad_bn_fused(self, dy, wd, addend, y_prev, bn_table, relu: bool):
+        """dgrad whose epilogue also does the first pass of the backward of the BatchNorm (+ReLU) that produced this
+        convolution's input (zsv_bn_bwd_fuse).  Returns (dz, partial, rows): dz = g * ReLU mask (bf16, shape of the
+        input), partial = fp32 [rows][4][cpad(Cin)] per-CTA sums for ``bn_bwd_finish``."""
+        dz = torch.empty((self.N, self.T, self.H, self.W, cpad(self.cin)), dtype=torch.bfloat16, device=dy.device)
+        cap = 8 * self.lib.zsv_sm_count()
+        partial = torch.empty((cap, 4, cpad(self.cin)), dtype=torch.float32, device=dy.device)
+        f = BnBwdFuse(ptr(y_prev), ptr(bn_table), int(relu), ptr(partial), cap, 0)
+        with _Timed("dgrad", self):
+            check(self.lib.zsv_conv3d_dgrad(C.byref(self.desc), ptr(dy), ptr(wd), ptr(dz), ptr(addend), C.byref(f),
+                                            _stream()), "zsv_conv3d_dgrad")
+        return dz, partial, int(f.rows_written)
 
     def wgrad(self, x, dy, want_bias: bool = False):
         dw = torch.empty((self.cout, self.cin, *self.kernel), dtype=torch.float32, device=dy.device)
@@ -207,16 +220,33 @@ def ncdhw_to_ndhwc(x: torch.Tensor) -> torch.Tensor:
 # batch norm
 # ------------------------------------------------------------------------------------------------
 def bn_finalize(ps, pq, channels: int, count: int, gamma, beta, running_mean, running_var,
-                momentum: float = BN_MOMENTUM, eps: float = BN_EPS):
+                momentum: float = BN_MOMENTUM, eps: float = BN_EPS, want_table: bool = False):
+    """-> (scale, shift, mean, invstd[, table]); table = fp32 [cpad(C)][4] constants for the fused BN backward."""
     lib = _lib.load()
     cp = cpad(channels)
-    out = torch.empty((4, cp), dtype=torch.float32, device=ps.device)
+    out = torch.empty((8 if want_table else 4, cp), dtype=torch.float32, device=ps.device)
     scale, shift, mean, invstd = out[0], out[1], out[2], out[3]
+    table = out[4:8].view(cp, 4) if want_table else None
     ws = workspace(lib.zsv_bn_finalize_workspace(channels), ps.device, "bn_finalize")
     check(lib.zsv_bn_finalize(ptr(ps), ptr(pq), ps.shape[0], channels, count, ptr(gamma), ptr(beta),
                               ptr(running_mean), ptr(running_var), momentum, eps, ptr(scale), ptr(shift), ptr(mean),
-                              ptr(invstd), ptr(ws), ws.numel(), _stream()), "zsv_bn_finalize")
+                              ptr(invstd), ptr(table), ptr(ws), ws.numel(), _stream()), "zsv_bn_finalize")
+    if want_table:
+        return scale, shift, mean, invstd, table
     return scale, shift, mean, invstd
+
+
+def bn_bwd_finish(dz, y, mean, invstd, gamma, partial, partial_rows: int, channels: int):
+    """Second pass of BatchNorm backward from the sums a fused dgrad left behind -> (dy, dgamma, dbeta)."""
+    lib = _lib.load()
+    rows = y.numel() // y.shape[-1]
+    dy = torch.empty_like(y)
+    dgb = torch.empty((2, channels), dtype=torch.float32, device=y.device)
+    ws = workspace(4 * cpad(channels) * 4, y.device, "bn_bwd_finish")
+    check(lib.zsv_bn_bwd_finish(ptr(dz), ptr(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(partial), partial_rows, ptr(dy),
+                                ptr(dgb[1]), ptr(dgb[0]), rows, channels, ptr(ws), ws.numel(), _stream()),
+          "zsv_bn_bwd_finish")
+    return dy, dgb[1], dgb[0]
 
 
 def bn_eval_scale_shift(channels: int, gamma, beta, running_mean, running_var, eps: float = BN_EPS):
