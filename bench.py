@@ -350,6 +350,11 @@ def run_b200(args):
                                  f"{n / prof_steps:4.0f} {1e3 * ms / n:9.1f} {fl / (ms / 1e3) / 1e12:8.1f} "
                                  f"{ms / prof_steps:7.3f}\n")
     peaks = load_peaks()
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_conv_dram_traffic.json")
+    if os.path.exists(tpath):       # dram__bytes_read+write per launch of the same kernels, from the committed ncu capture
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/r01_conv_dram_traffic.json (ncu, per launch)"
     km = {k: {"ms_per_step": v["ms"] / prof_steps, "calls_per_step": v["calls"] / prof_steps,
               "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 else None,
               "share_of_step": (v["ms"] / prof_steps) / ms_per_step} for k, v in kinds.items()}
@@ -360,7 +365,8 @@ def run_b200(args):
     roofline = {
         "bound": "tensor", "kernel": "igemm_kmajor_kernel (conv fprop + dgrad, tcgen05/TMA implicit GEMM)",
         "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-        "frac": (achieved / peaks["tflops_sustained"]) if achieved else None, "traffic": None,
+        "frac": (achieved / peaks["tflops_sustained"]) if achieved else None, "traffic": traffic,
+        "traffic_source": traffic_src,
         "peak_source": peaks["source"] + ", bf16_tflops_sustained (kernel timed inside a long step)",
         "avg_launch_ms": dom_ms / dom_calls if dom_calls else None,
         "flops_per_launch": dom_fl / dom_calls if dom_calls else None,
