@@ -55,11 +55,11 @@ def synthetic_batch(B, T, H, W, seed, n_classes=101):
     return x, cls[labels], labels
 
 
-def reference_step(network, B, T, H, W, seed):
+def reference_step(network, B, T, H, W, seed, arch="r2plus1d_18"):
     """main.py:170-195 on the reference modules (fp32 CPU, no optimizer step), with forward hooks recording
     every conv / block output."""
     torch.manual_seed(seed)
-    opt = SimpleNamespace(network="r2plus1d_18", fixconvs=False, nopretrained=False)
+    opt = SimpleNamespace(network=arch, fixconvs=False, nopretrained=False)
     model = network.get_network(opt).train()
     init = {k: checksum(v) for k, v in model.state_dict().items() if v.is_floating_point()}
     keys = {k: list(v.shape) for k, v in model.state_dict().items()}
@@ -82,7 +82,7 @@ def reference_step(network, B, T, H, W, seed):
     dead = sorted(k for k, p in model.named_parameters() if p.grad is None)
     bn_after = {k: checksum(v) for k, v in model.state_dict().items()
                 if k.endswith(("running_mean", "running_var")) and k.startswith("model.")}
-    return dict(config=dict(B=B, T=T, H=H, W=W, seed=seed), emb=emb.detach().numpy().tolist(), loss=float(loss),
+    return dict(config=dict(B=B, T=T, H=H, W=W, seed=seed, arch=arch), emb=emb.detach().numpy().tolist(), loss=float(loss),
                 acts=acts, grads=grads, dead=dead, bn_after=bn_after), init, keys
 
 
@@ -116,6 +116,11 @@ def main():
     json.dump(small, open(os.path.join(OUT, "r2plus1d_step_small.json"), "w"))
     full, _, _ = reference_step(network, 2, 16, 112, 112, seed=0)   # BASELINE.json config 1
     json.dump(full, open(os.path.join(OUT, "r2plus1d_step_bs2_16x112.json"), "w"))
+    # r3d_18 (network.py:28-30): the third backbone get_network can select
+    r3d, r3d_init, r3d_keys = reference_step(network, 2, 8, 32, 32, seed=0, arch="r3d_18")
+    json.dump(r3d_keys, open(os.path.join(OUT, "r3d_state_dict_keys.json"), "w"), indent=0)
+    json.dump(r3d_init, open(os.path.join(OUT, "r3d_init_seed0.json"), "w"))
+    json.dump(r3d, open(os.path.join(OUT, "r3d_step_small.json"), "w"))
     nearest_fixture()
     print("golden fixtures written to", OUT)
 

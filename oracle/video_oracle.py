@@ -164,6 +164,41 @@ def r2plus1d_18_features(sd: Dict[str, Tensor], x: Tensor, train: bool = True, t
     return x
 
 
+def _simple_block(net: _Net, x: Tensor, prefix: str, stride: int, has_ds: bool) -> Tensor:
+    """BasicBlock.forward (resnet.py:102-113) over Conv3DSimple 3x3x3 convolutions (resnet.py:18-34)."""
+    residual = x
+    out = net.conv(x, prefix + ".conv1.0", (stride, stride, stride), (1, 1, 1))
+    out = net.act(F.relu(net.bn(out, prefix + ".conv1.1")), prefix + ".conv1.1")
+    out = net.conv(out, prefix + ".conv2.0", (1, 1, 1), (1, 1, 1))
+    out = net.bn(out, prefix + ".conv2.1")
+    if has_ds:
+        residual = net.conv(x, prefix + ".downsample.0", (stride, stride, stride), (0, 0, 0))
+        residual = net.bn(residual, prefix + ".downsample.1")
+    out = net.act(F.relu(out + residual))
+    if net.trace is not None:
+        if out.requires_grad:
+            out.retain_grad()
+        net.trace[prefix] = out
+    return out
+
+
+def r3d_18_features(sd: Dict[str, Tensor], x: Tensor, train: bool = True, trace: Optional[dict] = None,
+                    prefix: str = "model.", emulate_bf16: bool = False) -> Tensor:
+    """VideoResNet.forward up to layer4 (resnet.py:243-249) for r3d_18 (resnet.py:293-314): BasicStem
+    (resnet.py:165-173), then layers=[2,2,2,2] of BasicBlock over Conv3DSimple."""
+    net = _Net({k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}, train, trace, emulate_bf16)
+    if emulate_bf16:
+        x = _RoundBf16Fwd.apply(x)
+    x = net.conv(x, "stem.0", (1, 2, 2), (1, 3, 3))
+    x = net.act(F.relu(net.bn(x, "stem.1")))
+    if trace is not None:
+        trace["stem"] = x
+    for li, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):
+        x = _simple_block(net, x, f"layer{li}.0", stride, has_ds=(li != 1))
+        x = _simple_block(net, x, f"layer{li}.1", 1, has_ds=False)
+    return x
+
+
 def embedding_head(sd: Dict[str, Tensor], feats: Tensor) -> Tensor:
     """network.py:595-596 with MLP network.py:613-618: mean over (T,H,W), Linear-ReLU-Linear, F.normalize."""
     f = feats.mean(dim=(2, 3, 4))
@@ -173,11 +208,13 @@ def embedding_head(sd: Dict[str, Tensor], feats: Tensor) -> Tensor:
 
 
 def model_forward(sd: Dict[str, Tensor], x: Tensor, train: bool = True, trace: Optional[dict] = None,
-                  emulate_bf16: bool = False) -> Tensor:
-    """network.Model.forward (network.py:533-600), live lines only: x [B,nc,3,T,H,W] -> emb [B*nc,300]."""
+                  emulate_bf16: bool = False, arch: str = "r2plus1d_18") -> Tensor:
+    """network.Model.forward (network.py:533-600), live lines only: x [B,nc,3,T,H,W] -> emb [B*nc,300].
+    arch selects the backbone like network.get_network (network.py:28-33)."""
     bs, nc = x.shape[:2]
     x = x.reshape(bs * nc, *x.shape[2:])
-    feats = r2plus1d_18_features(sd, x, train, trace, emulate_bf16=emulate_bf16)
+    backbone = r3d_18_features if "r3d" in arch else r2plus1d_18_features
+    feats = backbone(sd, x, train, trace, emulate_bf16=emulate_bf16)
     if trace is not None:
         trace["feats"] = feats
     return embedding_head(sd, feats)
@@ -220,13 +257,14 @@ def mse_loss(emb: Tensor, target: Tensor) -> Tensor:
 
 
 def train_step_grads(sd: Dict[str, Tensor], x: Tensor, target: Tensor, trace: Optional[dict] = None,
-                     loss_scale: float = 1.0, emulate_bf16: bool = False) -> Tuple[Tensor, Tensor, Dict[str, Tensor]]:
+                     loss_scale: float = 1.0, emulate_bf16: bool = False,
+                     arch: str = "r2plus1d_18") -> Tuple[Tensor, Tensor, Dict[str, Tensor]]:
     """One forward + backward of main.py:170-195 (no optimizer): returns (emb, loss, grads by state-dict key)."""
     params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()
               and not k.endswith(("running_mean", "running_var"))}
     work = dict(sd)
     work.update(params)
-    emb = model_forward(work, x, train=True, trace=trace, emulate_bf16=emulate_bf16)
+    emb = model_forward(work, x, train=True, trace=trace, emulate_bf16=emulate_bf16, arch=arch)
     loss = mse_loss(emb, target)
     (loss * loss_scale).backward()
     grads = {k: p.grad for k, p in params.items() if p.grad is not None}

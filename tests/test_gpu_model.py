@@ -158,7 +158,7 @@ def test_per_layer_activations_small():
         errs[rec.spec.name] = rel_err(got, trace[rec.spec.name])
         errs32[rec.spec.name] = rel_err(got, trace32[rec.spec.name])
     for spec, b in zip(engine.BLOCK_SPECS, runner.block_recs):
-        got = from_ndhwc(b.out, spec.convs[3].cout)
+        got = from_ndhwc(b.out, spec.convs[-1].cout)
         errs[spec.prefix] = rel_err(got, trace[spec.prefix])
         errs32[spec.prefix] = rel_err(got, trace32[spec.prefix])
     print("per-layer activation rel err vs emu :", {k: f"{v:.2e}" for k, v in errs.items()})
@@ -257,3 +257,56 @@ def test_variable_batch_and_fixconvs():
         assert emb.shape == (B, 300)
     assert model.model.stem[0].weight.grad is None
     assert model.output2emb_proj.layers[0].weight.grad is not None
+
+
+def test_r3d_18_forward_backward_vs_oracle():
+    """r3d_18 (network.py:28-30; 3x3x3 convolutions incl. stride (2,2,2) and the 3x7x7 stem) through the same kernels.
+    Embedding and loss must match the rounding-matched oracle within 1e-2.  Gradients of a 20-BatchNorm network at
+    batch 4 sit on the ReLU-mask noise floor of bf16 storage (a handful of flipped masks among the 4x512 hidden units
+    of the head alone is a 7 % rms change): the rounding-matched oracle itself is 11-16 % away
+    from the fp32 oracle there, so the gate is that the kernels are no further from fp32 than that oracle is."""
+    import statistics
+    from zeroshotvideoclassification_b200 import video_models as vm
+    B, T, H, W = 4, 8, 64, 64
+    torch.manual_seed(5)
+    model = vm.get_network(vm.default_opt("r3d_18"))
+    g = torch.Generator().manual_seed(6)
+    for name, m in model.named_modules():
+        if isinstance(m, torch.nn.BatchNorm3d):
+            m.weight.data = 0.5 + torch.rand(m.weight.shape, generator=g)
+            m.bias.data = 0.2 * torch.randn(m.bias.shape, generator=g)
+            if name.endswith("conv2.1"):
+                m.weight.data *= 0.1
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    x = torch.randn(B, 1, 3, T, H, W, generator=g)
+    cls = F.normalize(torch.randn(101, 300, generator=g))
+    z = cls[torch.randint(0, 101, (B,), generator=g)]
+    emb_emu, loss_emu, grads_emu = vo.train_step_grads({k: v.clone() for k, v in sd.items()}, x, z, emulate_bf16=True,
+                                                       arch="r3d_18")
+    emb_ref, loss_ref, grads_ref = vo.train_step_grads({k: v.clone() for k, v in sd.items()}, x, z, arch="r3d_18")
+    model = model.cuda().train()
+    emb, none = model(x.cuda())
+    assert none is None
+    loss = torch.nn.MSELoss()(emb, z.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    assert rel_err(emb.detach().cpu(), emb_emu) < 1e-2
+    assert abs(float(loss.detach()) - float(loss_emu)) < 1e-2 * abs(float(loss_emu))
+    ours32, emu32, ours_emu = [], [], {}
+    for name, p in model.named_parameters():
+        if name not in grads_ref:
+            assert p.grad is None, name          # dead in the reference (network.py:500-517)
+            continue
+        assert p.grad is not None and p.grad.dtype == torch.float32 and p.grad.shape == p.shape, name
+        gr = p.grad.cpu()
+        ours32.append(rms_rel_err(gr, grads_ref[name]))
+        emu32.append(rms_rel_err(grads_emu[name], grads_ref[name]))
+        ours_emu[name] = rms_rel_err(gr, grads_emu[name])
+    print("r3d_18 gradient rms-rel error: ours-vs-fp32 median %.2e | emu-vs-fp32 median %.2e | ours-vs-emu median %.2e max %.2e"
+          % (statistics.median(ours32), statistics.median(emu32), statistics.median(ours_emu.values()),
+             max(ours_emu.values())))
+    assert statistics.median(ours32) < max(3e-2, 1.5 * statistics.median(emu32))
+    # the last Linear sees no ReLU mask downstream: its gradient is a clean check of the head arithmetic
+    assert ours_emu["output2emb_proj.layers.1.weight"] < 1e-2
+    # a wrong kernel shows up as an O(1) error from some layer downwards, far above the noise floor
+    assert max(ours_emu.values()) < 0.5, sorted(ours_emu.items(), key=lambda kv: -kv[1])[:5]

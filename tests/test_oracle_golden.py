@@ -121,3 +121,41 @@ def test_compute_accuracy_restatement():
     pred[:50] = cls[(labels[:50] + 1) % 20]                 # 25 % wrong on purpose
     top1, top5 = no.compute_accuracy(pred, cls, true)
     assert top1 == 75.0 and top5 >= top1
+
+
+# ---- r3d_18: the third backbone network.get_network can select (network.py:28-30, resnet.py:293-314) ----
+@pytest.fixture(scope="module")
+def seeded_r3d():
+    from zeroshotvideoclassification_b200 import video_models as vm
+    torch.manual_seed(0)
+    return vm.get_network(vm.default_opt("r3d_18"))
+
+
+def test_r3d_module_tree_and_init_match_reference(seeded_r3d):
+    gold = _load("r3d_state_dict_keys.json")
+    got = {k: list(v.shape) for k, v in seeded_r3d.state_dict().items()}
+    assert list(got.keys()) == list(gold.keys()) and got == gold
+    assert sum(v.numel() for v in seeded_r3d.model.parameters()) == 33_371_472   # torchvision meta for r3d_18
+    init = _load("r3d_init_seed0.json")
+    for k, v in seeded_r3d.state_dict().items():
+        if v.is_floating_point():
+            c = checksum(v)
+            assert c["sum"] == init[k]["sum"] and c["samples"] == init[k]["samples"], k
+
+
+def test_oracle_reproduces_reference_r3d_step(seeded_r3d):
+    gold = _load("r3d_step_small.json")
+    cfg = gold["config"]
+    sd = {k: v.detach().clone() for k, v in seeded_r3d.state_dict().items()}
+    x, z, _ = synthetic_batch(cfg["B"], cfg["T"], cfg["H"], cfg["W"], cfg["seed"] + 100)
+    trace = {}
+    emb, loss, grads = vo.train_step_grads(sd, x, z, trace=trace, arch="r3d_18")
+    assert torch.allclose(emb, torch.tensor(gold["emb"]), atol=2e-5, rtol=1e-4)
+    assert _close(float(loss), gold["loss"], 1e-5)
+    for name, g in gold["acts"].items():
+        _check_sum(trace[name], g, 2e-4, name)
+    assert sorted(gold["grads"]) == sorted(grads.keys())
+    for name, g in gold["grads"].items():
+        _check_sum(grads[name], g, 1e-2 if grads[name].dim() == 1 else 2e-3, name)
+    for name in gold["dead"]:
+        assert name not in grads

@@ -1,3 +1,3 @@
-python -m pytest tests/test_gpu_graph.py -m gpu -x -q 2>&1 | tail -3 > gpurun_out/pytest_gpu.log
-python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench11.json 2> gpurun_out/bench11.err
-tail -4 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/bench11.err
+python tools/debug_r3d.py 2>/dev/null | grep -E "emb err|proj|stem|layer4.1|layer4.0.conv1.0|layer1.0.conv1.0.w" > gpurun_out/r3d_a.log
+ZSV_FUSE_BN_BWD=0 ZSV_OVERLAP_WGRAD=0 python tools/debug_r3d.py 2>/dev/null | grep -E "emb err|proj|stem|layer4.1|layer4.0.conv1.0|layer1.0.conv1.0.w" > gpurun_out/r3d_b.log
+echo "== default"; cat gpurun_out/r3d_a.log; echo "== no fuse, no overlap"; cat gpurun_out/r3d_b.log

@@ -84,7 +84,10 @@ int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, c
 // kernel argument blocks
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxTaps = 32;
-constexpr int kMaxMaps = 4;
+constexpr int kMaxMaps = 8;    // parity planes of a convolution with stride 2 in all three dimensions (r3d_18)
+struct alignas(64) MapPack {
+    CUtensorMap m[kMaxMaps];
+};
 constexpr uint32_t kPanelBytes = 128 * 128;  // 128 rows x 128 B
 constexpr int kWfoldWpad = 8;                // extra W columns of the ZSV_CONV_X_WFOLD layout
 
@@ -436,8 +439,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMa
 //                 barriers) that bounds the whole kernel, hence the wide group.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kIgemmThreads, 1)
-igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                    const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
                     const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
                     const __grid_constant__ IgemmArgs P) {
     extern __shared__ uint8_t smem_raw[];
@@ -501,7 +503,7 @@ igemm_kmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             const int w0 = iw * P.bw, h0 = ih * P.bh, t0 = itt * P.bt, n0 = in_ * P.bn;
             for (int tp = 0; tp < P.ntaps; ++tp) {
                 const Tap tap = P.taps[tp];
-                const CUtensorMap* mp = tap.map == 0 ? &mapA0 : (tap.map == 1 ? &mapA1 : (tap.map == 2 ? &mapA2 : &mapA3));
+                const CUtensorMap* mp = &mapsA.m[tap.map];
                 for (int c0 = 0; c0 < P.kdim; c0 += 64) {
                     mbar_wait(barEmpty + 8u * stage, phase ^ 1u);
                     if (leader) {
@@ -654,6 +656,7 @@ struct HaloArgs {
     FastDiv fd_tl0, fd_tl1, fd_tl2;
     int32_t debug;
     int32_t pf_dist;     // L2 prefetch distance in tiles (0 = off)
+    int32_t unaligned_mode;  // experiment: tap shifts that are not whole swizzle atoms (1: plain address, 2: + base offset)
     int32_t scratch_bytes;   // epilogue scratch in shared memory (BN-backward fusion sums), multiple of 1 KB
     int32_t bn_relu;
     const __nv_bfloat16* bn_y;
@@ -811,15 +814,18 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                         uint32_t b_lo = b_chunk_lo + static_cast<uint32_t>(P.tap0 + cp * P.tap_dcp) * tap_bytes16;
                         const uint32_t b_step = static_cast<uint32_t>(P.tap_dsh) * tap_bytes16;   // may wrap (negative step)
                         for (int sh = 0; sh < P.S; ++sh) {
-                            umma_bf16_lohi(tacc, a_lo, dhi, b_lo, dhi, idesc, acc);
+                            // experiment: matrix start not on a swizzle-atom boundary -> descriptor base offset (bits 49-51)
+                            const uint32_t ahi = P.unaligned_mode == 2
+                                                     ? (dhi | ((static_cast<uint32_t>(sh * inner_rows) & 7u) << 17)) : dhi;
+                            umma_bf16_lohi(tacc, a_lo, ahi, b_lo, dhi, idesc, acc);
                             acc = 1;
                             if (ksteps == 4) {   // common case: straight-line, constant accumulate flag
-                                umma_bf16_lohi(tacc, a_lo + 2u, dhi, b_lo + 2u, dhi, idesc, 1u);
-                                umma_bf16_lohi(tacc, a_lo + 4u, dhi, b_lo + 4u, dhi, idesc, 1u);
-                                umma_bf16_lohi(tacc, a_lo + 6u, dhi, b_lo + 6u, dhi, idesc, 1u);
+                                umma_bf16_lohi(tacc, a_lo + 2u, ahi, b_lo + 2u, dhi, idesc, 1u);
+                                umma_bf16_lohi(tacc, a_lo + 4u, ahi, b_lo + 4u, dhi, idesc, 1u);
+                                umma_bf16_lohi(tacc, a_lo + 6u, ahi, b_lo + 6u, dhi, idesc, 1u);
                             } else {
                                 for (int k = 1; k < ksteps; ++k)
-                                    umma_bf16_lohi(tacc, a_lo + 2u * k, dhi, b_lo + 2u * k, dhi, idesc, 1u);
+                                    umma_bf16_lohi(tacc, a_lo + 2u * k, ahi, b_lo + 2u * k, dhi, idesc, 1u);
                             }
                             a_lo += shift16;
                             b_lo += b_step;
@@ -905,8 +911,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 // grid = (panel pairs, N tiles, splits).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(192, 1)
-wgrad_mnmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+wgrad_mnmajor_kernel(const __grid_constant__ MapPack mapsA,
                      const __grid_constant__ CUtensorMap mapB, const __grid_constant__ WgradArgs P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -959,7 +964,7 @@ wgrad_mnmajor_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
             const int tp = p / P.kchunks;
             c0j[j] = (p - tp * P.kchunks) << 6;
             tapj[j] = P.taps[tp];
-            mpj[j] = tapj[j].map == 0 ? &mapA0 : (tapj[j].map == 1 ? &mapA1 : (tapj[j].map == 2 ? &mapA2 : &mapA3));
+            mpj[j] = &mapsA.m[tapj[j].map];
         }
         // position-tile coordinates advance incrementally with the k-block index
         int m = kb0;
@@ -1516,7 +1521,9 @@ int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtenso
         a.bn_partial = fuse->partial + (size_t)fuse->rows_used * 4 * a.ncols;
         fuse->rows_used += grid;
     }
-    igemm_kmajor_kernel<<<grid, kIgemmThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], mapB, mapOut, a);
+    MapPack pack;
+    for (int i = 0; i < kMaxMaps; ++i) pack.m[i] = maps[i];
+    igemm_kmajor_kernel<<<grid, kIgemmThreads, smem, stream>>>(pack, mapB, mapOut, a);
     ZSV_LAUNCH_CHECK("igemm_kmajor_kernel");
     return ZSV_OK;
 }
@@ -1575,8 +1582,8 @@ HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int k
             }
     if (const char* e = getenv("ZSV_DEBUG_HALO_BOX")) {   // tuning aid: force the box "b0,b1,b2,b3"
         int q[4];
-        if (sscanf(e, "%d,%d,%d,%d", &q[0], &q[1], &q[2], &q[3]) == 4 && (q[0] * q[1] * q[2]) % 8 == 0 &&
-            q[0] * q[1] * q[2] * q[3] <= 128)
+        if (sscanf(e, "%d,%d,%d,%d", &q[0], &q[1], &q[2], &q[3]) == 4 &&
+            ((q[0] * q[1] * q[2]) % 8 == 0 || getenv("ZSV_DEBUG_HALO_UNALIGNED")) && q[0] * q[1] * q[2] * q[3] <= 128)
             for (int i = 0; i < 4; ++i) p.b[i] = q[i];
         best = 1;
     }
@@ -1662,6 +1669,7 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
     a.fd_tl0 = make_fastdiv(p.tl[0]), a.fd_tl1 = make_fastdiv(p.tl[1]), a.fd_tl2 = make_fastdiv(p.tl[2]);
     if (const char* e = getenv("ZSV_DEBUG_EPI")) a.debug = atoi(e);
     a.pf_dist = 3;
+    if (const char* e = getenv("ZSV_DEBUG_HALO_UNALIGNED")) a.unaligned_mode = atoi(e);
     if (const char* e = getenv("ZSV_DEBUG_PF")) a.pf_dist = atoi(e);
     a.a_stage_bytes = p.a_stage_bytes, a.b_main_bytes = p.b_main_bytes, a.b_tail_bytes = p.b_tail_bytes;
     a.b_total_bytes = p.b_total_bytes;
@@ -2004,7 +2012,7 @@ extern "C" int zsv_conv3d_dgrad(const zsv_conv_desc* d, const void* dy, const vo
                 CUtensorMap maps[kMaxMaps];
                 rc = make_plain_map(&maps[0], dy, d->N, s.To, s.Ho, s.Wo, d->Cout, s.coutp, b);
                 if (rc) return rc;
-                maps[1] = maps[2] = maps[3] = maps[0];
+                for (int i = 1; i < kMaxMaps; ++i) maps[i] = maps[0];
                 CUtensorMap mapB;
                 uint64_t dims[3] = {(uint64_t)d->Cout, (uint64_t)d->Cin, (uint64_t)s.ntaps};
                 uint64_t strides[2] = {(uint64_t)s.coutp * 2, (uint64_t)s.coutp * 2 * d->Cin};
@@ -2055,7 +2063,9 @@ int plan_wgrad(const zsv_conv_desc* d, const Shape& s, WgradPlan* p) {
     p->kb_per_split = ceil_div(p->num_kb, splits);
     p->splits = ceil_div(p->num_kb, p->kb_per_split);
     const int stage = (2 + p->nbp) * kPanelBytes;
-    p->stages = std::max(1, std::min(4, (227 * 1024 - 2048) / stage));
+    int smem_cap = 227 * 1024;
+    if (const char* e = getenv("ZSV_DEBUG_WGRAD_SMEM_KB")) smem_cap = std::min(smem_cap, std::max(64, atoi(e)) * 1024);
+    p->stages = std::max(1, std::min(4, (smem_cap - 2048) / stage));
     p->ci_pitch = s.wfold ? 64 : s.cinp;
     p->co_pitch = p->n_tiles * p->bn_tile;
     p->ws_bytes = (size_t)p->splits * s.ftaps * p->ci_pitch * p->co_pitch * 4;
@@ -2119,7 +2129,9 @@ extern "C" int zsv_conv3d_wgrad(const zsv_conv_desc* d, const void* x, const voi
         return fail(ZSV_ERR_CUDA, "cudaFuncSetAttribute(wgrad) failed: %s", cudaGetErrorString(attr_err));
     const int smem = 1024 + p.stages * (2 + p.nbp) * kPanelBytes + 16 * p.stages + 64;
     dim3 grid(p.m_tiles, p.n_tiles, p.splits);
-    wgrad_mnmajor_kernel<<<grid, 192, smem, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, a);
+    MapPack pack;
+    for (int i = 0; i < kMaxMaps; ++i) pack.m[i] = maps[i];
+    wgrad_mnmajor_kernel<<<grid, 192, smem, st>>>(pack, mapB, a);
     ZSV_LAUNCH_CHECK("wgrad_mnmajor_kernel");
 
     const long long wtotal = (long long)s.ftaps * p.ci_pitch * p.co_pitch;

@@ -64,22 +64,44 @@ def _r2plus1d_specs():
     return stem, blocks
 
 
-STEM_SPECS, BLOCK_SPECS = _r2plus1d_specs()
+def _r3d_specs():
+    """r3d_18 (resnet.py:293-314): BasicStem 3x7x7 (resnet.py:165-173), BasicBlocks of two 3x3x3 Conv3DSimple
+    (resnet.py:18-34), stride (s,s,s) in the first convolution of layers 2-4."""
+    stem = [ConvSpec("stem.0", "stem.1", 3, 64, (3, 7, 7), (1, 2, 2), (1, 3, 3))]
+    blocks = []
+    cin = 64
+    for li, cout in ((1, 64), (2, 128), (3, 256), (4, 512)):
+        for bi in range(2):
+            s = 2 if (li > 1 and bi == 0) else 1
+            p = f"layer{li}.{bi}"
+            convs = [ConvSpec(p + ".conv1.0", p + ".conv1.1", cin, cout, (3, 3, 3), (s, s, s), (1, 1, 1)),
+                     ConvSpec(p + ".conv2.0", p + ".conv2.1", cout, cout, (3, 3, 3), (1, 1, 1), (1, 1, 1))]
+            ds = None
+            if s != 1 or cin != cout:
+                ds = ConvSpec(p + ".downsample.0", p + ".downsample.1", cin, cout, (1, 1, 1), (s, s, s), (0, 0, 0))
+            blocks.append(BlockSpec(p, convs, ds))
+            cin = cout
+    return stem, blocks
 
 
-def all_conv_specs() -> List[ConvSpec]:
-    out = list(STEM_SPECS)
-    for b in BLOCK_SPECS:
+ARCH_SPECS = {"r2plus1d_18": _r2plus1d_specs(), "r3d_18": _r3d_specs()}
+STEM_SPECS, BLOCK_SPECS = ARCH_SPECS["r2plus1d_18"]
+
+
+def all_conv_specs(arch: str = "r2plus1d_18") -> List[ConvSpec]:
+    stem, blocks = ARCH_SPECS[arch]
+    out = list(stem)
+    for b in blocks:
         out.extend(b.convs)
         if b.downsample is not None:
             out.append(b.downsample)
     return out
 
 
-def param_names() -> List[str]:
+def param_names(arch: str = "r2plus1d_18") -> List[str]:
     """Differentiable parameters of the backbone in the order they are passed to the autograd Function."""
     names = []
-    for c in all_conv_specs():
+    for c in all_conv_specs(arch):
         names += [c.name + ".weight", c.bn + ".weight", c.bn + ".bias"]
     return names
 
@@ -121,10 +143,10 @@ def _side_stream(device) -> "torch.cuda.Stream":
 _plan_cache: Dict[tuple, tuple] = {}
 
 
-def _network_plan(N, T, H, W, need_grad: bool):
+def _network_plan(N, T, H, W, need_grad: bool, arch: str = "r2plus1d_18"):
     """Geometry of every convolution for a clip batch of this shape (in all_conv_specs() order) and the one-launch
     weight re-pack for them."""
-    key = (N, T, H, W, need_grad)
+    key = (N, T, H, W, need_grad, arch)
     hit = _plan_cache.get(key)
     if hit is not None:
         return hit
@@ -135,15 +157,17 @@ def _network_plan(N, T, H, W, need_grad: bool):
         convs[spec.name], nd[spec.name] = op, need_grad and need_dgrad
         return (dims[0], op.To, op.Ho, op.Wo)
 
-    d = add(STEM_SPECS[0], (N, T, H, W), _lib.X_WFOLD, need_dgrad=False)
-    d = add(STEM_SPECS[1], d)
-    for b in BLOCK_SPECS:
+    stem, blocks = ARCH_SPECS[arch]
+    d = add(stem[0], (N, T, H, W), _lib.X_WFOLD, need_dgrad=False)
+    for sp in stem[1:]:
+        d = add(sp, d)
+    for b in blocks:
         d_in = d
         for c in b.convs:
             d = add(c, d)
         if b.downsample is not None:
             add(b.downsample, d_in)
-    names = [c.name for c in all_conv_specs()]
+    names = [c.name for c in all_conv_specs(arch)]
     plan = ops.PackPlan([convs[n] for n in names], [nd[n] for n in names])
     _plan_cache[key] = (names, plan)
     return names, plan
@@ -180,7 +204,9 @@ class BlockRec:
 class BackboneRunner:
     """Executes the backbone given a flat dict of parameter / buffer tensors (names relative to VideoResNet)."""
 
-    def __init__(self, tensors: Dict[str, torch.Tensor], train: bool, need_grad: bool):
+    def __init__(self, tensors: Dict[str, torch.Tensor], train: bool, need_grad: bool, arch: str = "r2plus1d_18"):
+        self.arch = arch
+        self.stem_specs, self.block_specs = ARCH_SPECS[arch]
         self.t = tensors
         self.train = train
         self.need_grad = need_grad
@@ -219,42 +245,44 @@ class BackboneRunner:
 
     def forward(self, x_ncdhw: torch.Tensor) -> torch.Tensor:
         N, _, T, H, W = x_ncdhw.shape
-        names, plan = _network_plan(N, T, H, W, self.need_grad)
+        names, plan = _network_plan(N, T, H, W, self.need_grad, self.arch)
         wfs, wds = plan.pack([self.t[n + ".weight"] for n in names])
         self.packed = {n: (wf, wd) for n, wf, wd in zip(names, wfs, wds)}
-        s0 = STEM_SPECS[0]
+        s0 = self.stem_specs[0]
         a = ops.repack_input(x_ncdhw, _lib.X_WFOLD, s0.padding[2])
-        a, _, _, rec, (T1, H1, W1) = self._unit(s0, a, (N, T, H, W), True, layout=_lib.X_WFOLD, need_dgrad=False)
+        a, _, _, rec, d = self._unit(s0, a, (N, T, H, W), True, layout=_lib.X_WFOLD, need_dgrad=False)
         self.stem_recs.append(rec)
-        a, _, _, rec, (T1, H1, W1) = self._unit(STEM_SPECS[1], a, (N, T1, H1, W1), True)
-        self.stem_recs.append(rec)
-        dims = (N, T1, H1, W1)
-        for b in BLOCK_SPECS:
+        for sp in self.stem_specs[1:]:
+            a, _, _, rec, d = self._unit(sp, a, (N, *d), True)
+            self.stem_recs.append(rec)
+        dims = (N, *d)
+        for b in self.block_specs:
             a, dims = self._block(b, a, dims)
         if self.nbt:
             torch._foreach_add_(self.nbt, 1)
         return a
 
     def _block(self, b: BlockSpec, x: torch.Tensor, dims):
+        """BasicBlock.forward (resnet.py:102-113): every convolution but the last is conv -> BN -> ReLU; the last one's
+        BatchNorm is applied together with the shortcut (identity or conv -> BN) and the final ReLU."""
         N = dims[0]
         recs = []
-        a, _, _, r, d1 = self._unit(b.convs[0], x, dims, True)
-        recs.append(r)
-        a, _, _, r, d2 = self._unit(b.convs[1], a, (N, *d1), True)
-        recs.append(r)
-        a, _, _, r, d3 = self._unit(b.convs[2], a, (N, *d2), True)
-        recs.append(r)
-        _, y_t, (sc, sh), r, d4 = self._unit(b.convs[3], a, (N, *d3), False, apply_now=False)
+        a, d = x, dims[1:]
+        for c in b.convs[:-1]:
+            a, _, _, r, d = self._unit(c, a, (N, *d), True)
+            recs.append(r)
+        last = b.convs[-1]
+        _, y_t, (sc, sh), r, d = self._unit(last, a, (N, *d), False, apply_now=False)
         recs.append(r)
         ds_rec = None
         if b.downsample is not None:
             _, y_d, (sc_d, sh_d), ds_rec, _ = self._unit(b.downsample, x, dims, False, apply_now=False)
-            out = ops.bn_apply(y_t, sc, sh, b.convs[3].cout, True, y2=y_d, scale2=sc_d, shift2=sh_d)
+            out = ops.bn_apply(y_t, sc, sh, last.cout, True, y2=y_d, scale2=sc_d, shift2=sh_d)
         else:
-            out = ops.bn_apply(y_t, sc, sh, b.convs[3].cout, True, residual=x)
+            out = ops.bn_apply(y_t, sc, sh, last.cout, True, residual=x)
         if self.need_grad:
             self.block_recs.append(BlockRec(recs, ds_rec, out, x))
-        return out, (N, *d4)
+        return out, (N, *d)
 
     # -- backward ----------------------------------------------------------------------------------
     def _conv_bwd(self, rec: UnitRec, dy, grads, want, addend=None, need_dx: bool = True,
@@ -309,8 +337,8 @@ class BackboneRunner:
     def block_backward(self, brec: BlockRec, g, grads, want, producer: Optional[UnitRec] = None):
         """g: gradient w.r.t. the block output -> gradient w.r.t. the block input (resnet.py:102-113 reversed).
         `producer`: the unit that produced the block input when it is a plain conv->BN->ReLU (the stem)."""
-        tail, ds = brec.units[3], brec.ds
         u = brec.units
+        tail, ds = u[-1], brec.ds
         if ds is not None:
             dy_t, dy_d, _, dg, db, dg2, db2 = ops.bn_bwd(
                 g, brec.out, True, tail.y, tail.mean, tail.invstd, self.t[tail.spec.bn + ".weight"],
@@ -322,9 +350,9 @@ class BackboneRunner:
                 g, brec.out, True, tail.y, tail.mean, tail.invstd, self.t[tail.spec.bn + ".weight"],
                 tail.spec.cout, want_dz=True)
         grads[tail.spec.bn + ".weight"], grads[tail.spec.bn + ".bias"] = dg, db
-        ga = self._conv_bwd(tail, dy_t, grads, want, producer=u[2])          # grad w.r.t. spatial2 output
-        ga = self._unit_bwd(u[2], ga, grads, want, producer=u[1])            # -> grad w.r.t. block conv1 output
-        ga = self._unit_bwd(u[1], ga, grads, want, producer=u[0])            # -> grad w.r.t. spatial1 output
+        ga = self._conv_bwd(tail, dy_t, grads, want, producer=u[-2])         # grad w.r.t. the previous unit's output
+        for i in range(len(u) - 2, 0, -1):
+            ga = self._unit_bwd(u[i], ga, grads, want, producer=u[i - 1])
         if ds is not None:
             gx = self._unit_bwd(u[0], ga, grads, want)                       # main branch
             return self._conv_bwd(ds, dy_d, grads, want, addend=gx)          # + projected shortcut
@@ -343,14 +371,15 @@ class BackboneRunner:
             brec = self.block_recs[bi]
             blk: Dict[str, torch.Tensor] = {}
             # the first block's input is the stem's conv->BN->ReLU output: its BatchNorm backward is fused as well
-            g = self.block_backward(brec, g, blk, want, producer=self.stem_recs[1] if bi == 0 else None)
+            g = self.block_backward(brec, g, blk, want, producer=self.stem_recs[-1] if bi == 0 else None)
             if sync is not None:
                 self.join_side(g[0].device if isinstance(g, tuple) else g.device)
                 sync.submit(blk)          # all-reduce of this block overlaps the next block's backward
             grads.update(blk)
         blk = {}
-        ga = self._unit_bwd(self.stem_recs[1], g, blk, want, producer=self.stem_recs[0])
-        self._unit_bwd(self.stem_recs[0], ga, blk, want, need_dx=False)
+        for si in range(len(self.stem_recs) - 1, 0, -1):
+            g = self._unit_bwd(self.stem_recs[si], g, blk, want, producer=self.stem_recs[si - 1])
+        self._unit_bwd(self.stem_recs[0], g, blk, want, need_dx=False)
         self.join_side(self.stem_recs[0].y.device)
         if sync is not None:
             sync.submit(blk)
@@ -376,12 +405,13 @@ def _module_tensors(module: torch.nn.Module) -> Dict[str, torch.Tensor]:
 class _BackboneFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, x, *params):
-        names = param_names()
+        arch = getattr(module, "arch", "r2plus1d_18")
+        names = param_names(arch)
         tensors = {k: v.detach() for k, v in _module_tensors(module).items()}
         for n, p in zip(names, params):
             tensors[n] = p.detach()
         need_grad = any(ctx.needs_input_grad[2:])
-        runner = BackboneRunner(tensors, train=module.training, need_grad=need_grad)
+        runner = BackboneRunner(tensors, train=module.training, need_grad=need_grad, arch=arch)
         feats = runner.forward(x)
         ctx.runner = runner if need_grad else None
         ctx.names = names
@@ -411,7 +441,7 @@ def backbone_forward(module: torch.nn.Module, x: torch.Tensor) -> torch.Tensor:
     ops._require_cuda(x, "backbone_forward")
     _lib.load()
     lookup = dict(module.named_parameters())
-    params = [lookup[n] for n in param_names()]
+    params = [lookup[n] for n in param_names(getattr(module, "arch", "r2plus1d_18"))]
     if not torch.is_grad_enabled():
         params = [p.detach() for p in params]
     return _BackboneFn.apply(module, x, *params)

@@ -62,6 +62,8 @@ class VideoResNet18(nn.Module):
     """R(2+1)D-18 backbone (resnet.r2plus1d_18, resnet.py:342-362).  ``forward`` returns ``(pooled, features)``
     like resnet.py:243-256 (the pooled vector is what the reference computes and then discards)."""
 
+    arch = "r2plus1d_18"
+
     def __init__(self, num_classes: int = 400):
         super().__init__()
         self.stem = _stem()
@@ -95,6 +97,67 @@ class VideoResNet18(nn.Module):
         feats = engine.backbone_forward(self, x)           # bf16 NDHWC, autograd-tracked
         f = engine.features_to_ncdhw(feats)                # [B,512,T',H',W'] fp32 view for API parity
         return f.mean(dim=(2, 3, 4)), f
+
+
+class SimpleResidualUnit(nn.Module):
+    """BasicBlock over plain 3x3x3 convolutions (Conv3DSimple, resnet.py:18-34; BasicBlock resnet.py:79-113).
+    conv1 = [conv, BN, ReLU], conv2 = [conv, BN]: child indices are part of the state-dict contract."""
+
+    def __init__(self, cin: int, cout: int, stride: int, shortcut: nn.Module | None):
+        super().__init__()
+        self.conv1 = nn.Sequential(nn.Conv3d(cin, cout, (3, 3, 3), stride, 1, bias=False), nn.BatchNorm3d(cout),
+                                   nn.ReLU(inplace=True))
+        self.conv2 = nn.Sequential(nn.Conv3d(cout, cout, (3, 3, 3), 1, 1, bias=False), nn.BatchNorm3d(cout))
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = shortcut
+        self.stride = stride
+
+
+class VideoResNet18R3D(nn.Module):
+    """r3d_18 backbone (resnet.r3d_18, resnet.py:293-314): BasicStem (resnet.py:165-173) + 4 x 2 BasicBlocks of
+    3x3x3 convolutions.  Same contract as VideoResNet18."""
+
+    arch = "r3d_18"
+
+    def __init__(self, num_classes: int = 400):
+        super().__init__()
+        self.stem = nn.Sequential(nn.Conv3d(3, 64, (3, 7, 7), (1, 2, 2), (1, 3, 3), bias=False), nn.BatchNorm3d(64),
+                                  nn.ReLU(inplace=True))
+        cin = 64
+        for i, cout in enumerate((64, 128, 256, 512), start=1):
+            stride = 1 if i == 1 else 2
+            units = []
+            for j in range(2):
+                s = stride if j == 0 else 1
+                shortcut = None
+                if j == 0 and (s != 1 or cin != cout):
+                    shortcut = nn.Sequential(nn.Conv3d(cin, cout, 1, (s, s, s), bias=False), nn.BatchNorm3d(cout))
+                units.append(SimpleResidualUnit(cin, cout, s, shortcut))
+                cin = cout
+            setattr(self, f"layer{i}", nn.Sequential(*units))
+        self.avgpool = nn.AdaptiveAvgPool3d((1, 1, 1))
+        self.fc = nn.Linear(512, num_classes)
+        for m in self.modules():                      # init scheme of resnet.py:226-236
+            if isinstance(m, nn.Conv3d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm3d):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.Linear):
+                nn.init.normal_(m.weight, 0, 0.01)
+                nn.init.zeros_(m.bias)
+
+    def forward(self, x: torch.Tensor):
+        feats = engine.backbone_forward(self, x)
+        f = engine.features_to_ncdhw(feats)
+        return f.mean(dim=(2, 3, 4)), f
+
+
+def r3d_18(pretrained: bool = False, **_) -> VideoResNet18R3D:
+    if pretrained:
+        raise RuntimeError("pretrained weights need network access; the reference never requests them "
+                           "(main.py:42 makes --nopretrained always False)")
+    return VideoResNet18R3D()
 
 
 def r2plus1d_18(pretrained: bool = False, **_) -> VideoResNet18:
@@ -150,13 +213,13 @@ class Model(nn.Module):
 def get_network(opt) -> nn.Module:
     """network.get_network (network.py:24-44): string dispatch on ``opt.network``."""
     name = opt.network
+    if "r3d" in name:                  # same test order as network.py:28-36
+        return Model(r3d_18, fixconvs=opt.fixconvs, nopretrained=opt.nopretrained)
     if "2plus1d" in name:
         return Model(r2plus1d_18, fixconvs=opt.fixconvs, nopretrained=opt.nopretrained)
     if "c3d" in name:
         from .c3d_model import C3D
         return C3D(fixconvs=opt.fixconvs, nopretrained=opt.nopretrained)
-    if "r3d" in name:
-        raise NotImplementedError("r3d_18 is a 'next' row of the scope table (SURVEY.md section 8f), not built yet")
     raise Exception("Network {} not available!".format(name))
 
 
