@@ -181,14 +181,16 @@ def _block_tensors(spec, g):
     return t
 
 
-@pytest.mark.parametrize("bi", range(8), ids=lambda i: f"block{i}")
-def test_single_block_forward_backward(bi):
+@pytest.mark.parametrize("arch,bi", [("r2plus1d_18", i) for i in range(8)] + [("r3d_18", i) for i in (0, 2, 4, 6, 7)],
+                         ids=lambda v: str(v))
+def test_single_block_forward_backward(arch, bi):
     """One residual block (resnet.py:102-113) forward + backward through the engine's tape vs the rounding-matched
     oracle: with only four BatchNorms in the path there is no chaotic amplification, so every activation, input
-    gradient and parameter gradient must agree within 1e-2 (north_star's per-layer tolerance)."""
+    gradient and parameter gradient must agree within 1e-2 (north_star's per-layer tolerance).  r3d_18 blocks cover
+    the 3x3x3 convolutions incl. stride (2,2,2) (eight parity planes) and their BN-fused dgrad."""
     from zeroshotvideoclassification_b200 import engine
     from tests.helpers import bf16_round, to_ndhwc
-    spec = engine.BLOCK_SPECS[bi]
+    spec = engine.ARCH_SPECS[arch][1][bi]
     g = torch.Generator().manual_seed(100 + bi)
     cin = spec.convs[0].cin
     N, T, H, W = 3, 4, 12, 12
@@ -202,17 +204,18 @@ def test_single_block_forward_backward(bi):
     work.update(params)
     xr = x.clone().requires_grad_(True)
     net = vo._Net(work, True, None, emulate_bf16=True)
-    out_ref = vo._basic_block(net, xr, spec.prefix, stride, spec.downsample is not None)
+    block_fn = vo._simple_block if arch == "r3d_18" else vo._basic_block
+    out_ref = block_fn(net, xr, spec.prefix, stride, spec.downsample is not None)
     gout = bf16_round(torch.randn(out_ref.shape, generator=g))
     out_ref.backward(gout)
 
     tens = {k: v.cuda() for k, v in t.items()}
-    runner = engine.BackboneRunner(tens, train=True, need_grad=True)
+    runner = engine.BackboneRunner(tens, train=True, need_grad=True, arch=arch)
     out, dims = runner._block(spec, to_ndhwc(x), (N, T, H, W))
     grads = {}
     gin = runner.block_backward(runner.block_recs[0], to_ndhwc(gout), grads, {})
     torch.cuda.synchronize()
-    cout = spec.convs[3].cout
+    cout = spec.convs[-1].cout
     assert rel_err(from_ndhwc(out, cout), out_ref.detach()) < 1e-2
     # backward: max-abs error is dominated by isolated ReLU-mask flips (an element next to zero whose stored bf16
     # activation differs by one ulp gets the full gradient instead of none), so gradients are gated on rms error
