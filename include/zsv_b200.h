@@ -79,14 +79,15 @@ int zsv_conv3d_pack_weight(const zsv_conv_desc* d, const float* w, void* w_fprop
 int zsv_conv3d_pack_weights(int n, const zsv_conv_desc* descs, const float* const* w, void* const* w_fprop,
                             void* const* w_dgrad, void* stream);
 
-/* Number of rows of the per-tile BatchNorm partial-statistics buffers written by fprop. */
+/* Number of rows of the BatchNorm partial-statistics buffers written by fprop: one per CTA of the persistent
+ * kernel (each CTA accumulates its tiles in shared memory in a fixed order). */
 int zsv_conv3d_stat_rows(const zsv_conv_desc* d);
 
 /* Forward convolution (aten::conv3d reached from resnet.py:40-52,181-184,271; network.py:102-117).
  *   x       : bf16 input in d->x_layout
  *   w_fprop : packed weights (which = 0)
  *   y       : bf16 [N][To][Ho][Wo][cpad(Cout)]
- *   part_sum, part_sq : optional fp32 [stat_rows][cpad(Cout)] per-tile sum / sum of squares of the
+ *   part_sum, part_sq : optional fp32 [stat_rows][cpad(Cout)] per-CTA sum / sum of squares of the
  *             bf16-rounded outputs (BatchNorm3d batch statistics, resnet.py:48); NULL to skip
  *   bias    : optional fp32 [Cout] (C3D); relu != 0 applies max(.,0) in the epilogue (network.py:147) */
 int zsv_conv3d_fprop(const zsv_conv_desc* d, const void* x, const void* w_fprop, void* y, float* part_sum,

@@ -193,6 +193,7 @@ struct EpiArgs {
     int bn_relu;
     float* bn_acc;               // smem [2][ncols] running sums of this CTA
     float* bn_scratch;           // smem [4 quadrants][2][width] per-tile sums
+    float* st_acc;               // smem [2][ncols] running BatchNorm statistics of this CTA (sum, sum of squares)
     int debug;   // tuning aid (ZSV_DEBUG_EPI bit mask): 1 = skip the TMA store, 2 = skip TMEM read + staging, 4 = skip stats
 };
 
@@ -242,8 +243,8 @@ __device__ __forceinline__ void xreduce32(float (&v)[32], int lane) {
 // memory (SWIZZLE_128B panels; rows that fall outside the tensor were staged as zeros).
 // Thread = (channel octet, row segment): it walks its rows with one 16-byte load each, accumulating 8 sums and 8 sums
 // of squares with packed fp32x2 adds/FMAs; the row segments of an octet sit on adjacent lanes and are combined with a
-// transposing shuffle reduction, after which every lane owns one or two finished column totals and writes them to the
-// per-tile partial row (deterministic, no atomics, no shared-memory scratch).
+// transposing shuffle reduction, after which every lane owns one or two finished column totals and adds them to the
+// CTA's running sums in shared memory (deterministic: fixed owner, fixed tile order, no atomics).
 __device__ __forceinline__ void tile_column_stats(const EpiArgs& E, uint32_t staging_u32, int width, int n_origin,
                                                   int m_tile, int et, int lane) {
     const int octs = width >> 3;
@@ -281,7 +282,9 @@ __device__ __forceinline__ void tile_column_stats(const EpiArgs& E, uint32_t sta
         asm("mov.b64 {%0, %1}, %2;" : "=f"(v[8 + 2 * j]), "=f"(v[8 + 2 * j + 1]) : "l"(q2[j]));
     }
     const int colbase = n_origin + oct * 8;
-    const long long rowoff = (long long)m_tile * E.part_pitch;
+    (void)m_tile;
+    // Every column total has exactly one owner thread (fixed for the whole kernel), which adds it to the CTA's running
+    // sum in shared memory: one partial row per CTA instead of one per tile (8624 -> 148 rows on layer 1).
     if (seg16) {
         xreduce_stage<16>(v, lane, 8);
         xreduce_stage<8>(v, lane, 4);
@@ -289,15 +292,18 @@ __device__ __forceinline__ void tile_column_stats(const EpiArgs& E, uint32_t sta
         xreduce_stage<2>(v, lane, 1);
         // lane bits (of its 16-lane group): bit3 = quantity, bits 2..0 = column within the octet
         const int col = colbase + (lane & 7);
-        if (active && col < E.ncols) ((lane & 8) ? E.part_sq : E.part_sum)[rowoff + col] = v[0];
+        if (active && col < E.ncols) E.st_acc[((lane & 8) ? E.ncols : 0) + col] += v[0];
     } else {
         xreduce_stage<16>(v, lane, 4);
         xreduce_stage<8>(v, lane, 2);
         xreduce_stage<4>(v, lane, 1);
         // bit2 = quantity, bit1 -> +4, bit0 -> +2, two adjacent columns per lane
         const int col = colbase + ((lane & 2) << 1) + ((lane & 1) << 1);
-        if (active && col < E.ncols)
-            *reinterpret_cast<float2*>(((lane & 4) ? E.part_sq : E.part_sum) + rowoff + col) = make_float2(v[0], v[1]);
+        if (active && col < E.ncols) {
+            float* dst = E.st_acc + ((lane & 4) ? E.ncols : 0) + col;
+            dst[0] += v[0];
+            dst[1] += v[1];
+        }
     }
 }
 
@@ -583,8 +589,9 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
         float* statbuf = reinterpret_cast<float*>(smem + statOff);
         E.bn_y = P.bn_y, E.bn_tab = P.bn_tab, E.bn_relu = P.bn_relu;
         E.bn_acc = statbuf;
+        E.st_acc = statbuf;
         E.bn_scratch = statbuf + 2 * P.ncols;
-        if (P.bn_y != nullptr)   // running sums start at zero; the first tile's barrier orders this before any use
+        if (P.bn_y != nullptr || P.part_sum != nullptr)   // running sums start at zero; the first tile's barriers order this before any use
             for (int i = et; i < 2 * P.ncols; i += kEpiWarps * 32) statbuf[i] = 0.f;
         int local = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
@@ -614,6 +621,12 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
             for (int i = et; i < 2 * P.ncols; i += kEpiWarps * 32) {
                 const int qn = i >= P.ncols ? 1 : 0;
                 P.bn_partial[((long long)blockIdx.x * 4 + qn) * P.ncols + (i - qn * P.ncols)] = statbuf[i];
+            }
+        } else if (P.part_sum != nullptr) {
+            named_bar_sync(1, kEpiWarps * 32);
+            for (int i = et; i < 2 * P.ncols; i += kEpiWarps * 32) {
+                const int qn = i >= P.ncols ? 1 : 0;
+                (qn ? P.part_sq : P.part_sum)[(long long)blockIdx.x * P.part_pitch + (i - qn * P.ncols)] = statbuf[i];
             }
         }
     }
@@ -864,8 +877,9 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         float* statbuf = reinterpret_cast<float*>(smem + statOff);
         E.bn_y = P.bn_y, E.bn_tab = P.bn_tab, E.bn_relu = P.bn_relu;
         E.bn_acc = statbuf;
+        E.st_acc = statbuf;
         E.bn_scratch = statbuf + 2 * P.ncols;
-        if (P.bn_y != nullptr)   // running sums start at zero; the first tile's barrier orders this before any use
+        if (P.bn_y != nullptr || P.part_sum != nullptr)   // running sums start at zero; the first tile's barriers order this before any use
             for (int i = et; i < 2 * P.ncols; i += kEpiWarps * 32) statbuf[i] = 0.f;
         // columns this tile owns: a non-last N tile only owns n_step of its bn_tile computed columns
         const int width = (n_tile + 1 < P.n_tiles) ? P.n_step : P.bn_tile;
@@ -891,10 +905,16 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
         if (et == 0) tma_store_wait_all();
         if (P.bn_y != nullptr) {
-            named_bar_sync(1, kEpiWarps * 32);
+            named_bar_sync(1, kEpiWarps * 32);   // every column owner has added its last tile
             for (int i = et; i < 2 * P.ncols; i += kEpiWarps * 32) {
                 const int qn = i >= P.ncols ? 1 : 0;
                 P.bn_partial[((long long)blockIdx.x * 4 + qn) * P.ncols + (i - qn * P.ncols)] = statbuf[i];
+            }
+        } else if (P.part_sum != nullptr) {
+            named_bar_sync(1, kEpiWarps * 32);
+            for (int i = et; i < 2 * P.ncols; i += kEpiWarps * 32) {
+                const int qn = i >= P.ncols ? 1 : 0;
+                (qn ? P.part_sq : P.part_sum)[(long long)blockIdx.x * P.part_pitch + (i - qn * P.ncols)] = statbuf[i];
             }
         }
     }
@@ -1481,7 +1501,7 @@ int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtenso
                  long long m_tiles, int n_tiles, cudaStream_t stream, BnFuseLaunch* fuse = nullptr) {
     // one persistent CTA per SM owns (almost) all shared memory: as many ring stages as fit, at most 8
     // two output staging buffers when at least 3 ring stages still fit beside them
-    const int scratch = fuse ? bn_scratch_bytes(a.ncols, a.bn_tile) : 0;
+    const int scratch = fuse ? bn_scratch_bytes(a.ncols, a.bn_tile) : (a.part_sum ? bn_scratch_bytes(a.ncols, 0) : 0);
     int nstg = 2;
     int stages = 8;
     while (stages > 2 && igemm_smem_bytes(a.bn_tile, stages, nstg, scratch) > 226 * 1024) --stages;
@@ -1544,7 +1564,8 @@ inline uint32_t align1k(uint32_t v) { return (v + 1023u) & ~1023u; }
 
 // act extents (W,H,T,N) of the GEMM-M space (stride-1 conv: output extents == input extents), reduction channels
 // kdim, output columns `cols`, filter (kt,kh,kw).  Only spatial 1xkhxkw (kh==3) and temporal ktx1x1 (kt==3).
-HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int kh, int kw, bool bn_fuse = false) {
+// scratch_mode: 0 = none, 1 = BatchNorm statistics (fprop), 2 = fused BatchNorm backward (dgrad)
+HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int kh, int kw, int scratch_mode = 0) {
     HaloPlan p;
     memset(&p, 0, sizeof(p));
     if (getenv("ZSV_DEBUG_NO_HALO")) return p;
@@ -1621,7 +1642,7 @@ HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int k
         const int staging1 = ((bn + 63) / 64) * (int)kPanelBytes;
         int nstg = 2, stages = 0, fixed = 0;
         for (; nstg >= 1; --nstg) {   // prefer two staging buffers if >= 3 activation stages still fit
-            p.scratch = bn_fuse ? bn_scratch_bytes(cpad(cols), bn) : 0;
+            p.scratch = scratch_mode == 2 ? bn_scratch_bytes(cpad(cols), bn) : (scratch_mode == 1 ? bn_scratch_bytes(cpad(cols), 0) : 0);
             fixed = 1024 + (int)p.b_total_bytes + nstg * staging1 + p.scratch + 256;
             const int avail = 226 * 1024 - fixed;
             stages = avail > 0 ? avail / (int)p.a_stage_bytes : 0;
@@ -1643,6 +1664,14 @@ HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int k
         return p;
     }
     return p;
+}
+
+// grid of the halo kernel: a multiple of n_tiles so that every CTA keeps one N tile
+int halo_grid(const HaloPlan& p) {
+    const long long want = p.m_tiles * p.n_tiles;
+    int grid = (int)std::min<long long>(want, (long long)(sm_count() / p.n_tiles) * p.n_tiles);
+    if (grid < p.n_tiles) grid = p.n_tiles;
+    return grid;
 }
 
 // act: tensor [N][T][H][W][pitch] providing the reduction channels (x for fprop, dy for dgrad); wimg: packed weight
@@ -1723,13 +1752,14 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
     });
     if (attr_err != cudaSuccess)
         return fail(ZSV_ERR_CUDA, "cudaFuncSetAttribute(halo igemm) failed: %s", cudaGetErrorString(attr_err));
-    // grid: a multiple of n_tiles so that every CTA keeps one N tile
-    const long long want = p.m_tiles * p.n_tiles;
-    int grid = (int)std::min<long long>(want, (long long)(sm_count() / p.n_tiles) * p.n_tiles);
-    if (grid < p.n_tiles) grid = p.n_tiles;
+    const int grid = halo_grid(p);
     a.scratch_bytes = p.scratch;
     if (fuse) {
         if (p.scratch < bn_scratch_bytes(a.ncols, p.bn_tile)) return fail(ZSV_ERR_UNSUPPORTED, "halo plan without BN-fusion scratch");
+    } else if (part_sum != nullptr && p.scratch < bn_scratch_bytes(a.ncols, 0)) {
+        return fail(ZSV_ERR_UNSUPPORTED, "halo plan without statistics scratch");
+    }
+    if (fuse) {
         if (fuse->rows_used + grid > fuse->capacity)
             return fail(ZSV_ERR_WORKSPACE, "dgrad: BN-fusion partial buffer holds %d rows, need %d", fuse->capacity,
                         fuse->rows_used + grid);
@@ -1831,13 +1861,16 @@ extern "C" int zsv_conv3d_pack_weights(int n, const zsv_conv_desc* descs, const 
 extern "C" int zsv_conv3d_stat_rows(const zsv_conv_desc* d) {
     Shape s;
     if (check_desc(d, &s)) return -1;
-    // one partial row per M tile; the tiling depends on which kernel fprop uses
+    // one partial row per CTA of the (persistent) fprop kernel; which kernel runs depends on the geometry
     if (!s.wfold && d->st == 1 && d->sh == 1 && d->sw == 1 && s.To == d->T && s.Ho == d->H && s.Wo == d->W) {
-        const HaloPlan hp = plan_halo(d->W, d->H, d->T, d->N, d->Cin, d->Cout, d->kt, d->kh, d->kw);
-        if (hp.ok) return (int)hp.m_tiles;
+        const HaloPlan hp = plan_halo(d->W, d->H, d->T, d->N, d->Cin, d->Cout, d->kt, d->kh, d->kw, 1);
+        if (hp.ok) return halo_grid(hp);
     }
     const Box b = choose_box(s.Wo, s.Ho, s.To, d->N, false);
-    return ceil_div(s.Wo, b.bw) * ceil_div(s.Ho, b.bh) * ceil_div(s.To, b.bt) * ceil_div(d->N, b.bn);
+    const long long m_tiles = (long long)ceil_div(s.Wo, b.bw) * ceil_div(s.Ho, b.bh) * ceil_div(s.To, b.bt) * ceil_div(d->N, b.bn);
+    int bn_tile, n_tiles;
+    choose_ntile(d->Cout, m_tiles, &bn_tile, &n_tiles);
+    return (int)std::min<long long>(m_tiles * n_tiles, sm_count());
 }
 
 extern "C" int zsv_conv3d_fprop(const zsv_conv_desc* d, const void* x, const void* w_fprop, void* y, float* part_sum,
@@ -1849,7 +1882,7 @@ extern "C" int zsv_conv3d_fprop(const zsv_conv_desc* d, const void* x, const voi
     if ((part_sum == nullptr) != (part_sq == nullptr)) return fail(ZSV_ERR_BAD_ARG, "fprop: need both stat buffers");
 
     if (!s.wfold && d->st == 1 && d->sh == 1 && d->sw == 1 && s.To == d->T && s.Ho == d->H && s.Wo == d->W) {
-        const HaloPlan hp = plan_halo(d->W, d->H, d->T, d->N, d->Cin, d->Cout, d->kt, d->kh, d->kw);
+        const HaloPlan hp = plan_halo(d->W, d->H, d->T, d->N, d->Cin, d->Cout, d->kt, d->kh, d->kw, part_sum ? 1 : 0);
         if (hp.ok) {
             // tap(cp, sh) = sh*kw + cp (spatial) or sh (temporal)
             int copy_off[kMaxCopies];
@@ -1927,7 +1960,7 @@ extern "C" int zsv_conv3d_dgrad(const zsv_conv_desc* d, const void* dy, const vo
     }
 
     if (d->st == 1 && d->sh == 1 && d->sw == 1 && s.To == d->T && s.Ho == d->H && s.Wo == d->W) {
-        const HaloPlan hp = plan_halo(d->W, d->H, d->T, d->N, d->Cout, d->Cin, d->kt, d->kh, d->kw, fuse != nullptr);
+        const HaloPlan hp = plan_halo(d->W, d->H, d->T, d->N, d->Cout, d->Cin, d->kt, d->kh, d->kw, fuse != nullptr ? 2 : 0);
         if (hp.ok) {
             // dx[i] = sum_j dy[i + p - j] w[j]: copy j reads dy at W offset p - j; along the shift dim the halo starts
             // at i0 + p - (S-1) and filter index j sits at halo slice S-1-j
