@@ -1,3 +1,4 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -12 > gpurun_out/pytest_gpu.log
-python bench.py --steps 20 --warmup 5 --no-cpu-baseline --layer-table > gpurun_out/bench13.json 2> gpurun_out/bench13.err
-tail -3 gpurun_out/pytest_gpu.log
+for i in 1 2; do
+python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/ab_a$i.json 2> /dev/null
+ZSV_DEBUG_WGRAD_MT1=1 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/ab_b$i.json 2> /dev/null
+done

@@ -168,6 +168,8 @@ struct WgradArgs {
     int32_t bn_tile, nbp;    // UMMA N, 64-wide dy panels per stage
     int32_t stages, tmem_cols;
     int32_t num_kb, kb_per_split;
+    int32_t mt;              // M tiles (pairs of x panels) per CTA: 2 halves how often the dy panels are re-read
+    int32_t acc_stride;      // TMEM columns between the accumulators of the M tiles
     float* ws;               // [split][tap][ci_pitch][co_pitch]
     Tap taps[kMaxTaps];
 };
@@ -941,7 +943,8 @@ wgrad_mnmajor_kernel(const __grid_constant__ MapPack mapsA,
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int stages = P.stages;
-    const uint32_t stageBytes = (2u + P.nbp) * kPanelBytes;
+    const uint32_t xpan = 2u * static_cast<uint32_t>(P.mt);            // x panels per stage
+    const uint32_t stageBytes = (xpan + P.nbp) * kPanelBytes;
     const uint32_t ringBytes = stages * stageBytes;
     const uint32_t barFull = base + ringBytes;
     const uint32_t barEmpty = barFull + 8u * stages;
@@ -968,18 +971,18 @@ wgrad_mnmajor_kernel(const __grid_constant__ MapPack mapsA,
     const int rows = P.bw * P.bh * P.bt * P.bn;
     const int kb0 = split * P.kb_per_split;
     const int kb1 = min(P.num_kb, kb0 + P.kb_per_split);
-    const int p0 = 2 * m_tile;
-    const int npan = min(2, P.npanels - p0);
+    const int p0 = 2 * P.mt * m_tile;                                  // first x panel of this CTA
+    const int npan = min(static_cast<int>(xpan), P.npanels - p0);     // panels that exist (>= 1)
 
     // warp-uniform loops, one elected lane issues (see igemm_kmajor_kernel)
     if (warp == 0) {
         const uint32_t leader = elect_one();
         const uint32_t tx = static_cast<uint32_t>(rows) * 128u * (npan + P.nbp);
-        // the (at most two) x panels of this M tile: tap geometry and channel offset are loop invariant
-        Tap tapj[2];
-        int c0j[2];
-        const CUtensorMap* mpj[2];
-        for (int j = 0; j < 2; ++j) {
+        // the (at most four) x panels of this CTA: tap geometry and channel offset are loop invariant
+        Tap tapj[4];
+        int c0j[4];
+        const CUtensorMap* mpj[4];
+        for (int j = 0; j < 4; ++j) {
             const int p = min(p0 + j, P.npanels - 1);
             const int tp = p / P.kchunks;
             c0j[j] = (p - tp * P.kchunks) << 6;
@@ -1002,12 +1005,11 @@ wgrad_mnmajor_kernel(const __grid_constant__ MapPack mapsA,
                 const uint32_t full = barFull + 8u * stage;
                 const uint32_t sa = base + stage * stageBytes;
                 mbar_expect_tx(full, tx);
-                tma_load_5d(sa, mpj[0], full, c0j[0], w0 + tapj[0].dw, h0 + tapj[0].dh, t0 + tapj[0].dt, n0);
-                if (npan > 1)
-                    tma_load_5d(sa + kPanelBytes, mpj[1], full, c0j[1], w0 + tapj[1].dw, h0 + tapj[1].dh,
-                                t0 + tapj[1].dt, n0);
+                for (int j = 0; j < npan; ++j)
+                    tma_load_5d(sa + j * kPanelBytes, mpj[j], full, c0j[j], w0 + tapj[j].dw, h0 + tapj[j].dh,
+                                t0 + tapj[j].dt, n0);
                 for (int j = 0; j < P.nbp; ++j)
-                    tma_load_5d(sa + (2 + j) * kPanelBytes, &mapB, full, n_tile * P.bn_tile + 64 * j, w0, h0, t0, n0);
+                    tma_load_5d(sa + (xpan + j) * kPanelBytes, &mapB, full, n_tile * P.bn_tile + 64 * j, w0, h0, t0, n0);
             }
             __syncwarp();
             if (++stage == static_cast<uint32_t>(stages)) {
@@ -1034,20 +1036,22 @@ wgrad_mnmajor_kernel(const __grid_constant__ MapPack mapsA,
         const uint32_t lbo = (kPanelBytes >> 4) << 16;
         uint32_t stage = 0, phase = 0;
         uint32_t acc = 0;
+        const int ntile = (npan + 1) >> 1;          // M tiles that have at least one panel
         for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(barFull + 8u * stage, phase);
             tc_fence_after();
             if (leader) {
                 const uint32_t sa = base + stage * stageBytes;
-                const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | lbo;
-                const uint32_t b_lo = (((sa + 2 * kPanelBytes) >> 4) & 0x3FFFu) | lbo;
+                const uint32_t b_lo = (((sa + xpan * kPanelBytes) >> 4) & 0x3FFFu) | lbo;
+                for (int t = 0; t < ntile; ++t) {   // M tiles of this CTA share the dy panels of the stage
+                    const uint32_t a_lo = (((sa + 2u * t * kPanelBytes) >> 4) & 0x3FFFu) | lbo;
+                    const uint32_t tacc = tmem_base + static_cast<uint32_t>(t * P.acc_stride);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {   // 16 position rows = 2048 B per step
-                    if (k < ksteps) {
-                        umma_bf16_lohi(tmem_base, a_lo + 128u * k, dhi, b_lo + 128u * k, dhi, idesc, acc);
-                        acc = 1;
+                    for (int k = 0; k < 8; ++k) {   // 16 position rows = 2048 B per step
+                        if (k < ksteps) umma_bf16_lohi(tacc, a_lo + 128u * k, dhi, b_lo + 128u * k, dhi, idesc, (k == 0) ? acc : 1u);
                     }
                 }
+                acc = 1;
                 umma_commit(barEmpty + 8u * stage);
             }
             __syncwarp();
@@ -1061,22 +1065,25 @@ wgrad_mnmajor_kernel(const __grid_constant__ MapPack mapsA,
     } else {
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        const int p = p0 + (row >> 6);
-        const int tp = p / P.kchunks;
-        const int ci = ((p - tp * P.kchunks) << 6) + (row & 63);
-        const bool valid = p < P.npanels && ci < P.ci_store;
-        float* dst = P.ws + (((long long)split * P.ntaps + tp) * P.ci_pitch + ci) * P.co_pitch + n_tile * P.bn_tile;
         mbar_wait(barTmem, 0);
         tc_fence_after();
-        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        for (int c = 0; c < P.bn_tile; c += 16) {
-            uint32_t v[16];
-            tmem_ld16(trow + c, v);
-            tmem_ld_wait();
-            if (valid) {
+        for (int t = 0; t < P.mt; ++t) {
+            const int p = p0 + 2 * t + (row >> 6);
+            const int tp = p / P.kchunks;
+            const int ci = ((p - tp * P.kchunks) << 6) + (row & 63);
+            const bool valid = p < P.npanels && ci < P.ci_store;
+            float* dst = P.ws + (((long long)split * P.ntaps + tp) * P.ci_pitch + ci) * P.co_pitch + n_tile * P.bn_tile;
+            const uint32_t trow = tmem_base + static_cast<uint32_t>(t * P.acc_stride) + (static_cast<uint32_t>(q * 32) << 16);
+            if (p0 + 2 * t >= P.npanels) break;   // warp-uniform: this M tile has no panel at all
+            for (int c = 0; c < P.bn_tile; c += 16) {
+                uint32_t v[16];
+                tmem_ld16(trow + c, v);
+                tmem_ld_wait();
+                if (valid) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<uint4*>(dst + c + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(dst + c + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
             }
         }
         tc_fence_before();
@@ -2072,7 +2079,7 @@ extern "C" int zsv_conv3d_dgrad(const zsv_conv_desc* d, const void* dy, const vo
 namespace {
 struct WgradPlan {
     Box box;
-    int num_kb, kchunks, npanels, m_tiles, bn_tile, n_tiles, nbp, splits, kb_per_split, stages, ci_pitch, co_pitch;
+    int num_kb, kchunks, npanels, m_tiles, bn_tile, n_tiles, nbp, splits, kb_per_split, stages, ci_pitch, co_pitch, mt;
     size_t ws_bytes;
 };
 int plan_wgrad(const zsv_conv_desc* d, const Shape& s, WgradPlan* p) {
@@ -2089,13 +2096,26 @@ int plan_wgrad(const zsv_conv_desc* d, const Shape& s, WgradPlan* p) {
     if (p->n_tiles > 1) p->bn_tile = (p->bn_tile + 63) & ~63;  // keep panel-aligned tile origins
     p->n_tiles = ceil_div(cols16, p->bn_tile);
     p->nbp = ceil_div(p->bn_tile, 64);
-    const int tiles = p->m_tiles * p->n_tiles;
+    // Optional: two M tiles per CTA share the dy panels of a stage (fewer L2 / DRAM re-reads of dy).  Measured: alone, the
+    // layer-1 / layer-2 spatial weight gradients get faster (244 -> 220 us, 148 -> 135 us) and shallow ones slower
+    // (178 -> 217 us on the temporal 144->64: 2 ring stages instead of 4, uneven tiles), hence the rule below; inside
+    // the training step, where these kernels run on the low-priority stream beside the BatchNorm kernels, the larger
+    // CTAs cost 0.8 % of step time (A/B in one session: 14.23 vs 14.12 ms), so it is off unless ZSV_WGRAD_MT2 is set.
     const int sms = std::max(1, sm_count());
+    p->mt = 1;
+    if (getenv("ZSV_WGRAD_MT2") && p->nbp >= 3 && p->m_tiles >= 2 &&
+        2 * (4 + p->nbp) * (int)kPanelBytes + 2048 <= 227 * 1024 && 2 * ((p->bn_tile + 31) & ~31) <= 512) {
+        const int tiles2 = ceil_div(p->m_tiles, 2) * p->n_tiles;
+        const int splits2 = std::min(std::max(1, (2 * sms) / tiles2), p->num_kb);
+        if (ceil_div(p->num_kb, splits2) >= 32) p->mt = 2;
+    }
+    p->m_tiles = ceil_div(p->m_tiles, p->mt);
+    const int tiles = p->m_tiles * p->n_tiles;
     int splits = std::max(1, (2 * sms) / tiles);
     splits = std::min(splits, p->num_kb);
     p->kb_per_split = ceil_div(p->num_kb, splits);
     p->splits = ceil_div(p->num_kb, p->kb_per_split);
-    const int stage = (2 + p->nbp) * kPanelBytes;
+    const int stage = (2 * p->mt + p->nbp) * kPanelBytes;
     int smem_cap = 227 * 1024;
     if (const char* e = getenv("ZSV_DEBUG_WGRAD_SMEM_KB")) smem_cap = std::min(smem_cap, std::max(64, atoi(e)) * 1024);
     p->stages = std::max(1, std::min(4, (smem_cap - 2048) / stage));
@@ -2140,7 +2160,9 @@ extern "C" int zsv_conv3d_wgrad(const zsv_conv_desc* d, const void* x, const voi
     a.bn_tile = p.bn_tile;
     a.nbp = p.nbp;
     a.stages = p.stages;
-    a.tmem_cols = pow2_cols(p.bn_tile);
+    a.mt = p.mt;
+    a.acc_stride = (p.bn_tile + 31) & ~31;
+    a.tmem_cols = pow2_cols(p.mt * a.acc_stride);
     a.num_kb = p.num_kb;
     a.kb_per_split = p.kb_per_split;
     a.ws = (float*)workspace;
@@ -2160,7 +2182,7 @@ extern "C" int zsv_conv3d_wgrad(const zsv_conv_desc* d, const void* x, const voi
     });
     if (attr_err != cudaSuccess)
         return fail(ZSV_ERR_CUDA, "cudaFuncSetAttribute(wgrad) failed: %s", cudaGetErrorString(attr_err));
-    const int smem = 1024 + p.stages * (2 + p.nbp) * kPanelBytes + 16 * p.stages + 64;
+    const int smem = 1024 + p.stages * (2 * p.mt + p.nbp) * kPanelBytes + 16 * p.stages + 64;
     dim3 grid(p.m_tiles, p.n_tiles, p.splits);
     MapPack pack;
     for (int i = 0; i < kMaxMaps; ++i) pack.m[i] = maps[i];
