@@ -433,7 +433,7 @@ def run_b200(args):
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cps, times, threads = cpu_reference_steps(4, 1, 2)
+        cps, times, threads = cpu_reference_steps(20, 1, 2)      # ~10-12 s of host work on the GPU box's cores
         cpu = {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port",
                "sample": f"{len(times)} steps x 2 clips (bs=2x3x16x112x112 fp32, BASELINE.json config 1) of the same "
                          f"training step; {sum(times):.1f} s of CPU work"}

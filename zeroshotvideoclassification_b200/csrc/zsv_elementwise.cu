@@ -375,8 +375,18 @@ bn_bwd_final_kernel(const float* __restrict__ partial, int nblocks, int nq, int 
     const int c = blockIdx.x * 32 + cl;
     for (int qi = 0; qi < nq; ++qi) {
         double s = 0.0;
-        if (c < Cp)
-            for (int b = rl; b < nblocks; b += 32) s += (double)partial[((long long)b * 4 + qi) * Cp + c];
+        if (c < Cp) {
+            // four independent loads in flight per thread: the chain of fp64 adds is short, the loads are what take time
+            int b = rl;
+            for (; b + 96 < nblocks; b += 128) {
+                const float v0 = partial[((long long)b * 4 + qi) * Cp + c];
+                const float v1 = partial[((long long)(b + 32) * 4 + qi) * Cp + c];
+                const float v2 = partial[((long long)(b + 64) * 4 + qi) * Cp + c];
+                const float v3 = partial[((long long)(b + 96) * 4 + qi) * Cp + c];
+                s += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+            }
+            for (; b < nblocks; b += 32) s += (double)partial[((long long)b * 4 + qi) * Cp + c];
+        }
         sh[rl][cl] = s;
         __syncthreads();
         if (rl == 0) {
