@@ -79,6 +79,21 @@ int zsv_conv3d_pack_weight(const zsv_conv_desc* d, const float* w, void* w_fprop
 int zsv_conv3d_pack_weights(int n, const zsv_conv_desc* descs, const float* const* w, void* const* w_fprop,
                             void* const* w_dgrad, void* stream);
 
+/* Inference (model.eval(), main.py:229-250): BatchNorm3d with running statistics is an affine map per output channel,
+ * so it folds into the convolution: packed weights w'[co] = w[co]*gamma[co]/sqrt(running_var[co]+eps) and a bias
+ * beta[co] - running_mean[co]*gamma[co]/sqrt(running_var[co]+eps), which zsv_conv3d_fprop applies (with ReLU and the
+ * residual addend) in its epilogue: one kernel per conv -> BN -> (+shortcut) -> ReLU group.  One launch for n convs. */
+typedef struct zsv_bn_fold {
+    const float* gamma;         /* NULL = 1 */
+    const float* beta;          /* NULL = 0 */
+    const float* running_mean;
+    const float* running_var;   /* NULL = do not fold this convolution */
+    float* bias_out;            /* out: fp32 [Cout] */
+    float eps;
+} zsv_bn_fold;
+int zsv_conv3d_pack_weights_folded(int n, const zsv_conv_desc* descs, const float* const* w, void* const* w_fprop,
+                                   const zsv_bn_fold* fold, void* stream);
+
 /* Number of rows of the BatchNorm partial-statistics buffers written by fprop: one per CTA of the persistent
  * kernel (each CTA accumulates its tiles in shared memory in a fixed order). */
 int zsv_conv3d_stat_rows(const zsv_conv_desc* d);
@@ -89,9 +104,11 @@ int zsv_conv3d_stat_rows(const zsv_conv_desc* d);
  *   y       : bf16 [N][To][Ho][Wo][cpad(Cout)]
  *   part_sum, part_sq : optional fp32 [stat_rows][cpad(Cout)] per-CTA sum / sum of squares of the
  *             bf16-rounded outputs (BatchNorm3d batch statistics, resnet.py:48); NULL to skip
- *   bias    : optional fp32 [Cout] (C3D); relu != 0 applies max(.,0) in the epilogue (network.py:147) */
+ *   bias    : optional fp32 [Cout] (C3D, folded BatchNorm); addend: optional bf16 tensor shaped like y added before
+ *             the activation (residual branch in the folded inference path, resnet.py:110); relu != 0 applies
+ *             max(.,0) in the epilogue (network.py:147, resnet.py:111) */
 int zsv_conv3d_fprop(const zsv_conv_desc* d, const void* x, const void* w_fprop, void* y, float* part_sum,
-                     float* part_sq, const float* bias, int relu, void* stream);
+                     float* part_sq, const float* bias, const void* addend, int relu, void* stream);
 
 /* Optional fusion of the first pass of BatchNorm3d backward into the data gradient.  The input of a convolution
  * is out = relu?(bn(y)) of the previous layer (resnet.py:48-49,95,182-186), so its data gradient g is exactly what

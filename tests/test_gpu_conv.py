@@ -246,3 +246,21 @@ def test_dgrad_with_fused_bn_backward_matches_two_pass(geom):
     assert rel_err(got_dg.cpu(), ref_dg.cpu()) < 1e-4
     assert rel_err(got_dy[..., :cin].float().cpu(), ref_dy[..., :cin].float().cpu()) < 1e-2
     assert float(got_dy[..., cin:].abs().max()) == 0.0 if cp_in > cin else True
+
+
+def test_fprop_bias_addend_relu_epilogue():
+    """Folded-BatchNorm inference epilogue: y = relu(conv(x) + bias + addend) in one kernel (resnet.py:110-111)."""
+    import torch
+    from zeroshotvideoclassification_b200 import ops
+    N, T, H, W, cin, cout = 2, 4, 12, 12, 144, 64
+    g = torch.Generator().manual_seed(21)
+    x = bf16_round(torch.randn(N, cin, T, H, W, generator=g))
+    w = bf16_round(torch.randn(cout, cin, 3, 1, 1, generator=g) * 0.05)
+    bias = torch.randn(cout, generator=g)
+    add = bf16_round(torch.randn(N, cout, T, H, W, generator=g))
+    ref = torch.relu(vo.conv3d(x, w, None, (1, 1, 1), (1, 0, 0)) + bias.view(1, -1, 1, 1, 1) + add)
+    op = ops.Conv3d(N, T, H, W, cin, cout, (3, 1, 1), (1, 1, 1), (1, 0, 0))
+    wf, _ = op.pack(w.cuda(), need_dgrad=False)
+    y, _, _ = op.fprop(to_ndhwc(x), wf, stats=False, bias=bias.cuda(), relu=True, addend=to_ndhwc(add))
+    torch.cuda.synchronize()
+    assert rel_err(from_ndhwc(y, cout), ref) < TOL

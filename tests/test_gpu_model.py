@@ -313,3 +313,35 @@ def test_r3d_18_forward_backward_vs_oracle():
     assert ours_emu["output2emb_proj.layers.1.weight"] < 1e-2
     # a wrong kernel shows up as an O(1) error from some layer downwards, far above the noise floor
     assert max(ours_emu.values()) < 0.5, sorted(ours_emu.items(), key=lambda kv: -kv[1])[:5]
+
+
+@pytest.mark.parametrize("arch", ["r2plus1d_18", "r3d_18"])
+def test_folded_inference_matches_unfolded_eval_and_tracks_weight_updates(arch):
+    """evaluate() path: the folded-BatchNorm forward (one kernel per conv group, cached packed weights) equals the
+    conv -> scale/shift eval path, and the cache follows in-place parameter updates (optimizer steps between epochs)."""
+    from zeroshotvideoclassification_b200 import video_models as vm
+    torch.manual_seed(2)
+    model = vm.get_network(vm.default_opt(arch)).cuda()
+    g = torch.Generator().manual_seed(3)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm3d):
+            m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g))
+            m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+            m.weight.data.copy_(0.5 + torch.rand(m.weight.shape, generator=g))
+            m.bias.data.copy_(0.2 * torch.randn(m.bias.shape, generator=g))
+    model.eval()
+    x = torch.randn(3, 2, 3, 8, 64, 64, generator=g).cuda()       # two clips per video (dataset.py:131)
+    with torch.no_grad():
+        emb_f, _ = model(x)                                       # folded path
+        emb_f2, _ = model(x)                                      # cached weights
+    emb_u, _ = model(x)                                           # grad enabled: generic eval path (scale/shift passes)
+    assert emb_f.shape == (6, 300)
+    assert torch.equal(emb_f, emb_f2)
+    assert rel_err(emb_f.cpu(), emb_u.detach().cpu()) < 1e-2
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    ref = vo.model_forward(sd, x.cpu(), train=False, arch=arch)
+    assert rel_err(emb_f.cpu(), ref) < 2e-2
+    with torch.no_grad():
+        model.model.stem[0].weight.mul_(1.5)                      # in-place update bumps the version counter
+        emb_g, _ = model(x)
+    assert rel_err(emb_g.cpu(), emb_f.cpu()) > 1e-3

@@ -1,9 +1,21 @@
-set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/pytest_gpu.log
-python bench.py --steps 20 --warmup 5 --layer-table > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err
-python bench.py --quick --no-graph --steps 1 --warmup 1 > gpurun_out/plain_quick.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv python bench.py --quick --no-graph --steps 1 --warmup 1 > gpurun_out/ncu.log 2>&1
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k "regex:igemm" -c 600 --csv --log-file gpurun_out/conv_traffic.csv python bench.py --quick --no-graph --steps 1 --warmup 1 > gpurun_out/ncu2.log 2>&1
-python tools/bench_bn.py > gpurun_out/bench_bn.log 2>&1
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/final_ref.json 2> gpurun_out/final_ref.err
-tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/final_bench.json; cat gpurun_out/final_ref.json
+python -m pytest tests -m gpu -x -q 2>&1 | tail -12 > gpurun_out/pytest_gpu.log
+python - > gpurun_out/eval_speed.log 2>&1 <<'PY'
+import torch, time, sys
+sys.path.insert(0, '.')
+import zeroshotvideoclassification_b200 as z
+torch.manual_seed(0)
+model = z.get_network(z.default_opt("r2plus1d_18")).cuda().eval()
+x = torch.randn(22, 1, 3, 16, 112, 112, device="cuda")
+def bench(fn, n=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize(); e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1)/n
+def folded():
+    with torch.no_grad(): model(x)
+def unfolded():
+    model(x)
+print("eval forward bs=22: folded %.2f ms, conv+scale/shift passes %.2f ms" % (bench(folded), bench(unfolded)))
+PY
+cat gpurun_out/pytest_gpu.log gpurun_out/eval_speed.log

@@ -12,7 +12,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libzsv_b200.so"
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 X_NDHWC = 0
 X_WFOLD = 1
 
@@ -34,6 +34,13 @@ class BnBwdFuse(C.Structure):
                 ("partial_rows", C.c_int32), ("rows_written", C.c_int32)]
 
 
+class BnFold(C.Structure):
+    """Mirror of ``zsv_bn_fold`` (include/zsv_b200.h)."""
+
+    _fields_ = [("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
+                ("bias_out", C.c_void_p), ("eps", C.c_float)]
+
+
 _P = C.c_void_p
 _I = C.c_int
 _LL = C.c_longlong
@@ -53,7 +60,8 @@ SIGNATURES = {
     "zsv_conv3d_pack_weight": (_I, [_DP, _P, _P, _P, _P]),
     "zsv_conv3d_pack_weights": (_I, [_I, _P, _P, _P, _P, _P]),
     "zsv_conv3d_stat_rows": (_I, [_DP]),
-    "zsv_conv3d_fprop": (_I, [_DP, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "zsv_conv3d_fprop": (_I, [_DP, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "zsv_conv3d_pack_weights_folded": (_I, [_I, _P, _P, _P, _P, _P]),
     "zsv_conv3d_dgrad": (_I, [_DP, _P, _P, _P, _P, C.POINTER(BnBwdFuse), _P]),
     "zsv_conv3d_wgrad_workspace": (_SZ, [_DP]),
     "zsv_conv3d_wgrad": (_I, [_DP, _P, _P, _P, _P, _SZ, _P]),

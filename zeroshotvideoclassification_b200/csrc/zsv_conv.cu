@@ -1197,14 +1197,23 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
 }
 
 // All convolutions of a network in ONE launch (the per-layer kernels are 5-15 us of mostly launch latency each).
-constexpr int kMaxPackItems = 56;
+constexpr int kMaxPackItems = 32;   // PackBatch travels as a kernel parameter (< 4 KB)
 struct PackItem {
     const float* w;
+    // optional inference-time BatchNorm folding (running statistics): w'[co] = w[co] * gamma/sqrt(var+eps),
+    // bias_out[co] = beta - mean * gamma/sqrt(var+eps)
+    const float* gamma;
+    const float* beta;
+    const float* rmean;
+    const float* rvar;
+    float* bias_out;
+    float eps;
     __nv_bfloat16* wf;
     __nv_bfloat16* wd;
     int32_t Cout, Cin, ntaps, kpitch, copitch, wfold_kw;
-    long long start;   // first flat element index of this item; [start, start + nf) fprop image, then the dgrad image
-    long long nf;
+    long long start;   // first flat element index of this item; [start, start + nf) fprop image, then the dgrad image,
+    long long nf;      // then (folding) Cout bias entries
+    long long nd;
 };
 struct PackBatch {
     int32_t n;
@@ -1224,6 +1233,7 @@ pack_weights_batched_kernel(const __grid_constant__ PackBatch B) {
         }
         const PackItem& I = B.it[lo];
         const long long i = g - I.start;
+        const bool fold = I.rvar != nullptr;
         if (i < I.nf) {
             const int k = static_cast<int>(i % I.kpitch);
             long long r = i / I.kpitch;
@@ -1236,8 +1246,9 @@ pack_weights_batched_kernel(const __grid_constant__ PackBatch B) {
             } else if (k < I.Cin) {
                 v = I.w[((long long)co * I.Cin + k) * I.ntaps + tap];
             }
+            if (fold) v *= (I.gamma ? I.gamma[co] : 1.f) * rsqrtf(I.rvar[co] + I.eps);
             I.wf[i] = __float2bfloat16(v);
-        } else {
+        } else if (i < I.nf + I.nd) {
             const long long j = i - I.nf;
             const int co = static_cast<int>(j % I.copitch);
             long long r = j / I.copitch;
@@ -1245,6 +1256,10 @@ pack_weights_batched_kernel(const __grid_constant__ PackBatch B) {
             const int tap = static_cast<int>(r / I.Cin);
             const float v = co < I.Cout ? I.w[((long long)co * I.Cin + ci) * I.ntaps + tap] : 0.f;
             I.wd[j] = __float2bfloat16(v);
+        } else {
+            const int co = static_cast<int>(i - I.nf - I.nd);
+            const float sc = (I.gamma ? I.gamma[co] : 1.f) * rsqrtf(I.rvar[co] + I.eps);
+            I.bias_out[co] = (I.beta ? I.beta[co] : 0.f) - I.rmean[co] * sc;
         }
     }
 }
@@ -1823,8 +1838,8 @@ extern "C" int zsv_conv3d_pack_weight(const zsv_conv_desc* d, const float* w, vo
     return ZSV_OK;
 }
 
-extern "C" int zsv_conv3d_pack_weights(int n, const zsv_conv_desc* descs, const float* const* w, void* const* w_fprop,
-                                       void* const* w_dgrad, void* stream) {
+static int pack_weights_impl(int n, const zsv_conv_desc* descs, const float* const* w, void* const* w_fprop,
+                             void* const* w_dgrad, const zsv_bn_fold* fold, void* stream) {
     if (n < 0 || (n > 0 && (!descs || !w || !w_fprop || !w_dgrad)))
         return fail(ZSV_ERR_BAD_ARG, "pack_weights: null array");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1849,10 +1864,18 @@ extern "C" int zsv_conv3d_pack_weights(int n, const zsv_conv_desc* descs, const 
             I.Cout = d->Cout, I.Cin = d->Cin, I.ntaps = s.ntaps, I.kpitch = s.kpitch, I.copitch = s.coutp;
             I.wfold_kw = s.wfold ? d->kw : 0;
             I.nf = I.wf ? (long long)s.ftaps * d->Cout * s.kpitch : 0;
-            const long long nd = I.wd ? (long long)s.ntaps * d->Cin * s.coutp : 0;
-            if (I.nf + nd == 0) continue;
+            I.nd = I.wd ? (long long)s.ntaps * d->Cin * s.coutp : 0;
+            long long nb = 0;
+            if (fold && fold[base + i].running_var) {
+                const zsv_bn_fold& f = fold[base + i];
+                if (!f.running_mean || !f.bias_out) return fail(ZSV_ERR_BAD_ARG, "pack_weights: incomplete zsv_bn_fold %d", base + i);
+                I.gamma = f.gamma, I.beta = f.beta, I.rmean = f.running_mean, I.rvar = f.running_var;
+                I.bias_out = f.bias_out, I.eps = f.eps;
+                nb = d->Cout;
+            }
+            if (I.nf + I.nd + nb == 0) continue;
             I.start = total;
-            total += I.nf + nd;
+            total += I.nf + I.nd + nb;
             ++m;
         }
         if (m == 0) continue;
@@ -1863,6 +1886,18 @@ extern "C" int zsv_conv3d_pack_weights(int n, const zsv_conv_desc* descs, const 
         ZSV_LAUNCH_CHECK("pack_weights_batched_kernel");
     }
     return ZSV_OK;
+}
+
+extern "C" int zsv_conv3d_pack_weights(int n, const zsv_conv_desc* descs, const float* const* w, void* const* w_fprop,
+                                       void* const* w_dgrad, void* stream) {
+    return pack_weights_impl(n, descs, w, w_fprop, w_dgrad, nullptr, stream);
+}
+
+extern "C" int zsv_conv3d_pack_weights_folded(int n, const zsv_conv_desc* descs, const float* const* w,
+                                              void* const* w_fprop, const zsv_bn_fold* fold, void* stream) {
+    if (n > 0 && !fold) return fail(ZSV_ERR_BAD_ARG, "pack_weights_folded: null fold array");
+    std::vector<void*> none((size_t)std::max(n, 1), nullptr);
+    return pack_weights_impl(n, descs, w, w_fprop, none.data(), fold, stream);
 }
 
 extern "C" int zsv_conv3d_stat_rows(const zsv_conv_desc* d) {
@@ -1881,7 +1916,7 @@ extern "C" int zsv_conv3d_stat_rows(const zsv_conv_desc* d) {
 }
 
 extern "C" int zsv_conv3d_fprop(const zsv_conv_desc* d, const void* x, const void* w_fprop, void* y, float* part_sum,
-                                float* part_sq, const float* bias, int relu, void* stream) {
+                                float* part_sq, const float* bias, const void* addend, int relu, void* stream) {
     Shape s;
     int rc = check_desc(d, &s);
     if (rc) return rc;
@@ -1896,7 +1931,7 @@ extern "C" int zsv_conv3d_fprop(const zsv_conv_desc* d, const void* x, const voi
             for (int c = 0; c < hp.ncopies; ++c) copy_off[c] = hp.spatial ? c - d->pw : 0;
             const int shift_org = hp.spatial ? -d->ph : -d->pt;
             return launch_halo(hp, x, d->Cin, s.cinp, w_fprop, d->Cout, s.kpitch, s.ntaps, y, s.coutp, d->W, d->H, d->T,
-                               d->N, copy_off, shift_org, 0, 1, hp.spatial ? d->kw : 1, nullptr, part_sum, part_sq, bias,
+                               d->N, copy_off, shift_org, 0, 1, hp.spatial ? d->kw : 1, addend, part_sum, part_sq, bias,
                                bias ? d->Cout : 0, relu, (cudaStream_t)stream);
         }
     }
@@ -1918,6 +1953,7 @@ extern "C" int zsv_conv3d_fprop(const zsv_conv_desc* d, const void* x, const voi
     a.o_sT = a.o_sH * s.Ho;
     a.o_sN = a.o_sT * s.To;
     a.out = (__nv_bfloat16*)y;
+    a.addend = (const __nv_bfloat16*)addend;
     a.part_sum = part_sum;
     a.part_sq = part_sq;
     a.bias = bias;

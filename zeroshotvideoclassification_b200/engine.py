@@ -173,6 +173,29 @@ def _network_plan(N, T, H, W, need_grad: bool, arch: str = "r2plus1d_18"):
     return names, plan
 
 
+_eval_pack_cache: Dict[tuple, tuple] = {}
+
+
+def _folded_weights(tensors: Dict[str, torch.Tensor], names, specs, plan, key):
+    """bf16 weight images with the inference-time BatchNorm folded in, plus the per-channel biases.  evaluate()
+    (main.py:224-257) runs many batches on fixed weights, so the result is cached until a parameter or a running
+    statistic changes (tensor version counters) or moves."""
+    src = []
+    for c in specs:
+        src += [tensors[c.name + ".weight"], tensors[c.bn + ".weight"], tensors[c.bn + ".bias"],
+                tensors[c.bn + ".running_mean"], tensors[c.bn + ".running_var"]]
+    stamp = tuple((t.data_ptr(), t._version) for t in src)
+    hit = _eval_pack_cache.get(key)
+    if hit is not None and hit[0] == stamp:
+        return hit[1]
+    wfs, biases = plan.pack_folded([tensors[c.name + ".weight"] for c in specs],
+                                   [(tensors[c.bn + ".weight"], tensors[c.bn + ".bias"], tensors[c.bn + ".running_mean"],
+                                     tensors[c.bn + ".running_var"]) for c in specs])
+    packed = {n: (wf, b) for n, wf, b in zip(names, wfs, biases)}
+    _eval_pack_cache[key] = (stamp, packed)
+    return packed
+
+
 # ----------------------------------------------------------------------------------------------------
 # tape records
 # ----------------------------------------------------------------------------------------------------
@@ -246,6 +269,8 @@ class BackboneRunner:
     def forward(self, x_ncdhw: torch.Tensor) -> torch.Tensor:
         N, _, T, H, W = x_ncdhw.shape
         names, plan = _network_plan(N, T, H, W, self.need_grad, self.arch)
+        if not self.train and not self.need_grad:
+            return self._forward_folded(x_ncdhw, names, plan)
         wfs, wds = plan.pack([self.t[n + ".weight"] for n in names])
         self.packed = {n: (wf, wd) for n, wf, wd in zip(names, wfs, wds)}
         s0 = self.stem_specs[0]
@@ -260,6 +285,37 @@ class BackboneRunner:
             a, dims = self._block(b, a, dims)
         if self.nbt:
             torch._foreach_add_(self.nbt, 1)
+        return a
+
+    # -- inference: BatchNorm folded into the convolutions ------------------------------------------
+    def _forward_folded(self, x_ncdhw: torch.Tensor, names, plan) -> torch.Tensor:
+        """model.eval() under no_grad (evaluate(), main.py:224-257): every conv -> BN -> (+shortcut) -> ReLU group is ONE
+        kernel -- running-statistics BatchNorm folded into the packed weights and a bias, residual add and ReLU in the
+        convolution's epilogue; no statistics, no tape, no separate normalisation passes."""
+        N, _, T, H, W = x_ncdhw.shape
+        specs = all_conv_specs(self.arch)
+        key = (self.arch, N, T, H, W, str(x_ncdhw.device), self.t[specs[0].name + ".weight"].data_ptr())
+        packed = _folded_weights(self.t, names, specs, plan, key)
+
+        def conv(spec, x, dims, relu, layout=_lib.X_NDHWC, addend=None):
+            op = _conv_for(spec, dims[0], dims[1], dims[2], dims[3], layout)
+            wf, bias = packed[spec.name]
+            y, _, _ = op.fprop(x, wf, stats=False, bias=bias, relu=relu, addend=addend)
+            return y, (dims[0], op.To, op.Ho, op.Wo)
+
+        s0 = self.stem_specs[0]
+        a = ops.repack_input(x_ncdhw, _lib.X_WFOLD, s0.padding[2])
+        a, d = conv(s0, a, (N, T, H, W), True, layout=_lib.X_WFOLD)
+        for sp in self.stem_specs[1:]:
+            a, d = conv(sp, a, d, True)
+        for b in self.block_specs:
+            x_in, d_in = a, d
+            for c in b.convs[:-1]:
+                a, d = conv(c, a, d, True)
+            shortcut = x_in
+            if b.downsample is not None:
+                shortcut, _ = conv(b.downsample, x_in, d_in, False)
+            a, d = conv(b.convs[-1], a, d, True, addend=shortcut)      # relu(bn(conv) + shortcut), resnet.py:110-111
         return a
 
     def _block(self, b: BlockSpec, x: torch.Tensor, dims):

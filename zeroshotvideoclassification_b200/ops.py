@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import BnBwdFuse, ConvDesc, check, cpad, ptr
+from ._lib import BnBwdFuse, BnFold, ConvDesc, check, cpad, ptr
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
@@ -100,7 +100,7 @@ class Conv3d:
         return wf, wd
 
     # -- forward ---------------------------------------------------------------------------------
-    def fprop(self, x, wf, stats: bool = True, bias=None, relu: bool = False):
+    def fprop(self, x, wf, stats: bool = True, bias=None, relu: bool = False, addend=None):
         y = torch.empty((self.N, self.To, self.Ho, self.Wo, cpad(self.cout)), dtype=torch.bfloat16, device=x.device)
         ps = pq = None
         if stats:
@@ -108,7 +108,7 @@ class Conv3d:
             pq = torch.empty_like(ps)
         with _Timed("fprop", self):
             check(self.lib.zsv_conv3d_fprop(C.byref(self.desc), ptr(x), ptr(wf), ptr(y), ptr(ps), ptr(pq), ptr(bias),
-                                            int(relu), _stream()), "zsv_conv3d_fprop")
+                                            ptr(addend), int(relu), _stream()), "zsv_conv3d_fprop")
         return y, ps, pq
 
     # -- backward --------------------------------------------------------------------------------
@@ -185,6 +185,36 @@ class PackPlan:
         wfs = [buf[o:o + c.wf_bytes // 2] for o, c in zip(self.wf_off, self.convs)]
         wds = [None if o is None else buf[o:o + c.wd_bytes // 2] for o, c in zip(self.wd_off, self.convs)]
         return wfs, wds
+
+    def pack_folded(self, weights, bns, eps: float = BN_EPS):
+        """Inference: weights with the BatchNorm that follows each convolution folded in (running statistics).
+        bns: (gamma, beta, running_mean, running_var) per convolution.  -> ([wf...], [bias fp32 [Cout]...])."""
+        dev = weights[0].device
+        buf = torch.empty(self.total, dtype=torch.bfloat16, device=dev)
+        nb = [c.cout for c in self.convs]
+        biases = torch.empty(sum(nb), dtype=torch.float32, device=dev)
+        base, keep, off = buf.data_ptr(), [], 0
+        folds = (BnFold * self.n)()
+        out_b = []
+        for i, (w, (gamma, beta, rm, rv)) in enumerate(zip(weights, bns)):
+            _require_cuda(w, "PackPlan.pack_folded")
+            tens = []
+            for t in (w, gamma, beta, rm, rv):
+                t = t.detach()
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    t = t.float().contiguous()
+                    keep.append(t)
+                tens.append(t)
+            self.w_arr[i] = tens[0].data_ptr()
+            self.wf_arr[i] = base + 2 * self.wf_off[i]
+            b = biases[off:off + nb[i]]
+            off += nb[i]
+            out_b.append(b)
+            folds[i] = BnFold(tens[1].data_ptr(), tens[2].data_ptr(), tens[3].data_ptr(), tens[4].data_ptr(), b.data_ptr(), eps)
+        check(self.lib.zsv_conv3d_pack_weights_folded(self.n, self.descs, self.w_arr, self.wf_arr, folds, _stream()),
+              "zsv_conv3d_pack_weights_folded")
+        wfs = [buf[o:o + c.wf_bytes // 2] for o, c in zip(self.wf_off, self.convs)]
+        return wfs, out_b
 
 
 # ------------------------------------------------------------------------------------------------
