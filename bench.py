@@ -223,7 +223,9 @@ def run_b200(args):
     optimizer = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=args.graph, fused=True)
     sync = zdist.GradSync() if world > 1 else None
     zdist.set_grad_sync(sync)
-    head_params = list(model.output2emb_proj.parameters())
+    # parameters whose gradients do not come out of the backbone Function (GradSync covers those): the MLP head of
+    # network.Model; C3D has no bucketed sync, all of its gradients are reduced after backward
+    head_params = list(model.output2emb_proj.parameters()) if hasattr(model, "output2emb_proj") else list(model.parameters())
 
     g = torch.Generator().manual_seed(1 + rank)
     x_host = torch.randn(B, 1, 3, 16, 112, 112, generator=g).pin_memory()
@@ -361,9 +363,11 @@ def run_b200(args):
                                  f"{n / prof_steps:4.0f} {1e3 * ms / n:9.1f} {fl / (ms / 1e3) / 1e12:8.1f} "
                                  f"{ms / prof_steps:7.3f}\n")
     peaks = load_peaks()
+    # algorithmic conv FLOPs per clip of the profiled iteration (242.449 GFLOP for R(2+1)D-18)
+    flop_per_clip = sum(v["flops"] for v in kinds.values()) / prof_steps / B if kinds else FLOP_PER_CLIP
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "r01_conv_dram_traffic.json")
-    if os.path.exists(tpath):       # dram__bytes_read+write per launch of the same kernels, from the committed ncu capture
+    if os.path.exists(tpath) and "2plus1d" in args.network:       # dram__bytes_read+write per launch of the same kernels, from the committed ncu capture
         tj = json.load(open(tpath))
         traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/r01_conv_dram_traffic.json (ncu, per launch)"
     km = {k: {"ms_per_step": v["ms"] / prof_steps, "calls_per_step": v["calls"] / prof_steps,
@@ -385,7 +389,7 @@ def run_b200(args):
         "timed_in": f"{prof_steps} kernel-by-kernel iterations right after the timed region "
                     f"({prof_ms_total / prof_steps:.2f} ms/step eager vs {ms_per_step:.2f} ms/step timed)",
         "by_kernel": km,
-        "whole_step_frac_of_tensor_peak": (value / world) * FLOP_PER_CLIP / (peaks["tflops_sustained"] * 1e12),
+        "whole_step_frac_of_tensor_peak": (value / world) * flop_per_clip / (peaks["tflops_sustained"] * 1e12),
     }
 
     if args.quick:
@@ -437,12 +441,16 @@ def run_b200(args):
         cpu = {"value": cps, "unit": "clips/s", "cores": threads, "kind": "port",
                "sample": f"{len(times)} steps x 2 clips (bs=2x3x16x112x112 fp32, BASELINE.json config 1) of the same "
                          f"training step; {sum(times):.1f} s of CPU work"}
+    metric = METRIC if "2plus1d" in args.network else f"{args.network} train clips/s (16x112^2, bf16)"
     line = {
-        "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+        "metric": metric, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
         "warmup": n_warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"R(2+1)D-18 end-to-end training step bs={B}/GPU, 16x112x112 synthetic clips, "
-                               f"Word2Vec-300 MSE regression, Adam (BASELINE.json configs[{1 if world == 1 else 2}])",
+        "config": {"workload": (f"R(2+1)D-18 end-to-end training step bs={B}/GPU, 16x112x112 synthetic clips, "
+                                f"Word2Vec-300 MSE regression, Adam (BASELINE.json configs[{1 if world == 1 else 2}])")
+                               if "2plus1d" in args.network else
+                               (f"{args.network} end-to-end training step bs={B}/GPU, 16x112x112 synthetic clips, Word2Vec-300 "
+                                f"MSE regression, Adam" + (" (BASELINE.json configs[3])" if "c3d" in args.network else "")),
                    "network": args.network, "per_gpu_batch": B, "global_batch": B * world, "clip": "3x16x112x112",
                    "parallelism": f"dp{world}" if world > 1 else "single",
                    "l2": "per-step working set (~6 GB of activations) is far larger than the 126 MB L2; no flush needed",
