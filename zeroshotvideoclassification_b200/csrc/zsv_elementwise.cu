@@ -658,7 +658,20 @@ int ew_blocks(long long work_items, int threads) {
     return (int)std::max<long long>(1, std::min<long long>(want, (long long)sm_count() * 8));
 }
 
-constexpr int kBwdMaxBlocks = 592;
+constexpr int kBwdMaxBlocks = 1184;   // capacity of the partial buffers (8 blocks per SM)
+
+// Grid-stride kernels run best with exactly as many blocks as can be resident at once: one more block than that
+// starts a second wave that leaves most SMs idle (592 blocks on 3 x 148 resident slots = 1.33 waves).
+template <typename F>
+int resident_grid(F kernel, int threads, size_t dyn_smem, long long work_blocks, int max_blocks) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 2;
+    }
+    const long long cap = std::min<long long>((long long)per_sm * sm_count(), max_blocks);
+    return (int)std::max<long long>(1, std::min<long long>(cap, work_blocks));
+}
 
 }  // namespace
 }  // namespace zsv
@@ -754,20 +767,20 @@ extern "C" int zsv_bn_apply(const void* y, const float* scale, const float* shif
     const int V = Cp >> 3;
     if (V > 256) return fail(ZSV_ERR_UNSUPPORTED, "bn_apply: channel pitch too large");
     const int R = std::max(1, 256 / V);
-    const int blocks = (int)std::max<long long>(1, std::min<long long>((long long)sm_count() * 8, ceil_div_ll(rows, (long long)R * 2)));
+    const long long work = ceil_div_ll(rows, (long long)R * 2);
     cudaStream_t st = (cudaStream_t)stream;
     const __nv_bfloat16* yb = (const __nv_bfloat16*)y;
     const __nv_bfloat16* y2b = (const __nv_bfloat16*)y2;
     const __nv_bfloat16* rb = (const __nv_bfloat16*)residual;
     __nv_bfloat16* ob = (__nv_bfloat16*)out;
     if (y2 && residual)
-        bn_apply_kernel<true, true><<<blocks, 256, 0, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, rows, Cp, R, relu);
+        bn_apply_kernel<true, true><<<resident_grid(bn_apply_kernel<true, true>, 256, 0, work, 1 << 20), 256, 0, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, rows, Cp, R, relu);
     else if (y2)
-        bn_apply_kernel<true, false><<<blocks, 256, 0, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, rows, Cp, R, relu);
+        bn_apply_kernel<true, false><<<resident_grid(bn_apply_kernel<true, false>, 256, 0, work, 1 << 20), 256, 0, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, rows, Cp, R, relu);
     else if (residual)
-        bn_apply_kernel<false, true><<<blocks, 256, 0, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, rows, Cp, R, relu);
+        bn_apply_kernel<false, true><<<resident_grid(bn_apply_kernel<false, true>, 256, 0, work, 1 << 20), 256, 0, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, rows, Cp, R, relu);
     else
-        bn_apply_kernel<false, false><<<blocks, 256, 0, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, rows, Cp, R, relu);
+        bn_apply_kernel<false, false><<<resident_grid(bn_apply_kernel<false, false>, 256, 0, work, 1 << 20), 256, 0, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, rows, Cp, R, relu);
     ZSV_LAUNCH_CHECK("bn_apply_kernel");
     return ZSV_OK;
 }
@@ -797,10 +810,9 @@ extern "C" int zsv_bn_bwd(const void* g, const void* out, int relu, const float*
     const int V = Cp >> 3;
     const int R = std::max(1, 256 / V);
     if (V > 256) return fail(ZSV_ERR_UNSUPPORTED, "bn_bwd: channel pitch too large");
-    const int nblocks = (int)std::max<long long>(1, std::min<long long>(kBwdMaxBlocks, ceil_div_ll(rows, (long long)R * 4)));
+    const size_t smem_r = (size_t)R * 4 * Cp * sizeof(float);
     float* partial = (float*)workspace;
     float* sums = partial + (size_t)kBwdMaxBlocks * 4 * Cp;
-    const size_t smem_r = (size_t)R * 4 * Cp * sizeof(float);
     const __nv_bfloat16 *gb = (const __nv_bfloat16*)g, *ob = (const __nv_bfloat16*)out, *yb = (const __nv_bfloat16*)y,
                         *y2b = (const __nv_bfloat16*)y2;
     static bool attr_done = false;
@@ -810,6 +822,9 @@ extern "C" int zsv_bn_bwd(const void* g, const void* out, int relu, const float*
         attr_done = true;
     }
     if (smem_r > 160 * 1024) return fail(ZSV_ERR_UNSUPPORTED, "bn_bwd: reduction scratch too large");
+    const long long work_r = ceil_div_ll(rows, (long long)R * 4);
+    const int nblocks = y2 ? resident_grid(bn_bwd_reduce_kernel<true>, 256, smem_r, work_r, kBwdMaxBlocks)
+                           : resident_grid(bn_bwd_reduce_kernel<false>, 256, smem_r, work_r, kBwdMaxBlocks);
     if (y2)
         bn_bwd_reduce_kernel<true><<<nblocks, 256, smem_r, st>>>(gb, ob, relu, mask_scale, mask_shift, yb, y2b, rows, Cp, R, partial);
     else
@@ -818,7 +833,9 @@ extern "C" int zsv_bn_bwd(const void* g, const void* out, int relu, const float*
     const int nq = y2 ? 4 : 2;
     bn_bwd_final_kernel<<<ceil_div(Cp, 32), 1024, 0, st>>>(partial, nblocks, nq, C, Cp, 1, mean, invstd, mean2, invstd2, sums, dgamma, dbeta, dgamma2, dbeta2);
     ZSV_LAUNCH_CHECK("bn_bwd_final_kernel");
-    const int blocks = (int)std::max<long long>(1, std::min<long long>((long long)sm_count() * 8, ceil_div_ll(rows, (long long)R * 2)));
+    const long long work_a = ceil_div_ll(rows, (long long)R * 2);
+    const int blocks = y2 ? resident_grid(bn_bwd_apply_kernel<true>, 256, 0, work_a, 1 << 20)
+                          : resident_grid(bn_bwd_apply_kernel<false>, 256, 0, work_a, 1 << 20);
     const float inv_count = (float)(1.0 / (double)rows);
     if (y2)
         bn_bwd_apply_kernel<true><<<blocks, 256, 0, st>>>(gb, ob, relu, mask_scale, mask_shift, yb, mean, invstd, gamma, y2b, mean2, invstd2, gamma2, sums, (__nv_bfloat16*)dy, (__nv_bfloat16*)dy2, (__nv_bfloat16*)dz, rows, C, Cp, R, inv_count);
@@ -846,7 +863,7 @@ extern "C" int zsv_bn_bwd_finish(const void* dz, const void* y, const float* mea
     const int V = Cp >> 3;
     if (V > 256) return fail(ZSV_ERR_UNSUPPORTED, "bn_bwd_finish: channel pitch too large");
     const int R = std::max(1, 256 / V);
-    const int blocks = (int)std::max<long long>(1, std::min<long long>((long long)sm_count() * 8, ceil_div_ll(rows, (long long)R * 2)));
+    const int blocks = resident_grid(bn_bwd_apply_kernel<false>, 256, 0, ceil_div_ll(rows, (long long)R * 2), 1 << 20);
     const float inv_count = (float)(1.0 / (double)rows);
     bn_bwd_apply_kernel<false><<<blocks, 256, 0, st>>>(
         (const __nv_bfloat16*)dz, nullptr, 0, nullptr, nullptr, (const __nv_bfloat16*)y, mean, invstd, gamma, nullptr,
