@@ -2147,7 +2147,12 @@ int plan_wgrad(const zsv_conv_desc* d, const Shape& s, WgradPlan* p) {
     }
     p->m_tiles = ceil_div(p->m_tiles, p->mt);
     const int tiles = p->m_tiles * p->n_tiles;
-    int splits = std::max(1, (2 * sms) / tiles);
+    // split the position axis so that the CTAs fill the GPU ONCE: measured against two waves (the previous choice) the
+    // step is 2.8 % faster (13.84 vs 14.23 ms) -- one pipeline fill/drain and one TMEM allocation per SM instead of two,
+    // and half as many split partials to write and to reduce in the finalize kernel
+    int waves = 1;
+    if (const char* e = getenv("ZSV_DEBUG_WGRAD_WAVES")) waves = std::max(1, atoi(e));
+    int splits = std::max(1, (waves * sms) / tiles);
     splits = std::min(splits, p->num_kb);
     p->kb_per_split = ceil_div(p->num_kb, splits);
     p->splits = ceil_div(p->num_kb, p->kb_per_split);
