@@ -1095,6 +1095,168 @@ wgrad_mnmajor_kernel(const __grid_constant__ MapPack mapsA,
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient of the temporal 3x1x1 stride-1 convolutions with a haloed activation tile.
+//
+// The generic kernel above gives every (tap, 64-channel chunk) panel pair its own CTA column, so the dy panels of a
+// position block are re-read once per M tile and x once per tap: 1.05 GB of DRAM reads for 0.46 GB of operands on
+// 144->64 (79 % DRAM utilisation).  Here one CTA owns ALL panels of its range of position blocks: the x tile carries a
+// halo of one T slice on both sides, the three tap views are descriptor offsets of whole T slices into that one tile
+// (the reduction index of an MN-major operand is the row, so a tap shift is a start-address offset), and the
+// (tap, chunk pair) accumulators sit side by side in TMEM.  x and dy are read once (x: + 2/b3 halo).
+// grid = position-block splits; ws[split][tap][ci][co].
+// ------------------------------------------------------------------------------------------------
+struct WgradHaloArgs {
+    int32_t b[4];            // position box: inner dims W, H, N and the T extent (rows = b0*b1*b2*b3, multiple of 16)
+    int32_t tl[4];
+    FastDiv fd_tl0, fd_tl1, fd_tl2;
+    int32_t nchunks, npairs; // 64-channel chunks of x, pairs of chunks (UMMA M = 128 = two chunks)
+    int32_t ntaps;
+    int32_t ci_pitch, co_pitch, bn_tile, nbp;
+    int32_t stages, tmem_cols, acc_stride;
+    int32_t num_kb, kb_per_split;
+    uint32_t a_chunk_bytes, stage_bytes;
+    float* ws;
+};
+
+__global__ void __launch_bounds__(192, 1)
+wgrad_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDy,
+                  const __grid_constant__ WgradHaloArgs P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int stages = P.stages;
+    const uint32_t ringBytes = stages * P.stage_bytes;
+    const uint32_t barFull = base + ringBytes;
+    const uint32_t barEmpty = barFull + 8u * stages;
+    const uint32_t barTmem = barEmpty + 8u * stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ringBytes + 16u * stages + 8u);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(barFull + 8u * s, 1);
+            mbar_init(barEmpty + 8u * s, 1);
+        }
+        mbar_init(barTmem, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), P.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int split = blockIdx.x;
+    const int kb0 = split * P.kb_per_split;
+    const int kb1 = min(P.num_kb, kb0 + P.kb_per_split);
+    const int inner = P.b[0] * P.b[1] * P.b[2];
+    const int rows = inner * P.b[3];
+    const int halo_rows = inner * (P.b[3] + P.ntaps - 1);
+    const uint32_t dyOff = 2u * static_cast<uint32_t>(P.npairs) * P.a_chunk_bytes;   // dy panels follow the chunk buffers
+
+    if (warp == 0) {
+        const uint32_t leader = elect_one();
+        const uint32_t tx = static_cast<uint32_t>(halo_rows) * 128u * P.nchunks + static_cast<uint32_t>(rows) * 128u * P.nbp;
+        uint32_t stage = 0, phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            int m, m3;
+            const int o0 = fdivmod(kb, P.fd_tl0, m) * P.b[0];
+            const int o1 = fdivmod(m, P.fd_tl1, m) * P.b[1];
+            const int o2 = fdivmod(m, P.fd_tl2, m3) * P.b[2];
+            const int o3 = m3 * P.b[3];
+            mbar_wait(barEmpty + 8u * stage, phase ^ 1u);
+            if (leader) {
+                const uint32_t full = barFull + 8u * stage;
+                const uint32_t sa = base + stage * P.stage_bytes;
+                mbar_expect_tx(full, tx);
+                for (int c = 0; c < P.nchunks; ++c)
+                    tma_load_5d(sa + c * P.a_chunk_bytes, &mapX, full, c << 6, o0, o1, o2, o3 - (P.ntaps >> 1));
+                for (int j = 0; j < P.nbp; ++j)
+                    tma_load_5d(sa + dyOff + j * kPanelBytes, &mapDy, full, 64 * j, o0, o1, o2, o3);
+            }
+            __syncwarp();
+            if (++stage == static_cast<uint32_t>(stages)) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t leader = elect_one();
+        const uint32_t idesc = umma_idesc_bf16(128, P.bn_tile, 1, 1);
+        const int ksteps = rows >> 4;
+        const uint32_t dhi = umma_desc_hi(1024, 2);
+        const uint32_t lboA = (P.a_chunk_bytes >> 4) << 16;     // second 64-channel half of M = the next chunk buffer
+        const uint32_t lboB = (kPanelBytes >> 4) << 16;
+        const uint32_t tap16 = (static_cast<uint32_t>(inner) * 128u) >> 4;   // one T slice of rows, in 16-byte units
+        uint32_t stage = 0, phase = 0;
+        uint32_t acc = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(barFull + 8u * stage, phase);
+            tc_fence_after();
+            if (leader) {
+                const uint32_t sa = base + stage * P.stage_bytes;
+                const uint32_t b_lo = (((sa + dyOff) >> 4) & 0x3FFFu) | lboB;
+                int a = 0;
+                for (int t = 0; t < P.ntaps; ++t) {
+                    for (int pr = 0; pr < P.npairs; ++pr, ++a) {
+                        const uint32_t a_lo = ((((sa + 2u * pr * P.a_chunk_bytes) >> 4) + t * tap16) & 0x3FFFu) | lboA;
+                        const uint32_t tacc = tmem_base + static_cast<uint32_t>(a * P.acc_stride);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {   // 16 position rows = 2048 B per step
+                            if (k < ksteps)
+                                umma_bf16_lohi(tacc, a_lo + 128u * k, dhi, b_lo + 128u * k, dhi, idesc, (k == 0) ? acc : 1u);
+                        }
+                    }
+                }
+                acc = 1;
+                umma_commit(barEmpty + 8u * stage);
+            }
+            __syncwarp();
+            if (++stage == static_cast<uint32_t>(stages)) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        }
+        if (leader) umma_commit(barTmem);
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        mbar_wait(barTmem, 0);
+        tc_fence_after();
+        int a = 0;
+        for (int t = 0; t < P.ntaps; ++t) {
+            for (int pr = 0; pr < P.npairs; ++pr, ++a) {
+                const int chunk = 2 * pr + (row >> 6);
+                const int ci = (chunk << 6) + (row & 63);
+                const bool valid = chunk < P.nchunks && ci < P.ci_pitch;
+                float* dst = P.ws + (((long long)split * P.ntaps + t) * P.ci_pitch + ci) * P.co_pitch;
+                const uint32_t trow = tmem_base + static_cast<uint32_t>(a * P.acc_stride) + (static_cast<uint32_t>(q * 32) << 16);
+                for (int c = 0; c < P.bn_tile; c += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(trow + c, v);
+                    tmem_ld_wait();
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4*>(dst + c + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, P.tmem_cols);
+    }
+}
+
 // dw[co][ci][tap] = sum_split ws[split][tap][ci][co]   (wfold: tap=(dt,dh), ci = dw*8 + c)
 // Transposing reduction through shared memory: a block owns 32 output channels x CI_T input channels x all taps; the
 // split partials are read coalesced along co, the state-dict layout is written in contiguous (ci, tap) runs per co.
@@ -2167,12 +2329,117 @@ int plan_wgrad(const zsv_conv_desc* d, const Shape& s, WgradPlan* p) {
 }
 }  // namespace
 
+namespace {
+struct WgradHaloPlan {
+    bool ok;
+    int b[4], tl[4];
+    int nchunks, npairs, bn_tile, nbp, stages, acc_stride, tmem_cols, num_kb, kb_per_split, splits, ci_pitch, co_pitch;
+    uint32_t a_chunk_bytes, stage_bytes;
+    int smem;
+    size_t ws_bytes;
+};
+
+// Temporal 3x1x1, stride 1, "same" padding, plain NDHWC input, all (tap, chunk pair) accumulators within 512 TMEM columns.
+WgradHaloPlan plan_wgrad_halo(const zsv_conv_desc* d, const Shape& s) {
+    WgradHaloPlan p;
+    memset(&p, 0, sizeof(p));
+    if (getenv("ZSV_DEBUG_NO_WGRAD_HALO")) return p;
+    if (s.wfold || d->kt != 3 || d->kh != 1 || d->kw != 1 || d->st != 1 || d->sh != 1 || d->sw != 1 || d->pt != 1 ||
+        d->ph != 0 || d->pw != 0)
+        return p;
+    const int cols16 = (d->Cout + 15) & ~15;
+    if (cols16 > 256) return p;
+    p.bn_tile = cols16;
+    p.nbp = ceil_div(p.bn_tile, 64);
+    p.nchunks = ceil_div(d->Cin, 64);
+    p.npairs = ceil_div(p.nchunks, 2);
+    p.acc_stride = (p.bn_tile + 31) & ~31;
+    if (3 * p.npairs * p.acc_stride > 512) return p;
+    p.tmem_cols = pow2_cols(3 * p.npairs * p.acc_stride);
+    // box (W, H, N | T): rows multiple of 16, <= 128, inner multiple of 8, fewest wasted rows and least halo
+    const int E[4] = {d->W, d->H, d->N, d->T};
+    double best = -1;
+    for (int b0 = 1; b0 <= std::min(E[0], 128); ++b0)
+        for (int b1 = 1; b1 <= std::min(E[1], 128 / b0); ++b1)
+            for (int b2 = 1; b2 <= std::min(E[2], 128 / (b0 * b1)); ++b2) {
+                const int inner = b0 * b1 * b2;
+                if (inner % 8) continue;
+                for (int b3 = 1; b3 <= std::min(E[3], 128 / inner); ++b3) {
+                    if ((inner * b3) % 16) continue;
+                    const double tiles = (double)ceil_div(E[0], b0) * ceil_div(E[1], b1) * ceil_div(E[2], b2) * ceil_div(E[3], b3);
+                    const double eff = ((double)E[0] * E[1] * E[2] * E[3]) / (tiles * inner * b3);
+                    const double halo = (double)(b3 + 2) / b3;
+                    const double score = eff * (inner * b3 / 128.0 + 1.0) / (0.5 + 0.5 * halo) + 1e-6 * b0;
+                    if (score > best) {
+                        best = score;
+                        p.b[0] = b0, p.b[1] = b1, p.b[2] = b2, p.b[3] = b3;
+                    }
+                }
+            }
+    if (best < 0) return p;
+    for (int i = 0; i < 4; ++i) p.tl[i] = ceil_div(E[i], p.b[i]);
+    p.num_kb = p.tl[0] * p.tl[1] * p.tl[2] * p.tl[3];
+    const int inner = p.b[0] * p.b[1] * p.b[2];
+    p.a_chunk_bytes = align1k((uint32_t)(inner * (p.b[3] + 2)) * 128u);
+    p.stage_bytes = 2u * p.npairs * p.a_chunk_bytes + (uint32_t)p.nbp * kPanelBytes;
+    p.stages = std::min(4, (int)((227 * 1024 - 2048) / p.stage_bytes));
+    if (p.stages < 2) return p;
+    const int splits = std::min(p.num_kb, std::max(1, sm_count()));
+    p.kb_per_split = ceil_div(p.num_kb, splits);
+    p.splits = ceil_div(p.num_kb, p.kb_per_split);
+    p.ci_pitch = s.cinp;
+    p.co_pitch = p.bn_tile;
+    p.ws_bytes = (size_t)p.splits * 3 * p.ci_pitch * p.co_pitch * 4;
+    p.smem = 1024 + p.stages * (int)p.stage_bytes + 16 * p.stages + 64;
+    p.ok = true;
+    return p;
+}
+
+int launch_wgrad_halo(const WgradHaloPlan& p, const zsv_conv_desc* d, const Shape& s, const void* x, const void* dy,
+                      void* workspace, cudaStream_t st) {
+    WgradHaloArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int i = 0; i < 4; ++i) a.b[i] = p.b[i], a.tl[i] = p.tl[i];
+    a.fd_tl0 = make_fastdiv(p.tl[0]), a.fd_tl1 = make_fastdiv(p.tl[1]), a.fd_tl2 = make_fastdiv(p.tl[2]);
+    a.nchunks = p.nchunks, a.npairs = p.npairs, a.ntaps = 3;
+    a.ci_pitch = p.ci_pitch, a.co_pitch = p.co_pitch, a.bn_tile = p.bn_tile, a.nbp = p.nbp;
+    a.stages = p.stages, a.tmem_cols = p.tmem_cols, a.acc_stride = p.acc_stride;
+    a.num_kb = p.num_kb, a.kb_per_split = p.kb_per_split;
+    a.a_chunk_bytes = p.a_chunk_bytes, a.stage_bytes = p.stage_bytes;
+    a.ws = (float*)workspace;
+    auto make = [&](CUtensorMap* m, const void* basep, int C, int pitch, int text) {
+        const uint64_t cB = (uint64_t)pitch * 2;
+        const uint64_t bW = cB, bH = cB * d->W, bT = bH * d->H, bN = bT * d->T;
+        uint64_t dims[5] = {(uint64_t)C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N, (uint64_t)d->T};
+        uint64_t str[4] = {bW, bH, bN, bT};
+        uint32_t box[5] = {64, (uint32_t)p.b[0], (uint32_t)p.b[1], (uint32_t)p.b[2], (uint32_t)text};
+        return make_map(m, basep, 5, dims, str, box);
+    };
+    CUtensorMap mX, mDy;
+    int rc = make(&mX, x, d->Cin, s.cinp, p.b[3] + 2);
+    if (rc) return rc;
+    rc = make(&mDy, dy, d->Cout, s.coutp, p.b[3]);
+    if (rc) return rc;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    if (attr_err != cudaSuccess)
+        return fail(ZSV_ERR_CUDA, "cudaFuncSetAttribute(wgrad halo) failed: %s", cudaGetErrorString(attr_err));
+    wgrad_halo_kernel<<<p.splits, 192, p.smem, st>>>(mX, mDy, a);
+    ZSV_LAUNCH_CHECK("wgrad_halo_kernel");
+    return ZSV_OK;
+}
+}  // namespace
+
 extern "C" size_t zsv_conv3d_wgrad_workspace(const zsv_conv_desc* d) {
     Shape s;
     if (check_desc(d, &s)) return 0;
     WgradPlan p;
     plan_wgrad(d, s, &p);
-    return p.ws_bytes;
+    const WgradHaloPlan hp = plan_wgrad_halo(d, s);
+    return hp.ok ? std::max(p.ws_bytes, hp.ws_bytes) : p.ws_bytes;
 }
 
 extern "C" int zsv_conv3d_wgrad(const zsv_conv_desc* d, const void* x, const void* dy, float* dw, void* workspace,
@@ -2181,11 +2448,24 @@ extern "C" int zsv_conv3d_wgrad(const zsv_conv_desc* d, const void* x, const voi
     int rc = check_desc(d, &s);
     if (rc) return rc;
     if (!x || !dy || !dw || !workspace) return fail(ZSV_ERR_BAD_ARG, "wgrad: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const WgradHaloPlan hp = plan_wgrad_halo(d, s);
+    if (hp.ok) {
+        if (workspace_bytes < hp.ws_bytes)
+            return fail(ZSV_ERR_WORKSPACE, "wgrad: workspace %zu < required %zu bytes", workspace_bytes, hp.ws_bytes);
+        rc = launch_wgrad_halo(hp, d, s, x, dy, workspace, st);
+        if (rc) return rc;
+        const long long wtotal = (long long)3 * hp.ci_pitch * hp.co_pitch;
+        const int blocks = (int)std::min<long long>(ceil_div_ll(wtotal, 256), 148 * 8);
+        wgrad_finalize_small_kernel<<<blocks, 256, 0, st>>>((const float*)workspace, dw, hp.splits, 3, hp.ci_pitch,
+                                                            hp.co_pitch, d->Cin, d->Cout, 0, s.ntaps);
+        ZSV_LAUNCH_CHECK("wgrad_finalize_kernel");
+        return ZSV_OK;
+    }
     WgradPlan p;
     plan_wgrad(d, s, &p);
     if (workspace_bytes < p.ws_bytes)
         return fail(ZSV_ERR_WORKSPACE, "wgrad: workspace %zu < required %zu bytes", workspace_bytes, p.ws_bytes);
-    cudaStream_t st = (cudaStream_t)stream;
 
     WgradArgs a;
     memset(&a, 0, sizeof(a));
