@@ -1117,6 +1117,14 @@ struct WgradHaloArgs {
     int32_t stages, tmem_cols, acc_stride;
     int32_t num_kb, kb_per_split;
     uint32_t a_chunk_bytes, stage_bytes;
+    // spatial 1x3x3 mode: blockIdx.y = filter column (W tap); the S = 3 filter rows are the halo taps.  With a single
+    // 64-channel chunk the two halves of an M = 128 MMA are two TAPS (same buffer, one halo slice apart).
+    int32_t ncopies;         // 1 (temporal) or kw (spatial)
+    int32_t copy_org;        // W coordinate offset of copy 0 (= -pw)
+    int32_t tap_stride;      // ws tap index = halo tap * tap_stride + copy
+    int32_t pair_taps;       // 1: M halves are consecutive halo taps of chunk 0; 0: consecutive chunks of one tap
+    int32_t nacc;            // accumulators per CTA
+    int32_t total_taps;      // taps of the whole filter (pitch of the tap axis of ws)
     float* ws;
 };
 
@@ -1151,12 +1159,13 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
 
     const int split = blockIdx.x;
+    const int copy = blockIdx.y;
     const int kb0 = split * P.kb_per_split;
     const int kb1 = min(P.num_kb, kb0 + P.kb_per_split);
     const int inner = P.b[0] * P.b[1] * P.b[2];
     const int rows = inner * P.b[3];
     const int halo_rows = inner * (P.b[3] + P.ntaps - 1);
-    const uint32_t dyOff = 2u * static_cast<uint32_t>(P.npairs) * P.a_chunk_bytes;   // dy panels follow the chunk buffers
+    const uint32_t dyOff = P.stage_bytes - static_cast<uint32_t>(P.nbp) * kPanelBytes;   // dy panels follow the x buffers
 
     if (warp == 0) {
         const uint32_t leader = elect_one();
@@ -1174,7 +1183,8 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 const uint32_t sa = base + stage * P.stage_bytes;
                 mbar_expect_tx(full, tx);
                 for (int c = 0; c < P.nchunks; ++c)
-                    tma_load_5d(sa + c * P.a_chunk_bytes, &mapX, full, c << 6, o0, o1, o2, o3 - (P.ntaps >> 1));
+                    tma_load_5d(sa + c * P.a_chunk_bytes, &mapX, full, c << 6, o0 + P.copy_org + copy, o1, o2,
+                                o3 - (P.ntaps >> 1));
                 for (int j = 0; j < P.nbp; ++j)
                     tma_load_5d(sa + dyOff + j * kPanelBytes, &mapDy, full, 64 * j, o0, o1, o2, o3);
             }
@@ -1200,15 +1210,29 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             if (leader) {
                 const uint32_t sa = base + stage * P.stage_bytes;
                 const uint32_t b_lo = (((sa + dyOff) >> 4) & 0x3FFFu) | lboB;
-                int a = 0;
-                for (int t = 0; t < P.ntaps; ++t) {
-                    for (int pr = 0; pr < P.npairs; ++pr, ++a) {
-                        const uint32_t a_lo = ((((sa + 2u * pr * P.a_chunk_bytes) >> 4) + t * tap16) & 0x3FFFu) | lboA;
+                if (P.pair_taps) {
+                    // one chunk: accumulator a covers halo taps 2a and 2a+1 (LBO = one halo slice)
+                    const uint32_t lboT = tap16 << 16;
+                    for (int a = 0; a < P.nacc; ++a) {
+                        const uint32_t a_lo = (((sa >> 4) + 2u * a * tap16) & 0x3FFFu) | lboT;
                         const uint32_t tacc = tmem_base + static_cast<uint32_t>(a * P.acc_stride);
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {   // 16 position rows = 2048 B per step
+                        for (int k = 0; k < 8; ++k) {
                             if (k < ksteps)
                                 umma_bf16_lohi(tacc, a_lo + 128u * k, dhi, b_lo + 128u * k, dhi, idesc, (k == 0) ? acc : 1u);
+                        }
+                    }
+                } else {
+                    int a = 0;
+                    for (int t = 0; t < P.ntaps; ++t) {
+                        for (int pr = 0; pr < P.npairs; ++pr, ++a) {
+                            const uint32_t a_lo = ((((sa + 2u * pr * P.a_chunk_bytes) >> 4) + t * tap16) & 0x3FFFu) | lboA;
+                            const uint32_t tacc = tmem_base + static_cast<uint32_t>(a * P.acc_stride);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {   // 16 position rows = 2048 B per step
+                                if (k < ksteps)
+                                    umma_bf16_lohi(tacc, a_lo + 128u * k, dhi, b_lo + 128u * k, dhi, idesc, (k == 0) ? acc : 1u);
+                            }
                         }
                     }
                 }
@@ -1228,23 +1252,28 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         const int row = q * 32 + lane;
         mbar_wait(barTmem, 0);
         tc_fence_after();
-        int a = 0;
-        for (int t = 0; t < P.ntaps; ++t) {
-            for (int pr = 0; pr < P.npairs; ++pr, ++a) {
-                const int chunk = 2 * pr + (row >> 6);
-                const int ci = (chunk << 6) + (row & 63);
-                const bool valid = chunk < P.nchunks && ci < P.ci_pitch;
-                float* dst = P.ws + (((long long)split * P.ntaps + t) * P.ci_pitch + ci) * P.co_pitch;
-                const uint32_t trow = tmem_base + static_cast<uint32_t>(a * P.acc_stride) + (static_cast<uint32_t>(q * 32) << 16);
-                for (int c = 0; c < P.bn_tile; c += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(trow + c, v);
-                    tmem_ld_wait();
-                    if (valid) {
+        for (int a = 0; a < P.nacc; ++a) {
+            int t, chunk;
+            if (P.pair_taps) {
+                t = 2 * a + (row >> 6);
+                chunk = 0;
+            } else {
+                t = a / P.npairs;
+                chunk = 2 * (a - t * P.npairs) + (row >> 6);
+            }
+            const int ci = (chunk << 6) + (row & 63);
+            const bool valid = t < P.ntaps && chunk < P.nchunks && ci < P.ci_pitch;
+            const int wtap = t * P.tap_stride + copy;
+            float* dst = P.ws + (((long long)split * P.total_taps + wtap) * P.ci_pitch + ci) * P.co_pitch;
+            const uint32_t trow = tmem_base + static_cast<uint32_t>(a * P.acc_stride) + (static_cast<uint32_t>(q * 32) << 16);
+            for (int c = 0; c < P.bn_tile; c += 16) {
+                uint32_t v[16];
+                tmem_ld16(trow + c, v);
+                tmem_ld_wait();
+                if (valid) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<uint4*>(dst + c + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(dst + c + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
             }
         }
@@ -2331,7 +2360,8 @@ int plan_wgrad(const zsv_conv_desc* d, const Shape& s, WgradPlan* p) {
 
 namespace {
 struct WgradHaloPlan {
-    bool ok;
+    bool ok, spatial;
+    int pair_taps, nacc, ncopies;
     int b[4], tl[4];
     int nchunks, npairs, bn_tile, nbp, stages, acc_stride, tmem_cols, num_kb, kb_per_split, splits, ci_pitch, co_pitch;
     uint32_t a_chunk_bytes, stage_bytes;
@@ -2339,14 +2369,18 @@ struct WgradHaloPlan {
     size_t ws_bytes;
 };
 
-// Temporal 3x1x1, stride 1, "same" padding, plain NDHWC input, all (tap, chunk pair) accumulators within 512 TMEM columns.
+// Stride-1 "same" convolutions on plain NDHWC input whose accumulators fit 512 TMEM columns:
+//   temporal 3x1x1: halo along T, one CTA column;  spatial 1x3xkw: halo along H, one CTA column per filter column.
 WgradHaloPlan plan_wgrad_halo(const zsv_conv_desc* d, const Shape& s) {
     WgradHaloPlan p;
     memset(&p, 0, sizeof(p));
     if (getenv("ZSV_DEBUG_NO_WGRAD_HALO")) return p;
-    if (s.wfold || d->kt != 3 || d->kh != 1 || d->kw != 1 || d->st != 1 || d->sh != 1 || d->sw != 1 || d->pt != 1 ||
-        d->ph != 0 || d->pw != 0)
-        return p;
+    if (s.wfold || d->st != 1 || d->sh != 1 || d->sw != 1) return p;
+    const bool temporal = d->kt == 3 && d->kh == 1 && d->kw == 1 && d->pt == 1 && d->ph == 0 && d->pw == 0;
+    const bool spatial = d->kt == 1 && d->kh == 3 && d->kw >= 1 && d->kw <= 3 && d->pt == 0 && d->ph == 1 &&
+                         d->pw == d->kw / 2 && !getenv("ZSV_DEBUG_NO_WGRAD_HALO_SPATIAL");
+    if (!temporal && !spatial) return p;
+    p.spatial = spatial;
     const int cols16 = (d->Cout + 15) & ~15;
     if (cols16 > 256) return p;
     p.bn_tile = cols16;
@@ -2354,10 +2388,13 @@ WgradHaloPlan plan_wgrad_halo(const zsv_conv_desc* d, const Shape& s) {
     p.nchunks = ceil_div(d->Cin, 64);
     p.npairs = ceil_div(p.nchunks, 2);
     p.acc_stride = (p.bn_tile + 31) & ~31;
-    if (3 * p.npairs * p.acc_stride > 512) return p;
-    p.tmem_cols = pow2_cols(3 * p.npairs * p.acc_stride);
-    // box (W, H, N | T): rows multiple of 16, <= 128, inner multiple of 8, fewest wasted rows and least halo
-    const int E[4] = {d->W, d->H, d->N, d->T};
+    p.pair_taps = p.nchunks == 1;
+    p.nacc = p.pair_taps ? 2 : 3 * p.npairs;          // 3 halo taps
+    if (p.nacc * p.acc_stride > 512) return p;
+    p.tmem_cols = pow2_cols(p.nacc * p.acc_stride);
+    p.ncopies = spatial ? d->kw : 1;
+    // box: inner dims then the halo dim -- temporal (W, H, N | T), spatial (W, T, N | H)
+    const int E[4] = {d->W, spatial ? d->T : d->H, d->N, spatial ? d->H : d->T};
     double best = -1;
     for (int b0 = 1; b0 <= std::min(E[0], 128); ++b0)
         for (int b1 = 1; b1 <= std::min(E[1], 128 / b0); ++b1)
@@ -2380,16 +2417,17 @@ WgradHaloPlan plan_wgrad_halo(const zsv_conv_desc* d, const Shape& s) {
     for (int i = 0; i < 4; ++i) p.tl[i] = ceil_div(E[i], p.b[i]);
     p.num_kb = p.tl[0] * p.tl[1] * p.tl[2] * p.tl[3];
     const int inner = p.b[0] * p.b[1] * p.b[2];
-    p.a_chunk_bytes = align1k((uint32_t)(inner * (p.b[3] + 2)) * 128u);
-    p.stage_bytes = 2u * p.npairs * p.a_chunk_bytes + (uint32_t)p.nbp * kPanelBytes;
+    // pair_taps reads up to one slice past the halo (the dummy second half of the last accumulator)
+    p.a_chunk_bytes = align1k((uint32_t)(inner * (p.b[3] + 2 + (p.pair_taps ? 1 : 0))) * 128u);
+    p.stage_bytes = (p.pair_taps ? 1u : 2u * p.npairs) * p.a_chunk_bytes + (uint32_t)p.nbp * kPanelBytes;
     p.stages = std::min(4, (int)((227 * 1024 - 2048) / p.stage_bytes));
     if (p.stages < 2) return p;
-    const int splits = std::min(p.num_kb, std::max(1, sm_count()));
+    const int splits = std::min(p.num_kb, std::max(1, sm_count() / p.ncopies));
     p.kb_per_split = ceil_div(p.num_kb, splits);
     p.splits = ceil_div(p.num_kb, p.kb_per_split);
     p.ci_pitch = s.cinp;
     p.co_pitch = p.bn_tile;
-    p.ws_bytes = (size_t)p.splits * 3 * p.ci_pitch * p.co_pitch * 4;
+    p.ws_bytes = (size_t)p.splits * s.ntaps * p.ci_pitch * p.co_pitch * 4;
     p.smem = 1024 + p.stages * (int)p.stage_bytes + 16 * p.stages + 64;
     p.ok = true;
     return p;
@@ -2406,13 +2444,25 @@ int launch_wgrad_halo(const WgradHaloPlan& p, const zsv_conv_desc* d, const Shap
     a.stages = p.stages, a.tmem_cols = p.tmem_cols, a.acc_stride = p.acc_stride;
     a.num_kb = p.num_kb, a.kb_per_split = p.kb_per_split;
     a.a_chunk_bytes = p.a_chunk_bytes, a.stage_bytes = p.stage_bytes;
+    a.ncopies = p.ncopies, a.copy_org = p.spatial ? -d->pw : 0, a.tap_stride = p.spatial ? d->kw : 1;
+    a.pair_taps = p.pair_taps, a.nacc = p.nacc, a.total_taps = s.ntaps;
     a.ws = (float*)workspace;
-    auto make = [&](CUtensorMap* m, const void* basep, int C, int pitch, int text) {
+    auto make = [&](CUtensorMap* m, const void* basep, int C, int pitch, int halo_ext) {
         const uint64_t cB = (uint64_t)pitch * 2;
         const uint64_t bW = cB, bH = cB * d->W, bT = bH * d->H, bN = bT * d->T;
-        uint64_t dims[5] = {(uint64_t)C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N, (uint64_t)d->T};
-        uint64_t str[4] = {bW, bH, bN, bT};
-        uint32_t box[5] = {64, (uint32_t)p.b[0], (uint32_t)p.b[1], (uint32_t)p.b[2], (uint32_t)text};
+        uint64_t dims[5], str[4];
+        dims[0] = C;
+        dims[1] = d->W, str[0] = bW;
+        if (p.spatial) {
+            dims[2] = d->T, str[1] = bT;
+            dims[3] = d->N, str[2] = bN;
+            dims[4] = d->H, str[3] = bH;
+        } else {
+            dims[2] = d->H, str[1] = bH;
+            dims[3] = d->N, str[2] = bN;
+            dims[4] = d->T, str[3] = bT;
+        }
+        uint32_t box[5] = {64, (uint32_t)p.b[0], (uint32_t)p.b[1], (uint32_t)p.b[2], (uint32_t)halo_ext};
         return make_map(m, basep, 5, dims, str, box);
     };
     CUtensorMap mX, mDy;
@@ -2427,7 +2477,7 @@ int launch_wgrad_halo(const WgradHaloPlan& p, const zsv_conv_desc* d, const Shap
     });
     if (attr_err != cudaSuccess)
         return fail(ZSV_ERR_CUDA, "cudaFuncSetAttribute(wgrad halo) failed: %s", cudaGetErrorString(attr_err));
-    wgrad_halo_kernel<<<p.splits, 192, p.smem, st>>>(mX, mDy, a);
+    wgrad_halo_kernel<<<dim3(p.splits, p.ncopies), 192, p.smem, st>>>(mX, mDy, a);
     ZSV_LAUNCH_CHECK("wgrad_halo_kernel");
     return ZSV_OK;
 }
@@ -2455,9 +2505,9 @@ extern "C" int zsv_conv3d_wgrad(const zsv_conv_desc* d, const void* x, const voi
             return fail(ZSV_ERR_WORKSPACE, "wgrad: workspace %zu < required %zu bytes", workspace_bytes, hp.ws_bytes);
         rc = launch_wgrad_halo(hp, d, s, x, dy, workspace, st);
         if (rc) return rc;
-        const long long wtotal = (long long)3 * hp.ci_pitch * hp.co_pitch;
+        const long long wtotal = (long long)s.ntaps * hp.ci_pitch * hp.co_pitch;
         const int blocks = (int)std::min<long long>(ceil_div_ll(wtotal, 256), 148 * 8);
-        wgrad_finalize_small_kernel<<<blocks, 256, 0, st>>>((const float*)workspace, dw, hp.splits, 3, hp.ci_pitch,
+        wgrad_finalize_small_kernel<<<blocks, 256, 0, st>>>((const float*)workspace, dw, hp.splits, s.ntaps, hp.ci_pitch,
                                                             hp.co_pitch, d->Cin, d->Cout, 0, s.ntaps);
         ZSV_LAUNCH_CHECK("wgrad_finalize_kernel");
         return ZSV_OK;
