@@ -221,7 +221,7 @@ def run_b200(args):
     criterion = torch.nn.MSELoss().to(dev)
     # main.py:131's torch.optim.Adam; capturable keeps its step counter on the device so the iteration can be graphed
     optimizer = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=args.graph, fused=True)
-    sync = zdist.GradSync() if world > 1 else None
+    sync = zdist.GradSync(bucket_bytes=int(float(os.environ.get("ZSV_BUCKET_MB", "32")) * (1 << 20))) if world > 1 else None
     zdist.set_grad_sync(sync)
     # parameters whose gradients do not come out of the backbone Function (GradSync covers those): the MLP head of
     # network.Model; C3D has no bucketed sync, all of its gradients are reduced after backward

@@ -264,3 +264,27 @@ def test_fprop_bias_addend_relu_epilogue():
     y, _, _ = op.fprop(to_ndhwc(x), wf, stats=False, bias=bias.cuda(), relu=True, addend=to_ndhwc(add))
     torch.cuda.synchronize()
     assert rel_err(from_ndhwc(y, cout), ref) < TOL
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[0] in ("spatial_64_64", "spatial_64_144", "spatial_odd_hw")],
+                         ids=lambda c: c[0])
+def test_row_linearised_kernel_opt_in(case, monkeypatch):
+    """igemm_lin_kernel (opt-in with ZSV_LIN=1; one haloed box per chunk, taps as unaligned descriptor offsets):
+    fprop with statistics and dgrad must match the oracle like the default kernels."""
+    from zeroshotvideoclassification_b200 import ops
+    monkeypatch.setenv("ZSV_LIN", "1")
+    name, N, T, H, W, cin, cout, k, s, p = case
+    x, w = _make(case)
+    op = ops.Conv3d(N, T, H, W, cin, cout, k, s, p)
+    wf, wd = op.pack(w.cuda(), need_dgrad=True)
+    y, ps, pq = op.fprop(to_ndhwc(x), wf, stats=True)
+    ref = vo.conv3d(x, w, None, s, p)
+    assert rel_err(from_ndhwc(y, cout), ref) < TOL
+    yb = y[..., :cout].float().reshape(-1, cout).double()
+    assert torch.allclose(ps.double().sum(0)[:cout].cpu(), yb.sum(0).cpu(), rtol=1e-4, atol=1e-2)
+    g = torch.Generator().manual_seed(4)
+    dy = bf16_round(torch.randn(ref.shape, generator=g))
+    dx_ref, _ = vo.conv3d_grads(x, w, dy, s, p)
+    dx = op.dgrad(to_ndhwc(dy), wd)
+    torch.cuda.synchronize()
+    assert rel_err(from_ndhwc(dx, cin), dx_ref) < TOL
