@@ -288,3 +288,29 @@ def test_row_linearised_kernel_opt_in(case, monkeypatch):
     dx = op.dgrad(to_ndhwc(dy), wd)
     torch.cuda.synchronize()
     assert rel_err(from_ndhwc(dx, cin), dx_ref) < TOL
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[0] in ("spatial_s2_64_230", "spatial_256_460", "temporal_s2_230_128",
+                                                                 "downsample_64_128", "c3d_27tap", "spatial_s2_odd")],
+                         ids=lambda c: c[0])
+def test_cta_pair_kernel_opt_in(case, monkeypatch):
+    """igemm_kmajor_kernel<pair> (opt-in with ZSV_2CTA=1: cluster of two CTAs, tcgen05 cta_group::2 MMAs with M = 256,
+    each CTA loading half of the B tile): fprop with statistics and dgrad must match the oracle, including an odd
+    number of M tiles (the peer's last tile is out of range) and several N tiles."""
+    from zeroshotvideoclassification_b200 import ops
+    monkeypatch.setenv("ZSV_2CTA", "1")
+    name, N, T, H, W, cin, cout, k, s, p = case
+    x, w = _make(case)
+    op = ops.Conv3d(N, T, H, W, cin, cout, k, s, p)
+    wf, wd = op.pack(w.cuda(), need_dgrad=True)
+    y, ps, pq = op.fprop(to_ndhwc(x), wf, stats=True)
+    ref = vo.conv3d(x, w, None, s, p)
+    assert rel_err(from_ndhwc(y, cout), ref) < TOL
+    yb = y[..., :cout].float().reshape(-1, cout).double()
+    assert torch.allclose(ps.double().sum(0)[:cout].cpu(), yb.sum(0).cpu(), rtol=1e-4, atol=1e-2)
+    g = torch.Generator().manual_seed(4)
+    dy = bf16_round(torch.randn(ref.shape, generator=g))
+    dx_ref, _ = vo.conv3d_grads(x, w, dy, s, p)
+    dx = op.dgrad(to_ndhwc(dy), wd)
+    torch.cuda.synchronize()
+    assert rel_err(from_ndhwc(dx, cin), dx_ref) < TOL

@@ -1,5 +1,7 @@
-T1="22,16,56,56,144,64,3,1,1,1,1,1,1,0,0"
-echo "== aligned box 8,1,1,8 (rows 64)"; ZSV_DEBUG_HALO_BOX=8,1,1,8 ZSV_DEBUG_EPI=7 python tools/bench_conv.py $T1 2>&1 | cut -c1-150
-echo "== unaligned box 4,1,1,16 (rows 64)"; ZSV_DEBUG_HALO_UNALIGNED=1 ZSV_DEBUG_HALO_BOX=4,1,1,16 ZSV_DEBUG_EPI=7 python tools/bench_conv.py $T1 2>&1 | cut -c1-150
-echo "== unaligned box 2,2,1,16 (rows 64)"; ZSV_DEBUG_HALO_UNALIGNED=1 ZSV_DEBUG_HALO_BOX=2,2,1,16 ZSV_DEBUG_EPI=7 python tools/bench_conv.py $T1 2>&1 | cut -c1-150
-echo "== aligned box 4,2,1,8 (rows 64)"; ZSV_DEBUG_HALO_BOX=4,2,1,8 ZSV_DEBUG_EPI=7 python tools/bench_conv.py $T1 2>&1 | cut -c1-150
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/pytest_gpu.log
+cat gpurun_out/pytest_gpu.log
+for i in 1 2; do
+python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/ab_a$i.json 2> /dev/null
+ZSV_DEBUG_KEEP_NSTG2=1 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/ab_b$i.json 2> /dev/null
+ZSV_2CTA=1 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/ab_c$i.json 2> /dev/null
+done

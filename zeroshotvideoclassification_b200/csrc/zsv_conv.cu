@@ -196,6 +196,7 @@ struct EpiArgs {
     float* bn_acc;               // smem [2][ncols] running sums of this CTA
     float* bn_scratch;           // smem [4 quadrants][2][width] per-tile sums
     float* st_acc;               // smem [2][ncols] running BatchNorm statistics of this CTA (sum, sum of squares)
+    int remote_arrive;           // CTA pair: the TMEM-empty barrier is a shared::cluster address in the leader CTA
     int debug;   // tuning aid (ZSV_DEBUG_EPI bit mask): 1 = skip the TMA store, 2 = skip TMEM read + staging, 4 = skip stats
 };
 
@@ -410,7 +411,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMa
     // accumulator buffer fully read: hand it back to the MMA warp
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar_tmem_empty);
+    if (lane == 0) {
+        if (E.remote_arrive) mbar_arrive_cluster(bar_tmem_empty);
+        else mbar_arrive(bar_tmem_empty);
+    }
     fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA store
     named_bar_sync(2, kEpiWarps * 32);
     if (et == 0 && !(E.debug & 1)) {
@@ -447,6 +451,12 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMa
 //                 BatchNorm partial sums.  The epilogue of a small-K tile is a latency chain (TMEM load, fences,
 //                 barriers) that bounds the whole kernel, hence the wide group.
 // ------------------------------------------------------------------------------------------------
+// k2 = CTA-pair variant (cluster of 2, tcgen05 cta_group::2): the pair computes two M tiles (one per CTA) against the same
+// N tile with M = 256 MMAs issued by the leader; every CTA loads its own A tile and HALF of the B tile (mapB then has a
+// box of bn_tile/2 rows), so B-operand shared-memory reads and B TMA bytes per SM halve.  "full" barriers live in the
+// leader and count both CTAs' bytes; "empty" and "TMEM full" are multicast commits; the peer's epilogue warps arrive on
+// the leader's "TMEM empty" barrier through its shared::cluster address.
+template <bool k2>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
                     const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
@@ -459,7 +469,8 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int stages = P.stages;
-    const uint32_t stageB = static_cast<uint32_t>(P.bn_tile) * 128u;
+    const uint32_t stageB = static_cast<uint32_t>(k2 ? (P.bn_tile >> 1) : P.bn_tile) * 128u;   // B rows held by this CTA
+    const uint32_t rank = k2 ? cluster_ctarank() : 0u;
     const uint32_t stageBytes = kPanelBytes + stageB;
     const uint32_t ringBytes = stages * stageBytes;
     const int out_panels = (P.bn_tile + 63) >> 6;                    // 64-channel output panels of one tile
@@ -480,20 +491,26 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(barTmemFull + 8u * b, 1);
-            mbar_init(barTmemEmpty + 8u * b, kEpiWarps);
+            mbar_init(barTmemEmpty + 8u * b, k2 ? 2 * kEpiWarps : kEpiWarps);
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), P.tmem_cols);
+    if (warp == 1) {
+        if (k2) tmem_alloc2(smem_u32(tmem_slot), P.tmem_cols);
+        else tmem_alloc(smem_u32(tmem_slot), P.tmem_cols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (k2) cluster_sync_all();     // the peer's barriers and TMEM exist before anything of the pair touches them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t acc_stride = static_cast<uint32_t>(P.tmem_cols) >> 1;
 
     const int rows = P.bw * P.bh * P.bt * P.bn;
     const int kchunks = (P.kdim + 63) >> 6;
-    const int num_tiles = P.m_tiles * P.n_tiles;
+    const int num_tiles = k2 ? ((P.m_tiles + 1) >> 1) * P.n_tiles : P.m_tiles * P.n_tiles;   // pair tiles when k2
+    const int first_tile = k2 ? (blockIdx.x >> 1) : blockIdx.x;
+    const int tile_step = k2 ? (gridDim.x >> 1) : gridDim.x;
 
     // Producer and MMA warps run their loops with all 32 lanes (warp-uniform control flow and addresses); only the
     // TMA / MMA / commit instructions themselves are issued by one elected lane.  The issuing thread is a scalar
@@ -501,11 +518,13 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
     // and dynamic parameter indexing.
     if (warp == 0) {
         const uint32_t leader = elect_one();
-        const uint32_t tx = static_cast<uint32_t>(rows) * 128u + stageB;
+        const uint32_t tx = (static_cast<uint32_t>(rows) * 128u + stageB) * (k2 ? 2u : 1u);   // both CTAs' bytes when k2
+        const uint32_t fullLeader = k2 ? mapa_shared(barFull, 0) : barFull;
         uint32_t stage = 0, phase = 0;   // ring position and phase continue across tiles
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
             int m, in_;
             const int n_tile = fdivmod(tile, P.fd_ntiles, m);
+            if (k2) m = 2 * m + static_cast<int>(rank);   // an M tile past the end reads zeros and stores nothing
             const int iw = fdivmod(m, P.fd_tw, m);
             const int ih = fdivmod(m, P.fd_th, m);
             const int itt = fdivmod(m, P.fd_tt, in_);
@@ -516,11 +535,19 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
                 for (int c0 = 0; c0 < P.kdim; c0 += 64) {
                     mbar_wait(barEmpty + 8u * stage, phase ^ 1u);
                     if (leader) {
-                        const uint32_t full = barFull + 8u * stage;
                         const uint32_t sa = base + stage * stageBytes;
-                        mbar_expect_tx(full, tx);
-                        tma_load_5d(sa, mp, full, c0, w0 + tap.dw, h0 + tap.dh, t0 + tap.dt, n0);
-                        tma_load_3d(sa + kPanelBytes, &mapB, full, c0, n_tile * P.bn_tile, tap.btap);
+                        if (k2) {
+                            const uint32_t full = fullLeader + 8u * stage;
+                            if (rank == 0) mbar_expect_tx(barFull + 8u * stage, tx);
+                            tma2_load_5d(sa, mp, full, c0, w0 + tap.dw, h0 + tap.dh, t0 + tap.dt, n0);
+                            tma2_load_3d(sa + kPanelBytes, &mapB, full, c0,
+                                         n_tile * P.bn_tile + static_cast<int>(rank) * (P.bn_tile >> 1), tap.btap);
+                        } else {
+                            const uint32_t full = barFull + 8u * stage;
+                            mbar_expect_tx(full, tx);
+                            tma_load_5d(sa, mp, full, c0, w0 + tap.dw, h0 + tap.dh, t0 + tap.dt, n0);
+                            tma_load_3d(sa + kPanelBytes, &mapB, full, c0, n_tile * P.bn_tile, tap.btap);
+                        }
                     }
                     __syncwarp();
                     if (++stage == static_cast<uint32_t>(stages)) {
@@ -530,14 +557,14 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 && rank == 0) {
         const uint32_t leader = elect_one();
-        const uint32_t idesc = umma_idesc_bf16(128, P.bn_tile, 0, 0);
+        const uint32_t idesc = umma_idesc_bf16(k2 ? 256 : 128, P.bn_tile, 0, 0);
         const uint32_t dhi = umma_desc_hi(1024, 2);
         const int tail_steps = ((P.kdim - ((kchunks - 1) << 6)) + 15) >> 4;
         uint32_t stage = 0, phase = 0;
         int local = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++local) {
             const uint32_t buf = local & 1;
             mbar_wait(barTmemEmpty + 8u * buf, ((local >> 1) & 1u) ^ 1u);   // epilogue drained this buffer
             tc_fence_after();
@@ -551,17 +578,24 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
                     if (leader) {
                         const uint32_t sa = base + stage * stageBytes;
                         const uint32_t a_lo = umma_desc_lo(sa), b_lo = umma_desc_lo(sa + kPanelBytes);
-                        umma_bf16_lohi(tacc, a_lo, dhi, b_lo, dhi, idesc, acc);
-                        acc = 1;
-                        if (ksteps == 4) {   // common case: straight-line, constant accumulate flag
-                            umma_bf16_lohi(tacc, a_lo + 2u, dhi, b_lo + 2u, dhi, idesc, 1u);
-                            umma_bf16_lohi(tacc, a_lo + 4u, dhi, b_lo + 4u, dhi, idesc, 1u);
-                            umma_bf16_lohi(tacc, a_lo + 6u, dhi, b_lo + 6u, dhi, idesc, 1u);
-                        } else {
+                        if (k2) {
+                            umma2_bf16_lohi(tacc, a_lo, dhi, b_lo, dhi, idesc, acc);
                             for (int k = 1; k < ksteps; ++k)
-                                umma_bf16_lohi(tacc, a_lo + 2u * k, dhi, b_lo + 2u * k, dhi, idesc, 1u);
+                                umma2_bf16_lohi(tacc, a_lo + 2u * k, dhi, b_lo + 2u * k, dhi, idesc, 1u);
+                            umma2_commit_mc(barEmpty + 8u * stage, 3);
+                        } else {
+                            umma_bf16_lohi(tacc, a_lo, dhi, b_lo, dhi, idesc, acc);
+                            if (ksteps == 4) {   // common case: straight-line, constant accumulate flag
+                                umma_bf16_lohi(tacc, a_lo + 2u, dhi, b_lo + 2u, dhi, idesc, 1u);
+                                umma_bf16_lohi(tacc, a_lo + 4u, dhi, b_lo + 4u, dhi, idesc, 1u);
+                                umma_bf16_lohi(tacc, a_lo + 6u, dhi, b_lo + 6u, dhi, idesc, 1u);
+                            } else {
+                                for (int k = 1; k < ksteps; ++k)
+                                    umma_bf16_lohi(tacc, a_lo + 2u * k, dhi, b_lo + 2u * k, dhi, idesc, 1u);
+                            }
+                            umma_commit(barEmpty + 8u * stage);
                         }
-                        umma_commit(barEmpty + 8u * stage);
+                        acc = 1;
                     }
                     __syncwarp();
                     if (++stage == static_cast<uint32_t>(stages)) {
@@ -570,10 +604,13 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
                     }
                 }
             }
-            if (leader) umma_commit(barTmemFull + 8u * buf);
+            if (leader) {
+                if (k2) umma2_commit_mc(barTmemFull + 8u * buf, 3);
+                else umma_commit(barTmemFull + 8u * buf);
+            }
             __syncwarp();
         }
-    } else {
+    } else if (warp >= 2) {
         const int q = warp & 3;               // TMEM lane quadrant this warp may read
         const int half = (warp - 2) >> 2;     // which of the warps of the quadrant (chunk index mod kEpiWarps/4)
         const int row = q * 32 + lane;
@@ -589,6 +626,8 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
         E.addend = P.addend, E.bias = P.bias, E.part_sum = P.part_sum, E.part_sq = P.part_sq;
         E.ncols = P.ncols, E.nbias = P.nbias, E.relu = P.relu, E.part_pitch = P.part_pitch;
         E.debug = P.debug;
+        E.remote_arrive = k2 ? 1 : 0;
+        const uint32_t tmemEmptyBar = k2 ? mapa_shared(barTmemEmpty, 0) : barTmemEmpty;
         float* statbuf = reinterpret_cast<float*>(smem + statOff);
         E.bn_y = P.bn_y, E.bn_tab = P.bn_tab, E.bn_relu = P.bn_relu;
         E.bn_acc = statbuf;
@@ -597,9 +636,10 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
         if (P.bn_y != nullptr || P.part_sum != nullptr)   // running sums start at zero; the first tile's barriers order this before any use
             for (int i = et; i < 2 * P.ncols; i += kEpiWarps * 32) statbuf[i] = 0.f;
         int local = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++local) {
             int m, in_;
             const int n_tile = fdivmod(tile, P.fd_ntiles, m);
+            if (k2) m = 2 * m + static_cast<int>(rank);
             const int m_tile = m;
             const int iw = fdivmod(m, P.fd_tw, m);
             const int ih = fdivmod(m, P.fd_th, m);
@@ -615,7 +655,7 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
             const uint32_t sb = (P.nstg == 2 ? (local & 1) : 0) * stagingBytes;
             const uint32_t trow = tmem_base + buf * acc_stride + (static_cast<uint32_t>(q * 32) << 16);
             epilogue_tile(E, &mapOut, smem + stagingOff + sb, base + stagingOff + sb, statbuf, trow,
-                          barTmemEmpty + 8u * buf, P.bn_tile, n_tile * P.bn_tile, valid, off, w0, h0, t0, n0, m_tile,
+                          tmemEmptyBar + 8u * buf, P.bn_tile, n_tile * P.bn_tile, valid, off, w0, h0, t0, n0, m_tile,
                           P.nstg == 2, q, half, row, lane, et);
         }
         if (et == 0) tma_store_wait_all();   // global writes of the last tile complete before the CTA exits
@@ -633,10 +673,12 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
             }
         }
     }
-    __syncthreads();
+    if (k2) cluster_sync_all();     // neither CTA leaves (or frees TMEM) while the pair still reads its shared memory
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, P.tmem_cols);
+        if (k2) tmem_dealloc2(tmem_base, P.tmem_cols);
+        else tmem_dealloc(tmem_base, P.tmem_cols);
     }
 }
 
@@ -877,6 +919,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         E.addend = P.addend, E.bias = P.bias, E.part_sum = P.part_sum, E.part_sq = P.part_sq;
         E.ncols = P.ncols, E.nbias = P.nbias, E.relu = P.relu, E.part_pitch = P.part_pitch;
         E.debug = P.debug;
+        E.remote_arrive = 0;
         float* statbuf = reinterpret_cast<float*>(smem + statOff);
         E.bn_y = P.bn_y, E.bn_tab = P.bn_tab, E.bn_relu = P.bn_relu;
         E.bn_acc = statbuf;
@@ -1135,6 +1178,7 @@ igemm_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         E.addend = P.addend, E.bias = P.bias, E.part_sum = P.part_sum, E.part_sq = P.part_sq;
         E.ncols = P.ncols, E.nbias = P.nbias, E.relu = P.relu, E.part_pitch = P.part_pitch;
         E.debug = P.debug;
+        E.remote_arrive = 0;
         float* statbuf = reinterpret_cast<float*>(smem + statOff);
         E.bn_y = P.bn_y, E.bn_tab = P.bn_tab, E.bn_relu = P.bn_relu;
         E.bn_acc = statbuf;
@@ -1963,31 +2007,56 @@ int igemm_smem_bytes(int bn_tile, int stages, int nstg, int scratch = 0) {
            16 * stages + 48 + 64;
 }
 
+// CTA pairs (cta_group::2) for the generic kernel: opt-in while it is being measured (ZSV_2CTA=1)
+bool igemm_use_pair(int bn_tile, long long m_tiles) {
+    const char* e = getenv("ZSV_2CTA");
+    return e && atoi(e) == 1 && (bn_tile % 16) == 0 && m_tiles >= 2;
+}
+// grid of the generic kernel (one BatchNorm partial row per CTA)
+int igemm_grid(int bn_tile, long long m_tiles, int n_tiles) {
+    if (igemm_use_pair(bn_tile, m_tiles))
+        return 2 * (int)std::min<long long>(((m_tiles + 1) / 2) * n_tiles, sm_count() / 2);
+    return (int)std::min<long long>(m_tiles * n_tiles, sm_count());
+}
+
 int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtensorMap& mapOut, IgemmArgs& a,
                  long long m_tiles, int n_tiles, cudaStream_t stream, BnFuseLaunch* fuse = nullptr) {
     // one persistent CTA per SM owns (almost) all shared memory: as many ring stages as fit, at most 8
     // two output staging buffers when at least 3 ring stages still fit beside them
     const int scratch = fuse ? bn_scratch_bytes(a.ncols, a.bn_tile) : (a.part_sum ? bn_scratch_bytes(a.ncols, 0) : 0);
+    // shared memory per ring stage: the A tile + the B rows THIS CTA holds (half of them in a CTA pair); the staging
+    // buffers always hold the full N tile
+    const bool pair = igemm_use_pair(a.bn_tile, m_tiles);
+    const int b_rows = pair ? a.bn_tile / 2 : a.bn_tile;
+    auto smem_for = [&](int stages_, int nstg_) {
+        return 1024 + stages_ * ((int)kPanelBytes + b_rows * 128) + nstg_ * ((a.bn_tile + 63) / 64) * (int)kPanelBytes + scratch +
+               16 * stages_ + 48 + 64;
+    };
     int nstg = 2;
+    if (const char* e = getenv("ZSV_DEBUG_NSTG")) nstg = atoi(e) == 1 ? 1 : 2;
     int stages = 8;
-    while (stages > 2 && igemm_smem_bytes(a.bn_tile, stages, nstg, scratch) > 226 * 1024) --stages;
-    if (stages < 3 || igemm_smem_bytes(a.bn_tile, stages, nstg, scratch) > 226 * 1024) {
-        nstg = 1;
-        stages = 8;
-        while (stages > 2 && igemm_smem_bytes(a.bn_tile, stages, nstg, scratch) > 226 * 1024) --stages;
+    while (stages > 2 && smem_for(stages, nstg) > 226 * 1024) --stages;
+    // a second staging buffer only overlaps the TMA store of a tile with the next epilogue; ring depth hides load
+    // latency for every k-block, so it wins when the two compete (wide N tiles)
+    if (nstg == 2 && stages < 5) {
+        int s1 = 8;
+        while (s1 > 2 && smem_for(s1, 1) > 226 * 1024) --s1;
+        if (s1 > stages && !getenv("ZSV_DEBUG_KEEP_NSTG2")) nstg = 1, stages = s1;
     }
     if (const char* e = getenv("ZSV_DEBUG_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));
     a.nstg = nstg;
     a.stages = stages;
     a.tmem_cols = 2 * pow2_cols(a.bn_tile);   // two accumulator buffers
     if (a.tmem_cols > 512) return fail(ZSV_ERR_UNSUPPORTED, "igemm: N tile %d too wide for two TMEM buffers", a.bn_tile);
-    const int smem = igemm_smem_bytes(a.bn_tile, stages, nstg, scratch);
+    const int smem = smem_for(stages, nstg);
     if (smem > 227 * 1024) return fail(ZSV_ERR_UNSUPPORTED, "igemm: shared memory budget exceeded (%d bytes)", smem);
     a.scratch_bytes = scratch;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(igemm_kmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_err = cudaFuncSetAttribute(igemm_kmajor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(igemm_kmajor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (attr_err != cudaSuccess)
         return fail(ZSV_ERR_CUDA, "cudaFuncSetAttribute(igemm) failed: %s", cudaGetErrorString(attr_err));
@@ -1997,8 +2066,9 @@ int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtenso
     a.fd_ntiles = make_fastdiv(n_tiles), a.fd_tw = make_fastdiv(a.tw), a.fd_th = make_fastdiv(a.th);
     a.fd_tt = make_fastdiv(a.tt);
     if (const char* e = getenv("ZSV_DEBUG_EPI")) a.debug = atoi(e);
-    const long long tiles = m_tiles * n_tiles;
-    const int grid = (int)std::min<long long>(tiles, sm_count());
+    const bool two = igemm_use_pair(a.bn_tile, m_tiles);
+    const long long tiles = two ? ((m_tiles + 1) / 2) * n_tiles : m_tiles * n_tiles;
+    const int grid = two ? 2 * (int)std::min<long long>(tiles, sm_count() / 2) : (int)std::min<long long>(tiles, sm_count());
     if (fuse) {
         if (fuse->rows_used + grid > fuse->capacity)
             return fail(ZSV_ERR_WORKSPACE, "dgrad: BN-fusion partial buffer holds %d rows, need %d", fuse->capacity,
@@ -2009,7 +2079,19 @@ int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtenso
     }
     MapPack pack;
     for (int i = 0; i < kMaxMaps; ++i) pack.m[i] = maps[i];
-    igemm_kmajor_kernel<<<grid, kIgemmThreads, smem, stream>>>(pack, mapB, mapOut, a);
+    if (two) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kIgemmThreads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr, cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_kmajor_kernel<true>, pack, mapB, mapOut, a);
+        if (e != cudaSuccess) return fail(ZSV_ERR_CUDA, "launch of igemm_kmajor_kernel<pair> failed: %s", cudaGetErrorString(e));
+    } else {
+        igemm_kmajor_kernel<false><<<grid, kIgemmThreads, smem, stream>>>(pack, mapB, mapOut, a);
+    }
     ZSV_LAUNCH_CHECK("igemm_kmajor_kernel");
     return ZSV_OK;
 }
@@ -2506,7 +2588,7 @@ extern "C" int zsv_conv3d_stat_rows(const zsv_conv_desc* d) {
     const long long m_tiles = (long long)ceil_div(s.Wo, b.bw) * ceil_div(s.Ho, b.bh) * ceil_div(s.To, b.bt) * ceil_div(d->N, b.bn);
     int bn_tile, n_tiles;
     choose_ntile(d->Cout, m_tiles, &bn_tile, &n_tiles);
-    return (int)std::min<long long>(m_tiles * n_tiles, sm_count());
+    return igemm_grid(bn_tile, m_tiles, n_tiles);
 }
 
 extern "C" int zsv_conv3d_fprop(const zsv_conv_desc* d, const void* x, const void* w_fprop, void* y, float* part_sum,
@@ -2567,7 +2649,8 @@ extern "C" int zsv_conv3d_fprop(const zsv_conv_desc* d, const void* x, const voi
     {
         uint64_t dims[3] = {(uint64_t)s.keff, (uint64_t)d->Cout, (uint64_t)s.ftaps};
         uint64_t strides[2] = {(uint64_t)s.kpitch * 2, (uint64_t)s.kpitch * 2 * d->Cout};
-        uint32_t box[3] = {64, (uint32_t)a.bn_tile, 1};
+        // a CTA pair loads half of the B rows per CTA
+        uint32_t box[3] = {64, (uint32_t)(igemm_use_pair(a.bn_tile, m_tiles) ? a.bn_tile / 2 : a.bn_tile), 1};
         rc = make_map(&mapB, w_fprop, 3, dims, strides, box);
         if (rc) return rc;
     }
@@ -2697,7 +2780,7 @@ extern "C" int zsv_conv3d_dgrad(const zsv_conv_desc* d, const void* dy, const vo
                 CUtensorMap mapB;
                 uint64_t dims[3] = {(uint64_t)d->Cout, (uint64_t)d->Cin, (uint64_t)s.ntaps};
                 uint64_t strides[2] = {(uint64_t)s.coutp * 2, (uint64_t)s.coutp * 2 * d->Cin};
-                uint32_t box[3] = {64, (uint32_t)a.bn_tile, 1};
+                uint32_t box[3] = {64, (uint32_t)(igemm_use_pair(a.bn_tile, m_tiles) ? a.bn_tile / 2 : a.bn_tile), 1};
                 rc = make_map(&mapB, w_dgrad, 3, dims, strides, box);
                 if (rc) return rc;
                 CUtensorMap mapOut;
