@@ -5,6 +5,7 @@
 // Reference call sites: nn.BatchNorm3d resnet.py:48,95,97,182,185,272; nn.ReLU resnet.py:49,95,98;
 // residual add resnet.py:110-111; nn.MaxPool3d network.py:103-118; input reshape network.py:534-535.
 #include <algorithm>
+#include <mutex>
 
 #include "zsv_internal.h"
 #include "zsv_ptx.cuh"
@@ -815,12 +816,11 @@ extern "C" int zsv_bn_bwd(const void* g, const void* out, int relu, const float*
     float* sums = partial + (size_t)kBwdMaxBlocks * 4 * Cp;
     const __nv_bfloat16 *gb = (const __nv_bfloat16*)g, *ob = (const __nv_bfloat16*)out, *yb = (const __nv_bfloat16*)y,
                         *y2b = (const __nv_bfloat16*)y2;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::once_flag attr_once;   // entry points may be called from several threads (autograd, DataParallel)
+    std::call_once(attr_once, [] {
         cudaFuncSetAttribute(bn_bwd_reduce_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         cudaFuncSetAttribute(bn_bwd_reduce_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        attr_done = true;
-    }
+    });
     if (smem_r > 160 * 1024) return fail(ZSV_ERR_UNSUPPORTED, "bn_bwd: reduction scratch too large");
     const long long work_r = ceil_div_ll(rows, (long long)R * 4);
     const int nblocks = y2 ? resident_grid(bn_bwd_reduce_kernel<true>, 256, smem_r, work_r, kBwdMaxBlocks)

@@ -7,6 +7,7 @@
 // Nearest class (main.py:183, main.py:321-322): scipy cdist(...,'cosine') + argmin / argsort[:, :k],
 // restated in fp64 with scipy's exact operation order so that indices are bit-identical.
 #include <algorithm>
+#include <mutex>
 
 #include "zsv_internal.h"
 #include "zsv_ptx.cuh"
@@ -480,12 +481,11 @@ extern "C" int zsv_nearest_class(const float* emb, const float* cls, int N, int 
     const size_t smem = sizeof(double) * ((size_t)R * C + R) + sizeof(float) * ((size_t)R * D + (size_t)nt * (kKC + 1));
     if (smem > 200 * 1024)
         return fail(ZSV_ERR_UNSUPPORTED, "nearest_class: class table too large for shared memory (%zu bytes)", smem);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static std::once_flag attr_once;
+    std::call_once(attr_once, [] {
         cudaFuncSetAttribute(nearest_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cudaFuncSetAttribute(nearest_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_done = true;
-    }
+    });
     if (R == 1)
         nearest_kernel<1><<<N, nt, smem, st>>>(emb, cls, N, C, D, k, idx_out, dist_out);
     else
