@@ -153,6 +153,14 @@ int zsv_relu_bwd(const void* g, const void* out, void* dz, long long rows, int C
  * zero columns on the left. */
 int zsv_repack_input(const float* x, void* out, int N, int C, int T, int H, int W, int layout, int wpad_left,
                      void* stream);
+/* Input pipeline stage fused with the layout conversion: decoded uint8 frames [N][T][Hs][Ws][3] (what the loader holds
+ * before auxiliary/transforms.py:41-56) -> ToFloatTensorInZeroOne ((x/255-1)/2) -> Resize(resize_short) (bilinear,
+ * align_corners=False, scale = resize_short/min(Hs,Ws)) -> crop x crop window at crop_ij[n] = (i, j) in the resized
+ * frame -> optional horizontal flip (flip[n] != 0; NULL = none) -> bf16 W-folded layout [N][T][crop][crop+8][8] of
+ * zsv_repack_input(layout=1).  crop_ij: device int32 [N][2]; flip: device uint8 [N].  A clip travels to the GPU as
+ * uint8 (0.6 MB instead of 2.4 MB of fp32) and the CPU transform disappears. */
+int zsv_clip_transform(const uint8_t* frames, void* out, int N, int T, int Hs, int Ws, int resize_short, int crop,
+                       const int32_t* crop_ij, const uint8_t* flip, int wpad_left, void* stream);
 /* bf16 NDHWC (pitch cpad(C)) <-> fp32 NCDHW, used by the per-module autograd shims and tests. */
 int zsv_ndhwc_to_ncdhw(const void* x, float* out, int N, int C, int T, int H, int W, void* stream);
 int zsv_ncdhw_to_ndhwc(const float* x, void* out, int N, int C, int T, int H, int W, void* stream);

@@ -107,6 +107,28 @@ def nearest_fixture():
     np.savez_compressed(os.path.join(OUT, "nearest_scipy.npz"), **out)
 
 
+def transform_fixture():
+    """The reference's own clip transform (auxiliary/transforms.py:41-56) on small random frames: the validation
+    pipeline as get_transform(True) builds it, and the training pipeline with its random decisions pinned
+    (crop origin (5, 9), flipped).  transforms.py:3 imports imageio for GIF dumps only; it is stubbed."""
+    import importlib
+    sys.modules.setdefault("imageio", types.ModuleType("imageio"))
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    tr = importlib.import_module("auxiliary.transforms")
+    g = torch.Generator().manual_seed(123)
+    out = {}
+    frames = torch.randint(0, 256, (1, 68, 90, 3), generator=g, dtype=torch.uint8)       # upscaled: short side 68 -> 128
+    out["landscape_frames"] = frames.numpy()
+    out["landscape_val"] = tr.get_transform(True)(frames).numpy()
+    frames = torch.randint(0, 256, (1, 200, 150, 3), generator=g, dtype=torch.uint8)     # downscaled: short side 150 -> 128
+    vid = tr.Resize(128)(tr.ToFloatTensorInZeroOne()(frames))
+    out["portrait_frames"] = frames.numpy()
+    out["portrait_train_5_9_flip"] = tr.crop(vid, 5, 9, 112, 112).flip(dims=(-1,)).numpy()
+    out["portrait_resized_hw"] = np.array(vid.shape[-2:])
+    np.savez_compressed(os.path.join(OUT, "clip_transform.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     network = import_reference()
@@ -122,6 +144,7 @@ def main():
     json.dump(r3d_init, open(os.path.join(OUT, "r3d_init_seed0.json"), "w"))
     json.dump(r3d, open(os.path.join(OUT, "r3d_step_small.json"), "w"))
     nearest_fixture()
+    transform_fixture()
     print("golden fixtures written to", OUT)
 
 

@@ -197,3 +197,42 @@ def test_maxpool_forward_backward():
         assert torch.equal(from_ndhwc(y, C), ref.detach())
         dx = ops.maxpool3d_bwd(to_ndhwc(dy), am, tuple(to_ndhwc(x).shape), C, k, p)
         assert torch.equal(from_ndhwc(dx, C), xr.grad)
+
+
+def test_clip_transform_matches_oracle_and_feeds_the_model():
+    """zsv_clip_transform (uint8 frames -> normalise -> Resize(128) -> crop 112 -> flip -> bf16 W-folded) vs the transform
+    oracle (pinned to the reference's transforms), per clip crop origins / flips, up- and down-scaling; and the model
+    gives the same embeddings from the GPU-transformed clips as from the fp32 batch the reference loader would build."""
+    import numpy as np
+    import torch
+    from oracle import transform_oracle as to
+    from zeroshotvideoclassification_b200 import ops
+    from zeroshotvideoclassification_b200 import video_models as vm
+    g = torch.Generator().manual_seed(8)
+    for (T, H, W) in ((4, 68, 90), (3, 200, 150), (2, 128, 171)):
+        N = 3
+        frames = torch.randint(0, 256, (N, T, H, W, 3), generator=g, dtype=torch.uint8)
+        scale = 128.0 / min(H, W)
+        hr, wr = int(np.floor(H * scale)), int(np.floor(W * scale))
+        ij = torch.tensor([[0, 0], [hr - 112, wr - 112], list(to.center_crop_origin(hr, wr))], dtype=torch.int32)
+        flip = torch.tensor([0, 1, 1], dtype=torch.uint8)
+        out = ops.clip_transform(frames.cuda(), ij, flip)
+        torch.cuda.synchronize()
+        assert out.shape == (N, T, 112, 120, 8)
+        got = out[:, :, :, 3:115, :3].float().cpu().permute(0, 4, 1, 2, 3)             # [N,3,T,112,112]
+        for n in range(N):
+            ref = to.clip_transform(frames[n], ij[n].tolist(), bool(flip[n]))
+            assert float((got[n] - ref).abs().max()) < 2.5e-3                           # bf16 rounding of values in [-0.5, 0]
+        assert float(out[:, :, :, :3].abs().max()) == 0.0 and float(out[:, :, :, 115:].abs().max()) == 0.0
+        assert float(out[..., 3:].abs().max()) == 0.0
+    # end to end: same embeddings as from the fp32 clips (bf16 rounding of the input is where both paths start)
+    torch.manual_seed(0)
+    model = vm.get_network(vm.default_opt("r2plus1d_18")).cuda().eval()
+    frames = torch.randint(0, 256, (2, 8, 136, 180, 3), generator=g, dtype=torch.uint8)
+    ij = torch.tensor([[3, 17], [8, 40]], dtype=torch.int32)
+    flip = torch.tensor([1, 0], dtype=torch.uint8)
+    x32 = torch.stack([to.clip_transform(frames[n], ij[n].tolist(), bool(flip[n])) for n in range(2)])[:, None]
+    with torch.no_grad():
+        emb_ref, _ = model(x32.cuda())
+        emb_gpu, _ = model(ops.clip_transform(frames.cuda(), ij, flip))
+    assert float((emb_ref - emb_gpu).abs().max() / emb_ref.abs().max()) < 2e-2

@@ -159,3 +159,17 @@ def test_oracle_reproduces_reference_r3d_step(seeded_r3d):
         _check_sum(grads[name], g, 1e-2 if grads[name].dim() == 1 else 2e-3, name)
     for name in gold["dead"]:
         assert name not in grads
+
+
+def test_transform_oracle_matches_reference_transform():
+    """oracle/transform_oracle.py == the reference's own transform functions (fixture from auxiliary/transforms.py)."""
+    from oracle import transform_oracle as to
+    z = np.load(os.path.join(GOLD, "clip_transform.npz"))
+    f = torch.from_numpy(z["landscape_frames"])
+    hr, wr = 128, int(np.floor(90 * (128.0 / 68)))
+    got = to.clip_transform(f, to.center_crop_origin(hr, wr), flip=False)
+    assert np.array_equal(got.numpy(), z["landscape_val"])                  # same torch ops in the same order
+    f = torch.from_numpy(z["portrait_frames"])
+    got = to.clip_transform(f, (5, 9), flip=True)
+    assert np.array_equal(got.numpy(), z["portrait_train_5_9_flip"])
+    assert tuple(z["portrait_resized_hw"]) == (int(np.floor(200 * (128.0 / 150))), 128)

@@ -73,6 +73,7 @@ SIGNATURES = {
     "zsv_l2norm_fwd": (_I, [_P, _P, _P, _I, _I, _F, _P]),
     "zsv_l2norm_bwd": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "zsv_repack_input": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "zsv_clip_transform": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     "zsv_ndhwc_to_ncdhw": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "zsv_ncdhw_to_ndhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "zsv_bn_finalize_workspace": (_SZ, [_I]),

@@ -926,3 +926,76 @@ extern "C" int zsv_maxpool3d_bwd(const void* dy, const int32_t* argmax, const vo
     ZSV_LAUNCH_CHECK("maxpool_bwd_kernel");
     return ZSV_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Input pipeline stage (auxiliary/transforms.py:41-56 get_transform): uint8 THWC frames ->
+//   ToFloatTensorInZeroOne  (x/255 - 1)/2                                   transforms.py:116-117
+//   Resize(128)             bilinear, align_corners=False, scale = 128/min(H,W)   transforms.py:99-108
+//   Center/RandomCrop(112)  window origin (i, j) per clip                   transforms.py:132-165
+//   RandomHorizontalFlip    per clip                                        transforms.py:189-195
+// fused with the layout conversion of zsv_repack_input: one pass from the decoded frames to the bf16 W-folded tensor
+// the first convolution reads.  One thread per output position (3 channels + 5 zero lanes = one 16-byte store).
+// ------------------------------------------------------------------------------------------------
+namespace zsv {
+namespace {
+__global__ void clip_transform_kernel(const uint8_t* __restrict__ frames, __nv_bfloat16* __restrict__ out, int N, int T,
+                                      int Hs, int Ws, int Hr, int Wr, float rscale, int crop, int Wp, int wl,
+                                      const int32_t* __restrict__ crop_ij, const uint8_t* __restrict__ flip) {
+    const long long total = (long long)N * T * crop * Wp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        const int wp = static_cast<int>(r % Wp);
+        r /= Wp;
+        const int h = static_cast<int>(r % crop);
+        r /= crop;
+        const int t = static_cast<int>(r % T);
+        const int n = static_cast<int>(r / T);
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const int w = wp - wl;
+        if (w >= 0 && w < crop) {
+            const int wsrc = flip != nullptr && flip[n] ? crop - 1 - w : w;
+            const int yo = crop_ij[2 * n] + h, xo = crop_ij[2 * n + 1] + wsrc;   // position in the resized frame
+            // PyTorch upsample_bilinear2d, align_corners = false, scale given: src = (dst + 0.5) / scale - 0.5, clamped at 0
+            float sy = rscale * (yo + 0.5f) - 0.5f, sx = rscale * (xo + 0.5f) - 0.5f;
+            sy = sy < 0.f ? 0.f : sy;
+            sx = sx < 0.f ? 0.f : sx;
+            const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+            const int y1 = y0 + (y0 < Hs - 1 ? 1 : 0), x1 = x0 + (x0 < Ws - 1 ? 1 : 0);
+            const float ly = sy - y0, lx = sx - x0;
+            const float hy = 1.f - ly, hx = 1.f - lx;
+            const uint8_t* f = frames + ((long long)n * T + t) * Hs * Ws * 3;
+            (void)Hr;
+            (void)Wr;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float p00 = (f[((long long)y0 * Ws + x0) * 3 + c] / 255.f - 1.0f) / 2.0f;
+                const float p01 = (f[((long long)y0 * Ws + x1) * 3 + c] / 255.f - 1.0f) / 2.0f;
+                const float p10 = (f[((long long)y1 * Ws + x0) * 3 + c] / 255.f - 1.0f) / 2.0f;
+                const float p11 = (f[((long long)y1 * Ws + x1) * 3 + c] / 255.f - 1.0f) / 2.0f;
+                v[c] = hy * (hx * p00 + lx * p01) + ly * (hx * p10 + lx * p11);
+            }
+        }
+        *reinterpret_cast<uint4*>(out + i * 8) = pack8(v);
+    }
+}
+}  // namespace
+}  // namespace zsv
+
+extern "C" int zsv_clip_transform(const uint8_t* frames, void* out, int N, int T, int Hs, int Ws, int resize_short,
+                                  int crop, const int32_t* crop_ij, const uint8_t* flip, int wpad_left, void* stream) {
+    if (!frames || !out || !crop_ij) return fail(ZSV_ERR_BAD_ARG, "clip_transform: null pointer");
+    if (N < 1 || T < 1 || Hs < 1 || Ws < 1 || resize_short < 1 || crop < 1) return fail(ZSV_ERR_BAD_ARG, "clip_transform: bad extents");
+    if (wpad_left < 0 || wpad_left > 8) return fail(ZSV_ERR_BAD_ARG, "clip_transform: wpad_left out of range");
+    // transforms.py:103-105: scale = float(size) / min(h, w); F.interpolate(scale_factor=scale) -> floor(in * scale)
+    const double scale = (double)resize_short / (double)std::min(Hs, Ws);
+    const int Hr = (int)floor((double)Hs * scale), Wr = (int)floor((double)Ws * scale);
+    if (Hr < crop || Wr < crop) return fail(ZSV_ERR_BAD_ARG, "clip_transform: crop %d larger than the resized frame %dx%d", crop, Hr, Wr);
+    const float rscale = (float)(1.0 / scale);
+    const int Wp = crop + 8;
+    const long long total = (long long)N * T * crop * Wp;
+    zsv::clip_transform_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        frames, (__nv_bfloat16*)out, N, T, Hs, Ws, Hr, Wr, rscale, crop, Wp, wpad_left, crop_ij, flip);
+    ZSV_LAUNCH_CHECK("clip_transform_kernel");
+    return ZSV_OK;
+}

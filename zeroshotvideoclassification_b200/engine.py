@@ -266,16 +266,24 @@ class BackboneRunner:
         rec = UnitRec(spec, op, x, wd, y, mean, invstd, out, relu, scale, shift, table) if self.need_grad else None
         return out, y, (scale, shift), rec, (op.To, op.Ho, op.Wo)
 
+    @staticmethod
+    def _input(x: torch.Tensor, wpad_left: int):
+        """fp32 NCDHW clips (main.py:167) or the bf16 W-folded tensor ops.clip_transform produced -> (folded, N, T, H, W)."""
+        if x.dtype == torch.bfloat16 and x.dim() == 5 and x.shape[-1] == 8:
+            N, T, H, Wp, _ = x.shape
+            return x.contiguous(), N, T, H, Wp - 8
+        N, _, T, H, W = x.shape
+        return ops.repack_input(x, _lib.X_WFOLD, wpad_left), N, T, H, W
+
     def forward(self, x_ncdhw: torch.Tensor) -> torch.Tensor:
-        N, _, T, H, W = x_ncdhw.shape
+        folded, N, T, H, W = self._input(x_ncdhw, self.stem_specs[0].padding[2])
         names, plan = _network_plan(N, T, H, W, self.need_grad, self.arch)
         if not self.train and not self.need_grad:
-            return self._forward_folded(x_ncdhw, names, plan)
+            return self._forward_folded(folded, (N, T, H, W), names, plan)
         wfs, wds = plan.pack([self.t[n + ".weight"] for n in names])
         self.packed = {n: (wf, wd) for n, wf, wd in zip(names, wfs, wds)}
         s0 = self.stem_specs[0]
-        a = ops.repack_input(x_ncdhw, _lib.X_WFOLD, s0.padding[2])
-        a, _, _, rec, d = self._unit(s0, a, (N, T, H, W), True, layout=_lib.X_WFOLD, need_dgrad=False)
+        a, _, _, rec, d = self._unit(s0, folded, (N, T, H, W), True, layout=_lib.X_WFOLD, need_dgrad=False)
         self.stem_recs.append(rec)
         for sp in self.stem_specs[1:]:
             a, _, _, rec, d = self._unit(sp, a, (N, *d), True)
@@ -288,13 +296,13 @@ class BackboneRunner:
         return a
 
     # -- inference: BatchNorm folded into the convolutions ------------------------------------------
-    def _forward_folded(self, x_ncdhw: torch.Tensor, names, plan) -> torch.Tensor:
+    def _forward_folded(self, folded: torch.Tensor, dims, names, plan) -> torch.Tensor:
         """model.eval() under no_grad (evaluate(), main.py:224-257): every conv -> BN -> (+shortcut) -> ReLU group is ONE
         kernel -- running-statistics BatchNorm folded into the packed weights and a bias, residual add and ReLU in the
         convolution's epilogue; no statistics, no tape, no separate normalisation passes."""
-        N, _, T, H, W = x_ncdhw.shape
+        N, T, H, W = dims
         specs = all_conv_specs(self.arch)
-        key = (self.arch, N, T, H, W, str(x_ncdhw.device), self.t[specs[0].name + ".weight"].data_ptr())
+        key = (self.arch, N, T, H, W, str(folded.device), self.t[specs[0].name + ".weight"].data_ptr())
         packed = _folded_weights(self.t, names, specs, plan, key)
 
         def conv(spec, x, dims, relu, layout=_lib.X_NDHWC, addend=None):
@@ -304,8 +312,7 @@ class BackboneRunner:
             return y, (dims[0], op.To, op.Ho, op.Wo)
 
         s0 = self.stem_specs[0]
-        a = ops.repack_input(x_ncdhw, _lib.X_WFOLD, s0.padding[2])
-        a, d = conv(s0, a, (N, T, H, W), True, layout=_lib.X_WFOLD)
+        a, d = conv(s0, folded, (N, T, H, W), True, layout=_lib.X_WFOLD)
         for sp in self.stem_specs[1:]:
             a, d = conv(sp, a, d, True)
         for b in self.block_specs:

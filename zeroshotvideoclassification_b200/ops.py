@@ -234,6 +234,26 @@ def repack_input(x: torch.Tensor, layout: int = _lib.X_NDHWC, wpad_left: int = 0
     return out
 
 
+def clip_transform(frames: torch.Tensor, crop_ij: torch.Tensor, flip: Optional[torch.Tensor] = None,
+                   resize_short: int = 128, crop: int = 112, wpad_left: int = 3) -> torch.Tensor:
+    """uint8 frames [N,T,Hs,Ws,3] (CUDA) -> the transform of auxiliary/transforms.py:41-56 (normalise, Resize(128),
+    crop 112 at crop_ij[n] = (i, j), optional flip) -> bf16 W-folded clips [N,T,112,120,8] that ``Model.forward``
+    accepts in place of the fp32 ``[B,nc,3,T,H,W]`` batch."""
+    _require_cuda(frames, "clip_transform")
+    lib = _lib.load()
+    if frames.dtype != torch.uint8 or frames.dim() != 5 or frames.shape[-1] != 3:
+        raise RuntimeError("clip_transform: expected uint8 frames [N,T,H,W,3]")
+    frames = frames.contiguous()
+    N, T, Hs, Ws, _ = frames.shape
+    crop_ij = crop_ij.to(device=frames.device, dtype=torch.int32).contiguous()
+    if flip is not None:
+        flip = flip.to(device=frames.device, dtype=torch.uint8).contiguous()
+    out = torch.empty((N, T, crop, crop + 8, 8), dtype=torch.bfloat16, device=frames.device)
+    check(lib.zsv_clip_transform(ptr(frames), ptr(out), N, T, Hs, Ws, resize_short, crop, ptr(crop_ij), ptr(flip),
+                                 wpad_left, _stream()), "zsv_clip_transform")
+    return out
+
+
 def ndhwc_to_ncdhw(x: torch.Tensor, channels: int) -> torch.Tensor:
     lib = _lib.load()
     N, T, H, W, _ = x.shape

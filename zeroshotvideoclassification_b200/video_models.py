@@ -202,8 +202,11 @@ class Model(nn.Module):
         nn.init.xavier_uniform_(self.special_tokens.weight)
 
     def forward(self, x: torch.Tensor):
-        bs, nc = x.shape[:2]
-        x = x.reshape(bs * nc, *x.shape[2:])
+        if x.dtype == torch.bfloat16 and x.dim() == 5 and x.shape[-1] == 8:
+            pass                             # clips already transformed on the GPU (ops.clip_transform): [B*nc,T,H,W+8,8]
+        else:
+            bs, nc = x.shape[:2]
+            x = x.reshape(bs * nc, *x.shape[2:])
         feats = engine.backbone_forward(self.model, x)
         lin1, lin2 = self.output2emb_proj.layers
         emb = engine.head_forward(feats, lin1.weight, lin1.bias, lin2.weight, lin2.bias)
