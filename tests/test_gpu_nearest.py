@@ -51,3 +51,17 @@ def test_edge_cases():
     assert np.array_equal(got[1].cpu().numpy(), np.sort(d2, axis=1)[:, :3])
     # empty batch
     assert ops.nearest_class(torch.zeros((0, 300)).cuda(), torch.from_numpy(cls).cuda(), k=1).shape == (0, 1)
+
+
+def test_class_overlap_filter_matches_scipy():
+    """filter_overlapping_classes (auxiliary/auxiliary_dataset.py:141-144): the kept-class mask is identical to scipy's."""
+    cdist = pytest.importorskip("scipy.spatial.distance").cdist
+    from zeroshotvideoclassification_b200 import class_overlap_mask
+    rng = np.random.default_rng(5)
+    train, test = _unit(rng, 664), _unit(rng, 101)
+    train[:20] = test[:20] + 0.02 * _unit(rng, 20)        # near-duplicates of test classes
+    train[20:25] = test[20:25]                             # exact overlaps (distance 0)
+    for tau in (0.0, 0.05, 0.5, 0.9):
+        ref = cdist(train, test, "cosine").min(1) > tau
+        got = class_overlap_mask(train, test, tau).cpu().numpy()
+        assert np.array_equal(got, ref), tau

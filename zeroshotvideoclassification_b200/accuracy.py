@@ -32,3 +32,13 @@ def compute_accuracy(predicted_embed, class_embed, true_embed):
     top1 = (y_pred[:, :1] == y).float().mean() * 100
     top5 = (y_pred == y).any(dim=1).float().mean() * 100
     return float(top1), float(top5)
+
+
+def class_overlap_mask(class_embedding, other_class_embedding, class_overlap: float) -> torch.Tensor:
+    """auxiliary/auxiliary_dataset.py:141-144 (filter_overlapping_classes): keep a training class iff its cosine
+    distance to the NEAREST test class exceeds ``class_overlap``:
+    ``cdist(class_embedding, ucf_class_embedding, 'cosine').min(1) > class_overlap``.  Same kernel as the nearest-class
+    search (fp64, scipy's operation order), so the mask is bit-identical to the reference's.  Returns bool [C] (CUDA)."""
+    emb = _as_cuda(class_embedding)
+    _, dist = ops.nearest_class(emb, _as_cuda(other_class_embedding, emb.device), 1, return_dist=True)
+    return dist[:, 0] > class_overlap
