@@ -220,7 +220,11 @@ def run_b200(args):
     zdist.broadcast_module(model)
     criterion = torch.nn.MSELoss().to(dev)
     # main.py:131's torch.optim.Adam; capturable keeps its step counter on the device so the iteration can be graphed
-    optimizer = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=args.graph, fused=True)
+    if args.optimizer == "zsv":
+        from zeroshotvideoclassification_b200.optim import FusedAdam
+        optimizer = FusedAdam(model.parameters(), lr=1e-3)
+    else:
+        optimizer = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=args.graph, fused=True)
     sync = zdist.GradSync(bucket_bytes=int(float(os.environ.get("ZSV_BUCKET_MB", "32")) * (1 << 20))) if world > 1 else None
     zdist.set_grad_sync(sync)
     # parameters whose gradients do not come out of the backbone Function (GradSync covers those): the MLP head of
@@ -455,7 +459,8 @@ def run_b200(args):
                    "parallelism": f"dp{world}" if world > 1 else "single",
                    "l2": "per-step working set (~6 GB of activations) is far larger than the 126 MB L2; no flush needed",
                    "loss_scaling": "none (bf16)", "weights": "random init (resnet.py:226-236)",
-                   "launch": graph_note, "optimizer": "torch.optim.Adam(fused=True) (main.py:131)"},
+                   "launch": graph_note, "optimizer": ("zsv FusedAdam (zsv_adam_step)" if args.optimizer == "zsv"
+                                 else "torch.optim.Adam(fused=True) (main.py:131)")},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "final_loss": final_loss, "host_enqueue_ms_per_step": host_ms_per_step,
     }
@@ -473,6 +478,8 @@ def main():
     ap.add_argument("--batch", type=int, default=22, help="clips per GPU (README.md:45)")
     ap.add_argument("--network", default="r2plus1d_18")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--optimizer", default="torch", choices=["torch", "zsv"],
+                    help="torch.optim.Adam (the reference's, default) or the C-ABI multi-tensor Adam")
     ap.add_argument("--layer-table", action="store_true", help="print a per-layer conv timing table to stderr")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="enqueue every iteration kernel by kernel instead of replaying one CUDA graph")

@@ -239,6 +239,14 @@ int zsv_l2norm_bwd(const float* demb, const float* emb, const float* onorm, floa
 int zsv_mse_fwd_bwd(const float* emb, const float* target, int B, int E, float grad_scale, float* loss, float* demb,
                     void* stream);
 
+/* Multi-tensor Adam with torch.optim.Adam semantics (main.py:131,203; no amsgrad): n parameter tensors in one launch
+ * per 72 tensors.  params / grads / exp_avg / exp_avg_sq / numel are HOST arrays of device pointers and sizes;
+ * `step` is a DEVICE float holding t, the 1-based step count of THIS update (the caller increments it on the
+ * stream beforehand), which keeps the update CUDA-graph capturable.  weight_decay is added to the gradient (L2). */
+int zsv_adam_step(int n, float* const* params, const float* const* grads, float* const* exp_avg,
+                  float* const* exp_avg_sq, const long long* numel, const float* step, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Zero-shot nearest-class search (main.py:183, main.py:321-322: scipy cdist(...,'cosine') then
  * argmin / argsort[:, :k]).  fp32 inputs promoted to fp64 exactly like scipy; ties resolved towards

@@ -236,3 +236,28 @@ def test_clip_transform_matches_oracle_and_feeds_the_model():
         emb_ref, _ = model(x32.cuda())
         emb_gpu, _ = model(ops.clip_transform(frames.cuda(), ij, flip))
     assert float((emb_ref - emb_gpu).abs().max() / emb_ref.abs().max()) < 2e-2
+
+
+def test_fused_adam_matches_torch_adam():
+    """zsv_adam_step == torch.optim.Adam (main.py:131) over several steps, ragged tensor sizes, with and without weight
+    decay; state dicts interchange."""
+    import torch
+    from zeroshotvideoclassification_b200.optim import FusedAdam
+    for wd in (0.0, 1e-2):
+        g = torch.Generator().manual_seed(3)
+        shapes = [(64, 3, 1, 7, 7), (45,), (1,), (300, 512), (7, 13, 3)] + [(17,)] * 80      # > 72 tensors: two launches
+        ref = [torch.nn.Parameter(torch.randn(s, generator=g).cuda()) for s in shapes]
+        mine = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+        o_ref = torch.optim.Adam(ref, lr=1e-3, weight_decay=wd)
+        o_mine = FusedAdam(mine, lr=1e-3, weight_decay=wd)
+        for _ in range(5):
+            for a, b in zip(ref, mine):
+                gr = torch.randn(a.shape, generator=g).cuda()
+                a.grad, b.grad = gr.clone(), gr.clone()
+            o_ref.step()
+            o_mine.step()
+        for a, b in zip(ref, mine):
+            assert torch.allclose(a, b, rtol=2e-6, atol=2e-7)
+        sd = o_mine.state_dict()
+        assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 5.0
+        o_ref.load_state_dict(sd)          # same state layout as torch.optim.Adam

@@ -87,6 +87,7 @@ SIGNATURES = {
     "zsv_head_fwd": (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _F, _P, _P, _P, _P, _P]),
     "zsv_head_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
     "zsv_mse_fwd_bwd": (_I, [_P, _P, _I, _I, _F, _P, _P, _P]),
+    "zsv_adam_step": (_I, [_I, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P]),
     "zsv_nearest_class": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "zsv_maxpool3d_fwd": (_I, [_P, _P, _P] + [_I] * 11 + [_P]),
     "zsv_maxpool3d_bwd": (_I, [_P, _P, _P, _P] + [_I] * 11 + [_P]),

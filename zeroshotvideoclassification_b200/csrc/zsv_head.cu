@@ -7,6 +7,7 @@
 // Nearest class (main.py:183, main.py:321-322): scipy cdist(...,'cosine') + argmin / argsort[:, :k],
 // restated in fp64 with scipy's exact operation order so that indices are bit-identical.
 #include <algorithm>
+#include <string.h>
 #include <mutex>
 
 #include "zsv_internal.h"
@@ -491,5 +492,90 @@ extern "C" int zsv_nearest_class(const float* emb, const float* cls, int N, int 
     else
         nearest_kernel<8><<<ceil_div(N, 8), 128, smem, st>>>(emb, cls, N, C, D, k, idx_out, dist_out);
     ZSV_LAUNCH_CHECK("nearest_kernel");
+    return ZSV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-tensor Adam (torch.optim.Adam semantics, main.py:131,203): one launch updates up to kMaxAdamItems parameter
+// tensors; the step counter lives on the device (read here, incremented by the caller), so the update is CUDA-graph
+// capturable.  HBM-bound: 28 bytes per parameter.
+//   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// ------------------------------------------------------------------------------------------------
+namespace zsv {
+namespace {
+constexpr int kMaxAdamItems = 72;
+struct AdamItem {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    long long start;   // first flat element index
+};
+struct AdamBatch {
+    int32_t n;
+    long long total;
+    float lr, beta1, beta2, eps, weight_decay;
+    const float* step;   // device scalar: t (already incremented)
+    AdamItem it[kMaxAdamItems];
+};
+
+__global__ void __launch_bounds__(256)
+adam_multi_tensor_kernel(const __grid_constant__ AdamBatch B) {
+    const float t = *B.step;
+    const float bc1 = 1.f - powf(B.beta1, t);
+    const float bc2_sqrt = sqrtf(1.f - powf(B.beta2, t));
+    const float step_size = B.lr / bc1;
+    for (long long gidx = blockIdx.x * (long long)blockDim.x + threadIdx.x; gidx < B.total;
+         gidx += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = B.n - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (B.it[mid].start <= gidx) lo = mid;
+            else hi = mid - 1;
+        }
+        const AdamItem& I = B.it[lo];
+        const long long i = gidx - I.start;
+        float p = I.p[i];
+        float g = I.g[i];
+        if (B.weight_decay != 0.f) g = fmaf(B.weight_decay, p, g);
+        float m = I.m[i], v = I.v[i];
+        m = m + (1.f - B.beta1) * (g - m);                    // lerp, like torch
+        v = B.beta2 * v + (1.f - B.beta2) * g * g;
+        const float denom = sqrtf(v) / bc2_sqrt + B.eps;
+        p -= step_size * (m / denom);
+        I.p[i] = p;
+        I.m[i] = m;
+        I.v[i] = v;
+    }
+}
+}  // namespace
+}  // namespace zsv
+
+extern "C" int zsv_adam_step(int n, float* const* params, const float* const* grads, float* const* exp_avg,
+                             float* const* exp_avg_sq, const long long* numel, const float* step, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, void* stream) {
+    if (n < 0 || (n > 0 && (!params || !grads || !exp_avg || !exp_avg_sq || !numel)) || !step)
+        return fail(ZSV_ERR_BAD_ARG, "adam_step: null array");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int base = 0; base < n; base += zsv::kMaxAdamItems) {
+        zsv::AdamBatch B;
+        memset(&B, 0, sizeof(B));
+        B.lr = lr, B.beta1 = beta1, B.beta2 = beta2, B.eps = eps, B.weight_decay = weight_decay, B.step = step;
+        long long total = 0;
+        int m = 0;
+        for (int i = base; i < std::min(n, base + zsv::kMaxAdamItems); ++i) {
+            if (numel[i] <= 0) continue;
+            if (!params[i] || !grads[i] || !exp_avg[i] || !exp_avg_sq[i]) return fail(ZSV_ERR_BAD_ARG, "adam_step: null tensor %d", i);
+            B.it[m].p = params[i], B.it[m].g = grads[i], B.it[m].m = exp_avg[i], B.it[m].v = exp_avg_sq[i];
+            B.it[m].start = total;
+            total += numel[i];
+            ++m;
+        }
+        if (m == 0) continue;
+        B.n = m, B.total = total;
+        const int blocks = (int)std::min<long long>(ceil_div_ll(total, 256 * 4), (long long)sm_count() * 8);
+        zsv::adam_multi_tensor_kernel<<<std::max(1, blocks), 256, 0, st>>>(B);
+        ZSV_LAUNCH_CHECK("adam_multi_tensor_kernel");
+    }
     return ZSV_OK;
 }
