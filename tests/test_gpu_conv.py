@@ -293,12 +293,13 @@ def test_row_linearised_kernel_opt_in(case, monkeypatch):
 @pytest.mark.parametrize("case", [c for c in CASES if c[0] in ("spatial_s2_64_230", "spatial_256_460", "temporal_s2_230_128",
                                                                  "downsample_64_128", "c3d_27tap", "spatial_s2_odd")],
                          ids=lambda c: c[0])
-def test_cta_pair_kernel_opt_in(case, monkeypatch):
-    """igemm_kmajor_kernel<pair> (opt-in with ZSV_2CTA=1: cluster of two CTAs, tcgen05 cta_group::2 MMAs with M = 256,
-    each CTA loading half of the B tile): fprop with statistics and dgrad must match the oracle, including an odd
-    number of M tiles (the peer's last tile is out of range) and several N tiles."""
+@pytest.mark.parametrize("pair", ["1", "0"])
+def test_cta_pair_and_single_cta_kernels(case, pair, monkeypatch):
+    """igemm_kmajor_kernel<pair> (the default: cluster of two CTAs, tcgen05 cta_group::2 MMAs with M = 256, each CTA
+    loading half of the B tile) and the single-CTA kernel (ZSV_2CTA=0): fprop with statistics and dgrad must match the
+    oracle, including an odd number of M tiles (the peer's last tile is out of range) and several N tiles."""
     from zeroshotvideoclassification_b200 import ops
-    monkeypatch.setenv("ZSV_2CTA", "1")
+    monkeypatch.setenv("ZSV_2CTA", pair)
     name, N, T, H, W, cin, cout, k, s, p = case
     x, w = _make(case)
     op = ops.Conv3d(N, T, H, W, cin, cout, k, s, p)
@@ -313,4 +314,41 @@ def test_cta_pair_kernel_opt_in(case, monkeypatch):
     dx_ref, _ = vo.conv3d_grads(x, w, dy, s, p)
     dx = op.dgrad(to_ndhwc(dy), wd)
     torch.cuda.synchronize()
+    assert rel_err(from_ndhwc(dx, cin), dx_ref) < TOL
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[0] in ("spatial_64_64", "spatial_64_144", "temporal_144_64",
+                                                                 "temporal_45_64", "spatial_odd_hw")],
+                         ids=lambda c: c[0])
+def test_halo_cta_pair_kernel(case, monkeypatch):
+    """igemm_halo_kernel<pair> (cluster of two CTAs, M = 256, half of the resident weight rows per CTA; chosen by default
+    where the weight image starves the activation ring, forced here with ZSV_HALO_2CTA=1): fprop with statistics, dgrad
+    and dgrad with the fused BatchNorm backward must match the oracle / the single-CTA kernel, odd M-tile counts
+    included (the peer's last tile is out of range)."""
+    from zeroshotvideoclassification_b200 import ops
+    name, N, T, H, W, cin, cout, k, s, p = case
+    x, w = _make(case)
+    g = torch.Generator().manual_seed(4)
+    ref = vo.conv3d(x, w, None, s, p)
+    dy = bf16_round(torch.randn(ref.shape, generator=g))
+    tab = torch.rand(cpad(cin), 4, generator=g).cuda()
+    monkeypatch.setenv("ZSV_HALO_2CTA", "0")
+    op = ops.Conv3d(N, T, H, W, cin, cout, k, s, p)       # (the statistics row count is fixed at construction)
+    wf, wd = op.pack(w.cuda(), need_dgrad=True)
+    y0, ps0, _ = op.fprop(to_ndhwc(x), wf, stats=True)
+    dx0 = op.dgrad(to_ndhwc(dy), wd)
+    dz0, part0, r0 = op.dgrad_bn_fused(to_ndhwc(dy), wd, None, to_ndhwc(x), tab, True)
+    monkeypatch.setenv("ZSV_HALO_2CTA", "1")
+    op = ops.Conv3d(N, T, H, W, cin, cout, k, s, p)
+    y, ps, pq = op.fprop(to_ndhwc(x), wf, stats=True)
+    dx = op.dgrad(to_ndhwc(dy), wd)
+    dz, part, r1 = op.dgrad_bn_fused(to_ndhwc(dy), wd, None, to_ndhwc(x), tab, True)
+    torch.cuda.synchronize()
+    assert rel_err(from_ndhwc(y, cout), ref) < TOL
+    # (not bit-equal: where the single-CTA plan does not fit, the generic kernel runs and sums K in another order)
+    for a, b in ((y, y0), (dx, dx0), (dz, dz0)):
+        assert rel_err(a.float().cpu(), b.float().cpu()) < 5e-3
+    assert torch.allclose(ps.double().sum(0), ps0.double().sum(0), rtol=1e-3, atol=5e-2)
+    assert torch.allclose(part[:r1, :2].double().sum(0), part0[:r0, :2].double().sum(0), rtol=1e-4, atol=1e-2)   # rows 2-3: finish pass
+    dx_ref, _ = vo.conv3d_grads(x, w, dy, s, p)
     assert rel_err(from_ndhwc(dx, cin), dx_ref) < TOL

@@ -50,5 +50,9 @@ for spec in sys.argv[1:]:
     t_fn = bench(lambda: op.fprop(x, wf, stats=False))
     t_d = bench(lambda: op.dgrad(dy, wd))
     t_w = bench(lambda: op.wgrad(x, dy))
+    t_df = float("nan")
+    if wd is not None and s == (1, 1, 1):
+        tab = torch.rand(ops.cpad(cin), 4, device="cuda")           # (mean, invstd, gamma, beta) rows of bn_finalize
+        t_df = bench(lambda: op.dgrad_bn_fused(dy, wd, None, x, tab, True))
     print(f"{spec:48s} fprop {t_f:8.1f} us {flops / t_f / 1e6:7.1f} TF/s (no stats {t_fn:8.1f} us) | dgrad {t_d:8.1f} us {flops / t_d / 1e6:7.1f} TF/s"
-          f" | wgrad {t_w:8.1f} us {flops / t_w / 1e6:7.1f} TF/s")
+          f" (bn-fused {t_df:8.1f} us) | wgrad {t_w:8.1f} us {flops / t_w / 1e6:7.1f} TF/s")

@@ -101,11 +101,12 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    path = Path(os.environ["ZSV_LIB_PATH"]) if os.environ.get("ZSV_LIB_PATH") else LIB_PATH   # A/B of two builds
+    if not path.exists():
         raise RuntimeError(
-            f"{LIB_PATH} is missing: build it with `python -m zeroshotvideoclassification_b200.build` "
+            f"{path} is missing: build it with `python -m zeroshotvideoclassification_b200.build` "
             "(or __graft_entry__.build()). There is no CPU or PyTorch fallback for this path.")
-    lib = C.CDLL(os.fspath(LIB_PATH))
+    lib = C.CDLL(os.fspath(path))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res

@@ -198,6 +198,8 @@ struct EpiArgs {
     float* st_acc;               // smem [2][ncols] running BatchNorm statistics of this CTA (sum, sum of squares)
     int remote_arrive;           // CTA pair: the TMEM-empty barrier is a shared::cluster address in the leader CTA
     int debug;   // tuning aid (ZSV_DEBUG_EPI bit mask): 1 = skip the TMA store, 2 = skip TMEM read + staging, 4 = skip stats
+    uint32_t bar_full, full_phase;   // "accumulator complete" barrier of this tile: waited for inside epilogue_tile, AFTER
+                                     // the global loads of the tile's first chunks are in flight
 };
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -316,8 +318,21 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMa
                                               long long off, int o0, int o1, int o2, int o3, int m_tile,
                                               bool keep_one_store_in_flight, int q, int half, int row, int lane,
                                               int et, int srow_idx = -1) {
-    (void)q;
     if (srow_idx < 0) srow_idx = row;   // row of the staging tile this thread writes (differs from its TMEM lane in lin mode)
+    // Global operands of the tile (shortcut addend, BatchNorm input of the fused backward) do not depend on the
+    // accumulator: pull this thread's row into L1 before the accumulator wait, so that the loads in emit_chunk hit
+    // (waiting for them was the top stall of this kernel in the ncu source view).  Prefetching into REGISTERS instead
+    // pins 32 registers through the whole epilogue and was measured 20% slower on the epilogue-bound temporal convs.
+    constexpr int kChunkStride = 4 * kEpiWarps;
+    if ((E.bn_y != nullptr || E.addend != nullptr) && valid && !(E.debug & 2)) {
+        for (int c = 0; c < width; c += 64) {
+            if (n_origin + c >= E.ncols) break;
+            if (E.bn_y != nullptr) prefetch_l1(E.bn_y + off + n_origin + c);
+            if (E.addend != nullptr) prefetch_l1(E.addend + off + n_origin + c);
+        }
+    }
+    mbar_wait(E.bar_full, E.full_phase);
+    tc_fence_after();
     // the staging buffer about to be written must have been read by the TMA store that used it last
     if (et == 0) {
         if (keep_one_store_in_flight) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -359,9 +374,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMa
         if (E.bn_y != nullptr) {
 #pragma unroll
             for (int hlf = 0; hlf < 2; ++hlf) {
-                const bool in = valid && (col + 8 * hlf < E.ncols);
+                const bool inr = valid && (col + 8 * hlf < E.ncols);
                 uint4 a = make_uint4(0u, 0u, 0u, 0u);
-                if (in) a = *reinterpret_cast<const uint4*>(E.bn_y + off + col + 8 * hlf);
+                if (inr) a = *reinterpret_cast<const uint4*>(E.bn_y + off + col + 8 * hlf);
                 const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -369,7 +384,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMa
                     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (col + 8 * hlf < E.ncols) t = __ldg(E.bn_tab + col + 8 * hlf + j);
                     if (E.bn_relu && !(fmaf(yv, t.x, t.y) > 0.f)) f[8 * hlf + j] = 0.f;
-                    xh[8 * hlf + j] = in ? fmaf(yv, t.z, t.w) : 0.f;
+                    xh[8 * hlf + j] = inr ? fmaf(yv, t.z, t.w) : 0.f;
                 }
             }
         }
@@ -398,7 +413,6 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMa
     };
     // two TMEM loads in flight per wait: the thread's chunks are 16*kEpiWarps/4 columns apart (the other warps of the
     // quadrant take the chunks in between)
-    constexpr int kChunkStride = 4 * kEpiWarps;
     for (int c = half * 16; c < width && !(E.debug & 2); c += 2 * kChunkStride) {
         uint32_t v0[16], v1[16];
         const bool two = c + kChunkStride < width;
@@ -650,8 +664,7 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
             const long long off = (long long)(n0 + n) * P.o_sN + (long long)(t0 + t) * P.o_sT +
                                   (long long)(h0 + h) * P.o_sH + (long long)(w0 + w) * P.o_sW;
             const uint32_t buf = local & 1;
-            mbar_wait(barTmemFull + 8u * buf, (local >> 1) & 1u);
-            tc_fence_after();
+            E.bar_full = barTmemFull + 8u * buf, E.full_phase = (local >> 1) & 1u;
             const uint32_t sb = (P.nstg == 2 ? (local & 1) : 0) * stagingBytes;
             const uint32_t trow = tmem_base + buf * acc_stride + (static_cast<uint32_t>(q * 32) << 16);
             epilogue_tile(E, &mapOut, smem + stagingOff + sb, base + stagingOff + sb, statbuf, trow,
@@ -726,6 +739,11 @@ struct HaloArgs {
     const float* bias;
 };
 
+// k2 = true: CTA pair (cluster of 2, tcgen05 cta_group::2) on M = 256 tiles, each CTA holding HALF of the resident weight
+// rows -- the shared memory that frees is what buys a deep activation ring for the 9-tap 64<->144 convolutions, whose
+// 162 KB weight image otherwise leaves two ring stages (every load latency exposed).  Barrier protocol as in
+// igemm_kmajor_kernel<true>.
+template <bool k2>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAtail,
                   const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBtail,
@@ -738,6 +756,8 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int stages = P.stages;
+    const uint32_t rank = k2 ? cluster_ctarank() : 0u;
+    const int b_rows = k2 ? (P.bn_tile >> 1) : P.bn_tile;   // weight rows resident in THIS CTA
     const uint32_t ringOff = P.b_total_bytes;
     const uint32_t ringBytes = stages * P.a_stage_bytes;
     const int out_panels = (P.bn_tile + 63) >> 6;
@@ -759,14 +779,18 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(barTmemFull + 8u * i, 1);
-            mbar_init(barTmemEmpty + 8u * i, kEpiWarps);
+            mbar_init(barTmemEmpty + 8u * i, k2 ? 2 * kEpiWarps : kEpiWarps);
         }
         mbar_init(barB, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), P.tmem_cols);
+    if (warp == 1) {
+        if (k2) tmem_alloc2(smem_u32(tmem_slot), P.tmem_cols);
+        else tmem_alloc(smem_u32(tmem_slot), P.tmem_cols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (k2) cluster_sync_all();
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t acc_stride = static_cast<uint32_t>(P.tmem_cols) >> 1;
@@ -778,9 +802,11 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const uint32_t tail_row_bytes = static_cast<uint32_t>(P.tail_box) * 2u;
     const uint32_t per_tap_bytes = nmain * P.b_main_bytes + (nmain < P.nchunks ? P.b_tail_bytes : 0u);
     // this CTA's N tile is fixed (its weight tile is resident); M tiles are strided over the CTAs that share it
-    const int n_tile = blockIdx.x % P.n_tiles;
-    const int m_first = blockIdx.x / P.n_tiles;
-    const int m_stride = gridDim.x / P.n_tiles;
+    // (a CTA pair takes M tiles 2i and 2i+1 and always the whole N range)
+    const int n_tile = k2 ? 0 : blockIdx.x % P.n_tiles;
+    const int m_first = k2 ? (blockIdx.x >> 1) : blockIdx.x / P.n_tiles;
+    const int m_stride = k2 ? (gridDim.x >> 1) : gridDim.x / P.n_tiles;
+    const int m_count = k2 ? ((P.m_tiles + 1) >> 1) : P.m_tiles;
     const int n_origin = n_tile * P.n_step;
 
     if (warp == 0) {
@@ -788,17 +814,22 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         if (leader) {
             // resident weights: [tap][chunk] tiles
             uint32_t btx = 0;
-            for (int c = 0; c < P.nchunks; ++c) btx += static_cast<uint32_t>(P.bn_tile) * (c < nmain ? 128u : tail_row_bytes);
-            mbar_expect_tx(barB, btx * P.ntaps);
+            for (int c = 0; c < P.nchunks; ++c) btx += static_cast<uint32_t>(b_rows) * (c < nmain ? 128u : tail_row_bytes);
+            const uint32_t barBLeader = k2 ? mapa_shared(barB, 0) : barB;   // the pair's MMA issuer waits for both halves
+            if (rank == 0) mbar_expect_tx(barB, btx * P.ntaps * (k2 ? 2u : 1u));
             for (int tp = 0; tp < P.ntaps; ++tp)
                 for (int c = 0; c < P.nchunks; ++c) {
                     const uint32_t dst = base + tp * per_tap_bytes + (c < nmain ? c * P.b_main_bytes : nmain * P.b_main_bytes);
-                    tma_load_3d(dst, c < nmain ? &mapB : &mapBtail, barB, c << 6, n_origin, tp);
+                    if (k2) tma2_load_3d(dst, c < nmain ? &mapB : &mapBtail, barBLeader, c << 6,
+                                         n_origin + static_cast<int>(rank) * b_rows, tp);
+                    else tma_load_3d(dst, c < nmain ? &mapB : &mapBtail, barB, c << 6, n_origin, tp);
                 }
         }
         __syncwarp();
+        const uint32_t fullLeader = k2 ? mapa_shared(barFull, 0) : barFull;
         uint32_t stage = 0, phase = 0;
-        for (int mt = m_first; mt < P.m_tiles; mt += m_stride) {
+        for (int it = m_first; it < m_count; it += m_stride) {
+            const int mt = k2 ? 2 * it + static_cast<int>(rank) : it;   // an M tile past the end reads zeros, stores nothing
             int m, m3;
             const int o0 = fdivmod(mt, P.fd_tl0, m) * P.b[0];
             const int o1 = fdivmod(m, P.fd_tl1, m) * P.b[1];
@@ -811,15 +842,21 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 for (int cp = 0; cp < P.ncopies; ++cp) {
                     mbar_wait(barEmpty + 8u * stage, phase ^ 1u);
                     if (leader) {
-                        const uint32_t full = barFull + 8u * stage;
-                        mbar_expect_tx(full, tx);
-                        tma_load_5d(base + ringOff + stage * P.a_stage_bytes, mp, full, c << 6, o0 + P.copy_off[cp], o1, o2,
-                                    o3 + P.shift_org);
+                        if (k2) {
+                            if (rank == 0) mbar_expect_tx(barFull + 8u * stage, 2u * tx);
+                            tma2_load_5d(base + ringOff + stage * P.a_stage_bytes, mp, fullLeader + 8u * stage, c << 6,
+                                         o0 + P.copy_off[cp], o1, o2, o3 + P.shift_org);
+                        } else {
+                            const uint32_t full = barFull + 8u * stage;
+                            mbar_expect_tx(full, tx);
+                            tma_load_5d(base + ringOff + stage * P.a_stage_bytes, mp, full, c << 6, o0 + P.copy_off[cp], o1,
+                                        o2, o3 + P.shift_org);
+                        }
                         // Pull the same box of a tile `pf_dist` iterations ahead into L2: a TMA load keeps one request
                         // per 128-byte row outstanding until its data returns, which caps DRAM-sourced loads near
                         // 3 TB/s chip-wide; L2 hits return ~6x sooner.
                         if (cp == 0 && P.pf_dist > 0) {
-                            const int mp_ = mt + P.pf_dist * m_stride;
+                            const int mp_ = mt + P.pf_dist * m_stride * (k2 ? 2 : 1);
                             if (mp_ < P.m_tiles) {
                                 int q1, q2, q3;
                                 const int p0 = fdivmod(mp_, P.fd_tl0, q1) * P.b[0];
@@ -837,9 +874,9 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 && rank == 0) {
         const uint32_t leader = elect_one();
-        const uint32_t idesc = umma_idesc_bf16(128, P.bn_tile, 0, 0);
+        const uint32_t idesc = umma_idesc_bf16(k2 ? 256 : 128, P.bn_tile, 0, 0);
         const uint32_t tail_layout = P.tail_box == 16 ? 6u : (P.tail_box == 32 ? 4u : 2u);
         const uint32_t hi_main = umma_desc_hi(1024, 2);
         const uint32_t hi_tail = umma_desc_hi(tail_row_bytes * 8u, tail_layout);
@@ -849,7 +886,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         tc_fence_after();
         uint32_t stage = 0, phase = 0;
         int local = 0;
-        for (int mt = m_first; mt < P.m_tiles; mt += m_stride, ++local) {
+        for (int it = m_first; it < m_count; it += m_stride, ++local) {
             const uint32_t buf = local & 1;
             mbar_wait(barTmemEmpty + 8u * buf, ((local >> 1) & 1u) ^ 1u);
             tc_fence_after();
@@ -866,7 +903,23 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                     mbar_wait(barFull + 8u * stage, phase);
                     tc_fence_after();
                     if (P.debug & 8) {   // tuning aid: consume the stage without issuing MMAs
-                        if (leader) mbar_arrive(barEmpty + 8u * stage);
+                        if (leader) {
+                            mbar_arrive(barEmpty + 8u * stage);
+                            if (k2) mbar_arrive_cluster(mapa_shared(barEmpty + 8u * stage, 1));
+                        }
+                    } else if (leader && k2) {
+                        uint32_t a_lo = umma_desc_lo(base + ringOff + stage * P.a_stage_bytes);
+                        uint32_t b_lo = b_chunk_lo + static_cast<uint32_t>(P.tap0 + cp * P.tap_dcp) * tap_bytes16;
+                        const uint32_t b_step = static_cast<uint32_t>(P.tap_dsh) * tap_bytes16;
+                        for (int sh = 0; sh < P.S; ++sh) {
+                            umma2_bf16_lohi(tacc, a_lo, dhi, b_lo, dhi, idesc, acc);
+                            acc = 1;
+                            for (int k = 1; k < ksteps; ++k)
+                                umma2_bf16_lohi(tacc, a_lo + 2u * k, dhi, b_lo + 2u * k, dhi, idesc, 1u);
+                            a_lo += shift16;
+                            b_lo += b_step;
+                        }
+                        umma2_commit_mc(barEmpty + 8u * stage, 3);
                     } else if (leader) {
                         uint32_t a_lo = umma_desc_lo(base + ringOff + stage * P.a_stage_bytes);
                         uint32_t b_lo = b_chunk_lo + static_cast<uint32_t>(P.tap0 + cp * P.tap_dcp) * tap_bytes16;
@@ -898,12 +951,18 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 }
             }
             if (leader) {
-                if (P.debug & 8) mbar_arrive(barTmemFull + 8u * buf);
-                else umma_commit(barTmemFull + 8u * buf);
+                if (P.debug & 8) {
+                    mbar_arrive(barTmemFull + 8u * buf);
+                    if (k2) mbar_arrive_cluster(mapa_shared(barTmemFull + 8u * buf, 1));
+                } else if (k2) {
+                    umma2_commit_mc(barTmemFull + 8u * buf, 3);
+                } else {
+                    umma_commit(barTmemFull + 8u * buf);
+                }
             }
             __syncwarp();
         }
-    } else {
+    } else if (warp >= 2) {
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         const int row = q * 32 + lane;
@@ -919,7 +978,8 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         E.addend = P.addend, E.bias = P.bias, E.part_sum = P.part_sum, E.part_sq = P.part_sq;
         E.ncols = P.ncols, E.nbias = P.nbias, E.relu = P.relu, E.part_pitch = P.part_pitch;
         E.debug = P.debug;
-        E.remote_arrive = 0;
+        E.remote_arrive = k2 ? 1 : 0;
+        const uint32_t tmemEmptyBar = k2 ? mapa_shared(barTmemEmpty, 0) : barTmemEmpty;
         float* statbuf = reinterpret_cast<float*>(smem + statOff);
         E.bn_y = P.bn_y, E.bn_tab = P.bn_tab, E.bn_relu = P.bn_relu;
         E.bn_acc = statbuf;
@@ -930,7 +990,8 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         // columns this tile owns: a non-last N tile only owns n_step of its bn_tile computed columns
         const int width = (n_tile + 1 < P.n_tiles) ? P.n_step : P.bn_tile;
         int local = 0;
-        for (int mt = m_first; mt < P.m_tiles; mt += m_stride, ++local) {
+        for (int it = m_first; it < m_count; it += m_stride, ++local) {
+            const int mt = k2 ? 2 * it + static_cast<int>(rank) : it;
             int m, m3;
             const int o0 = fdivmod(mt, P.fd_tl0, m) * P.b[0];
             const int o1 = fdivmod(m, P.fd_tl1, m) * P.b[1];
@@ -941,12 +1002,11 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             const long long off = (long long)(o0 + i0) * P.os[0] + (long long)(o1 + i1) * P.os[1] +
                                   (long long)(o2 + i2) * P.os[2] + (long long)(o3 + i3) * P.os[3];
             const uint32_t buf = local & 1;
-            mbar_wait(barTmemFull + 8u * buf, (local >> 1) & 1u);
-            tc_fence_after();
+            E.bar_full = barTmemFull + 8u * buf, E.full_phase = (local >> 1) & 1u;
             const uint32_t sb = (P.nstg == 2 ? (local & 1) : 0) * stagingBytes;
             const uint32_t trow = tmem_base + buf * acc_stride + (static_cast<uint32_t>(q * 32) << 16);
             epilogue_tile(E, &mapOut, smem + stagingOff + sb, base + stagingOff + sb, statbuf, trow,
-                          barTmemEmpty + 8u * buf, width, n_origin, valid, off, o0, o1, o2, o3, mt, P.nstg == 2, q, half,
+                          tmemEmptyBar + 8u * buf, width, n_origin, valid, off, o0, o1, o2, o3, mt, P.nstg == 2, q, half,
                           row, lane, et);
         }
         if (et == 0) tma_store_wait_all();
@@ -964,10 +1024,12 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             }
         }
     }
-    __syncthreads();
+    if (k2) cluster_sync_all();     // neither CTA leaves (or frees TMEM) while the pair still reads its shared memory
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, P.tmem_cols);
+        if (k2) tmem_dealloc2(tmem_base, P.tmem_cols);
+        else tmem_dealloc(tmem_base, P.tmem_cols);
     }
 }
 
@@ -1196,8 +1258,7 @@ igemm_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const long long off = (long long)(w0 + wl) * P.os_w + (long long)(h0 + hl) * P.os_h + (long long)t_ * P.os_t +
                                   (long long)n_ * P.os_n;
             const uint32_t buf = local & 1;
-            mbar_wait(barTmemFull + 8u * buf, (local >> 1) & 1u);
-            tc_fence_after();
+            E.bar_full = barTmemFull + 8u * buf, E.full_phase = (local >> 1) & 1u;
             const uint32_t trow = tmem_base + buf * acc_stride + (static_cast<uint32_t>(q * 32) << 16);
             epilogue_tile(E, &mapOut, smem + stagingOff, base + stagingOff, statbuf, trow, barTmemEmpty + 8u * buf, P.bn_tile,
                           0, valid, off, w0, h0, t_, n_, tile, false, q, half, row, lane, et, srow);
@@ -2007,10 +2068,12 @@ int igemm_smem_bytes(int bn_tile, int stages, int nstg, int scratch = 0) {
            16 * stages + 48 + 64;
 }
 
-// CTA pairs (cta_group::2) for the generic kernel: opt-in while it is being measured (ZSV_2CTA=1)
+// CTA pairs (cta_group::2) for the generic kernel
 bool igemm_use_pair(int bn_tile, long long m_tiles) {
+    // on by default since the cluster-scope "accumulator drained" arrive is relaxed (profiles/r01_halo_pair_ab.txt:
+    // +1.5% on the whole training step); ZSV_2CTA=0 runs the single-CTA kernel
     const char* e = getenv("ZSV_2CTA");
-    return e && atoi(e) == 1 && (bn_tile % 16) == 0 && m_tiles >= 2;
+    return !(e && atoi(e) == 0) && (bn_tile % 16) == 0 && m_tiles >= 2;
 }
 // grid of the generic kernel (one BatchNorm partial row per CTA)
 int igemm_grid(int bn_tile, long long m_tiles, int n_tiles) {
@@ -2100,6 +2163,7 @@ int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtenso
 struct HaloPlan {
     bool ok;
     bool spatial;       // shift dim = H (taps along W are copies) ; otherwise shift dim = T
+    bool pair;          // CTA-pair variant: M = 256 tiles, half of the weight rows resident per CTA
     int b[4], tl[4], O[4];
     int S, ncopies, stages, nstg, bn_tile, n_step, n_tiles, nchunks, tail_box;
     long long m_tiles;
@@ -2113,9 +2177,10 @@ inline uint32_t align1k(uint32_t v) { return (v + 1023u) & ~1023u; }
 // act extents (W,H,T,N) of the GEMM-M space (stride-1 conv: output extents == input extents), reduction channels
 // kdim, output columns `cols`, filter (kt,kh,kw).  Only spatial 1xkhxkw (kh==3) and temporal ktx1x1 (kt==3).
 // scratch_mode: 0 = none, 1 = BatchNorm statistics (fprop), 2 = fused BatchNorm backward (dgrad)
-HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int kh, int kw, int scratch_mode = 0) {
+HaloPlan plan_halo_impl(int W, int H, int T, int N, int kdim, int cols, int kt, int kh, int kw, int scratch_mode, bool pair) {
     HaloPlan p;
     memset(&p, 0, sizeof(p));
+    p.pair = pair;
     if (getenv("ZSV_DEBUG_NO_HALO")) return p;
     if (kt == 1 && kh == 3 && kw >= 1 && kw <= kMaxCopies) {
         p.spatial = true;
@@ -2172,7 +2237,8 @@ HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int k
     const int ntaps = kt * kh * kw;
     const int cols16 = (cols + 15) & ~15;
     // N tiling: origins step by multiples of 64 (output panels), the last tile takes the remainder
-    const int max_nt = getenv("ZSV_DEBUG_HALO_NSPLIT") ? 4 : 1;
+    const int max_nt = (getenv("ZSV_DEBUG_HALO_NSPLIT") && !pair) ? 4 : 1;
+    if (pair && p.m_tiles < 2) return p;
     for (int nt = 1; nt <= max_nt; ++nt) {
         int n_step, bn;
         if (nt == 1) {
@@ -2184,8 +2250,9 @@ HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int k
             if (bn < n_step) bn = n_step;
         }
         if (bn > 256) continue;
-        p.b_main_bytes = align1k((uint32_t)bn * 128u);
-        p.b_tail_bytes = align1k((uint32_t)bn * (uint32_t)p.tail_box * 2u);
+        const uint32_t b_rows = pair ? (uint32_t)bn / 2 : (uint32_t)bn;   // bn is a multiple of 16: whole swizzle atoms
+        p.b_main_bytes = align1k(b_rows * 128u);
+        p.b_tail_bytes = align1k(b_rows * (uint32_t)p.tail_box * 2u);
         p.b_total_bytes = (uint32_t)ntaps * (nmain * p.b_main_bytes + (nmain < p.nchunks ? p.b_tail_bytes : 0u));
         const int staging1 = ((bn + 63) / 64) * (int)kPanelBytes;
         int nstg = 2, stages = 0, fixed = 0;
@@ -2214,8 +2281,31 @@ HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int k
     return p;
 }
 
+// The pair variant is chosen where the resident weight image starves the activation ring (or does not fit at all):
+// at most 2 stages alone, and at least 4 with the image split over the pair.  ZSV_HALO_2CTA=0 / 1 forces never / whenever
+// it plans.
+HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int kh, int kw, int scratch_mode = 0) {
+    const HaloPlan one = plan_halo_impl(W, H, T, N, kdim, cols, kt, kh, kw, scratch_mode, false);
+    const char* e = getenv("ZSV_HALO_2CTA");
+    const int mode = e ? atoi(e) : -1;
+    if (mode == 0) return one;
+    if (mode < 0 && one.ok && one.stages > 2) return one;
+    const HaloPlan two = plan_halo_impl(W, H, T, N, kdim, cols, kt, kh, kw, scratch_mode, true);
+    if (getenv("ZSV_DEBUG_PLAN"))
+        fprintf(stderr, "[zsv] halo plan k=%d cols=%d taps=%dx%dx%d: single ok=%d stages=%d nstg=%d box=%d,%d,%d,%d | pair ok=%d stages=%d nstg=%d\n",
+                kdim, cols, kt, kh, kw, (int)one.ok, one.stages, one.nstg, one.b[0], one.b[1], one.b[2], one.b[3], (int)two.ok,
+                two.stages, two.nstg);
+    if (!two.ok) return one;
+    if (mode == 1) return two;
+    // measured (profiles/r01_halo_pair_ab.txt): the pair pays off where it reaches a 4-deep ring and the single-CTA
+    // plan has at most two stages or does not exist (the generic kernel would run); epilogue-bound temporal
+    // convolutions with a 3-stage single-CTA plan are faster as they are
+    return two.stages >= 4 ? two : one;
+}
+
 // grid of the halo kernel: a multiple of n_tiles so that every CTA keeps one N tile
 int halo_grid(const HaloPlan& p) {
+    if (p.pair) return 2 * (int)std::min<long long>((p.m_tiles + 1) / 2, sm_count() / 2);
     const long long want = p.m_tiles * p.n_tiles;
     int grid = (int)std::min<long long>(want, (long long)(sm_count() / p.n_tiles) * p.n_tiles);
     if (grid < p.n_tiles) grid = p.n_tiles;
@@ -2283,7 +2373,7 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
     {
         uint64_t dims[3] = {(uint64_t)actC, (uint64_t)wRows, (uint64_t)ntaps};
         uint64_t str[2] = {(uint64_t)wKpitch * 2, (uint64_t)wKpitch * 2 * wRows};
-        uint32_t box[3] = {64, (uint32_t)p.bn_tile, 1};
+        uint32_t box[3] = {64, (uint32_t)(p.pair ? p.bn_tile / 2 : p.bn_tile), 1};
         rc = make_map(&mB, wimg, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
         box[0] = (uint32_t)p.tail_box;
@@ -2296,7 +2386,9 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(igemm_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_err = cudaFuncSetAttribute(igemm_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(igemm_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (attr_err != cudaSuccess)
         return fail(ZSV_ERR_CUDA, "cudaFuncSetAttribute(halo igemm) failed: %s", cudaGetErrorString(attr_err));
@@ -2315,7 +2407,19 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
         a.bn_partial = fuse->partial + (size_t)fuse->rows_used * 4 * a.ncols;
         fuse->rows_used += grid;
     }
-    igemm_halo_kernel<<<grid, kIgemmThreads, p.smem, st>>>(mA, mAt, mB, mBt, mO, a);
+    if (p.pair) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kIgemmThreads), cfg.dynamicSmemBytes = p.smem, cfg.stream = st;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr, cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_halo_kernel<true>, mA, mAt, mB, mBt, mO, a);
+        if (e != cudaSuccess) return fail(ZSV_ERR_CUDA, "launch of igemm_halo_kernel<pair> failed: %s", cudaGetErrorString(e));
+    } else {
+        igemm_halo_kernel<false><<<grid, kIgemmThreads, p.smem, st>>>(mA, mAt, mB, mBt, mO, a);
+    }
     ZSV_LAUNCH_CHECK("igemm_halo_kernel");
     return ZSV_OK;
 }

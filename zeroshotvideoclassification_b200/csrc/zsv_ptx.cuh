@@ -195,8 +195,14 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
+// Arrive on a barrier of a CTA of the cluster.  RELAXED: the callers signal "TMEM accumulator drained" (ordered by
+// tcgen05.fence::before_thread_sync / after_thread_sync, not by this arrive) -- the .release.cluster form compiles to
+// ERRBAR + MEMBAR.ALL.GPU and was 17% of the pair kernel's stall samples.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t slot_smem, uint32_t ncols) {  // whole warp, in both CTAs
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols)
