@@ -158,7 +158,7 @@ def test_fprop_full_size_layer1_linearity():
 
 
 def test_batched_weight_pack_matches_per_conv_pack():
-    """zsv_conv3d_pack_weights (one launch for a list of convolutions) writes the same bf16 images as
+    """zsv_conv3d_pack_weights (one tiled launch for a list of convolutions) writes the same bf16 images as
     zsv_conv3d_pack_weight per convolution, including the W-folded first-layer image and a conv without dgrad image."""
     import torch
     from zeroshotvideoclassification_b200 import _lib, ops
@@ -167,7 +167,11 @@ def test_batched_weight_pack_matches_per_conv_pack():
              (45, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), _lib.X_NDHWC, True),
              (64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1), _lib.X_NDHWC, True),
              (64, 230, (1, 3, 3), (1, 2, 2), (0, 1, 1), _lib.X_NDHWC, False),
-             (64, 128, (1, 1, 1), (2, 2, 2), (0, 0, 0), _lib.X_NDHWC, True)]
+             (64, 128, (1, 1, 1), (2, 2, 2), (0, 0, 0), _lib.X_NDHWC, True),
+             (128, 230, (1, 3, 3), (1, 1, 1), (0, 1, 1), _lib.X_NDHWC, True),      # Cout pad lanes in the dgrad image
+             (230, 128, (3, 1, 1), (1, 1, 1), (1, 0, 0), _lib.X_NDHWC, True),      # Cin pad lanes, several ci chunks
+             (64, 72, (3, 3, 3), (1, 1, 1), (1, 1, 1), _lib.X_NDHWC, True),        # 27 taps (C3D): 32-channel chunks
+             (9, 19, (1, 3, 3), (1, 1, 1), (0, 1, 1), _lib.X_NDHWC, True)]         # everything ragged
     convs, ws, nd = [], [], []
     for cin, cout, k, s, p, layout, need in geoms:
         convs.append(ops.Conv3d(2, 8, 32, 32, cin, cout, k, s, p, layout))
@@ -176,7 +180,7 @@ def test_batched_weight_pack_matches_per_conv_pack():
     plan = ops.PackPlan(convs, nd)
     n0 = _lib.launch_count()
     wfs, wds = plan.pack(ws)
-    assert _lib.launch_count() - n0 == 1
+    assert _lib.launch_count() - n0 == 2       # the tiled kernel + the element-wise one for the W-folded image
     for c, w, need, wf, wd in zip(convs, ws, nd, wfs, wds):
         wf1, wd1 = c.pack(w, need_dgrad=need)
         assert torch.equal(wf.view(torch.int16), wf1.view(torch.int16))
