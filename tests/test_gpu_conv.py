@@ -353,6 +353,39 @@ def test_halo_cta_pair_kernel(case, monkeypatch):
     for a, b in ((y, y0), (dx, dx0), (dz, dz0)):
         assert rel_err(a.float().cpu(), b.float().cpu()) < 5e-3
     assert torch.allclose(ps.double().sum(0), ps0.double().sum(0), rtol=1e-3, atol=5e-2)
-    assert torch.allclose(part[:r1, :2].double().sum(0), part0[:r0, :2].double().sum(0), rtol=1e-4, atol=1e-2)   # rows 2-3: finish pass
+    assert torch.allclose(part[:r1, :2].double().sum(0), part0[:r0, :2].double().sum(0), rtol=1e-3, atol=5e-2)   # rows 2-3: finish pass
     dx_ref, _ = vo.conv3d_grads(x, w, dy, s, p)
     assert rel_err(from_ndhwc(dx, cin), dx_ref) < TOL
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[0] in ("spatial_64_64", "spatial_64_144", "c3d_27tap")] +
+                         [("spatial_w56_ragged_h", 1, 3, 13, 56, 72, 40, (1, 3, 3), (1, 1, 1), (0, 1, 1))],
+                         ids=lambda c: c[0])
+def test_halo_w_taps_by_descriptor_offset(case, monkeypatch):
+    """Halo kernel with the W taps served from ONE widened box (descriptor start offsets of one row, 8-row groups
+    (8 + kw - 1) rows apart) against the same kernel with kw W-shifted copies (ZSV_HALO_WSHIFT=0): same MMAs in the
+    same order, so fprop / dgrad / fused-BN dgrad are bit-identical; and both match the oracle."""
+    from zeroshotvideoclassification_b200 import ops
+    name, N, T, H, W, cin, cout, k, s, p = case
+    x, w = _make(case)
+    g = torch.Generator().manual_seed(4)
+    ref = vo.conv3d(x, w, None, s, p)
+    dy = bf16_round(torch.randn(ref.shape, generator=g))
+    tab = torch.rand(cpad(cin), 4, generator=g).cuda()
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("ZSV_HALO_WSHIFT", mode)
+        op = ops.Conv3d(N, T, H, W, cin, cout, k, s, p)
+        wf, wd = op.pack(w.cuda(), need_dgrad=True)
+        y, ps, pq = op.fprop(to_ndhwc(x), wf, stats=True)
+        dx = op.dgrad(to_ndhwc(dy), wd)
+        dz, part, r = op.dgrad_bn_fused(to_ndhwc(dy), wd, None, to_ndhwc(x), tab, True)
+        torch.cuda.synchronize()
+        outs[mode] = (y, dx, dz, ps.double().sum(0), part[:r, :2].double().sum(0))
+    assert rel_err(from_ndhwc(outs["1"][0], cout), ref) < TOL
+    dx_ref, _ = vo.conv3d_grads(x, w, dy, s, p)
+    assert rel_err(from_ndhwc(outs["1"][1], cin), dx_ref) < TOL
+    for a, b in zip(outs["0"][:3], outs["1"][:3]):
+        assert torch.equal(a, b)
+    assert torch.allclose(outs["0"][3], outs["1"][3], rtol=1e-6, atol=1e-4)
+    assert torch.allclose(outs["0"][4], outs["1"][4], rtol=1e-5, atol=1e-3)

@@ -729,6 +729,9 @@ struct HaloArgs {
     int32_t pf_dist;     // L2 prefetch distance in tiles (0 = off)
     int32_t unaligned_mode;  // experiment: tap shifts that are not whole swizzle atoms (1: plain address, 2: + base offset)
     int32_t scratch_bytes;   // epilogue scratch in shared memory (BN-backward fusion sums), multiple of 1 KB
+    int32_t wshift;          // 1: ONE box per chunk, widened by kw-1 along W; the W taps are descriptor start offsets
+    int32_t w_ext;           // box extent along W in that mode (b[0] + kw - 1)
+    int32_t min_off;         // smallest copy_off: W origin of the widened box relative to the tile
     int32_t bn_relu;
     const __nv_bfloat16* bn_y;
     const float4* bn_tab;
@@ -797,7 +800,10 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 
     const int inner_rows = P.b[0] * P.b[1] * P.b[2];
     const int rows = inner_rows * P.b[3];
-    const int halo_rows = inner_rows * (P.b[3] + P.S - 1);
+    // rows of one staged box: with wshift every W run of b[0] positions carries its kw-1 halo columns
+    const int ld_inner_rows = P.wshift ? P.w_ext * P.b[1] * P.b[2] : inner_rows;
+    const int halo_rows = ld_inner_rows * (P.b[3] + P.S - 1);
+    const int nload = P.wshift ? 1 : P.ncopies;   // TMA loads (ring stages) per channel chunk
     const int nmain = (P.tail_box == 64) ? P.nchunks : P.nchunks - 1;   // chunks that use the 128-byte-row maps
     const uint32_t tail_row_bytes = static_cast<uint32_t>(P.tail_box) * 2u;
     const uint32_t per_tap_bytes = nmain * P.b_main_bytes + (nmain < P.nchunks ? P.b_tail_bytes : 0u);
@@ -839,18 +845,19 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 const bool main_chunk = c < nmain;
                 const uint32_t tx = static_cast<uint32_t>(halo_rows) * (main_chunk ? 128u : tail_row_bytes);
                 const CUtensorMap* mp = main_chunk ? &mapA : &mapAtail;
-                for (int cp = 0; cp < P.ncopies; ++cp) {
+                for (int cp = 0; cp < nload; ++cp) {
+                    const int w_org = o0 + (P.wshift ? P.min_off : P.copy_off[cp]);
                     mbar_wait(barEmpty + 8u * stage, phase ^ 1u);
                     if (leader) {
                         if (k2) {
                             if (rank == 0) mbar_expect_tx(barFull + 8u * stage, 2u * tx);
                             tma2_load_5d(base + ringOff + stage * P.a_stage_bytes, mp, fullLeader + 8u * stage, c << 6,
-                                         o0 + P.copy_off[cp], o1, o2, o3 + P.shift_org);
+                                         w_org, o1, o2, o3 + P.shift_org);
                         } else {
                             const uint32_t full = barFull + 8u * stage;
                             mbar_expect_tx(full, tx);
-                            tma_load_5d(base + ringOff + stage * P.a_stage_bytes, mp, full, c << 6, o0 + P.copy_off[cp], o1,
-                                        o2, o3 + P.shift_org);
+                            tma_load_5d(base + ringOff + stage * P.a_stage_bytes, mp, full, c << 6, w_org, o1, o2,
+                                        o3 + P.shift_org);
                         }
                         // Pull the same box of a tile `pf_dist` iterations ahead into L2: a TMA load keeps one request
                         // per 128-byte row outstanding until its data returns, which caps DRAM-sourced loads near
@@ -862,7 +869,8 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                                 const int p0 = fdivmod(mp_, P.fd_tl0, q1) * P.b[0];
                                 const int p1 = fdivmod(q1, P.fd_tl1, q2) * P.b[1];
                                 const int p2 = fdivmod(q2, P.fd_tl2, q3) * P.b[2];
-                                tma_prefetch_5d(mp, c << 6, p0 + P.copy_off[0], p1, p2, q3 * P.b[3] + P.shift_org);
+                                tma_prefetch_5d(mp, c << 6, p0 + (P.wshift ? P.min_off : P.copy_off[0]), p1, p2,
+                                                q3 * P.b[3] + P.shift_org);
                             }
                         }
                     }
@@ -880,6 +888,9 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const uint32_t tail_layout = P.tail_box == 16 ? 6u : (P.tail_box == 32 ? 4u : 2u);
         const uint32_t hi_main = umma_desc_hi(1024, 2);
         const uint32_t hi_tail = umma_desc_hi(tail_row_bytes * 8u, tail_layout);
+        // wshift: consecutive 8-row groups of the A operand (one W run each) are w_ext rows apart in the staged box
+        const uint32_t hi_main_a = P.wshift ? umma_desc_hi(static_cast<uint32_t>(P.w_ext) * 128u, 2) : hi_main;
+        const uint32_t hi_tail_a = P.wshift ? umma_desc_hi(static_cast<uint32_t>(P.w_ext) * tail_row_bytes, tail_layout) : hi_tail;
         const int tail_steps = ((P.kdim - ((P.nchunks - 1) << 6)) + 15) >> 4;
         const uint32_t tap_bytes16 = per_tap_bytes >> 4;   // descriptor start addresses count 16-byte units
         mbar_wait(barB, 0);
@@ -896,10 +907,14 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 const bool main_chunk = c < nmain;
                 const uint32_t row_bytes = main_chunk ? 128u : tail_row_bytes;
                 const uint32_t dhi = main_chunk ? hi_main : hi_tail;
+                const uint32_t dhi_a = main_chunk ? hi_main_a : hi_tail_a;
                 const int ksteps = (c + 1 < P.nchunks) ? 4 : tail_steps;
-                const uint32_t shift16 = (static_cast<uint32_t>(inner_rows) * row_bytes) >> 4;
+                const uint32_t shift16 = (static_cast<uint32_t>(ld_inner_rows) * row_bytes) >> 4;
                 const uint32_t b_chunk_lo = umma_desc_lo(base + (main_chunk ? c * P.b_main_bytes : nmain * P.b_main_bytes));
-                for (int cp = 0; cp < P.ncopies; ++cp) {
+                for (int ld = 0; ld < nload; ++ld) {
+                    // W taps served by this stage: all of them (wshift: start offsets into one widened box) or one copy
+                    const int cp_lo = P.wshift ? 0 : ld;
+                    const int cp_hi = P.wshift ? P.ncopies : ld + 1;
                     mbar_wait(barFull + 8u * stage, phase);
                     tc_fence_after();
                     if (P.debug & 8) {   // tuning aid: consume the stage without issuing MMAs
@@ -908,38 +923,44 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                             if (k2) mbar_arrive_cluster(mapa_shared(barEmpty + 8u * stage, 1));
                         }
                     } else if (leader && k2) {
-                        uint32_t a_lo = umma_desc_lo(base + ringOff + stage * P.a_stage_bytes);
-                        uint32_t b_lo = b_chunk_lo + static_cast<uint32_t>(P.tap0 + cp * P.tap_dcp) * tap_bytes16;
                         const uint32_t b_step = static_cast<uint32_t>(P.tap_dsh) * tap_bytes16;
-                        for (int sh = 0; sh < P.S; ++sh) {
-                            umma2_bf16_lohi(tacc, a_lo, dhi, b_lo, dhi, idesc, acc);
-                            acc = 1;
-                            for (int k = 1; k < ksteps; ++k)
-                                umma2_bf16_lohi(tacc, a_lo + 2u * k, dhi, b_lo + 2u * k, dhi, idesc, 1u);
-                            a_lo += shift16;
-                            b_lo += b_step;
+                        for (int cp = cp_lo; cp < cp_hi; ++cp) {
+                            uint32_t a_lo = umma_desc_lo(base + ringOff + stage * P.a_stage_bytes) +
+                                            (P.wshift ? (static_cast<uint32_t>(P.copy_off[cp] - P.min_off) * row_bytes) >> 4 : 0u);
+                            uint32_t b_lo = b_chunk_lo + static_cast<uint32_t>(P.tap0 + cp * P.tap_dcp) * tap_bytes16;
+                            for (int sh = 0; sh < P.S; ++sh) {
+                                umma2_bf16_lohi(tacc, a_lo, dhi_a, b_lo, dhi, idesc, acc);
+                                acc = 1;
+                                for (int k = 1; k < ksteps; ++k)
+                                    umma2_bf16_lohi(tacc, a_lo + 2u * k, dhi_a, b_lo + 2u * k, dhi, idesc, 1u);
+                                a_lo += shift16;
+                                b_lo += b_step;
+                            }
                         }
                         umma2_commit_mc(barEmpty + 8u * stage, 3);
                     } else if (leader) {
-                        uint32_t a_lo = umma_desc_lo(base + ringOff + stage * P.a_stage_bytes);
-                        uint32_t b_lo = b_chunk_lo + static_cast<uint32_t>(P.tap0 + cp * P.tap_dcp) * tap_bytes16;
                         const uint32_t b_step = static_cast<uint32_t>(P.tap_dsh) * tap_bytes16;   // may wrap (negative step)
-                        for (int sh = 0; sh < P.S; ++sh) {
-                            // experiment: matrix start not on a swizzle-atom boundary -> descriptor base offset (bits 49-51)
-                            const uint32_t ahi = P.unaligned_mode == 2
-                                                     ? (dhi | ((static_cast<uint32_t>(sh * inner_rows) & 7u) << 17)) : dhi;
-                            umma_bf16_lohi(tacc, a_lo, ahi, b_lo, dhi, idesc, acc);
-                            acc = 1;
-                            if (ksteps == 4) {   // common case: straight-line, constant accumulate flag
-                                umma_bf16_lohi(tacc, a_lo + 2u, ahi, b_lo + 2u, dhi, idesc, 1u);
-                                umma_bf16_lohi(tacc, a_lo + 4u, ahi, b_lo + 4u, dhi, idesc, 1u);
-                                umma_bf16_lohi(tacc, a_lo + 6u, ahi, b_lo + 6u, dhi, idesc, 1u);
-                            } else {
-                                for (int k = 1; k < ksteps; ++k)
-                                    umma_bf16_lohi(tacc, a_lo + 2u * k, ahi, b_lo + 2u * k, dhi, idesc, 1u);
+                        for (int cp = cp_lo; cp < cp_hi; ++cp) {
+                            uint32_t a_lo = umma_desc_lo(base + ringOff + stage * P.a_stage_bytes) +
+                                            (P.wshift ? (static_cast<uint32_t>(P.copy_off[cp] - P.min_off) * row_bytes) >> 4 : 0u);
+                            uint32_t b_lo = b_chunk_lo + static_cast<uint32_t>(P.tap0 + cp * P.tap_dcp) * tap_bytes16;
+                            for (int sh = 0; sh < P.S; ++sh) {
+                                // experiment: matrix start not on a swizzle-atom boundary -> descriptor base offset (bits 49-51)
+                                const uint32_t ahi = P.unaligned_mode == 2
+                                                         ? (dhi_a | ((static_cast<uint32_t>(sh * inner_rows) & 7u) << 17)) : dhi_a;
+                                umma_bf16_lohi(tacc, a_lo, ahi, b_lo, dhi, idesc, acc);
+                                acc = 1;
+                                if (ksteps == 4) {   // common case: straight-line, constant accumulate flag
+                                    umma_bf16_lohi(tacc, a_lo + 2u, ahi, b_lo + 2u, dhi, idesc, 1u);
+                                    umma_bf16_lohi(tacc, a_lo + 4u, ahi, b_lo + 4u, dhi, idesc, 1u);
+                                    umma_bf16_lohi(tacc, a_lo + 6u, ahi, b_lo + 6u, dhi, idesc, 1u);
+                                } else {
+                                    for (int k = 1; k < ksteps; ++k)
+                                        umma_bf16_lohi(tacc, a_lo + 2u * k, ahi, b_lo + 2u * k, dhi, idesc, 1u);
+                                }
+                                a_lo += shift16;
+                                b_lo += b_step;
                             }
-                            a_lo += shift16;
-                            b_lo += b_step;
                         }
                         umma_commit(barEmpty + 8u * stage);
                     }
@@ -2269,6 +2290,7 @@ struct HaloPlan {
     bool ok;
     bool spatial;       // shift dim = H (taps along W are copies) ; otherwise shift dim = T
     bool pair;          // CTA-pair variant: M = 256 tiles, half of the weight rows resident per CTA
+    bool wshift;        // W taps by descriptor offset into one widened box (spatial, b[0] == 8)
     int b[4], tl[4], O[4];
     int S, ncopies, stages, nstg, bn_tile, n_step, n_tiles, nchunks, tail_box;
     long long m_tiles;
@@ -2333,7 +2355,11 @@ HaloPlan plan_halo_impl(int W, int H, int T, int N, int kdim, int cols, int kt, 
     }
     p.m_tiles = (long long)p.tl[0] * p.tl[1] * p.tl[2] * p.tl[3];
     const int inner = p.b[0] * p.b[1] * p.b[2];
-    const int halo_rows = inner * (p.b[3] + p.S - 1);
+    // W taps as descriptor start offsets (one load per chunk instead of kw): every 8-row group of the MMA's A operand
+    // must be one W run of the box, i.e. b[0] == 8; consecutive groups are then (8 + kw - 1) rows apart (descriptor SBO)
+    const char* ew = getenv("ZSV_HALO_WSHIFT");
+    p.wshift = p.spatial && kw > 1 && p.b[0] == 8 && !(ew && atoi(ew) == 0);
+    const int halo_rows = (p.wshift ? (p.b[0] + kw - 1) * p.b[1] * p.b[2] : inner) * (p.b[3] + p.S - 1);
     p.a_stage_bytes = align1k((uint32_t)halo_rows * 128u);
     p.nchunks = ceil_div(kdim, 64);
     const int tail = kdim - 64 * (p.nchunks - 1);
@@ -2394,7 +2420,7 @@ HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int k
     const char* e = getenv("ZSV_HALO_2CTA");
     const int mode = e ? atoi(e) : -1;
     if (mode == 0) return one;
-    if (mode < 0 && one.ok && one.stages > 2) return one;
+    if (mode < 0 && one.ok && one.stages > (one.wshift ? 1 : 2)) return one;
     const HaloPlan two = plan_halo_impl(W, H, T, N, kdim, cols, kt, kh, kw, scratch_mode, true);
     if (getenv("ZSV_DEBUG_PLAN"))
         fprintf(stderr, "[zsv] halo plan k=%d cols=%d taps=%dx%dx%d: single ok=%d stages=%d nstg=%d box=%d,%d,%d,%d | pair ok=%d stages=%d nstg=%d\n",
@@ -2405,7 +2431,8 @@ HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int k
     // measured (profiles/r01_halo_pair_ab.txt): the pair pays off where it reaches a 4-deep ring and the single-CTA
     // plan has at most two stages or does not exist (the generic kernel would run); epilogue-bound temporal
     // convolutions with a 3-stage single-CTA plan are faster as they are
-    return two.stages >= 4 ? two : one;
+    // (a stage of the W-shift layout carries all kw W taps: three of them are as much work in flight as nine before)
+    return two.stages >= (two.wshift ? 3 : 4) ? two : one;
 }
 
 // grid of the halo kernel: a multiple of n_tiles so that every CTA keeps one N tile
@@ -2432,6 +2459,10 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
     else a.os[0] = sW, a.os[1] = sH, a.os[2] = sN, a.os[3] = sT;
     a.S = p.S, a.ncopies = p.ncopies, a.shift_org = shift_org;
     for (int c = 0; c < p.ncopies; ++c) a.copy_off[c] = copy_off[c];
+    a.wshift = p.wshift ? 1 : 0;
+    a.w_ext = p.b[0] + (p.wshift ? p.ncopies - 1 : 0);
+    a.min_off = copy_off[0];
+    for (int c = 1; c < p.ncopies; ++c) a.min_off = std::min(a.min_off, copy_off[c]);
     a.tap0 = tap0, a.tap_dcp = tap_dcp, a.tap_dsh = tap_dsh;
     a.kdim = actC, a.nchunks = p.nchunks, a.tail_box = p.tail_box, a.ntaps = ntaps;
     a.ncols = outPitch, a.nbias = nbias, a.bn_tile = p.bn_tile, a.n_step = p.n_step, a.n_tiles = p.n_tiles;
@@ -2450,7 +2481,7 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
 
     // activation maps in box order
     auto act_map = [&](CUtensorMap* m, const void* basep, int C, int pitch, int boxc, int shift_ext,
-                       CUtensorMapSwizzle sw) {
+                       CUtensorMapSwizzle sw, int w_ext) {
         const uint64_t cB = (uint64_t)pitch * 2;
         const uint64_t bW = cB, bH = cB * W, bT = bH * H, bN = bT * T;
         uint64_t dims[5], str[4];
@@ -2465,15 +2496,15 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
             dims[3] = N, str[2] = bN;
             dims[4] = T, str[3] = bT;
         }
-        uint32_t box[5] = {(uint32_t)boxc, (uint32_t)p.b[0], (uint32_t)p.b[1], (uint32_t)p.b[2], (uint32_t)shift_ext};
+        uint32_t box[5] = {(uint32_t)boxc, (uint32_t)w_ext, (uint32_t)p.b[1], (uint32_t)p.b[2], (uint32_t)shift_ext};
         return make_map(m, basep, 5, dims, str, box, sw);
     };
     const CUtensorMapSwizzle tail_sw = p.tail_box == 16 ? CU_TENSOR_MAP_SWIZZLE_32B
                                      : (p.tail_box == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
     CUtensorMap mA, mAt, mB, mBt, mO;
-    int rc = act_map(&mA, act, actC, actPitch, 64, p.b[3] + p.S - 1, CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = act_map(&mA, act, actC, actPitch, 64, p.b[3] + p.S - 1, CU_TENSOR_MAP_SWIZZLE_128B, a.w_ext);
     if (rc) return rc;
-    rc = act_map(&mAt, act, actC, actPitch, p.tail_box, p.b[3] + p.S - 1, tail_sw);
+    rc = act_map(&mAt, act, actC, actPitch, p.tail_box, p.b[3] + p.S - 1, tail_sw, a.w_ext);
     if (rc) return rc;
     {
         uint64_t dims[3] = {(uint64_t)actC, (uint64_t)wRows, (uint64_t)ntaps};
@@ -2485,7 +2516,7 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
         rc = make_map(&mBt, wimg, 3, dims, str, box, tail_sw);
         if (rc) return rc;
     }
-    rc = act_map(&mO, out, outPitch, outPitch, 64, p.b[3], CU_TENSOR_MAP_SWIZZLE_128B);
+    rc = act_map(&mO, out, outPitch, outPitch, 64, p.b[3], CU_TENSOR_MAP_SWIZZLE_128B, p.b[0]);
     if (rc) return rc;
 
     static std::once_flag once;
