@@ -114,32 +114,37 @@ bn_finalize_kernel(const float* __restrict__ part_sum, const float* __restrict__
     sh1[rl][cl] = a;
     sh2[rl][cl] = b;
     __syncthreads();
-    if (rl == 0 && c < Cp) {
+    // One chunk (the persistent convolution kernels write at most one partial row per SM): this block already holds
+    // every row of its channels -- no chunk sums, no ticket, no second pass.  This kernel sits on the dependent chain
+    // 37 times per step, its latency is all it costs.
+    if (nchunks > 1) {
+        if (rl == 0 && c < Cp) {
+            a = b = 0.0;
+            for (int r = 0; r < 32; ++r) {
+                a += sh1[r][cl];
+                b += sh2[r][cl];
+            }
+            chunk[((long long)blockIdx.y * 2 + 0) * Cp + c] = a;
+            chunk[((long long)blockIdx.y * 2 + 1) * Cp + c] = b;
+            __threadfence();   // publish before the ticket
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) last = (atomicAdd(&tickets[blockIdx.x], 1u) == (unsigned)(nchunks - 1));
+        __syncthreads();
+        if (!last) return;
+        __threadfence();       // the other blocks' chunk sums are visible from here on
         a = b = 0.0;
-        for (int r = 0; r < 32; ++r) {
-            a += sh1[r][cl];
-            b += sh2[r][cl];
+        if (c < Cp) {
+            for (int r = rl; r < nchunks; r += 32) {
+                a += __ldcg(chunk + ((long long)r * 2 + 0) * Cp + c);
+                b += __ldcg(chunk + ((long long)r * 2 + 1) * Cp + c);
+            }
         }
-        chunk[((long long)blockIdx.y * 2 + 0) * Cp + c] = a;
-        chunk[((long long)blockIdx.y * 2 + 1) * Cp + c] = b;
-        __threadfence();   // publish before the ticket
+        sh1[rl][cl] = a;
+        sh2[rl][cl] = b;
+        __syncthreads();
+        if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) last = (atomicAdd(&tickets[blockIdx.x], 1u) == (unsigned)(nchunks - 1));
-    __syncthreads();
-    if (!last) return;
-    __threadfence();       // the other blocks' chunk sums are visible from here on
-    a = b = 0.0;
-    if (c < Cp) {
-        for (int r = rl; r < nchunks; r += 32) {
-            a += __ldcg(chunk + ((long long)r * 2 + 0) * Cp + c);
-            b += __ldcg(chunk + ((long long)r * 2 + 1) * Cp + c);
-        }
-    }
-    sh1[rl][cl] = a;
-    sh2[rl][cl] = b;
-    __syncthreads();
-    if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;
     if (rl == 0 && c < Cp) {
         double s1 = 0.0, s2 = 0.0;
         for (int r = 0; r < 32; ++r) {
@@ -370,33 +375,55 @@ bn_bwd_final_kernel(const float* __restrict__ partial, int nblocks, int nq, int 
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ mean2,
                     const float* __restrict__ invstd2, float* __restrict__ sums, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, float* __restrict__ dgamma2, float* __restrict__ dbeta2) {
-    __shared__ double sh[32][33];
-    __shared__ double tot[4][32];
-    const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cl;
-    for (int qi = 0; qi < nq; ++qi) {
-        double s = 0.0;
-        if (c < Cp) {
-            // four independent loads in flight per thread: the chain of fp64 adds is short, the loads are what take time
-            int b = rl;
-            for (; b + 96 < nblocks; b += 128) {
-                const float v0 = partial[((long long)b * 4 + qi) * Cp + c];
-                const float v1 = partial[((long long)(b + 32) * 4 + qi) * Cp + c];
-                const float v2 = partial[((long long)(b + 64) * 4 + qi) * Cp + c];
-                const float v3 = partial[((long long)(b + 96) * 4 + qi) * Cp + c];
-                s += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+    // 8 channels (one 32-byte sector per partial row) x 128 row lanes per block: Cp/8 blocks instead of Cp/32, and a
+    // thread's loads (<= 10 rows x nq quantities for the 1184-row partials of bn_bwd_reduce) are all independent, so the
+    // kernel is one memory round trip plus a shared-memory tree -- it sits on the dependent chain 34 times per step.
+    __shared__ double sh[4][128][9];
+    __shared__ double tot[4][8];
+    const int cl = threadIdx.x & 7, rl = threadIdx.x >> 3;
+    const int c = blockIdx.x * 8 + cl;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    if (c < Cp) {
+        int b = rl;
+        for (; b + 384 < nblocks; b += 512) {   // four rows x nq quantities in flight
+#pragma unroll
+            for (int qi = 0; qi < 4; ++qi) {
+                if (qi < nq) {
+                    const float v0 = partial[((long long)b * 4 + qi) * Cp + c];
+                    const float v1 = partial[((long long)(b + 128) * 4 + qi) * Cp + c];
+                    const float v2 = partial[((long long)(b + 256) * 4 + qi) * Cp + c];
+                    const float v3 = partial[((long long)(b + 384) * 4 + qi) * Cp + c];
+                    s[qi] += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+                }
             }
-            for (; b < nblocks; b += 32) s += (double)partial[((long long)b * 4 + qi) * Cp + c];
         }
-        sh[rl][cl] = s;
-        __syncthreads();
-        if (rl == 0) {
-            s = 0.0;
-            for (int r = 0; r < 32; ++r) s += sh[r][cl];
-            tot[qi][cl] = s;
+        for (; b < nblocks; b += 128) {
+#pragma unroll
+            for (int qi = 0; qi < 4; ++qi)
+                if (qi < nq) s[qi] += (double)partial[((long long)b * 4 + qi) * Cp + c];
         }
-        __syncthreads();
     }
+#pragma unroll
+    for (int qi = 0; qi < 4; ++qi) sh[qi][rl][cl] = s[qi];
+    __syncthreads();
+    // two-level tree in a fixed order: 256 threads sum 16 rows each, 32 threads sum the 8 partial results
+    __shared__ double part[4][8][9];
+    if (threadIdx.x < 256) {
+        const int qi = threadIdx.x >> 6, pr = (threadIdx.x >> 3) & 7, cc = threadIdx.x & 7;
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) t += sh[qi][pr * 16 + r][cc];
+        part[qi][pr][cc] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int qi = threadIdx.x >> 3, cc = threadIdx.x & 7;
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += part[qi][r][cc];
+        tot[qi][cc] = t;
+    }
+    __syncthreads();
     if (rl != 0 || c >= Cp) return;
     const double s1 = tot[0][cl];
     double s2 = tot[1][cl];
@@ -733,8 +760,9 @@ extern "C" int zsv_bn_finalize(const float* part_sum, const float* part_sq, int 
     if (workspace_bytes < zsv_bn_finalize_workspace(C)) return fail(ZSV_ERR_WORKSPACE, "bn_finalize: workspace too small");
     const int Cp = cpad(C);
     cudaStream_t st = (cudaStream_t)stream;
-    // ~128 partial rows per chunk keeps every stage-1 block busy while spreading large layers over many SMs
-    int nchunks = std::max(1, std::min(kFinalizeMaxChunks, ceil_div(part_rows, 128)));
+    // up to 512 partial rows (16 loads in flight per thread) in one stage; beyond that ~128 rows per chunk spread
+    // large row counts over many SMs
+    int nchunks = part_rows <= 512 ? 1 : std::max(1, std::min(kFinalizeMaxChunks, ceil_div(part_rows, 128)));
     const int rows_per_chunk = ceil_div(part_rows, nchunks);
     nchunks = ceil_div(part_rows, rows_per_chunk);
     if (ceil_div(Cp, 32) * sizeof(unsigned int) > kTicketBytes) return fail(ZSV_ERR_UNSUPPORTED, "bn_finalize: too many channels");
@@ -831,7 +859,7 @@ extern "C" int zsv_bn_bwd(const void* g, const void* out, int relu, const float*
         bn_bwd_reduce_kernel<false><<<nblocks, 256, smem_r, st>>>(gb, ob, relu, mask_scale, mask_shift, yb, y2b, rows, Cp, R, partial);
     ZSV_LAUNCH_CHECK("bn_bwd_reduce_kernel");
     const int nq = y2 ? 4 : 2;
-    bn_bwd_final_kernel<<<ceil_div(Cp, 32), 1024, 0, st>>>(partial, nblocks, nq, C, Cp, 1, mean, invstd, mean2, invstd2, sums, dgamma, dbeta, dgamma2, dbeta2);
+    bn_bwd_final_kernel<<<ceil_div(Cp, 8), 1024, 0, st>>>(partial, nblocks, nq, C, Cp, 1, mean, invstd, mean2, invstd2, sums, dgamma, dbeta, dgamma2, dbeta2);
     ZSV_LAUNCH_CHECK("bn_bwd_final_kernel");
     const long long work_a = ceil_div_ll(rows, (long long)R * 2);
     const int blocks = y2 ? resident_grid(bn_bwd_apply_kernel<true>, 256, 0, work_a, 1 << 20)
@@ -857,7 +885,7 @@ extern "C" int zsv_bn_bwd_finish(const void* dz, const void* y, const float* mea
     if (workspace_bytes < 4 * (size_t)Cp * sizeof(float)) return fail(ZSV_ERR_WORKSPACE, "bn_bwd_finish: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     float* sums = (float*)workspace;
-    bn_bwd_final_kernel<<<ceil_div(Cp, 32), 1024, 0, st>>>(partial, partial_rows, 2, C, Cp, 0, mean, invstd, nullptr, nullptr,
+    bn_bwd_final_kernel<<<ceil_div(Cp, 8), 1024, 0, st>>>(partial, partial_rows, 2, C, Cp, 0, mean, invstd, nullptr, nullptr,
                                                           sums, dgamma, dbeta, nullptr, nullptr);
     ZSV_LAUNCH_CHECK("bn_bwd_final_kernel");
     const int V = Cp >> 3;
