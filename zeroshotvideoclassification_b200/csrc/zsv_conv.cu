@@ -732,6 +732,7 @@ struct HaloArgs {
     int32_t wshift;          // 1: ONE box per chunk, widened by kw-1 along W; the W taps are descriptor start offsets
     int32_t w_ext;           // box extent along W in that mode (b[0] + kw - 1)
     int32_t min_off;         // smallest copy_off: W origin of the widened box relative to the tile
+    int32_t w_first, w_step; // row of W tap cp inside the widened box = w_first + cp * w_step (copy_off is arithmetic)
     int32_t bn_relu;
     const __nv_bfloat16* bn_y;
     const float4* bn_tab;
@@ -926,7 +927,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                         const uint32_t b_step = static_cast<uint32_t>(P.tap_dsh) * tap_bytes16;
                         for (int cp = cp_lo; cp < cp_hi; ++cp) {
                             uint32_t a_lo = umma_desc_lo(base + ringOff + stage * P.a_stage_bytes) +
-                                            (P.wshift ? (static_cast<uint32_t>(P.copy_off[cp] - P.min_off) * row_bytes) >> 4 : 0u);
+                                            (P.wshift ? (static_cast<uint32_t>(P.w_first + cp * P.w_step) * row_bytes) >> 4 : 0u);
                             uint32_t b_lo = b_chunk_lo + static_cast<uint32_t>(P.tap0 + cp * P.tap_dcp) * tap_bytes16;
                             for (int sh = 0; sh < P.S; ++sh) {
                                 umma2_bf16_lohi(tacc, a_lo, dhi_a, b_lo, dhi, idesc, acc);
@@ -938,25 +939,47 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                             }
                         }
                         umma2_commit_mc(barEmpty + 8u * stage, 3);
-                    } else if (leader) {
+                    } else if (leader && !P.wshift) {
+                        // one W copy per stage.  This issue loop is the scalar bottleneck of the short-K temporal
+                        // convolutions: no per-tap parameter indexing, straight-line k-steps.
+                        uint32_t a_lo = umma_desc_lo(base + ringOff + stage * P.a_stage_bytes);
+                        uint32_t b_lo = b_chunk_lo + static_cast<uint32_t>(P.tap0 + ld * P.tap_dcp) * tap_bytes16;
                         const uint32_t b_step = static_cast<uint32_t>(P.tap_dsh) * tap_bytes16;   // may wrap (negative step)
-                        for (int cp = cp_lo; cp < cp_hi; ++cp) {
-                            uint32_t a_lo = umma_desc_lo(base + ringOff + stage * P.a_stage_bytes) +
-                                            (P.wshift ? (static_cast<uint32_t>(P.copy_off[cp] - P.min_off) * row_bytes) >> 4 : 0u);
+                        for (int sh = 0; sh < P.S; ++sh) {
+                            // experiment: matrix start not on a swizzle-atom boundary -> descriptor base offset (bits 49-51)
+                            const uint32_t ahi = P.unaligned_mode == 2
+                                                     ? (dhi | ((static_cast<uint32_t>(sh * inner_rows) & 7u) << 17)) : dhi;
+                            umma_bf16_lohi(tacc, a_lo, ahi, b_lo, dhi, idesc, acc);
+                            acc = 1;
+                            if (ksteps == 4) {   // common case: straight-line, constant accumulate flag
+                                umma_bf16_lohi(tacc, a_lo + 2u, ahi, b_lo + 2u, dhi, idesc, 1u);
+                                umma_bf16_lohi(tacc, a_lo + 4u, ahi, b_lo + 4u, dhi, idesc, 1u);
+                                umma_bf16_lohi(tacc, a_lo + 6u, ahi, b_lo + 6u, dhi, idesc, 1u);
+                            } else {
+                                for (int k = 1; k < ksteps; ++k)
+                                    umma_bf16_lohi(tacc, a_lo + 2u * k, ahi, b_lo + 2u * k, dhi, idesc, 1u);
+                            }
+                            a_lo += shift16;
+                            b_lo += b_step;
+                        }
+                        umma_commit(barEmpty + 8u * stage);
+                    } else if (leader) {
+                        // all kw W taps from one widened box: start offsets of whole rows, SBO = w_ext rows (dhi_a)
+                        const uint32_t b_step = static_cast<uint32_t>(P.tap_dsh) * tap_bytes16;
+                        const uint32_t stage_lo = umma_desc_lo(base + ringOff + stage * P.a_stage_bytes);
+                        for (int cp = 0; cp < P.ncopies; ++cp) {
+                            uint32_t a_lo = stage_lo + ((static_cast<uint32_t>(P.w_first + cp * P.w_step) * row_bytes) >> 4);
                             uint32_t b_lo = b_chunk_lo + static_cast<uint32_t>(P.tap0 + cp * P.tap_dcp) * tap_bytes16;
                             for (int sh = 0; sh < P.S; ++sh) {
-                                // experiment: matrix start not on a swizzle-atom boundary -> descriptor base offset (bits 49-51)
-                                const uint32_t ahi = P.unaligned_mode == 2
-                                                         ? (dhi_a | ((static_cast<uint32_t>(sh * inner_rows) & 7u) << 17)) : dhi_a;
-                                umma_bf16_lohi(tacc, a_lo, ahi, b_lo, dhi, idesc, acc);
+                                umma_bf16_lohi(tacc, a_lo, dhi_a, b_lo, dhi, idesc, acc);
                                 acc = 1;
-                                if (ksteps == 4) {   // common case: straight-line, constant accumulate flag
-                                    umma_bf16_lohi(tacc, a_lo + 2u, ahi, b_lo + 2u, dhi, idesc, 1u);
-                                    umma_bf16_lohi(tacc, a_lo + 4u, ahi, b_lo + 4u, dhi, idesc, 1u);
-                                    umma_bf16_lohi(tacc, a_lo + 6u, ahi, b_lo + 6u, dhi, idesc, 1u);
+                                if (ksteps == 4) {
+                                    umma_bf16_lohi(tacc, a_lo + 2u, dhi_a, b_lo + 2u, dhi, idesc, 1u);
+                                    umma_bf16_lohi(tacc, a_lo + 4u, dhi_a, b_lo + 4u, dhi, idesc, 1u);
+                                    umma_bf16_lohi(tacc, a_lo + 6u, dhi_a, b_lo + 6u, dhi, idesc, 1u);
                                 } else {
                                     for (int k = 1; k < ksteps; ++k)
-                                        umma_bf16_lohi(tacc, a_lo + 2u * k, ahi, b_lo + 2u * k, dhi, idesc, 1u);
+                                        umma_bf16_lohi(tacc, a_lo + 2u * k, dhi_a, b_lo + 2u * k, dhi, idesc, 1u);
                                 }
                                 a_lo += shift16;
                                 b_lo += b_step;
@@ -2463,6 +2486,10 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
     a.w_ext = p.b[0] + (p.wshift ? p.ncopies - 1 : 0);
     a.min_off = copy_off[0];
     for (int c = 1; c < p.ncopies; ++c) a.min_off = std::min(a.min_off, copy_off[c]);
+    a.w_first = copy_off[0] - a.min_off;
+    a.w_step = p.ncopies > 1 ? copy_off[1] - copy_off[0] : 0;
+    for (int c = 2; c < p.ncopies && p.wshift; ++c)
+        if (copy_off[c] - copy_off[c - 1] != a.w_step) return fail(ZSV_ERR_UNSUPPORTED, "halo igemm: W taps must be evenly spaced");
     a.tap0 = tap0, a.tap_dcp = tap_dcp, a.tap_dsh = tap_dsh;
     a.kdim = actC, a.nchunks = p.nchunks, a.tail_box = p.tail_box, a.ntaps = ntaps;
     a.ncols = outPitch, a.nbias = nbias, a.bn_tile = p.bn_tile, a.n_step = p.n_step, a.n_tiles = p.n_tiles;
