@@ -74,3 +74,44 @@ def test_gradsync_single_process_is_a_noop():
     sync = zdist.GradSync()
     sync.submit({"w": torch.ones(3)})
     assert sync.finish() == {} and sync.world == 1
+
+
+def _acc_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from zeroshotvideoclassification_b200 import dist as zdist
+    zdist.init_from_env("gloo")
+    n = 10001
+    g = torch.Generator().manual_seed(7)
+    hit1 = torch.rand(n, generator=g) < 0.3          # the same synthetic per-row outcomes on every rank
+    hit5 = hit1 | (torch.rand(n, generator=g) < 0.4)
+    lo, hi = zdist.shard_rows(n, rank, world)
+    counts = torch.tensor([int(hit1[lo:hi].sum()), int(hit5[lo:hi].sum()), hi - lo], dtype=torch.int64)
+    top1, top5 = zdist.reduce_accuracy_counts(counts)
+    ok = abs(top1 - 100.0 * float(hit1.float().mean())) < 1e-4 and abs(top5 - 100.0 * float(hit5.float().mean())) < 1e-4
+    ok &= counts[2].item() == hi - lo            # the caller's tensor is not modified by the reduction
+    q.put((rank, ok, (lo, hi)))
+    dist.destroy_process_group()
+
+
+def test_sharded_accuracy_world2_gloo():
+    """Evaluation shards rows over ranks: the row ranges tile [0, N) and the all-reduced hit
+    counts give the global top-1 / top-5 on every rank."""
+    from zeroshotvideoclassification_b200 import dist as zdist
+    for n, w in ((10, 3), (7, 8), (10000, 8), (0, 2)):
+        rs = [zdist.shard_rows(n, r, w) for r in range(w)]
+        assert rs[0][0] == 0 and rs[-1][1] == n and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+        assert max(h - l for l, h in rs) - min(h - l for l, h in rs) <= 1
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_acc_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res), res
+    with pytest.raises(ValueError):
+        zdist.reduce_accuracy_counts(torch.zeros(3, dtype=torch.int64))

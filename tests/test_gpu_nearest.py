@@ -65,3 +65,26 @@ def test_class_overlap_filter_matches_scipy():
         ref = cdist(train, test, "cosine").min(1) > tau
         got = class_overlap_mask(train, test, tau).cpu().numpy()
         assert np.array_equal(got, ref), tau
+
+
+def test_sharded_accuracy_equals_compute_accuracy():
+    """dist.compute_accuracy_sharded (single process: one shard) and accuracy.count_correct agree with
+    compute_accuracy and with the oracle's top-1 / top-5 (main.py:316-325)."""
+    from zeroshotvideoclassification_b200 import compute_accuracy
+    from zeroshotvideoclassification_b200 import accuracy, dist as zdist
+    rng = np.random.default_rng(11)
+    cls = _unit(rng, 101)
+    labels = rng.integers(0, 101, 3000)
+    true = cls[labels]
+    pred = true + 0.8 * _unit(rng, 3000)
+    ref = compute_accuracy(pred, cls, true)
+    assert zdist.compute_accuracy_sharded(pred, cls, true) == ref
+    c = accuracy.count_correct(pred[:0], cls, true[:0]).cpu().tolist()
+    assert c == [0, 0, 0]
+    parts = sum(accuracy.count_correct(pred[lo:hi], cls, true[lo:hi]) for lo, hi in
+                (zdist.shard_rows(3000, r, 7) for r in range(7))).cpu().tolist()
+    assert parts[2] == 3000 and (100.0 * parts[0] / 3000, 100.0 * parts[1] / 3000) == pytest.approx(ref, abs=1e-4)
+    dist = no.cosine_distance_table(pred.astype(np.float32), cls)
+    top5 = no.topk_lowest_index(dist, 5)
+    assert ref[0] == pytest.approx(100.0 * float((top5[:, 0] == labels).mean()), abs=1e-4)
+    assert ref[1] == pytest.approx(100.0 * float((top5 == labels[:, None]).any(1).mean()), abs=1e-4)

@@ -34,6 +34,19 @@ def compute_accuracy(predicted_embed, class_embed, true_embed):
     return float(top1), float(top5)
 
 
+def count_correct(predicted_embed, class_embed, true_embed) -> torch.Tensor:
+    """int64 [3] on the GPU: (top-1 hits, top-5 hits, rows) of main.py:316-325 for these rows; the summable form of
+    ``compute_accuracy`` that ``dist.compute_accuracy_sharded`` all-reduces.  Zero rows give zeros."""
+    pred = _as_cuda(predicted_embed)
+    cls = _as_cuda(class_embed, pred.device)
+    k = min(5, cls.shape[0])
+    y_pred = ops.nearest_class(pred, cls, k)
+    y = ops.nearest_class(_as_cuda(true_embed, pred.device), cls, 1)
+    top1 = (y_pred[:, :1] == y).sum()
+    top5 = (y_pred == y).any(dim=1).sum()
+    return torch.stack([top1, top5, torch.tensor(pred.shape[0], device=pred.device)]).to(torch.int64)
+
+
 def class_overlap_mask(class_embedding, other_class_embedding, class_overlap: float) -> torch.Tensor:
     """auxiliary/auxiliary_dataset.py:141-144 (filter_overlapping_classes): keep a training class iff its cosine
     distance to the NEAREST test class exceeds ``class_overlap``:

@@ -13,7 +13,7 @@ parameters (network.py:500-517, never reached by forward) have no gradient and a
 from __future__ import annotations
 
 import os
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -127,3 +127,33 @@ def broadcast_module(module: torch.nn.Module, src: int = 0) -> None:
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src)
+
+
+# -- evaluation: rows are independent, so the nearest-class search shards over ranks ----------
+def shard_rows(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced row range [lo, hi) of rank ``rank``; ranges of all ranks tile [0, n) (some may be empty)."""
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def reduce_accuracy_counts(counts: torch.Tensor, group=None) -> Tuple[float, float]:
+    """``counts`` = int64 [3] (top-1 hits, top-5 hits, rows) of this rank's rows; SUM over ranks, then the two
+    percentages ``compute_accuracy`` (main.py:316-325) returns.  One exchange step of 24 bytes."""
+    counts = counts.clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    c1, c5, n = (int(v) for v in counts.tolist())
+    if n == 0:
+        raise ValueError("accuracy of zero samples")
+    return 100.0 * c1 / n, 100.0 * c5 / n
+
+
+def compute_accuracy_sharded(predicted_embed, class_embed, true_embed, group=None) -> Tuple[float, float]:
+    """``compute_accuracy`` with the N rows split over the ranks of ``group``: every rank holds the full embedding
+    tables (as evaluate() does, main.py:254-256), scores its own row range with the nearest-class kernel and the hit
+    counts are all-reduced.  Same result on every rank, equal to the single-GPU call."""
+    from . import accuracy
+    assert len(predicted_embed) == len(true_embed), "True and predicted labels must have the same number of samples"
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    lo, hi = shard_rows(len(predicted_embed), rank, world)
+    return reduce_accuracy_counts(accuracy.count_correct(predicted_embed[lo:hi], class_embed, true_embed[lo:hi]), group)
