@@ -382,7 +382,7 @@ def run_b200(args):
     dom_calls = sum(kinds[k]["calls"] for k in ("fprop", "dgrad") if k in kinds)
     achieved = dom_fl / (dom_ms / 1e3) / 1e12 if dom_ms > 0 else None
     roofline = {
-        "bound": "tensor", "kernel": "igemm_kmajor_kernel (conv fprop + dgrad, tcgen05/TMA implicit GEMM)",
+        "bound": "tensor", "kernel": "igemm_halo_kernel + igemm_kmajor_kernel (conv fprop + dgrad: one tcgen05/TMA implicit-GEMM family, CTA pairs)",
         "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
         "frac": (achieved / peaks["tflops_sustained"]) if achieved else None, "traffic": traffic,
         "traffic_source": traffic_src,
