@@ -12,7 +12,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libzsv_b200.so"
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 X_NDHWC = 0
 X_WFOLD = 1
 
@@ -107,12 +107,13 @@ def load() -> C.CDLL:
             f"{path} is missing: build it with `python -m zeroshotvideoclassification_b200.build` "
             "(or __graft_entry__.build()). There is no CPU or PyTorch fallback for this path.")
     lib = C.CDLL(os.fspath(path))
+    lib.zsv_abi_version.restype = C.c_int
+    if lib.zsv_abi_version() != ABI_VERSION:       # first: a stale build may lack newer symbols altogether
+        raise RuntimeError(f"libzsv_b200.so ABI {lib.zsv_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.zsv_abi_version() != ABI_VERSION:
-        raise RuntimeError(f"libzsv_b200.so ABI {lib.zsv_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
     _lib = lib
     return lib
 
