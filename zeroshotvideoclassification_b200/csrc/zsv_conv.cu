@@ -594,8 +594,14 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
                         const uint32_t a_lo = umma_desc_lo(sa), b_lo = umma_desc_lo(sa + kPanelBytes);
                         if (k2) {
                             umma2_bf16_lohi(tacc, a_lo, dhi, b_lo, dhi, idesc, acc);
-                            for (int k = 1; k < ksteps; ++k)
-                                umma2_bf16_lohi(tacc, a_lo + 2u * k, dhi, b_lo + 2u * k, dhi, idesc, 1u);
+                            if (ksteps == 4) {   // common case: straight-line, constant accumulate flag
+                                umma2_bf16_lohi(tacc, a_lo + 2u, dhi, b_lo + 2u, dhi, idesc, 1u);
+                                umma2_bf16_lohi(tacc, a_lo + 4u, dhi, b_lo + 4u, dhi, idesc, 1u);
+                                umma2_bf16_lohi(tacc, a_lo + 6u, dhi, b_lo + 6u, dhi, idesc, 1u);
+                            } else {
+                                for (int k = 1; k < ksteps; ++k)
+                                    umma2_bf16_lohi(tacc, a_lo + 2u * k, dhi, b_lo + 2u * k, dhi, idesc, 1u);
+                            }
                             umma2_commit_mc(barEmpty + 8u * stage, 3);
                         } else {
                             umma_bf16_lohi(tacc, a_lo, dhi, b_lo, dhi, idesc, acc);
@@ -703,8 +709,13 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
 //   * the weight tile of this CTA (all taps, all channel chunks) is loaded ONCE and stays resident, and
 //   * the activation box is ordered with the tap ("shift") dimension OUTERMOST in shared memory and carries a halo of
 //     S-1 extra slices, so the S taps along that dimension are the same staged tile read at descriptor offsets of
-//     whole swizzle atoms (inner_rows % 8 == 0); taps along W (spatial convs) are separate, W-shifted copies.
-// One staged (chunk, copy) tile therefore feeds S x ksteps MMAs: 177 MAC per ingested byte for the 64->144 conv.
+//     whole swizzle atoms (inner_rows % 8 == 0);
+//   * taps along W (spatial convs): with b[0] == 8 the box is widened by kw-1 columns and the W taps are start offsets
+//     of one 128-byte row each -- every 8-row group of the A operand is one W run, consecutive groups are w_ext rows
+//     apart (descriptor SBO = w_ext * 128); the swizzle is a function of the absolute shared-memory address, so start
+//     addresses and group strides that are not multiples of the 1 KB atom address exactly the rows TMA wrote
+//     (bit-exact against the copy version, tests/test_gpu_conv.py).  Other box widths load kw W-shifted copies.
+// One staged chunk therefore feeds kw x S x ksteps MMAs: ~420 MAC per ingested byte for the 64->144 conv.
 // Channel tails of 16 / 32 use SWIZZLE_32B / SWIZZLE_64B tiles so they cost 1/4 / 1/2 of a full chunk.
 // Same persistent warp-specialised structure and epilogue as igemm_kmajor_kernel; a CTA keeps one N tile.
 // ------------------------------------------------------------------------------------------------
@@ -932,8 +943,14 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                             for (int sh = 0; sh < P.S; ++sh) {
                                 umma2_bf16_lohi(tacc, a_lo, dhi_a, b_lo, dhi, idesc, acc);
                                 acc = 1;
-                                for (int k = 1; k < ksteps; ++k)
-                                    umma2_bf16_lohi(tacc, a_lo + 2u * k, dhi_a, b_lo + 2u * k, dhi, idesc, 1u);
+                                if (ksteps == 4) {   // common case: straight-line, constant accumulate flag
+                                    umma2_bf16_lohi(tacc, a_lo + 2u, dhi_a, b_lo + 2u, dhi, idesc, 1u);
+                                    umma2_bf16_lohi(tacc, a_lo + 4u, dhi_a, b_lo + 4u, dhi, idesc, 1u);
+                                    umma2_bf16_lohi(tacc, a_lo + 6u, dhi_a, b_lo + 6u, dhi, idesc, 1u);
+                                } else {
+                                    for (int k = 1; k < ksteps; ++k)
+                                        umma2_bf16_lohi(tacc, a_lo + 2u * k, dhi_a, b_lo + 2u * k, dhi, idesc, 1u);
+                                }
                                 a_lo += shift16;
                                 b_lo += b_step;
                             }
