@@ -72,6 +72,19 @@ def test_no_cpu_fallback():
     model = vm.get_network(vm.default_opt())
     with pytest.raises(RuntimeError):
         model(torch.zeros(1, 1, 3, 8, 32, 32))
+    # optimizer, graph runner and the accuracy helpers added later follow the same rule
+    from zeroshotvideoclassification_b200.optim import FusedAdam
+    from zeroshotvideoclassification_b200.graph import GraphedStep
+    from zeroshotvideoclassification_b200 import accuracy
+    p = torch.nn.Parameter(torch.zeros(4))
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError):
+        FusedAdam([p]).step()
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            GraphedStep(lambda x: x, (torch.zeros(2),))
+        with pytest.raises((RuntimeError, AssertionError)):
+            accuracy.class_overlap_mask(torch.zeros(3, 300), torch.zeros(2, 300), 0.05)
 
 
 def test_product_does_not_import_oracle():
