@@ -42,7 +42,8 @@ def import_reference():
 
 def checksum(t: torch.Tensor):
     t = t.detach().double().flatten()
-    idx = torch.linspace(0, t.numel() - 1, steps=min(8, t.numel())).long()
+    # (fp32 linspace: the end point of a >2^24-element tensor rounds up by one, hence the clamp)
+    idx = torch.linspace(0, t.numel() - 1, steps=min(8, t.numel())).long().clamp_(max=t.numel() - 1)
     return {"sum": float(t.sum()), "abs": float(t.abs().sum()), "sq": float((t * t).sum()),
             "samples": [float(v) for v in t[idx]]}
 
@@ -84,6 +85,36 @@ def reference_step(network, B, T, H, W, seed, arch="r2plus1d_18"):
                 if k.endswith(("running_mean", "running_var")) and k.startswith("model.")}
     return dict(config=dict(B=B, T=T, H=H, W=W, seed=seed, arch=arch), emb=emb.detach().numpy().tolist(), loss=float(loss),
                 acts=acts, grads=grads, dead=dead, bn_after=bn_after), init, keys
+
+
+def reference_c3d_step(network, B, T, H, W, seed):
+    """main.py:170-195 on the reference's network.C3D (network.py:95-180; fp32 CPU, no optimizer step) with
+    Dropout p set to 0 (network.py:124: the mask is not reproducible across devices), forward hooks on every
+    conv / pool / linear."""
+    torch.manual_seed(seed)
+    opt = SimpleNamespace(network="c3d", fixconvs=False, nopretrained=False)
+    model = network.get_network(opt).train()
+    model.dropout.p = 0.0
+    init = {k: checksum(v) for k, v in model.state_dict().items() if v.is_floating_point()}
+    keys = {k: list(v.shape) for k, v in model.state_dict().items()}
+    x, z, _ = synthetic_batch(B, T, H, W, seed + 100)
+    acts = {}
+
+    def hook(name):
+        def fn(_m, _i, o):
+            acts[name] = checksum(o)
+        return fn
+
+    for name, m in model.named_modules():
+        if isinstance(m, (torch.nn.Conv3d, torch.nn.MaxPool3d, torch.nn.Linear)):
+            m.register_forward_hook(hook(name))
+    emb = model(x)
+    loss = torch.nn.MSELoss()(emb, z)
+    loss.backward()
+    grads = {k: checksum(p.grad) for k, p in model.named_parameters() if p.grad is not None}
+    dead = sorted(k for k, p in model.named_parameters() if p.grad is None)
+    return dict(config=dict(B=B, T=T, H=H, W=W, seed=seed, arch="c3d"), emb=emb.detach().numpy().tolist(),
+                loss=float(loss), acts=acts, grads=grads, dead=dead), init, keys
 
 
 def nearest_fixture():
@@ -143,6 +174,11 @@ def main():
     json.dump(r3d_keys, open(os.path.join(OUT, "r3d_state_dict_keys.json"), "w"), indent=0)
     json.dump(r3d_init, open(os.path.join(OUT, "r3d_init_seed0.json"), "w"))
     json.dump(r3d, open(os.path.join(OUT, "r3d_step_small.json"), "w"))
+    # C3D (network.py:95-180): fc6 needs 8192 = 512 x 1 x 4 x 4 features, so the clip is the full 16 x 112 x 112
+    c3d, c3d_init, c3d_keys = reference_c3d_step(network, 2, 16, 112, 112, seed=0)
+    json.dump(c3d_keys, open(os.path.join(OUT, "c3d_state_dict_keys.json"), "w"), indent=0)
+    json.dump(c3d_init, open(os.path.join(OUT, "c3d_init_seed0.json"), "w"))
+    json.dump(c3d, open(os.path.join(OUT, "c3d_step_bs2_16x112.json"), "w"))
     nearest_fixture()
     transform_fixture()
     print("golden fixtures written to", OUT)

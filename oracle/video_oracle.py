@@ -220,35 +220,56 @@ def model_forward(sd: Dict[str, Tensor], x: Tensor, train: bool = True, trace: O
     return embedding_head(sd, feats)
 
 
-def c3d_forward(sd: Dict[str, Tensor], x: Tensor, train: bool = False, emulate_bf16: bool = False) -> Tensor:
-    """network.C3D.forward (network.py:143-180).  Dropout(p=0.1) (network.py:167) is only applied in train
-    mode; parity tests run with train=False (or p=0) because the mask is not reproducible across devices.
+def c3d_forward(sd: Dict[str, Tensor], x: Tensor, train: bool = False, emulate_bf16: bool = False,
+                trace: Optional[dict] = None, dropout_p: float = 0.10) -> Tensor:
+    """network.C3D.forward (network.py:143-180).  Dropout(p=0.1) (network.py:124,167) is only applied in train
+    mode; parity tests run with train=False or dropout_p=0 because the mask is not reproducible across devices.
     emulate_bf16: bf16 rounding at the storage points of the B200 path (input clip, weight copies, every
-    conv+bias+ReLU output and its gradient); arithmetic stays fp32."""
+    conv+bias+ReLU output and its gradient); arithmetic stays fp32.  trace: records the output of every
+    conv (pre-ReLU, as a forward hook on the nn.Conv3d sees it), pool and linear by module name."""
     bs, nc = x.shape[:2]
     h = x.reshape(bs * nc, *x.shape[2:])
     if emulate_bf16:
         h = _RoundBf16Fwd.apply(h)
 
+    def keep(name, t):
+        if trace is not None:
+            if t.requires_grad:
+                t.retain_grad()
+            trace[name] = t
+        return t
+
     def conv(name, t):
         w = sd[name + ".weight"]
         if emulate_bf16:
             w = _RoundBf16Fwd.apply(w)
-        y = F.relu(F.conv3d(t, w, sd[name + ".bias"], padding=1))
-        return _RoundBf16Both.apply(y) if emulate_bf16 else y
+        y = F.relu(keep(name, F.conv3d(t, w, sd[name + ".bias"], padding=1)))
+        y = _RoundBf16Both.apply(y) if emulate_bf16 else y
+        return keep(name + ":out", y)
 
-    h = F.max_pool3d(conv("conv1", h), (1, 2, 2), (1, 2, 2))
-    h = F.max_pool3d(conv("conv2", h), (2, 2, 2), (2, 2, 2))
-    h = F.max_pool3d(conv("conv3b", conv("conv3a", h)), (2, 2, 2), (2, 2, 2))
-    h = F.max_pool3d(conv("conv4b", conv("conv4a", h)), (2, 2, 2), (2, 2, 2))
-    h = F.max_pool3d(conv("conv5b", conv("conv5a", h)), (2, 2, 2), (2, 2, 2), padding=(0, 1, 1))
+    h = keep("pool1", F.max_pool3d(conv("conv1", h), (1, 2, 2), (1, 2, 2)))
+    h = keep("pool2", F.max_pool3d(conv("conv2", h), (2, 2, 2), (2, 2, 2)))
+    h = keep("pool3", F.max_pool3d(conv("conv3b", conv("conv3a", h)), (2, 2, 2), (2, 2, 2)))
+    h = keep("pool4", F.max_pool3d(conv("conv4b", conv("conv4a", h)), (2, 2, 2), (2, 2, 2)))
+    h = keep("pool5", F.max_pool3d(conv("conv5b", conv("conv5a", h)), (2, 2, 2), (2, 2, 2), padding=(0, 1, 1)))
     h = h.reshape(-1, 8192)
-    h = F.relu(F.linear(h, sd["fc6.weight"], sd["fc6.bias"]))
-    if train:
-        h = F.dropout(h, p=0.10, training=True)
+    h = F.relu(keep("fc6", F.linear(h, sd["fc6.weight"], sd["fc6.bias"])))
+    if train and dropout_p > 0:
+        h = F.dropout(h, p=dropout_p, training=True)
     h = h.reshape(bs, nc, -1).mean(1).reshape(bs, -1)
-    h = F.linear(h, sd["regressor.weight"], sd["regressor.bias"])
+    h = keep("regressor", F.linear(h, sd["regressor.weight"], sd["regressor.bias"]))
     return F.normalize(h, dim=-1)
+
+
+def c3d_train_step_grads(sd: Dict[str, Tensor], x: Tensor, target: Tensor, trace: Optional[dict] = None,
+                         emulate_bf16: bool = False) -> Tuple[Tensor, Tensor, Dict[str, Tensor]]:
+    """One forward + backward of main.py:170-195 on network.C3D with Dropout p = 0 (no optimizer):
+    returns (emb, loss, grads by state-dict key); fc7 / fc8 (network.py:121-122, never used by forward) get none."""
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()}
+    emb = c3d_forward(params, x, train=True, emulate_bf16=emulate_bf16, trace=trace, dropout_p=0.0)
+    loss = mse_loss(emb, target)
+    loss.backward()
+    return emb.detach(), loss.detach(), {k: p.grad for k, p in params.items() if p.grad is not None}
 
 
 def mse_loss(emb: Tensor, target: Tensor) -> Tensor:

@@ -161,6 +161,47 @@ def test_oracle_reproduces_reference_r3d_step(seeded_r3d):
         assert name not in grads
 
 
+# ---- C3D (network.py:95-180): pinned against the reference's own module on the full 16x112x112 clip ----
+@pytest.fixture(scope="module")
+def seeded_c3d():
+    from zeroshotvideoclassification_b200 import video_models as vm
+    torch.manual_seed(0)
+    return vm.get_network(vm.default_opt("c3d"))
+
+
+def test_c3d_module_tree_and_init_match_reference(seeded_c3d):
+    gold = _load("c3d_state_dict_keys.json")
+    got = {k: list(v.shape) for k, v in seeded_c3d.state_dict().items()}
+    assert list(got.keys()) == list(gold.keys()) and got == gold        # conv1 .. conv5b, fc6, fc7, fc8, regressor
+    assert sum(v.numel() for v in seeded_c3d.parameters()) == 81_220_115
+    init = _load("c3d_init_seed0.json")
+    for k, v in seeded_c3d.state_dict().items():
+        c = checksum(v)
+        assert c["sum"] == init[k]["sum"] and c["abs"] == init[k]["abs"] and c["samples"] == init[k]["samples"], k
+
+
+def test_oracle_reproduces_reference_c3d_step(seeded_c3d):
+    """oracle.c3d_forward + autograd == network.C3D forward + backward (Dropout p = 0) on the same weights / clips:
+    every conv, pool and linear output, the embedding, the loss and every live gradient."""
+    gold = _load("c3d_step_bs2_16x112.json")
+    cfg = gold["config"]
+    sd = {k: v.detach().clone() for k, v in seeded_c3d.state_dict().items()}
+    x, z, _ = synthetic_batch(cfg["B"], cfg["T"], cfg["H"], cfg["W"], cfg["seed"] + 100)
+    trace = {}
+    emb, loss, grads = vo.c3d_train_step_grads(sd, x, z, trace=trace)
+    assert torch.allclose(emb, torch.tensor(gold["emb"]), atol=2e-5, rtol=1e-4)
+    assert _close(float(loss), gold["loss"], 1e-5)
+    assert len(gold["acts"]) == 15
+    for name, g in gold["acts"].items():
+        _check_sum(trace[name], g, 2e-4, name)
+    assert sorted(gold["grads"]) == sorted(grads.keys())
+    for name, g in gold["grads"].items():
+        _check_sum(grads[name], g, 2e-3, name)
+    assert gold["dead"] == ["fc7.bias", "fc7.weight", "fc8.bias", "fc8.weight"]
+    for name in gold["dead"]:
+        assert name not in grads
+
+
 def test_transform_oracle_matches_reference_transform():
     """oracle/transform_oracle.py == the reference's own transform functions (fixture from auxiliary/transforms.py)."""
     from oracle import transform_oracle as to
