@@ -26,9 +26,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION/INFO; stdout must carry exactly one JSON line
-if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("ZSV_KEEP_NCCL_DEBUG"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# NCCL's own log (NCCL_DEBUG=INFO/VERSION) is left alone: _capture_stdout() routes everything libraries print on fd 1
+# to stderr, so stdout still carries exactly one JSON line.
 
 _REAL_STDOUT = None
 
@@ -190,6 +189,150 @@ def run_reference(args):
                 "torch CPU kernels, all host threads",
     }
     emit(line)
+
+
+# ----------------------------------------------------------------------------------------------------
+# library arm: the reference's iteration on stock PyTorch (cuDNN / cuBLAS) on the same GPU -- the path to beat
+# ----------------------------------------------------------------------------------------------------
+def library_baseline(network: str, batch: int, steps: int, warmup: int, device):
+    from oracle import library_arm
+    return library_arm.run(network, batch, steps, warmup, device)
+
+
+def run_library(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    torch.cuda.set_device(0)
+    res = library_baseline(args.network, args.batch, args.steps, args.warmup, torch.device("cuda", 0))
+    best = res["variants"].get(res["best"], {}) if res["best"] else {}
+    emit({
+        "impl": "library", "metric": METRIC if "2plus1d" in args.network else f"{args.network} train clips/s (16x112^2, bf16)",
+        "value": res["clips_per_s"], "unit": "clips/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": best.get("ms_per_step"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if res["best"] and "bf16" in res["best"] else "fp16", "data": "synthetic",
+        "config": {"workload": f"{args.network} end-to-end training step bs={args.batch}, 16x112x112 synthetic clips, stock "
+                               f"PyTorch modules through cuDNN/cuBLAS (best of two variants: {res['best']})",
+                   "network": args.network, "per_gpu_batch": args.batch},
+        "library_baseline": res, "gpu_launches": 0,
+    })
+
+
+# ----------------------------------------------------------------------------------------------------
+# zero-shot evaluation workload (BASELINE.json configs[4]): 10k clip embeddings vs 101 / 51 / 200 class tables
+# ----------------------------------------------------------------------------------------------------
+def nearest_workload(dev, steps: int = 20, warmup: int = 3, n_rows: int = 10_000, k: int = 5):
+    """main.py:316-325's cdist + argsort[:, :5] for N = 10 000 embeddings against C in {101, 51, 200} class vectors
+    (UCF101 / HMDB51 / ActivityNet tables), D = 300.  Per C: device time of zsv_nearest_class with the inputs resident
+    (CUDA events around one call, L2 flushed before every call), the same call end to end from pinned HOST arrays
+    (H2D of both tables and D2H of the int64 indices inside the timed region), scipy on one host core (the
+    reference's own call), and the parity of the result (top-1 indices and top-5 sets) against it."""
+    import numpy as np
+    import torch
+    from scipy.spatial.distance import cdist
+    from zeroshotvideoclassification_b200 import _lib, ops
+
+    peaks = load_peaks()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # 2x the 126 MB L2
+    rng = np.random.default_rng(5)
+    out = {"rows": n_rows, "dim": 300, "k": k, "l2": "flushed (256 MB write) before every timed call", "tables": {}}
+    launches0 = _lib.launch_count()
+    for C in (101, 51, 200):
+        emb = rng.standard_normal((n_rows, 300)).astype(np.float32)
+        emb /= np.linalg.norm(emb, axis=1, keepdims=True)
+        cls = rng.standard_normal((C, 300)).astype(np.float32)
+        cls /= np.linalg.norm(cls, axis=1, keepdims=True)
+        emb_h, cls_h = torch.from_numpy(emb).pin_memory(), torch.from_numpy(cls).pin_memory()
+        idx_h = torch.empty((n_rows, k), dtype=torch.int64).pin_memory()
+        emb_d, cls_d = emb_h.to(dev), cls_h.to(dev)
+        dev_us, e2e_us = [], []
+        for i in range(warmup + steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            idx = ops.nearest_class(emb_d, cls_d, k)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= warmup:
+                dev_us.append(1e3 * e0.elapsed_time(e1))
+        for i in range(warmup + steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            idx = ops.nearest_class(emb_h.to(dev, non_blocking=True), cls_h.to(dev, non_blocking=True), k)
+            idx_h.copy_(idx, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= warmup:
+                e2e_us.append(1e3 * e0.elapsed_time(e1))
+        t0 = time.perf_counter()
+        d = cdist(emb, cls, "cosine")                      # main.py:321
+        top = d.argsort(1)[:, :k]                          # main.py:322-324
+        cpu_s = time.perf_counter() - t0
+        got = idx_h.numpy()
+        us, eus = statistics.median(dev_us), statistics.median(e2e_us)
+        alg_bytes = (n_rows + C) * 300 * 4 + n_rows * k * 8
+        out["tables"][str(C)] = {
+            "device_us": us, "device_us_best": min(dev_us), "gb_per_s": alg_bytes / us / 1e3,
+            "frac_of_hbm_peak": alg_bytes / us / 1e3 / peaks["hbm_gbs"], "algorithmic_bytes": alg_bytes,
+            "fp64_gflops": 2.0 * n_rows * C * 300 / us / 1e3,
+            "e2e_us": eus, "h2d_bytes": (n_rows + C) * 300 * 4, "d2h_bytes": n_rows * k * 8,
+            "cpu_scipy_s": cpu_s, "cpu_cores": 1, "speedup_e2e_vs_scipy": cpu_s * 1e6 / eus,
+            "top1_bit_equal": bool(np.array_equal(got[:, 0], d.argmin(1))),
+            "top5_sets_equal": bool(all(set(a) == set(b) for a, b in zip(got.tolist(), top.tolist()))),
+        }
+    out["gpu_launches"] = _lib.launch_count() - launches0
+    del flush
+    return out
+
+
+def run_nearest(args):
+    import torch
+    from zeroshotvideoclassification_b200 import _lib, build
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    build.build()
+    _lib.load()
+    torch.cuda.set_device(0)
+    res = nearest_workload(torch.device("cuda", 0), args.steps, max(args.warmup, 3))
+    t200 = res["tables"]["200"]
+    total_us = sum(t["device_us"] for t in res["tables"].values())
+    total_e2e = sum(t["e2e_us"] for t in res["tables"].values())
+    total_cpu = sum(t["cpu_scipy_s"] for t in res["tables"].values())
+    emit({
+        "metric": "zero-shot nearest-class search, 10k embeddings x {101,51,200} classes, top-5 (rows/s)",
+        "value": 3 * res["rows"] / (total_us / 1e6), "unit": "rows/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_us / 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[4]: 10k x 300 unit-norm embeddings vs 101/51/200-class tables, "
+                               "cosine distance (scipy cdist order, fp64) + 5 smallest per row", "l2": res["l2"]},
+        "roofline": {"bound": "hbm", "achieved": t200["gb_per_s"], "peak": load_peaks()["hbm_gbs"], "unit": "GB/s",
+                     "frac": t200["frac_of_hbm_peak"], "traffic": None,
+                     "note": "C=200 table; (N+C)*300*4 + N*5*8 algorithmic bytes; the kernel is bound by its sequential "
+                             "fp64 chains (scipy's summation order), not by HBM"},
+        "cpu_baseline": {"value": 3 * res["rows"] / total_cpu, "unit": "rows/s", "cores": 1, "kind": "reference",
+                         "sample": "scipy cdist(...,'cosine') + argsort, the reference's own call (main.py:321-324), all three tables"},
+        "e2e": {"value": 3 * res["rows"] / (total_e2e / 1e6), "unit": "rows/s",
+                "h2d_bytes_per_step": sum(t["h2d_bytes"] for t in res["tables"].values()),
+                "d2h_bytes_per_step": sum(t["d2h_bytes"] for t in res["tables"].values())},
+        "gpu_launches": res["gpu_launches"], "nearest": res,
+    })
+
+
+def subprocess_line(extra_args, timeout=600):
+    """Run this script again with other arguments (another network / workload) and return its JSON line."""
+    cmd = [sys.executable, os.path.abspath(__file__)] + extra_args
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout, env=env)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": f"rc {r.returncode}: {r.stderr[-300:]}"}
+    except Exception as exc:
+        return {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -369,11 +512,16 @@ def run_b200(args):
     peaks = load_peaks()
     # algorithmic conv FLOPs per clip of the profiled iteration (242.449 GFLOP for R(2+1)D-18)
     flop_per_clip = sum(v["flops"] for v in kinds.values()) / prof_steps / B if kinds else FLOP_PER_CLIP
+    # dram__bytes_read+write per launch of the same kernels, from the committed ncu capture -- only if that capture was
+    # taken from THIS build of the kernels (the file records the csrc fingerprint build.py stamps the library with)
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_conv_dram_traffic.json")
-    if os.path.exists(tpath) and "2plus1d" in args.network:       # dram__bytes_read+write per launch of the same kernels, from the committed ncu capture
+    tpath = os.path.join(ROOT, "profiles", "r02_conv_dram_traffic.json")
+    if os.path.exists(tpath) and "2plus1d" in args.network:
         tj = json.load(open(tpath))
-        traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/r01_conv_dram_traffic.json (ncu, per launch)"
+        if tj.get("build_fingerprint") == build._fingerprint():
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/r02_conv_dram_traffic.json (ncu, per launch, this build)"
+        else:
+            traffic_src = "profiles/r02_conv_dram_traffic.json is from another build of csrc/ (fingerprint differs): not reported"
     km = {k: {"ms_per_step": v["ms"] / prof_steps, "calls_per_step": v["calls"] / prof_steps,
               "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 else None,
               "share_of_step": (v["ms"] / prof_steps) / ms_per_step} for k, v in kinds.items()}
@@ -437,8 +585,31 @@ def run_b200(args):
     e2e = {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
            "ms_per_step": float(t.item()) / args.steps}
 
+    # ---- data-parallel correctness on the hardware (N > 1) ----
+    consistency = None
+    if world > 1:
+        consistency = replica_consistency(model, step, x_dev, z_dev, zdist, dist, dev, world)
+
     if rank != 0:
         return
+    extras = {}
+    if world == 1 and args.extras and "2plus1d" in args.network:
+        # free the step's captured pools before other workloads run on this GPU
+        gstep = None
+        torch.cuda.empty_cache()
+        extras["library_baseline"] = library_baseline(args.network, B, min(args.steps, 20), 3, dev)
+        lib = extras["library_baseline"].get("clips_per_s")
+        extras["speedup_vs_library"] = (e2e_value / lib) if lib else None
+        extras["nearest"] = nearest_workload(dev, 10, 3)
+        c3d = subprocess_line(["--network", "c3d", "--no-extras", "--no-cpu-baseline", "--library", "--steps",
+                               str(min(args.steps, 20)), "--warmup", "3"])
+        extras["c3d"] = {k: c3d.get(k) for k in ("metric", "value", "unit", "ms_per_step", "e2e", "roofline", "gpu_launches",
+                                                 "final_loss", "library_baseline", "speedup_vs_library", "error",
+                                                 "config") if k in c3d}
+    elif world == 1 and args.library:
+        extras["library_baseline"] = library_baseline(args.network, B, min(args.steps, 20), 3, dev)
+        lib = extras["library_baseline"].get("clips_per_s")
+        extras["speedup_vs_library"] = (e2e_value / lib) if lib else None
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cps, times, threads = cpu_reference_steps(20, 1, 2)      # ~10-12 s of host work on the GPU box's cores
@@ -466,7 +637,62 @@ def run_b200(args):
     }
     if sync is not None:
         line["allreduce_bytes_per_step"] = sync.bytes_per_step
+    if consistency is not None:
+        line["replicas_consistent"] = consistency["ok"]
+        line["replica_check"] = consistency
+    line.update(extras)
     emit(line)
+
+
+def replica_consistency(model, step, x_dev, z_dev, zdist, dist, dev, world):
+    """Two checks on the real N-GPU job (every rank calls this).
+    (1) Gradient exchange: on the same weights and each rank's own batch, the gradients the overlapped, bucketed
+        GradSync path leaves in param.grad must equal the mean over ranks of the purely local gradients (computed with
+        the exchange switched off, then averaged by ONE plain all-reduce of the whole flat vector).
+    (2) Replicas stay identical: after all the optimizer steps of this run, a checksum of every parameter has the same
+        value on every rank (all-reduce MIN == all-reduce MAX)."""
+    import torch
+    params = [p for p in model.parameters() if p.requires_grad]
+    saved = {id(p): p.detach().clone() for p in params}
+
+    def grads_of_one_backward():
+        for p in params:
+            p.grad = None
+        out = model(x_dev)
+        emb = out[0] if isinstance(out, tuple) else out
+        torch.nn.functional.mse_loss(emb, z_dev).backward()
+        live = [p for p in params if p.grad is not None]
+        return live, torch.cat([p.grad.detach().reshape(-1).float() for p in live])
+
+    sync = zdist.active_grad_sync()
+    zdist.set_grad_sync(None)
+    live, local = grads_of_one_backward()
+    dist.all_reduce(local, op=dist.ReduceOp.SUM)
+    local /= world
+    zdist.set_grad_sync(sync)
+    live2, _ = grads_of_one_backward()
+    head = list(model.output2emb_proj.parameters()) if hasattr(model, "output2emb_proj") else params
+    zdist.sync_head_grads(head)
+    synced = torch.cat([p.grad.detach().reshape(-1).float() for p in live2])
+    scale = float(local.abs().max())
+    err = float((synced - local).abs().max()) / max(scale, 1e-30)
+    with torch.no_grad():                       # the check must not advance training
+        for p in params:
+            p.copy_(saved[id(p)])
+            p.grad = None
+    chk = torch.stack([p.detach().double().sum() for p in params]).sum().reshape(1)
+    chk2 = torch.stack([p.detach().double().abs().sum() for p in params]).sum().reshape(1)
+    v = torch.cat([chk, chk2])
+    lo, hi = v.clone(), v.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    same = bool(torch.equal(lo, hi))
+    errt = torch.tensor([err], device=dev, dtype=torch.float64)
+    dist.all_reduce(errt, op=dist.ReduceOp.MAX)
+    err = float(errt.item())
+    return {"ok": same and err <= 1e-5, "param_checksums_equal_on_all_ranks": same,
+            "grad_sync_vs_mean_of_local_max_rel_err": err, "grad_tolerance": 1e-5, "gradients_compared": int(local.numel()),
+            "param_checksum": float(v[0].item())}
 
 
 def main():
@@ -474,7 +700,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "library"],
+                    help="b200: this repo; reference: the CPU arm (oracle port); library: stock PyTorch/cuDNN on the GPU")
+    ap.add_argument("--workload", default="train", choices=["train", "nearest"],
+                    help="train: the training step (headline); nearest: BASELINE.json configs[4], 10k x {101,51,200} top-5")
+    ap.add_argument("--no-extras", dest="extras", action="store_false",
+                    help="N=1 main line only: skip the library baseline, the nearest-class workload and the C3D line")
+    ap.add_argument("--library", action="store_true", help="also time the stock-PyTorch (cuDNN) arm of this network")
     ap.add_argument("--batch", type=int, default=22, help="clips per GPU (README.md:45)")
     ap.add_argument("--network", default="r2plus1d_18")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -490,6 +722,10 @@ def main():
     _capture_stdout()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "library":
+        run_library(args)
+    elif args.workload == "nearest":
+        run_nearest(args)
     else:
         run_b200(args)
     try:

@@ -107,6 +107,7 @@ class _Net:
             if y.requires_grad:
                 y.retain_grad()
             self.trace[name] = y
+            self.trace[name + ":in"] = x.detach()      # teacher-forced per-layer tests feed the kernels exactly this
         return y
 
     def bn(self, x: Tensor, name: str) -> Tensor:
@@ -243,6 +244,8 @@ def c3d_forward(sd: Dict[str, Tensor], x: Tensor, train: bool = False, emulate_b
         w = sd[name + ".weight"]
         if emulate_bf16:
             w = _RoundBf16Fwd.apply(w)
+        if trace is not None:
+            trace[name + ":in"] = t.detach()
         y = F.relu(keep(name, F.conv3d(t, w, sd[name + ".bias"], padding=1)))
         y = _RoundBf16Both.apply(y) if emulate_bf16 else y
         return keep(name + ":out", y)

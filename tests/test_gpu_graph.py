@@ -94,3 +94,42 @@ def test_prefetch_pipeline_matches_direct_calls():
             gb.prefetch(*pinned[i + 1])
         piped.append(float(loss))
     assert piped == direct
+
+
+def test_eval_after_graph_replays_sees_the_new_weights():
+    """evaluate() (main.py:224-257) after more training through graph replays must use the CURRENT weights and running
+    statistics: replays write them through raw pointers, which tensor version counters do not see, so the folded
+    inference weights are dropped on every replay (engine.note_weights_changed)."""
+    from zeroshotvideoclassification_b200.graph import GraphedStep
+    xs, zs = _data(2)
+    model, opt, step = _make()
+    gstep = GraphedStep(step, (xs[0], zs[0]), model=model, optimizer=opt)
+
+    def evaluate():
+        model.eval()
+        with torch.no_grad():
+            emb, _ = model(xs[2].cuda())
+        model.train()
+        return emb.clone()
+
+    gstep(xs[0], zs[0])
+    e1 = evaluate()
+    assert torch.equal(e1, evaluate())                    # cached folded weights: same answer
+    for x, z in zip(xs, zs):
+        gstep(x, z)                                       # replays only: no Python-side in-place op on any parameter
+    e2 = evaluate()
+    assert not torch.equal(e1, e2), "eval served stale folded weights after graph replays"
+    # and it is the answer a freshly folded model gives
+    from zeroshotvideoclassification_b200 import engine
+    engine.note_weights_changed()
+    assert torch.equal(e2, evaluate())
+
+
+def test_second_backward_through_the_backbone_raises():
+    model, _, _ = _make()
+    xs, zs = _data(2)
+    emb, _ = model(xs[0].cuda())
+    loss = F.mse_loss(emb, zs[0].cuda())
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="second time"):
+        loss.backward()

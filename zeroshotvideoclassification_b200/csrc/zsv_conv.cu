@@ -317,8 +317,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMa
                                               uint32_t bar_tmem_empty, int width, int n_origin, bool valid,
                                               long long off, int o0, int o1, int o2, int o3, int m_tile,
                                               bool keep_one_store_in_flight, int q, int half, int row, int lane,
-                                              int et, int srow_idx = -1) {
-    if (srow_idx < 0) srow_idx = row;   // row of the staging tile this thread writes (differs from its TMEM lane in lin mode)
+                                              int et) {
+    const int srow_idx = row;           // row of the staging tile this thread writes == its TMEM lane
     // Global operands of the tile (shortcut addend, BatchNorm input of the fused backward) do not depend on the
     // accumulator: pull this thread's row into L1 before the accumulator wait, so that the loads in emit_chunk hit
     // (waiting for them was the top stall of this kernel in the ncu source view).  Prefetching into REGISTERS instead
@@ -1091,258 +1091,6 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         tc_fence_after();
         if (k2) tmem_dealloc2(tmem_base, P.tmem_cols);
         else tmem_dealloc(tmem_base, P.tmem_cols);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Row-linearised implicit GEMM for stride-1 1x3x3 convolutions (fprop and dgrad).
-//
-// One TMA box per channel chunk carries the tile WITH its halo in both spatial dimensions: (bw+2) columns x (bh+2)
-// rows of one (t, n) plane, stored row after row (LW = bw+2 rows of shared memory per image line).  The GEMM-M index
-// enumerates that padded line layout, m = hl*LW + wl, so the input of filter tap (dh, dw) for ALL 128 M rows is the
-// same staged tile read from row offset dh*LW + dw: nine taps are nine descriptor start addresses, not nine loads
-// (a start address that is not a multiple of the 8-row swizzle atom is fine: the swizzle is a function of the
-// absolute shared-memory address, measured).  The price is M rows spent on the two halo columns of every line
-// (112 of 128 rows useful for bw = 14, bh = 8); the gain is 3x fewer activation bytes through TMA / L2 than the
-// W-shifted copies of igemm_halo_kernel and 9x fewer than the per-tap loads of igemm_kmajor_kernel.
-// Weights are resident (b_resident) when all taps fit beside the activation ring, otherwise streamed tap by tap
-// through their own ring.  Epilogue: the shared epilogue_tile with a dense staging row per valid output.
-// ------------------------------------------------------------------------------------------------
-struct LinArgs {
-    int32_t bw, bh, LW;          // tile: bw x bh outputs of one (t, n) plane; LW = bw + 2
-    int32_t W, H, T, N;          // extents (stride 1, "same" padding: output == input extents)
-    int32_t tw, th;              // tiles per plane
-    FastDiv fd_tw, fd_th, fd_T;
-    int32_t m_tiles;
-    int32_t kdim, nchunks, tail_steps, tail_box;
-    int32_t bn_tile, ncols, nbias, relu, part_pitch;
-    int32_t b_resident, nA, nB;
-    uint32_t a_stage_bytes, b_main_bytes, b_tail_bytes, b_total_bytes, staging_bytes;
-    int32_t scratch_bytes, tmem_cols;
-    int32_t org_w, org_h;        // halo origin relative to the tile origin (-1, -1)
-    int32_t a_off16[9];          // A start offset of each tap in 16-byte units
-    int32_t btap[9];             // weight tap index of each tap
-    long long os_w, os_h, os_t, os_n;   // output element strides
-    int32_t bn_relu, debug;
-    const __nv_bfloat16* addend;
-    const float* bias;
-    float* part_sum;
-    float* part_sq;
-    const __nv_bfloat16* bn_y;
-    const float4* bn_tab;
-    float* bn_partial;
-};
-
-__global__ void __launch_bounds__(kIgemmThreads, 1)
-igemm_lin_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                 const __grid_constant__ CUtensorMap mapBtail, const __grid_constant__ CUtensorMap mapOut,
-                 const __grid_constant__ LinArgs P) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t base = (raw + 1023u) & ~1023u;
-    uint8_t* smem = smem_raw + (base - raw);
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-
-    // layout: [resident B | B ring] [A ring] [staging] [scratch] [barriers]
-    const uint32_t bBytes = P.b_resident ? P.b_total_bytes : static_cast<uint32_t>(P.nB) * P.b_main_bytes;
-    const uint32_t ringAOff = bBytes;
-    const uint32_t stagingOff = ringAOff + static_cast<uint32_t>(P.nA) * P.a_stage_bytes;
-    const uint32_t statOff = stagingOff + P.staging_bytes;
-    const uint32_t barOff = statOff + static_cast<uint32_t>(P.scratch_bytes);
-    const uint32_t barFullA = base + barOff;
-    const uint32_t barEmptyA = barFullA + 8u * P.nA;
-    const uint32_t barFullB = barEmptyA + 8u * P.nA;       // nB entries (streamed), entry 0 doubles as the resident-B barrier
-    const uint32_t barEmptyB = barFullB + 8u * max(P.nB, 1);
-    const uint32_t barTmemFull = barEmptyB + 8u * max(P.nB, 1);
-    const uint32_t barTmemEmpty = barTmemFull + 16u;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + barOff + 16u * P.nA + 16u * max(P.nB, 1) + 32u);
-
-    if (warp == 0 && lane == 0) {
-        for (int i = 0; i < P.nA; ++i) {
-            mbar_init(barFullA + 8u * i, 1);
-            mbar_init(barEmptyA + 8u * i, 1);
-        }
-        for (int i = 0; i < max(P.nB, 1); ++i) {
-            mbar_init(barFullB + 8u * i, 1);
-            mbar_init(barEmptyB + 8u * i, 1);
-        }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(barTmemFull + 8u * i, 1);
-            mbar_init(barTmemEmpty + 8u * i, kEpiWarps);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), P.tmem_cols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t acc_stride = static_cast<uint32_t>(P.tmem_cols) >> 1;
-
-    const int nmain = (P.tail_box == 64) ? P.nchunks : P.nchunks - 1;
-    const uint32_t tail_row_bytes = static_cast<uint32_t>(P.tail_box) * 2u;
-    const uint32_t per_tap_bytes = nmain * P.b_main_bytes + (nmain < P.nchunks ? P.b_tail_bytes : 0u);
-    const int halo_rows = P.LW * (P.bh + 2);
-
-    if (warp == 0) {
-        const uint32_t leader = elect_one();
-        if (P.b_resident && leader) {
-            uint32_t btx = 0;
-            for (int c = 0; c < P.nchunks; ++c) btx += static_cast<uint32_t>(P.bn_tile) * (c < nmain ? 128u : tail_row_bytes);
-            mbar_expect_tx(barFullB, btx * 9u);
-            for (int tp = 0; tp < 9; ++tp)
-                for (int c = 0; c < P.nchunks; ++c) {
-                    const uint32_t dst = base + tp * per_tap_bytes + (c < nmain ? c * P.b_main_bytes : nmain * P.b_main_bytes);
-                    tma_load_3d(dst, c < nmain ? &mapB : &mapBtail, barFullB, c << 6, 0, tp);
-                }
-        }
-        __syncwarp();
-        uint32_t ia = 0, pa = 0, ib = 0, pb = 0;
-        const uint32_t txA = static_cast<uint32_t>(halo_rows) * 128u;
-        const uint32_t txB = static_cast<uint32_t>(P.bn_tile) * 128u;
-        for (int tile = blockIdx.x; tile < P.m_tiles; tile += gridDim.x) {
-            int m, m2, n_;
-            const int w0 = fdivmod(tile, P.fd_tw, m) * P.bw;
-            const int h0 = fdivmod(m, P.fd_th, m2) * P.bh;
-            const int t_ = fdivmod(m2, P.fd_T, n_);
-            for (int c = 0; c < P.nchunks; ++c) {
-                mbar_wait(barEmptyA + 8u * ia, pa ^ 1u);
-                if (leader) {
-                    mbar_expect_tx(barFullA + 8u * ia, txA);
-                    tma_load_5d(base + ringAOff + ia * P.a_stage_bytes, &mapA, barFullA + 8u * ia, c << 6, w0 + P.org_w,
-                                h0 + P.org_h, t_, n_);
-                }
-                __syncwarp();
-                if (++ia == static_cast<uint32_t>(P.nA)) ia = 0, pa ^= 1u;
-                if (!P.b_resident) {
-                    for (int tp = 0; tp < 9; ++tp) {
-                        mbar_wait(barEmptyB + 8u * ib, pb ^ 1u);
-                        if (leader) {
-                            mbar_expect_tx(barFullB + 8u * ib, txB);
-                            tma_load_3d(base + ib * P.b_main_bytes, &mapB, barFullB + 8u * ib, c << 6, 0, P.btap[tp]);
-                        }
-                        __syncwarp();
-                        if (++ib == static_cast<uint32_t>(P.nB)) ib = 0, pb ^= 1u;
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        const uint32_t leader = elect_one();
-        const uint32_t idesc = umma_idesc_bf16(128, P.bn_tile, 0, 0);
-        const uint32_t tail_layout = P.tail_box == 16 ? 6u : (P.tail_box == 32 ? 4u : 2u);
-        const uint32_t hi_main = umma_desc_hi(1024, 2);
-        const uint32_t hi_tailB = umma_desc_hi(tail_row_bytes * 8u, tail_layout);
-        const uint32_t tap_bytes16 = per_tap_bytes >> 4;
-        if (P.b_resident) {
-            mbar_wait(barFullB, 0);
-            tc_fence_after();
-        }
-        uint32_t ia = 0, pa = 0, ib = 0, pb = 0;
-        int local = 0;
-        for (int tile = blockIdx.x; tile < P.m_tiles; tile += gridDim.x, ++local) {
-            const uint32_t buf = local & 1;
-            mbar_wait(barTmemEmpty + 8u * buf, ((local >> 1) & 1u) ^ 1u);
-            tc_fence_after();
-            const uint32_t tacc = tmem_base + buf * acc_stride;
-            uint32_t acc = 0;
-            for (int c = 0; c < P.nchunks; ++c) {
-                const bool main_chunk = c < nmain;
-                const int ksteps = (c + 1 < P.nchunks) ? 4 : P.tail_steps;
-                // resident weights: the tail chunk is a narrow (SWIZZLE_32B / 64B) tile; streamed weights: always 128-byte rows
-                const uint32_t bhi = (P.b_resident && !main_chunk) ? hi_tailB : hi_main;
-                const uint32_t b_chunk_lo = umma_desc_lo(base + (main_chunk ? c * P.b_main_bytes : nmain * P.b_main_bytes));
-                mbar_wait(barFullA + 8u * ia, pa);
-                tc_fence_after();
-                const uint32_t a_base = umma_desc_lo(base + ringAOff + ia * P.a_stage_bytes);
-                for (int tp = 0; tp < 9; ++tp) {
-                    uint32_t b_lo;
-                    if (P.b_resident) {
-                        b_lo = b_chunk_lo + static_cast<uint32_t>(P.btap[tp]) * tap_bytes16;
-                    } else {
-                        mbar_wait(barFullB + 8u * ib, pb);
-                        tc_fence_after();
-                        b_lo = umma_desc_lo(base + ib * P.b_main_bytes);
-                    }
-                    if (leader) {
-                        const uint32_t a_lo = a_base + static_cast<uint32_t>(P.a_off16[tp]);
-                        umma_bf16_lohi(tacc, a_lo, hi_main, b_lo, bhi, idesc, acc);
-                        for (int k = 1; k < ksteps; ++k)
-                            umma_bf16_lohi(tacc, a_lo + 2u * k, hi_main, b_lo + 2u * k, bhi, idesc, 1u);
-                        if (!P.b_resident) umma_commit(barEmptyB + 8u * ib);
-                    }
-                    acc = 1;
-                    __syncwarp();
-                    if (!P.b_resident && ++ib == static_cast<uint32_t>(P.nB)) ib = 0, pb ^= 1u;
-                }
-                if (leader) umma_commit(barEmptyA + 8u * ia);
-                __syncwarp();
-                if (++ia == static_cast<uint32_t>(P.nA)) ia = 0, pa ^= 1u;
-            }
-            if (leader) umma_commit(barTmemFull + 8u * buf);
-            __syncwarp();
-        }
-    } else {
-        const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
-        const int row = q * 32 + lane;
-        const int hl = row / P.LW;
-        const int wl = row - hl * P.LW;
-        const int nvalid = P.bw * P.bh;
-        // dense staging row: valid outputs first (the TMA store box is bw x bh), the halo-column / overflow rows after them
-        const bool in_tile = hl < P.bh && wl < P.bw;
-        int srow;
-        if (in_tile) srow = hl * P.bw + wl;
-        else if (hl < P.bh) srow = nvalid + hl * 2 + (wl - P.bw);
-        else srow = nvalid + P.bh * 2 + (row - P.bh * P.LW);
-        const int et = threadIdx.x - 64;
-        EpiArgs E;
-        E.addend = P.addend, E.bias = P.bias, E.part_sum = P.part_sum, E.part_sq = P.part_sq;
-        E.ncols = P.ncols, E.nbias = P.nbias, E.relu = P.relu, E.part_pitch = P.part_pitch;
-        E.debug = P.debug;
-        E.remote_arrive = 0;
-        float* statbuf = reinterpret_cast<float*>(smem + statOff);
-        E.bn_y = P.bn_y, E.bn_tab = P.bn_tab, E.bn_relu = P.bn_relu;
-        E.bn_acc = statbuf;
-        E.st_acc = statbuf;
-        E.bn_scratch = statbuf + 2 * P.ncols;
-        if (P.bn_y != nullptr || P.part_sum != nullptr)
-            for (int i = et; i < 2 * P.ncols; i += kEpiWarps * 32) statbuf[i] = 0.f;
-        int local = 0;
-        for (int tile = blockIdx.x; tile < P.m_tiles; tile += gridDim.x, ++local) {
-            int m, m2, n_;
-            const int w0 = fdivmod(tile, P.fd_tw, m) * P.bw;
-            const int h0 = fdivmod(m, P.fd_th, m2) * P.bh;
-            const int t_ = fdivmod(m2, P.fd_T, n_);
-            const bool valid = in_tile && (w0 + wl) < P.W && (h0 + hl) < P.H;
-            const long long off = (long long)(w0 + wl) * P.os_w + (long long)(h0 + hl) * P.os_h + (long long)t_ * P.os_t +
-                                  (long long)n_ * P.os_n;
-            const uint32_t buf = local & 1;
-            E.bar_full = barTmemFull + 8u * buf, E.full_phase = (local >> 1) & 1u;
-            const uint32_t trow = tmem_base + buf * acc_stride + (static_cast<uint32_t>(q * 32) << 16);
-            epilogue_tile(E, &mapOut, smem + stagingOff, base + stagingOff, statbuf, trow, barTmemEmpty + 8u * buf, P.bn_tile,
-                          0, valid, off, w0, h0, t_, n_, tile, false, q, half, row, lane, et, srow);
-        }
-        if (et == 0) tma_store_wait_all();
-        if (P.bn_y != nullptr) {
-            named_bar_sync(1, kEpiWarps * 32);
-            for (int i = et; i < 2 * P.ncols; i += kEpiWarps * 32) {
-                const int qn = i >= P.ncols ? 1 : 0;
-                P.bn_partial[((long long)blockIdx.x * 4 + qn) * P.ncols + (i - qn * P.ncols)] = statbuf[i];
-            }
-        } else if (P.part_sum != nullptr) {
-            named_bar_sync(1, kEpiWarps * 32);
-            for (int i = et; i < 2 * P.ncols; i += kEpiWarps * 32) {
-                const int qn = i >= P.ncols ? 1 : 0;
-                (qn ? P.part_sq : P.part_sum)[(long long)blockIdx.x * P.part_pitch + (i - qn * P.ncols)] = statbuf[i];
-            }
-        }
-    }
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, P.tmem_cols);
     }
 }
 
@@ -2604,154 +2352,6 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
     return ZSV_OK;
 }
 
-// ---- row-linearised kernel planning -----------------------------------------------------------------
-struct LinPlan {
-    bool ok;
-    int bw, bh, LW, tw, th;
-    long long m_tiles;
-    int nchunks, tail_box, tail_steps, bn_tile, b_resident, nA, nB, scratch, smem, tmem_cols;
-    uint32_t a_stage_bytes, b_main_bytes, b_tail_bytes, b_total_bytes, staging_bytes;
-};
-
-// 1x3x3, stride 1, padding (0,1,1) on plain NDHWC tensors.  kdim = reduction channels, cols = output channels.
-// scratch_mode as in plan_halo.  `which`: 0 fprop, 1 dgrad (selects the enabling rule).
-LinPlan plan_lin(int W, int H, int T, int N, int kdim, int cols, int kt, int kh, int kw, int scratch_mode, int which) {
-    LinPlan p;
-    memset(&p, 0, sizeof(p));
-    // Opt-in (ZSV_LIN=1).  Measured on B200 (profiles/r01_lin_kernel_ab.txt): correct (the parity tests run it), but
-    // slower than the kernels it would replace on the layers that matter -- 64->144 fprop 243 vs 207 us, 144->64 dgrad
-    // 588 vs 290 us, 128->288 dgrad 145 vs 98 us; faster only on 128->230 dgrad (122 vs 174 us).  The activation bytes
-    // through TMA drop as intended, but the time of a tile is (TMA time) + (MMA operand time), not their maximum, and
-    // with the 162 KB resident weight image of 144->64 only two activation buffers fit, so every load latency is
-    // exposed.  Kept for the 2-CTA follow-up (split weights leave room for a deeper activation ring).
-    const char* e = getenv("ZSV_LIN");
-    if (!(e && atoi(e) == 1)) return p;
-    if (kt != 1 || kh != 3 || kw != 3) return p;
-    const int cols16 = (cols + 15) & ~15;
-    if (cols16 > 256) return p;
-    (void)which;
-    long long best = -1;
-    for (int bw = 1; bw <= std::min(W, 126); ++bw) {
-        const int LW = bw + 2;
-        const int bh = std::min(H, 128 / LW);
-        if (bh < 1) continue;
-        const long long tiles = (long long)ceil_div(W, bw) * ceil_div(H, bh);
-        if (best < 0 || tiles < best || (tiles == best && bw > p.bw)) {
-            best = tiles;
-            p.bw = bw, p.bh = bh, p.LW = LW;
-        }
-    }
-    if (best < 0) return p;
-    p.tw = ceil_div(W, p.bw), p.th = ceil_div(H, p.bh);
-    p.m_tiles = (long long)p.tw * p.th * T * N;
-    p.bn_tile = cols16;
-    p.tmem_cols = 2 * pow2_cols(p.bn_tile);
-    p.nchunks = ceil_div(kdim, 64);
-    const int tail = kdim - 64 * (p.nchunks - 1);
-    p.tail_steps = (tail + 15) >> 4;
-    p.a_stage_bytes = align1k((uint32_t)(2 * p.LW + 2 + 128) * 128u);
-    p.b_main_bytes = align1k((uint32_t)p.bn_tile * 128u);
-    p.staging_bytes = (uint32_t)((p.bn_tile + 63) / 64) * kPanelBytes;
-    p.scratch = scratch_mode == 2 ? bn_scratch_bytes(cpad(cols), p.bn_tile) : (scratch_mode == 1 ? bn_scratch_bytes(cpad(cols), 0) : 0);
-    const int fixed = 1024 + (int)p.staging_bytes + p.scratch + 512;
-    // resident weights: narrow tail tile like igemm_halo_kernel
-    const int tail_box_res = tail <= 16 ? 16 : (tail <= 32 ? 32 : 64);
-    const int nmain_res = tail_box_res == 64 ? p.nchunks : p.nchunks - 1;
-    const uint32_t b_tail_res = align1k((uint32_t)p.bn_tile * (uint32_t)tail_box_res * 2u);
-    const uint32_t b_total_res = 9u * (nmain_res * p.b_main_bytes + (nmain_res < p.nchunks ? b_tail_res : 0u));
-    const int budget = 226 * 1024;
-    if (fixed + (int)b_total_res + 2 * (int)p.a_stage_bytes <= budget) {
-        p.b_resident = 1;
-        p.tail_box = tail_box_res;
-        p.b_tail_bytes = b_tail_res;
-        p.b_total_bytes = b_total_res;
-        p.nA = std::min(4, (budget - fixed - (int)b_total_res) / (int)p.a_stage_bytes);
-        p.nB = 0;
-        p.smem = fixed + (int)b_total_res + p.nA * (int)p.a_stage_bytes;
-    } else {
-        p.b_resident = 0;
-        p.tail_box = 64;
-        p.b_tail_bytes = p.b_main_bytes;
-        p.b_total_bytes = 0;
-        p.nA = 2;
-        p.nB = std::min(8, (budget - fixed - 2 * (int)p.a_stage_bytes) / (int)p.b_main_bytes);
-        if (p.nB < 3) return p;
-        p.smem = fixed + 2 * (int)p.a_stage_bytes + p.nB * (int)p.b_main_bytes;
-    }
-    p.ok = true;
-    return p;
-}
-
-int lin_grid(const LinPlan& p) { return (int)std::min<long long>(p.m_tiles, sm_count()); }
-
-// act [N][T][H][W][actPitch] with actC reduction channels; wimg [9][wRows][wKpitch]; out [N][T][H][W][outPitch]
-int launch_lin(const LinPlan& p, bool dgrad, const void* act, int actC, int actPitch, const void* wimg, int wRows,
-               int wKpitch, void* out, int outPitch, int W, int H, int T, int N, const void* addend, float* part_sum,
-               float* part_sq, const float* bias, int nbias, int relu, cudaStream_t st, BnFuseLaunch* fuse) {
-    LinArgs a;
-    memset(&a, 0, sizeof(a));
-    a.bw = p.bw, a.bh = p.bh, a.LW = p.LW, a.W = W, a.H = H, a.T = T, a.N = N, a.tw = p.tw, a.th = p.th;
-    a.fd_tw = make_fastdiv(p.tw), a.fd_th = make_fastdiv(p.th), a.fd_T = make_fastdiv(T);
-    a.m_tiles = (int)p.m_tiles;
-    a.kdim = actC, a.nchunks = p.nchunks, a.tail_steps = p.tail_steps, a.tail_box = p.tail_box;
-    a.bn_tile = p.bn_tile, a.ncols = outPitch, a.nbias = nbias, a.relu = relu, a.part_pitch = outPitch;
-    a.b_resident = p.b_resident, a.nA = p.nA, a.nB = p.nB;
-    a.a_stage_bytes = p.a_stage_bytes, a.b_main_bytes = p.b_main_bytes, a.b_tail_bytes = p.b_tail_bytes;
-    a.b_total_bytes = p.b_total_bytes, a.staging_bytes = p.staging_bytes;
-    a.scratch_bytes = p.scratch, a.tmem_cols = p.tmem_cols;
-    a.org_w = -1, a.org_h = -1;
-    for (int jh = 0; jh < 3; ++jh)
-        for (int jw = 0; jw < 3; ++jw) {
-            const int tp = jh * 3 + jw;
-            const int rows = dgrad ? (2 - jh) * p.LW + (2 - jw) : jh * p.LW + jw;
-            a.a_off16[tp] = rows * 8;
-            a.btap[tp] = tp;
-        }
-    a.os_w = outPitch, a.os_h = (long long)outPitch * W, a.os_t = a.os_h * H, a.os_n = a.os_t * T;
-    a.addend = (const __nv_bfloat16*)addend, a.bias = bias, a.part_sum = part_sum, a.part_sq = part_sq;
-    if (const char* e = getenv("ZSV_DEBUG_EPI")) a.debug = atoi(e);
-    if (a.tmem_cols > 512) return fail(ZSV_ERR_UNSUPPORTED, "lin igemm: N tile too wide");
-    const int grid = lin_grid(p);
-    if (fuse) {
-        if (p.scratch < bn_scratch_bytes(a.ncols, p.bn_tile)) return fail(ZSV_ERR_UNSUPPORTED, "lin plan without BN-fusion scratch");
-        if (fuse->rows_used + grid > fuse->capacity)
-            return fail(ZSV_ERR_WORKSPACE, "dgrad: BN-fusion partial buffer holds %d rows, need %d", fuse->capacity,
-                        fuse->rows_used + grid);
-        a.bn_y = fuse->y, a.bn_tab = fuse->tab, a.bn_relu = fuse->relu;
-        a.bn_partial = fuse->partial + (size_t)fuse->rows_used * 4 * a.ncols;
-        fuse->rows_used += grid;
-    } else if (part_sum != nullptr && p.scratch < bn_scratch_bytes(a.ncols, 0)) {
-        return fail(ZSV_ERR_UNSUPPORTED, "lin plan without statistics scratch");
-    }
-    CUtensorMap mA, mB, mBt, mO;
-    int rc = make_plain_map(&mA, act, N, T, H, W, actC, actPitch, Box{p.LW, p.bh + 2, 1, 1});
-    if (rc) return rc;
-    rc = make_plain_map(&mO, out, N, T, H, W, outPitch, outPitch, Box{p.bw, p.bh, 1, 1});
-    if (rc) return rc;
-    {
-        uint64_t dims[3] = {(uint64_t)actC, (uint64_t)wRows, 9};
-        uint64_t str[2] = {(uint64_t)wKpitch * 2, (uint64_t)wKpitch * 2 * wRows};
-        uint32_t box[3] = {64, (uint32_t)p.bn_tile, 1};
-        rc = make_map(&mB, wimg, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc) return rc;
-        const CUtensorMapSwizzle tail_sw = p.tail_box == 16 ? CU_TENSOR_MAP_SWIZZLE_32B
-                                         : (p.tail_box == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
-        box[0] = (uint32_t)p.tail_box;
-        rc = make_map(&mBt, wimg, 3, dims, str, box, tail_sw);
-        if (rc) return rc;
-    }
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(igemm_lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    });
-    if (attr_err != cudaSuccess)
-        return fail(ZSV_ERR_CUDA, "cudaFuncSetAttribute(lin igemm) failed: %s", cudaGetErrorString(attr_err));
-    igemm_lin_kernel<<<grid, kIgemmThreads, p.smem, st>>>(mA, mB, mBt, mO, a);
-    ZSV_LAUNCH_CHECK("igemm_lin_kernel");
-    return ZSV_OK;
-}
-
 }  // namespace
 }  // namespace zsv
 
@@ -2884,8 +2484,6 @@ extern "C" int zsv_conv3d_stat_rows(const zsv_conv_desc* d) {
     if (check_desc(d, &s)) return -1;
     // one partial row per CTA of the (persistent) fprop kernel; which kernel runs depends on the geometry
     if (!s.wfold && d->st == 1 && d->sh == 1 && d->sw == 1 && s.To == d->T && s.Ho == d->H && s.Wo == d->W) {
-        const LinPlan lp = plan_lin(d->W, d->H, d->T, d->N, d->Cin, d->Cout, d->kt, d->kh, d->kw, 1, 0);
-        if (lp.ok) return lin_grid(lp);
         const HaloPlan hp = plan_halo(d->W, d->H, d->T, d->N, d->Cin, d->Cout, d->kt, d->kh, d->kw, 1);
         if (hp.ok) return halo_grid(hp);
     }
@@ -2905,10 +2503,6 @@ extern "C" int zsv_conv3d_fprop(const zsv_conv_desc* d, const void* x, const voi
     if ((part_sum == nullptr) != (part_sq == nullptr)) return fail(ZSV_ERR_BAD_ARG, "fprop: need both stat buffers");
 
     if (!s.wfold && d->st == 1 && d->sh == 1 && d->sw == 1 && s.To == d->T && s.Ho == d->H && s.Wo == d->W) {
-        const LinPlan lp = plan_lin(d->W, d->H, d->T, d->N, d->Cin, d->Cout, d->kt, d->kh, d->kw, part_sum ? 1 : 0, 0);
-        if (lp.ok && d->ph == 1 && d->pw == 1)
-            return launch_lin(lp, false, x, d->Cin, s.cinp, w_fprop, d->Cout, s.kpitch, y, s.coutp, d->W, d->H, d->T, d->N,
-                              addend, part_sum, part_sq, bias, bias ? d->Cout : 0, relu, (cudaStream_t)stream, nullptr);
         const HaloPlan hp = plan_halo(d->W, d->H, d->T, d->N, d->Cin, d->Cout, d->kt, d->kh, d->kw, part_sum ? 1 : 0);
         if (hp.ok) {
             // tap(cp, sh) = sh*kw + cp (spatial) or sh (temporal)
@@ -2989,13 +2583,6 @@ extern "C" int zsv_conv3d_dgrad(const zsv_conv_desc* d, const void* dy, const vo
     }
 
     if (d->st == 1 && d->sh == 1 && d->sw == 1 && s.To == d->T && s.Ho == d->H && s.Wo == d->W) {
-        const LinPlan lp = plan_lin(d->W, d->H, d->T, d->N, d->Cout, d->Cin, d->kt, d->kh, d->kw, fuse != nullptr ? 2 : 0, 1);
-        if (lp.ok && d->ph == 1 && d->pw == 1) {
-            rc = launch_lin(lp, true, dy, d->Cout, s.coutp, w_dgrad, d->Cin, s.coutp, dx, s.cinp, d->W, d->H, d->T, d->N,
-                            addend, nullptr, nullptr, nullptr, 0, 0, st, fuse);
-            if (fuse) bnf->rows_written = fuse->rows_used;
-            return rc;
-        }
         const HaloPlan hp = plan_halo(d->W, d->H, d->T, d->N, d->Cout, d->Cin, d->kt, d->kh, d->kw, fuse != nullptr ? 2 : 0);
         if (hp.ok) {
             // dx[i] = sum_j dy[i + p - j] w[j]: copy j reads dy at W offset p - j; along the shift dim the halo starts

@@ -176,6 +176,14 @@ def _network_plan(N, T, H, W, need_grad: bool, arch: str = "r2plus1d_18"):
 _eval_pack_cache: Dict[tuple, tuple] = {}
 
 
+def note_weights_changed() -> None:
+    """Drop the folded inference weights.  Tensor version counters do not see writes made through raw pointers
+    (zsv_bn_finalize updates running_mean / running_var, zsv_adam_step the parameters, a CUDA-graph replay does both
+    without running any Python), so every such site calls this: a training-mode forward, FusedAdam.step and
+    GraphedStep.__call__.  Re-folding is one launch per evaluate() (main.py:224-257)."""
+    _eval_pack_cache.clear()
+
+
 def _folded_weights(tensors: Dict[str, torch.Tensor], names, specs, plan, key):
     """bf16 weight images with the inference-time BatchNorm folded in, plus the per-channel biases.  evaluate()
     (main.py:224-257) runs many batches on fixed weights, so the result is cached until a parameter or a running
@@ -280,6 +288,8 @@ class BackboneRunner:
         names, plan = _network_plan(N, T, H, W, self.need_grad, self.arch)
         if not self.train and not self.need_grad:
             return self._forward_folded(folded, (N, T, H, W), names, plan)
+        if self.train:
+            note_weights_changed()       # this forward rewrites the running statistics through raw pointers
         wfs, wds = plan.pack([self.t[n + ".weight"] for n in names])
         self.packed = {n: (wf, wd) for n, wf, wd in zip(names, wfs, wds)}
         s0 = self.stem_specs[0]
@@ -477,6 +487,7 @@ class _BackboneFn(torch.autograd.Function):
         runner = BackboneRunner(tensors, train=module.training, need_grad=need_grad, arch=arch)
         feats = runner.forward(x)
         ctx.runner = runner if need_grad else None
+        ctx.consumed = False
         ctx.names = names
         ctx.want = {n: ctx.needs_input_grad[2 + i] for i, n in enumerate(names)}
         ctx.param_meta = [(p.dtype, p.shape) for p in params]
@@ -485,9 +496,14 @@ class _BackboneFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         if ctx.runner is None:
+            if ctx.consumed:
+                raise RuntimeError("backbone backward called a second time: the activation tape of this forward was "
+                                   "released by the first backward (retain_graph is not supported on this path; "
+                                   "the reference back-propagates once per iteration, main.py:195)")
             return (None, None) + tuple(None for _ in ctx.names)
         grads = ctx.runner.backward(g, ctx.want)
         ctx.runner = None
+        ctx.consumed = True
         out = []
         for n, (dt, shape) in zip(ctx.names, ctx.param_meta):
             gr = grads.get(n) if ctx.want[n] else None

@@ -134,8 +134,7 @@ class GraphedStep:
                 s.copy_(st, non_blocking=True)
             self._staging_free.record(cur)
             self._has_prefetch = False
-            self.graph.replay()
-            self.replays += 1
+            self._replay()
             return self.static_outputs
         if len(inputs) != len(self.static_inputs):
             raise RuntimeError(f"GraphedStep: expected {len(self.static_inputs)} inputs, got {len(inputs)}")
@@ -147,6 +146,11 @@ class GraphedStep:
         for s, t in zip(self.static_inputs, inputs):
             if t is not s:
                 s.copy_(t, non_blocking=True)
+        self._replay()
+        return self.static_outputs
+
+    def _replay(self) -> None:
+        from . import engine
+        engine.note_weights_changed()    # a replay rewrites parameters / running statistics without any Python running
         self.graph.replay()
         self.replays += 1
-        return self.static_outputs

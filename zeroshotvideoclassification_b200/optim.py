@@ -28,6 +28,8 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         lib = _lib.load()
+        from . import engine
+        engine.note_weights_changed()        # parameters are written through raw pointers (no version-counter bump)
         for gi, group in enumerate(self.param_groups):
             ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
