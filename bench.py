@@ -364,8 +364,10 @@ def run_b200(args):
     criterion = torch.nn.MSELoss().to(dev)
     # main.py:131's torch.optim.Adam; capturable keeps its step counter on the device so the iteration can be graphed
     if args.optimizer == "zsv":
+        # main.py:131's Adam on the C ABI: same update rule and state layout; the convolution weights' bf16 images for
+        # the next iteration come out of the same pass (zsv_adam_pack_step), step counters and lr live on the device
         from zeroshotvideoclassification_b200.optim import FusedAdam
-        optimizer = FusedAdam(model.parameters(), lr=1e-3)
+        optimizer = FusedAdam(model.parameters(), lr=1e-3, model=model)
     else:
         optimizer = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=args.graph, fused=True)
     sync = zdist.GradSync(bucket_bytes=int(float(os.environ.get("ZSV_BUCKET_MB", "32")) * (1 << 20))) if world > 1 else None
@@ -630,7 +632,8 @@ def run_b200(args):
                    "parallelism": f"dp{world}" if world > 1 else "single",
                    "l2": "per-step working set (~6 GB of activations) is far larger than the 126 MB L2; no flush needed",
                    "loss_scaling": "none (bf16)", "weights": "random init (resnet.py:226-236)",
-                   "launch": graph_note, "optimizer": ("zsv FusedAdam (zsv_adam_step)" if args.optimizer == "zsv"
+                   "launch": graph_note, "optimizer": ("zsv FusedAdam: torch.optim.Adam's update rule (main.py:131) fused with the bf16 "
+                                 "weight re-pack (zsv_adam_pack_step)" if args.optimizer == "zsv"
                                  else "torch.optim.Adam(fused=True) (main.py:131)")},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "final_loss": final_loss, "host_enqueue_ms_per_step": host_ms_per_step,
@@ -710,8 +713,9 @@ def main():
     ap.add_argument("--batch", type=int, default=22, help="clips per GPU (README.md:45)")
     ap.add_argument("--network", default="r2plus1d_18")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--optimizer", default="torch", choices=["torch", "zsv"],
-                    help="torch.optim.Adam (the reference's, default) or the C-ABI multi-tensor Adam")
+    ap.add_argument("--optimizer", default="zsv", choices=["torch", "zsv"],
+                    help="zsv: FusedAdam on the C ABI, Adam + bf16 weight re-pack in one pass (default); "
+                         "torch: torch.optim.Adam(fused=True), the reference's optimizer object unchanged")
     ap.add_argument("--layer-table", action="store_true", help="print a per-layer conv timing table to stderr")
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="enqueue every iteration kernel by kernel instead of replaying one CUDA graph")

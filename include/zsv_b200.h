@@ -142,8 +142,10 @@ int zsv_conv3d_wgrad(const zsv_conv_desc* d, const void* x, const void* dy, floa
 size_t zsv_bias_grad_workspace(int C);
 int zsv_bias_grad(const void* dy, float* db, long long rows, int C, void* workspace, size_t workspace_bytes,
                   void* stream);
-/* ReLU backward on channels-last bf16: dz = g * [out > 0] (C3D conv+bias+ReLU, network.py:147-162). */
-int zsv_relu_bwd(const void* g, const void* out, void* dz, long long rows, int C, void* stream);
+/* ReLU backward on channels-last bf16: dz = g * [out > 0] (C3D conv+bias+ReLU, network.py:147-162).  bias_grad (optional,
+ * fp32 [C]): the bias gradient sum over the rows of dz, taken in the same pass (workspace: zsv_bias_grad_workspace(C)). */
+int zsv_relu_bwd(const void* g, const void* out, void* dz, long long rows, int C, float* bias_grad, void* workspace,
+                 size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Layout conversion at the PyTorch boundary.
@@ -220,16 +222,23 @@ int zsv_bn_bwd_finish(const void* dz, const void* y, const float* mean, const fl
 int zsv_head_fwd(const void* feat, int B, int P, int C, const float* w1, const float* b1, int Hd, const float* w2,
                  const float* b2, int E, float eps, float* pooled, float* hidden, float* onorm, float* emb,
                  void* stream);
-/* Backward given demb [B][E]; grads for w1,b1,w2,b2 (fp32, overwritten) and dfeat (bf16 [B][P][cpad(C)]). */
+/* Backward given demb [B][E]; grads for w1,b1,w2,b2 (fp32, overwritten) and dfeat (bf16 [B][P][cpad(C)]).
+ * scratch: zsv_head_bwd_scratch(B, C, Hd, E) bytes. */
+size_t zsv_head_bwd_scratch(int B, int C, int Hd, int E);
 int zsv_head_bwd(const float* demb, const float* emb, const float* onorm, const float* pooled, const float* hidden,
                  int B, int P, int C, const float* w1, int Hd, const float* w2, int E, float eps, float* dw1,
-                 float* db1, float* dw2, float* db2, void* dfeat, float* scratch, void* stream);
-/* Plain fp32 Linear (C3D fc6 / regressor, network.py:120,132,166,178): out = act(x W^T + b), weight-streaming.
- * Backward: optional ReLU mask from the forward output `act` (needs scratch [B][J]); dx, dw, db optional. */
+                 float* db1, float* dw2, float* db2, void* dfeat, float* scratch, size_t scratch_bytes, void* stream);
+/* Plain fp32 Linear (C3D fc6 / regressor, network.py:120,132,166,178): out = act(x W^T + b) with W [J][K] in the
+ * state_dict layout.  Weight-streaming: every pass reads W once (per 24 batch rows); reductions that are split over
+ * thread blocks are combined in a fixed order through the workspace (zsv_linear_workspace(B, K, J) bytes; forward
+ * accepts NULL and then does not split).
+ * Backward: `act` (optional) is the forward OUTPUT of a layer that ended in ReLU, its mask is applied to dy first;
+ * dx, dw, db are each optional. */
+size_t zsv_linear_workspace(int B, int K, int J);
 int zsv_linear_fwd(const float* x, const float* w, const float* bias, float* out, int B, int K, int J, int relu,
-                   void* stream);
+                   void* workspace, size_t workspace_bytes, void* stream);
 int zsv_linear_bwd(const float* dy, const float* x, const float* w, const float* act, int B, int K, int J, float* dx,
-                   float* dw, float* db, float* scratch, void* stream);
+                   float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream);
 /* F.normalize(dim=-1) forward / backward (network.py:179, network.py:596). */
 int zsv_l2norm_fwd(const float* o, float* emb, float* onorm, int B, int E, float eps, void* stream);
 int zsv_l2norm_bwd(const float* demb, const float* emb, const float* onorm, float* dout, int B, int E, float eps,
@@ -239,13 +248,30 @@ int zsv_l2norm_bwd(const float* demb, const float* emb, const float* onorm, floa
 int zsv_mse_fwd_bwd(const float* emb, const float* target, int B, int E, float grad_scale, float* loss, float* demb,
                     void* stream);
 
-/* Multi-tensor Adam with torch.optim.Adam semantics (main.py:131,203; no amsgrad): n parameter tensors in one launch
- * per 72 tensors.  params / grads / exp_avg / exp_avg_sq / numel are HOST arrays of device pointers and sizes;
- * `step` is a DEVICE float holding t, the 1-based step count of THIS update (the caller increments it on the
- * stream beforehand), which keeps the update CUDA-graph capturable.  weight_decay is added to the gradient (L2). */
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer step (main.py:131,200-203: torch.optim.Adam, no amsgrad), multi-tensor, CUDA-graph capturable.
+ *   g' = g*grad_scale + weight_decay*p ; m += (1-beta1)*(g'-m) ; v = beta2*v + (1-beta2)*g'^2 ;
+ *   p -= lr/(1-beta1^t) * m / (sqrt(v)/sqrt(1-beta2^t) + eps)
+ * params / grads / exp_avg / exp_avg_sq / steps (/ numel) are HOST arrays of device pointers (sizes); steps[i] is a
+ * DEVICE float holding t, the 1-based count of THIS update of tensor i (the caller increments it on the stream
+ * beforehand).  lr_dev (optional) is a DEVICE float read at run time instead of `lr`, so that a learning-rate
+ * schedule (main.py:133,374) reaches the replays of a captured graph.  grad_scale folds the 1/world of a summed
+ * all-reduce or the 1/scale of a GradScaler (main.py:195-203) into the update; 1 = none.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct zsv_adam_hyper {
+    float lr, beta1, beta2, eps, weight_decay, grad_scale;
+    const float* lr_dev;
+} zsv_adam_hyper;
 int zsv_adam_step(int n, float* const* params, const float* const* grads, float* const* exp_avg,
-                  float* const* exp_avg_sq, const long long* numel, const float* step, float lr, float beta1,
-                  float beta2, float eps, float weight_decay, void* stream);
+                  float* const* exp_avg_sq, const long long* numel, const float* const* steps,
+                  const zsv_adam_hyper* hyper, void* stream);
+/* The same update for n convolution weights [Cout][Cin][kt][kh][kw] (descs[i]: only Cin, Cout, kt, kh, kw are read;
+ * x_layout must be ZSV_CONV_X_NDHWC), FUSED with the bf16 re-pack the next forward / backward needs: the updated weights
+ * are written as the fprop image w_fprop[i] and the dgrad image w_dgrad[i] (either may be NULL) of
+ * zsv_conv3d_packed_weight_bytes -- the separate zsv_conv3d_pack_weights pass over the fp32 masters disappears. */
+int zsv_adam_pack_step(int n, const zsv_conv_desc* descs, float* const* params, const float* const* grads,
+                       float* const* exp_avg, float* const* exp_avg_sq, const float* const* steps,
+                       void* const* w_fprop, void* const* w_dgrad, const zsv_adam_hyper* hyper, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Zero-shot nearest-class search (main.py:183, main.py:321-322: scipy cdist(...,'cosine') then
@@ -257,13 +283,17 @@ int zsv_nearest_class(const float* emb, const float* cls, int N, int C, int D, i
 
 /* ------------------------------------------------------------------------------------------------
  * MaxPool3d for C3D (network.py:103-118): kernel == stride, optional H/W padding with -inf.
+ * argmax: one byte per output element (index of the selected position inside its window).
  * ---------------------------------------------------------------------------------------------- */
-int zsv_maxpool3d_fwd(const void* x, void* y, int32_t* argmax, int N, int T, int H, int W, int C, int kt, int kh,
+int zsv_maxpool3d_fwd(const void* x, void* y, uint8_t* argmax, int N, int T, int H, int W, int C, int kt, int kh,
                       int kw, int pt, int ph, int pw, void* stream);
-/* relu_mask_src (optional): the pooled tensor itself (a ReLU output); positions where it is <= 0 get no gradient,
- * which fuses the ReLU backward of network.py:147-162 into the pooling backward. */
-int zsv_maxpool3d_bwd(const void* dy, const int32_t* argmax, const void* relu_mask_src, void* dx, int N, int T, int H,
-                      int W, int C, int kt, int kh, int kw, int pt, int ph, int pw, void* stream);
+/* relu_pooled (optional): the pooling OUTPUT y when the pooled tensor was a ReLU output (network.py:147-162): the
+ * selected element equals y, so dy * [y > 0] is the ReLU backward of that element and the larger input is not re-read.
+ * bias_grad (optional, fp32 [C]): sum over all positions of the gradient written to dx (the bias gradient of the
+ * convolution in front of the ReLU), taken in the same pass; workspace: zsv_bias_grad_workspace(C) bytes. */
+int zsv_maxpool3d_bwd(const void* dy, const uint8_t* argmax, const void* relu_pooled, void* dx, int N, int T, int H,
+                      int W, int C, int kt, int kh, int kw, int pt, int ph, int pw, float* bias_grad, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -197,6 +197,68 @@ def test_maxpool_forward_backward():
         assert torch.equal(from_ndhwc(y, C), ref.detach())
         dx = ops.maxpool3d_bwd(to_ndhwc(dy), am, tuple(to_ndhwc(x).shape), C, k, p)
         assert torch.equal(from_ndhwc(dx, C), xr.grad)
+        assert am.dtype == torch.uint8
+
+
+def test_pool_and_relu_backward_with_fused_bias_gradient():
+    """C3D backward of conv+bias -> ReLU [-> MaxPool3d] (network.py:147-163): the pooling backward takes the ReLU mask
+    from the POOLED tensor and emits the bias gradient (column sums of dz) in the same pass; likewise zsv_relu_bwd."""
+    from zeroshotvideoclassification_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    for (shape, k, p) in (((2, 64, 4, 8, 8), (1, 2, 2), (0, 0, 0)), ((3, 128, 4, 8, 6), (2, 2, 2), (0, 0, 0)),
+                          ((2, 512, 2, 7, 7), (2, 2, 2), (0, 1, 1)), ((1, 24, 2, 4, 4), (2, 2, 2), (0, 0, 0))):
+        pre = bf16_round(torch.randn(*shape, generator=g))
+        pre[:, :, :, :2, :2] = -pre[:, :, :, :2, :2].abs()          # some windows are all-negative: pooled value 0
+        xr = pre.clone().requires_grad_(True)
+        act = F.relu(xr)
+        ref = F.max_pool3d(act, k, k, padding=p)
+        dy = bf16_round(torch.randn(ref.shape, generator=g))
+        ref.backward(dy)
+        C = shape[1]
+        a = to_ndhwc(act.detach())
+        y, am = ops.maxpool3d_fwd(a, C, k, p)
+        dz, db = ops.maxpool3d_bwd(to_ndhwc(dy), am, tuple(a.shape), C, k, p, relu_pooled=y, want_bias=True)
+        torch.cuda.synchronize()
+        got = from_ndhwc(dz, C)
+        # where a window is all zeros after the ReLU, torch sends dy to its first element and the ReLU backward then
+        # zeroes it: same result, dz = 0
+        assert torch.equal(got, xr.grad), (shape, float((got - xr.grad).abs().max()))
+        assert rel_err(db.cpu(), xr.grad.sum((0, 2, 3, 4))) < 1e-5
+        # plain ReLU backward with the bias gradient
+        xr2 = pre.clone().requires_grad_(True)
+        out = F.relu(xr2)
+        gy = bf16_round(torch.randn(shape, generator=g))
+        out.backward(gy)
+        dz2, db2 = ops.relu_bwd(to_ndhwc(gy), to_ndhwc(out.detach()), C, want_bias=True)
+        assert torch.equal(from_ndhwc(dz2, C), xr2.grad)
+        assert rel_err(db2.cpu(), xr2.grad.sum((0, 2, 3, 4))) < 1e-5
+        assert torch.equal(from_ndhwc(ops.relu_bwd(to_ndhwc(gy), to_ndhwc(out.detach()), C), C), xr2.grad)
+
+
+@pytest.mark.parametrize("B,K,J", [(22, 8192, 4096), (22, 4096, 300), (22, 512, 512), (5, 512, 300), (1, 37, 5),
+                                   (30, 1030, 77), (50, 256, 64)])
+def test_linear_forward_backward(B, K, J):
+    """zsv_linear_fwd / zsv_linear_bwd (C3D fc6 / regressor, network.py:120,132,166,178; the MLP head's layers) vs
+    torch on the CPU: full C3D sizes, odd sizes (scalar path), more rows than one 24-row pass."""
+    from zeroshotvideoclassification_b200 import ops
+    g = torch.Generator().manual_seed(B * 7 + J)
+    x = torch.randn(B, K, generator=g)
+    w = torch.randn(J, K, generator=g) / K ** 0.5
+    b = torch.randn(J, generator=g)
+    dy = torch.randn(B, J, generator=g)
+    for relu in (False, True):
+        xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+        ref = F.linear(xr, wr, br)
+        if relu:
+            ref = F.relu(ref)
+        ref.backward(dy)
+        out = ops.linear_fwd(x.cuda(), w.cuda(), b.cuda(), relu)
+        dx, dw, db = ops.linear_bwd(dy.cuda(), x.cuda(), w.cuda(), out if relu else None)
+        torch.cuda.synchronize()
+        assert rel_err(out.cpu(), ref.detach()) < 2e-5
+        assert rel_err(dx.cpu(), xr.grad) < 2e-5
+        assert rel_err(dw.cpu(), wr.grad) < 2e-5
+        assert rel_err(db.cpu(), br.grad) < 2e-5
 
 
 def test_clip_transform_matches_oracle_and_feeds_the_model():
@@ -261,3 +323,79 @@ def test_fused_adam_matches_torch_adam():
         sd = o_mine.state_dict()
         assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 5.0
         o_ref.load_state_dict(sd)          # same state layout as torch.optim.Adam
+
+
+def test_fused_adam_lr_schedule_and_late_parameters():
+    """The learning rate is read from a device scalar that follows group['lr'] (main.py:133,374: MultiStepLR), and every
+    tensor has its own step counter: a parameter that starts receiving gradients later gets its own bias correction."""
+    from zeroshotvideoclassification_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(4)
+    ref = [torch.nn.Parameter(torch.randn(33, 7, generator=g).cuda()), torch.nn.Parameter(torch.randn(129, generator=g).cuda())]
+    mine = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    o_ref, o_mine = torch.optim.Adam(ref, lr=1e-2), FusedAdam(mine, lr=1e-2)
+    s_ref = torch.optim.lr_scheduler.MultiStepLR(o_ref, [2, 4], gamma=0.1)
+    s_mine = torch.optim.lr_scheduler.MultiStepLR(o_mine, [2, 4], gamma=0.1)
+    for it in range(6):
+        for i, (a, b) in enumerate(zip(ref, mine)):
+            if i == 1 and it < 2:
+                a.grad = b.grad = None           # the second tensor joins at step 2
+                continue
+            gr = torch.randn(a.shape, generator=g).cuda()
+            a.grad, b.grad = gr.clone(), gr.clone()
+        o_ref.step(), o_mine.step()
+        s_ref.step(), s_mine.step()
+    for a, b in zip(ref, mine):
+        assert torch.allclose(a, b, rtol=2e-6, atol=2e-7)
+    assert float(o_mine.state[mine[0]]["step"]) == 6.0 and float(o_mine.state[mine[1]]["step"]) == 4.0
+
+
+@pytest.mark.parametrize("network", ["r2plus1d_18", "c3d"])
+def test_fused_adam_writes_the_packed_weight_images(network):
+    """FusedAdam(model=...) == torch.optim.Adam on every parameter, and the bf16 weight images it leaves behind
+    (zsv_adam_pack_step, engine.PackedWeights) are bit-identical to re-packing the updated fp32 weights; the next
+    forward uses them (no re-pack launch) and a weight changed behind the optimizer's back is noticed."""
+    from zeroshotvideoclassification_b200 import _lib, engine, video_models as vm
+    from zeroshotvideoclassification_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    m_ref = vm.get_network(vm.default_opt(network)).cuda().train()
+    torch.manual_seed(0)
+    m_mine = vm.get_network(vm.default_opt(network)).cuda().train()
+    if network == "c3d":
+        m_ref.dropout.p = m_mine.dropout.p = 0.0
+    o_ref = torch.optim.Adam(m_ref.parameters(), lr=1e-3)
+    o_mine = FusedAdam(m_mine.parameters(), lr=1e-3, model=m_mine)
+    g = torch.Generator().manual_seed(2)
+    shape = (2, 1, 3, 16, 112, 112) if network == "c3d" else (2, 1, 3, 8, 32, 32)
+    for it in range(3):
+        x = torch.randn(*shape, generator=g).cuda()
+        z = F.normalize(torch.randn(2, 300, generator=g)).cuda()
+        o_mine.zero_grad(set_to_none=True)
+        out = m_mine(x)
+        F.mse_loss(out[0] if isinstance(out, tuple) else out, z).backward()
+        # both optimizers get the SAME gradients (two bf16 networks one ulp apart drift chaotically, DESIGN.md section 4)
+        for a, b in zip(m_ref.parameters(), m_mine.parameters()):
+            a.grad = None if b.grad is None else b.grad.detach().clone()
+        o_ref.step()
+        o_mine.step()
+    for (k, a), (_, b) in zip(m_ref.named_parameters(), m_mine.named_parameters()):
+        assert torch.allclose(a, b, rtol=2e-6, atol=2e-7), k
+    pw = o_mine._packed
+    assert pw is not None and pw.fresh()
+    wfs, wds = pw.plan.pack([w.detach() for w in pw.weights])
+    for i, (wf, wd) in enumerate(zip(wfs, wds)):
+        assert torch.equal(wf, pw.wfs[i]), i
+        assert (wd is None) == (pw.wds[i] is None) and (wd is None or torch.equal(wd, pw.wds[i])), i
+    # the next forward takes the published images: no pack kernel among its launches
+    n0 = _lib.launch_count()
+    with torch.no_grad():
+        m_mine(x)
+    n_pub = _lib.launch_count() - n0
+    with torch.no_grad():
+        pw.weights[1].mul_(1.0)                               # in-place op: version bump -> images are stale
+    assert not pw.fresh() and engine.published_for(pw.weights[0]) is None
+    n0 = _lib.launch_count()
+    with torch.no_grad():
+        m_mine(x)
+    assert _lib.launch_count() - n0 > n_pub                   # this forward re-packed
+    engine.ensure_packed_fresh()
+    assert pw.fresh()

@@ -133,3 +133,38 @@ def test_second_backward_through_the_backbone_raises():
     loss.backward(retain_graph=True)
     with pytest.raises(RuntimeError, match="second time"):
         loss.backward()
+
+
+def test_graphed_fused_adam_follows_the_lr_schedule():
+    """GraphedStep + FusedAdam(model=...): the captured update reads the learning rate from a device scalar that is
+    refreshed before every replay, and the captured forward reads the weight images the captured update writes; the
+    trajectory equals the eager one with the same optimizer and schedule (main.py:133,374: MultiStepLR)."""
+    from zeroshotvideoclassification_b200 import video_models as vm
+    from zeroshotvideoclassification_b200.graph import GraphedStep
+    from zeroshotvideoclassification_b200.optim import FusedAdam
+    xs, zs = _data(2)
+    runs = []
+    for graphed in (False, True):
+        torch.manual_seed(0)
+        model = vm.get_network(vm.default_opt("r2plus1d_18")).cuda().train()
+        opt = FusedAdam(model.parameters(), lr=1e-2, model=model)
+        sched = torch.optim.lr_scheduler.MultiStepLR(opt, [2], gamma=0.01)
+
+        def step(X, Z):
+            opt.zero_grad(set_to_none=True)
+            emb, _ = model(X)
+            loss = F.mse_loss(emb, Z)
+            loss.backward()
+            opt.step()
+            return loss
+
+        fn = GraphedStep(step, (xs[0], zs[0]), model=model, optimizer=opt) if graphed else step
+        losses = []
+        for it in range(5):
+            x, z = xs[it % 3], zs[it % 3]
+            losses.append(float(fn(x.cuda(), z.cuda())))
+            sched.step()
+        runs.append((losses, {k: v.detach().clone() for k, v in model.state_dict().items()}))
+    assert runs[0][0] == runs[1][0], (runs[0][0], runs[1][0])
+    for k in runs[0][1]:
+        assert torch.equal(runs[0][1][k], runs[1][1][k]), k

@@ -12,7 +12,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libzsv_b200.so"
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 X_NDHWC = 0
 X_WFOLD = 1
 
@@ -32,6 +32,13 @@ class BnBwdFuse(C.Structure):
 
     _fields_ = [("y", C.c_void_p), ("table", C.c_void_p), ("relu", C.c_int32), ("partial", C.c_void_p),
                 ("partial_rows", C.c_int32), ("rows_written", C.c_int32)]
+
+
+class AdamHyper(C.Structure):
+    """Mirror of ``zsv_adam_hyper`` (include/zsv_b200.h)."""
+
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float), ("grad_scale", C.c_float), ("lr_dev", C.c_void_p)]
 
 
 class BnFold(C.Structure):
@@ -67,9 +74,10 @@ SIGNATURES = {
     "zsv_conv3d_wgrad": (_I, [_DP, _P, _P, _P, _P, _SZ, _P]),
     "zsv_bias_grad_workspace": (_SZ, [_I]),
     "zsv_bias_grad": (_I, [_P, _P, _LL, _I, _P, _SZ, _P]),
-    "zsv_relu_bwd": (_I, [_P, _P, _P, _LL, _I, _P]),
-    "zsv_linear_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "zsv_linear_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "zsv_relu_bwd": (_I, [_P, _P, _P, _LL, _I, _P, _P, _SZ, _P]),
+    "zsv_linear_workspace": (_SZ, [_I, _I, _I]),
+    "zsv_linear_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _SZ, _P]),
+    "zsv_linear_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _SZ, _P]),
     "zsv_l2norm_fwd": (_I, [_P, _P, _P, _I, _I, _F, _P]),
     "zsv_l2norm_bwd": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "zsv_repack_input": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
@@ -85,12 +93,14 @@ SIGNATURES = {
     "zsv_bn_bwd": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _P, _SZ,
                         _P]),
     "zsv_head_fwd": (_I, [_P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _F, _P, _P, _P, _P, _P]),
-    "zsv_head_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _I, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "zsv_head_bwd_scratch": (_SZ, [_I, _I, _I, _I]),
+    "zsv_head_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _I, _F, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "zsv_mse_fwd_bwd": (_I, [_P, _P, _I, _I, _F, _P, _P, _P]),
-    "zsv_adam_step": (_I, [_I, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _P]),
+    "zsv_adam_step": (_I, [_I, _P, _P, _P, _P, _P, _P, C.POINTER(AdamHyper), _P]),
+    "zsv_adam_pack_step": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(AdamHyper), _P]),
     "zsv_nearest_class": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "zsv_maxpool3d_fwd": (_I, [_P, _P, _P] + [_I] * 11 + [_P]),
-    "zsv_maxpool3d_bwd": (_I, [_P, _P, _P, _P] + [_I] * 11 + [_P]),
+    "zsv_maxpool3d_bwd": (_I, [_P, _P, _P, _P] + [_I] * 11 + [_P, _P, _SZ, _P]),
 }
 
 _lib = None

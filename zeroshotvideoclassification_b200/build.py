@@ -17,7 +17,7 @@ CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libzsv_b200.so"
 STAMP = PKG_DIR / ".libzsv_b200.stamp"
 
-SOURCES = ["zsv_common.cu", "zsv_conv.cu", "zsv_elementwise.cu", "zsv_head.cu"]
+SOURCES = ["zsv_common.cu", "zsv_conv.cu", "zsv_elementwise.cu", "zsv_head.cu", "zsv_linear.cu", "zsv_optim.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -38,30 +38,55 @@ def _conv(N, T, H, W, cin, cout, layout):
     return op
 
 
+_plan_cache: Dict[tuple, tuple] = {}
+
+
+def _trunk_plan(N, T, H, W):
+    """Geometry of the 8 convolutions for a clip batch of this shape and the one-launch weight re-pack for them."""
+    key = (N, T, H, W)
+    hit = _plan_cache.get(key)
+    if hit is not None:
+        return hit
+    convs, dims = [], (T, H, W)
+    for i, (name, cin, cout, pool) in enumerate(_C3D_LAYERS):
+        convs.append(_conv(N, *dims, cin, cout, _lib.X_WFOLD if i == 0 else _lib.X_NDHWC))
+        if pool is not None:
+            (kt, kh, kw), (pt, ph, pw) = pool
+            dims = ((dims[0] + 2 * pt - kt) // kt + 1, (dims[1] + 2 * ph - kh) // kh + 1, (dims[2] + 2 * pw - kw) // kw + 1)
+    plan = ops.PackPlan(convs, [i > 0 for i in range(len(convs))])
+    _plan_cache[key] = (convs, plan)
+    return convs, plan
+
+
 class _TrunkFn(torch.autograd.Function):
     """conv1 .. pool5 (network.py:147-163): x [B,3,T,H,W] fp32 -> bf16 [B,T',H',W',512]."""
 
     @staticmethod
     def forward(ctx, x, *wb):
+        from . import engine
         need_grad = any(ctx.needs_input_grad[1:])
         N, _, T, H, W = x.shape
         a = ops.repack_input(x, _lib.X_WFOLD, 1)
+        convs, plan = _trunk_plan(N, T, H, W)
+        weights = [wb[2 * i].detach() for i in range(len(_C3D_LAYERS))]
+        pub = engine.published_for(weights[0])
+        if pub is not None:              # images written by the optimizer step (zsv_adam_pack_step): nothing to re-pack
+            wfs, wds = pub.wfs, pub.wds
+        else:
+            wfs, wds = plan.pack(weights)
         tape = []
-        dims = (T, H, W)
         for i, (name, cin, cout, pool) in enumerate(_C3D_LAYERS):
-            w, b = wb[2 * i].detach(), wb[2 * i + 1].detach().float().contiguous()
-            layout = _lib.X_WFOLD if i == 0 else _lib.X_NDHWC
-            op = _conv(N, *dims, cin, cout, layout)
-            wf, wd = op.pack(w, need_dgrad=need_grad and i > 0)
-            y, _, _ = op.fprop(a, wf, stats=False, bias=b, relu=True)
-            rec = dict(op=op, x=a, wd=wd, out=y, pool=None)
+            b = wb[2 * i + 1].detach().float().contiguous()
+            op = convs[i]
+            y, _, _ = op.fprop(a, wfs[i], stats=False, bias=b, relu=True)
+            rec = dict(op=op, x=a, wd=wds[i], out=y, pool=None)
             a = y
             if pool is not None:
                 k, p = pool
                 pooled, am = ops.maxpool3d_fwd(y, cout, k, p)
-                rec["pool"] = (k, p, am, tuple(y.shape))
+                rec["pool"] = (k, p, am, tuple(y.shape), pooled)
+                rec["out"] = None        # backward takes the ReLU mask from the pooled tensor: the big one can go
                 a = pooled
-                dims = tuple(pooled.shape[1:4])
             tape.append(rec)
         ctx.tape = tape if need_grad else None
         ctx.n = len(wb)
@@ -77,13 +102,16 @@ class _TrunkFn(torch.autograd.Function):
             rec = ctx.tape[i]
             name, cin, cout, _ = _C3D_LAYERS[i]
             op = rec["op"]
+            want = ctx.needs_input_grad[1 + 2 * i] or ctx.needs_input_grad[2 + 2 * i]
+            # pool + ReLU backward and the bias gradient (column sums of dz) in one pass over the tensor
             if rec["pool"] is not None:
-                k, p, am, shape = rec["pool"]
-                dz = ops.maxpool3d_bwd(g, am, shape, cout, k, p, relu_mask_src=rec["out"])   # pool + ReLU backward
+                k, p, am, shape, pooled = rec["pool"]
+                res = ops.maxpool3d_bwd(g, am, shape, cout, k, p, relu_pooled=pooled, want_bias=want)
             else:
-                dz = ops.relu_bwd(g, rec["out"], cout)
-            if ctx.needs_input_grad[1 + 2 * i]:
-                dw, db = op.wgrad(rec["x"], dz, want_bias=True)
+                res = ops.relu_bwd(g, rec["out"], cout, want_bias=want)
+            dz, db = res if want else (res, None)
+            if want:
+                dw, _ = op.wgrad(rec["x"], dz)
                 grads[2 * i], grads[2 * i + 1] = dw, db
             if i > 0:
                 g = op.dgrad(dz, rec["wd"])
@@ -146,6 +174,11 @@ class C3D(nn.Module):
                     p.requires_grad = False
             for p in self.fc6.parameters():
                 p.requires_grad = False
+
+    def packed_plan(self):
+        """(PackPlan, conv weights) for ``optim.FusedAdam(model=...)``: the layout of the bf16 weight images."""
+        _, plan = _trunk_plan(1, 16, 112, 112)
+        return plan, [getattr(self, name).weight for name, *_ in _C3D_LAYERS]
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         ops._require_cuda(x, "C3D.forward")

@@ -35,7 +35,7 @@ int sm_count() {
 }  // namespace zsv
 
 extern "C" const char* zsv_last_error(void) { return zsv::g_err; }
-extern "C" int zsv_abi_version(void) { return 7; }
+extern "C" int zsv_abi_version(void) { return 8; }
 extern "C" int zsv_cpad(int c) { return zsv::cpad(c); }
 extern "C" int zsv_sm_count(void) { return zsv::sm_count(); }
 extern "C" unsigned long long zsv_launch_count(void) { return zsv::g_launches.load(std::memory_order_relaxed); }

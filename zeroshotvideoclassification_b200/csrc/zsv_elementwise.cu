@@ -539,10 +539,11 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __
 }
 
 // ------------------------------------------------------------------------------------------------
-// MaxPool3d (kernel == stride), NDHWC, 8 channels per thread, argmax = flat window index (int8 range)
+// MaxPool3d (kernel == stride), NDHWC, 8 channels per thread, argmax = flat window index (one byte per element: the
+// window has at most 8 positions; the index tensor of C3D's pool1 is 70 MB instead of 283 MB as int32)
 // ------------------------------------------------------------------------------------------------
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                                   int32_t* __restrict__ argmax, int N, int T, int H, int W, int Cp, int kt, int kh,
+                                   uint8_t* __restrict__ argmax, int N, int T, int H, int W, int Cp, int kt, int kh,
                                    int kw, int pt, int ph, int pw, int To, int Ho, int Wo) {
     const int V = Cp >> 3;
     const long long total = (long long)N * To * Ho * Wo * V;
@@ -575,24 +576,56 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
                         if (f[j] > best[j] || bi[j] < 0) best[j] = f[j], bi[j] = code;
                 }
         *reinterpret_cast<uint4*>(y + i * 8) = pack8(best);
-        int32_t* am = argmax + i * 8;
+        uint32_t lo = 0, hi = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) am[j] = bi[j];
+        for (int j = 0; j < 4; ++j) {
+            lo |= static_cast<uint32_t>(bi[j] & 0xff) << (8 * j);
+            hi |= static_cast<uint32_t>(bi[j + 4] & 0xff) << (8 * j);
+        }
+        *reinterpret_cast<uint2*>(argmax + i * 8) = make_uint2(lo, hi);
     }
 }
 
-// dz = g * [out > 0]  (C3D: ReLU after conv+bias, network.py:147-162)
-__global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ out,
-                                __nv_bfloat16* __restrict__ dz, long long nvec) {
+// Per-thread channel sums -> one partial row per block.  Every thread of these grid-stride kernels always works on the
+// same channel octet (the host makes gridDim.x * 256 a multiple of V = Cp/8), so it keeps 8 running sums; the block
+// combines the threads of an octet in a fixed order: deterministic, no atomics.  partial: [gridDim.x][Cp].
+__device__ __forceinline__ void block_channel_sums(const float (&acc)[8], int V, int Cp, float* __restrict__ partial) {
+    __shared__ float red[256][9];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
+    __syncthreads();
+    // thread t's octet is (blockIdx.x * 256 + t) % V == (t + shift) % V
+    const int shift = static_cast<int>((static_cast<long long>(blockIdx.x) * 256) % V);
+    for (int c = threadIdx.x; c < Cp; c += 256) {
+        const int oct = c >> 3, j = c & 7;
+        int t0 = oct - shift;
+        if (t0 < 0) t0 += V;
+        float s = 0.f;
+        for (int t = t0; t < 256; t += V) s += red[t][j];
+        partial[static_cast<long long>(blockIdx.x) * Cp + c] = s;
+    }
+}
+
+// dz = g * [out > 0]  (C3D: ReLU after conv+bias, network.py:147-162); optional bias-gradient partial sums of dz
+__global__ void __launch_bounds__(256)
+relu_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ out,
+                __nv_bfloat16* __restrict__ dz, long long nvec, int V, int Cp, float* __restrict__ partial) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
          i += (long long)gridDim.x * blockDim.x) {
         float a[8], b[8];
         unpack8(*reinterpret_cast<const uint4*>(g + i * 8), a);
         unpack8(*reinterpret_cast<const uint4*>(out + i * 8), b);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = b[j] > 0.f ? a[j] : 0.f;
+        for (int j = 0; j < 8; ++j) {
+            a[j] = b[j] > 0.f ? a[j] : 0.f;
+            acc[j] += a[j];
+        }
         *reinterpret_cast<uint4*>(dz + i * 8) = pack8(a);
     }
+    if (partial != nullptr) block_channel_sums(acc, V, Cp, partial);
 }
 
 // per-block column sums of a bf16 [rows][Cp] tensor -> partial[block][Cp] (fp32); block = V groups x R row lanes
@@ -640,13 +673,22 @@ colsum_final_kernel(const float* __restrict__ partial, int nblocks, int C, int C
     }
 }
 
-__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const int32_t* __restrict__ argmax,
-                                   const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ dx, int N, int T, int H, int W, int Cp, int kt, int kh,
-                                   int kw, int pt, int ph, int pw, int To, int Ho, int Wo) {
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ argmax,
+                   const __nv_bfloat16* __restrict__ pooled, __nv_bfloat16* __restrict__ dx, int N, int T, int H, int W,
+                   int Cp, int kt, int kh, int kw, int pt, int ph, int pw, int To, int Ho, int Wo,
+                   float* __restrict__ partial) {
     // one thread per input vector: windows do not overlap (kernel == stride), so each input element belongs to
-    // exactly one window and the gradient is a gather
+    // exactly one window and the gradient is a gather.
+    // pooled (optional) = the pooling OUTPUT when its input was a ReLU output: the selected element is that value, so
+    // dz = dy * [pooled > 0] fuses the ReLU backward (network.py:147-162) without re-reading the (4-8x larger) input.
+    // partial (optional): bias-gradient sums of dz -- each window's masked dy is counted once, by the thread of the
+    // window's first position.
     const int V = Cp >> 3;
     const long long total = (long long)N * T * H * W * V;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         long long r = i;
@@ -667,18 +709,26 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const i
             const long long oi = ((((long long)n * To + to) * Ho + ho) * Wo + wo) * V + g;
             float f[8];
             unpack8(*reinterpret_cast<const uint4*>(dy + oi * 8), f);
-            const int32_t* am = argmax + oi * 8;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = am[j] == code ? f[j] : 0.f;
-            if (mask_src != nullptr) {  // fused ReLU backward of the tensor that was pooled
+            if (pooled != nullptr) {
                 float m[8];
-                unpack8(*reinterpret_cast<const uint4*>(mask_src + i * 8), m);
+                unpack8(*reinterpret_cast<const uint4*>(pooled + oi * 8), m);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = m[j] > 0.f ? o[j] : 0.f;
+                for (int j = 0; j < 8; ++j) f[j] = m[j] > 0.f ? f[j] : 0.f;
+            }
+            const uint2 am = *reinterpret_cast<const uint2*>(argmax + oi * 8);
+            // first in-bounds position of the window (padding can cut the leading ones off)
+            const int t_first = max(to * kt - pt, 0), h_first = max(ho * kh - ph, 0), w_first = max(wo * kw - pw, 0);
+            const bool first = t == t_first && h == h_first && w == w_first;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int sel = static_cast<int>(((j < 4 ? am.x : am.y) >> (8 * (j & 3))) & 0xffu);
+                o[j] = sel == code ? f[j] : 0.f;
+                if (first) acc[j] += f[j];
             }
         }
         *reinterpret_cast<uint4*>(dx + i * 8) = pack8(o);
     }
+    if (partial != nullptr) block_channel_sums(acc, V, Cp, partial);
 }
 
 int ew_blocks(long long work_items, int threads) {
@@ -900,12 +950,13 @@ extern "C" int zsv_bn_bwd_finish(const void* dz, const void* y, const float* mea
     return ZSV_OK;
 }
 
-extern "C" int zsv_maxpool3d_fwd(const void* x, void* y, int32_t* argmax, int N, int T, int H, int W, int C, int kt,
+extern "C" int zsv_maxpool3d_fwd(const void* x, void* y, uint8_t* argmax, int N, int T, int H, int W, int C, int kt,
                                  int kh, int kw, int pt, int ph, int pw, void* stream) {
     if (!x || !y || !argmax) return fail(ZSV_ERR_BAD_ARG, "maxpool_fwd: null pointer");
     const int Cp = cpad(C);
     const int To = (T + 2 * pt - kt) / kt + 1, Ho = (H + 2 * ph - kh) / kh + 1, Wo = (W + 2 * pw - kw) / kw + 1;
     if (To < 1 || Ho < 1 || Wo < 1) return fail(ZSV_ERR_BAD_ARG, "maxpool_fwd: empty output");
+    if (kt * kh * kw > 255) return fail(ZSV_ERR_UNSUPPORTED, "maxpool_fwd: window larger than 255 positions");
     const long long total = (long long)N * To * Ho * Wo * (Cp >> 3);
     maxpool_fwd_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)x, (__nv_bfloat16*)y, argmax, N, T, H, W, Cp, kt, kh, kw, pt, ph, pw, To, Ho, Wo);
@@ -913,13 +964,38 @@ extern "C" int zsv_maxpool3d_fwd(const void* x, void* y, int32_t* argmax, int N,
     return ZSV_OK;
 }
 
-extern "C" int zsv_relu_bwd(const void* g, const void* out, void* dz, long long rows, int C, void* stream) {
-    if (!g || !out || !dz) return fail(ZSV_ERR_BAD_ARG, "relu_bwd: null pointer");
-    const long long nvec = rows * (cpad(C) >> 3);
-    relu_bwd_kernel<<<ew_blocks(nvec, 1024), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)g, (const __nv_bfloat16*)out, (__nv_bfloat16*)dz, nvec);
-    ZSV_LAUNCH_CHECK("relu_bwd_kernel");
+// grid of the backward kernels that also emit bias-gradient partial rows: total threads a multiple of V
+static int bias_fused_grid(long long work_items, int V) {
+    int blocks = (int)std::max<long long>(1, std::min<long long>(ceil_div_ll(work_items, 256), kBwdMaxBlocks));
+    while (((long long)blocks * 256) % V != 0) --blocks;     // V <= 256 divides 256 for power-of-two pitches; else shrink
+    return std::max(blocks, 1);
+}
+
+static int bias_fused_finish(const float* partial, int nblocks, int C, float* db, cudaStream_t st) {
+    colsum_final_kernel<<<ceil_div(cpad(C), 32), 1024, 0, st>>>(partial, nblocks, C, cpad(C), db);
+    ZSV_LAUNCH_CHECK("colsum_final_kernel");
     return ZSV_OK;
+}
+
+extern "C" int zsv_relu_bwd(const void* g, const void* out, void* dz, long long rows, int C, float* bias_grad,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+    if (!g || !out || !dz) return fail(ZSV_ERR_BAD_ARG, "relu_bwd: null pointer");
+    const int Cp = cpad(C), V = Cp >> 3;
+    const long long nvec = rows * V;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bias_grad == nullptr) {
+        relu_bwd_kernel<<<ew_blocks(nvec, 1024), 256, 0, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)out,
+                                                              (__nv_bfloat16*)dz, nvec, V, Cp, nullptr);
+        ZSV_LAUNCH_CHECK("relu_bwd_kernel");
+        return ZSV_OK;
+    }
+    if (!workspace || workspace_bytes < zsv_bias_grad_workspace(C)) return fail(ZSV_ERR_WORKSPACE, "relu_bwd: workspace too small");
+    if ((256 % V) != 0 && V > 256) return fail(ZSV_ERR_UNSUPPORTED, "relu_bwd: channel pitch too large for the fused bias gradient");
+    const int blocks = bias_fused_grid(nvec, V);
+    relu_bwd_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)out, (__nv_bfloat16*)dz, nvec, V,
+                                            Cp, (float*)workspace);
+    ZSV_LAUNCH_CHECK("relu_bwd_kernel");
+    return bias_fused_finish((const float*)workspace, blocks, C, bias_grad, st);
 }
 
 extern "C" size_t zsv_bias_grad_workspace(int C) { return (size_t)kBwdMaxBlocks * cpad(C) * sizeof(float); }
@@ -941,17 +1017,26 @@ extern "C" int zsv_bias_grad(const void* dy, float* db, long long rows, int C, v
     return ZSV_OK;
 }
 
-extern "C" int zsv_maxpool3d_bwd(const void* dy, const int32_t* argmax, const void* relu_mask_src, void* dx, int N,
+extern "C" int zsv_maxpool3d_bwd(const void* dy, const uint8_t* argmax, const void* relu_pooled, void* dx, int N,
                                  int T, int H, int W, int C, int kt, int kh, int kw, int pt, int ph, int pw,
-                                 void* stream) {
+                                 float* bias_grad, void* workspace, size_t workspace_bytes, void* stream) {
     if (!dy || !dx || !argmax) return fail(ZSV_ERR_BAD_ARG, "maxpool_bwd: null pointer");
-    const int Cp = cpad(C);
+    const int Cp = cpad(C), V = Cp >> 3;
     const int To = (T + 2 * pt - kt) / kt + 1, Ho = (H + 2 * ph - kh) / kh + 1, Wo = (W + 2 * pw - kw) / kw + 1;
-    const long long total = (long long)N * T * H * W * (Cp >> 3);
-    maxpool_bwd_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)dy, argmax, (const __nv_bfloat16*)relu_mask_src, (__nv_bfloat16*)dx, N, T, H, W, Cp, kt, kh,
-        kw, pt, ph, pw, To, Ho, Wo);
+    const long long total = (long long)N * T * H * W * V;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* partial = nullptr;
+    int blocks = ew_blocks(total, 256);
+    if (bias_grad != nullptr) {
+        if (!workspace || workspace_bytes < zsv_bias_grad_workspace(C)) return fail(ZSV_ERR_WORKSPACE, "maxpool_bwd: workspace too small");
+        if (V > 256) return fail(ZSV_ERR_UNSUPPORTED, "maxpool_bwd: channel pitch too large for the fused bias gradient");
+        blocks = bias_fused_grid(total, V);
+        partial = (float*)workspace;
+    }
+    maxpool_bwd_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, argmax, (const __nv_bfloat16*)relu_pooled,
+                                               (__nv_bfloat16*)dx, N, T, H, W, Cp, kt, kh, kw, pt, ph, pw, To, Ho, Wo, partial);
     ZSV_LAUNCH_CHECK("maxpool_bwd_kernel");
+    if (bias_grad != nullptr) return bias_fused_finish(partial, blocks, C, bias_grad, st);
     return ZSV_OK;
 }
 

@@ -33,37 +33,6 @@ __global__ void pool_kernel(const __nv_bfloat16* __restrict__ feat, float* __res
     pooled[(long long)b * C + c] = acc / (float)P;
 }
 
-// out[b][j] = act(sum_k x[b][k] * w[j][k] + bias[j]); one warp per output feature j, 8 batch rows per pass.
-// gridDim.y > 1 spreads the 8-row groups over blocks (small weight matrices: more warps instead of fewer weight reads).
-__global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                  const float* __restrict__ bias, float* __restrict__ out, int B, int K, int J,
-                                  int relu) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= J) return;
-    const float* wr = w + (long long)warp * K;
-    for (int b0 = blockIdx.y * 8; b0 < B; b0 += 8 * gridDim.y) {
-        float acc[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        for (int k = lane; k < K; k += 32) {
-            const float wv = wr[k];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (b0 + i < B) acc[i] = fmaf(wv, x[(long long)(b0 + i) * K + k], acc[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float s = warp_sum(acc[i]);
-            if (lane == 0 && b0 + i < B) {
-                float v = s + (bias ? bias[warp] : 0.f);
-                if (relu) v = fmaxf(v, 0.f);
-                out[(long long)(b0 + i) * J + warp] = v;
-            }
-        }
-    }
-}
-
 // emb[b] = o[b] / max(||o[b]||, eps); one warp per row
 __global__ void normalize_fwd_kernel(const float* __restrict__ o, float* __restrict__ emb, float* __restrict__ onorm,
                                      int B, int E, float eps) {
@@ -97,88 +66,6 @@ __global__ void normalize_bwd_kernel(const float* __restrict__ demb, const float
         const float g = demb[(long long)b * E + e];
         dout[(long long)b * E + e] = nrm > eps ? (g - emb[(long long)b * E + e] * dot) / nrm : g / eps;
     }
-}
-
-// dw[j][k] = sum_b dy[b][j] * x[b][k];  db[j] = sum_b dy[b][j]
-__global__ void linear_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw,
-                                    float* __restrict__ db, int B, int K, int J) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= (long long)J * K) return;
-    const int j = static_cast<int>(i / K), k = static_cast<int>(i - (long long)j * K);
-    float acc = 0.f, accb = 0.f;
-    for (int b = 0; b < B; ++b) {
-        const float g = dy[(long long)b * J + j];
-        acc = fmaf(g, x[(long long)b * K + k], acc);
-        accb += g;
-    }
-    dw[i] = acc;
-    if (k == 0 && db) db[j] = accb;
-}
-
-// dx[b][k] = (sum_j dy[b][j] * w[j][k]) * (mask ? [act[b][k] > 0] : 1); one thread per k, 8 batch rows per pass,
-// so the weight matrix is streamed ceil(B/8) times with coalesced rows
-__global__ void linear_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
-                                    const float* __restrict__ act, float* __restrict__ dx, int B, int K, int J) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= K) return;
-    for (int b0 = 0; b0 < B; b0 += 8) {
-        float acc[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        for (int j = 0; j < J; ++j) {
-            const float wv = w[(long long)j * K + k];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (b0 + i < B) acc[i] = fmaf(dy[(long long)(b0 + i) * J + j], wv, acc[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (b0 + i < B) {
-                const long long o = (long long)(b0 + i) * K + k;
-                dx[o] = (act && !(act[o] > 0.f)) ? 0.f : acc[i];
-            }
-        }
-    }
-}
-
-// dx for small weight matrices: block = 32 k lanes x 8 slices of the J reduction, 8 batch rows; the slices are combined
-// in fixed order through shared memory.  grid = (ceil(K/32), ceil(B/8)).
-__global__ void __launch_bounds__(256)
-linear_dgrad_tile_kernel(const float* __restrict__ dy, const float* __restrict__ w, const float* __restrict__ act,
-                         float* __restrict__ dx, int B, int K, int J) {
-    __shared__ float red[8][8][33];
-    const int kl = threadIdx.x & 31, sl = threadIdx.x >> 5;
-    const int k = blockIdx.x * 32 + kl;
-    const int b0 = blockIdx.y * 8;
-    const int jper = (J + 7) >> 3;
-    const int j0 = sl * jper, j1 = min(J, j0 + jper);
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-#pragma unroll 4
-    for (int j = j0; j < j1; ++j) {
-        const float wv = k < K ? w[(long long)j * K + k] : 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (b0 + i < B) acc[i] = fmaf(dy[(long long)(b0 + i) * J + j], wv, acc[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) red[sl][i][kl] = acc[i];
-    __syncthreads();
-    const int i = sl;   // 8 warps -> 8 batch rows
-    if (b0 + i < B && k < K) {
-        float s2 = 0.f;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) s2 += red[t][i][kl];
-        const long long o = (long long)(b0 + i) * K + k;
-        dx[o] = (act && !(act[o] > 0.f)) ? 0.f : s2;
-    }
-}
-
-__global__ void relu_mask_kernel(const float* __restrict__ dy, const float* __restrict__ act, float* __restrict__ out,
-                                 long long n) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i < n) out[i] = act[i] > 0.f ? dy[i] : 0.f;
 }
 
 // dfeat[b][p][c] = dpooled[b][c] / P
@@ -362,84 +249,57 @@ extern "C" int zsv_head_fwd(const void* feat, int B, int P, int C, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     pool_kernel<<<dim3(ceil_div(C, 128), B), 128, 0, st>>>((const __nv_bfloat16*)feat, pooled, B, P, C, cpad(C));
     ZSV_LAUNCH_CHECK("pool_kernel");
-    const int bgroups = ceil_div(B, 8);
-    linear_fwd_kernel<<<dim3(ceil_div(Hd * 32, 256), bgroups), 256, 0, st>>>(pooled, w1, b1, hidden, B, C, Hd, 1);
-    ZSV_LAUNCH_CHECK("linear_fwd_kernel(1)");
+    int rc = linear_forward(pooled, w1, b1, hidden, B, C, Hd, 1, nullptr, 0, st);
+    if (rc) return rc;
     // raw projection goes to emb, then normalised in place
-    linear_fwd_kernel<<<dim3(ceil_div(E * 32, 256), bgroups), 256, 0, st>>>(hidden, w2, b2, emb, B, Hd, E, 0);
-    ZSV_LAUNCH_CHECK("linear_fwd_kernel(2)");
+    rc = linear_forward(hidden, w2, b2, emb, B, Hd, E, 0, nullptr, 0, st);
+    if (rc) return rc;
     normalize_fwd_kernel<<<ceil_div(B * 32, 128), 128, 0, st>>>(emb, emb, onorm, B, E, eps);
     ZSV_LAUNCH_CHECK("normalize_fwd_kernel");
     return ZSV_OK;
 }
 
+extern "C" size_t zsv_head_bwd_scratch(int B, int C, int Hd, int E) {
+    if (B < 1 || C < 1 || Hd < 1 || E < 1) return 0;
+    const size_t fixed = sizeof(float) * (size_t)B * ((size_t)E + Hd + C);
+    return fixed + std::max(linear_workspace_bytes(B, Hd, E), linear_workspace_bytes(B, C, Hd));
+}
+
 extern "C" int zsv_head_bwd(const float* demb, const float* emb, const float* onorm, const float* pooled,
                             const float* hidden, int B, int P, int C, const float* w1, int Hd, const float* w2, int E,
                             float eps, float* dw1, float* db1, float* dw2, float* db2, void* dfeat, float* scratch,
-                            void* stream) {
+                            size_t scratch_bytes, void* stream) {
     if (!demb || !emb || !onorm || !pooled || !hidden || !w1 || !w2 || !scratch)
         return fail(ZSV_ERR_BAD_ARG, "head_bwd: null pointer");
+    if (scratch_bytes < zsv_head_bwd_scratch(B, C, Hd, E))
+        return fail(ZSV_ERR_WORKSPACE, "head_bwd: scratch %zu < required %zu bytes", scratch_bytes, zsv_head_bwd_scratch(B, C, Hd, E));
     cudaStream_t st = (cudaStream_t)stream;
-    // scratch: do [B][E] | dh [B][Hd] | dpooled [B][C]
+    // scratch: do [B][E] | dh [B][Hd] | dpooled [B][C] | split partials of the data gradients
     float* dout = scratch;
     float* dh = dout + (size_t)B * E;
     float* dpooled = dh + (size_t)B * Hd;
+    float* ws = dpooled + (size_t)B * C;
+    const size_t ws_bytes = scratch_bytes - sizeof(float) * (size_t)B * ((size_t)E + Hd + C);
     normalize_bwd_kernel<<<ceil_div(B * 32, 128), 128, 0, st>>>(demb, emb, onorm, dout, B, E, eps);
     ZSV_LAUNCH_CHECK("normalize_bwd_kernel");
+    int rc;
     if (dw2) {
-        linear_wgrad_kernel<<<ceil_div(E * Hd, 256), 256, 0, st>>>(dout, hidden, dw2, db2, B, Hd, E);
-        ZSV_LAUNCH_CHECK("linear_wgrad_kernel(2)");
+        rc = linear_wgrad(dout, hidden, dw2, db2, B, Hd, E, st);
+        if (rc) return rc;
     }
-    linear_dgrad_tile_kernel<<<dim3(ceil_div(Hd, 32), ceil_div(B, 8)), 256, 0, st>>>(dout, w2, hidden, dh, B, Hd, E);
-    ZSV_LAUNCH_CHECK("linear_dgrad_kernel(2)");
+    rc = linear_dgrad(dout, w2, hidden, dh, B, Hd, E, ws, ws_bytes, st);      // ReLU mask of the hidden layer applied to dh
+    if (rc) return rc;
     if (dw1) {
-        linear_wgrad_kernel<<<ceil_div(Hd * C, 256), 256, 0, st>>>(dh, pooled, dw1, db1, B, C, Hd);
-        ZSV_LAUNCH_CHECK("linear_wgrad_kernel(1)");
+        rc = linear_wgrad(dh, pooled, dw1, db1, B, C, Hd, st);
+        if (rc) return rc;
     }
     if (dfeat) {
-        linear_dgrad_tile_kernel<<<dim3(ceil_div(C, 32), ceil_div(B, 8)), 256, 0, st>>>(dh, w1, nullptr, dpooled, B, C, Hd);
-        ZSV_LAUNCH_CHECK("linear_dgrad_kernel(1)");
+        rc = linear_dgrad(dh, w1, nullptr, dpooled, B, C, Hd, ws, ws_bytes, st);
+        if (rc) return rc;
         const long long total = (long long)B * P * cpad(C);
         pool_bwd_kernel<<<(int)std::min<long long>(ceil_div_ll(total, 256), 148 * 8), 256, 0, st>>>(
             dpooled, (__nv_bfloat16*)dfeat, B, P, C, cpad(C));
         ZSV_LAUNCH_CHECK("pool_bwd_kernel");
-    }
-    return ZSV_OK;
-}
-
-extern "C" int zsv_linear_fwd(const float* x, const float* w, const float* bias, float* out, int B, int K, int J,
-                              int relu, void* stream) {
-    if (!x || !w || !out) return fail(ZSV_ERR_BAD_ARG, "linear_fwd: null pointer");
-    if (B < 1 || K < 1 || J < 1) return fail(ZSV_ERR_BAD_ARG, "linear_fwd: bad sizes");
-    // small weight matrix: one block row per 8 batch rows; large (C3D fc6): stream W once per pass over all rows
-    const int gy = (long long)K * J <= (1LL << 20) ? ceil_div(B, 8) : 1;
-    linear_fwd_kernel<<<dim3(ceil_div(J * 32, 256), gy), 256, 0, (cudaStream_t)stream>>>(x, w, bias, out, B, K, J, relu);
-    ZSV_LAUNCH_CHECK("linear_fwd_kernel");
-    return ZSV_OK;
-}
-
-extern "C" int zsv_linear_bwd(const float* dy, const float* x, const float* w, const float* act, int B, int K, int J,
-                              float* dx, float* dw, float* db, float* scratch, void* stream) {
-    if (!dy || !x || !w) return fail(ZSV_ERR_BAD_ARG, "linear_bwd: null pointer");
-    cudaStream_t st = (cudaStream_t)stream;
-    const float* g = dy;
-    if (act) {  // ReLU on the forward output: mask dy first (scratch [B][J])
-        if (!scratch) return fail(ZSV_ERR_BAD_ARG, "linear_bwd: relu mask needs scratch");
-        const long long n = (long long)B * J;
-        relu_mask_kernel<<<(int)ceil_div_ll(n, 256), 256, 0, st>>>(dy, act, scratch, n);
-        ZSV_LAUNCH_CHECK("relu_mask_kernel");
-        g = scratch;
-    }
-    if (dw) {
-        linear_wgrad_kernel<<<(int)ceil_div_ll((long long)J * K, 256), 256, 0, st>>>(g, x, dw, db, B, K, J);
-        ZSV_LAUNCH_CHECK("linear_wgrad_kernel");
-    }
-    if (dx) {
-        if ((long long)K * J <= (1LL << 20))   // small weight matrix: parallelise over (b, k)
-            linear_dgrad_tile_kernel<<<dim3(ceil_div(K, 32), ceil_div(B, 8)), 256, 0, st>>>(g, w, nullptr, dx, B, K, J);
-        else                                   // large (C3D fc6): stream W ceil(B/8) times
-            linear_dgrad_kernel<<<ceil_div(K, 128), 128, 0, st>>>(g, w, nullptr, dx, B, K, J);
-        ZSV_LAUNCH_CHECK("linear_dgrad_kernel");
     }
     return ZSV_OK;
 }
@@ -492,90 +352,5 @@ extern "C" int zsv_nearest_class(const float* emb, const float* cls, int N, int 
     else
         nearest_kernel<8><<<ceil_div(N, 8), 128, smem, st>>>(emb, cls, N, C, D, k, idx_out, dist_out);
     ZSV_LAUNCH_CHECK("nearest_kernel");
-    return ZSV_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Multi-tensor Adam (torch.optim.Adam semantics, main.py:131,203): one launch updates up to kMaxAdamItems parameter
-// tensors; the step counter lives on the device (read here, incremented by the caller), so the update is CUDA-graph
-// capturable.  HBM-bound: 28 bytes per parameter.
-//   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
-// ------------------------------------------------------------------------------------------------
-namespace zsv {
-namespace {
-constexpr int kMaxAdamItems = 72;
-struct AdamItem {
-    float* p;
-    const float* g;
-    float* m;
-    float* v;
-    long long start;   // first flat element index
-};
-struct AdamBatch {
-    int32_t n;
-    long long total;
-    float lr, beta1, beta2, eps, weight_decay;
-    const float* step;   // device scalar: t (already incremented)
-    AdamItem it[kMaxAdamItems];
-};
-
-__global__ void __launch_bounds__(256)
-adam_multi_tensor_kernel(const __grid_constant__ AdamBatch B) {
-    const float t = *B.step;
-    const float bc1 = 1.f - powf(B.beta1, t);
-    const float bc2_sqrt = sqrtf(1.f - powf(B.beta2, t));
-    const float step_size = B.lr / bc1;
-    for (long long gidx = blockIdx.x * (long long)blockDim.x + threadIdx.x; gidx < B.total;
-         gidx += (long long)gridDim.x * blockDim.x) {
-        int lo = 0, hi = B.n - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (B.it[mid].start <= gidx) lo = mid;
-            else hi = mid - 1;
-        }
-        const AdamItem& I = B.it[lo];
-        const long long i = gidx - I.start;
-        float p = I.p[i];
-        float g = I.g[i];
-        if (B.weight_decay != 0.f) g = fmaf(B.weight_decay, p, g);
-        float m = I.m[i], v = I.v[i];
-        m = m + (1.f - B.beta1) * (g - m);                    // lerp, like torch
-        v = B.beta2 * v + (1.f - B.beta2) * g * g;
-        const float denom = sqrtf(v) / bc2_sqrt + B.eps;
-        p -= step_size * (m / denom);
-        I.p[i] = p;
-        I.m[i] = m;
-        I.v[i] = v;
-    }
-}
-}  // namespace
-}  // namespace zsv
-
-extern "C" int zsv_adam_step(int n, float* const* params, const float* const* grads, float* const* exp_avg,
-                             float* const* exp_avg_sq, const long long* numel, const float* step, float lr, float beta1,
-                             float beta2, float eps, float weight_decay, void* stream) {
-    if (n < 0 || (n > 0 && (!params || !grads || !exp_avg || !exp_avg_sq || !numel)) || !step)
-        return fail(ZSV_ERR_BAD_ARG, "adam_step: null array");
-    cudaStream_t st = (cudaStream_t)stream;
-    for (int base = 0; base < n; base += zsv::kMaxAdamItems) {
-        zsv::AdamBatch B;
-        memset(&B, 0, sizeof(B));
-        B.lr = lr, B.beta1 = beta1, B.beta2 = beta2, B.eps = eps, B.weight_decay = weight_decay, B.step = step;
-        long long total = 0;
-        int m = 0;
-        for (int i = base; i < std::min(n, base + zsv::kMaxAdamItems); ++i) {
-            if (numel[i] <= 0) continue;
-            if (!params[i] || !grads[i] || !exp_avg[i] || !exp_avg_sq[i]) return fail(ZSV_ERR_BAD_ARG, "adam_step: null tensor %d", i);
-            B.it[m].p = params[i], B.it[m].g = grads[i], B.it[m].m = exp_avg[i], B.it[m].v = exp_avg_sq[i];
-            B.it[m].start = total;
-            total += numel[i];
-            ++m;
-        }
-        if (m == 0) continue;
-        B.n = m, B.total = total;
-        const int blocks = (int)std::min<long long>(ceil_div_ll(total, 256 * 4), (long long)sm_count() * 8);
-        zsv::adam_multi_tensor_kernel<<<std::max(1, blocks), 256, 0, st>>>(B);
-        ZSV_LAUNCH_CHECK("adam_multi_tensor_kernel");
-    }
     return ZSV_OK;
 }

@@ -21,6 +21,15 @@ int sm_count();
 // Count one kernel launch issued by this library (read back through zsv_launch_count()).
 void count_launch();
 
+// fp32 Linear layers with few batch rows (zsv_linear.cu); shared by the C3D entry points and the embedding head.
+// ws may be NULL for linear_forward (the reduction is then not split over blocks).
+size_t linear_workspace_bytes(int B, int K, int J);
+int linear_forward(const float* x, const float* w, const float* bias, float* out, int B, int K, int J, int relu,
+                   float* ws, size_t ws_bytes, cudaStream_t st);
+int linear_dgrad(const float* g, const float* w, const float* act_in, float* dx, int B, int K, int J, float* ws,
+                 size_t ws_bytes, cudaStream_t st);
+int linear_wgrad(const float* g, const float* x, float* dw, float* db, int B, int K, int J, cudaStream_t st);
+
 #define ZSV_CUDA_CHECK(expr)                                                                            \
     do {                                                                                                \
         cudaError_t _e = (expr);                                                                        \

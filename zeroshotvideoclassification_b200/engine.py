@@ -176,6 +176,55 @@ def _network_plan(N, T, H, W, need_grad: bool, arch: str = "r2plus1d_18"):
 _eval_pack_cache: Dict[tuple, tuple] = {}
 
 
+class PackedWeights:
+    """bf16 weight images of a network kept current by the optimizer instead of being re-packed by every forward.
+
+    ``optim.FusedAdam(model=...)`` updates the fp32 master weights and writes their bf16 images in the same kernel
+    (zsv_adam_pack_step) into ``buf``; the forward pass takes its operands from here while ``fresh()``: every weight
+    still has the address and version counter recorded when the images were written.  Anything that changes a weight
+    through PyTorch (load_state_dict, an in-place op, another optimizer) bumps the version and the next forward (or
+    ``ensure_packed_fresh`` before a graph replay) re-packs."""
+
+    def __init__(self, plan: "ops.PackPlan", weights: List[torch.Tensor]):
+        self.plan, self.weights = plan, list(weights)
+        self.buf = torch.empty(plan.total, dtype=torch.bfloat16, device=weights[0].device)
+        self.wfs, self.wds = plan.views(self.buf)
+        self.stamp = None
+
+    def _now(self):
+        return tuple((w.data_ptr(), w._version) for w in self.weights)
+
+    def fresh(self) -> bool:
+        return self.stamp is not None and self.stamp == self._now()
+
+    def mark(self) -> None:
+        self.stamp = self._now()
+
+    def refresh(self) -> None:
+        self.plan.pack([w.detach() for w in self.weights], out=self.buf)
+        self.mark()
+
+
+_published: Dict[int, PackedWeights] = {}      # key: data_ptr of the first convolution weight of the network
+
+
+def publish_packed(pw: PackedWeights) -> None:
+    _published[pw.weights[0].data_ptr()] = pw
+
+
+def published_for(first_weight: torch.Tensor) -> Optional[PackedWeights]:
+    pw = _published.get(first_weight.data_ptr())
+    return pw if pw is not None and pw.fresh() else None
+
+
+def ensure_packed_fresh() -> None:
+    """Before a CUDA-graph replay: a captured forward reads the published images without any Python running, so images
+    whose master weights were changed behind the optimizer's back are re-packed now."""
+    for pw in _published.values():
+        if not pw.fresh():
+            pw.refresh()
+
+
 def note_weights_changed() -> None:
     """Drop the folded inference weights.  Tensor version counters do not see writes made through raw pointers
     (zsv_bn_finalize updates running_mean / running_var, zsv_adam_step the parameters, a CUDA-graph replay does both
@@ -290,7 +339,11 @@ class BackboneRunner:
             return self._forward_folded(folded, (N, T, H, W), names, plan)
         if self.train:
             note_weights_changed()       # this forward rewrites the running statistics through raw pointers
-        wfs, wds = plan.pack([self.t[n + ".weight"] for n in names])
+        pub = published_for(self.t[names[0] + ".weight"])
+        if pub is not None:          # images written by the optimizer step (zsv_adam_pack_step): nothing to re-pack
+            wfs, wds = pub.wfs, pub.wds
+        else:
+            wfs, wds = plan.pack([self.t[n + ".weight"] for n in names])
         self.packed = {n: (wf, wd) for n, wf, wd in zip(names, wfs, wds)}
         s0 = self.stem_specs[0]
         a, _, _, rec, d = self._unit(s0, folded, (N, T, H, W), True, layout=_lib.X_WFOLD, need_dgrad=False)

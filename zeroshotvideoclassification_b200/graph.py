@@ -150,7 +150,9 @@ class GraphedStep:
         return self.static_outputs
 
     def _replay(self) -> None:
-        from . import engine
+        from . import engine, optim
         engine.note_weights_changed()    # a replay rewrites parameters / running statistics without any Python running
+        engine.ensure_packed_fresh()     # weight images the captured forward reads must match the current masters
+        optim.sync_all_lr()              # learning rates live in device scalars: a schedule reaches the replays
         self.graph.replay()
         self.replays += 1

@@ -163,28 +163,38 @@ class PackPlan:
             else:
                 self.wd_off.append(None)
         self.total = off
-        self.w_arr, self.wf_arr, self.wd_arr = (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_void_p * n)()
 
-    def pack(self, weights):
-        """weights: fp32 CUDA tensors in conv order -> ([wf...], [wd or None...]) views of one bf16 buffer."""
+    def _arrays(self):
+        # per call: a plan is cached globally and may be used from several threads / devices at once
+        n = self.n
+        return (C.c_void_p * n)(), (C.c_void_p * n)(), (C.c_void_p * n)()
+
+    def views(self, buf):
+        """([wf...], [wd or None...]) views of a packed buffer laid out by this plan."""
+        wfs = [buf[o:o + c.wf_bytes // 2] for o, c in zip(self.wf_off, self.convs)]
+        wds = [None if o is None else buf[o:o + c.wd_bytes // 2] for o, c in zip(self.wd_off, self.convs)]
+        return wfs, wds
+
+    def pack(self, weights, out=None):
+        """weights: fp32 CUDA tensors in conv order -> ([wf...], [wd or None...]) views of one bf16 buffer (``out`` or
+        a fresh one)."""
         dev = weights[0].device
-        buf = torch.empty(self.total, dtype=torch.bfloat16, device=dev)
+        buf = out if out is not None else torch.empty(self.total, dtype=torch.bfloat16, device=dev)
         base = buf.data_ptr()
         keep = []
+        w_arr, wf_arr, wd_arr = self._arrays()
         for i, w in enumerate(weights):
             _require_cuda(w, "PackPlan.pack")
             w = w.detach()
             if w.dtype != torch.float32 or not w.is_contiguous():
                 w = w.float().contiguous()
                 keep.append(w)
-            self.w_arr[i] = w.data_ptr()
-            self.wf_arr[i] = base + 2 * self.wf_off[i]
-            self.wd_arr[i] = None if self.wd_off[i] is None else base + 2 * self.wd_off[i]
-        check(self.lib.zsv_conv3d_pack_weights(self.n, self.descs, self.w_arr, self.wf_arr, self.wd_arr, _stream()),
+            w_arr[i] = w.data_ptr()
+            wf_arr[i] = base + 2 * self.wf_off[i]
+            wd_arr[i] = None if self.wd_off[i] is None else base + 2 * self.wd_off[i]
+        check(self.lib.zsv_conv3d_pack_weights(self.n, self.descs, w_arr, wf_arr, wd_arr, _stream()),
               "zsv_conv3d_pack_weights")
-        wfs = [buf[o:o + c.wf_bytes // 2] for o, c in zip(self.wf_off, self.convs)]
-        wds = [None if o is None else buf[o:o + c.wd_bytes // 2] for o, c in zip(self.wd_off, self.convs)]
-        return wfs, wds
+        return self.views(buf)
 
     def pack_folded(self, weights, bns, eps: float = BN_EPS):
         """Inference: weights with the BatchNorm that follows each convolution folded in (running statistics).
@@ -196,6 +206,7 @@ class PackPlan:
         base, keep, off = buf.data_ptr(), [], 0
         folds = (BnFold * self.n)()
         out_b = []
+        w_arr, wf_arr, _ = self._arrays()
         for i, (w, (gamma, beta, rm, rv)) in enumerate(zip(weights, bns)):
             _require_cuda(w, "PackPlan.pack_folded")
             tens = []
@@ -205,13 +216,13 @@ class PackPlan:
                     t = t.float().contiguous()
                     keep.append(t)
                 tens.append(t)
-            self.w_arr[i] = tens[0].data_ptr()
-            self.wf_arr[i] = base + 2 * self.wf_off[i]
+            w_arr[i] = tens[0].data_ptr()
+            wf_arr[i] = base + 2 * self.wf_off[i]
             b = biases[off:off + nb[i]]
             off += nb[i]
             out_b.append(b)
             folds[i] = BnFold(tens[1].data_ptr(), tens[2].data_ptr(), tens[3].data_ptr(), tens[4].data_ptr(), b.data_ptr(), eps)
-        check(self.lib.zsv_conv3d_pack_weights_folded(self.n, self.descs, self.w_arr, self.wf_arr, folds, _stream()),
+        check(self.lib.zsv_conv3d_pack_weights_folded(self.n, self.descs, w_arr, wf_arr, folds, _stream()),
               "zsv_conv3d_pack_weights_folded")
         wfs = [buf[o:o + c.wf_bytes // 2] for o, c in zip(self.wf_off, self.convs)]
         return wfs, out_b
@@ -372,11 +383,11 @@ def head_bwd(demb, emb, saved, feat_shape, channels: int, w1, w2, need_wgrad: bo
     dw2 = torch.empty_like(w2) if need_wgrad else None
     db2 = torch.empty(E, dtype=torch.float32, device=dev) if need_wgrad else None
     dfeat = torch.empty(feat_shape, dtype=torch.bfloat16, device=dev) if need_dfeat else None
-    scratch = torch.empty(B * (E + Hd + channels), dtype=torch.float32, device=dev)
+    scratch = torch.empty(lib.zsv_head_bwd_scratch(B, channels, Hd, E), dtype=torch.uint8, device=dev)
     demb = demb.float().contiguous()
     check(lib.zsv_head_bwd(ptr(demb), ptr(emb), ptr(onorm), ptr(pooled), ptr(hidden), B, P, channels, ptr(w1), Hd,
                            ptr(w2), E, eps, ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(dfeat), ptr(scratch),
-                           _stream()), "zsv_head_bwd")
+                           scratch.numel(), _stream()), "zsv_head_bwd")
     return dw1, db1, dw2, db2, dfeat
 
 
@@ -414,29 +425,42 @@ def maxpool3d_fwd(x, channels: int, kernel, padding=(0, 0, 0)):
     pt, ph, pw = padding
     To, Ho, Wo = (T + 2 * pt - kt) // kt + 1, (H + 2 * ph - kh) // kh + 1, (W + 2 * pw - kw) // kw + 1
     y = torch.empty((N, To, Ho, Wo, cp), dtype=torch.bfloat16, device=x.device)
-    am = torch.empty((N, To, Ho, Wo, cp), dtype=torch.int32, device=x.device)
+    am = torch.empty((N, To, Ho, Wo, cp), dtype=torch.uint8, device=x.device)
     check(lib.zsv_maxpool3d_fwd(ptr(x), ptr(y), ptr(am), N, T, H, W, channels, kt, kh, kw, pt, ph, pw, _stream()),
           "zsv_maxpool3d_fwd")
     return y, am
 
 
-def maxpool3d_bwd(dy, argmax, in_shape, channels: int, kernel, padding=(0, 0, 0), relu_mask_src=None):
+def maxpool3d_bwd(dy, argmax, in_shape, channels: int, kernel, padding=(0, 0, 0), relu_pooled=None,
+                  want_bias: bool = False):
+    """-> dx, or (dx, db) with want_bias.  relu_pooled: the pooling output when the pooled tensor was a ReLU output (its
+    ReLU backward is fused); db: bias gradient of the convolution in front of that ReLU, from the same pass."""
     lib = _lib.load()
     N, T, H, W, cp = in_shape
     kt, kh, kw = kernel
     pt, ph, pw = padding
     dx = torch.empty(in_shape, dtype=torch.bfloat16, device=dy.device)
-    check(lib.zsv_maxpool3d_bwd(ptr(dy), ptr(argmax), ptr(relu_mask_src), ptr(dx), N, T, H, W, channels, kt, kh, kw,
-                                pt, ph, pw, _stream()), "zsv_maxpool3d_bwd")
-    return dx
+    db = ws = None
+    if want_bias:
+        db = torch.empty(channels, dtype=torch.float32, device=dy.device)
+        ws = workspace(lib.zsv_bias_grad_workspace(channels), dy.device, "bias_grad")
+    check(lib.zsv_maxpool3d_bwd(ptr(dy), ptr(argmax), ptr(relu_pooled), ptr(dx), N, T, H, W, channels, kt, kh, kw,
+                                pt, ph, pw, ptr(db), ptr(ws), ws.numel() if ws is not None else 0, _stream()),
+          "zsv_maxpool3d_bwd")
+    return (dx, db) if want_bias else dx
 
 
-def relu_bwd(g, out, channels: int):
+def relu_bwd(g, out, channels: int, want_bias: bool = False):
     lib = _lib.load()
     dz = torch.empty_like(g)
     rows = g.numel() // g.shape[-1]
-    check(lib.zsv_relu_bwd(ptr(g), ptr(out), ptr(dz), rows, channels, _stream()), "zsv_relu_bwd")
-    return dz
+    db = ws = None
+    if want_bias:
+        db = torch.empty(channels, dtype=torch.float32, device=g.device)
+        ws = workspace(lib.zsv_bias_grad_workspace(channels), g.device, "bias_grad")
+    check(lib.zsv_relu_bwd(ptr(g), ptr(out), ptr(dz), rows, channels, ptr(db), ptr(ws),
+                           ws.numel() if ws is not None else 0, _stream()), "zsv_relu_bwd")
+    return (dz, db) if want_bias else dz
 
 
 def bias_grad(dy, channels: int):
@@ -453,7 +477,9 @@ def linear_fwd(x, w, b, relu: bool):
     B, K = x.shape
     J = w.shape[0]
     out = torch.empty((B, J), dtype=torch.float32, device=x.device)
-    check(lib.zsv_linear_fwd(ptr(x), ptr(w), ptr(b), ptr(out), B, K, J, int(relu), _stream()), "zsv_linear_fwd")
+    ws = workspace(lib.zsv_linear_workspace(B, K, J), x.device, "linear")
+    check(lib.zsv_linear_fwd(ptr(x), ptr(w), ptr(b), ptr(out), B, K, J, int(relu), ptr(ws), ws.numel(), _stream()),
+          "zsv_linear_fwd")
     return out
 
 
@@ -465,8 +491,8 @@ def linear_bwd(dy, x, w, act=None, need_dx=True, need_dw=True):
     dx = torch.empty((B, K), dtype=torch.float32, device=dev) if need_dx else None
     dw = torch.empty((J, K), dtype=torch.float32, device=dev) if need_dw else None
     db = torch.empty((J,), dtype=torch.float32, device=dev) if need_dw else None
-    scratch = torch.empty((B, J), dtype=torch.float32, device=dev) if act is not None else None
-    check(lib.zsv_linear_bwd(ptr(dy), ptr(x), ptr(w), ptr(act), B, K, J, ptr(dx), ptr(dw), ptr(db), ptr(scratch),
+    ws = workspace(lib.zsv_linear_workspace(B, K, J), dev, "linear")
+    check(lib.zsv_linear_bwd(ptr(dy), ptr(x), ptr(w), ptr(act), B, K, J, ptr(dx), ptr(dw), ptr(db), ptr(ws), ws.numel(),
                              _stream()), "zsv_linear_bwd")
     return dx, dw, db
 
