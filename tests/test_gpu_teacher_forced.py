@@ -20,11 +20,16 @@ pytestmark = pytest.mark.gpu
 
 TOL = 1e-2          # north_star
 TOL_WGRAD = 2e-3    # fp32 accumulation over >= 1e4 positions
-# The two Cin = 3 first layers (stem.0, C3D conv1): dW = sum over ~1e5..1e6 positions of x * dy with random signs, so the
-# sum is ~sqrt(N) * sigma and the bf16 rounding of the two operands (2^-9 each, uncorrelated) leaves ~2^-9 * sqrt(2) of
-# that scale whatever N is; with only 6.6 k / 5.2 k weights the largest one is not far above the typical one, and the
-# max-norm ratio lands at 2-3e-3 (measured 2.3e-3 / 2.8e-3) instead of ~1e-3 on the wide layers.
-TOL_WGRAD_FIRST = 4e-3
+# The three smallest weight tensors (stem.0 6.6 k, stem.3 8.6 k, C3D conv1 5.2 k weights): dW = sum over ~1e5..1e6
+# positions of x * dy with random signs, so the sum is ~sqrt(N) * sigma and the bf16 rounding of the two operands
+# (2^-9 each, uncorrelated) leaves ~2^-9 * sqrt(2) of that scale whatever N is; with so few weights the largest one
+# is not far above the typical one and the max-norm ratio lands at 2-3e-3 (measured 2.3e-3 / 3.0e-3 / 2.8e-3)
+# instead of ~1e-3 on the wide layers.
+TOL_WGRAD_SMALL = 4e-3
+
+
+def _wgrad_tol(cin, cout, kernel):
+    return TOL_WGRAD_SMALL if cin * cout * kernel[0] * kernel[1] * kernel[2] < 10_000 else TOL_WGRAD
 
 
 @pytest.fixture(scope="module")
@@ -68,14 +73,16 @@ def test_every_convolution_teacher_forced(r2plus1d_trace):
     sd, trace, _ = r2plus1d_trace
     specs = engine.all_conv_specs("r2plus1d_18")
     assert len(specs) == 37
-    worst = {}
+    worst, bad = {}, []
     for spec in specs:
         errs = _conv_case(spec, sd, trace)
         for k, v in errs.items():
-            tol = (TOL_WGRAD_FIRST if spec.cin == 3 else TOL_WGRAD) if k == "wgrad" else TOL
-            assert v <= tol, (spec.name, k, v)
+            tol = _wgrad_tol(spec.cin, spec.cout, spec.kernel) if k == "wgrad" else TOL
+            if not v <= tol:
+                bad.append((spec.name, k, v, tol))
             worst[k] = max(worst.get(k, 0.0), v)
     print("worst teacher-forced conv errors", worst)
+    assert not bad, bad
 
 
 def test_every_batchnorm_teacher_forced(r2plus1d_trace):
@@ -83,7 +90,7 @@ def test_every_batchnorm_teacher_forced(r2plus1d_trace):
     instances on the oracle's conv output and the oracle's gradient w.r.t. the BatchNorm output."""
     from zeroshotvideoclassification_b200 import engine, ops
     sd, trace, grads = r2plus1d_trace
-    worst = {}
+    worst, bad = {}, []
     for spec in engine.all_conv_specs("r2plus1d_18"):
         C = spec.cout
         y_ref = trace[spec.name].detach()
@@ -109,14 +116,16 @@ def test_every_batchnorm_teacher_forced(r2plus1d_trace):
             "dgamma": rel_err(dg.cpu(), grads["model." + spec.bn + ".weight"]),
             "dbeta": rel_err(db.cpu(), grads["model." + spec.bn + ".bias"]),
         }
-        for k, v in errs.items():
-            assert v <= TOL, (spec.bn, k, v)
-            worst[k] = max(worst.get(k, 0.0), v)
         # running statistics after this one training-mode forward (momentum 0.1, unbiased variance); same max-norm
         # measure (a channel whose mean is ~0 has no meaningful element-wise relative error)
-        assert rel_err(rm.cpu(), 0.1 * trace[spec.bn + ":mean"]) <= TOL, spec.bn
-        assert rel_err(rv.cpu(), 0.9 + 0.1 * trace[spec.bn + ":var"] * rows / (rows - 1)) <= TOL, spec.bn
+        errs["running_mean"] = rel_err(rm.cpu(), 0.1 * trace[spec.bn + ":mean"])
+        errs["running_var"] = rel_err(rv.cpu(), 0.9 + 0.1 * trace[spec.bn + ":var"] * rows / (rows - 1))
+        for k, v in errs.items():
+            if not v <= TOL:
+                bad.append((spec.bn, k, v))
+            worst[k] = max(worst.get(k, 0.0), v)
     print("worst teacher-forced BatchNorm errors", worst)
+    assert not bad, bad
 
 
 def test_c3d_convolutions_teacher_forced():
@@ -129,7 +138,7 @@ def test_c3d_convolutions_teacher_forced():
     trace = {}
     vo.c3d_train_step_grads(sd, x, z, trace=trace)
     names = ["conv1", "conv2", "conv3a", "conv3b", "conv4a", "conv4b", "conv5a", "conv5b"]
-    worst = {}
+    worst, bad = {}, []
     for i, name in enumerate(names):
         w, b = sd[name + ".weight"], sd[name + ".bias"]
         x_in = trace[name + ":in"]
@@ -152,10 +161,12 @@ def test_c3d_convolutions_teacher_forced():
             errs["dgrad"] = rel_err(from_ndhwc(op.dgrad(dzd, wd), cin), dx_ref)
         torch.cuda.synchronize()
         for k, v in errs.items():
-            tol = (TOL_WGRAD_FIRST if first else TOL_WGRAD) if k == "wgrad" else TOL
-            assert v <= tol, (name, k, v)
+            tol = _wgrad_tol(cin, cout, (3, 3, 3)) if k == "wgrad" else TOL
+            if not v <= tol:
+                bad.append((name, k, v, tol))
             worst[k] = max(worst.get(k, 0.0), v)
     print("worst teacher-forced C3D errors", worst)
+    assert not bad, bad
 
 
 @pytest.mark.parametrize("cin,cout,kernel,padding,dims", [

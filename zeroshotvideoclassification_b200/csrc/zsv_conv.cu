@@ -1453,36 +1453,57 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     }
 }
 
-// dw[co][ci][tap] = sum_split ws[split][tap][ci][co]   (wfold: tap=(dt,dh), ci = dw*8 + c)
-// Transposing reduction through shared memory: a block owns 32 output channels x CI_T input channels x all taps; the
-// split partials are read coalesced along co, the state-dict layout is written in contiguous (ci, tap) runs per co.
+// dw[co][ci][tap] = sum_split ws[split][tap][ci][co]
+// Transposing reduction through shared memory: a block owns 32 output channels x ci_tile input channels x all taps.
+// The split partials are read coalesced along co, four (tap, ci) rows per warp in flight; the tile is staged in OUTPUT
+// order (row = co, column j = ci * ntaps + tap, odd pitch: conflict-free both ways) and the state-dict layout is
+// written in contiguous runs of ci_tile * ntaps floats per output channel.  The element-wise kernel below writes one
+// 4-byte element per 32-byte sector instead (20-45 us per layer-3/4 tensor; this kernel: the time of reading the
+// partials once).
 __global__ void __launch_bounds__(256)
 wgrad_finalize_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int ntaps, int ci_pitch,
                       int co_pitch, int Cin, int Cout, int ci_tile) {
-    extern __shared__ float tile[];   // [ntaps][ci_tile][33]
+    extern __shared__ float tile[];   // [32][run | 1]
+    const int run = ci_tile * ntaps;
+    const int pitch = run | 1;
     const int co0 = blockIdx.x * 32;
     const int ci0 = blockIdx.y * ci_tile;
     const long long split_stride = (long long)ntaps * ci_pitch * co_pitch;
     const int lane_co = threadIdx.x & 31;
-    const int row0 = threadIdx.x >> 5;    // 8 (tap, ci) rows per pass
-    const int nrows = ntaps * ci_tile;
-    for (int r = row0; r < nrows; r += 8) {
-        const int tap = r / ci_tile, ci = r - tap * ci_tile;
-        float acc = 0.f;
-        if (ci0 + ci < ci_pitch && co0 + lane_co < co_pitch) {
-            const float* p = ws + ((long long)tap * ci_pitch + ci0 + ci) * co_pitch + co0 + lane_co;
-            for (int sp = 0; sp < splits; ++sp) acc += p[sp * split_stride];
+    const int warp = threadIdx.x >> 5;
+    const bool co_ok = co0 + lane_co < co_pitch;
+    for (int r0 = warp; r0 < run; r0 += 32) {          // rows r0, r0+8, r0+16, r0+24 of this warp
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* p[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = r0 + 8 * u;
+            const int tap = r / ci_tile, ci = r - tap * ci_tile;
+            ok[u] = r < run && co_ok && ci0 + ci < ci_pitch;
+            p[u] = ws + ((long long)tap * ci_pitch + ci0 + ci) * co_pitch + co0 + lane_co;
         }
-        tile[(tap * ci_tile + ci) * 33 + lane_co] = acc;
+        for (int sp = 0; sp < splits; ++sp) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (ok[u]) acc[u] += p[u][sp * split_stride];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = r0 + 8 * u;
+            if (r < run) {
+                const int tap = r / ci_tile, ci = r - tap * ci_tile;
+                tile[lane_co * pitch + ci * ntaps + tap] = acc[u];
+            }
+        }
     }
     __syncthreads();
-    const int run = ci_tile * ntaps;      // contiguous floats per output channel
-    for (int i = threadIdx.x; i < 32 * run; i += 256) {
-        const int co = i / run;
-        const int j = i - co * run;       // j = ci * ntaps + tap
-        const int ci = j / ntaps, tap = j - ci * ntaps;
-        if (co0 + co < Cout && ci0 + ci < Cin)
-            dw[((long long)(co0 + co) * Cin + ci0 + ci) * ntaps + tap] = tile[(tap * ci_tile + ci) * 33 + co];
+    const int ci_len = min(ci_tile, Cin - ci0);
+    const int len = ci_len * ntaps;   // contiguous floats per output channel
+    for (int i = threadIdx.x; i < 32 * len; i += 256) {
+        const int co = i / len;
+        const int j = i - co * len;
+        if (co0 + co < Cout) dw[((long long)(co0 + co) * Cin + ci0) * ntaps + j] = tile[co * pitch + j];
     }
 }
 
@@ -2712,19 +2733,10 @@ int plan_wgrad(const zsv_conv_desc* d, const Shape& s, WgradPlan* p) {
     if (p->n_tiles > 1) p->bn_tile = (p->bn_tile + 63) & ~63;  // keep panel-aligned tile origins
     p->n_tiles = ceil_div(cols16, p->bn_tile);
     p->nbp = ceil_div(p->bn_tile, 64);
-    // Optional: two M tiles per CTA share the dy panels of a stage (fewer L2 / DRAM re-reads of dy).  Measured: alone, the
-    // layer-1 / layer-2 spatial weight gradients get faster (244 -> 220 us, 148 -> 135 us) and shallow ones slower
-    // (178 -> 217 us on the temporal 144->64: 2 ring stages instead of 4, uneven tiles), hence the rule below; inside
-    // the training step, where these kernels run on the low-priority stream beside the BatchNorm kernels, the larger
-    // CTAs cost 0.8 % of step time (A/B in one session: 14.23 vs 14.12 ms), so it is off unless ZSV_WGRAD_MT2 is set.
+    // (two M tiles per CTA sharing the dy panels of a stage were measured in round 1: 10 % faster alone on the layer-1 / 2
+    // spatial weight gradients, 0.8 % slower inside the training step; the option is gone, the kernel keeps one)
     const int sms = std::max(1, sm_count());
     p->mt = 1;
-    if (getenv("ZSV_WGRAD_MT2") && p->nbp >= 3 && p->m_tiles >= 2 &&
-        2 * (4 + p->nbp) * (int)kPanelBytes + 2048 <= 227 * 1024 && 2 * ((p->bn_tile + 31) & ~31) <= 512) {
-        const int tiles2 = ceil_div(p->m_tiles, 2) * p->n_tiles;
-        const int splits2 = std::min(std::max(1, (2 * sms) / tiles2), p->num_kb);
-        if (ceil_div(p->num_kb, splits2) >= 32) p->mt = 2;
-    }
     p->m_tiles = ceil_div(p->m_tiles, p->mt);
     const int tiles = p->m_tiles * p->n_tiles;
     // split the position axis so that the CTAs fill the GPU ONCE: measured against two waves (the previous choice) the
@@ -2872,6 +2884,32 @@ int launch_wgrad_halo(const WgradHaloPlan& p, const zsv_conv_desc* d, const Shap
 }
 }  // namespace
 
+namespace {
+// split partials ws[split][tap][ci][co] -> dw[co][ci][tap] (fp32, the state-dict layout)
+int launch_wgrad_finalize(const zsv_conv_desc* d, const Shape& s, const float* ws, float* dw, int splits, int ci_pitch,
+                          int co_pitch, cudaStream_t st) {
+    const long long wtotal = (long long)s.ftaps * ci_pitch * co_pitch;
+    if (s.wfold || getenv("ZSV_DEBUG_FINALIZE_SMALL")) {
+        // W-folded first layer (tap = (dt,dh), ci = dw*8 + c): a few thousand weights, element-wise
+        const int blocks = (int)std::min<long long>(ceil_div_ll(wtotal, 256), 148 * 8);
+        wgrad_finalize_small_kernel<<<blocks, 256, 0, st>>>(ws, dw, splits, s.ftaps, ci_pitch, co_pitch, d->Cin, d->Cout,
+                                                            s.wfold ? d->kw : 0, s.ntaps);
+        ZSV_LAUNCH_CHECK("wgrad_finalize_small_kernel");
+        return ZSV_OK;
+    }
+    // input channels per block: runs of ~256-288 floats per output channel; fewer when that leaves SMs without a block
+    // (small tensors summed over many splits)
+    int ci_tile = std::max(8, std::min(64, (288 / s.ftaps) & ~7));
+    while (ci_tile > 8 && (long long)ceil_div(d->Cout, 32) * ceil_div(d->Cin, ci_tile) < sm_count()) ci_tile >>= 1;
+    const size_t fsm = (size_t)32 * ((ci_tile * s.ftaps) | 1) * sizeof(float);
+    if (fsm > 48 * 1024) return fail(ZSV_ERR_UNSUPPORTED, "wgrad finalize: %d taps do not fit the staging tile", s.ftaps);
+    dim3 fgrid(ceil_div(d->Cout, 32), ceil_div(d->Cin, ci_tile));
+    wgrad_finalize_kernel<<<fgrid, 256, fsm, st>>>(ws, dw, splits, s.ftaps, ci_pitch, co_pitch, d->Cin, d->Cout, ci_tile);
+    ZSV_LAUNCH_CHECK("wgrad_finalize_kernel");
+    return ZSV_OK;
+}
+}  // namespace
+
 extern "C" size_t zsv_conv3d_wgrad_workspace(const zsv_conv_desc* d) {
     Shape s;
     if (check_desc(d, &s)) return 0;
@@ -2894,12 +2932,7 @@ extern "C" int zsv_conv3d_wgrad(const zsv_conv_desc* d, const void* x, const voi
             return fail(ZSV_ERR_WORKSPACE, "wgrad: workspace %zu < required %zu bytes", workspace_bytes, hp.ws_bytes);
         rc = launch_wgrad_halo(hp, d, s, x, dy, workspace, st);
         if (rc) return rc;
-        const long long wtotal = (long long)s.ntaps * hp.ci_pitch * hp.co_pitch;
-        const int blocks = (int)std::min<long long>(ceil_div_ll(wtotal, 256), 148 * 8);
-        wgrad_finalize_small_kernel<<<blocks, 256, 0, st>>>((const float*)workspace, dw, hp.splits, s.ntaps, hp.ci_pitch,
-                                                            hp.co_pitch, d->Cin, d->Cout, 0, s.ntaps);
-        ZSV_LAUNCH_CHECK("wgrad_finalize_kernel");
-        return ZSV_OK;
+        return launch_wgrad_finalize(d, s, (const float*)workspace, dw, hp.splits, hp.ci_pitch, hp.co_pitch, st);
     }
     WgradPlan p;
     plan_wgrad(d, s, &p);
@@ -2949,18 +2982,5 @@ extern "C" int zsv_conv3d_wgrad(const zsv_conv_desc* d, const void* x, const voi
     wgrad_mnmajor_kernel<<<grid, 192, smem, st>>>(pack, mapB, a);
     ZSV_LAUNCH_CHECK("wgrad_mnmajor_kernel");
 
-    const long long wtotal = (long long)s.ftaps * p.ci_pitch * p.co_pitch;
-    if (s.wfold || wtotal < (1LL << 22)) {
-        const int blocks = (int)std::min<long long>(ceil_div_ll(wtotal, 256), 148 * 8);
-        wgrad_finalize_small_kernel<<<blocks, 256, 0, st>>>((const float*)workspace, dw, p.splits, s.ftaps, p.ci_pitch,
-                                                            p.co_pitch, d->Cin, d->Cout, s.wfold ? d->kw : 0, s.ntaps);
-    } else {
-        const int ci_tile = s.ftaps <= 9 ? 32 : 8;
-        const size_t fsm = (size_t)s.ftaps * ci_tile * 33 * sizeof(float);
-        dim3 fgrid(ceil_div(d->Cout, 32), ceil_div(d->Cin, ci_tile));
-        wgrad_finalize_kernel<<<fgrid, 256, fsm, st>>>((const float*)workspace, dw, p.splits, s.ftaps, p.ci_pitch,
-                                                       p.co_pitch, d->Cin, d->Cout, ci_tile);
-    }
-    ZSV_LAUNCH_CHECK("wgrad_finalize_kernel");
-    return ZSV_OK;
+    return launch_wgrad_finalize(d, s, (const float*)workspace, dw, p.splits, p.ci_pitch, p.co_pitch, st);
 }
