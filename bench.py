@@ -370,11 +370,13 @@ def run_b200(args):
         optimizer = FusedAdam(model.parameters(), lr=1e-3, model=model)
     else:
         optimizer = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=args.graph, fused=True)
-    sync = zdist.GradSync(bucket_bytes=int(float(os.environ.get("ZSV_BUCKET_MB", "32")) * (1 << 20))) if world > 1 else None
+    sync = zdist.GradSync(bucket_bytes=int(float(os.environ.get("ZSV_BUCKET_MB", "8")) * (1 << 20))) if world > 1 else None
     zdist.set_grad_sync(sync)
     # parameters whose gradients do not come out of the backbone Function (GradSync covers those): the MLP head of
     # network.Model; C3D has no bucketed sync, all of its gradients are reduced after backward
     head_params = list(model.output2emb_proj.parameters()) if hasattr(model, "output2emb_proj") else list(model.parameters())
+    if sync is not None:
+        sync.attach(head_params)          # all-reduced in place from a post-accumulate hook, during backward
 
     g = torch.Generator().manual_seed(1 + rank)
     x_host = torch.randn(B, 1, 3, 16, 112, 112, generator=g).pin_memory()
@@ -401,8 +403,8 @@ def run_b200(args):
             pred = nearest_class(emb.detach(), cls_dev, 1)[:, 0]
             acc_sum.add_((pred == labels_dev).float().mean())
         loss.backward()
-        if world > 1:
-            zdist.sync_head_grads(head_params)
+        if sync is not None:
+            sync.finish()                 # no-op when the backbone's backward already waited for everything
         optimizer.step()
         cur.wait_stream(acc_stream)
         return loss
@@ -640,6 +642,7 @@ def run_b200(args):
     }
     if sync is not None:
         line["allreduce_bytes_per_step"] = sync.bytes_per_step
+        line["allreduce_collectives_per_step"] = sync.collectives_per_step
     if consistency is not None:
         line["replicas_consistent"] = consistency["ok"]
         line["replica_check"] = consistency
@@ -668,14 +671,19 @@ def replica_consistency(model, step, x_dev, z_dev, zdist, dist, dev, world):
         return live, torch.cat([p.grad.detach().reshape(-1).float() for p in live])
 
     sync = zdist.active_grad_sync()
-    zdist.set_grad_sync(None)
+    head = list(model.output2emb_proj.parameters()) if hasattr(model, "output2emb_proj") else params
+    zdist.set_grad_sync(None)            # exchange off: purely local gradients
+    if sync is not None:
+        sync.detach()
     live, local = grads_of_one_backward()
     dist.all_reduce(local, op=dist.ReduceOp.SUM)
     local /= world
-    zdist.set_grad_sync(sync)
+    zdist.set_grad_sync(sync)            # exchange on: arena slices + head hooks, overlapped with backward
+    if sync is not None:
+        sync.attach(head)
     live2, _ = grads_of_one_backward()
-    head = list(model.output2emb_proj.parameters()) if hasattr(model, "output2emb_proj") else params
-    zdist.sync_head_grads(head)
+    if sync is not None:
+        sync.finish()
     synced = torch.cat([p.grad.detach().reshape(-1).float() for p in live2])
     scale = float(local.abs().max())
     err = float((synced - local).abs().max()) / max(scale, 1e-30)

@@ -48,7 +48,29 @@ def _worker(rank, world, port, bucket_bytes, q):
         p.grad = torch.full_like(p, float(rank))
     zdist.sync_head_grads(list(lin.parameters()))
     ok &= all(bool(torch.allclose(p.grad, torch.full_like(p, 0.5))) for p in lin.parameters())
-    q.put((rank, ok, sync.bytes_reduced))
+    nbytes_dict = sync.bytes_reduced
+    # flat arena: slices handed over block by block are averaged IN PLACE, merged until the bucket threshold is met
+    arena = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    before = sync.bytes_reduced
+    sync.submit_range(arena, 0, 300)
+    sync.submit_range(arena, 300, 640)      # extends the pending slice
+    sync.submit_range(arena, 700, 1000)     # a gap: the pending slice is flushed first
+    sync.finish()
+    expect = torch.arange(1000, dtype=torch.float32) * 1.5
+    ok &= bool(torch.allclose(arena[:640], expect[:640])) and bool(torch.allclose(arena[700:], expect[700:]))
+    ok &= bool(torch.equal(arena[640:700], torch.arange(640, 700, dtype=torch.float32) * (rank + 1)))   # untouched gap
+    ok &= sync.bytes_reduced - before == 4 * (640 + 300)
+    # parameters accumulated by autograd: reduced in place from a post-accumulate hook during backward
+    lin2 = torch.nn.Linear(3, 2)
+    with torch.no_grad():
+        for p in lin2.parameters():
+            p.fill_(1.0)
+    sync.attach(list(lin2.parameters()))
+    lin2(torch.full((1, 3), float(rank + 1))).sum().backward()
+    sync.finish()
+    ok &= bool(torch.allclose(lin2.weight.grad, torch.full((2, 3), 1.5))) and bool(torch.allclose(lin2.bias.grad, torch.ones(2)))
+    sync.detach()
+    q.put((rank, ok, nbytes_dict))
     dist.destroy_process_group()
 
 

@@ -345,3 +345,31 @@ def test_folded_inference_matches_unfolded_eval_and_tracks_weight_updates(arch):
         model.model.stem[0].weight.mul_(1.5)                      # in-place update bumps the version counter
         emb_g, _ = model(x)
     assert rel_err(emb_g.cpu(), emb_f.cpu()) > 1e-3
+
+
+def test_backbone_gradients_live_in_one_flat_arena():
+    """The backbone's backward writes every parameter gradient into ONE flat fp32 buffer in the order it is produced
+    (ops.GradArena), and ``param.grad`` is a view of it (autograd adopts the returned tensors, no copy): the
+    data-parallel exchange all-reduces contiguous slices of that buffer in place (dist.GradSync.submit_range)."""
+    from zeroshotvideoclassification_b200 import video_models as vm
+    torch.manual_seed(0)
+    model = vm.get_network(vm.default_opt("r2plus1d_18")).cuda().train()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 1, 3, 8, 32, 32, generator=g).cuda()
+    z = F.normalize(torch.randn(2, 300, generator=g)).cuda()
+    emb, _ = model(x)
+    F.mse_loss(emb, z).backward()
+    grads = [p.grad for p in model.model.parameters() if p.grad is not None]
+    assert len(grads) == 3 * 37
+    lo = min(t.data_ptr() for t in grads)
+    hi = max(t.data_ptr() + 4 * t.numel() for t in grads)
+    live = sum(t.numel() for t in grads)
+    assert live == 31_300_125                                      # backbone parameters that receive a gradient
+    # one buffer: the span is the live gradients plus alignment padding / unused BatchNorm rows, nothing else
+    assert hi - lo <= 4 * (live + 64 * 2 * 37 + 4 * 7232), (hi - lo, 4 * live)
+    storages = {t.untyped_storage().data_ptr() for t in grads}
+    assert len(storages) == 1
+    # deepest block first: layer4.1's last BatchNorm sits at the front, the stem's first convolution at the back
+    first = model.model.layer4[1].conv2[1].weight.grad.data_ptr()
+    last = model.model.stem[0].weight.grad.data_ptr()
+    assert first == lo and last == max(t.data_ptr() for t in grads)

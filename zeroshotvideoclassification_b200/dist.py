@@ -20,20 +20,81 @@ import torch.distributed as dist
 
 
 class GradSync:
-    """Bucketed asynchronous all-reduce(average) of gradients handed over in backward order."""
+    """Asynchronous all-reduce(average) of gradients handed over in backward order.
 
-    def __init__(self, group=None, bucket_bytes: int = 32 << 20):
+    Two ways in:
+      * ``submit_range(flat, lo, hi)`` -- the backbone's backward writes every gradient into one flat arena
+        (ops.GradArena) in the order it is produced and hands over the slice each residual block filled; slices are
+        all-reduced IN PLACE as soon as ``bucket_bytes`` are pending, so there is no gather copy, no scaling pass and no
+        copy back (with NCCL the average is the collective's own AVG op);
+      * ``attach(params)`` -- parameters whose gradients autograd accumulates itself (the MLP head): a
+        post-accumulate hook all-reduces ``param.grad`` in place the moment it exists, i.e. before the backbone's
+        backward even starts, instead of a second blocking collective after ``loss.backward()``.
+    ``finish()`` makes the current stream wait for everything in flight (called by the backbone's backward)."""
+
+    def __init__(self, group=None, bucket_bytes: int = 8 << 20):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.bucket_bytes = bucket_bytes
-        self._pending: List[tuple] = []       # (work, flat, [(name, tensor)])
+        self._works: List[tuple] = []         # (work, tensor reduced in place, needs_scale)
+        self._pending: List[tuple] = []       # dict API: (work, flat, [(name, tensor)])
         self._cur: List[tuple] = []
         self._cur_bytes = 0
+        self._range = None                    # (flat, lo, hi) handed over but not yet flushed
         self.bytes_reduced = 0
         self.bytes_per_step = 0           # bytes all-reduced by the most recent backward pass
         self._step_bytes = 0
+        self._hooks = []
+        self.collectives_per_step = 0
+        self._step_collectives = 0
+        nccl = dist.is_initialized() and dist.get_backend(group) == "nccl"
+        self._op = dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM      # gloo (CPU tests) has no AVG: SUM + scale
 
-    # called from the backward pass with fresh fp32 gradients
+    def _all_reduce(self, t: torch.Tensor) -> None:
+        work = dist.all_reduce(t, op=self._op, group=self.group, async_op=True)
+        self._works.append((work, t, self._op == dist.ReduceOp.SUM))
+        n = t.numel() * t.element_size()
+        self.bytes_reduced += n
+        self._step_bytes += n
+        self._step_collectives += 1
+
+    # -- flat arena ------------------------------------------------------------------------------------------
+    def submit_range(self, flat: torch.Tensor, lo: int, hi: int) -> None:
+        """flat[lo:hi] is final on the current stream; consecutive calls extend one pending slice."""
+        if self.world == 1 or hi <= lo:
+            return
+        if self._range is not None and self._range[0] is flat and self._range[2] == lo:
+            self._range = (flat, self._range[1], hi)
+        else:
+            self._flush_range()
+            self._range = (flat, lo, hi)
+        if (self._range[2] - self._range[1]) * flat.element_size() >= self.bucket_bytes:
+            self._flush_range()
+
+    def _flush_range(self) -> None:
+        if self._range is not None:
+            flat, lo, hi = self._range
+            self._range = None
+            self._all_reduce(flat[lo:hi])
+
+    # -- parameters accumulated by autograd ------------------------------------------------------------------------
+    def attach(self, params) -> None:
+        if self.world == 1:
+            return
+        for p in params:
+            if p.requires_grad:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    def _on_grad(self, p: torch.Tensor) -> None:
+        if p.grad is not None:
+            self._all_reduce(p.grad)
+
+    def detach(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+    # -- dict API: called with fresh fp32 gradients (kept for callers without an arena) ----------------------------
     def submit(self, grads: Dict[str, torch.Tensor]) -> None:
         if self.world == 1:
             return
@@ -50,26 +111,30 @@ class GradSync:
         items = self._cur
         self._cur, self._cur_bytes = [], 0
         flat = torch.cat([g.reshape(-1) for _, g in items])
-        self.bytes_reduced += flat.numel() * flat.element_size()
-        self._step_bytes += flat.numel() * flat.element_size()
-        # SUM + scale keeps gloo (CPU tests) and NCCL on the same code path
-        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self._pending.append((work, flat, items))
+        self._all_reduce(flat)
+        self._pending.append((flat, items))
 
     def finish(self) -> Dict[str, torch.Tensor]:
-        """Wait for every bucket; returns the averaged gradients keyed like the submitted ones."""
+        """Wait (on the current stream) for every collective in flight; returns the averaged gradients of the dict API
+        keyed like the submitted ones (arena slices and attached parameters are averaged in place)."""
         self.flush()
-        out: Dict[str, torch.Tensor] = {}
-        for work, flat, items in self._pending:
+        self._flush_range()
+        for work, t, needs_scale in self._works:
             work.wait()
-            flat.mul_(1.0 / self.world)
+            if needs_scale:
+                t.mul_(1.0 / self.world)
+        self._works = []
+        out: Dict[str, torch.Tensor] = {}
+        for flat, items in self._pending:
             off = 0
             for name, g in items:
                 n = g.numel()
                 out[name] = flat[off:off + n].view(g.shape)
                 off += n
         self._pending = []
-        self.bytes_per_step, self._step_bytes = self._step_bytes, 0
+        if self._step_collectives:        # a second finish() of the same step (nothing in flight) keeps the counters
+            self.bytes_per_step, self._step_bytes = self._step_bytes, 0
+            self.collectives_per_step, self._step_collectives = self._step_collectives, 0
         return out
 
 
@@ -105,7 +170,8 @@ def init_from_env(backend: Optional[str] = None):
 
 
 def sync_head_grads(params) -> None:
-    """All-reduce(average) the (tiny) gradients of parameters outside the backbone Function (the MLP head)."""
+    """All-reduce(average) the (tiny) gradients of parameters outside the backbone Function (the MLP head), blocking.
+    Not needed for parameters handed to ``GradSync.attach`` (they are reduced from a hook during backward)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return
     gs = [p.grad for p in params if p.grad is not None]

@@ -293,6 +293,7 @@ class BackboneRunner:
         self.stem_recs: List[UnitRec] = []
         self.block_recs: List[BlockRec] = []
         self._side_keep: List[tuple] = []       # tensors in use by weight gradients running on the side stream
+        self.arena: Optional[ops.GradArena] = None   # flat gradient buffer of the backward pass in progress
         self.packed: Dict[str, tuple] = {}      # bf16 weight images of the whole network, packed in one launch
         self.nbt: List[torch.Tensor] = []       # num_batches_tracked counters, bumped once per forward in one launch
 
@@ -421,14 +422,16 @@ class BackboneRunner:
                 main = torch.cuda.current_stream(dy.device)
                 side = _side_stream(dy.device)
                 side.wait_stream(main)                     # dy (and x) are complete on the main stream
+                dw_out = self._take(rec.spec.cout, rec.spec.cin, *rec.spec.kernel)    # allocated on the main stream
                 with torch.cuda.stream(side):
-                    dw, _ = rec.op.wgrad(rec.x, dy)
+                    dw, _ = rec.op.wgrad(rec.x, dy, out=dw_out)
                 # x / dy were allocated on the main stream: keep them referenced until the main stream has joined
                 # the side stream (join_side), so the caching allocator cannot hand their memory out early
                 self._side_keep.append((rec.x, dy, dw))
                 grads[rec.spec.name + ".weight"] = dw
             else:
-                grads[rec.spec.name + ".weight"], _ = rec.op.wgrad(rec.x, dy)
+                grads[rec.spec.name + ".weight"], _ = rec.op.wgrad(
+                    rec.x, dy, out=self._take(rec.spec.cout, rec.spec.cin, *rec.spec.kernel))
         if not need_dx:
             return None
         # Fusing pays when the tile's main loop is long compared with its epilogue (few output channels, deep reduction:
@@ -452,10 +455,12 @@ class BackboneRunner:
         gamma = self.t[rec.spec.bn + ".weight"]
         if isinstance(gin, tuple):
             dz, partial, nrows = gin
-            dy, dgamma, dbeta = ops.bn_bwd_finish(dz, rec.y, rec.mean, rec.invstd, gamma, partial, nrows, rec.spec.cout)
+            dy, dgamma, dbeta = ops.bn_bwd_finish(dz, rec.y, rec.mean, rec.invstd, gamma, partial, nrows, rec.spec.cout,
+                                                  grad_out=self._take(2, rec.spec.cout))
         else:
             dy, _, _, dgamma, dbeta, _, _ = ops.bn_bwd(gin, None, 2 if rec.relu else 0, rec.y, rec.mean, rec.invstd,
-                                                       gamma, rec.spec.cout, mask_scale=rec.scale, mask_shift=rec.shift)
+                                                       gamma, rec.spec.cout, mask_scale=rec.scale, mask_shift=rec.shift,
+                                                       grad_out=self._take(2, rec.spec.cout))
         grads[rec.spec.bn + ".weight"] = dgamma
         grads[rec.spec.bn + ".bias"] = dbeta
         return self._conv_bwd(rec, dy, grads, want, addend, need_dx, producer)
@@ -468,13 +473,14 @@ class BackboneRunner:
         if ds is not None:
             dy_t, dy_d, _, dg, db, dg2, db2 = ops.bn_bwd(
                 g, brec.out, True, tail.y, tail.mean, tail.invstd, self.t[tail.spec.bn + ".weight"],
-                tail.spec.cout, y2=ds.y, mean2=ds.mean, invstd2=ds.invstd, gamma2=self.t[ds.spec.bn + ".weight"])
+                tail.spec.cout, y2=ds.y, mean2=ds.mean, invstd2=ds.invstd, gamma2=self.t[ds.spec.bn + ".weight"],
+                grad_out=self._take(4, tail.spec.cout))
             grads[ds.spec.bn + ".weight"], grads[ds.spec.bn + ".bias"] = dg2, db2
             dz = None
         else:
             dy_t, _, dz, dg, db, _, _ = ops.bn_bwd(
                 g, brec.out, True, tail.y, tail.mean, tail.invstd, self.t[tail.spec.bn + ".weight"],
-                tail.spec.cout, want_dz=True)
+                tail.spec.cout, want_dz=True, grad_out=self._take(2, tail.spec.cout))
         grads[tail.spec.bn + ".weight"], grads[tail.spec.bn + ".bias"] = dg, db
         ga = self._conv_bwd(tail, dy_t, grads, want, producer=u[-2])         # grad w.r.t. the previous unit's output
         for i in range(len(u) - 2, 0, -1):
@@ -484,8 +490,14 @@ class BackboneRunner:
             return self._conv_bwd(ds, dy_d, grads, want, addend=gx)          # + projected shortcut
         return self._unit_bwd(u[0], ga, grads, want, addend=dz, producer=producer)   # + identity shortcut
 
+    def _take(self, *shape) -> Optional[torch.Tensor]:
+        """Slice of this backward pass's gradient arena (None outside ``backward``: the op allocates its own)."""
+        return self.arena.take(*shape) if self.arena is not None else None
+
     def backward(self, g: torch.Tensor, want: Dict[str, bool]) -> Dict[str, torch.Tensor]:
-        """g: gradient w.r.t. the backbone output (bf16 NDHWC).  Returns grads keyed by parameter name."""
+        """g: gradient w.r.t. the backbone output (bf16 NDHWC).  Returns grads keyed by parameter name; all of them are
+        views of ONE flat fp32 arena laid out in the order they are produced, so the data-parallel exchange all-reduces
+        contiguous slices in place."""
         if not self.train:
             raise NotImplementedError("backward through eval-mode BatchNorm is not part of the hot path "
                                       "(the reference only back-propagates in train mode, main.py:143,195)")
@@ -493,26 +505,31 @@ class BackboneRunner:
         sync = zdist.active_grad_sync()
         grads: Dict[str, torch.Tensor] = {}
         g = g.contiguous()
+        # one slot per convolution: its weight, (dgamma, dbeta) of its BatchNorm (4 rows when two share a pass)
+        numels = []
+        for c in all_conv_specs(self.arch):
+            numels += [c.cout * c.cin * c.kernel[0] * c.kernel[1] * c.kernel[2], 4 * c.cout]
+        self.arena = ops.GradArena(g.device, numels)
+        mark = 0
         for bi in range(len(self.block_recs) - 1, -1, -1):
             brec = self.block_recs[bi]
-            blk: Dict[str, torch.Tensor] = {}
             # the first block's input is the stem's conv->BN->ReLU output: its BatchNorm backward is fused as well
-            g = self.block_backward(brec, g, blk, want, producer=self.stem_recs[-1] if bi == 0 else None)
+            g = self.block_backward(brec, g, grads, want, producer=self.stem_recs[-1] if bi == 0 else None)
+            dev = g[0].device if isinstance(g, tuple) else g.device
             if sync is not None:
-                self.join_side(g[0].device if isinstance(g, tuple) else g.device)
-                sync.submit(blk)          # all-reduce of this block overlaps the next block's backward
-            grads.update(blk)
-        blk = {}
+                self.join_side(dev)
+                sync.submit_range(self.arena.buf, mark, self.arena.off)   # overlaps the next block's backward
+                mark = self.arena.off
+            elif len(self._side_keep) > 12:
+                self.join_side(dev)       # bound the tensors pinned for the side stream (single GPU)
         for si in range(len(self.stem_recs) - 1, 0, -1):
-            g = self._unit_bwd(self.stem_recs[si], g, blk, want, producer=self.stem_recs[si - 1])
-        self._unit_bwd(self.stem_recs[0], g, blk, want, need_dx=False)
+            g = self._unit_bwd(self.stem_recs[si], g, grads, want, producer=self.stem_recs[si - 1])
+        self._unit_bwd(self.stem_recs[0], g, grads, want, need_dx=False)
         self.join_side(self.stem_recs[0].y.device)
         if sync is not None:
-            sync.submit(blk)
-            grads.update(blk)
-            grads.update(sync.finish())   # averaged gradients replace the local ones
-        else:
-            grads.update(blk)
+            sync.submit_range(self.arena.buf, mark, self.arena.off)
+            sync.finish()                 # averaged in place: the views in `grads` now hold the global gradients
+        self.arena = None
         return grads
 
 

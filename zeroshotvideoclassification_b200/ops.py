@@ -66,6 +66,29 @@ def workspace(nbytes: int, device, tag: str = "default") -> torch.Tensor:
     return buf
 
 
+class GradArena:
+    """One flat fp32 buffer for all parameter gradients of one backward pass, carved in the order the gradients are
+    produced (deepest block first).  The data-parallel exchange all-reduces contiguous slices of it in place -- no
+    gather copy, no copy back (dist.GradSync.submit_range) -- and every ``param.grad`` is a view of it."""
+
+    ALIGN = 64      # elements: every tensor starts on a 256-byte boundary
+
+    def __init__(self, device, numels):
+        self.capacity = sum((n + self.ALIGN - 1) // self.ALIGN * self.ALIGN for n in numels)
+        self.buf = torch.empty(max(self.capacity, 1), dtype=torch.float32, device=device)
+        self.off = 0
+
+    def take(self, *shape) -> torch.Tensor:
+        n = 1
+        for d in shape:
+            n *= d
+        if self.off + n > self.capacity:
+            raise RuntimeError("GradArena: more gradients than the plan announced")
+        out = self.buf[self.off:self.off + n].view(*shape)
+        self.off += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        return out
+
+
 class Conv3d:
     """One convolution of fixed geometry: descriptor + derived sizes.  Mirrors an ``nn.Conv3d`` of the
     reference (resnet.py:40-52,181-184,271; network.py:102-117)."""
@@ -132,8 +155,9 @@ class Conv3d:
                                             _stream()), "zsv_conv3d_dgrad")
         return dz, partial, int(f.rows_written)
 
-    def wgrad(self, x, dy, want_bias: bool = False):
-        dw = torch.empty((self.cout, self.cin, *self.kernel), dtype=torch.float32, device=dy.device)
+    def wgrad(self, x, dy, want_bias: bool = False, out=None):
+        dw = out if out is not None else torch.empty((self.cout, self.cin, *self.kernel), dtype=torch.float32,
+                                                     device=dy.device)
         ws = workspace(self.wgrad_ws, dy.device, "wgrad")
         with _Timed("wgrad", self):
             check(self.lib.zsv_conv3d_wgrad(C.byref(self.desc), ptr(x), ptr(dy), ptr(dw), ptr(ws), ws.numel(),
@@ -297,12 +321,13 @@ def bn_finalize(ps, pq, channels: int, count: int, gamma, beta, running_mean, ru
     return scale, shift, mean, invstd
 
 
-def bn_bwd_finish(dz, y, mean, invstd, gamma, partial, partial_rows: int, channels: int):
-    """Second pass of BatchNorm backward from the sums a fused dgrad left behind -> (dy, dgamma, dbeta)."""
+def bn_bwd_finish(dz, y, mean, invstd, gamma, partial, partial_rows: int, channels: int, grad_out=None):
+    """Second pass of BatchNorm backward from the sums a fused dgrad left behind -> (dy, dgamma, dbeta).
+    grad_out: optional fp32 [2][channels] buffer that receives (dbeta, dgamma) (a slice of the gradient arena)."""
     lib = _lib.load()
     rows = y.numel() // y.shape[-1]
     dy = torch.empty_like(y)
-    dgb = torch.empty((2, channels), dtype=torch.float32, device=y.device)
+    dgb = grad_out if grad_out is not None else torch.empty((2, channels), dtype=torch.float32, device=y.device)
     ws = workspace(4 * cpad(channels) * 4, y.device, "bn_bwd_finish")
     check(lib.zsv_bn_bwd_finish(ptr(dz), ptr(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(partial), partial_rows, ptr(dy),
                                 ptr(dgb[1]), ptr(dgb[0]), rows, channels, ptr(ws), ws.numel(), _stream()),
@@ -329,7 +354,7 @@ def bn_apply(y, scale, shift, channels: int, relu: bool, y2=None, scale2=None, s
 
 
 def bn_bwd(g, out, relu, y, mean, invstd, gamma, channels: int, y2=None, mean2=None, invstd2=None, gamma2=None,
-           want_dz: bool = False, mask_scale=None, mask_shift=None):
+           want_dz: bool = False, mask_scale=None, mask_shift=None, grad_out=None):
     """Returns (dy, dy2, dz, dgamma, dbeta, dgamma2, dbeta2).  relu: False/0, True/1 (mask from `out`) or 2 (mask
     recomputed from y with the forward's scale/shift)."""
     relu = int(relu)
@@ -338,7 +363,8 @@ def bn_bwd(g, out, relu, y, mean, invstd, gamma, channels: int, y2=None, mean2=N
     dy = torch.empty_like(y)
     dy2 = torch.empty_like(y2) if y2 is not None else None
     dz = torch.empty_like(y) if want_dz else None
-    dgb = torch.empty((4, channels), dtype=torch.float32, device=y.device)
+    # (dgamma, dbeta[, dgamma2, dbeta2]) rows; grad_out: a slice of the gradient arena with that many rows
+    dgb = grad_out if grad_out is not None else torch.empty((4, channels), dtype=torch.float32, device=y.device)
     ws_bytes = lib.zsv_bn_bwd_workspace(channels)
     ws = workspace(ws_bytes, y.device, "bn_bwd")
     has2 = y2 is not None
