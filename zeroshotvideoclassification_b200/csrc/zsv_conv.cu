@@ -189,13 +189,19 @@ struct EpiArgs {
     float* part_sq;
     int ncols, nbias, relu, part_pitch;
     // BatchNorm-backward fusion (dgrad): the tile written is dz = g * [ReLU mask of the BatchNorm that produced this
-    // conv's input], and the CTA accumulates sum(dz) and sum(dz * xhat) per channel (see zsv_bn_bwd_fuse)
-    const __nv_bfloat16* bn_y;   // pre-BatchNorm tensor, same layout as the output
+    // conv's input], and the CTA accumulates sum(dz) and sum(dz * y) per channel (see zsv_bn_bwd_fuse).  The y tile of
+    // the output positions is TMA-loaded into shared memory (mapY, same geometry as the output map) while the tile's
+    // accumulator is read out; mask and sums are then ONE pass over the two staged tiles (bn_column_pass).
+    const __nv_bfloat16* bn_y;   // pre-BatchNorm tensor, same layout as the output (non-null = fusion requested)
     const float4* bn_tab;        // per channel (scale, shift, invstd, -mean*invstd); scale/shift give the ReLU mask
     int bn_relu;
-    float* bn_acc;               // smem [2][ncols] running sums of this CTA
-    float* bn_scratch;           // smem [4 quadrants][2][width] per-tile sums
-    float* st_acc;               // smem [2][ncols] running BatchNorm statistics of this CTA (sum, sum of squares)
+    const CUtensorMap* mapY;     // tensor map of bn_y with the boxes of the output map
+    uint32_t ybuf_u32;           // smem [out panels][128 rows][128 B] (SWIZZLE_128B): y of the current tile
+    uint32_t bar_y, y_phase;     // "y tile landed" barrier and the parity of the current tile
+    uint32_t y_rows;             // rows of one box (every 64-channel panel of a y tile brings y_rows * 128 bytes)
+    int has_next, n0, n1, n2, n3, next_origin;   // box coordinates / first channel of this CTA's NEXT tile (y prefetch)
+    float* st_acc;               // smem [2][ncols] running sums of this CTA: BatchNorm statistics (sum, sum of squares)
+                                 // in fprop, (sum dz, sum dz*y) in the fused backward
     int remote_arrive;           // CTA pair: the TMEM-empty barrier is a shared::cluster address in the leader CTA
     int debug;   // tuning aid (ZSV_DEBUG_EPI bit mask): 1 = skip the TMA store, 2 = skip TMEM read + staging, 4 = skip stats
     uint32_t bar_full, full_phase;   // "accumulator complete" barrier of this tile: waited for inside epilogue_tile, AFTER
@@ -224,23 +230,6 @@ __device__ __forceinline__ void xreduce_stage(float (&v)[16], int lane, int m) {
         const float send = upper ? v[i] : v[i + n / 2];
         const float keep = upper ? v[i + n / 2] : v[i];
         v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-    }
-}
-
-// 32 values per lane -> after 5 exchange stages lane L holds the sum over all 32 lanes of value index L
-__device__ __forceinline__ void xreduce32(float (&v)[32], int lane) {
-#pragma unroll
-    for (int st = 0; st < 5; ++st) {
-        const int m = 16 >> st;       // lane bit exchanged in this stage == live values after it
-        const bool upper = (lane & m) != 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            if (i < m) {
-                const float send = upper ? v[i] : v[i + m];
-                const float keep = upper ? v[i + m] : v[i];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-            }
-        }
     }
 }
 
@@ -312,6 +301,92 @@ __device__ __forceinline__ void tile_column_stats(const EpiArgs& E, uint32_t sta
     }
 }
 
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Fused BatchNorm backward, per output tile: the staged tile holds g (the data gradient, bf16), ybuf the pre-BatchNorm
+// values y of the same positions.  One pass, same thread layout as tile_column_stats (thread = channel octet x row
+// segment, conflict-free 16-byte accesses): dz = g * [y*scale + shift > 0] is written back in place (ReLU) and the
+// column sums of dz and dz*y go to the CTA's running sums.  A thread keeps one octet for the whole tile, so the eight
+// (scale, shift) pairs live in registers.  Rows outside the tensor were staged as zeros and contribute nothing.
+__device__ __forceinline__ void bn_column_pass(const EpiArgs& E, uint32_t staging_u32, int width, int n_origin, int et,
+                                               int lane) {
+    const int octs = width >> 3;
+    const bool seg16 = octs <= 16;
+    const int segs = seg16 ? 16 : 8;
+    const int ntasks = octs * segs;
+    if ((et & ~31) >= ntasks) return;              // whole warp idle
+    const bool active = et < ntasks;
+    const int oct = active ? (seg16 ? et >> 4 : et >> 3) : 0;
+    const int seg = et & (segs - 1);
+    const int colbase = n_origin + oct * 8;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active && colbase + j < E.ncols) t = __ldg(E.bn_tab + colbase + j);
+        sc[j] = t.x, sh[j] = t.y;
+    }
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    if (active) {
+        const uint32_t off0 = static_cast<uint32_t>(oct >> 3) * kPanelBytes + static_cast<uint32_t>(seg) * 128u +
+                              (static_cast<uint32_t>((oct ^ seg) & 7) << 4);
+        const uint32_t step = static_cast<uint32_t>(segs) * 128u;
+        const int nrows = seg16 ? 8 : 16;
+#pragma unroll 4
+        for (int u = 0; u < nrows; ++u) {
+            const uint32_t off = off0 + static_cast<uint32_t>(u) * step;
+            uint4 g = lds128(staging_u32 + off);
+            const uint4 yv = lds128(E.ybuf_u32 + off);
+            uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+            const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float y0 = bf16_lo(yw[j]), y1 = bf16_hi(yw[j]);
+                if (E.bn_relu) {
+                    if (!(fmaf(y0, sc[2 * j], sh[2 * j]) > 0.f)) gw[j] &= 0xFFFF0000u;
+                    if (!(fmaf(y1, sc[2 * j + 1], sh[2 * j + 1]) > 0.f)) gw[j] &= 0x0000FFFFu;
+                }
+                const float g0 = bf16_lo(gw[j]), g1 = bf16_hi(gw[j]);
+                s[2 * j] += g0, s[2 * j + 1] += g1;
+                q[2 * j] = fmaf(g0, y0, q[2 * j]), q[2 * j + 1] = fmaf(g1, y1, q[2 * j + 1]);
+            }
+            if (E.bn_relu) sts128(staging_u32 + off, make_uint4(gw[0], gw[1], gw[2], gw[3]));
+        }
+    }
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = s[j], v[8 + j] = q[j];
+    if (seg16) {
+        xreduce_stage<16>(v, lane, 8);
+        xreduce_stage<8>(v, lane, 4);
+        xreduce_stage<4>(v, lane, 2);
+        xreduce_stage<2>(v, lane, 1);
+        const int col = colbase + (lane & 7);
+        if (active && col < E.ncols) E.st_acc[((lane & 8) ? E.ncols : 0) + col] += v[0];
+    } else {
+        xreduce_stage<16>(v, lane, 4);
+        xreduce_stage<8>(v, lane, 2);
+        xreduce_stage<4>(v, lane, 1);
+        const int col = colbase + ((lane & 2) << 1) + ((lane & 1) << 1);
+        if (active && col < E.ncols) {
+            float* dst = E.st_acc + ((lane & 4) ? E.ncols : 0) + col;
+            dst[0] += v[0];
+            dst[1] += v[1];
+        }
+    }
+}
+
+// (fused BatchNorm backward) start the TMA load of one y tile: panels of 64 channels, same boxes as the output stores
+__device__ __forceinline__ void load_y_tile(const EpiArgs& E, int width, int n_origin, int o0, int o1, int o2, int o3) {
+    mbar_expect_tx(E.bar_y, static_cast<uint32_t>((width + 63) >> 6) * E.y_rows * 128u);
+    for (int p = 0; p * 64 < width; ++p)
+        tma_load_5d(E.ybuf_u32 + p * kPanelBytes, E.mapY, E.bar_y, n_origin + 64 * p, o0, o1, o2, o3);
+}
+
 __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMap* mapOut, uint8_t* staging,
                                               uint32_t staging_u32, float* statbuf, uint32_t trow,
                                               uint32_t bar_tmem_empty, int width, int n_origin, bool valid,
@@ -324,11 +399,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMa
     // (waiting for them was the top stall of this kernel in the ncu source view).  Prefetching into REGISTERS instead
     // pins 32 registers through the whole epilogue and was measured 20% slower on the epilogue-bound temporal convs.
     constexpr int kChunkStride = 4 * kEpiWarps;
-    if ((E.bn_y != nullptr || E.addend != nullptr) && valid && !(E.debug & 2)) {
+    if (E.addend != nullptr && valid && !(E.debug & 2)) {
         for (int c = 0; c < width; c += 64) {
             if (n_origin + c >= E.ncols) break;
-            if (E.bn_y != nullptr) prefetch_l1(E.bn_y + off + n_origin + c);
-            if (E.addend != nullptr) prefetch_l1(E.addend + off + n_origin + c);
+            prefetch_l1(E.addend + off + n_origin + c);
         }
     }
     mbar_wait(E.bar_full, E.full_phase);
@@ -370,41 +444,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMa
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-        float xh[16];   // xhat of the BatchNorm input at this row (BN-backward fusion only)
-        if (E.bn_y != nullptr) {
-#pragma unroll
-            for (int hlf = 0; hlf < 2; ++hlf) {
-                const bool inr = valid && (col + 8 * hlf < E.ncols);
-                uint4 a = make_uint4(0u, 0u, 0u, 0u);
-                if (inr) a = *reinterpret_cast<const uint4*>(E.bn_y + off + col + 8 * hlf);
-                const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float yv = (j & 1) ? bf16_hi(aw[j >> 1]) : bf16_lo(aw[j >> 1]);
-                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (col + 8 * hlf < E.ncols) t = __ldg(E.bn_tab + col + 8 * hlf + j);
-                    if (E.bn_relu && !(fmaf(yv, t.x, t.y) > 0.f)) f[8 * hlf + j] = 0.f;
-                    xh[8 * hlf + j] = inr ? fmaf(yv, t.z, t.w) : 0.f;
-                }
-            }
-        }
         uint32_t pk[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) pk[j] = valid ? pack_bf16x2(f[2 * j], f[2 * j + 1]) : 0u;
-        if (E.bn_y != nullptr) {
-            // sums over the 32 rows of this warp for 16 columns x {dz, dz*xhat}, of the bf16-rounded dz that is stored
-            float red[32];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                red[2 * j] = bf16_lo(pk[j]);
-                red[2 * j + 1] = bf16_hi(pk[j]);
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) red[16 + j] = red[j] * xh[j];
-            xreduce32(red, lane);
-            // lane = quantity * 16 + column
-            E.bn_scratch[((q << 1) + (lane >> 4)) * width + c + (lane & 15)] = red[0];
-        }
         // SWIZZLE_128B staging: 16-byte chunk index XOR (row & 7) inside the 64-channel panel
         uint8_t* prow = staging + static_cast<uint32_t>(c >> 6) * kPanelBytes + srow;
         const uint32_t ch = static_cast<uint32_t>(c & 63) >> 3;
@@ -431,6 +473,13 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMa
     }
     fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA store
     named_bar_sync(2, kEpiWarps * 32);
+    if (E.bn_y != nullptr) {
+        // fused BatchNorm backward: ReLU mask + column sums over the staged gradient and the y tile, then the store
+        mbar_wait(E.bar_y, E.y_phase);
+        bn_column_pass(E, staging_u32, width, n_origin, et, lane);
+        fence_proxy_async_smem();        // masked tile (generic-proxy writes) -> visible to the TMA store
+        named_bar_sync(3, kEpiWarps * 32);   // every thread is done with the y tile and the staged tile is final
+    }
     if (et == 0 && !(E.debug & 1)) {
         for (int p = 0; p * 64 < width; ++p) {
             const int ccol = n_origin + 64 * p;
@@ -438,18 +487,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMa
         }
         tma_store_commit();
     }
-    for (int e = et; E.bn_y != nullptr && e < 2 * width; e += kEpiWarps * 32) {
-        // column owner: quadrants in fixed order, then into the CTA's running sum (one owner per column: deterministic)
-        const int qn = e >= width ? 1 : 0;
-        const int cc = e - qn * width;
-        const int col = n_origin + cc;
-        if (col < E.ncols) {
-            float sum = 0.f;
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) sum += E.bn_scratch[((qq << 1) + qn) * width + cc];
-            E.bn_acc[qn * E.ncols + col] += sum;
-        }
-    }
+    // y of this CTA's next tile: lands while that tile's accumulator is read out
+    if (et == 0 && E.bn_y != nullptr && E.has_next) load_y_tile(E, width, E.next_origin, E.n0, E.n1, E.n2, E.n3);
     if (E.part_sum != nullptr && !(E.debug & 4)) tile_column_stats(E, staging_u32, width, n_origin, m_tile, et, lane);
 }
 
@@ -474,7 +513,7 @@ template <bool k2>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
                     const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
-                    const __grid_constant__ IgemmArgs P) {
+                    const __grid_constant__ CUtensorMap mapY, const __grid_constant__ IgemmArgs P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -490,13 +529,15 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
     const int out_panels = (P.bn_tile + 63) >> 6;                    // 64-channel output panels of one tile
     const uint32_t stagingOff = ringBytes;                           // [nstg][out_panels][128 rows][128 B], SWIZZLE_128B
     const uint32_t stagingBytes = out_panels * kPanelBytes;
-    const uint32_t statOff = stagingOff + P.nstg * stagingBytes;     // 4 KB of fp32 scratch for the BN column sums
+    const uint32_t ybufOff = stagingOff + P.nstg * stagingBytes;     // y tile of the fused BatchNorm backward (one buffer)
+    const uint32_t statOff = ybufOff + (P.bn_y != nullptr ? stagingBytes : 0u);   // fp32 running column sums
     const uint32_t barOff = statOff + static_cast<uint32_t>(P.scratch_bytes);
     const uint32_t barFull = base + barOff;
     const uint32_t barEmpty = barFull + 8u * stages;
     const uint32_t barTmemFull = barEmpty + 8u * stages;   // [2]
     const uint32_t barTmemEmpty = barTmemFull + 16u;       // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + barOff + 16u * stages + 32u);
+    const uint32_t barY = barFull + 16u * stages + 40u;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -507,6 +548,7 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
             mbar_init(barTmemFull + 8u * b, 1);
             mbar_init(barTmemEmpty + 8u * b, k2 ? 2 * kEpiWarps : kEpiWarps);
         }
+        mbar_init(barY, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -650,21 +692,45 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
         const uint32_t tmemEmptyBar = k2 ? mapa_shared(barTmemEmpty, 0) : barTmemEmpty;
         float* statbuf = reinterpret_cast<float*>(smem + statOff);
         E.bn_y = P.bn_y, E.bn_tab = P.bn_tab, E.bn_relu = P.bn_relu;
-        E.bn_acc = statbuf;
         E.st_acc = statbuf;
-        E.bn_scratch = statbuf + 2 * P.ncols;
+        E.mapY = &mapY, E.ybuf_u32 = base + ybufOff, E.bar_y = barY;
+        E.y_rows = static_cast<uint32_t>(rows);
         if (P.bn_y != nullptr || P.part_sum != nullptr)   // running sums start at zero; the first tile's barriers order this before any use
             for (int i = et; i < 2 * P.ncols; i += kEpiWarps * 32) statbuf[i] = 0.f;
-        int local = 0;
-        for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++local) {
+        // box origin / first channel of a tile of this CTA
+        auto tile_origin = [&](int tile, int& w0, int& h0, int& t0, int& n0, int& m_tile) {
             int m, in_;
             const int n_tile = fdivmod(tile, P.fd_ntiles, m);
             if (k2) m = 2 * m + static_cast<int>(rank);
-            const int m_tile = m;
+            m_tile = m;
             const int iw = fdivmod(m, P.fd_tw, m);
             const int ih = fdivmod(m, P.fd_th, m);
             const int itt = fdivmod(m, P.fd_tt, in_);
-            const int w0 = iw * P.bw, h0 = ih * P.bh, t0 = itt * P.bt, n0 = in_ * P.bn;
+            w0 = iw * P.bw, h0 = ih * P.bh, t0 = itt * P.bt, n0 = in_ * P.bn;
+            return n_tile;
+        };
+        if (P.bn_y != nullptr) {
+            // rows of the y buffer that no box ever writes must not hold NaN bit patterns (0 * NaN in the column pass)
+            uint32_t* yz = reinterpret_cast<uint32_t*>(smem + ybufOff);
+            for (uint32_t i = et; i < stagingBytes / 4u; i += kEpiWarps * 32) yz[i] = 0u;
+            fence_proxy_async_smem();
+            named_bar_sync(1, kEpiWarps * 32);
+            if (et == 0 && first_tile < num_tiles) {
+                int w0, h0, t0, n0, mt_;
+                const int nt0 = tile_origin(first_tile, w0, h0, t0, n0, mt_);
+                load_y_tile(E, P.bn_tile, nt0 * P.bn_tile, w0, h0, t0, n0);
+            }
+        }
+        int local = 0;
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++local) {
+            int w0, h0, t0, n0, m_tile;
+            const int n_tile = tile_origin(tile, w0, h0, t0, n0, m_tile);
+            E.y_phase = local & 1u;
+            E.has_next = tile + tile_step < num_tiles;
+            if (P.bn_y != nullptr && E.has_next) {
+                int mt_;
+                E.next_origin = tile_origin(tile + tile_step, E.n0, E.n1, E.n2, E.n3, mt_) * P.bn_tile;
+            }
             const bool valid =
                 row < rows && (w0 + w) < P.OW && (h0 + h) < P.OH && (t0 + t) < P.OT && (n0 + n) < P.ON;
             const long long off = (long long)(n0 + n) * P.o_sN + (long long)(t0 + t) * P.o_sT +
@@ -762,7 +828,8 @@ template <bool k2>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAtail,
                   const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBtail,
-                  const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ HaloArgs P) {
+                  const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapY,
+                  const __grid_constant__ HaloArgs P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -778,7 +845,8 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int out_panels = (P.bn_tile + 63) >> 6;
     const uint32_t stagingOff = ringOff + ringBytes;
     const uint32_t stagingBytes = out_panels * kPanelBytes;
-    const uint32_t statOff = stagingOff + P.nstg * stagingBytes;
+    const uint32_t ybufOff = stagingOff + P.nstg * stagingBytes;     // y tile of the fused BatchNorm backward (one buffer)
+    const uint32_t statOff = ybufOff + (P.bn_y != nullptr ? stagingBytes : 0u);
     const uint32_t barOff = statOff + static_cast<uint32_t>(P.scratch_bytes);
     const uint32_t barFull = base + barOff;
     const uint32_t barEmpty = barFull + 8u * stages;
@@ -786,6 +854,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const uint32_t barTmemEmpty = barTmemFull + 16u;
     const uint32_t barB = barTmemEmpty + 16u;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + barOff + 16u * stages + 40u);
+    const uint32_t barY = barFull + 16u * stages + 48u;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -797,6 +866,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             mbar_init(barTmemEmpty + 8u * i, k2 ? 2 * kEpiWarps : kEpiWarps);
         }
         mbar_init(barB, 1);
+        mbar_init(barY, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -1043,21 +1113,43 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const uint32_t tmemEmptyBar = k2 ? mapa_shared(barTmemEmpty, 0) : barTmemEmpty;
         float* statbuf = reinterpret_cast<float*>(smem + statOff);
         E.bn_y = P.bn_y, E.bn_tab = P.bn_tab, E.bn_relu = P.bn_relu;
-        E.bn_acc = statbuf;
         E.st_acc = statbuf;
-        E.bn_scratch = statbuf + 2 * P.ncols;
+        E.mapY = &mapY, E.ybuf_u32 = base + ybufOff, E.bar_y = barY;
+        E.y_rows = static_cast<uint32_t>(rows);
         if (P.bn_y != nullptr || P.part_sum != nullptr)   // running sums start at zero; the first tile's barriers order this before any use
             for (int i = et; i < 2 * P.ncols; i += kEpiWarps * 32) statbuf[i] = 0.f;
         // columns this tile owns: a non-last N tile only owns n_step of its bn_tile computed columns
         const int width = (n_tile + 1 < P.n_tiles) ? P.n_step : P.bn_tile;
-        int local = 0;
-        for (int it = m_first; it < m_count; it += m_stride, ++local) {
+        // box origin of M tile `it` of this CTA
+        auto tile_origin = [&](int it, int& o0, int& o1, int& o2, int& o3) {
             const int mt = k2 ? 2 * it + static_cast<int>(rank) : it;
             int m, m3;
-            const int o0 = fdivmod(mt, P.fd_tl0, m) * P.b[0];
-            const int o1 = fdivmod(m, P.fd_tl1, m) * P.b[1];
-            const int o2 = fdivmod(m, P.fd_tl2, m3) * P.b[2];
-            const int o3 = m3 * P.b[3];
+            o0 = fdivmod(mt, P.fd_tl0, m) * P.b[0];
+            o1 = fdivmod(m, P.fd_tl1, m) * P.b[1];
+            o2 = fdivmod(m, P.fd_tl2, m3) * P.b[2];
+            o3 = m3 * P.b[3];
+            return mt;
+        };
+        if (P.bn_y != nullptr) {
+            // rows of the y buffer that no box ever writes must not hold NaN bit patterns (0 * NaN in the column pass)
+            uint32_t* yz = reinterpret_cast<uint32_t*>(smem + ybufOff);
+            for (uint32_t i = et; i < stagingBytes / 4u; i += kEpiWarps * 32) yz[i] = 0u;
+            fence_proxy_async_smem();
+            named_bar_sync(1, kEpiWarps * 32);
+            if (et == 0 && m_first < m_count) {
+                int o0, o1, o2, o3;
+                tile_origin(m_first, o0, o1, o2, o3);
+                load_y_tile(E, width, n_origin, o0, o1, o2, o3);
+            }
+        }
+        E.next_origin = n_origin;
+        int local = 0;
+        for (int it = m_first; it < m_count; it += m_stride, ++local) {
+            int o0, o1, o2, o3;
+            const int mt = tile_origin(it, o0, o1, o2, o3);
+            E.y_phase = local & 1u;
+            E.has_next = it + m_stride < m_count;
+            if (P.bn_y != nullptr && E.has_next) tile_origin(it + m_stride, E.n0, E.n1, E.n2, E.n3);
             const bool valid = row < rows && (o0 + i0) < P.O[0] && (o1 + i1) < P.O[1] && (o2 + i2) < P.O[2] &&
                                (o3 + i3) < P.O[3];
             const long long off = (long long)(o0 + i0) * P.os[0] + (long long)(o1 + i1) * P.os[1] +
@@ -1472,24 +1564,26 @@ wgrad_finalize_kernel(const float* __restrict__ ws, float* __restrict__ dw, int 
     const int lane_co = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const bool co_ok = co0 + lane_co < co_pitch;
-    for (int r0 = warp; r0 < run; r0 += 32) {          // rows r0, r0+8, r0+16, r0+24 of this warp
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        const float* p[4];
-        bool ok[4];
+    constexpr int kU = 8;                               // (tap, ci) rows of a warp in flight
+    for (int r0 = warp; r0 < run; r0 += 8 * kU) {       // rows r0, r0+8, ... of this warp
+        float acc[kU];
+        const float* p[kU];
+        bool ok[kU];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kU; ++u) {
             const int r = r0 + 8 * u;
             const int tap = r / ci_tile, ci = r - tap * ci_tile;
+            acc[u] = 0.f;
             ok[u] = r < run && co_ok && ci0 + ci < ci_pitch;
             p[u] = ws + ((long long)tap * ci_pitch + ci0 + ci) * co_pitch + co0 + lane_co;
         }
         for (int sp = 0; sp < splits; ++sp) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < kU; ++u)
                 if (ok[u]) acc[u] += p[u][sp * split_stride];
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kU; ++u) {
             const int r = r0 + 8 * u;
             if (r < run) {
                 const int tap = r / ci_tile, ci = r - tap * ci_tile;
@@ -1995,13 +2089,9 @@ struct BnFuseLaunch {
     int rows_used;
 };
 
-// shared-memory scratch of the fused BatchNorm-backward sums: [2][ncols] running + [4][2][bn_tile] per tile
+// shared-memory scratch of the per-CTA running column sums: [2][ncols] fp32 (BatchNorm statistics in fprop,
+// (sum dz, sum dz*y) in the fused BatchNorm backward)
 int bn_scratch_bytes(int ncols, int bn_tile) { return (((2 * ncols + 8 * bn_tile) * 4) + 1023) & ~1023; }
-
-int igemm_smem_bytes(int bn_tile, int stages, int nstg, int scratch = 0) {
-    return 1024 + stages * (kPanelBytes + bn_tile * 128) + nstg * ((bn_tile + 63) / 64) * kPanelBytes + scratch +
-           16 * stages + 48 + 64;
-}
 
 // CTA pairs (cta_group::2) for the generic kernel
 bool igemm_use_pair(int bn_tile, long long m_tiles) {
@@ -2018,17 +2108,21 @@ int igemm_grid(int bn_tile, long long m_tiles, int n_tiles) {
 }
 
 int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtensorMap& mapOut, IgemmArgs& a,
-                 long long m_tiles, int n_tiles, cudaStream_t stream, BnFuseLaunch* fuse = nullptr) {
+                 long long m_tiles, int n_tiles, cudaStream_t stream, BnFuseLaunch* fuse = nullptr,
+                 const CUtensorMap* mapY = nullptr) {
     // one persistent CTA per SM owns (almost) all shared memory: as many ring stages as fit, at most 8
     // two output staging buffers when at least 3 ring stages still fit beside them
-    const int scratch = fuse ? bn_scratch_bytes(a.ncols, a.bn_tile) : (a.part_sum ? bn_scratch_bytes(a.ncols, 0) : 0);
+    if (fuse && !mapY) return fail(ZSV_ERR_BAD_ARG, "igemm: BN-backward fusion without a tensor map for y");
+    const int scratch = (fuse || a.part_sum) ? bn_scratch_bytes(a.ncols, 0) : 0;
+    // fused BatchNorm backward: one more tile-sized buffer, for y
+    const int ybuf = fuse ? ((a.bn_tile + 63) / 64) * (int)kPanelBytes : 0;
     // shared memory per ring stage: the A tile + the B rows THIS CTA holds (half of them in a CTA pair); the staging
     // buffers always hold the full N tile
     const bool pair = igemm_use_pair(a.bn_tile, m_tiles);
     const int b_rows = pair ? a.bn_tile / 2 : a.bn_tile;
     auto smem_for = [&](int stages_, int nstg_) {
-        return 1024 + stages_ * ((int)kPanelBytes + b_rows * 128) + nstg_ * ((a.bn_tile + 63) / 64) * (int)kPanelBytes + scratch +
-               16 * stages_ + 48 + 64;
+        return 1024 + stages_ * ((int)kPanelBytes + b_rows * 128) + nstg_ * ((a.bn_tile + 63) / 64) * (int)kPanelBytes + ybuf +
+               scratch + 16 * stages_ + 48 + 64;
     };
     int nstg = 2;
     if (const char* e = getenv("ZSV_DEBUG_NSTG")) nstg = atoi(e) == 1 ? 1 : 2;
@@ -2085,10 +2179,10 @@ int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtenso
         attr.id = cudaLaunchAttributeClusterDimension;
         attr.val.clusterDim.x = 2, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
         cfg.attrs = &attr, cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_kmajor_kernel<true>, pack, mapB, mapOut, a);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_kmajor_kernel<true>, pack, mapB, mapOut, mapY ? *mapY : mapOut, a);
         if (e != cudaSuccess) return fail(ZSV_ERR_CUDA, "launch of igemm_kmajor_kernel<pair> failed: %s", cudaGetErrorString(e));
     } else {
-        igemm_kmajor_kernel<false><<<grid, kIgemmThreads, smem, stream>>>(pack, mapB, mapOut, a);
+        igemm_kmajor_kernel<false><<<grid, kIgemmThreads, smem, stream>>>(pack, mapB, mapOut, mapY ? *mapY : mapOut, a);
     }
     ZSV_LAUNCH_CHECK("igemm_kmajor_kernel");
     return ZSV_OK;
@@ -2197,8 +2291,9 @@ HaloPlan plan_halo_impl(int W, int H, int T, int N, int kdim, int cols, int kt, 
         const int staging1 = ((bn + 63) / 64) * (int)kPanelBytes;
         int nstg = 2, stages = 0, fixed = 0;
         for (; nstg >= 1; --nstg) {   // prefer two staging buffers if >= 3 activation stages still fit
-            p.scratch = scratch_mode == 2 ? bn_scratch_bytes(cpad(cols), bn) : (scratch_mode == 1 ? bn_scratch_bytes(cpad(cols), 0) : 0);
-            fixed = 1024 + (int)p.b_total_bytes + nstg * staging1 + p.scratch + 256;
+            p.scratch = scratch_mode != 0 ? bn_scratch_bytes(cpad(cols), 0) : 0;
+            // (fused BatchNorm backward: one more tile-sized buffer, for y)
+            fixed = 1024 + (int)p.b_total_bytes + nstg * staging1 + (scratch_mode == 2 ? staging1 : 0) + p.scratch + 256;
             const int avail = 226 * 1024 - fixed;
             stages = avail > 0 ? avail / (int)p.a_stage_bytes : 0;
             if (stages >= (nstg == 2 ? 3 : 2)) break;
@@ -2331,6 +2426,11 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
     }
     rc = act_map(&mO, out, outPitch, outPitch, 64, p.b[3], CU_TENSOR_MAP_SWIZZLE_128B, p.b[0]);
     if (rc) return rc;
+    CUtensorMap mY = mO;
+    if (fuse) {   // y of the output positions (fused BatchNorm backward): the geometry of the output map
+        rc = act_map(&mY, fuse->y, outPitch, outPitch, 64, p.b[3], CU_TENSOR_MAP_SWIZZLE_128B, p.b[0]);
+        if (rc) return rc;
+    }
 
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
@@ -2343,9 +2443,7 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
         return fail(ZSV_ERR_CUDA, "cudaFuncSetAttribute(halo igemm) failed: %s", cudaGetErrorString(attr_err));
     const int grid = halo_grid(p);
     a.scratch_bytes = p.scratch;
-    if (fuse) {
-        if (p.scratch < bn_scratch_bytes(a.ncols, p.bn_tile)) return fail(ZSV_ERR_UNSUPPORTED, "halo plan without BN-fusion scratch");
-    } else if (part_sum != nullptr && p.scratch < bn_scratch_bytes(a.ncols, 0)) {
+    if ((fuse || part_sum != nullptr) && p.scratch < bn_scratch_bytes(a.ncols, 0)) {
         return fail(ZSV_ERR_UNSUPPORTED, "halo plan without statistics scratch");
     }
     if (fuse) {
@@ -2364,10 +2462,10 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
         attr.id = cudaLaunchAttributeClusterDimension;
         attr.val.clusterDim.x = 2, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
         cfg.attrs = &attr, cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_halo_kernel<true>, mA, mAt, mB, mBt, mO, a);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_halo_kernel<true>, mA, mAt, mB, mBt, mO, mY, a);
         if (e != cudaSuccess) return fail(ZSV_ERR_CUDA, "launch of igemm_halo_kernel<pair> failed: %s", cudaGetErrorString(e));
     } else {
-        igemm_halo_kernel<false><<<grid, kIgemmThreads, p.smem, st>>>(mA, mAt, mB, mBt, mO, a);
+        igemm_halo_kernel<false><<<grid, kIgemmThreads, p.smem, st>>>(mA, mAt, mB, mBt, mO, mY, a);
     }
     ZSV_LAUNCH_CHECK("igemm_halo_kernel");
     return ZSV_OK;
@@ -2706,7 +2804,17 @@ extern "C" int zsv_conv3d_dgrad(const zsv_conv_desc* d, const void* dy, const vo
                     rc = make_map(&mapOut, (const char*)dx + class_off * 2, 5, odims, ostr, obox);
                     if (rc) return rc;
                 }
-                rc = launch_igemm(maps, mapB, mapOut, a, m_tiles, n_tiles, st, fuse);
+                CUtensorMap mapY;
+                if (fuse) {   // y of the positions of this parity class: the geometry of the output map
+                    const uint64_t cB = (uint64_t)s.cinp * 2;
+                    uint64_t odims[5] = {(uint64_t)s.cinp, (uint64_t)QW, (uint64_t)QH, (uint64_t)QT, (uint64_t)d->N};
+                    uint64_t ostr[4] = {cB * d->sw, cB * d->W * d->sh, cB * d->W * d->H * d->st,
+                                        cB * d->W * d->H * d->T};
+                    uint32_t obox[5] = {64, (uint32_t)b.bw, (uint32_t)b.bh, (uint32_t)b.bt, (uint32_t)b.bn};
+                    rc = make_map(&mapY, fuse->y, 5, odims, ostr, obox);
+                    if (rc) return rc;
+                }
+                rc = launch_igemm(maps, mapB, mapOut, a, m_tiles, n_tiles, st, fuse, fuse ? &mapY : nullptr);
                 if (rc) return rc;
             }
     if (fuse) bnf->rows_written = fuse->rows_used;
@@ -2889,8 +2997,12 @@ namespace {
 int launch_wgrad_finalize(const zsv_conv_desc* d, const Shape& s, const float* ws, float* dw, int splits, int ci_pitch,
                           int co_pitch, cudaStream_t st) {
     const long long wtotal = (long long)s.ftaps * ci_pitch * co_pitch;
-    if (s.wfold || getenv("ZSV_DEBUG_FINALIZE_SMALL")) {
-        // W-folded first layer (tap = (dt,dh), ci = dw*8 + c): a few thousand weights, element-wise
+    // Small tensors reduced over many splits (layers 1-2, stem): one thread per element keeps the whole GPU busy where the
+    // tiled kernel would have a few dozen blocks each walking all splits (measured: 10 us vs 95 us on 144->64 with 147
+    // splits); from ~1 M weights on (layers 3-4) the element-wise kernel's scattered 4-byte stores dominate and the
+    // tiled one wins (44 -> 32 us on 512->1152, 28 -> 14 us on 1152->512).  Also the W-folded first layer
+    // (tap = (dt,dh), ci = dw*8 + c).
+    if (s.wfold || wtotal < (1LL << 20) || getenv("ZSV_DEBUG_FINALIZE_SMALL")) {
         const int blocks = (int)std::min<long long>(ceil_div_ll(wtotal, 256), 148 * 8);
         wgrad_finalize_small_kernel<<<blocks, 256, 0, st>>>(ws, dw, splits, s.ftaps, ci_pitch, co_pitch, d->Cin, d->Cout,
                                                             s.wfold ? d->kw : 0, s.ntaps);
@@ -2900,7 +3012,7 @@ int launch_wgrad_finalize(const zsv_conv_desc* d, const Shape& s, const float* w
     // input channels per block: runs of ~256-288 floats per output channel; fewer when that leaves SMs without a block
     // (small tensors summed over many splits)
     int ci_tile = std::max(8, std::min(64, (288 / s.ftaps) & ~7));
-    while (ci_tile > 8 && (long long)ceil_div(d->Cout, 32) * ceil_div(d->Cin, ci_tile) < sm_count()) ci_tile >>= 1;
+    while (ci_tile > 8 && (long long)ceil_div(d->Cout, 32) * ceil_div(d->Cin, ci_tile) < 2LL * sm_count()) ci_tile >>= 1;
     const size_t fsm = (size_t)32 * ((ci_tile * s.ftaps) | 1) * sizeof(float);
     if (fsm > 48 * 1024) return fail(ZSV_ERR_UNSUPPORTED, "wgrad finalize: %d taps do not fit the staging tile", s.ftaps);
     dim3 fgrid(ceil_div(d->Cout, 32), ceil_div(d->Cin, ci_tile));

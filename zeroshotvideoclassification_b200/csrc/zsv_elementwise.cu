@@ -935,7 +935,8 @@ extern "C" int zsv_bn_bwd_finish(const void* dz, const void* y, const float* mea
     if (workspace_bytes < 4 * (size_t)Cp * sizeof(float)) return fail(ZSV_ERR_WORKSPACE, "bn_bwd_finish: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     float* sums = (float*)workspace;
-    bn_bwd_final_kernel<<<ceil_div(Cp, 8), 1024, 0, st>>>(partial, partial_rows, 2, C, Cp, 0, mean, invstd, nullptr, nullptr,
+    // the convolution epilogue leaves (sum dz, sum dz*y) against the RAW pre-activation; converted to sum dz*xhat in fp64
+    bn_bwd_final_kernel<<<ceil_div(Cp, 8), 1024, 0, st>>>(partial, partial_rows, 2, C, Cp, 1, mean, invstd, nullptr, nullptr,
                                                           sums, dgamma, dbeta, nullptr, nullptr);
     ZSV_LAUNCH_CHECK("bn_bwd_final_kernel");
     const int V = Cp >> 3;

@@ -27,6 +27,7 @@ constexpr int kKC = 512;       // forward: k chunk of x staged in shared memory
 constexpr int kFwdRows = 32;   // forward: output features per block (8 warps x 4)
 constexpr int kDgK = 1024;     // dgrad / wgrad: k columns per block (256 threads x 4)
 constexpr int kDgJ = 64;       // dgrad: output features staged per shared-memory pass
+constexpr long long kSmallMatrix = 1LL << 20;   // weights up to here: the latency-bound kernels for small matrices
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -286,6 +287,71 @@ linear_wgrad_kernel(const float* __restrict__ g, const float* __restrict__ x, fl
     }
 }
 
+// ---- small weight matrices (the MLP head: 512 x 512, 300 x 512): latency-bound, parallelism over (row, output) -------
+// out[b][j] = act(sum_k x[b][k] * w[j][k] + bias[j]); one warp per output feature j, 8 batch rows per block row
+__global__ void linear_fwd_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                        const float* __restrict__ bias, float* __restrict__ out, int B, int K, int J,
+                                        int relu) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= J) return;
+    const float* wr = w + (long long)warp * K;
+    for (int b0 = blockIdx.y * 8; b0 < B; b0 += 8 * gridDim.y) {
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int k = lane; k < K; k += 32) {
+            const float wv = wr[k];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (b0 + i < B) acc[i] = fmaf(wv, x[(long long)(b0 + i) * K + k], acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float s = warp_sum(acc[i]);
+            if (lane == 0 && b0 + i < B) {
+                float v = s + (bias ? bias[warp] : 0.f);
+                if (relu) v = fmaxf(v, 0.f);
+                out[(long long)(b0 + i) * J + warp] = v;
+            }
+        }
+    }
+}
+
+// dx[b][k] = (sum_j g[b][j] * w[j][k]) * (act ? [act[b][k] > 0] : 1): block = 32 k lanes x 8 slices of the j reduction,
+// 8 batch rows; the slices are combined in fixed order through shared memory.  grid = (ceil(K/32), ceil(B/8)).
+__global__ void __launch_bounds__(256)
+linear_dgrad_small_kernel(const float* __restrict__ g, const float* __restrict__ w, const float* __restrict__ act,
+                          float* __restrict__ dx, int B, int K, int J) {
+    __shared__ float red[8][8][33];
+    const int kl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int k = blockIdx.x * 32 + kl;
+    const int b0 = blockIdx.y * 8;
+    const int jper = (J + 7) >> 3;
+    const int j0 = sl * jper, j1 = min(J, j0 + jper);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 4
+    for (int j = j0; j < j1; ++j) {
+        const float wv = k < K ? w[(long long)j * K + k] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (b0 + i < B) acc[i] = fmaf(g[(long long)(b0 + i) * J + j], wv, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[sl][i][kl] = acc[i];
+    __syncthreads();
+    const int i = sl;   // 8 warps -> 8 batch rows
+    if (b0 + i < B && k < K) {
+        float s2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) s2 += red[t][i][kl];
+        const long long o = (long long)(b0 + i) * K + k;
+        dx[o] = (act && !(act[o] > 0.f)) ? 0.f : s2;
+    }
+}
+
 __global__ void relu_mask_kernel(const float* __restrict__ dy, const float* __restrict__ act, float* __restrict__ out,
                                  long long n) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -313,6 +379,11 @@ size_t linear_workspace_bytes(int B, int K, int J) {
 
 int linear_forward(const float* x, const float* w, const float* bias, float* out, int B, int K, int J, int relu,
                    float* ws, size_t ws_bytes, cudaStream_t st) {
+    if ((long long)K * J <= kSmallMatrix) {
+        linear_fwd_small_kernel<<<dim3(ceil_div(J * 32, 256), ceil_div(B, 8)), 256, 0, st>>>(x, w, bias, out, B, K, J, relu);
+        ZSV_LAUNCH_CHECK("linear_fwd_small_kernel");
+        return ZSV_OK;
+    }
     const int splits = ws ? fwd_splits(K, J) : 1;       // no workspace: the k reduction stays inside one block
     if (splits > 1 && ws_bytes < sizeof(float) * (size_t)splits * B * J)
         return fail(ZSV_ERR_WORKSPACE, "linear_fwd: workspace too small (%zu bytes)", ws_bytes);
@@ -346,6 +417,11 @@ int linear_forward(const float* x, const float* w, const float* bias, float* out
 // activation of the layer INPUT whose ReLU mask is applied to dx (the MLP head's hidden layer)
 int linear_dgrad(const float* g, const float* w, const float* act_in, float* dx, int B, int K, int J, float* ws,
                  size_t ws_bytes, cudaStream_t st) {
+    if ((long long)K * J <= kSmallMatrix) {
+        linear_dgrad_small_kernel<<<dim3(ceil_div(K, 32), ceil_div(B, 8)), 256, 0, st>>>(g, w, act_in, dx, B, K, J);
+        ZSV_LAUNCH_CHECK("linear_dgrad_small_kernel");
+        return ZSV_OK;
+    }
     const int splits = dgrad_splits(K, J);
     const int jps = ceil_div(ceil_div(J, splits), kDgJ) * kDgJ;
     const int nsplit = ceil_div(J, jps);

@@ -123,8 +123,10 @@ def _conv_for(spec: ConvSpec, N, T, H, W, layout=_lib.X_NDHWC) -> ops.Conv3d:
 
 import os
 
-# fuse the reduction pass of BatchNorm backward into the epilogue of the dgrad that produces its input gradient
-FUSE_BN_BWD = os.environ.get("ZSV_FUSE_BN_BWD", "1") != "0"
+# fuse the reduction pass of BatchNorm backward into the epilogue of the dgrad that produces its input gradient:
+# 0 = never, 1 = only where the tile's main loop is long (the round-1 rule: spatial 1x3x3 dgrads), 2 = every stride-1 dgrad
+# (default since the fused epilogue became one shared-memory pass over the staged tile and a TMA-loaded y tile)
+FUSE_BN_BWD = int(os.environ.get("ZSV_FUSE_BN_BWD", "2"))
 
 # run the weight-gradient GEMMs on a second stream: they only depend on dy, nothing in the backward chain depends on
 # them, and being tensor / L2 bound they overlap with the HBM-bound BatchNorm-backward kernels of the next layer
@@ -434,11 +436,13 @@ class BackboneRunner:
                     rec.x, dy, out=self._take(rec.spec.cout, rec.spec.cin, *rec.spec.kernel))
         if not need_dx:
             return None
-        # Fusing pays when the tile's main loop is long compared with its epilogue (few output channels, deep reduction:
-        # the spatial 1x3x3 convolutions); measured on the wide, shallow temporal dgrads it triples their time.
+        # Round 1's fused epilogue (a shuffle reduction per 16-column chunk) only paid where the tile's main loop is long
+        # compared with its epilogue (spatial 1x3x3: few output channels, deep reduction) and tripled the time of the
+        # wide, shallow temporal dgrads; mode 1 keeps that rule for A/B runs.
         op = rec.op
-        deep = op.cout * op.kernel[0] * op.kernel[1] * op.kernel[2] >= 8 * op.cin and op.stride == (1, 1, 1)
-        if producer is not None and FUSE_BN_BWD and deep:
+        deep = op.cout * op.kernel[0] * op.kernel[1] * op.kernel[2] >= 8 * op.cin
+        fuse = FUSE_BN_BWD and op.stride == (1, 1, 1) and (deep or FUSE_BN_BWD >= 2)
+        if producer is not None and fuse:
             return rec.op.dgrad_bn_fused(dy, rec.wd, addend, producer.y, producer.table, producer.relu)
         return rec.op.dgrad(dy, rec.wd, addend)
 
