@@ -197,7 +197,9 @@ def test_batched_weight_pack_matches_per_conv_pack():
     (230, 128, (3, 1, 1), (2, 1, 1), (1, 0, 0), 8, 12, 12, True, False),   # temporal stride 2: parity-class launches
     (144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0), 4, 12, 12, False, False),   # BatchNorm without ReLU
     (300, 520, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, 10, 10, True, False),   # wide layers: several N tiles
-], ids=["temporal", "spatial+addend", "temporal-s2", "norelu", "wide"])
+    (256, 96, (1, 3, 3), (1, 1, 1), (0, 1, 1), 2, 14, 14, True, True),     # 256 gradient channels: N tiles capped at 192
+    (512, 80, (3, 1, 1), (1, 1, 1), (1, 0, 0), 2, 7, 7, True, False),      # 512 gradient channels, tiny planes (layer 4)
+], ids=["temporal", "spatial+addend", "temporal-s2", "norelu", "wide", "n256", "n512"])
 def test_dgrad_with_fused_bn_backward_matches_two_pass(geom):
     """dgrad with zsv_bn_bwd_fuse + zsv_bn_bwd_finish == plain dgrad followed by the two-pass zsv_bn_bwd
     (same masks, same rounding points; only the order of the fp32 partial sums differs)."""

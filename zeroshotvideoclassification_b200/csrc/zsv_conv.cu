@@ -321,16 +321,17 @@ __device__ __forceinline__ void bn_column_pass(const EpiArgs& E, uint32_t stagin
     const int oct = active ? (seg16 ? et >> 4 : et >> 3) : 0;
     const int seg = et & (segs - 1);
     const int colbase = n_origin + oct * 8;
-    float sc[8], sh[8];
+    // packed fp32 pairs throughout (FFMA2 / FADD2), the ReLU mask from the packed bf16 BatchNorm output like
+    // bn_bwd_reduce_kernel: ~4 instructions per channel pair and row
+    f32x2 sc[4], sh[4], s2[4], q2[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active && colbase + j < E.ncols) t = __ldg(E.bn_tab + colbase + j);
-        sc[j] = t.x, sh[j] = t.y;
+    for (int j = 0; j < 4; ++j) {
+        float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+        if (active && colbase + 2 * j < E.ncols) t0 = __ldg(E.bn_tab + colbase + 2 * j);
+        if (active && colbase + 2 * j + 1 < E.ncols) t1 = __ldg(E.bn_tab + colbase + 2 * j + 1);
+        sc[j] = f2_make(t0.x, t1.x), sh[j] = f2_make(t0.y, t1.y);
+        s2[j] = q2[j] = 0ull;
     }
-    float s[8], q[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
     if (active) {
         const uint32_t off0 = static_cast<uint32_t>(oct >> 3) * kPanelBytes + static_cast<uint32_t>(seg) * 128u +
                               (static_cast<uint32_t>((oct ^ seg) & 7) << 4);
@@ -339,23 +340,30 @@ __device__ __forceinline__ void bn_column_pass(const EpiArgs& E, uint32_t stagin
 #pragma unroll 4
         for (int u = 0; u < nrows; ++u) {
             const uint32_t off = off0 + static_cast<uint32_t>(u) * step;
-            uint4 g = lds128(staging_u32 + off);
+            const uint4 g = lds128(staging_u32 + off);
             const uint4 yv = lds128(E.ybuf_u32 + off);
             uint32_t gw[4] = {g.x, g.y, g.z, g.w};
             const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float y0 = bf16_lo(yw[j]), y1 = bf16_hi(yw[j]);
+                const f32x2 y2 = f2_from_bf16x2(yw[j]);
                 if (E.bn_relu) {
-                    if (!(fmaf(y0, sc[2 * j], sh[2 * j]) > 0.f)) gw[j] &= 0xFFFF0000u;
-                    if (!(fmaf(y1, sc[2 * j + 1], sh[2 * j + 1]) > 0.f)) gw[j] &= 0x0000FFFFu;
+                    const uint32_t bn_out = f2_to_bf16x2(f2_fma(y2, sc[j], sh[j]));
+                    const __nv_bfloat162 ob = *reinterpret_cast<const __nv_bfloat162*>(&bn_out);
+                    gw[j] &= __hgt2_mask(ob, __float2bfloat162_rn(0.f));
                 }
-                const float g0 = bf16_lo(gw[j]), g1 = bf16_hi(gw[j]);
-                s[2 * j] += g0, s[2 * j + 1] += g1;
-                q[2 * j] = fmaf(g0, y0, q[2 * j]), q[2 * j + 1] = fmaf(g1, y1, q[2 * j + 1]);
+                const f32x2 g2 = f2_from_bf16x2(gw[j]);
+                s2[j] = f2_add(s2[j], g2);
+                q2[j] = f2_fma(g2, y2, q2[j]);
             }
             if (E.bn_relu) sts128(staging_u32 + off, make_uint4(gw[0], gw[1], gw[2], gw[3]));
         }
+    }
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        f2_split(s2[j], s[2 * j], s[2 * j + 1]);
+        f2_split(q2[j], q[2 * j], q[2 * j + 1]);
     }
     float v[16];
 #pragma unroll
@@ -1932,15 +1940,15 @@ Box choose_box(int OW, int OH, int OT, int ON, bool rows16) {
 }
 
 // N tile (multiple of 16, <= 256) for `cols` output channels given the number of M tiles.
-void choose_ntile(int cols, long long m_tiles, int* bn_tile, int* n_tiles) {
+void choose_ntile(int cols, long long m_tiles, int* bn_tile, int* n_tiles, int max_bn = 256) {
     const int cols16 = (cols + 15) & ~15;
     const int sms = std::max(1, sm_count());
     double best = 1e300;
-    int best_bn = std::min(cols16, 256), best_n = ceil_div(cols16, std::min(cols16, 256));
-    for (int nt = ceil_div(cols16, 256); nt <= ceil_div(cols16, 256) + 6 && nt <= ceil_div(cols16, 16); ++nt) {
+    int best_bn = std::min(cols16, max_bn), best_n = ceil_div(cols16, std::min(cols16, max_bn));
+    for (int nt = ceil_div(cols16, max_bn); nt <= ceil_div(cols16, max_bn) + 6 && nt <= ceil_div(cols16, 16); ++nt) {
         int bn = ((ceil_div(cols16, nt) + 15) & ~15);
         if (nt > 1) bn = (bn + 63) & ~63;   // the output is stored in 64-channel panels: tile origins stay panel-aligned
-        if (bn > 256) continue;
+        if (bn > max_bn) continue;
         if (nt > 1 && (long long)bn * (nt - 1) >= cols16) continue;   // last tile would be empty
         if (bn < 64 && cols16 >= 64) continue;
         const long long ctas = m_tiles * nt;
@@ -2783,7 +2791,9 @@ extern "C" int zsv_conv3d_dgrad(const zsv_conv_desc* d, const void* dy, const vo
                         }
                 const long long m_tiles = (long long)a.tw * a.th * a.tt * a.tn;
                 int n_tiles;
-                choose_ntile(d->Cin, m_tiles, &a.bn_tile, &n_tiles);
+                // fused BatchNorm backward: a second tile-sized buffer (y) lives beside the output staging, so N tiles stay
+                // at 192 columns (3 panels) and the ring keeps 3-4 stages
+                choose_ntile(d->Cin, m_tiles, &a.bn_tile, &n_tiles, fuse ? 192 : 256);
                 CUtensorMap maps[kMaxMaps];
                 rc = make_plain_map(&maps[0], dy, d->N, s.To, s.Ho, s.Wo, d->Cout, s.coutp, b);
                 if (rc) return rc;

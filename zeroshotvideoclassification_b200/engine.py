@@ -124,8 +124,9 @@ def _conv_for(spec: ConvSpec, N, T, H, W, layout=_lib.X_NDHWC) -> ops.Conv3d:
 import os
 
 # fuse the reduction pass of BatchNorm backward into the epilogue of the dgrad that produces its input gradient:
-# 0 = never, 1 = only where the tile's main loop is long (the round-1 rule: spatial 1x3x3 dgrads), 2 = every stride-1 dgrad
-# (default since the fused epilogue became one shared-memory pass over the staged tile and a TMA-loaded y tile)
+# 0 = never, 1 = only where the tile's main loop is long (the round-1 rule: spatial 1x3x3 dgrads), 2 = also the shallow
+# dgrads of layers 2-4 (default since the fused epilogue became one shared-memory pass over the staged tile and a
+# TMA-loaded y tile), 3 = every stride-1 dgrad
 FUSE_BN_BWD = int(os.environ.get("ZSV_FUSE_BN_BWD", "2"))
 
 # run the weight-gradient GEMMs on a second stream: they only depend on dy, nothing in the backward chain depends on
@@ -439,9 +440,13 @@ class BackboneRunner:
         # Round 1's fused epilogue (a shuffle reduction per 16-column chunk) only paid where the tile's main loop is long
         # compared with its epilogue (spatial 1x3x3: few output channels, deep reduction) and tripled the time of the
         # wide, shallow temporal dgrads; mode 1 keeps that rule for A/B runs.
+        # With the one-pass epilogue (round 2) fusing wins everywhere except on shallow-K dgrads of the big layer-1
+        # tensors (temporal 144->64 at 16x56x56: the kernel is epilogue-bound, the fused epilogue costs +140 us where the
+        # separate reduction pass costs 105 us; measured, profiles/r02_fuse_modes.txt): those keep the two-pass form.
         op = rec.op
         deep = op.cout * op.kernel[0] * op.kernel[1] * op.kernel[2] >= 8 * op.cin
-        fuse = FUSE_BN_BWD and op.stride == (1, 1, 1) and (deep or FUSE_BN_BWD >= 2)
+        small = op.N * op.T * op.H * op.W * op.cin < 64_000_000
+        fuse = FUSE_BN_BWD and op.stride == (1, 1, 1) and (deep or (FUSE_BN_BWD == 2 and small) or FUSE_BN_BWD >= 3)
         if producer is not None and fuse:
             return rec.op.dgrad_bn_fused(dy, rec.wd, addend, producer.y, producer.table, producer.relu)
         return rec.op.dgrad(dy, rec.wd, addend)
