@@ -662,6 +662,7 @@ def replica_consistency(model, step, x_dev, z_dev, zdist, dist, dev, world):
     saved = {id(p): p.detach().clone() for p in params}
 
     def grads_of_one_backward():
+        torch.manual_seed(4321)          # same Dropout mask in both passes (C3D, network.py:124,167)
         for p in params:
             p.grad = None
         out = model(x_dev)
