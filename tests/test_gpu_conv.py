@@ -272,28 +272,43 @@ def test_fprop_bias_addend_relu_epilogue():
     assert rel_err(from_ndhwc(y, cout), ref) < TOL
 
 
-@pytest.mark.parametrize("case", [c for c in CASES if c[0] in ("spatial_64_64", "spatial_64_144", "spatial_odd_hw")],
-                         ids=lambda c: c[0])
-def test_row_linearised_kernel_opt_in(case, monkeypatch):
-    """igemm_lin_kernel (opt-in with ZSV_LIN=1; one haloed box per chunk, taps as unaligned descriptor offsets):
-    fprop with statistics and dgrad must match the oracle like the default kernels."""
+PAIR_WGRAD_CASES = [c for c in CASES if c[0] in ("spatial_s2_64_230", "temporal_s2_230_128", "spatial_256_460",
+                                                  "spatial_odd_hw", "c3d_27tap", "downsample_64_128")] + [
+    # layer-4 shapes: 7x7 planes (a 7x1x2x8 position box fills its 112-row slot), several N tiles, ragged last M tile
+    ("l4_spatial_512_600", 9, 2, 7, 7, 512, 600, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+    ("l4_temporal_921_512", 9, 2, 7, 7, 921, 512, (3, 1, 1), (1, 1, 1), (1, 0, 0)),
+    ("l4_ds_256_512", 5, 4, 14, 14, 256, 512, (1, 1, 1), (2, 2, 2), (0, 0, 0)),
+    # a box that does not fill its slot (5*3*2 = 30 rows in a 32-row slot: zeroed tail rows) and N/2 not a panel multiple
+    ("ragged_box", 1, 2, 3, 5, 200, 176, (1, 3, 3), (1, 1, 1), (0, 1, 1)),
+]
+
+
+@pytest.mark.parametrize("case", PAIR_WGRAD_CASES, ids=lambda c: c[0])
+@pytest.mark.parametrize("splits", ["", "1", "3"], ids=["plan", "split1", "split3"])
+def test_wgrad_cta_pair_kernel(case, splits, monkeypatch):
+    """wgrad_pair_kernel (cluster of two CTAs, cta_group::2 MMAs with M = 256, MN-major operands, each CTA loading its
+    own two x panels and half of the dy columns; forced on with ZSV_WGRAD_PAIR=2 so that every geometry it can run is
+    covered): the weight gradient must match the oracle with the planned split-K factor, without split-K and with a
+    forced one, and agree with the generic single-CTA kernel (ZSV_WGRAD_PAIR=0)."""
     from zeroshotvideoclassification_b200 import ops
-    monkeypatch.setenv("ZSV_LIN", "1")
     name, N, T, H, W, cin, cout, k, s, p = case
     x, w = _make(case)
-    op = ops.Conv3d(N, T, H, W, cin, cout, k, s, p)
-    wf, wd = op.pack(w.cuda(), need_dgrad=True)
-    y, ps, pq = op.fprop(to_ndhwc(x), wf, stats=True)
-    ref = vo.conv3d(x, w, None, s, p)
-    assert rel_err(from_ndhwc(y, cout), ref) < TOL
-    yb = y[..., :cout].float().reshape(-1, cout).double()
-    assert torch.allclose(ps.double().sum(0)[:cout].cpu(), yb.sum(0).cpu(), rtol=1e-4, atol=1e-2)
-    g = torch.Generator().manual_seed(4)
-    dy = bf16_round(torch.randn(ref.shape, generator=g))
-    dx_ref, _ = vo.conv3d_grads(x, w, dy, s, p)
-    dx = op.dgrad(to_ndhwc(dy), wd)
+    y = vo.conv3d(x, w, None, s, p)
+    g = torch.Generator().manual_seed(2)
+    dy = bf16_round(torch.randn(y.shape, generator=g))
+    _, dw_ref = vo.conv3d_grads(x, w, dy, s, p)
+    monkeypatch.setenv("ZSV_WGRAD_PAIR", "2")
+    if splits:
+        monkeypatch.setenv("ZSV_DEBUG_WGRAD_SPLITS", splits)
+    op = ops.Conv3d(N, T, H, W, cin, cout, k, s, p)          # (the workspace size is fixed at construction)
+    dw, _ = op.wgrad(to_ndhwc(x), to_ndhwc(dy))
     torch.cuda.synchronize()
-    assert rel_err(from_ndhwc(dx, cin), dx_ref) < TOL
+    assert rel_err(dw.cpu(), dw_ref) < 2e-3, name
+    monkeypatch.setenv("ZSV_WGRAD_PAIR", "0")
+    op0 = ops.Conv3d(N, T, H, W, cin, cout, k, s, p)
+    dw0, _ = op0.wgrad(to_ndhwc(x), to_ndhwc(dy))
+    torch.cuda.synchronize()
+    assert rel_err(dw.cpu(), dw0.cpu()) < 1e-3, name
 
 
 @pytest.mark.parametrize("case", [c for c in CASES if c[0] in ("spatial_s2_64_230", "spatial_256_460", "temporal_s2_230_128",

@@ -1553,6 +1553,205 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Weight gradient of the wide layers (layers 2-4) on CTA pairs: cluster of 2, tcgen05 cta_group::2, M = 256.
+//
+// The generic kernel above computes 128 x <=256 output tiles: (128 + 256) * 2 bytes of operands per reduction row for
+// 32 K MACs, i.e. 96 B/clk/SM at tensor rate against ~42 B/clk/SM the L2->SM path delivers, and on layer 4 (2 156
+// positions, 72 x-panels x 1152 output channels) it needs 180 CTAs with a two-stage ring: 85-98 us against a 16 us
+// tensor floor.  Here a pair of CTAs owns a 256 x <=256 tile: each CTA loads the two 64-channel x panels of ITS 128
+// accumulator rows and HALF of the dy columns (the MMA reads the other half from the peer's shared memory), so
+// operand bytes per SM and MAC halve; the position box is free of the 128-row limit of an M tile (rows only have to
+// be padded to the K = 16 granule: 7 x 1 x 2 x 8 = 112 positions of a layer-4 tensor fill a block completely) and the
+// tail rows of a padded slot are zeroed once.  Split-K only where the tiles would leave SMs idle.
+// grid = (2 * M tiles, N tiles, splits), cluster (2,1,1); ws[split][tap][ci][co] as for the generic kernel.
+// ------------------------------------------------------------------------------------------------
+struct WgradPairArgs {
+    int32_t bw, bh, bt, bn;  // box of positions forming one K block
+    int32_t tw, th, tt, tn;
+    int32_t rows, slot_rows; // rows of one box, rows of its shared-memory slot (multiple of 16, tail rows stay zero)
+    int32_t kchunks, npanels, ntaps;
+    int32_t ci_store, ci_pitch, co_pitch;
+    int32_t bn_tile, half_n, nbh;   // UMMA N, columns per CTA, 64-wide dy panels per CTA
+    int32_t stages, tmem_cols;
+    int32_t num_kb, kb_per_split;
+    float* ws;
+    Tap taps[kMaxTaps];
+};
+
+__global__ void __launch_bounds__(192, 1)
+wgrad_pair_kernel(const __grid_constant__ MapPack mapsA, const __grid_constant__ CUtensorMap mapB,
+                  const __grid_constant__ WgradPairArgs P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int stages = P.stages;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t panelBytes = static_cast<uint32_t>(P.slot_rows) * 128u;
+    const uint32_t stageBytes = (2u + P.nbh) * panelBytes;
+    const uint32_t ringBytes = stages * stageBytes;
+    const uint32_t barFull = base + ringBytes;
+    const uint32_t barEmpty = barFull + 8u * stages;
+    const uint32_t barTmem = barEmpty + 8u * stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ringBytes + 16u * stages + 8u);
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(barFull + 8u * s, 1);
+            mbar_init(barEmpty + 8u * s, 1);
+        }
+        mbar_init(barTmem, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc2(smem_u32(tmem_slot), P.tmem_cols);
+    if (P.rows < P.slot_rows) {
+        // rows of a slot past the box are never written by TMA: they are reduction rows and must read as zeros
+        const uint32_t tail16 = static_cast<uint32_t>(P.slot_rows - P.rows) * 8u;   // 16-byte vectors per panel
+        const uint32_t npan = stages * (2u + P.nbh);
+        for (uint32_t i = threadIdx.x; i < npan * tail16; i += blockDim.x) {
+            const uint32_t pn = i / tail16, v = i - pn * tail16;
+            *reinterpret_cast<uint4*>(smem + pn * panelBytes + static_cast<uint32_t>(P.rows) * 128u + v * 16u) =
+                make_uint4(0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async_smem();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int m_tile = blockIdx.x >> 1;
+    const int n_tile = blockIdx.y;
+    const int split = blockIdx.z;
+    const int kb0 = split * P.kb_per_split;
+    const int kb1 = min(P.num_kb, kb0 + P.kb_per_split);
+    const int p0 = 4 * m_tile + 2 * static_cast<int>(rank);     // first x panel of THIS CTA (its 128 accumulator rows)
+
+    if (warp == 0) {
+        const uint32_t leader = elect_one();
+        const uint32_t tx = 2u * static_cast<uint32_t>(P.rows) * 128u * (2u + P.nbh);   // both CTAs' bytes
+        const uint32_t fullLeader = mapa_shared(barFull, 0);
+        // the two x panels of this CTA (a panel past the end repeats the last one; its rows are never stored)
+        Tap tapj[2];
+        int c0j[2];
+        const CUtensorMap* mpj[2];
+        for (int j = 0; j < 2; ++j) {
+            const int p = min(p0 + j, P.npanels - 1);
+            const int tp = p / P.kchunks;
+            c0j[j] = (p - tp * P.kchunks) << 6;
+            tapj[j] = P.taps[tp];
+            mpj[j] = &mapsA.m[tapj[j].map];
+        }
+        const int nb0 = n_tile * P.bn_tile + static_cast<int>(rank) * P.half_n;   // first dy channel of this CTA
+        int m = kb0;
+        int iw = m % P.tw;
+        m /= P.tw;
+        int ih = m % P.th;
+        m /= P.th;
+        int it = m % P.tt;
+        int in_ = m / P.tt;
+        uint32_t stage = 0, phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(barEmpty + 8u * stage, phase ^ 1u);
+            if (leader) {
+                const int w0 = iw * P.bw, h0 = ih * P.bh, t0 = it * P.bt, n0 = in_ * P.bn;
+                const uint32_t full = fullLeader + 8u * stage;
+                const uint32_t sa = base + stage * stageBytes;
+                if (rank == 0) mbar_expect_tx(barFull + 8u * stage, tx);
+                for (int j = 0; j < 2; ++j)
+                    tma2_load_5d(sa + j * panelBytes, mpj[j], full, c0j[j], w0 + tapj[j].dw, h0 + tapj[j].dh,
+                                 t0 + tapj[j].dt, n0);
+                for (int j = 0; j < P.nbh; ++j)
+                    tma2_load_5d(sa + (2u + j) * panelBytes, &mapB, full, nb0 + 64 * j, w0, h0, t0, n0);
+            }
+            __syncwarp();
+            if (++stage == static_cast<uint32_t>(stages)) {
+                stage = 0;
+                phase ^= 1u;
+            }
+            if (++iw == P.tw) {
+                iw = 0;
+                if (++ih == P.th) {
+                    ih = 0;
+                    if (++it == P.tt) {
+                        it = 0;
+                        ++in_;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && rank == 0) {
+        const uint32_t leader = elect_one();
+        const uint32_t idesc = umma_idesc_bf16(256, P.bn_tile, 1, 1);
+        const int ksteps = P.slot_rows >> 4;
+        // MN-major SWIZZLE_128B descriptors: LBO = panel stride (next 64 channels), SBO = 1024 B (next 8 positions)
+        const uint32_t dhi = umma_desc_hi(1024, 2);
+        const uint32_t lbo = (panelBytes >> 4) << 16;
+        uint32_t stage = 0, phase = 0;
+        uint32_t acc = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(barFull + 8u * stage, phase);
+            tc_fence_after();
+            if (leader) {
+                const uint32_t sa = base + stage * stageBytes;
+                const uint32_t a_lo = ((sa >> 4) & 0x3FFFu) | lbo;
+                const uint32_t b_lo = (((sa + 2u * panelBytes) >> 4) & 0x3FFFu) | lbo;
+                umma2_bf16_lohi(tmem_base, a_lo, dhi, b_lo, dhi, idesc, acc);
+                for (int k = 1; k < ksteps; ++k)   // 16 position rows = 2048 B per step
+                    umma2_bf16_lohi(tmem_base, a_lo + 128u * k, dhi, b_lo + 128u * k, dhi, idesc, 1u);
+                acc = 1;
+                umma2_commit_mc(barEmpty + 8u * stage, 3);
+            }
+            __syncwarp();
+            if (++stage == static_cast<uint32_t>(stages)) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        }
+        if (leader) umma2_commit_mc(barTmem, 3);
+        __syncwarp();
+    } else if (warp >= 2) {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int p = p0 + (row >> 6);
+        const int tp = min(p, P.npanels - 1) / P.kchunks;
+        const int ci = ((p - tp * P.kchunks) << 6) + (row & 63);
+        const bool valid = p < P.npanels && ci < P.ci_store;
+        float* dst = P.ws + (((long long)split * P.ntaps + tp) * P.ci_pitch + ci) * P.co_pitch + n_tile * P.bn_tile;
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        mbar_wait(barTmem, 0);
+        tc_fence_after();
+        for (int c = 0; c < P.bn_tile; c += 32) {
+            uint32_t v0[16], v1[16];
+            const bool two = c + 16 < P.bn_tile;
+            tmem_ld16(trow + c, v0);
+            if (two) tmem_ld16(trow + c + 16, v1);
+            tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(dst + c + 4 * j) = make_uint4(v0[4 * j], v0[4 * j + 1], v0[4 * j + 2], v0[4 * j + 3]);
+                if (two) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(dst + c + 16 + 4 * j) =
+                            make_uint4(v1[4 * j], v1[4 * j + 1], v1[4 * j + 2], v1[4 * j + 3]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    cluster_sync_all();     // neither CTA leaves (or frees TMEM) while the pair still reads its shared memory
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, P.tmem_cols);
+    }
+}
+
 // dw[co][ci][tap] = sum_split ws[split][tap][ci][co]
 // Transposing reduction through shared memory: a block owns 32 output channels x ci_tile input channels x all taps.
 // The split partials are read coalesced along co, four (tap, ci) rows per warp in flight; the tile is staged in OUTPUT
@@ -2878,6 +3077,141 @@ int plan_wgrad(const zsv_conv_desc* d, const Shape& s, WgradPlan* p) {
 }  // namespace
 
 namespace {
+// ---- CTA-pair weight gradient (wgrad_pair_kernel) ---------------------------------------------------
+struct WgradPairPlan {
+    bool ok;
+    Box box;
+    int rows, slot_rows, num_kb, kchunks, npanels, m_tiles, bn_tile, half_n, nbh, n_tiles, splits, kb_per_split, stages;
+    int ci_pitch, co_pitch, tmem_cols, smem;
+    size_t ws_bytes;
+};
+
+// Plain-layout convolutions with at least one full 256-row M tile (taps x 64-channel chunks >= 4) and >= 128 output
+// channels: layers 2-4.  Picks the position box (least padding of the K = 16 granule), the N tiling and the split-K
+// factor from a small time model: waves x (k-blocks per item x L2-bound block time + fixed cost per item) + the traffic
+// of the split partials.
+WgradPairPlan plan_wgrad_pair(const zsv_conv_desc* d, const Shape& s) {
+    WgradPairPlan p;
+    memset(&p, 0, sizeof(p));
+    const char* e = getenv("ZSV_WGRAD_PAIR");
+    if (e && atoi(e) == 0) return p;
+    if (s.wfold) return p;
+    p.kchunks = ceil_div(s.keff, 64);
+    p.npanels = s.ftaps * p.kchunks;
+    const bool force = e && atoi(e) == 2;      // tests: every layout the kernel can run
+    if (!force && (p.npanels < 4 || d->Cout < 128)) return p;
+    const int OW = s.Wo, OH = s.Ho, OT = s.To, ON = d->N;
+    const double total = (double)OW * OH * OT * ON;
+    const int pairs = std::max(1, sm_count() / 2);
+    const int cols16 = (d->Cout + 15) & ~15;
+    p.m_tiles = ceil_div(p.npanels, 4);
+    double best = 1e300;
+    for (int nt = ceil_div(cols16, 256); nt <= ceil_div(cols16, 256) + 3 && nt <= ceil_div(cols16, 16); ++nt) {
+        const int bn = (ceil_div(cols16, nt) + 15) & ~15;
+        if (bn > 256 || (nt > 1 && bn * (nt - 1) >= cols16)) continue;
+        const int nbh = ceil_div(bn / 2, 64);
+        // widest slot that still leaves a 3-deep ring
+        const int max_slot = std::min(256, ((220 * 1024 / 3) / ((2 + nbh) * 128)) & ~15);
+        Box bb{1, 1, 1, 1};
+        double bscore = -1;
+        for (int bw = 1; bw <= std::min(OW, max_slot); ++bw)
+            for (int bh = 1; bh <= std::min(OH, max_slot / bw); ++bh)
+                for (int bt = 1; bt <= std::min(OT, max_slot / (bw * bh)); ++bt)
+                    for (int bnn = 1; bnn <= std::min(ON, max_slot / (bw * bh * bt)); ++bnn) {
+                        const int rows = bw * bh * bt * bnn;
+                        const int slot = (rows + 15) & ~15;
+                        if (slot > max_slot) continue;
+                        const double tiles = (double)ceil_div(OW, bw) * ceil_div(OH, bh) * ceil_div(OT, bt) * ceil_div(ON, bnn);
+                        // MMA rows spent per useful position, plus ~1.5 k-steps of barrier / issue latency per block
+                        const double score = total / (tiles * (slot + 24.0)) + 1e-7 * bw;
+                        if (score > bscore) bscore = score, bb = Box{bw, bh, bt, bnn};
+                    }
+        if (bscore < 0) continue;
+        const int rows = bb.rows(), slot = (rows + 15) & ~15;
+        const int num_kb = ceil_div(OW, bb.bw) * ceil_div(OH, bb.bh) * ceil_div(OT, bb.bt) * ceil_div(ON, bb.bn);
+        // time of one k-block in clocks: L2 -> SM ingest (~42 B/clk/SM) against the MMA itself (4096 MAC/clk/SM)
+        const double t_kb = std::max(slot * (2.0 + nbh) * 128.0 / 42.0, slot * 256.0 * bn / 8192.0) + 150.0;
+        const long long tiles = (long long)p.m_tiles * nt;
+        const double ws_clk = (double)s.ftaps * (double)(s.cinp) * (double)(nt * bn) * 8.0 / 3400.0;   // write + read per split
+        for (int sp = 1; sp <= std::min(num_kb, 64); ++sp) {
+            const int kbs = ceil_div(num_kb, sp);
+            const int sp_eff = ceil_div(num_kb, kbs);
+            const double waves = (double)ceil_div_ll(tiles * sp_eff, pairs);
+            const double cost = waves * (kbs * t_kb + 4000.0) + sp_eff * ws_clk;
+            if (cost < best) {
+                best = cost;
+                p.box = bb, p.rows = rows, p.slot_rows = slot, p.num_kb = num_kb;
+                p.bn_tile = bn, p.half_n = bn / 2, p.nbh = nbh, p.n_tiles = nt;
+                p.kb_per_split = kbs, p.splits = sp_eff;
+            }
+        }
+    }
+    if (best >= 1e300) return p;
+    if (const char* f = getenv("ZSV_DEBUG_WGRAD_SPLITS")) {
+        const int sp = std::max(1, std::min(p.num_kb, atoi(f)));
+        p.kb_per_split = ceil_div(p.num_kb, sp);
+        p.splits = ceil_div(p.num_kb, p.kb_per_split);
+    }
+    const int stage = (2 + p.nbh) * p.slot_rows * 128;
+    p.stages = std::max(2, std::min(6, (225 * 1024 - 1024) / stage));
+    p.smem = 1024 + p.stages * stage + 16 * p.stages + 64;
+    if (p.smem > 227 * 1024) return p;
+    p.tmem_cols = pow2_cols(p.bn_tile);
+    p.ci_pitch = s.cinp;
+    p.co_pitch = p.n_tiles * p.bn_tile;
+    p.ws_bytes = (size_t)p.splits * s.ftaps * p.ci_pitch * p.co_pitch * 4;
+    p.ok = true;
+    if (getenv("ZSV_DEBUG_PLAN"))
+        fprintf(stderr, "[zsv] wgrad pair plan %d->%d taps %d pos %dx%dx%dx%d: box %d,%d,%d,%d rows %d/%d kb %d  M tiles %d  N %d x %d  "
+                        "splits %d x %d kb  stages %d\n", d->Cin, d->Cout, s.ftaps, OW, OH, OT, ON, p.box.bw, p.box.bh, p.box.bt,
+                p.box.bn, p.rows, p.slot_rows, p.num_kb, p.m_tiles, p.n_tiles, p.bn_tile, p.splits, p.kb_per_split, p.stages);
+    return p;
+}
+
+int launch_wgrad_pair(const WgradPairPlan& p, const zsv_conv_desc* d, const Shape& s, const void* x, const void* dy,
+                      void* workspace, cudaStream_t st) {
+    WgradPairArgs a;
+    memset(&a, 0, sizeof(a));
+    const Box& b = p.box;
+    a.bw = b.bw, a.bh = b.bh, a.bt = b.bt, a.bn = b.bn;
+    a.tw = ceil_div(s.Wo, b.bw), a.th = ceil_div(s.Ho, b.bh), a.tt = ceil_div(s.To, b.bt), a.tn = ceil_div(d->N, b.bn);
+    a.rows = p.rows, a.slot_rows = p.slot_rows;
+    a.kchunks = p.kchunks, a.npanels = p.npanels, a.ntaps = s.ftaps;
+    a.ci_store = p.ci_pitch, a.ci_pitch = p.ci_pitch, a.co_pitch = p.co_pitch;
+    a.bn_tile = p.bn_tile, a.half_n = p.half_n, a.nbh = p.nbh;
+    a.stages = p.stages, a.tmem_cols = p.tmem_cols;
+    a.num_kb = p.num_kb, a.kb_per_split = p.kb_per_split;
+    a.ws = (float*)workspace;
+    CUtensorMap maps[kMaxMaps];
+    int nmaps;
+    int rc = build_fwd_taps(d, s, x, b, a.taps, maps, &nmaps);
+    if (rc) return rc;
+    CUtensorMap mapB;
+    rc = make_plain_map(&mapB, dy, d->N, s.To, s.Ho, s.Wo, d->Cout, s.coutp, b);
+    if (rc) return rc;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    if (attr_err != cudaSuccess)
+        return fail(ZSV_ERR_CUDA, "cudaFuncSetAttribute(wgrad pair) failed: %s", cudaGetErrorString(attr_err));
+    MapPack pack;
+    for (int i = 0; i < kMaxMaps; ++i) pack.m[i] = maps[i];
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * p.m_tiles, p.n_tiles, p.splits), cfg.blockDim = dim3(192), cfg.dynamicSmemBytes = p.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr, cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, wgrad_pair_kernel, pack, mapB, a);
+    if (e != cudaSuccess) return fail(ZSV_ERR_CUDA, "launch of wgrad_pair_kernel failed: %s", cudaGetErrorString(e));
+    ZSV_LAUNCH_CHECK("wgrad_pair_kernel");
+    return ZSV_OK;
+}
+
 struct WgradHaloPlan {
     bool ok, spatial;
     int pair_taps, nacc, ncopies;
@@ -3038,7 +3372,11 @@ extern "C" size_t zsv_conv3d_wgrad_workspace(const zsv_conv_desc* d) {
     WgradPlan p;
     plan_wgrad(d, s, &p);
     const WgradHaloPlan hp = plan_wgrad_halo(d, s);
-    return hp.ok ? std::max(p.ws_bytes, hp.ws_bytes) : p.ws_bytes;
+    const WgradPairPlan pp = plan_wgrad_pair(d, s);
+    size_t need = p.ws_bytes;
+    if (hp.ok) need = std::max(need, hp.ws_bytes);
+    if (pp.ok) need = std::max(need, pp.ws_bytes);
+    return need;
 }
 
 extern "C" int zsv_conv3d_wgrad(const zsv_conv_desc* d, const void* x, const void* dy, float* dw, void* workspace,
@@ -3055,6 +3393,14 @@ extern "C" int zsv_conv3d_wgrad(const zsv_conv_desc* d, const void* x, const voi
         rc = launch_wgrad_halo(hp, d, s, x, dy, workspace, st);
         if (rc) return rc;
         return launch_wgrad_finalize(d, s, (const float*)workspace, dw, hp.splits, hp.ci_pitch, hp.co_pitch, st);
+    }
+    const WgradPairPlan pp = plan_wgrad_pair(d, s);
+    if (pp.ok) {
+        if (workspace_bytes < pp.ws_bytes)
+            return fail(ZSV_ERR_WORKSPACE, "wgrad: workspace %zu < required %zu bytes", workspace_bytes, pp.ws_bytes);
+        rc = launch_wgrad_pair(pp, d, s, x, dy, workspace, st);
+        if (rc) return rc;
+        return launch_wgrad_finalize(d, s, (const float*)workspace, dw, pp.splits, pp.ci_pitch, pp.co_pitch, st);
     }
     WgradPlan p;
     plan_wgrad(d, s, &p);
