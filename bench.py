@@ -237,6 +237,21 @@ def nearest_workload(dev, steps: int = 20, warmup: int = 3, n_rows: int = 10_000
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # 2x the 126 MB L2
     rng = np.random.default_rng(5)
     out = {"rows": n_rows, "dim": 300, "k": k, "l2": "flushed (256 MB write) before every timed call", "tables": {}}
+    # what the FP64 units of this GPU deliver: cuBLAS DGEMM 4096^3, measured here (the kernel issues one DFMA per
+    # (row, class, k) in scipy's order, so its bound is the FP64 pipe, not HBM)
+    a64 = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+    for _ in range(2):
+        torch.mm(a64, a64)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(3):
+        torch.mm(a64, a64)
+    g1.record()
+    torch.cuda.synchronize()
+    fp64_peak = 3 * 2.0 * 4096 ** 3 / (g0.elapsed_time(g1) * 1e-3) / 1e12
+    out["fp64_peak_tflops"] = fp64_peak
+    out["fp64_peak_source"] = "cuBLAS DGEMM 4096^3 timed in this run"
+    del a64
     launches0 = _lib.launch_count()
     for C in (101, 51, 200):
         emb = rng.standard_normal((n_rows, 300)).astype(np.float32)
@@ -277,6 +292,7 @@ def nearest_workload(dev, steps: int = 20, warmup: int = 3, n_rows: int = 10_000
             "device_us": us, "device_us_best": min(dev_us), "gb_per_s": alg_bytes / us / 1e3,
             "frac_of_hbm_peak": alg_bytes / us / 1e3 / peaks["hbm_gbs"], "algorithmic_bytes": alg_bytes,
             "fp64_gflops": 2.0 * n_rows * C * 300 / us / 1e3,
+            "frac_of_fp64_peak": 2.0 * n_rows * C * 300 / us / 1e6 / fp64_peak,
             "e2e_us": eus, "h2d_bytes": (n_rows + C) * 300 * 4, "d2h_bytes": n_rows * k * 8,
             "cpu_scipy_s": cpu_s, "cpu_cores": 1, "speedup_e2e_vs_scipy": cpu_s * 1e6 / eus,
             "top1_bit_equal": bool(np.array_equal(got[:, 0], d.argmin(1))),
@@ -310,8 +326,10 @@ def run_nearest(args):
                                "cosine distance (scipy cdist order, fp64) + 5 smallest per row", "l2": res["l2"]},
         "roofline": {"bound": "hbm", "achieved": t200["gb_per_s"], "peak": load_peaks()["hbm_gbs"], "unit": "GB/s",
                      "frac": t200["frac_of_hbm_peak"], "traffic": None,
-                     "note": "C=200 table; (N+C)*300*4 + N*5*8 algorithmic bytes; the kernel is bound by its sequential "
-                             "fp64 chains (scipy's summation order), not by HBM"},
+                     "note": "C=200 table; (N+C)*300*4 + N*5*8 algorithmic bytes; the kernel is bound by the FP64 pipe "
+                             "(N*C*300 DFMAs in scipy's summation order), not by HBM: see fp64",
+                     "fp64": {"achieved_tflops": t200["fp64_gflops"] / 1e3, "peak_tflops": res["fp64_peak_tflops"],
+                              "frac": t200["frac_of_fp64_peak"], "peak_source": res["fp64_peak_source"]}},
         "cpu_baseline": {"value": 3 * res["rows"] / total_cpu, "unit": "rows/s", "cores": 1, "kind": "reference",
                          "sample": "scipy cdist(...,'cosine') + argsort, the reference's own call (main.py:321-324), all three tables"},
         "e2e": {"value": 3 * res["rows"] / (total_e2e / 1e6), "unit": "rows/s",

@@ -53,6 +53,22 @@ def test_edge_cases():
     assert ops.nearest_class(torch.zeros((0, 300)).cuda(), torch.from_numpy(cls).cuda(), k=1).shape == (0, 1)
 
 
+@pytest.mark.parametrize("N,C,D", [(37, 1500, 301), (1100, 700, 300), (25, 130, 64), (3000, 9, 302), (1, 5, 3)],
+                         ids=["cluster8_two_rounds_odd_D", "many_rows_wide_table", "second_row_block", "tiny_table", "one_row"])
+def test_kernel_variants_bit_exact(N, C, D):
+    """Every launch shape of zsv_nearest_class: the cluster kernel (class tiles over up to 8 CTAs, several rounds,
+    8-row fallback for wide tables, more than one row block) and the per-block kernel with a ragged last block."""
+    from zeroshotvideoclassification_b200 import ops
+    rng = np.random.default_rng(N + C)
+    emb, cls = _unit(rng, N, D), _unit(rng, C, D)
+    dist = no.cosine_distance_table(emb, cls)
+    k = min(5, C)
+    ref = no.topk_lowest_index(dist, k)
+    idx, d = ops.nearest_class(torch.from_numpy(emb).cuda(), torch.from_numpy(cls).cuda(), k=k, return_dist=True)
+    assert np.array_equal(idx.cpu().numpy(), ref)
+    assert np.array_equal(d.cpu().numpy(), np.take_along_axis(dist, ref, axis=1))
+
+
 def test_class_overlap_filter_matches_scipy():
     """filter_overlapping_classes (auxiliary/auxiliary_dataset.py:141-144): the kept-class mask is identical to scipy's."""
     cdist = pytest.importorskip("scipy.spatial.distance").cdist

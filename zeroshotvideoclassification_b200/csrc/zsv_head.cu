@@ -7,6 +7,7 @@
 // Nearest class (main.py:183, main.py:321-322): scipy cdist(...,'cosine') + argmin / argsort[:, :k],
 // restated in fp64 with scipy's exact operation order so that indices are bit-identical.
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 
@@ -106,131 +107,319 @@ __global__ void mse_kernel(const float* __restrict__ emb, const float* __restric
 // nearest class.  scipy's cdist_cosine: norms = sqrt(sum of squares), dot = sum of products, both fp64 in the
 // order scipy 1.18.1 compiles them (2-lane reduction: even-k and odd-k accumulators over the first D - D%2
 // terms, total = even + odd, then the odd tail term; see oracle/nearest_oracle.py).  Products of two fp32
-// values are exact in fp64, so fma == mul+add here.  cosine = dot / (nu*nv), clipped to +-1, d = 1 - cosine.
-// block = nt threads (one class each per tile) x R embedding rows; distances staged in shared memory,
-// then one warp per row extracts the k smallest (lowest index wins ties, NaN sorts last).
+// values are exact in fp64, so one DFMA per (row, class, k) equals scipy's mul + add bit for bit.
+// cosine = dot / (nu*nv), clipped to +-1, d = 1 - cosine.
+//
+// The dot products are a register-tiled fp64 contraction (the FP64 pipe is the bound: N*C*D DFMAs at 64 per clock
+// and SM).  A warp owns R embedding rows x 128 class slots (lane l: classes 2l, 2l+1, 64+2l, 64+2l+1) for ONE of scipy's two
+// accumulation lanes: the even-k warp and the odd-k warp of a tile run side by side and meet at the end
+// (total = even + odd), so a thread carries R*4 accumulators and the operand loads of the next k overlap the DFMAs
+// of the current one.  A block is 2 (parity) x G (row groups) x TC (class tiles) warps.  Both operands are staged
+// k-major as doubles in shared memory, 16 k at a time: per k a thread reads its four classes with two 16-byte loads
+// and its R rows with R/2 broadcast loads, for 4R DFMAs; the next chunk travels global -> registers meanwhile.
+// Norms ride along: thread i squares class slot i (and row i) of every staged chunk, in scipy's order.
+// The staging buffers alternate, so there is one block barrier per chunk.
+//   evaluation (main.py:321, thousands of rows): a block of G = 2 or 3 row groups walks all class tiles itself.
+//   train-time batch (main.py:183, ~22 rows x several hundred classes): the class tiles of one 24-row block are spread
+//   over a cluster of up to 8 CTAs; each writes its keys into the leader's table through distributed shared memory.
+// Distances are staged in shared memory [rows][C] as order-preserving 64-bit keys (NaN last); one warp per row then
+// extracts the k smallest with three warp-wide integer min reductions per pick (high word, low word, index: lowest
+// index wins ties).
 // ------------------------------------------------------------------------------------------------
-constexpr int kKC = 32;  // k-chunk of the class tile staged in shared memory
+constexpr int kNK = 16;    // k-chunk staged in shared memory
+constexpr int kCT = 128;   // class slots of one warp tile (32 lanes x 4)
+
+// four consecutive fp32 of row `row` starting at column k (zeros past the end of the row / table)
+__device__ __forceinline__ float4 ld_row4(const float* __restrict__ base, long long row, int nrows, int k, int D,
+                                          bool vec) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < nrows && k < D) {
+        const float* p = base + row * D + k;
+        if (vec) {
+            v = __ldg(reinterpret_cast<const float4*>(p));      // D % 4 == 0 and a 16-byte aligned base
+        } else {
+            v.x = p[0];
+            if (k + 1 < D) v.y = p[1];
+            if (k + 2 < D) v.z = p[2];
+            if (k + 3 < D) v.w = p[3];
+        }
+    }
+    return v;
+}
+
+// order-preserving map double -> uint64 (every NaN becomes the largest key but one; all-ones marks "taken")
+__device__ __forceinline__ unsigned long long dist_key(double d) {
+    if (d != d) return 0xFFFFFFFFFFFFFFFEull;
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_dist(unsigned long long key) {
+    if (key == 0xFFFFFFFFFFFFFFFEull) return __longlong_as_double(0x7FF8000000000000ll);
+    const unsigned long long b = (key >> 63) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
+    return __longlong_as_double((long long)b);
+}
+
+// class slot (within a 128-slot warp tile) of accumulator column c of a lane: {2l, 2l+1, 64+2l, 64+2l+1}, so that each
+// of the two 16-byte operand loads of a k step is contiguous across the warp (no bank conflicts)
+__device__ __forceinline__ int nearest_slot(int lane, int c) { return 2 * lane + (c & 1) + 64 * (c >> 1); }
 
 template <int R>
-__global__ void __launch_bounds__(R == 1 ? 1024 : 128)
+__device__ __forceinline__ void nearest_kstep(const double* __restrict__ qc, const double* __restrict__ qe,
+                                              double (&acc)[R][4]) {
+    double c[4], e[R];
+    *reinterpret_cast<double2*>(&c[0]) = *reinterpret_cast<const double2*>(qc);
+    *reinterpret_cast<double2*>(&c[2]) = *reinterpret_cast<const double2*>(qc + 64);
+#pragma unroll
+    for (int r = 0; r < R; r += 2) *reinterpret_cast<double2*>(&e[r]) = *reinterpret_cast<const double2*>(qe + r);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[r][j] = fma(e[r], c[j], acc[r][j]);
+}
+
+template <int R, int G, int TC, bool CL>
+__global__ void __launch_bounds__(64 * G * TC, CL ? 1 : 384 / (64 * G * TC))
 nearest_kernel(const float* __restrict__ emb, const float* __restrict__ cls, int N, int C, int D, int k,
-               int64_t* __restrict__ idx_out, double* __restrict__ dist_out) {
+               int64_t* __restrict__ idx_out, double* __restrict__ dist_out, int vec, int ncta) {
+    constexpr int NT = 64 * G * TC;      // threads
+    constexpr int RB = G * R;            // rows per block
+    constexpr int CS = TC * kCT;         // class slots per pass
+    constexpr int CP = CS + 2;           // pitch of a staged k-row of classes (keeps 16-byte alignment, spreads banks)
+    constexpr int NCF = (CS * 4 + NT - 1) / NT;   // float4 prefetch registers for the class chunk
+    constexpr int NCN = (CS + NT - 1) / NT;       // class slots whose norm a thread accumulates
+    constexpr int SB = kNK * (CP + RB);           // doubles of one staging buffer
     extern __shared__ double smd[];
-    double* dist = smd;                                               // [R][C]
-    double* nrm_e = dist + (size_t)R * C;                         // [R]
-    float* s_e = reinterpret_cast<float*>(nrm_e + R);             // [R][D]
-    float* s_c = s_e + (size_t)R * D;                             // [nt][kKC+1]
-    const int nt = blockDim.x;                                    // classes per tile = threads per block
-    const int i0 = blockIdx.x * R;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < R * D; i += nt) {
-        const int r = i / D, kk = i - r * D;
-        s_e[i] = (i0 + r < N) ? emb[(long long)(i0 + r) * D + kk] : 0.f;
-    }
-    __syncthreads();
+    double* dist = smd;                              // [RB][C] distance keys (cluster mode: only the leader's is used)
+    double* nrm_e = dist + (size_t)RB * C;           // [RB]
+    double* nrm_c = nrm_e + RB;                      // [CS]
+    double* stage = nrm_c + CS;                      // 2 x { [kNK][CP] classes, [kNK][RB] rows }
+    double* part = stage + 2 * SB;                   // cluster mode: [RB][CS] odd-lane partial sums (else they sit in dist)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int par = warp & 1;                        // scipy's accumulation lane of this warp: even or odd k
+    const int g = (warp >> 1) % G, t = (warp >> 1) / G;
+    const int rank = CL ? (int)cluster_ctarank() : 0;
+    const long long i0 = (long long)(CL ? blockIdx.x / ncta : blockIdx.x) * RB;
     const int Deven = D & ~1;
-    if (tid < R) {  // scipy _row_norms, same even/odd order as the dot products
-        double s0 = 0.0, s1 = 0.0;
-        for (int kk = 0; kk < Deven; kk += 2) {
-            const double v0 = (double)s_e[tid * D + kk], v1 = (double)s_e[tid * D + kk + 1];
-            s0 = __dadd_rn(s0, __dmul_rn(v0, v0));
-            s1 = __dadd_rn(s1, __dmul_rn(v1, v1));
-        }
-        double s = __dadd_rn(s0, s1);
-        if (Deven < D) {
-            const double v = (double)s_e[tid * D + Deven];
-            s = __dadd_rn(s, __dmul_rn(v, v));
-        }
-        nrm_e[tid] = sqrt(s);
-    }
-    __syncthreads();
-    for (int j0 = 0; j0 < C; j0 += nt) {
-        const int j = j0 + tid;
-        double acc0[R], acc1[R];  // even-k / odd-k accumulators
-        double cc0 = 0.0, cc1 = 0.0;      // squared norm of this thread's class row, same order
+    const int nchunks = (D + kNK - 1) / kNK;
+    const int ntiles = (C + CS - 1) / CS;
+    const int npass = CL ? (ntiles + ncta - 1) / ncta : ntiles;
+    // staging: float4 number n of this thread covers class slot (tid + NT n) / 4, k offset 4 * (tid & 3)
+    const int fq = tid & 3;
+    const bool erow = tid < RB * 4;                  // this thread also stages a row float4
+    const int er = tid >> 2;
+    const uint32_t dist_leader = CL ? mapa_shared(smem_u32(dist), 0) : 0u;
+
+    double ee0 = 0.0, ee1 = 0.0;                     // squared norm of row `tid` (threads < RB), scipy's two lanes
+    for (int pass = 0; pass < npass; ++pass) {
+        const int j0 = (CL ? pass * ncta + rank : pass) * CS;
+        if (j0 >= C) break;                          // (cluster mode: this CTA has no tile in the last round)
+        double acc[R][4];
+        double cc0[NCN], cc1[NCN];
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc0[r] = acc1[r] = 0.0;
-        for (int k0 = 0; k0 < D; k0 += kKC) {
-            __syncthreads();
-            for (int i = tid; i < nt * kKC; i += nt) {
-                const int jj = i / kKC, kk = i - jj * kKC;
-                s_c[jj * (kKC + 1) + kk] = (j0 + jj < C && k0 + kk < D) ? cls[(long long)(j0 + jj) * D + k0 + kk] : 0.f;
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+#pragma unroll
+        for (int n = 0; n < NCN; ++n) cc0[n] = cc1[n] = 0.0;
+
+        float4 pc[NCF], pe;
+        auto fetch = [&](int k0) {
+#pragma unroll
+            for (int n = 0; n < NCF; ++n) {
+                const int i = tid + NT * n;
+                pc[n] = i < CS * 4 ? ld_row4(cls, j0 + (i >> 2), C, k0 + 4 * fq, D, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            __syncthreads();
-            const int kmax = min(kKC, Deven - k0);  // kKC is even, so chunk-local parity == global parity
-            for (int kk = 0; kk < kmax; kk += 2) {
-                const double c0 = (double)s_c[tid * (kKC + 1) + kk], c1 = (double)s_c[tid * (kKC + 1) + kk + 1];
-                cc0 = __dadd_rn(cc0, __dmul_rn(c0, c0));
-                cc1 = __dadd_rn(cc1, __dmul_rn(c1, c1));
+            pe = erow ? ld_row4(emb, i0 + er, N, k0 + 4 * fq, D, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        auto put = [&](double* buf) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    acc0[r] = __dadd_rn(acc0[r], __dmul_rn((double)s_e[r * D + k0 + kk], c0));
-                    acc1[r] = __dadd_rn(acc1[r], __dmul_rn((double)s_e[r * D + k0 + kk + 1], c1));
+            for (int n = 0; n < NCF; ++n) {
+                const int i = tid + NT * n;
+                if (i < CS * 4) {
+                    double* d = buf + (4 * fq) * CP + (i >> 2);
+                    d[0] = (double)pc[n].x, d[CP] = (double)pc[n].y, d[2 * CP] = (double)pc[n].z, d[3 * CP] = (double)pc[n].w;
                 }
             }
-            if (Deven < D && k0 <= Deven && Deven < k0 + kKC) {  // odd tail term, added after even + odd
-                const double ct = (double)s_c[tid * (kKC + 1) + (Deven - k0)];
-                cc0 = __dadd_rn(__dadd_rn(cc0, cc1), __dmul_rn(ct, ct));
-                cc1 = 0.0;
+            if (erow) {
+                double* d = buf + kNK * CP + (4 * fq) * RB + er;
+                d[0] = (double)pe.x, d[RB] = (double)pe.y, d[2 * RB] = (double)pe.z, d[3 * RB] = (double)pe.w;
+            }
+        };
+        fetch(0);
+        put(stage);
+        if (nchunks > 1) fetch(kNK);
+        __syncthreads();
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int k0 = ch * kNK;
+            // chunk ch + 1 (in registers) goes to the other buffer, chunk ch + 2 starts its way from global memory,
+            // then chunk ch is contracted: one barrier per chunk
+            if (ch + 1 < nchunks) put(stage + ((ch + 1) & 1) * SB);
+            if (ch + 2 < nchunks) fetch(k0 + 2 * kNK);
+            const double* s_c = stage + (ch & 1) * SB;
+            const double* s_e = s_c + kNK * CP;
+            const int kmax = min(kNK, Deven - k0);   // kNK is even: chunk-local parity == global parity
+            const double* qc = s_c + par * CP + t * kCT + 2 * lane;
+            const double* qe = s_e + par * RB + g * R;
+            if (kmax == kNK) {
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    acc0[r] = __dadd_rn(__dadd_rn(acc0[r], acc1[r]), __dmul_rn((double)s_e[r * D + Deven], ct));
-                    acc1[r] = 0.0;
+                for (int i = 0; i < kNK / 2; ++i) nearest_kstep<R>(qc + 2 * i * CP, qe + 2 * i * RB, acc);
+            } else {
+                for (int kk = par; kk < kmax; kk += 2) nearest_kstep<R>(qc + (kk - par) * CP, qe + (kk - par) * RB, acc);
+            }
+            // norms of class slot tid (+ NT n) and, on the first pass, of row tid
+#pragma unroll
+            for (int n = 0; n < NCN; ++n) {
+                const int slot = tid + NT * n;
+                if (slot < CS) {
+                    const double* q = s_c + slot;
+                    for (int kk = 0; kk < kmax; kk += 2) {
+                        const double v0 = q[kk * CP], v1 = q[(kk + 1) * CP];
+                        cc0[n] = fma(v0, v0, cc0[n]);
+                        cc1[n] = fma(v1, v1, cc1[n]);
+                    }
+                }
+            }
+            if (pass == 0 && tid < RB) {
+                for (int kk = 0; kk < kmax; kk += 2) {
+                    const double v0 = s_e[kk * RB + tid], v1 = s_e[(kk + 1) * RB + tid];
+                    ee0 = fma(v0, v0, ee0);
+                    ee1 = fma(v1, v1, ee1);
+                }
+            }
+            __syncthreads();
+        }
+        // the last chunk is still staged: it holds the odd tail column (D odd) at row Deven - k0
+        const double* s_c = stage + ((nchunks - 1) & 1) * SB;
+        const double* s_e = s_c + kNK * CP;
+        const int kt = Deven - (nchunks - 1) * kNK;
+        const bool tail = Deven < D;
+#pragma unroll
+        for (int n = 0; n < NCN; ++n) {
+            const int slot = tid + NT * n;
+            if (slot < CS) {
+                double s = cc0[n] + cc1[n];
+                if (tail) {
+                    const double v = s_c[kt * CP + slot];
+                    s = fma(v, v, s);
+                }
+                nrm_c[slot] = sqrt(s);
+            }
+        }
+        if (pass == 0 && tid < RB) {
+            double s = ee0 + ee1;
+            if (tail) {
+                const double v = s_e[kt * RB + tid];
+                s = fma(v, v, s);
+            }
+            nrm_e[tid] = sqrt(s);
+        }
+        // the odd-k warp hands its sums to the even-k warp of the same tile
+        double* pbase = CL ? part + (size_t)(g * R) * CS + t * kCT : dist + (size_t)(g * R) * C + j0 + t * kCT;
+        const int ppitch = CL ? CS : C;
+        if (par) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int sl = nearest_slot(lane, c);
+                if (j0 + t * kCT + sl < C) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) pbase[(size_t)r * ppitch + sl] = acc[r][c];
                 }
             }
         }
-        if (j < C) {
-            // when D is odd the tail step above already folded the lanes (and zeroed the odd one: x + 0.0 == x)
-            const double nv = sqrt(__dadd_rn(cc0, cc1));
+        double ct[4], et[R];
+        if (tail && !par) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                double cosine = __dadd_rn(acc0[r], acc1[r]) / (nrm_e[r] * nv);
-                if (fabs(cosine) > 1.0) cosine = copysign(1.0, cosine);
-                dist[(size_t)r * C + j] = 1.0 - cosine;
+            for (int c = 0; c < 4; ++c) ct[c] = s_c[kt * CP + t * kCT + nearest_slot(lane, c)];
+#pragma unroll
+            for (int r = 0; r < R; ++r) et[r] = s_e[kt * RB + g * R + r];
+        }
+        __syncthreads();
+        if (!par) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int sl = nearest_slot(lane, c);
+                const int slot = t * kCT + sl;
+                const int j = j0 + slot;
+                if (j < C) {
+                    const double nv = nrm_c[slot];
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        double dot = acc[r][c] + pbase[(size_t)r * ppitch + sl];          // even + odd
+                        if (tail) dot = fma(et[r], ct[c], dot);
+                        double cosine = dot / (nrm_e[g * R + r] * nv);
+                        if (fabs(cosine) > 1.0) cosine = copysign(1.0, cosine);
+                        const unsigned long long key = dist_key(1.0 - cosine);
+                        if (CL) {
+                            const uint32_t a = dist_leader + (uint32_t)(((size_t)(g * R + r) * C + j) * 8);
+                            asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(a), "l"(key) : "memory");
+                        } else {
+                            *reinterpret_cast<unsigned long long*>(dist + (size_t)(g * R + r) * C + j) = key;
+                        }
+                    }
+                }
             }
         }
     }
-    __syncthreads();
+    if (CL) {
+        cluster_sync_all();            // every CTA's keys have landed in the leader's table
+        if (rank != 0) return;
+    } else {
+        __syncthreads();
+    }
     // selection: warp w handles rows w, w + #warps, ...
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int r = warp; r < R; r += (nt >> 5)) {
+    constexpr unsigned kFull = 0xffffffffu;
+    constexpr unsigned long long kTaken = 0xFFFFFFFFFFFFFFFFull;
+    for (int r = warp; r < RB; r += NT / 32) {
         if (i0 + r >= N) continue;
-        double* dr = dist + (size_t)r * C;
-        for (int sel = 0; sel < k; ++sel) {
-            double best = 0.0;
-            int bidx = -1;   // -1: nothing yet
-            bool bnan = true;
-            for (int j = lane; j < C; j += 32) {
-                const double v = dr[j];
-                if (v == -1.0e300) continue;  // already taken (distances live in [0,2])
-                const bool vnan = v != v;
-                bool better;
-                if (bidx < 0) better = true;
-                else if (bnan != vnan) better = bnan;          // a number beats NaN
-                else if (vnan) better = false;                 // both NaN: lower index (seen first) stays
-                else better = v < best;
-                if (better) best = v, bidx = j, bnan = vnan;
-            }
+        unsigned long long* dr = reinterpret_cast<unsigned long long*>(dist) + (size_t)r * C;
+        if (C <= 128) {
+            // the lane's (at most four) keys, classes lane, lane + 32, ..., sorted once in registers by (key, index);
+            // every pick then compares the lanes' heads
+            unsigned long long v[4];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
-                const int on = __shfl_xor_sync(0xffffffffu, (int)bnan, o);
-                bool better;
-                if (oi < 0) better = false;
-                else if (bidx < 0) better = true;
-                else if ((bool)on != bnan) better = bnan;
-                else if (bnan) better = oi < bidx;
-                else better = (ov < best) || (ov == best && oi < bidx);
-                if (better) best = ov, bidx = oi, bnan = (bool)on;
+            for (int m = 0; m < 4; ++m) v[m] = lane + 32 * m < C ? dr[lane + 32 * m] : kTaken;
+            int id[4] = {lane, lane + 32, lane + 64, lane + 96};
+            auto cx = [&](int a, int b) {
+                if (v[b] < v[a] || (v[b] == v[a] && id[b] < id[a])) {
+                    const unsigned long long tv = v[a];
+                    v[a] = v[b], v[b] = tv;
+                    const int ti = id[a];
+                    id[a] = id[b], id[b] = ti;
+                }
+            };
+            cx(0, 1), cx(2, 3), cx(0, 2), cx(1, 3), cx(1, 2);
+            for (int sel = 0; sel < k; ++sel) {
+                const unsigned hi = (unsigned)(v[0] >> 32), lo = (unsigned)v[0];
+                const unsigned mhi = __reduce_min_sync(kFull, hi);
+                const unsigned mlo = __reduce_min_sync(kFull, hi == mhi ? lo : 0xFFFFFFFFu);
+                const bool mine = hi == mhi && lo == mlo;
+                const int widx = (int)__reduce_min_sync(kFull, mine ? (unsigned)id[0] : 0x7FFFFFFFu);
+                if (mine && id[0] == widx) {
+                    idx_out[(i0 + r) * k + sel] = widx;
+                    if (dist_out) dist_out[(i0 + r) * k + sel] = key_dist(v[0]);
+                    v[0] = v[1], v[1] = v[2], v[2] = v[3], v[3] = kTaken;
+                    id[0] = id[1], id[1] = id[2], id[2] = id[3];
+                }
             }
-            if (lane == 0) {
-                idx_out[(long long)(i0 + r) * k + sel] = bidx;
-                if (dist_out) dist_out[(long long)(i0 + r) * k + sel] = best;
+            continue;
+        }
+        for (int sel = 0; sel < k; ++sel) {
+            unsigned long long best = kTaken;
+            int bidx = 0x7FFFFFFF;
+            for (int j = lane; j < C; j += 32) {
+                const unsigned long long v = dr[j];
+                if (v < best) best = v, bidx = j;      // ascending j: the first of equal keys stays
             }
-            __syncwarp();
-            if (bidx >= 0 && (bidx & 31) == lane) dr[bidx] = -1.0e300;
+            const unsigned hi = (unsigned)(best >> 32), lo = (unsigned)best;
+            const unsigned mhi = __reduce_min_sync(kFull, hi);
+            const unsigned mlo = __reduce_min_sync(kFull, hi == mhi ? lo : 0xFFFFFFFFu);
+            const bool mine = hi == mhi && lo == mlo;
+            const int widx = (int)__reduce_min_sync(kFull, mine ? (unsigned)bidx : 0x7FFFFFFFu);
+            if (mine && bidx == widx) {
+                idx_out[(i0 + r) * k + sel] = widx;
+                if (dist_out) dist_out[(i0 + r) * k + sel] = key_dist(best);
+                dr[widx] = kTaken;
+            }
             __syncwarp();
         }
     }
@@ -333,24 +522,57 @@ extern "C" int zsv_nearest_class(const float* emb, const float* cls, int N, int 
     if (N < 0 || C < 1 || D < 1 || k < 1 || k > 8 || k > C) return fail(ZSV_ERR_BAD_ARG, "nearest_class: bad sizes");
     if (N == 0) return ZSV_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    // few rows (train-time batch, main.py:183): one row per block so the grid still covers the SMs;
-    // many rows (evaluation, main.py:321): 8 rows per block amortise the class-table traffic
-    const int R = N <= 2048 ? 1 : 8;
-    // R == 1: the fp64 chain of one (row, class) pair is sequential by construction (scipy's order), so the block is made
-    // as wide as the class table (up to 1024 threads) instead of walking 128-class tiles one after the other
-    const int nt = R == 1 ? std::min(1024, ceil_div(C, 128) * 128) : 128;
-    const size_t smem = sizeof(double) * ((size_t)R * C + R) + sizeof(float) * ((size_t)R * D + (size_t)nt * (kKC + 1));
-    if (smem > 200 * 1024)
-        return fail(ZSV_ERR_UNSUPPORTED, "nearest_class: class table too large for shared memory (%zu bytes)", smem);
+    const int vec = (D % 4 == 0) && (reinterpret_cast<uintptr_t>(emb) % 16 == 0) && (reinterpret_cast<uintptr_t>(cls) % 16 == 0);
+    auto smem_of = [&](int RB, bool cl) {
+        return sizeof(double) * ((size_t)RB * C + RB + kCT + 2 * (size_t)kNK * (kCT + 2 + RB) + (cl ? (size_t)RB * kCT : 0));
+    };
+    // many rows (evaluation, main.py:321): a block owns 8 G rows and walks the class tiles, G = 2..3 whichever divides
+    // the blocks over the SMs with the least idle tail.  Few rows (the train-time batch, main.py:183) or a class table
+    // whose distance rows would not fit beside the staging buffers: the class tiles of a row block are spread over a
+    // cluster of up to 8 CTAs that write their keys into the leader's table (distributed shared memory).
+    int G = 0;
+    if (const char* e = getenv("ZSV_DEBUG_NEAREST_G")) {
+        G = atoi(e);
+        if (G < 2 || G > 3 || smem_of(8 * G, false) > 100 * 1024) G = 0;
+    } else if (N >= 1024) {
+        double best = 0.0;
+        for (int g = 3; g >= 2; --g) {
+            if (smem_of(8 * g, false) > 100 * 1024) continue;
+            const double per_sm = (double)ceil_div(N, 8 * g) / sm_count();
+            const double eff = per_sm / ceil(per_sm) * (g == 3 ? 1.0 : 0.97);   // fewer rows per staged class tile cost a little
+            if (eff > best) best = eff, G = g;
+        }
+    }
     static std::once_flag attr_once;
     std::call_once(attr_once, [] {
-        cudaFuncSetAttribute(nearest_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cudaFuncSetAttribute(nearest_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(nearest_kernel<8, 3, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(nearest_kernel<8, 2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(nearest_kernel<8, 3, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(nearest_kernel<8, 1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     });
-    if (R == 1)
-        nearest_kernel<1><<<N, nt, smem, st>>>(emb, cls, N, C, D, k, idx_out, dist_out);
-    else
-        nearest_kernel<8><<<ceil_div(N, 8), 128, smem, st>>>(emb, cls, N, C, D, k, idx_out, dist_out);
+    if (G) {
+        const size_t smem = smem_of(8 * G, false);
+        if (G == 3)
+            nearest_kernel<8, 3, 1, false><<<ceil_div(N, 24), 192, smem, st>>>(emb, cls, N, C, D, k, idx_out, dist_out, vec, 1);
+        else
+            nearest_kernel<8, 2, 1, false><<<ceil_div(N, 16), 128, smem, st>>>(emb, cls, N, C, D, k, idx_out, dist_out, vec, 1);
+    } else {
+        const int g = smem_of(24, true) <= 200 * 1024 ? 3 : 1;
+        const size_t smem = smem_of(8 * g, true);
+        if (smem > 200 * 1024)
+            return fail(ZSV_ERR_UNSUPPORTED, "nearest_class: class table too large for shared memory (%zu bytes)", smem);
+        const int ncta = std::min(8, ceil_div(C, kCT));
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(ncta * ceil_div(N, 8 * g)), cfg.blockDim = dim3(64 * g), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = ncta, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr, cfg.numAttrs = 1;
+        cudaError_t e = g == 3 ? cudaLaunchKernelEx(&cfg, nearest_kernel<8, 3, 1, true>, emb, cls, N, C, D, k, idx_out, dist_out, vec, ncta)
+                               : cudaLaunchKernelEx(&cfg, nearest_kernel<8, 1, 1, true>, emb, cls, N, C, D, k, idx_out, dist_out, vec, ncta);
+        if (e != cudaSuccess) return fail(ZSV_ERR_CUDA, "launch of nearest_kernel (cluster) failed: %s", cudaGetErrorString(e));
+    }
     ZSV_LAUNCH_CHECK("nearest_kernel");
     return ZSV_OK;
 }
