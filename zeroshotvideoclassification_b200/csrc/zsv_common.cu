@@ -3,6 +3,8 @@
 #include <mutex>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "zsv_internal.h"
 
 namespace zsv {
@@ -19,6 +21,15 @@ int fail(int status, const char* fmt, ...) {
 
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+bool pdl_allowed() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("ZSV_PDL");
+        v = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return v != 0;
+}
 
 int sm_count() {
     static int n = 0;

@@ -522,6 +522,7 @@ __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
                     const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
                     const __grid_constant__ CUtensorMap mapY, const __grid_constant__ IgemmArgs P) {
+    pdl_wait();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -838,6 +839,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                   const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBtail,
                   const __grid_constant__ CUtensorMap mapOut, const __grid_constant__ CUtensorMap mapY,
                   const __grid_constant__ HaloArgs P) {
+    pdl_wait();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -1202,6 +1204,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 __global__ void __launch_bounds__(192, 1)
 wgrad_mnmajor_kernel(const __grid_constant__ MapPack mapsA,
                      const __grid_constant__ CUtensorMap mapB, const __grid_constant__ WgradArgs P) {
+    pdl_wait();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -1398,6 +1401,7 @@ struct WgradHaloArgs {
 __global__ void __launch_bounds__(192, 1)
 wgrad_halo_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDy,
                   const __grid_constant__ WgradHaloArgs P) {
+    pdl_wait();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -1582,6 +1586,7 @@ struct WgradPairArgs {
 __global__ void __launch_bounds__(192, 1)
 wgrad_pair_kernel(const __grid_constant__ MapPack mapsA, const __grid_constant__ CUtensorMap mapB,
                   const __grid_constant__ WgradPairArgs P) {
+    pdl_wait();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -1762,6 +1767,7 @@ wgrad_pair_kernel(const __grid_constant__ MapPack mapsA, const __grid_constant__
 __global__ void __launch_bounds__(256)
 wgrad_finalize_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int ntaps, int ci_pitch,
                       int co_pitch, int Cin, int Cout, int ci_tile) {
+    pdl_wait();
     extern __shared__ float tile[];   // [32][run | 1]
     const int run = ci_tile * ntaps;
     const int pitch = run | 1;
@@ -1814,6 +1820,7 @@ wgrad_finalize_kernel(const float* __restrict__ ws, float* __restrict__ dw, int 
 __global__ void wgrad_finalize_small_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int ntaps,
                                             int ci_pitch, int co_pitch, int Cin, int Cout, int wfold_kw,
                                             int wfold_taps) {
+    pdl_wait();
     const long long total = (long long)ntaps * ci_pitch * co_pitch;
     const long long split_stride = total;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -1846,6 +1853,7 @@ __global__ void wgrad_finalize_small_kernel(const float* __restrict__ ws, float*
 __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
                                    __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int ntaps, int kpitch,
                                    int copitch, int wfold_kw) {
+    pdl_wait();
     const int ftaps = wfold_kw > 0 ? ntaps / wfold_kw : ntaps;
     const long long nf = wf ? (long long)ftaps * Cout * kpitch : 0;
     const long long nd = wd ? (long long)ntaps * Cin * copitch : 0;
@@ -1903,6 +1911,7 @@ struct PackBatch {
 
 __global__ void __launch_bounds__(256)
 pack_weights_batched_kernel(const __grid_constant__ PackBatch B) {
+    pdl_wait();
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < B.total;
          g += (long long)gridDim.x * blockDim.x) {
         int lo = 0, hi = B.n - 1;   // last item with start <= g
@@ -1972,6 +1981,7 @@ struct PackTileBatch {
 
 __global__ void __launch_bounds__(256)
 pack_weights_tiled_kernel(const __grid_constant__ PackTileBatch B) {
+    pdl_wait();
     __shared__ __align__(16) __nv_bfloat16 tile[kPackCo][kPackElems + 8];
     int lo = 0, hi = B.n - 1;   // last item with unit_start <= blockIdx.x
     while (lo < hi) {
@@ -2382,14 +2392,15 @@ int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtenso
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kIgemmThreads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = 2, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr, cfg.numAttrs = 1;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+        pdl_attribute(&attr[1]);
+        cfg.attrs = attr, cfg.numAttrs = 2;
         cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_kmajor_kernel<true>, pack, mapB, mapOut, mapY ? *mapY : mapOut, a);
         if (e != cudaSuccess) return fail(ZSV_ERR_CUDA, "launch of igemm_kmajor_kernel<pair> failed: %s", cudaGetErrorString(e));
     } else {
-        igemm_kmajor_kernel<false><<<grid, kIgemmThreads, smem, stream>>>(pack, mapB, mapOut, mapY ? *mapY : mapOut, a);
+        zsv::launch(igemm_kmajor_kernel<false>, grid, kIgemmThreads, smem, stream, pack, mapB, mapOut, mapY ? *mapY : mapOut, a);
     }
     ZSV_LAUNCH_CHECK("igemm_kmajor_kernel");
     return ZSV_OK;
@@ -2665,14 +2676,15 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kIgemmThreads), cfg.dynamicSmemBytes = p.smem, cfg.stream = st;
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = 2, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr, cfg.numAttrs = 1;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+        pdl_attribute(&attr[1]);
+        cfg.attrs = attr, cfg.numAttrs = 2;
         cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_halo_kernel<true>, mA, mAt, mB, mBt, mO, mY, a);
         if (e != cudaSuccess) return fail(ZSV_ERR_CUDA, "launch of igemm_halo_kernel<pair> failed: %s", cudaGetErrorString(e));
     } else {
-        igemm_halo_kernel<false><<<grid, kIgemmThreads, p.smem, st>>>(mA, mAt, mB, mBt, mO, mY, a);
+        zsv::launch(igemm_halo_kernel<false>, grid, kIgemmThreads, p.smem, st, mA, mAt, mB, mBt, mO, mY, a);
     }
     ZSV_LAUNCH_CHECK("igemm_halo_kernel");
     return ZSV_OK;
@@ -2715,8 +2727,7 @@ extern "C" int zsv_conv3d_pack_weight(const zsv_conv_desc* d, const float* w, vo
     const long long n = (w_fprop ? (long long)s.ftaps * d->Cout * s.kpitch : 0) +
                         (w_dgrad ? (long long)s.ntaps * d->Cin * s.coutp : 0);
     const int blocks = (int)std::min<long long>(ceil_div_ll(n, 256), 148 * 16);
-    pack_weight_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
-        w, (__nv_bfloat16*)w_fprop, (__nv_bfloat16*)w_dgrad, d->Cout, d->Cin, s.ntaps, s.kpitch, s.coutp,
+    zsv::launch(pack_weight_kernel, blocks, 256, 0, (cudaStream_t)stream, w, (__nv_bfloat16*)w_fprop, (__nv_bfloat16*)w_dgrad, d->Cout, d->Cin, s.ntaps, s.kpitch, s.coutp,
         s.wfold ? d->kw : 0);
     ZSV_LAUNCH_CHECK("pack_weight_kernel");
     return ZSV_OK;
@@ -2780,14 +2791,14 @@ static int pack_weights_impl(int n, const zsv_conv_desc* descs, const float* con
             ++m;
         }
         if (TB.n > 0) {
-            pack_weights_tiled_kernel<<<TB.units, 256, 0, st>>>(TB);
+            zsv::launch(pack_weights_tiled_kernel, TB.units, 256, 0, st, TB);
             ZSV_LAUNCH_CHECK("pack_weights_tiled_kernel");
         }
         if (m == 0) continue;
         B.n = m;
         B.total = total;
         const int blocks = (int)std::min<long long>(ceil_div_ll(total, 256), (long long)sm_count() * 16);
-        pack_weights_batched_kernel<<<blocks, 256, 0, st>>>(B);
+        zsv::launch(pack_weights_batched_kernel, blocks, 256, 0, st, B);
         ZSV_LAUNCH_CHECK("pack_weights_batched_kernel");
     }
     return ZSV_OK;
@@ -3202,10 +3213,11 @@ int launch_wgrad_pair(const WgradPairPlan& p, const zsv_conv_desc* d, const Shap
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * p.m_tiles, p.n_tiles, p.splits), cfg.blockDim = dim3(192), cfg.dynamicSmemBytes = p.smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr, cfg.numAttrs = 1;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    pdl_attribute(&attr[1]);
+    cfg.attrs = attr, cfg.numAttrs = 2;
     cudaError_t e = cudaLaunchKernelEx(&cfg, wgrad_pair_kernel, pack, mapB, a);
     if (e != cudaSuccess) return fail(ZSV_ERR_CUDA, "launch of wgrad_pair_kernel failed: %s", cudaGetErrorString(e));
     ZSV_LAUNCH_CHECK("wgrad_pair_kernel");
@@ -3330,7 +3342,7 @@ int launch_wgrad_halo(const WgradHaloPlan& p, const zsv_conv_desc* d, const Shap
     });
     if (attr_err != cudaSuccess)
         return fail(ZSV_ERR_CUDA, "cudaFuncSetAttribute(wgrad halo) failed: %s", cudaGetErrorString(attr_err));
-    wgrad_halo_kernel<<<dim3(p.splits, p.ncopies), 192, p.smem, st>>>(mX, mDy, a);
+    zsv::launch(wgrad_halo_kernel, dim3(p.splits, p.ncopies), 192, p.smem, st, mX, mDy, a);
     ZSV_LAUNCH_CHECK("wgrad_halo_kernel");
     return ZSV_OK;
 }
@@ -3348,7 +3360,7 @@ int launch_wgrad_finalize(const zsv_conv_desc* d, const Shape& s, const float* w
     // (tap = (dt,dh), ci = dw*8 + c).
     if (s.wfold || wtotal < (1LL << 20) || getenv("ZSV_DEBUG_FINALIZE_SMALL")) {
         const int blocks = (int)std::min<long long>(ceil_div_ll(wtotal, 256), 148 * 8);
-        wgrad_finalize_small_kernel<<<blocks, 256, 0, st>>>(ws, dw, splits, s.ftaps, ci_pitch, co_pitch, d->Cin, d->Cout,
+        zsv::launch(wgrad_finalize_small_kernel, blocks, 256, 0, st, ws, dw, splits, s.ftaps, ci_pitch, co_pitch, d->Cin, d->Cout,
                                                             s.wfold ? d->kw : 0, s.ntaps);
         ZSV_LAUNCH_CHECK("wgrad_finalize_small_kernel");
         return ZSV_OK;
@@ -3360,7 +3372,7 @@ int launch_wgrad_finalize(const zsv_conv_desc* d, const Shape& s, const float* w
     const size_t fsm = (size_t)32 * ((ci_tile * s.ftaps) | 1) * sizeof(float);
     if (fsm > 48 * 1024) return fail(ZSV_ERR_UNSUPPORTED, "wgrad finalize: %d taps do not fit the staging tile", s.ftaps);
     dim3 fgrid(ceil_div(d->Cout, 32), ceil_div(d->Cin, ci_tile));
-    wgrad_finalize_kernel<<<fgrid, 256, fsm, st>>>(ws, dw, splits, s.ftaps, ci_pitch, co_pitch, d->Cin, d->Cout, ci_tile);
+    zsv::launch(wgrad_finalize_kernel, fgrid, 256, fsm, st, ws, dw, splits, s.ftaps, ci_pitch, co_pitch, d->Cin, d->Cout, ci_tile);
     ZSV_LAUNCH_CHECK("wgrad_finalize_kernel");
     return ZSV_OK;
 }
@@ -3447,7 +3459,7 @@ extern "C" int zsv_conv3d_wgrad(const zsv_conv_desc* d, const void* x, const voi
     dim3 grid(p.m_tiles, p.n_tiles, p.splits);
     MapPack pack;
     for (int i = 0; i < kMaxMaps; ++i) pack.m[i] = maps[i];
-    wgrad_mnmajor_kernel<<<grid, 192, smem, st>>>(pack, mapB, a);
+    zsv::launch(wgrad_mnmajor_kernel, grid, 192, smem, st, pack, mapB, a);
     ZSV_LAUNCH_CHECK("wgrad_mnmajor_kernel");
 
     return launch_wgrad_finalize(d, s, (const float*)workspace, dw, p.splits, p.ci_pitch, p.co_pitch, st);

@@ -30,6 +30,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // fp32 NCDHW -> bf16 [N][T][H][Wp][Cp]; column w of the source lands at column w + wl; pad columns/lanes are zero.
 __global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int C,
                                       int T, int H, int W, int Cp, int Wp, int wl) {
+    pdl_wait();
     const int V = Cp >> 3;
     const long long thw = (long long)T * H * W;
     const long long total = (long long)N * T * H * Wp * V;
@@ -59,6 +60,7 @@ __global__ void ncdhw_to_ndhwc_kernel(const float* __restrict__ x, __nv_bfloat16
 
 __global__ void ndhwc_to_ncdhw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int N, int C,
                                       int T, int H, int W, int Cp) {
+    pdl_wait();
     const int V = Cp >> 3;
     const long long thw = (long long)T * H * W;
     const long long total = (long long)N * thw * V;
@@ -96,6 +98,7 @@ bn_finalize_kernel(const float* __restrict__ part_sum, const float* __restrict__
                    float* __restrict__ running_var, float momentum, float eps, float* __restrict__ scale,
                    float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ invstd_out,
                    float4* __restrict__ bwd_table) {
+    pdl_wait();
     __shared__ double sh1[32][33];
     __shared__ double sh2[32][33];
     __shared__ int last;
@@ -183,6 +186,7 @@ bn_finalize_kernel(const float* __restrict__ part_sum, const float* __restrict__
 __global__ void bn_eval_kernel(int C, int Cp, const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ rm, const float* __restrict__ rv, float eps,
                                float* __restrict__ scale, float* __restrict__ shift) {
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= Cp) return;
     if (c < C) {
@@ -226,6 +230,7 @@ bn_apply_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ s
                 const __nv_bfloat16* __restrict__ y2, const float* __restrict__ scale2,
                 const float* __restrict__ shift2, const __nv_bfloat16* __restrict__ res,
                 __nv_bfloat16* __restrict__ out, long long rows, int Cp, int R, int relu) {
+    pdl_wait();
     const int V = Cp >> 3;
     const int vl = threadIdx.x % V;
     const int rl = threadIdx.x / V;
@@ -289,6 +294,7 @@ bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* _
                      const float* __restrict__ mask_scale, const float* __restrict__ mask_shift,
                      const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ y2, long long rows, int Cp,
                      int R, float* __restrict__ partial) {
+    pdl_wait();
     extern __shared__ float sm[];  // [R][4][Cp] reduction scratch
     const int V = Cp >> 3;
     const int vl = threadIdx.x % V;
@@ -375,6 +381,7 @@ bn_bwd_final_kernel(const float* __restrict__ partial, int nblocks, int nq, int 
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ mean2,
                     const float* __restrict__ invstd2, float* __restrict__ sums, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, float* __restrict__ dgamma2, float* __restrict__ dbeta2) {
+    pdl_wait();
     // 8 channels (one 32-byte sector per partial row) x 128 row lanes per block: Cp/8 blocks instead of Cp/32, and a
     // thread's loads (<= 10 rows x nq quantities for the 1184-row partials of bn_bwd_reduce) are all independent, so the
     // kernel is one memory round trip plus a shared-memory tree -- it sits on the dependent chain 34 times per step.
@@ -458,6 +465,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __
                     const float* __restrict__ invstd2, const float* __restrict__ gamma2,
                     const float* __restrict__ sums, __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dy2,
                     __nv_bfloat16* __restrict__ dz, long long rows, int C, int Cp, int R, float inv_count) {
+    pdl_wait();
     const int V = Cp >> 3;
     const int vl = threadIdx.x % V;
     const int rl = threadIdx.x / V;
@@ -545,6 +553,7 @@ bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                    uint8_t* __restrict__ argmax, int N, int T, int H, int W, int Cp, int kt, int kh,
                                    int kw, int pt, int ph, int pw, int To, int Ho, int Wo) {
+    pdl_wait();
     const int V = Cp >> 3;
     const long long total = (long long)N * To * Ho * Wo * V;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -610,6 +619,7 @@ __device__ __forceinline__ void block_channel_sums(const float (&acc)[8], int V,
 __global__ void __launch_bounds__(256)
 relu_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ out,
                 __nv_bfloat16* __restrict__ dz, long long nvec, int V, int Cp, float* __restrict__ partial) {
+    pdl_wait();
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -631,6 +641,7 @@ relu_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __rest
 // per-block column sums of a bf16 [rows][Cp] tensor -> partial[block][Cp] (fp32); block = V groups x R row lanes
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int Cp, int R, float* __restrict__ partial) {
+    pdl_wait();
     extern __shared__ float sm[];  // [R][Cp]
     const int V = Cp >> 3;
     const int vl = threadIdx.x % V, rl = threadIdx.x / V;
@@ -658,6 +669,7 @@ colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C
 
 __global__ void __launch_bounds__(1024)
 colsum_final_kernel(const float* __restrict__ partial, int nblocks, int C, int Cp, float* __restrict__ out) {
+    pdl_wait();
     __shared__ double sh[32][33];
     const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cl;
@@ -678,6 +690,7 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restri
                    const __nv_bfloat16* __restrict__ pooled, __nv_bfloat16* __restrict__ dx, int N, int T, int H, int W,
                    int Cp, int kt, int kh, int kw, int pt, int ph, int pw, int To, int Ho, int Wo,
                    float* __restrict__ partial) {
+    pdl_wait();
     // one thread per input vector: windows do not overlap (kernel == stride), so each input element belongs to
     // exactly one window and the gradient is a gather.
     // pooled (optional) = the pooling OUTPUT when its input was a ReLU output: the selected element is that value, so
@@ -770,7 +783,7 @@ extern "C" int zsv_repack_input(const float* x, void* out, int N, int C, int T, 
         return fail(ZSV_ERR_BAD_ARG, "repack_input: unknown layout %d", layout);
     }
     const long long total = (long long)N * T * H * Wp * (Cp >> 3);
-    ncdhw_to_ndhwc_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, N, C, T, H,
+    zsv::launch(ncdhw_to_ndhwc_kernel, ew_blocks(total, 256), 256, 0, (cudaStream_t)stream, x, (__nv_bfloat16*)out, N, C, T, H,
                                                                                    W, Cp, Wp, wl);
     ZSV_LAUNCH_CHECK("ncdhw_to_ndhwc_kernel");
     return ZSV_OK;
@@ -784,7 +797,7 @@ extern "C" int zsv_ndhwc_to_ncdhw(const void* x, float* out, int N, int C, int T
     if (!x || !out) return fail(ZSV_ERR_BAD_ARG, "ndhwc_to_ncdhw: null pointer");
     const int Cp = cpad(C);
     const long long total = (long long)N * T * H * W * (Cp >> 3);
-    ndhwc_to_ncdhw_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, N, C,
+    zsv::launch(ndhwc_to_ncdhw_kernel, ew_blocks(total, 256), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, out, N, C,
                                                                                    T, H, W, Cp);
     ZSV_LAUNCH_CHECK("ndhwc_to_ncdhw_kernel");
     return ZSV_OK;
@@ -818,8 +831,7 @@ extern "C" int zsv_bn_finalize(const float* part_sum, const float* part_sq, int 
     if (ceil_div(Cp, 32) * sizeof(unsigned int) > kTicketBytes) return fail(ZSV_ERR_UNSUPPORTED, "bn_finalize: too many channels");
     unsigned int* tickets = (unsigned int*)workspace;
     double* chunk = (double*)((char*)workspace + kTicketBytes);
-    bn_finalize_kernel<<<dim3(ceil_div(Cp, 32), nchunks), 1024, 0, st>>>(
-        part_sum, part_sq, part_rows, C, Cp, rows_per_chunk, chunk, tickets, (double)count, gamma, beta, running_mean,
+    zsv::launch(bn_finalize_kernel, dim3(ceil_div(Cp, 32), nchunks), 1024, 0, st, part_sum, part_sq, part_rows, C, Cp, rows_per_chunk, chunk, tickets, (double)count, gamma, beta, running_mean,
         running_var, momentum, eps, scale, shift, mean, invstd, (float4*)bwd_table);
     ZSV_LAUNCH_CHECK("bn_finalize_kernel");
     return ZSV_OK;
@@ -829,7 +841,7 @@ extern "C" int zsv_bn_eval_scale_shift(int C, const float* gamma, const float* b
                                        const float* running_var, float eps, float* scale, float* shift, void* stream) {
     if (!running_mean || !running_var || !scale || !shift) return fail(ZSV_ERR_BAD_ARG, "bn_eval: null pointer");
     const int Cp = cpad(C);
-    bn_eval_kernel<<<ceil_div(Cp, 128), 128, 0, (cudaStream_t)stream>>>(C, Cp, gamma, beta, running_mean, running_var,
+    zsv::launch(bn_eval_kernel, ceil_div(Cp, 128), 128, 0, (cudaStream_t)stream, C, Cp, gamma, beta, running_mean, running_var,
                                                                         eps, scale, shift);
     ZSV_LAUNCH_CHECK("bn_eval_kernel");
     return ZSV_OK;
@@ -853,13 +865,13 @@ extern "C" int zsv_bn_apply(const void* y, const float* scale, const float* shif
     const __nv_bfloat16* rb = (const __nv_bfloat16*)residual;
     __nv_bfloat16* ob = (__nv_bfloat16*)out;
     if (y2 && residual)
-        bn_apply_kernel<true, true><<<resident_grid(bn_apply_kernel<true, true>, 256, 0, work, 1 << 20), 256, 0, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, rows, Cp, R, relu);
+        zsv::launch(bn_apply_kernel<true, true>, resident_grid(bn_apply_kernel<true, true>, 256, 0, work, 1 << 20), 256, 0, st, yb, scale, shift, y2b, scale2, shift2, rb, ob, rows, Cp, R, relu);
     else if (y2)
-        bn_apply_kernel<true, false><<<resident_grid(bn_apply_kernel<true, false>, 256, 0, work, 1 << 20), 256, 0, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, rows, Cp, R, relu);
+        zsv::launch(bn_apply_kernel<true, false>, resident_grid(bn_apply_kernel<true, false>, 256, 0, work, 1 << 20), 256, 0, st, yb, scale, shift, y2b, scale2, shift2, rb, ob, rows, Cp, R, relu);
     else if (residual)
-        bn_apply_kernel<false, true><<<resident_grid(bn_apply_kernel<false, true>, 256, 0, work, 1 << 20), 256, 0, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, rows, Cp, R, relu);
+        zsv::launch(bn_apply_kernel<false, true>, resident_grid(bn_apply_kernel<false, true>, 256, 0, work, 1 << 20), 256, 0, st, yb, scale, shift, y2b, scale2, shift2, rb, ob, rows, Cp, R, relu);
     else
-        bn_apply_kernel<false, false><<<resident_grid(bn_apply_kernel<false, false>, 256, 0, work, 1 << 20), 256, 0, st>>>(yb, scale, shift, y2b, scale2, shift2, rb, ob, rows, Cp, R, relu);
+        zsv::launch(bn_apply_kernel<false, false>, resident_grid(bn_apply_kernel<false, false>, 256, 0, work, 1 << 20), 256, 0, st, yb, scale, shift, y2b, scale2, shift2, rb, ob, rows, Cp, R, relu);
     ZSV_LAUNCH_CHECK("bn_apply_kernel");
     return ZSV_OK;
 }
@@ -904,21 +916,21 @@ extern "C" int zsv_bn_bwd(const void* g, const void* out, int relu, const float*
     const int nblocks = y2 ? resident_grid(bn_bwd_reduce_kernel<true>, 256, smem_r, work_r, kBwdMaxBlocks)
                            : resident_grid(bn_bwd_reduce_kernel<false>, 256, smem_r, work_r, kBwdMaxBlocks);
     if (y2)
-        bn_bwd_reduce_kernel<true><<<nblocks, 256, smem_r, st>>>(gb, ob, relu, mask_scale, mask_shift, yb, y2b, rows, Cp, R, partial);
+        zsv::launch(bn_bwd_reduce_kernel<true>, nblocks, 256, smem_r, st, gb, ob, relu, mask_scale, mask_shift, yb, y2b, rows, Cp, R, partial);
     else
-        bn_bwd_reduce_kernel<false><<<nblocks, 256, smem_r, st>>>(gb, ob, relu, mask_scale, mask_shift, yb, y2b, rows, Cp, R, partial);
+        zsv::launch(bn_bwd_reduce_kernel<false>, nblocks, 256, smem_r, st, gb, ob, relu, mask_scale, mask_shift, yb, y2b, rows, Cp, R, partial);
     ZSV_LAUNCH_CHECK("bn_bwd_reduce_kernel");
     const int nq = y2 ? 4 : 2;
-    bn_bwd_final_kernel<<<ceil_div(Cp, 8), 1024, 0, st>>>(partial, nblocks, nq, C, Cp, 1, mean, invstd, mean2, invstd2, sums, dgamma, dbeta, dgamma2, dbeta2);
+    zsv::launch(bn_bwd_final_kernel, ceil_div(Cp, 8), 1024, 0, st, partial, nblocks, nq, C, Cp, 1, mean, invstd, mean2, invstd2, sums, dgamma, dbeta, dgamma2, dbeta2);
     ZSV_LAUNCH_CHECK("bn_bwd_final_kernel");
     const long long work_a = ceil_div_ll(rows, (long long)R * 2);
     const int blocks = y2 ? resident_grid(bn_bwd_apply_kernel<true>, 256, 0, work_a, 1 << 20)
                           : resident_grid(bn_bwd_apply_kernel<false>, 256, 0, work_a, 1 << 20);
     const float inv_count = (float)(1.0 / (double)rows);
     if (y2)
-        bn_bwd_apply_kernel<true><<<blocks, 256, 0, st>>>(gb, ob, relu, mask_scale, mask_shift, yb, mean, invstd, gamma, y2b, mean2, invstd2, gamma2, sums, (__nv_bfloat16*)dy, (__nv_bfloat16*)dy2, (__nv_bfloat16*)dz, rows, C, Cp, R, inv_count);
+        zsv::launch(bn_bwd_apply_kernel<true>, blocks, 256, 0, st, gb, ob, relu, mask_scale, mask_shift, yb, mean, invstd, gamma, y2b, mean2, invstd2, gamma2, sums, (__nv_bfloat16*)dy, (__nv_bfloat16*)dy2, (__nv_bfloat16*)dz, rows, C, Cp, R, inv_count);
     else
-        bn_bwd_apply_kernel<false><<<blocks, 256, 0, st>>>(gb, ob, relu, mask_scale, mask_shift, yb, mean, invstd, gamma, y2b, mean2, invstd2, gamma2, sums, (__nv_bfloat16*)dy, (__nv_bfloat16*)dy2, (__nv_bfloat16*)dz, rows, C, Cp, R, inv_count);
+        zsv::launch(bn_bwd_apply_kernel<false>, blocks, 256, 0, st, gb, ob, relu, mask_scale, mask_shift, yb, mean, invstd, gamma, y2b, mean2, invstd2, gamma2, sums, (__nv_bfloat16*)dy, (__nv_bfloat16*)dy2, (__nv_bfloat16*)dz, rows, C, Cp, R, inv_count);
     ZSV_LAUNCH_CHECK("bn_bwd_apply_kernel");
     return ZSV_OK;
 }
@@ -936,7 +948,7 @@ extern "C" int zsv_bn_bwd_finish(const void* dz, const void* y, const float* mea
     cudaStream_t st = (cudaStream_t)stream;
     float* sums = (float*)workspace;
     // the convolution epilogue leaves (sum dz, sum dz*y) against the RAW pre-activation; converted to sum dz*xhat in fp64
-    bn_bwd_final_kernel<<<ceil_div(Cp, 8), 1024, 0, st>>>(partial, partial_rows, 2, C, Cp, 1, mean, invstd, nullptr, nullptr,
+    zsv::launch(bn_bwd_final_kernel, ceil_div(Cp, 8), 1024, 0, st, partial, partial_rows, 2, C, Cp, 1, mean, invstd, nullptr, nullptr,
                                                           sums, dgamma, dbeta, nullptr, nullptr);
     ZSV_LAUNCH_CHECK("bn_bwd_final_kernel");
     const int V = Cp >> 3;
@@ -944,8 +956,7 @@ extern "C" int zsv_bn_bwd_finish(const void* dz, const void* y, const float* mea
     const int R = std::max(1, 256 / V);
     const int blocks = resident_grid(bn_bwd_apply_kernel<false>, 256, 0, ceil_div_ll(rows, (long long)R * 2), 1 << 20);
     const float inv_count = (float)(1.0 / (double)rows);
-    bn_bwd_apply_kernel<false><<<blocks, 256, 0, st>>>(
-        (const __nv_bfloat16*)dz, nullptr, 0, nullptr, nullptr, (const __nv_bfloat16*)y, mean, invstd, gamma, nullptr,
+    zsv::launch(bn_bwd_apply_kernel<false>, blocks, 256, 0, st, (const __nv_bfloat16*)dz, nullptr, 0, nullptr, nullptr, (const __nv_bfloat16*)y, mean, invstd, gamma, nullptr,
         nullptr, nullptr, nullptr, sums, (__nv_bfloat16*)dy, nullptr, nullptr, rows, C, Cp, R, inv_count);
     ZSV_LAUNCH_CHECK("bn_bwd_apply_kernel");
     return ZSV_OK;
@@ -959,8 +970,7 @@ extern "C" int zsv_maxpool3d_fwd(const void* x, void* y, uint8_t* argmax, int N,
     if (To < 1 || Ho < 1 || Wo < 1) return fail(ZSV_ERR_BAD_ARG, "maxpool_fwd: empty output");
     if (kt * kh * kw > 255) return fail(ZSV_ERR_UNSUPPORTED, "maxpool_fwd: window larger than 255 positions");
     const long long total = (long long)N * To * Ho * Wo * (Cp >> 3);
-    maxpool_fwd_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, (__nv_bfloat16*)y, argmax, N, T, H, W, Cp, kt, kh, kw, pt, ph, pw, To, Ho, Wo);
+    zsv::launch(maxpool_fwd_kernel, ew_blocks(total, 256), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, argmax, N, T, H, W, Cp, kt, kh, kw, pt, ph, pw, To, Ho, Wo);
     ZSV_LAUNCH_CHECK("maxpool_fwd_kernel");
     return ZSV_OK;
 }
@@ -973,7 +983,7 @@ static int bias_fused_grid(long long work_items, int V) {
 }
 
 static int bias_fused_finish(const float* partial, int nblocks, int C, float* db, cudaStream_t st) {
-    colsum_final_kernel<<<ceil_div(cpad(C), 32), 1024, 0, st>>>(partial, nblocks, C, cpad(C), db);
+    zsv::launch(colsum_final_kernel, ceil_div(cpad(C), 32), 1024, 0, st, partial, nblocks, C, cpad(C), db);
     ZSV_LAUNCH_CHECK("colsum_final_kernel");
     return ZSV_OK;
 }
@@ -985,7 +995,7 @@ extern "C" int zsv_relu_bwd(const void* g, const void* out, void* dz, long long 
     const long long nvec = rows * V;
     cudaStream_t st = (cudaStream_t)stream;
     if (bias_grad == nullptr) {
-        relu_bwd_kernel<<<ew_blocks(nvec, 1024), 256, 0, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)out,
+        zsv::launch(relu_bwd_kernel, ew_blocks(nvec, 1024), 256, 0, st, (const __nv_bfloat16*)g, (const __nv_bfloat16*)out,
                                                               (__nv_bfloat16*)dz, nvec, V, Cp, nullptr);
         ZSV_LAUNCH_CHECK("relu_bwd_kernel");
         return ZSV_OK;
@@ -993,7 +1003,7 @@ extern "C" int zsv_relu_bwd(const void* g, const void* out, void* dz, long long 
     if (!workspace || workspace_bytes < zsv_bias_grad_workspace(C)) return fail(ZSV_ERR_WORKSPACE, "relu_bwd: workspace too small");
     if ((256 % V) != 0 && V > 256) return fail(ZSV_ERR_UNSUPPORTED, "relu_bwd: channel pitch too large for the fused bias gradient");
     const int blocks = bias_fused_grid(nvec, V);
-    relu_bwd_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)out, (__nv_bfloat16*)dz, nvec, V,
+    zsv::launch(relu_bwd_kernel, blocks, 256, 0, st, (const __nv_bfloat16*)g, (const __nv_bfloat16*)out, (__nv_bfloat16*)dz, nvec, V,
                                             Cp, (float*)workspace);
     ZSV_LAUNCH_CHECK("relu_bwd_kernel");
     return bias_fused_finish((const float*)workspace, blocks, C, bias_grad, st);
@@ -1010,10 +1020,10 @@ extern "C" int zsv_bias_grad(const void* dy, float* db, long long rows, int C, v
     const int R = std::max(1, 256 / V);
     const int nblocks = (int)std::max<long long>(1, std::min<long long>(kBwdMaxBlocks, ceil_div_ll(rows, (long long)R * 4)));
     cudaStream_t st = (cudaStream_t)stream;
-    colsum_partial_kernel<<<nblocks, 256, (size_t)R * Cp * sizeof(float), st>>>((const __nv_bfloat16*)dy, rows, Cp, R,
+    zsv::launch(colsum_partial_kernel, nblocks, 256, (size_t)R * Cp * sizeof(float), st, (const __nv_bfloat16*)dy, rows, Cp, R,
                                                                                  (float*)workspace);
     ZSV_LAUNCH_CHECK("colsum_partial_kernel");
-    colsum_final_kernel<<<ceil_div(Cp, 32), 1024, 0, st>>>((const float*)workspace, nblocks, C, Cp, db);
+    zsv::launch(colsum_final_kernel, ceil_div(Cp, 32), 1024, 0, st, (const float*)workspace, nblocks, C, Cp, db);
     ZSV_LAUNCH_CHECK("colsum_final_kernel");
     return ZSV_OK;
 }
@@ -1034,7 +1044,7 @@ extern "C" int zsv_maxpool3d_bwd(const void* dy, const uint8_t* argmax, const vo
         blocks = bias_fused_grid(total, V);
         partial = (float*)workspace;
     }
-    maxpool_bwd_kernel<<<blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, argmax, (const __nv_bfloat16*)relu_pooled,
+    zsv::launch(maxpool_bwd_kernel, blocks, 256, 0, st, (const __nv_bfloat16*)dy, argmax, (const __nv_bfloat16*)relu_pooled,
                                                (__nv_bfloat16*)dx, N, T, H, W, Cp, kt, kh, kw, pt, ph, pw, To, Ho, Wo, partial);
     ZSV_LAUNCH_CHECK("maxpool_bwd_kernel");
     if (bias_grad != nullptr) return bias_fused_finish(partial, blocks, C, bias_grad, st);
@@ -1055,6 +1065,7 @@ namespace {
 __global__ void clip_transform_kernel(const uint8_t* __restrict__ frames, __nv_bfloat16* __restrict__ out, int N, int T,
                                       int Hs, int Ws, int Hr, int Wr, float rscale, int crop, int Wp, int wl,
                                       const int32_t* __restrict__ crop_ij, const uint8_t* __restrict__ flip) {
+    pdl_wait();
     const long long total = (long long)N * T * crop * Wp;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -1108,8 +1119,7 @@ extern "C" int zsv_clip_transform(const uint8_t* frames, void* out, int N, int T
     const float rscale = (float)(1.0 / scale);
     const int Wp = crop + 8;
     const long long total = (long long)N * T * crop * Wp;
-    zsv::clip_transform_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        frames, (__nv_bfloat16*)out, N, T, Hs, Ws, Hr, Wr, rscale, crop, Wp, wpad_left, crop_ij, flip);
+    zsv::launch(zsv::clip_transform_kernel, ew_blocks(total, 256), 256, 0, (cudaStream_t)stream, frames, (__nv_bfloat16*)out, N, T, Hs, Ws, Hr, Wr, rscale, crop, Wp, wpad_left, crop_ij, flip);
     ZSV_LAUNCH_CHECK("clip_transform_kernel");
     return ZSV_OK;
 }

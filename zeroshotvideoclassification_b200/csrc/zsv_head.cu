@@ -26,6 +26,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // pooled[b][c] = mean_p feat[b][p][c]
 __global__ void pool_kernel(const __nv_bfloat16* __restrict__ feat, float* __restrict__ pooled, int B, int P, int C,
                             int Cp) {
+    pdl_wait();
     const int b = blockIdx.y;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -37,6 +38,7 @@ __global__ void pool_kernel(const __nv_bfloat16* __restrict__ feat, float* __res
 // emb[b] = o[b] / max(||o[b]||, eps); one warp per row
 __global__ void normalize_fwd_kernel(const float* __restrict__ o, float* __restrict__ emb, float* __restrict__ onorm,
                                      int B, int E, float eps) {
+    pdl_wait();
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (b >= B) return;
@@ -56,6 +58,7 @@ __global__ void normalize_fwd_kernel(const float* __restrict__ o, float* __restr
 __global__ void normalize_bwd_kernel(const float* __restrict__ demb, const float* __restrict__ emb,
                                      const float* __restrict__ onorm, float* __restrict__ dout, int B, int E,
                                      float eps) {
+    pdl_wait();
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (b >= B) return;
@@ -72,6 +75,7 @@ __global__ void normalize_bwd_kernel(const float* __restrict__ demb, const float
 // dfeat[b][p][c] = dpooled[b][c] / P
 __global__ void pool_bwd_kernel(const float* __restrict__ dpooled, __nv_bfloat16* __restrict__ dfeat, int B, int P,
                                 int C, int Cp) {
+    pdl_wait();
     const long long total = (long long)B * P * Cp;
     const float invP = 1.f / (float)P;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -85,6 +89,7 @@ __global__ void pool_bwd_kernel(const float* __restrict__ dpooled, __nv_bfloat16
 // loss = mean((emb-target)^2) ; demb = 2*(emb-target)/(B*E)*grad_scale ; single block (B*E is tiny)
 __global__ void mse_kernel(const float* __restrict__ emb, const float* __restrict__ target, int n, float grad_scale,
                            float* __restrict__ loss, float* __restrict__ demb) {
+    pdl_wait();
     __shared__ float sh[32];
     float acc = 0.f;
     const float k = 2.f * grad_scale / (float)n;
@@ -181,6 +186,7 @@ template <int R, int G, int TC, bool CL>
 __global__ void __launch_bounds__(64 * G * TC, CL ? 1 : 384 / (64 * G * TC))
 nearest_kernel(const float* __restrict__ emb, const float* __restrict__ cls, int N, int C, int D, int k,
                int64_t* __restrict__ idx_out, double* __restrict__ dist_out, int vec, int ncta) {
+    pdl_wait();
     constexpr int NT = 64 * G * TC;      // threads
     constexpr int RB = G * R;            // rows per block
     constexpr int CS = TC * kCT;         // class slots per pass
@@ -436,14 +442,14 @@ extern "C" int zsv_head_fwd(const void* feat, int B, int P, int C, const float* 
     if (!feat || !w1 || !w2 || !pooled || !hidden || !onorm || !emb) return fail(ZSV_ERR_BAD_ARG, "head_fwd: null pointer");
     if (B < 1 || P < 1 || C < 1 || Hd < 1 || E < 1) return fail(ZSV_ERR_BAD_ARG, "head_fwd: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
-    pool_kernel<<<dim3(ceil_div(C, 128), B), 128, 0, st>>>((const __nv_bfloat16*)feat, pooled, B, P, C, cpad(C));
+    zsv::launch(pool_kernel, dim3(ceil_div(C, 128), B), 128, 0, st, (const __nv_bfloat16*)feat, pooled, B, P, C, cpad(C));
     ZSV_LAUNCH_CHECK("pool_kernel");
     int rc = linear_forward(pooled, w1, b1, hidden, B, C, Hd, 1, nullptr, 0, st);
     if (rc) return rc;
     // raw projection goes to emb, then normalised in place
     rc = linear_forward(hidden, w2, b2, emb, B, Hd, E, 0, nullptr, 0, st);
     if (rc) return rc;
-    normalize_fwd_kernel<<<ceil_div(B * 32, 128), 128, 0, st>>>(emb, emb, onorm, B, E, eps);
+    zsv::launch(normalize_fwd_kernel, ceil_div(B * 32, 128), 128, 0, st, emb, emb, onorm, B, E, eps);
     ZSV_LAUNCH_CHECK("normalize_fwd_kernel");
     return ZSV_OK;
 }
@@ -469,7 +475,7 @@ extern "C" int zsv_head_bwd(const float* demb, const float* emb, const float* on
     float* dpooled = dh + (size_t)B * Hd;
     float* ws = dpooled + (size_t)B * C;
     const size_t ws_bytes = scratch_bytes - sizeof(float) * (size_t)B * ((size_t)E + Hd + C);
-    normalize_bwd_kernel<<<ceil_div(B * 32, 128), 128, 0, st>>>(demb, emb, onorm, dout, B, E, eps);
+    zsv::launch(normalize_bwd_kernel, ceil_div(B * 32, 128), 128, 0, st, demb, emb, onorm, dout, B, E, eps);
     ZSV_LAUNCH_CHECK("normalize_bwd_kernel");
     int rc;
     if (dw2) {
@@ -486,8 +492,7 @@ extern "C" int zsv_head_bwd(const float* demb, const float* emb, const float* on
         rc = linear_dgrad(dh, w1, nullptr, dpooled, B, C, Hd, ws, ws_bytes, st);
         if (rc) return rc;
         const long long total = (long long)B * P * cpad(C);
-        pool_bwd_kernel<<<(int)std::min<long long>(ceil_div_ll(total, 256), 148 * 8), 256, 0, st>>>(
-            dpooled, (__nv_bfloat16*)dfeat, B, P, C, cpad(C));
+        zsv::launch(pool_bwd_kernel, (int)std::min<long long>(ceil_div_ll(total, 256), 148 * 8), 256, 0, st, dpooled, (__nv_bfloat16*)dfeat, B, P, C, cpad(C));
         ZSV_LAUNCH_CHECK("pool_bwd_kernel");
     }
     return ZSV_OK;
@@ -495,7 +500,7 @@ extern "C" int zsv_head_bwd(const float* demb, const float* emb, const float* on
 
 extern "C" int zsv_l2norm_fwd(const float* o, float* emb, float* onorm, int B, int E, float eps, void* stream) {
     if (!o || !emb || !onorm) return fail(ZSV_ERR_BAD_ARG, "l2norm_fwd: null pointer");
-    normalize_fwd_kernel<<<ceil_div(B * 32, 128), 128, 0, (cudaStream_t)stream>>>(o, emb, onorm, B, E, eps);
+    zsv::launch(normalize_fwd_kernel, ceil_div(B * 32, 128), 128, 0, (cudaStream_t)stream, o, emb, onorm, B, E, eps);
     ZSV_LAUNCH_CHECK("normalize_fwd_kernel");
     return ZSV_OK;
 }
@@ -503,7 +508,7 @@ extern "C" int zsv_l2norm_fwd(const float* o, float* emb, float* onorm, int B, i
 extern "C" int zsv_l2norm_bwd(const float* demb, const float* emb, const float* onorm, float* dout, int B, int E,
                               float eps, void* stream) {
     if (!demb || !emb || !onorm || !dout) return fail(ZSV_ERR_BAD_ARG, "l2norm_bwd: null pointer");
-    normalize_bwd_kernel<<<ceil_div(B * 32, 128), 128, 0, (cudaStream_t)stream>>>(demb, emb, onorm, dout, B, E, eps);
+    zsv::launch(normalize_bwd_kernel, ceil_div(B * 32, 128), 128, 0, (cudaStream_t)stream, demb, emb, onorm, dout, B, E, eps);
     ZSV_LAUNCH_CHECK("normalize_bwd_kernel");
     return ZSV_OK;
 }
@@ -511,7 +516,7 @@ extern "C" int zsv_l2norm_bwd(const float* demb, const float* emb, const float* 
 extern "C" int zsv_mse_fwd_bwd(const float* emb, const float* target, int B, int E, float grad_scale, float* loss,
                                float* demb, void* stream) {
     if (!emb || !target) return fail(ZSV_ERR_BAD_ARG, "mse: null pointer");
-    mse_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(emb, target, B * E, grad_scale, loss, demb);
+    zsv::launch(mse_kernel, 1, 1024, 0, (cudaStream_t)stream, emb, target, B * E, grad_scale, loss, demb);
     ZSV_LAUNCH_CHECK("mse_kernel");
     return ZSV_OK;
 }
@@ -553,9 +558,9 @@ extern "C" int zsv_nearest_class(const float* emb, const float* cls, int N, int 
     if (G) {
         const size_t smem = smem_of(8 * G, false);
         if (G == 3)
-            nearest_kernel<8, 3, 1, false><<<ceil_div(N, 24), 192, smem, st>>>(emb, cls, N, C, D, k, idx_out, dist_out, vec, 1);
+            zsv::launch(nearest_kernel<8, 3, 1, false>, ceil_div(N, 24), 192, smem, st, emb, cls, N, C, D, k, idx_out, dist_out, vec, 1);
         else
-            nearest_kernel<8, 2, 1, false><<<ceil_div(N, 16), 128, smem, st>>>(emb, cls, N, C, D, k, idx_out, dist_out, vec, 1);
+            zsv::launch(nearest_kernel<8, 2, 1, false>, ceil_div(N, 16), 128, smem, st, emb, cls, N, C, D, k, idx_out, dist_out, vec, 1);
     } else {
         const int g = smem_of(24, true) <= 200 * 1024 ? 3 : 1;
         const size_t smem = smem_of(8 * g, true);
@@ -565,10 +570,11 @@ extern "C" int zsv_nearest_class(const float* emb, const float* cls, int N, int 
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(ncta * ceil_div(N, 8 * g)), cfg.blockDim = dim3(64 * g), cfg.dynamicSmemBytes = smem, cfg.stream = st;
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeClusterDimension;
-        attr.val.clusterDim.x = ncta, attr.val.clusterDim.y = 1, attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr, cfg.numAttrs = 1;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = ncta, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+        pdl_attribute(&attr[1]);
+        cfg.attrs = attr, cfg.numAttrs = 2;
         cudaError_t e = g == 3 ? cudaLaunchKernelEx(&cfg, nearest_kernel<8, 3, 1, true>, emb, cls, N, C, D, k, idx_out, dist_out, vec, ncta)
                                : cudaLaunchKernelEx(&cfg, nearest_kernel<8, 1, 1, true>, emb, cls, N, C, D, k, idx_out, dist_out, vec, ncta);
         if (e != cudaSuccess) return fail(ZSV_ERR_CUDA, "launch of nearest_kernel (cluster) failed: %s", cudaGetErrorString(e));

@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
+
+#include <utility>
 
 #include "../../include/zsv_b200.h"
 
@@ -20,6 +23,26 @@ int sm_count();
 
 // Count one kernel launch issued by this library (read back through zsv_launch_count()).
 void count_launch();
+
+// Programmatic dependent launch (ZSV_PDL=0 turns it off).  Every kernel of this library is launched with the
+// programmatic-stream-serialization attribute and executes griddepcontrol.wait before it touches global memory, so a
+// grid is set up and scheduled while the previous kernel of its stream drains (inside a captured CUDA graph the edge
+// becomes a programmatic dependency) and results do not change.
+bool pdl_allowed();
+inline void pdl_attribute(cudaLaunchAttribute* a) {
+    a->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    a->val.programmaticStreamSerializationAllowed = pdl_allowed() ? 1 : 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr;
+    pdl_attribute(&attr);
+    cfg.attrs = &attr, cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(std::forward<Args>(args))...);
+}
 
 // fp32 Linear layers with few batch rows (zsv_linear.cu); shared by the C3D entry points and the embedding head.
 // ws may be NULL for linear_forward (the reduction is then not split over blocks).

@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include "zsv_internal.h"
+#include "zsv_ptx.cuh"
 
 namespace zsv {
 namespace {
@@ -41,6 +42,7 @@ template <bool kVec>
 __global__ void __launch_bounds__(256)
 linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                   float* __restrict__ out, float* __restrict__ partial, int B, int K, int J, int relu, int k_per_split) {
+    pdl_wait();
     extern __shared__ float xs[];                       // [kBT][kKC + 4]
     constexpr int kPitch = kKC + 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -123,6 +125,7 @@ linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
 // out[b][j] = act(sum_s partial[s][b][j] + bias[j])   (fixed order: deterministic)
 __global__ void linear_fwd_finish_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
                                          float* __restrict__ out, int splits, long long n, int J, int relu) {
+    pdl_wait();
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     float s = 0.f;
@@ -137,6 +140,7 @@ template <bool kVec>
 __global__ void __launch_bounds__(256)
 linear_dgrad_kernel(const float* __restrict__ g, const float* __restrict__ w, float* __restrict__ dst, int B, int K, int J,
                     int j_per_split) {
+    pdl_wait();
     __shared__ __align__(16) float gs[kDgJ][kBT];       // g[b][j] transposed: one 16-byte broadcast load = 4 batch rows
     const int k = blockIdx.x * kDgK + threadIdx.x * 4;
     const int b0 = blockIdx.z * kBT;
@@ -201,6 +205,7 @@ linear_dgrad_kernel(const float* __restrict__ g, const float* __restrict__ w, fl
 // dx[i] = (sum_s partial[s][i]) * (act ? [act[i] > 0] : 1)
 __global__ void linear_dgrad_finish_kernel(const float* __restrict__ partial, const float* __restrict__ act,
                                            float* __restrict__ dx, int splits, long long n) {
+    pdl_wait();
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     float s = 0.f;
@@ -213,6 +218,7 @@ template <bool kVec>
 __global__ void __launch_bounds__(256)
 linear_wgrad_kernel(const float* __restrict__ g, const float* __restrict__ x, float* __restrict__ dw,
                     float* __restrict__ db, int B, int K, int J, int jt) {
+    pdl_wait();
     extern __shared__ float gsm[];                      // [jt][kBT] per batch pass
     const int k = blockIdx.x * kDgK + threadIdx.x * 4;
     const int j0 = blockIdx.y * jt;
@@ -292,6 +298,7 @@ linear_wgrad_kernel(const float* __restrict__ g, const float* __restrict__ x, fl
 __global__ void linear_fwd_small_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                         const float* __restrict__ bias, float* __restrict__ out, int B, int K, int J,
                                         int relu) {
+    pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= J) return;
@@ -323,6 +330,7 @@ __global__ void linear_fwd_small_kernel(const float* __restrict__ x, const float
 __global__ void __launch_bounds__(256)
 linear_dgrad_small_kernel(const float* __restrict__ g, const float* __restrict__ w, const float* __restrict__ act,
                           float* __restrict__ dx, int B, int K, int J) {
+    pdl_wait();
     __shared__ float red[8][8][33];
     const int kl = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const int k = blockIdx.x * 32 + kl;
@@ -354,6 +362,7 @@ linear_dgrad_small_kernel(const float* __restrict__ g, const float* __restrict__
 
 __global__ void relu_mask_kernel(const float* __restrict__ dy, const float* __restrict__ act, float* __restrict__ out,
                                  long long n) {
+    pdl_wait();
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) out[i] = act[i] > 0.f ? dy[i] : 0.f;
 }
@@ -380,7 +389,7 @@ size_t linear_workspace_bytes(int B, int K, int J) {
 int linear_forward(const float* x, const float* w, const float* bias, float* out, int B, int K, int J, int relu,
                    float* ws, size_t ws_bytes, cudaStream_t st) {
     if ((long long)K * J <= kSmallMatrix) {
-        linear_fwd_small_kernel<<<dim3(ceil_div(J * 32, 256), ceil_div(B, 8)), 256, 0, st>>>(x, w, bias, out, B, K, J, relu);
+        zsv::launch(linear_fwd_small_kernel, dim3(ceil_div(J * 32, 256), ceil_div(B, 8)), 256, 0, st, x, w, bias, out, B, K, J, relu);
         ZSV_LAUNCH_CHECK("linear_fwd_small_kernel");
         return ZSV_OK;
     }
@@ -401,13 +410,13 @@ int linear_forward(const float* x, const float* w, const float* bias, float* out
     const dim3 grid(ceil_div(J, kFwdRows), nsplit, ceil_div(B, kBT));
     float* partial = nsplit > 1 ? ws : nullptr;
     if (vec_ok(x, K) && vec_ok(w, K))
-        linear_fwd_kernel<true><<<grid, 256, smem, st>>>(x, w, bias, out, partial, B, K, J, relu, kps);
+        zsv::launch(linear_fwd_kernel<true>, grid, 256, smem, st, x, w, bias, out, partial, B, K, J, relu, kps);
     else
-        linear_fwd_kernel<false><<<grid, 256, smem, st>>>(x, w, bias, out, partial, B, K, J, relu, kps);
+        zsv::launch(linear_fwd_kernel<false>, grid, 256, smem, st, x, w, bias, out, partial, B, K, J, relu, kps);
     ZSV_LAUNCH_CHECK("linear_fwd_kernel");
     if (nsplit > 1) {
         const long long n = (long long)B * J;
-        linear_fwd_finish_kernel<<<(int)ceil_div_ll(n, 256), 256, 0, st>>>(partial, bias, out, nsplit, n, J, relu);
+        zsv::launch(linear_fwd_finish_kernel, (int)ceil_div_ll(n, 256), 256, 0, st, partial, bias, out, nsplit, n, J, relu);
         ZSV_LAUNCH_CHECK("linear_fwd_finish_kernel");
     }
     return ZSV_OK;
@@ -418,7 +427,7 @@ int linear_forward(const float* x, const float* w, const float* bias, float* out
 int linear_dgrad(const float* g, const float* w, const float* act_in, float* dx, int B, int K, int J, float* ws,
                  size_t ws_bytes, cudaStream_t st) {
     if ((long long)K * J <= kSmallMatrix) {
-        linear_dgrad_small_kernel<<<dim3(ceil_div(K, 32), ceil_div(B, 8)), 256, 0, st>>>(g, w, act_in, dx, B, K, J);
+        zsv::launch(linear_dgrad_small_kernel, dim3(ceil_div(K, 32), ceil_div(B, 8)), 256, 0, st, g, w, act_in, dx, B, K, J);
         ZSV_LAUNCH_CHECK("linear_dgrad_small_kernel");
         return ZSV_OK;
     }
@@ -431,13 +440,13 @@ int linear_dgrad(const float* g, const float* w, const float* act_in, float* dx,
     const dim3 grid(ceil_div(K, kDgK), nsplit, ceil_div(B, kBT));
     float* dst = direct ? dx : ws;
     if (vec_ok(w, K) && vec_ok(dst, K))
-        linear_dgrad_kernel<true><<<grid, 256, 0, st>>>(g, w, dst, B, K, J, jps);
+        zsv::launch(linear_dgrad_kernel<true>, grid, 256, 0, st, g, w, dst, B, K, J, jps);
     else
-        linear_dgrad_kernel<false><<<grid, 256, 0, st>>>(g, w, dst, B, K, J, jps);
+        zsv::launch(linear_dgrad_kernel<false>, grid, 256, 0, st, g, w, dst, B, K, J, jps);
     ZSV_LAUNCH_CHECK("linear_dgrad_kernel");
     if (!direct) {
         const long long n = (long long)B * K;
-        linear_dgrad_finish_kernel<<<(int)ceil_div_ll(n, 256), 256, 0, st>>>(ws, act_in, dx, nsplit, n);
+        zsv::launch(linear_dgrad_finish_kernel, (int)ceil_div_ll(n, 256), 256, 0, st, ws, act_in, dx, nsplit, n);
         ZSV_LAUNCH_CHECK("linear_dgrad_finish_kernel");
     }
     return ZSV_OK;
@@ -451,15 +460,15 @@ int linear_wgrad(const float* g, const float* x, float* dw, float* db, int B, in
     const dim3 grid(kb, ceil_div(J, jt));
     const size_t smem = (size_t)jt * kBT * sizeof(float);
     if (vec_ok(x, K) && vec_ok(dw, K))
-        linear_wgrad_kernel<true><<<grid, 256, smem, st>>>(g, x, dw, db, B, K, J, jt);
+        zsv::launch(linear_wgrad_kernel<true>, grid, 256, smem, st, g, x, dw, db, B, K, J, jt);
     else
-        linear_wgrad_kernel<false><<<grid, 256, smem, st>>>(g, x, dw, db, B, K, J, jt);
+        zsv::launch(linear_wgrad_kernel<false>, grid, 256, smem, st, g, x, dw, db, B, K, J, jt);
     ZSV_LAUNCH_CHECK("linear_wgrad_kernel");
     return ZSV_OK;
 }
 
 int relu_mask(const float* dy, const float* act, float* out, long long n, cudaStream_t st) {
-    relu_mask_kernel<<<(int)ceil_div_ll(n, 256), 256, 0, st>>>(dy, act, out, n);
+    zsv::launch(relu_mask_kernel, (int)ceil_div_ll(n, 256), 256, 0, st, dy, act, out, n);
     ZSV_LAUNCH_CHECK("relu_mask_kernel");
     return ZSV_OK;
 }

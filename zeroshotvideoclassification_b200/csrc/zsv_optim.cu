@@ -17,6 +17,7 @@
 #include <cuda_bf16.h>
 
 #include "zsv_internal.h"
+#include "zsv_ptx.cuh"
 
 namespace zsv {
 namespace {
@@ -71,6 +72,7 @@ struct PlainBatch {
 
 __global__ void __launch_bounds__(256)
 adam_plain_kernel(const __grid_constant__ PlainBatch B) {
+    pdl_wait();
     for (int unit = blockIdx.x; unit < B.units; unit += gridDim.x) {
         int lo = 0, hi = B.n - 1;   // last item with unit_start <= unit
         while (lo < hi) {
@@ -122,6 +124,7 @@ struct PackBatch {
 
 __global__ void __launch_bounds__(256)
 adam_pack_tiled_kernel(const __grid_constant__ PackBatch B) {
+    pdl_wait();
     __shared__ __align__(16) __nv_bfloat16 tile[kPackCo][kPackElems + 8];
     int lo = 0, hi = B.n - 1;   // last item with unit_start <= blockIdx.x
     while (lo < hi) {
@@ -257,7 +260,7 @@ extern "C" int zsv_adam_step(int n, float* const* params, const float* const* gr
         if (m == 0) continue;
         B.n = m, B.units = (int)units;
         const int blocks = (int)std::min<long long>(units, (long long)sm_count() * 8);
-        adam_plain_kernel<<<blocks, 256, 0, st>>>(B);
+        zsv::launch(adam_plain_kernel, blocks, 256, 0, st, B);
         ZSV_LAUNCH_CHECK("adam_plain_kernel");
     }
     return ZSV_OK;
@@ -302,7 +305,7 @@ extern "C" int zsv_adam_pack_step(int n, const zsv_conv_desc* descs, float* cons
         }
         if (m == 0) continue;
         B.n = m, B.units = (int)units;
-        adam_pack_tiled_kernel<<<(int)units, 256, 0, st>>>(B);
+        zsv::launch(adam_pack_tiled_kernel, (int)units, 256, 0, st, B);
         ZSV_LAUNCH_CHECK("adam_pack_tiled_kernel");
     }
     return ZSV_OK;

@@ -195,6 +195,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// Programmatic dependent launch: block until the kernels this grid depends on have completed and their writes are
+// visible (returns at once for a grid launched without a programmatic dependency).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Let the next kernel of the stream be scheduled now (it still waits in its own pdl_wait for this grid to finish).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l1(const void* p) {
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }
