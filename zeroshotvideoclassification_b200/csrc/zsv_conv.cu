@@ -2066,7 +2066,7 @@ struct Shape {
     int To, Ho, Wo;
     int cinp, coutp;
     bool wfold;
-    int keff;    // reduction channels per tap on the x side (Cin, or 64 for wfold)
+    int keff;    // reduction channels per tap on the x side (Cin; wfold: the W window, 8 * kw rounded up to 16)
     int kpitch;  // channel pitch of the fprop weight image
     int ntaps;   // kt*kh*kw
     int ftaps;   // taps seen by fprop/wgrad kernels (kw folded away for wfold)
@@ -2094,7 +2094,9 @@ int check_desc(const zsv_conv_desc* d, Shape* s) {
         if (s->cinp != 8 || d->kw > 8) return fail(ZSV_ERR_UNSUPPORTED, "wfold layout needs Cin <= 8 and kw <= 8");
         if ((s->Wo - 1) * d->sw + 8 > d->W + kWfoldWpad || d->pw > kWfoldWpad)
             return fail(ZSV_ERR_UNSUPPORTED, "wfold layout: window exceeds padded row");
-        s->keff = 64;
+        // the W window of a tap is kw positions x 8 channel lanes of the 64-element row: k-steps (and TMA bytes) past it
+        // would multiply zeros (C3D's 3x3x3 first layer: K = 32 per tap instead of 64)
+        s->keff = std::min(64, (8 * d->kw + 15) & ~15);
         s->kpitch = 64;
         s->ftaps = d->kt * d->kh;
     } else if (d->x_layout == ZSV_CONV_X_NDHWC) {
@@ -2225,7 +2227,7 @@ int make_x_map(CUtensorMap* m, const zsv_conv_desc* d, const Shape& s, const voi
         const long long Wp = d->W + kWfoldWpad;
         const long long rowB = Wp * 8 * 2;
         // column (pw - d->pw .. ) : repack placed exactly d->pw zero columns on the left, so window start = sw*wo
-        dims[0] = 64;
+        dims[0] = s.keff;
         dims[1] = s.Wo;
         dims[2] = (d->H - ph_ + d->sh - 1) / d->sh;
         dims[3] = (d->T - pt_ + d->st - 1) / d->st;

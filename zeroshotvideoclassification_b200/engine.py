@@ -440,13 +440,14 @@ class BackboneRunner:
         # Round 1's fused epilogue (a shuffle reduction per 16-column chunk) only paid where the tile's main loop is long
         # compared with its epilogue (spatial 1x3x3: few output channels, deep reduction) and tripled the time of the
         # wide, shallow temporal dgrads; mode 1 keeps that rule for A/B runs.
-        # With the one-pass epilogue (round 2) fusing wins everywhere except on shallow-K dgrads of the big layer-1
-        # tensors (temporal 144->64 at 16x56x56: the kernel is epilogue-bound, the fused epilogue costs +140 us where the
-        # separate reduction pass costs 105 us; measured, profiles/r02_fuse_modes.txt): those keep the two-pass form.
+        # With the one-pass epilogue (round 2) fusing wins wherever the tile's reduction is at least 384 deep; on the
+        # shallow-K dgrads (temporal 144->64 and the stem's 45->64, K = 192) the kernel is epilogue-bound and the fused
+        # epilogue costs more than the separate reduction pass (144->64: +140 us against 105 us; 45->64: 163 us fused
+        # against 71 us + ~60 us; measured, profiles/r02_fuse_modes.txt): those keep the two-pass form.
         op = rec.op
-        deep = op.cout * op.kernel[0] * op.kernel[1] * op.kernel[2] >= 8 * op.cin
-        small = op.N * op.T * op.H * op.W * op.cin < 64_000_000
-        fuse = FUSE_BN_BWD and op.stride == (1, 1, 1) and (deep or (FUSE_BN_BWD == 2 and small) or FUSE_BN_BWD >= 3)
+        kdepth = op.cout * op.kernel[0] * op.kernel[1] * op.kernel[2]
+        deep = kdepth >= 8 * op.cin
+        fuse = FUSE_BN_BWD and op.stride == (1, 1, 1) and (deep or (FUSE_BN_BWD == 2 and kdepth >= 384) or FUSE_BN_BWD >= 3)
         if producer is not None and fuse:
             return rec.op.dgrad_bn_fused(dy, rec.wd, addend, producer.y, producer.table, producer.relu)
         return rec.op.dgrad(dy, rec.wd, addend)
