@@ -20,6 +20,7 @@
 #include <mutex>
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 #include <vector>
 
 #include "zsv_internal.h"
@@ -140,6 +141,7 @@ struct IgemmArgs {
     int32_t part_pitch;
     int32_t m_tiles, n_tiles;
     int32_t nstg;            // output staging buffers (2 = the TMA store of tile i overlaps the epilogue of tile i+1)
+    int32_t nybuf;           // y buffers of the fused BatchNorm backward (2 = y is requested a whole tile ahead)
     FastDiv fd_ntiles, fd_tw, fd_th, fd_tt;
     int32_t debug;
     int32_t scratch_bytes;   // epilogue scratch in shared memory (BN-backward fusion sums), multiple of 1 KB
@@ -198,6 +200,9 @@ struct EpiArgs {
     const CUtensorMap* mapY;     // tensor map of bn_y with the boxes of the output map
     uint32_t ybuf_u32;           // smem [out panels][128 rows][128 B] (SWIZZLE_128B): y of the current tile
     uint32_t bar_y, y_phase;     // "y tile landed" barrier and the parity of the current tile
+    uint32_t ynext_u32, bar_ynext;   // buffer / barrier that receive the y tile of this CTA's NEXT tile
+    int y_early;                 // two y buffers: the next tile's y is requested at the top of this tile's epilogue (a whole
+                                 // tile ahead) instead of after this tile's column pass
     uint32_t y_rows;             // rows of one box (every 64-channel panel of a y tile brings y_rows * 128 bytes)
     int has_next, n0, n1, n2, n3, next_origin;   // box coordinates / first channel of this CTA's NEXT tile (y prefetch)
     float* st_acc;               // smem [2][ncols] running sums of this CTA: BatchNorm statistics (sum, sum of squares)
@@ -389,10 +394,11 @@ __device__ __forceinline__ void bn_column_pass(const EpiArgs& E, uint32_t stagin
 }
 
 // (fused BatchNorm backward) start the TMA load of one y tile: panels of 64 channels, same boxes as the output stores
-__device__ __forceinline__ void load_y_tile(const EpiArgs& E, int width, int n_origin, int o0, int o1, int o2, int o3) {
-    mbar_expect_tx(E.bar_y, static_cast<uint32_t>((width + 63) >> 6) * E.y_rows * 128u);
+__device__ __forceinline__ void load_y_tile(const EpiArgs& E, uint32_t ybuf, uint32_t bar, int width, int n_origin, int o0,
+                                            int o1, int o2, int o3) {
+    mbar_expect_tx(bar, static_cast<uint32_t>((width + 63) >> 6) * E.y_rows * 128u);
     for (int p = 0; p * 64 < width; ++p)
-        tma_load_5d(E.ybuf_u32 + p * kPanelBytes, E.mapY, E.bar_y, n_origin + 64 * p, o0, o1, o2, o3);
+        tma_load_5d(ybuf + p * kPanelBytes, E.mapY, bar, n_origin + 64 * p, o0, o1, o2, o3);
 }
 
 __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMap* mapOut, uint8_t* staging,
@@ -407,6 +413,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMa
     // (waiting for them was the top stall of this kernel in the ncu source view).  Prefetching into REGISTERS instead
     // pins 32 registers through the whole epilogue and was measured 20% slower on the epilogue-bound temporal convs.
     constexpr int kChunkStride = 4 * kEpiWarps;
+    // (two y buffers) y of this CTA's next tile: its buffer was last read by the column pass of the previous tile
+    if (et == 0 && E.bn_y != nullptr && E.has_next && E.y_early)
+        load_y_tile(E, E.ynext_u32, E.bar_ynext, width, E.next_origin, E.n0, E.n1, E.n2, E.n3);
     if (E.addend != nullptr && valid && !(E.debug & 2)) {
         for (int c = 0; c < width; c += 64) {
             if (n_origin + c >= E.ncols) break;
@@ -495,8 +504,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMa
         }
         tma_store_commit();
     }
-    // y of this CTA's next tile: lands while that tile's accumulator is read out
-    if (et == 0 && E.bn_y != nullptr && E.has_next) load_y_tile(E, width, E.next_origin, E.n0, E.n1, E.n2, E.n3);
+    // (one y buffer) y of this CTA's next tile: lands while that tile's accumulator is read out
+    if (et == 0 && E.bn_y != nullptr && E.has_next && !E.y_early)
+        load_y_tile(E, E.ynext_u32, E.bar_ynext, width, E.next_origin, E.n0, E.n1, E.n2, E.n3);
     if (E.part_sum != nullptr && !(E.debug & 4)) tile_column_stats(E, staging_u32, width, n_origin, m_tile, et, lane);
 }
 
@@ -539,14 +549,14 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
     const uint32_t stagingOff = ringBytes;                           // [nstg][out_panels][128 rows][128 B], SWIZZLE_128B
     const uint32_t stagingBytes = out_panels * kPanelBytes;
     const uint32_t ybufOff = stagingOff + P.nstg * stagingBytes;     // y tile of the fused BatchNorm backward (one buffer)
-    const uint32_t statOff = ybufOff + (P.bn_y != nullptr ? stagingBytes : 0u);   // fp32 running column sums
+    const uint32_t statOff = ybufOff + (P.bn_y != nullptr ? P.nybuf * stagingBytes : 0u);   // fp32 running column sums
     const uint32_t barOff = statOff + static_cast<uint32_t>(P.scratch_bytes);
     const uint32_t barFull = base + barOff;
     const uint32_t barEmpty = barFull + 8u * stages;
     const uint32_t barTmemFull = barEmpty + 8u * stages;   // [2]
     const uint32_t barTmemEmpty = barTmemFull + 16u;       // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + barOff + 16u * stages + 32u);
-    const uint32_t barY = barFull + 16u * stages + 40u;
+    const uint32_t barY = barFull + 16u * stages + 40u;   // [2]
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -556,8 +566,8 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
         for (int b = 0; b < 2; ++b) {
             mbar_init(barTmemFull + 8u * b, 1);
             mbar_init(barTmemEmpty + 8u * b, k2 ? 2 * kEpiWarps : kEpiWarps);
+            mbar_init(barY + 8u * b, 1);
         }
-        mbar_init(barY, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -627,53 +637,46 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
         const uint32_t idesc = umma_idesc_bf16(k2 ? 256 : 128, P.bn_tile, 0, 0);
         const uint32_t dhi = umma_desc_hi(1024, 2);
         const int tail_steps = ((P.kdim - ((kchunks - 1) << 6)) + 15) >> 4;
-        uint32_t stage = 0, phase = 0;
+        // ring position as running sums: descriptor low word of the A panel (B follows it), barrier addresses
+        const uint32_t ring_lo = umma_desc_lo(base), stage16 = stageBytes >> 4, b_off16 = kPanelBytes >> 4;
+        uint32_t stage = 0, phase = 0, a_lo = ring_lo, bar_full = barFull, bar_empty = barEmpty;
+        uint32_t acc = 0;
+        // one ring stage = one (tap, 64-channel chunk): KS k-steps of K = 16
+        auto run_stage = [&](auto ks_tag, uint32_t tacc) {
+            constexpr int KS = decltype(ks_tag)::value;
+            mbar_wait(bar_full, phase);
+            tc_fence_after();
+            if (leader) {
+                const uint32_t b_lo = a_lo + b_off16;
+#pragma unroll
+                for (int k = 0; k < KS; ++k) {
+                    if (k2) umma2_bf16_lohi(tacc, a_lo + 2u * k, dhi, b_lo + 2u * k, dhi, idesc, k == 0 ? acc : 1u);
+                    else umma_bf16_lohi(tacc, a_lo + 2u * k, dhi, b_lo + 2u * k, dhi, idesc, k == 0 ? acc : 1u);
+                }
+                if (k2) umma2_commit_mc(bar_empty, 3);
+                else umma_commit(bar_empty);
+            }
+            acc = 1u;
+            __syncwarp();
+            if (++stage == static_cast<uint32_t>(stages)) {
+                stage = 0, phase ^= 1u, a_lo = ring_lo, bar_full = barFull, bar_empty = barEmpty;
+            } else {
+                a_lo += stage16, bar_full += 8u, bar_empty += 8u;
+            }
+        };
         int local = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++local) {
             const uint32_t buf = local & 1;
             mbar_wait(barTmemEmpty + 8u * buf, ((local >> 1) & 1u) ^ 1u);   // epilogue drained this buffer
             tc_fence_after();
             const uint32_t tacc = tmem_base + buf * acc_stride;
-            uint32_t acc = 0;
+            acc = 0;
             for (int tp = 0; tp < P.ntaps; ++tp) {
-                for (int c = 0; c < kchunks; ++c) {
-                    const int ksteps = (c + 1 < kchunks) ? 4 : tail_steps;
-                    mbar_wait(barFull + 8u * stage, phase);
-                    tc_fence_after();
-                    if (leader) {
-                        const uint32_t sa = base + stage * stageBytes;
-                        const uint32_t a_lo = umma_desc_lo(sa), b_lo = umma_desc_lo(sa + kPanelBytes);
-                        if (k2) {
-                            umma2_bf16_lohi(tacc, a_lo, dhi, b_lo, dhi, idesc, acc);
-                            if (ksteps == 4) {   // common case: straight-line, constant accumulate flag
-                                umma2_bf16_lohi(tacc, a_lo + 2u, dhi, b_lo + 2u, dhi, idesc, 1u);
-                                umma2_bf16_lohi(tacc, a_lo + 4u, dhi, b_lo + 4u, dhi, idesc, 1u);
-                                umma2_bf16_lohi(tacc, a_lo + 6u, dhi, b_lo + 6u, dhi, idesc, 1u);
-                            } else {
-                                for (int k = 1; k < ksteps; ++k)
-                                    umma2_bf16_lohi(tacc, a_lo + 2u * k, dhi, b_lo + 2u * k, dhi, idesc, 1u);
-                            }
-                            umma2_commit_mc(barEmpty + 8u * stage, 3);
-                        } else {
-                            umma_bf16_lohi(tacc, a_lo, dhi, b_lo, dhi, idesc, acc);
-                            if (ksteps == 4) {   // common case: straight-line, constant accumulate flag
-                                umma_bf16_lohi(tacc, a_lo + 2u, dhi, b_lo + 2u, dhi, idesc, 1u);
-                                umma_bf16_lohi(tacc, a_lo + 4u, dhi, b_lo + 4u, dhi, idesc, 1u);
-                                umma_bf16_lohi(tacc, a_lo + 6u, dhi, b_lo + 6u, dhi, idesc, 1u);
-                            } else {
-                                for (int k = 1; k < ksteps; ++k)
-                                    umma_bf16_lohi(tacc, a_lo + 2u * k, dhi, b_lo + 2u * k, dhi, idesc, 1u);
-                            }
-                            umma_commit(barEmpty + 8u * stage);
-                        }
-                        acc = 1;
-                    }
-                    __syncwarp();
-                    if (++stage == static_cast<uint32_t>(stages)) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
-                }
+                for (int c = 0; c + 1 < kchunks; ++c) run_stage(std::integral_constant<int, 4>{}, tacc);
+                if (tail_steps == 4) run_stage(std::integral_constant<int, 4>{}, tacc);
+                else if (tail_steps == 1) run_stage(std::integral_constant<int, 1>{}, tacc);
+                else if (tail_steps == 2) run_stage(std::integral_constant<int, 2>{}, tacc);
+                else run_stage(std::integral_constant<int, 3>{}, tacc);
             }
             if (leader) {
                 if (k2) umma2_commit_mc(barTmemFull + 8u * buf, 3);
@@ -703,6 +706,7 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
         E.bn_y = P.bn_y, E.bn_tab = P.bn_tab, E.bn_relu = P.bn_relu;
         E.st_acc = statbuf;
         E.mapY = &mapY, E.ybuf_u32 = base + ybufOff, E.bar_y = barY;
+        E.ynext_u32 = E.ybuf_u32, E.bar_ynext = barY, E.y_early = P.nybuf == 2;
         E.y_rows = static_cast<uint32_t>(rows);
         if (P.bn_y != nullptr || P.part_sum != nullptr)   // running sums start at zero; the first tile's barriers order this before any use
             for (int i = et; i < 2 * P.ncols; i += kEpiWarps * 32) statbuf[i] = 0.f;
@@ -721,20 +725,26 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
         if (P.bn_y != nullptr) {
             // rows of the y buffer that no box ever writes must not hold NaN bit patterns (0 * NaN in the column pass)
             uint32_t* yz = reinterpret_cast<uint32_t*>(smem + ybufOff);
-            for (uint32_t i = et; i < stagingBytes / 4u; i += kEpiWarps * 32) yz[i] = 0u;
+            for (uint32_t i = et; i < P.nybuf * stagingBytes / 4u; i += kEpiWarps * 32) yz[i] = 0u;
             fence_proxy_async_smem();
             named_bar_sync(1, kEpiWarps * 32);
             if (et == 0 && first_tile < num_tiles) {
                 int w0, h0, t0, n0, mt_;
                 const int nt0 = tile_origin(first_tile, w0, h0, t0, n0, mt_);
-                load_y_tile(E, P.bn_tile, nt0 * P.bn_tile, w0, h0, t0, n0);
+                load_y_tile(E, E.ybuf_u32, barY, P.bn_tile, nt0 * P.bn_tile, w0, h0, t0, n0);
             }
         }
         int local = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++local) {
             int w0, h0, t0, n0, m_tile;
             const int n_tile = tile_origin(tile, w0, h0, t0, n0, m_tile);
-            E.y_phase = local & 1u;
+            if (P.nybuf == 2) {   // y buffers and their barriers alternate with the tiles
+                const uint32_t yb = local & 1u;
+                E.ybuf_u32 = base + ybufOff + yb * stagingBytes, E.bar_y = barY + 8u * yb, E.y_phase = (local >> 1) & 1u;
+                E.ynext_u32 = base + ybufOff + (yb ^ 1u) * stagingBytes, E.bar_ynext = barY + 8u * (yb ^ 1u);
+            } else {
+                E.y_phase = local & 1u;
+            }
             E.has_next = tile + tile_step < num_tiles;
             if (P.bn_y != nullptr && E.has_next) {
                 int mt_;
@@ -796,6 +806,43 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxCopies = 8;
 
+// MMAs of one ring stage of the halo kernel: `ncp` W taps x 3 taps along the shift dimension x KS k-steps (K = 16
+// each), fully unrolled per W tap.  Descriptor low words advance by running sums (a_tap / b_tap per shift tap, a_cp / b_cp
+// per W tap; unsigned wrap-around encodes negative steps), the high words never change.
+template <bool k2, int KS>
+__device__ __forceinline__ void issue_stage3(uint32_t tacc, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t a_tap, uint32_t b_tap, uint32_t a_cp, uint32_t b_cp, int ncp,
+                                             uint32_t idesc, uint32_t acc) {
+    for (int cp = 0; cp < ncp; ++cp) {
+        uint32_t a = a_lo, b = b_lo;
+        if (k2) {
+#pragma unroll
+            for (int sh = 0; sh < 3; ++sh) {
+#pragma unroll
+                for (int k = 0; k < KS; ++k)
+                    umma2_bf16_lohi(tacc, a + 2u * k, a_hi, b + 2u * k, b_hi, idesc, (sh == 0 && k == 0) ? acc : 1u);
+                a += a_tap;
+                b += b_tap;
+            }
+        } else {
+            // single CTA (the temporal convolutions): measured faster with the shift taps as a loop (one box, A/B of
+            // two builds, profiles/r02_issue_loop.txt: 144->64 dgrad 102 us against 112 us fully unrolled)
+#pragma unroll 1
+            for (int sh = 0; sh < 3; ++sh) {
+#pragma unroll
+                for (int k = 0; k < KS; ++k) umma_bf16_lohi(tacc, a + 2u * k, a_hi, b + 2u * k, b_hi, idesc, k == 0 ? acc : 1u);
+                acc = 1u;
+                a += a_tap;
+                b += b_tap;
+            }
+        }
+        acc = 1u;
+        a_lo += a_cp;
+        b_lo += b_cp;
+    }
+}
+
+
 struct HaloArgs {
     int32_t b[4];        // box extents in smem row order: inner dims 0..2, then the shift dim (output extent)
     int32_t tl[4];       // tile counts per box dim
@@ -813,8 +860,8 @@ struct HaloArgs {
     FastDiv fd_tl0, fd_tl1, fd_tl2;
     int32_t debug;
     int32_t pf_dist;     // L2 prefetch distance in tiles (0 = off)
-    int32_t unaligned_mode;  // experiment: tap shifts that are not whole swizzle atoms (1: plain address, 2: + base offset)
     int32_t scratch_bytes;   // epilogue scratch in shared memory (BN-backward fusion sums), multiple of 1 KB
+    int32_t nybuf;           // y buffers of the fused BatchNorm backward (2 = y is requested a whole tile ahead)
     int32_t wshift;          // 1: ONE box per chunk, widened by kw-1 along W; the W taps are descriptor start offsets
     int32_t w_ext;           // box extent along W in that mode (b[0] + kw - 1)
     int32_t min_off;         // smallest copy_off: W origin of the widened box relative to the tile
@@ -856,7 +903,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const uint32_t stagingOff = ringOff + ringBytes;
     const uint32_t stagingBytes = out_panels * kPanelBytes;
     const uint32_t ybufOff = stagingOff + P.nstg * stagingBytes;     // y tile of the fused BatchNorm backward (one buffer)
-    const uint32_t statOff = ybufOff + (P.bn_y != nullptr ? stagingBytes : 0u);
+    const uint32_t statOff = ybufOff + (P.bn_y != nullptr ? P.nybuf * stagingBytes : 0u);
     const uint32_t barOff = statOff + static_cast<uint32_t>(P.scratch_bytes);
     const uint32_t barFull = base + barOff;
     const uint32_t barEmpty = barFull + 8u * stages;
@@ -864,7 +911,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const uint32_t barTmemEmpty = barTmemFull + 16u;
     const uint32_t barB = barTmemEmpty + 16u;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + barOff + 16u * stages + 40u);
-    const uint32_t barY = barFull + 16u * stages + 48u;
+    const uint32_t barY = barFull + 16u * stages + 48u;   // [2]
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -877,6 +924,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
         mbar_init(barB, 1);
         mbar_init(barY, 1);
+        mbar_init(barY + 8u, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -975,122 +1023,83 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             }
         }
     } else if (warp == 1 && rank == 0) {
+        // The issuing thread is a scalar bottleneck of the small-N convolutions (ncu source view, profiles/r02_issue_loop.txt:
+        // it never waited, it ran 16-20 instructions per MMA at 5-7 clk each while the tensor pipe idled), so everything
+        // that does not change from stage to stage is computed once, descriptor words and barrier addresses are running
+        // sums, and a stage is issued as straight-line code (issue_stage3).
         const uint32_t leader = elect_one();
         const uint32_t idesc = umma_idesc_bf16(k2 ? 256 : 128, P.bn_tile, 0, 0);
         const uint32_t tail_layout = P.tail_box == 16 ? 6u : (P.tail_box == 32 ? 4u : 2u);
-        const uint32_t hi_main = umma_desc_hi(1024, 2);
-        const uint32_t hi_tail = umma_desc_hi(tail_row_bytes * 8u, tail_layout);
-        // wshift: consecutive 8-row groups of the A operand (one W run each) are w_ext rows apart in the staged box
-        const uint32_t hi_main_a = P.wshift ? umma_desc_hi(static_cast<uint32_t>(P.w_ext) * 128u, 2) : hi_main;
-        const uint32_t hi_tail_a = P.wshift ? umma_desc_hi(static_cast<uint32_t>(P.w_ext) * tail_row_bytes, tail_layout) : hi_tail;
         const int tail_steps = ((P.kdim - ((P.nchunks - 1) << 6)) + 15) >> 4;
         const uint32_t tap_bytes16 = per_tap_bytes >> 4;   // descriptor start addresses count 16-byte units
+        // the chunks before the last are 64 channels wide (128-byte rows, four k-steps); the last one may use the
+        // narrow-row maps (tail_box 16 / 32) and fewer k-steps
+        const bool narrow_last = nmain < P.nchunks;
+        const uint32_t rb_last = narrow_last ? tail_row_bytes : 128u;
+        const uint32_t bhi_main = umma_desc_hi(1024, 2);
+        const uint32_t bhi_last = narrow_last ? umma_desc_hi(tail_row_bytes * 8u, tail_layout) : bhi_main;
+        // wshift: consecutive 8-row groups of the A operand (one W run each) are w_ext rows apart in the staged box
+        const uint32_t ahi_main = P.wshift ? umma_desc_hi(static_cast<uint32_t>(P.w_ext) * 128u, 2) : bhi_main;
+        const uint32_t ahi_last = P.wshift ? umma_desc_hi(static_cast<uint32_t>(P.w_ext) * rb_last, narrow_last ? tail_layout : 2u)
+                                           : bhi_last;
+        const uint32_t tap16_main = (static_cast<uint32_t>(ld_inner_rows) * 128u) >> 4;     // one slice along the shift dim
+        const uint32_t tap16_last = (static_cast<uint32_t>(ld_inner_rows) * rb_last) >> 4;
+        const uint32_t w0_main = P.wshift ? (static_cast<uint32_t>(P.w_first) * 128u) >> 4 : 0u;   // row of the first W tap
+        const uint32_t w0_last = P.wshift ? (static_cast<uint32_t>(P.w_first) * rb_last) >> 4 : 0u;
+        const uint32_t cp16_main = P.wshift ? (static_cast<uint32_t>(P.w_step) * 128u) >> 4 : 0u;  // from W tap to W tap
+        const uint32_t cp16_last = P.wshift ? (static_cast<uint32_t>(P.w_step) * rb_last) >> 4 : 0u;
+        const uint32_t b_cp = static_cast<uint32_t>(P.tap_dcp) * tap_bytes16;     // may wrap (negative step)
+        const uint32_t b_step = static_cast<uint32_t>(P.tap_dsh) * tap_bytes16;   // may wrap (negative step)
+        const uint32_t b_first = umma_desc_lo(base) + static_cast<uint32_t>(P.tap0) * tap_bytes16;   // chunk 0, first tap
+        const uint32_t b_chunk16 = P.b_main_bytes >> 4;
+        const uint32_t ring_lo = umma_desc_lo(base + ringOff), stage16 = P.a_stage_bytes >> 4;
+        const int ncp = P.wshift ? P.ncopies : 1;   // W taps per stage
+        const int full_chunks = P.nchunks - 1;
         mbar_wait(barB, 0);
         tc_fence_after();
-        uint32_t stage = 0, phase = 0;
+        uint32_t stage = 0, phase = 0, stage_lo = ring_lo, bar_full = barFull, bar_empty = barEmpty;
+        uint32_t acc = 0;
+        // one chunk = `nload` ring stages (one per W copy, or a single widened box)
+        auto run_chunk = [&](auto ks_tag, uint32_t tacc, uint32_t w0, uint32_t ahi, uint32_t b_lo, uint32_t bhi, uint32_t tap16,
+                             uint32_t cp16) {
+            constexpr int KS = decltype(ks_tag)::value;
+            for (int ld = 0; ld < nload; ++ld) {
+                mbar_wait(bar_full, phase);
+                tc_fence_after();
+                if (P.debug & 8) {   // tuning aid: consume the stage without issuing MMAs
+                    if (leader) {
+                        mbar_arrive(bar_empty);
+                        if (k2) mbar_arrive_cluster(mapa_shared(bar_empty, 1));
+                    }
+                } else if (leader) {
+                    issue_stage3<k2, KS>(tacc, stage_lo + w0, ahi, b_lo, bhi, tap16, b_step, cp16, b_cp, ncp, idesc, acc);
+                    if (k2) umma2_commit_mc(bar_empty, 3);
+                    else umma_commit(bar_empty);
+                }
+                acc = 1u;
+                __syncwarp();
+                b_lo += b_cp;   // copies mode: stage `ld` carries W tap `ld`
+                if (++stage == static_cast<uint32_t>(stages)) {
+                    stage = 0, phase ^= 1u, stage_lo = ring_lo, bar_full = barFull, bar_empty = barEmpty;
+                } else {
+                    stage_lo += stage16, bar_full += 8u, bar_empty += 8u;
+                }
+            }
+        };
         int local = 0;
         for (int it = m_first; it < m_count; it += m_stride, ++local) {
             const uint32_t buf = local & 1;
             mbar_wait(barTmemEmpty + 8u * buf, ((local >> 1) & 1u) ^ 1u);
             tc_fence_after();
             const uint32_t tacc = tmem_base + buf * acc_stride;
-            uint32_t acc = 0;   // 0 only for the very first MMA of the tile
-            for (int c = 0; c < P.nchunks; ++c) {
-                const bool main_chunk = c < nmain;
-                const uint32_t row_bytes = main_chunk ? 128u : tail_row_bytes;
-                const uint32_t dhi = main_chunk ? hi_main : hi_tail;
-                const uint32_t dhi_a = main_chunk ? hi_main_a : hi_tail_a;
-                const int ksteps = (c + 1 < P.nchunks) ? 4 : tail_steps;
-                const uint32_t shift16 = (static_cast<uint32_t>(ld_inner_rows) * row_bytes) >> 4;
-                const uint32_t b_chunk_lo = umma_desc_lo(base + (main_chunk ? c * P.b_main_bytes : nmain * P.b_main_bytes));
-                for (int ld = 0; ld < nload; ++ld) {
-                    // W taps served by this stage: all of them (wshift: start offsets into one widened box) or one copy
-                    const int cp_lo = P.wshift ? 0 : ld;
-                    const int cp_hi = P.wshift ? P.ncopies : ld + 1;
-                    mbar_wait(barFull + 8u * stage, phase);
-                    tc_fence_after();
-                    if (P.debug & 8) {   // tuning aid: consume the stage without issuing MMAs
-                        if (leader) {
-                            mbar_arrive(barEmpty + 8u * stage);
-                            if (k2) mbar_arrive_cluster(mapa_shared(barEmpty + 8u * stage, 1));
-                        }
-                    } else if (leader && k2) {
-                        const uint32_t b_step = static_cast<uint32_t>(P.tap_dsh) * tap_bytes16;
-                        for (int cp = cp_lo; cp < cp_hi; ++cp) {
-                            uint32_t a_lo = umma_desc_lo(base + ringOff + stage * P.a_stage_bytes) +
-                                            (P.wshift ? (static_cast<uint32_t>(P.w_first + cp * P.w_step) * row_bytes) >> 4 : 0u);
-                            uint32_t b_lo = b_chunk_lo + static_cast<uint32_t>(P.tap0 + cp * P.tap_dcp) * tap_bytes16;
-                            for (int sh = 0; sh < P.S; ++sh) {
-                                umma2_bf16_lohi(tacc, a_lo, dhi_a, b_lo, dhi, idesc, acc);
-                                acc = 1;
-                                if (ksteps == 4) {   // common case: straight-line, constant accumulate flag
-                                    umma2_bf16_lohi(tacc, a_lo + 2u, dhi_a, b_lo + 2u, dhi, idesc, 1u);
-                                    umma2_bf16_lohi(tacc, a_lo + 4u, dhi_a, b_lo + 4u, dhi, idesc, 1u);
-                                    umma2_bf16_lohi(tacc, a_lo + 6u, dhi_a, b_lo + 6u, dhi, idesc, 1u);
-                                } else {
-                                    for (int k = 1; k < ksteps; ++k)
-                                        umma2_bf16_lohi(tacc, a_lo + 2u * k, dhi_a, b_lo + 2u * k, dhi, idesc, 1u);
-                                }
-                                a_lo += shift16;
-                                b_lo += b_step;
-                            }
-                        }
-                        umma2_commit_mc(barEmpty + 8u * stage, 3);
-                    } else if (leader && !P.wshift) {
-                        // one W copy per stage.  This issue loop is the scalar bottleneck of the short-K temporal
-                        // convolutions: no per-tap parameter indexing, straight-line k-steps.
-                        uint32_t a_lo = umma_desc_lo(base + ringOff + stage * P.a_stage_bytes);
-                        uint32_t b_lo = b_chunk_lo + static_cast<uint32_t>(P.tap0 + ld * P.tap_dcp) * tap_bytes16;
-                        const uint32_t b_step = static_cast<uint32_t>(P.tap_dsh) * tap_bytes16;   // may wrap (negative step)
-                        for (int sh = 0; sh < P.S; ++sh) {
-                            // experiment: matrix start not on a swizzle-atom boundary -> descriptor base offset (bits 49-51)
-                            const uint32_t ahi = P.unaligned_mode == 2
-                                                     ? (dhi | ((static_cast<uint32_t>(sh * inner_rows) & 7u) << 17)) : dhi;
-                            umma_bf16_lohi(tacc, a_lo, ahi, b_lo, dhi, idesc, acc);
-                            acc = 1;
-                            if (ksteps == 4) {   // common case: straight-line, constant accumulate flag
-                                umma_bf16_lohi(tacc, a_lo + 2u, ahi, b_lo + 2u, dhi, idesc, 1u);
-                                umma_bf16_lohi(tacc, a_lo + 4u, ahi, b_lo + 4u, dhi, idesc, 1u);
-                                umma_bf16_lohi(tacc, a_lo + 6u, ahi, b_lo + 6u, dhi, idesc, 1u);
-                            } else {
-                                for (int k = 1; k < ksteps; ++k)
-                                    umma_bf16_lohi(tacc, a_lo + 2u * k, ahi, b_lo + 2u * k, dhi, idesc, 1u);
-                            }
-                            a_lo += shift16;
-                            b_lo += b_step;
-                        }
-                        umma_commit(barEmpty + 8u * stage);
-                    } else if (leader) {
-                        // all kw W taps from one widened box: start offsets of whole rows, SBO = w_ext rows (dhi_a)
-                        const uint32_t b_step = static_cast<uint32_t>(P.tap_dsh) * tap_bytes16;
-                        const uint32_t stage_lo = umma_desc_lo(base + ringOff + stage * P.a_stage_bytes);
-                        for (int cp = 0; cp < P.ncopies; ++cp) {
-                            uint32_t a_lo = stage_lo + ((static_cast<uint32_t>(P.w_first + cp * P.w_step) * row_bytes) >> 4);
-                            uint32_t b_lo = b_chunk_lo + static_cast<uint32_t>(P.tap0 + cp * P.tap_dcp) * tap_bytes16;
-                            for (int sh = 0; sh < P.S; ++sh) {
-                                umma_bf16_lohi(tacc, a_lo, dhi_a, b_lo, dhi, idesc, acc);
-                                acc = 1;
-                                if (ksteps == 4) {
-                                    umma_bf16_lohi(tacc, a_lo + 2u, dhi_a, b_lo + 2u, dhi, idesc, 1u);
-                                    umma_bf16_lohi(tacc, a_lo + 4u, dhi_a, b_lo + 4u, dhi, idesc, 1u);
-                                    umma_bf16_lohi(tacc, a_lo + 6u, dhi_a, b_lo + 6u, dhi, idesc, 1u);
-                                } else {
-                                    for (int k = 1; k < ksteps; ++k)
-                                        umma_bf16_lohi(tacc, a_lo + 2u * k, dhi_a, b_lo + 2u * k, dhi, idesc, 1u);
-                                }
-                                a_lo += shift16;
-                                b_lo += b_step;
-                            }
-                        }
-                        umma_commit(barEmpty + 8u * stage);
-                    }
-                    __syncwarp();
-                    if (++stage == static_cast<uint32_t>(stages)) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
-                }
-            }
+            acc = 0;   // 0 only for the very first MMA of the tile
+            uint32_t b_lo = b_first;
+            for (int c = 0; c < full_chunks; ++c, b_lo += b_chunk16)
+                run_chunk(std::integral_constant<int, 4>{}, tacc, w0_main, ahi_main, b_lo, bhi_main, tap16_main, cp16_main);
+            if (tail_steps == 4) run_chunk(std::integral_constant<int, 4>{}, tacc, w0_last, ahi_last, b_lo, bhi_last, tap16_last, cp16_last);
+            else if (tail_steps == 1) run_chunk(std::integral_constant<int, 1>{}, tacc, w0_last, ahi_last, b_lo, bhi_last, tap16_last, cp16_last);
+            else if (tail_steps == 2) run_chunk(std::integral_constant<int, 2>{}, tacc, w0_last, ahi_last, b_lo, bhi_last, tap16_last, cp16_last);
+            else run_chunk(std::integral_constant<int, 3>{}, tacc, w0_last, ahi_last, b_lo, bhi_last, tap16_last, cp16_last);
             if (leader) {
                 if (P.debug & 8) {
                     mbar_arrive(barTmemFull + 8u * buf);
@@ -1125,6 +1134,7 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         E.bn_y = P.bn_y, E.bn_tab = P.bn_tab, E.bn_relu = P.bn_relu;
         E.st_acc = statbuf;
         E.mapY = &mapY, E.ybuf_u32 = base + ybufOff, E.bar_y = barY;
+        E.ynext_u32 = E.ybuf_u32, E.bar_ynext = barY, E.y_early = P.nybuf == 2;
         E.y_rows = static_cast<uint32_t>(rows);
         if (P.bn_y != nullptr || P.part_sum != nullptr)   // running sums start at zero; the first tile's barriers order this before any use
             for (int i = et; i < 2 * P.ncols; i += kEpiWarps * 32) statbuf[i] = 0.f;
@@ -1143,13 +1153,13 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         if (P.bn_y != nullptr) {
             // rows of the y buffer that no box ever writes must not hold NaN bit patterns (0 * NaN in the column pass)
             uint32_t* yz = reinterpret_cast<uint32_t*>(smem + ybufOff);
-            for (uint32_t i = et; i < stagingBytes / 4u; i += kEpiWarps * 32) yz[i] = 0u;
+            for (uint32_t i = et; i < P.nybuf * stagingBytes / 4u; i += kEpiWarps * 32) yz[i] = 0u;
             fence_proxy_async_smem();
             named_bar_sync(1, kEpiWarps * 32);
             if (et == 0 && m_first < m_count) {
                 int o0, o1, o2, o3;
                 tile_origin(m_first, o0, o1, o2, o3);
-                load_y_tile(E, width, n_origin, o0, o1, o2, o3);
+                load_y_tile(E, E.ybuf_u32, barY, width, n_origin, o0, o1, o2, o3);
             }
         }
         E.next_origin = n_origin;
@@ -1157,7 +1167,13 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         for (int it = m_first; it < m_count; it += m_stride, ++local) {
             int o0, o1, o2, o3;
             const int mt = tile_origin(it, o0, o1, o2, o3);
-            E.y_phase = local & 1u;
+            if (P.nybuf == 2) {   // y buffers and their barriers alternate with the tiles
+                const uint32_t yb = local & 1u;
+                E.ybuf_u32 = base + ybufOff + yb * stagingBytes, E.bar_y = barY + 8u * yb, E.y_phase = (local >> 1) & 1u;
+                E.ynext_u32 = base + ybufOff + (yb ^ 1u) * stagingBytes, E.bar_ynext = barY + 8u * (yb ^ 1u);
+            } else {
+                E.y_phase = local & 1u;
+            }
             E.has_next = it + m_stride < m_count;
             if (P.bn_y != nullptr && E.has_next) tile_origin(it + m_stride, E.n0, E.n1, E.n2, E.n3);
             const bool valid = row < rows && (o0 + i0) < P.O[0] && (o1 + i1) < P.O[1] && (o2 + i2) < P.O[2] &&
@@ -2339,9 +2355,10 @@ int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtenso
     // buffers always hold the full N tile
     const bool pair = igemm_use_pair(a.bn_tile, m_tiles);
     const int b_rows = pair ? a.bn_tile / 2 : a.bn_tile;
+    int nybuf = fuse ? 1 : 0;
     auto smem_for = [&](int stages_, int nstg_) {
-        return 1024 + stages_ * ((int)kPanelBytes + b_rows * 128) + nstg_ * ((a.bn_tile + 63) / 64) * (int)kPanelBytes + ybuf +
-               scratch + 16 * stages_ + 48 + 64;
+        return 1024 + stages_ * ((int)kPanelBytes + b_rows * 128) + nstg_ * ((a.bn_tile + 63) / 64) * (int)kPanelBytes +
+               nybuf * ybuf + scratch + 16 * stages_ + 48 + 64;
     };
     int nstg = 2;
     if (const char* e = getenv("ZSV_DEBUG_NSTG")) nstg = atoi(e) == 1 ? 1 : 2;
@@ -2354,8 +2371,18 @@ int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtenso
         while (s1 > 2 && smem_for(s1, 1) > 226 * 1024) --s1;
         if (s1 > stages && !getenv("ZSV_DEBUG_KEEP_NSTG2")) nstg = 1, stages = s1;
     }
+    // fused BatchNorm backward: a second y buffer (y requested a whole tile ahead) if the ring keeps >= 4 stages and
+    // loses at most one
+    if (fuse && !(getenv("ZSV_NYBUF") && atoi(getenv("ZSV_NYBUF")) == 1)) {
+        nybuf = 2;
+        int s2 = 8;
+        while (s2 > 2 && smem_for(s2, nstg) > 226 * 1024) --s2;
+        if (s2 >= 4 && s2 >= stages - 1 && smem_for(s2, nstg) <= 226 * 1024) stages = s2;
+        else nybuf = 1;
+    }
     if (const char* e = getenv("ZSV_DEBUG_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));
     a.nstg = nstg;
+    a.nybuf = nybuf;
     a.stages = stages;
     a.tmem_cols = 2 * pow2_cols(a.bn_tile);   // two accumulator buffers
     if (a.tmem_cols > 512) return fail(ZSV_ERR_UNSUPPORTED, "igemm: N tile %d too wide for two TMEM buffers", a.bn_tile);
@@ -2415,7 +2442,7 @@ struct HaloPlan {
     bool pair;          // CTA-pair variant: M = 256 tiles, half of the weight rows resident per CTA
     bool wshift;        // W taps by descriptor offset into one widened box (spatial, b[0] == 8)
     int b[4], tl[4], O[4];
-    int S, ncopies, stages, nstg, bn_tile, n_step, n_tiles, nchunks, tail_box;
+    int S, ncopies, stages, nstg, nybuf, bn_tile, n_step, n_tiles, nchunks, tail_box;
     long long m_tiles;
     uint32_t a_stage_bytes, b_main_bytes, b_tail_bytes, b_total_bytes;
     int smem;
@@ -2467,7 +2494,7 @@ HaloPlan plan_halo_impl(int W, int H, int T, int N, int kdim, int cols, int kt, 
     if (const char* e = getenv("ZSV_DEBUG_HALO_BOX")) {   // tuning aid: force the box "b0,b1,b2,b3"
         int q[4];
         if (sscanf(e, "%d,%d,%d,%d", &q[0], &q[1], &q[2], &q[3]) == 4 &&
-            ((q[0] * q[1] * q[2]) % 8 == 0 || getenv("ZSV_DEBUG_HALO_UNALIGNED")) && q[0] * q[1] * q[2] * q[3] <= 128)
+            (q[0] * q[1] * q[2]) % 8 == 0 && q[0] * q[1] * q[2] * q[3] <= 128)
             for (int i = 0; i < 4; ++i) p.b[i] = q[i];
         best = 1;
     }
@@ -2519,6 +2546,15 @@ HaloPlan plan_halo_impl(int W, int H, int T, int N, int kdim, int cols, int kt, 
             if (stages >= (nstg == 2 ? 3 : 2)) break;
         }
         if (nstg < 1) continue;
+        // fused BatchNorm backward: a second y buffer (y requested a whole tile ahead) if the ring stays deep enough and
+        // loses at most one stage
+        p.nybuf = scratch_mode == 2 ? 1 : 0;
+        if (scratch_mode == 2 && !(getenv("ZSV_NYBUF") && atoi(getenv("ZSV_NYBUF")) == 1)) {
+            const int avail2 = 226 * 1024 - fixed - staging1;
+            const int stages2 = avail2 > 0 ? avail2 / (int)p.a_stage_bytes : 0;
+            // (the ring depths plan_halo asks of a pair plan must survive: 3 with the W-shift layout, else 4)
+            if (stages2 >= (p.wshift ? 3 : 4) && stages2 >= std::min(stages, 8) - 1) p.nybuf = 2, fixed += staging1, stages = stages2;
+        }
         stages = std::min(stages, 8);
         if (const char* e = getenv("ZSV_DEBUG_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));
         if (const char* e = getenv("ZSV_DEBUG_NSTG")) {
@@ -2597,10 +2633,10 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
     a.m_tiles = (int)p.m_tiles, a.stages = p.stages, a.relu = relu, a.tmem_cols = 2 * pow2_cols(p.bn_tile);
     a.part_pitch = outPitch;
     a.nstg = p.nstg;
+    a.nybuf = fuse ? std::max(p.nybuf, 1) : 0;
     a.fd_tl0 = make_fastdiv(p.tl[0]), a.fd_tl1 = make_fastdiv(p.tl[1]), a.fd_tl2 = make_fastdiv(p.tl[2]);
     if (const char* e = getenv("ZSV_DEBUG_EPI")) a.debug = atoi(e);
     a.pf_dist = 3;
-    if (const char* e = getenv("ZSV_DEBUG_HALO_UNALIGNED")) a.unaligned_mode = atoi(e);
     if (const char* e = getenv("ZSV_DEBUG_PF")) a.pf_dist = atoi(e);
     a.a_stage_bytes = p.a_stage_bytes, a.b_main_bytes = p.b_main_bytes, a.b_tail_bytes = p.b_tail_bytes;
     a.b_total_bytes = p.b_total_bytes;

@@ -197,6 +197,9 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 }
 // Programmatic dependent launch: block until the kernels this grid depends on have completed and their writes are
 // visible (returns at once for a grid launched without a programmatic dependency).
+// (An early griddepcontrol.launch_dependents right after the wait -- the next kernel's blocks become resident while this
+// grid still runs -- was measured 8 % SLOWER on the training step, profiles/r02_pdl_early_trigger.txt: waiting blocks take
+// the slots the side-stream weight gradients would have filled.)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // Let the next kernel of the stream be scheduled now (it still waits in its own pdl_wait for this grid to finish).
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
