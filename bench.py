@@ -536,12 +536,13 @@ def run_b200(args):
     flop_per_clip = sum(v["flops"] for v in kinds.values()) / prof_steps / B if kinds else FLOP_PER_CLIP
     # dram__bytes_read+write per launch of the same kernels, from the committed ncu capture -- only if that capture was
     # taken from THIS build of the kernels (the file records the csrc fingerprint build.py stamps the library with)
-    traffic, traffic_src = None, None
+    traffic, traffic_src, tensor_pipe = None, None, None
     tpath = os.path.join(ROOT, "profiles", "r02_conv_dram_traffic.json")
     if os.path.exists(tpath) and "2plus1d" in args.network:
         tj = json.load(open(tpath))
         if tj.get("build_fingerprint") == build._fingerprint():
             traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/r02_conv_dram_traffic.json (ncu, per launch, this build)"
+            tensor_pipe = tj.get("tensor_pipe_active_pct_time_weighted")
         else:
             traffic_src = "profiles/r02_conv_dram_traffic.json is from another build of csrc/ (fingerprint differs): not reported"
     km = {k: {"ms_per_step": v["ms"] / prof_steps, "calls_per_step": v["calls"] / prof_steps,
@@ -556,6 +557,8 @@ def run_b200(args):
         "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
         "frac": (achieved / peaks["tflops_sustained"]) if achieved else None, "traffic": traffic,
         "traffic_source": traffic_src,
+        # sm__pipe_tensor_subpipe_hmma_cycles_active (counts tcgen05 work), time-weighted over the same launches, same capture
+        "tensor_pipe_active_pct": tensor_pipe,
         "peak_source": peaks["source"] + ", bf16_tflops_sustained (kernel timed inside a long step)",
         "avg_launch_ms": dom_ms / dom_calls if dom_calls else None,
         "flops_per_launch": dom_fl / dom_calls if dom_calls else None,
