@@ -502,6 +502,11 @@ def run_b200(args):
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pe0.record()
     for _ in range(prof_steps):
+        # Eager enqueue is host-bound (~15 ms of Python per 12 ms step), so an event pair recorded around a call would
+        # also time the launch latency of an idle GPU (and the host gap inside calls that launch two kernels).  A spin
+        # kernel ahead of every profiled step lets the host run a whole step ahead: the kernels then execute back to
+        # back and the events are taken at kernel boundaries on the device.
+        torch.cuda._sleep(int(15e6))     # measured 30-90 ms on B200: longer than the host needs for one step
         step(x_dev, z_dev)
     pe1.record()
     barrier()
@@ -563,8 +568,10 @@ def run_b200(args):
         "avg_launch_ms": dom_ms / dom_calls if dom_calls else None,
         "flops_per_launch": dom_fl / dom_calls if dom_calls else None,
         "share_of_step": (dom_ms / prof_steps) / ms_per_step if ms_per_step else None,
-        "timed_in": f"{prof_steps} kernel-by-kernel iterations right after the timed region "
-                    f"({prof_ms_total / prof_steps:.2f} ms/step eager vs {ms_per_step:.2f} ms/step timed)",
+        "timed_in": f"{prof_steps} kernel-by-kernel iterations right after the timed region, CUDA events around every "
+                    f"convolution call on the launching stream, weight gradients on the same stream, the host kept a step "
+                    f"ahead by a spin kernel so that no launch latency is inside an interval "
+                    f"({prof_ms_total / prof_steps:.2f} ms/step incl. the spin vs {ms_per_step:.2f} ms/step timed)",
         "by_kernel": km,
         "whole_step_frac_of_tensor_peak": (value / world) * flop_per_clip / (peaks["tflops_sustained"] * 1e12),
     }
