@@ -211,6 +211,9 @@ struct EpiArgs {
     int debug;   // tuning aid (ZSV_DEBUG_EPI bit mask): 1 = skip the TMA store, 2 = skip TMEM read + staging, 4 = skip stats
     uint32_t bar_full, full_phase;   // "accumulator complete" barrier of this tile: waited for inside epilogue_tile, AFTER
                                      // the global loads of the tile's first chunks are in flight
+    // split epilogue (kSplit kernels): hand-over of this tile's staging buffer between the convert and the finish group
+    uint32_t bar_staged, bar_free;
+    uint32_t stg_phase;              // parity of this use of the staging buffer
 };
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -510,6 +513,214 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMa
     if (E.part_sum != nullptr && !(E.debug & 4)) tile_column_stats(E, staging_u32, width, n_origin, m_tile, et, lane);
 }
 
+// ================================================================================================
+// Split epilogue (kSplit kernels; tiles of at most 64 output channels).
+// The per-tile epilogue of the narrow layer-1 kernels is a serial chain that bounds them (ncu source view,
+// profiles/r02_issue_loop.txt: ~1000 clk of set-up and waits, ~950 clk of TMEM read-out and ~1800 clk of statistics per
+// 128 x 64 tile against 1300 clk of MMA time).  Here the eight epilogue warps form TWO groups that work on consecutive
+// tiles at the same time:
+//   convert group (warps 2-5, epilogue_convert): waits for the accumulator, TMEM -> registers -> (+bias, +addend, ReLU) ->
+//       bf16 -> SWIZZLE_128B staging tile, hands the accumulator back to the MMA warp and the staged tile to the other group;
+//   finish group (warps 6-9, epilogue_finish): fused BatchNorm-backward column pass or BatchNorm statistics over the staged
+//       tile, TMA store, then frees the staging buffer ("staged" / "free" mbarriers per staging buffer; one named barrier
+//       of 128 threads inside the group).
+// Measured on one box (two builds): 45->64 fprop 100.8 -> 80.5 us, dgrad 71.0 -> 59.0 us, 144->64 fprop 116 -> 108 us.
+// Tiles wider than 64 channels are bound by the read-out, which needs all eight warps: they keep the single group.
+// ================================================================================================
+constexpr int kGroupThreads = 128;
+
+// Thread layout of the 128-thread column passes (channel octets x row segments): 16 segments of 8 rows (width <= 64).
+// Segment g owns rows g, g + 16, ...: the 8 lanes of a quarter warp read one 16-byte chunk of 8 different rows, which the
+// 128-byte swizzle spreads over all banks (address(row, chunk) = row*128 + ((chunk ^ (row & 7)) << 4)).
+__device__ __forceinline__ void tile_column_stats_g(const EpiArgs& E, uint32_t staging_u32, int width, int n_origin, int eb,
+                                                    int lane) {
+    const int ntasks = (width >> 3) * 16;          // <= 128
+    if ((eb & ~31) >= ntasks) return;              // whole warp idle
+    const bool active = eb < ntasks;
+    const int oct = active ? eb >> 4 : 0;
+    const int seg = eb & 15;
+    uint64_t s2[4] = {0ull, 0ull, 0ull, 0ull}, q2[4] = {0ull, 0ull, 0ull, 0ull};
+    if (active) {
+        const uint32_t a0 = staging_u32 + static_cast<uint32_t>(seg) * 128u + (static_cast<uint32_t>((oct ^ seg) & 7) << 4);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint4 v = lds128(a0 + static_cast<uint32_t>(u) * 2048u);
+            add2_sq2(s2[0], q2[0], v.x);
+            add2_sq2(s2[1], q2[1], v.y);
+            add2_sq2(s2[2], q2[2], v.z);
+            add2_sq2(s2[3], q2[3], v.w);
+        }
+    }
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(v[2 * j]), "=f"(v[2 * j + 1]) : "l"(s2[j]));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(v[8 + 2 * j]), "=f"(v[8 + 2 * j + 1]) : "l"(q2[j]));
+    }
+    xreduce_stage<16>(v, lane, 8);
+    xreduce_stage<8>(v, lane, 4);
+    xreduce_stage<4>(v, lane, 2);
+    xreduce_stage<2>(v, lane, 1);
+    // lane bits (of its 16-lane group): bit3 = quantity, bits 2..0 = column within the octet
+    const int col = n_origin + oct * 8 + (lane & 7);
+    if (active && col < E.ncols) E.st_acc[((lane & 8) ? E.ncols : 0) + col] += v[0];
+}
+
+__device__ __forceinline__ void bn_column_pass_g(const EpiArgs& E, uint32_t staging_u32, int width, int n_origin, int eb,
+                                                 int lane) {
+    const int ntasks = (width >> 3) * 16;
+    if ((eb & ~31) >= ntasks) return;
+    const bool active = eb < ntasks;
+    const int oct = active ? eb >> 4 : 0;
+    const int seg = eb & 15;
+    const int colbase = n_origin + oct * 8;
+    f32x2 sc[4], sh[4], s2[4], q2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+        if (active && colbase + 2 * j < E.ncols) t0 = __ldg(E.bn_tab + colbase + 2 * j);
+        if (active && colbase + 2 * j + 1 < E.ncols) t1 = __ldg(E.bn_tab + colbase + 2 * j + 1);
+        sc[j] = f2_make(t0.x, t1.x), sh[j] = f2_make(t0.y, t1.y);
+        s2[j] = q2[j] = 0ull;
+    }
+    if (active) {
+        const uint32_t off0 = static_cast<uint32_t>(seg) * 128u + (static_cast<uint32_t>((oct ^ seg) & 7) << 4);
+#pragma unroll 4
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t off = off0 + static_cast<uint32_t>(u) * 2048u;
+            const uint4 g = lds128(staging_u32 + off);
+            const uint4 yv = lds128(E.ybuf_u32 + off);
+            uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+            const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const f32x2 y2 = f2_from_bf16x2(yw[j]);
+                if (E.bn_relu) {
+                    const uint32_t bn_out = f2_to_bf16x2(f2_fma(y2, sc[j], sh[j]));
+                    const __nv_bfloat162 ob = *reinterpret_cast<const __nv_bfloat162*>(&bn_out);
+                    gw[j] &= __hgt2_mask(ob, __float2bfloat162_rn(0.f));
+                }
+                const f32x2 g2 = f2_from_bf16x2(gw[j]);
+                s2[j] = f2_add(s2[j], g2);
+                q2[j] = f2_fma(g2, y2, q2[j]);
+            }
+            if (E.bn_relu) sts128(staging_u32 + off, make_uint4(gw[0], gw[1], gw[2], gw[3]));
+        }
+    }
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        f2_split(s2[j], v[2 * j], v[2 * j + 1]);
+        f2_split(q2[j], v[8 + 2 * j], v[8 + 2 * j + 1]);
+    }
+    xreduce_stage<16>(v, lane, 8);
+    xreduce_stage<8>(v, lane, 4);
+    xreduce_stage<4>(v, lane, 2);
+    xreduce_stage<2>(v, lane, 1);
+    const int col = colbase + (lane & 7);
+    if (active && col < E.ncols) E.st_acc[((lane & 8) ? E.ncols : 0) + col] += v[0];
+}
+
+// Convert group, one tile: accumulator -> staged bf16 tile.  `row` = this thread's TMEM lane = row of the staging tile.
+__device__ __forceinline__ void epilogue_convert(const EpiArgs& E, uint8_t* staging, uint32_t trow, uint32_t bar_tmem_empty,
+                                                 int width, int n_origin, bool valid, long long off, int row, int lane) {
+    if (E.addend != nullptr && valid && !(E.debug & 2)) {   // the shortcut addend does not depend on the accumulator
+        for (int c = 0; c < width; c += 64) {
+            if (n_origin + c >= E.ncols) break;
+            prefetch_l1(E.addend + off + n_origin + c);
+        }
+    }
+    mbar_wait(E.bar_full, E.full_phase);
+    tc_fence_after();
+    // the staging buffer about to be written: the finish group is done with its previous tile (store read, sums taken)
+    mbar_wait(E.bar_free, E.stg_phase ^ 1u);
+    const uint32_t srow = static_cast<uint32_t>(row) * 128u;
+    const uint32_t sxor = static_cast<uint32_t>(row & 7);
+    auto emit_chunk = [&](int c, const uint32_t (&v)[16]) {
+        const int col = n_origin + c;
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        if (E.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (col + j < E.nbias) f[j] += __ldg(E.bias + col + j);
+        }
+        if (E.addend != nullptr && valid) {
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                if (col + 8 * hlf < E.ncols) {
+                    const uint4 a = *reinterpret_cast<const uint4*>(E.addend + off + col + 8 * hlf);
+                    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        f[8 * hlf + 2 * j] += bf16_lo(aw[j]);
+                        f[8 * hlf + 2 * j + 1] += bf16_hi(aw[j]);
+                    }
+                }
+            }
+        }
+        if (E.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk[j] = valid ? pack_bf16x2(f[2 * j], f[2 * j + 1]) : 0u;
+        uint8_t* prow = staging + static_cast<uint32_t>(c >> 6) * kPanelBytes + srow;
+        const uint32_t ch = static_cast<uint32_t>(c & 63) >> 3;
+        *reinterpret_cast<uint4*>(prow + ((ch ^ sxor) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(prow + (((ch + 1) ^ sxor) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    };
+    // the warp reads every chunk of its lane quadrant, two TMEM loads in flight per wait
+    for (int c = 0; c < width && !(E.debug & 2); c += 32) {
+        uint32_t v0[16], v1[16];
+        const bool two = c + 16 < width;
+        tmem_ld16(trow + c, v0);
+        if (two) tmem_ld16(trow + c + 16, v1);
+        tmem_ld_wait();
+        emit_chunk(c, v0);
+        if (two) emit_chunk(c + 16, v1);
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA store the other group issues
+    __syncwarp();
+    if (lane == 0) {
+        if (E.remote_arrive) mbar_arrive_cluster(bar_tmem_empty);   // accumulator buffer back to the MMA warp
+        else mbar_arrive(bar_tmem_empty);
+        mbar_arrive(E.bar_staged);
+    }
+}
+
+// Finish group, one tile: column pass / statistics over the staged tile, TMA store, staging buffer released.
+__device__ __forceinline__ void epilogue_finish(const EpiArgs& E, const CUtensorMap* mapOut, uint32_t staging_u32, int width,
+                                                int n_origin, int o0, int o1, int o2, int o3, int eb, int lane) {
+    // (two y buffers) y of this CTA's next tile: its buffer was last read by the column pass of the previous tile
+    if (eb == 0 && E.bn_y != nullptr && E.has_next && E.y_early)
+        load_y_tile(E, E.ynext_u32, E.bar_ynext, width, E.next_origin, E.n0, E.n1, E.n2, E.n3);
+    mbar_wait(E.bar_staged, E.stg_phase);
+    if (E.bn_y != nullptr) {
+        mbar_wait(E.bar_y, E.y_phase);
+        bn_column_pass_g(E, staging_u32, width, n_origin, eb, lane);
+        fence_proxy_async_smem();                // masked tile (generic-proxy writes) -> visible to the TMA store
+        named_bar_sync(1, kGroupThreads);        // every thread is done with the y tile and the staged tile is final
+    }
+    if (eb == 0 && !(E.debug & 1)) {
+        for (int p = 0; p * 64 < width; ++p) {
+            const int ccol = n_origin + 64 * p;
+            if (ccol < E.ncols) tma_store_5d(mapOut, staging_u32 + p * kPanelBytes, ccol, o0, o1, o2, o3);
+        }
+        tma_store_commit();
+    }
+    if (eb == 0 && E.bn_y != nullptr && E.has_next && !E.y_early)
+        load_y_tile(E, E.ynext_u32, E.bar_ynext, width, E.next_origin, E.n0, E.n1, E.n2, E.n3);
+    if (E.part_sum != nullptr && !(E.debug & 4)) tile_column_stats_g(E, staging_u32, width, n_origin, eb, lane);
+    // release the staging buffer: the store has read it and every thread of the group has taken its sums
+    if (eb == 0) tma_store_wait_read();
+    named_bar_sync(1, kGroupThreads);
+    if (eb == 0) mbar_arrive(E.bar_free);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K-major implicit GEMM: out[pos][co] = sum_{tap, ci} act[pos + tap][ci] * w[tap][co][ci]
 //
@@ -527,7 +738,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& E, const CUtensorMa
 // box of bn_tile/2 rows), so B-operand shared-memory reads and B TMA bytes per SM halve.  "full" barriers live in the
 // leader and count both CTAs' bytes; "empty" and "TMEM full" are multicast commits; the peer's epilogue warps arrive on
 // the leader's "TMEM empty" barrier through its shared::cluster address.
-template <bool k2>
+template <bool k2, bool kSplit>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
                     const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
@@ -557,6 +768,9 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
     const uint32_t barTmemEmpty = barTmemFull + 16u;       // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + barOff + 16u * stages + 32u);
     const uint32_t barY = barFull + 16u * stages + 40u;   // [2]
+    const uint32_t barStaged = barY + 16u;                // [2] (kSplit) staging buffer written by the 4 convert warps
+    const uint32_t barFree = barStaged + 16u;             // [2] (kSplit) staging buffer released by the finish group
+    constexpr int kCvtWarps = kSplit ? 4 : kEpiWarps;     // warps that read the accumulator out
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -565,8 +779,12 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(barTmemFull + 8u * b, 1);
-            mbar_init(barTmemEmpty + 8u * b, k2 ? 2 * kEpiWarps : kEpiWarps);
+            mbar_init(barTmemEmpty + 8u * b, k2 ? 2 * kCvtWarps : kCvtWarps);
             mbar_init(barY + 8u * b, 1);
+            if (kSplit) {
+                mbar_init(barStaged + 8u * b, 4);
+                mbar_init(barFree + 8u * b, 1);
+            }
         }
         fence_barrier_init();
     }
@@ -685,6 +903,108 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
             __syncwarp();
         }
     } else if (warp >= 2) {
+      if constexpr (kSplit) {
+        const bool finish = warp >= 6;        // finish group (warps 6-9) / convert group (warps 2-5)
+        const int q = warp & 3;               // TMEM lane quadrant a convert warp may read
+        const int row = q * 32 + lane;
+        int r = row;
+        const int w = r % P.bw;
+        r /= P.bw;
+        const int h = r % P.bh;
+        r /= P.bh;
+        const int t = r % P.bt;
+        const int n = r / P.bt;
+        const int eb = (threadIdx.x - 64) & (kGroupThreads - 1);   // thread index within the group
+        EpiArgs E;
+        E.addend = P.addend, E.bias = P.bias, E.part_sum = P.part_sum, E.part_sq = P.part_sq;
+        E.ncols = P.ncols, E.nbias = P.nbias, E.relu = P.relu, E.part_pitch = P.part_pitch;
+        E.debug = P.debug;
+        E.remote_arrive = k2 ? 1 : 0;
+        const uint32_t tmemEmptyBar = k2 ? mapa_shared(barTmemEmpty, 0) : barTmemEmpty;
+        float* statbuf = reinterpret_cast<float*>(smem + statOff);
+        E.bn_y = P.bn_y, E.bn_tab = P.bn_tab, E.bn_relu = P.bn_relu;
+        E.st_acc = statbuf;
+        E.mapY = &mapY, E.ybuf_u32 = base + ybufOff, E.bar_y = barY;
+        E.ynext_u32 = E.ybuf_u32, E.bar_ynext = barY, E.y_early = P.nybuf == 2;
+        E.y_rows = static_cast<uint32_t>(rows);
+        auto tile_origin = [&](int tile, int& w0, int& h0, int& t0, int& n0, int& m_tile) {
+            int m, in_;
+            const int n_tile = fdivmod(tile, P.fd_ntiles, m);
+            if (k2) m = 2 * m + static_cast<int>(rank);
+            m_tile = m;
+            const int iw = fdivmod(m, P.fd_tw, m);
+            const int ih = fdivmod(m, P.fd_th, m);
+            const int itt = fdivmod(m, P.fd_tt, in_);
+            w0 = iw * P.bw, h0 = ih * P.bh, t0 = itt * P.bt, n0 = in_ * P.bn;
+            return n_tile;
+        };
+        if (finish) {
+            if (P.bn_y != nullptr || P.part_sum != nullptr)   // running sums of this CTA start at zero
+                for (int i = eb; i < 2 * P.ncols; i += kGroupThreads) statbuf[i] = 0.f;
+            if (P.bn_y != nullptr) {
+                // rows of the y buffer that no box ever writes must not hold NaN bit patterns (0 * NaN in the column pass)
+                uint32_t* yz = reinterpret_cast<uint32_t*>(smem + ybufOff);
+                for (uint32_t i = eb; i < P.nybuf * stagingBytes / 4u; i += kGroupThreads) yz[i] = 0u;
+                fence_proxy_async_smem();
+            }
+            named_bar_sync(1, kGroupThreads);
+            if (P.bn_y != nullptr && eb == 0 && first_tile < num_tiles) {
+                int w0, h0, t0, n0, mt_;
+                const int nt0 = tile_origin(first_tile, w0, h0, t0, n0, mt_);
+                load_y_tile(E, E.ybuf_u32, barY, P.bn_tile, nt0 * P.bn_tile, w0, h0, t0, n0);
+            }
+        }
+        int local = 0;
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++local) {
+            int w0, h0, t0, n0, m_tile;
+            const int n_tile = tile_origin(tile, w0, h0, t0, n0, m_tile);
+            const uint32_t buf = local & 1;
+            // staging buffer of this tile and the parity of this use of it
+            const uint32_t sbi = P.nstg == 2 ? buf : 0u;
+            const uint32_t sb = sbi * stagingBytes;
+            E.bar_staged = barStaged + 8u * sbi, E.bar_free = barFree + 8u * sbi;
+            E.stg_phase = (P.nstg == 2 ? (local >> 1) : local) & 1u;
+            if (!finish) {
+                const bool valid =
+                    row < rows && (w0 + w) < P.OW && (h0 + h) < P.OH && (t0 + t) < P.OT && (n0 + n) < P.ON;
+                const long long off = (long long)(n0 + n) * P.o_sN + (long long)(t0 + t) * P.o_sT +
+                                      (long long)(h0 + h) * P.o_sH + (long long)(w0 + w) * P.o_sW;
+                E.bar_full = barTmemFull + 8u * buf, E.full_phase = (local >> 1) & 1u;
+                const uint32_t trow = tmem_base + buf * acc_stride + (static_cast<uint32_t>(q * 32) << 16);
+                epilogue_convert(E, smem + stagingOff + sb, trow, tmemEmptyBar + 8u * buf, P.bn_tile, n_tile * P.bn_tile,
+                                 valid, off, row, lane);
+            } else {
+                E.has_next = tile + tile_step < num_tiles;
+                if (P.bn_y != nullptr) {
+                    if (E.has_next) {
+                        int mt_;
+                        E.next_origin = tile_origin(tile + tile_step, E.n0, E.n1, E.n2, E.n3, mt_) * P.bn_tile;
+                    }
+                    if (P.nybuf == 2) {   // y buffers and their barriers alternate with the tiles
+                        E.ybuf_u32 = base + ybufOff + buf * stagingBytes, E.bar_y = barY + 8u * buf, E.y_phase = (local >> 1) & 1u;
+                        E.ynext_u32 = base + ybufOff + (buf ^ 1u) * stagingBytes, E.bar_ynext = barY + 8u * (buf ^ 1u);
+                    } else {
+                        E.y_phase = local & 1u;
+                    }
+                }
+                epilogue_finish(E, &mapOut, base + stagingOff + sb, P.bn_tile, n_tile * P.bn_tile, w0, h0, t0, n0, eb, lane);
+            }
+        }
+        if (finish) {
+            if (eb == 0) tma_store_wait_all();   // global writes of the last tile complete before the CTA exits
+            if (P.bn_y != nullptr) {
+                for (int i = eb; i < 2 * P.ncols; i += kGroupThreads) {   // (the last tile's named barrier ordered the sums)
+                    const int qn = i >= P.ncols ? 1 : 0;
+                    P.bn_partial[((long long)blockIdx.x * 4 + qn) * P.ncols + (i - qn * P.ncols)] = statbuf[i];
+                }
+            } else if (P.part_sum != nullptr) {
+                for (int i = eb; i < 2 * P.ncols; i += kGroupThreads) {
+                    const int qn = i >= P.ncols ? 1 : 0;
+                    (qn ? P.part_sq : P.part_sum)[(long long)blockIdx.x * P.part_pitch + (i - qn * P.ncols)] = statbuf[i];
+                }
+            }
+        }
+      } else {
         const int q = warp & 3;               // TMEM lane quadrant this warp may read
         const int half = (warp - 2) >> 2;     // which of the warps of the quadrant (chunk index mod kEpiWarps/4)
         const int row = q * 32 + lane;
@@ -776,6 +1096,8 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
                 (qn ? P.part_sq : P.part_sum)[(long long)blockIdx.x * P.part_pitch + (i - qn * P.ncols)] = statbuf[i];
             }
         }
+    
+      }
     }
     if (k2) cluster_sync_all();     // neither CTA leaves (or frees TMEM) while the pair still reads its shared memory
     else __syncthreads();
@@ -879,8 +1201,8 @@ struct HaloArgs {
 // k2 = true: CTA pair (cluster of 2, tcgen05 cta_group::2) on M = 256 tiles, each CTA holding HALF of the resident weight
 // rows -- the shared memory that frees is what buys a deep activation ring for the 9-tap 64<->144 convolutions, whose
 // 162 KB weight image otherwise leaves two ring stages (every load latency exposed).  Barrier protocol as in
-// igemm_kmajor_kernel<true>.
-template <bool k2>
+// igemm_kmajor_kernel<true, *>.
+template <bool k2, bool kSplit>
 __global__ void __launch_bounds__(kIgemmThreads, 1)
 igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAtail,
                   const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBtail,
@@ -912,6 +1234,9 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const uint32_t barB = barTmemEmpty + 16u;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + barOff + 16u * stages + 40u);
     const uint32_t barY = barFull + 16u * stages + 48u;   // [2]
+    const uint32_t barStaged = barY + 16u;                // [2] (kSplit) staging buffer written by the 4 convert warps
+    const uint32_t barFree = barStaged + 16u;             // [2] (kSplit) staging buffer released by the finish group
+    constexpr int kCvtWarps = kSplit ? 4 : kEpiWarps;     // warps that read the accumulator out
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -920,11 +1245,14 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(barTmemFull + 8u * i, 1);
-            mbar_init(barTmemEmpty + 8u * i, k2 ? 2 * kEpiWarps : kEpiWarps);
+            mbar_init(barTmemEmpty + 8u * i, k2 ? 2 * kCvtWarps : kCvtWarps);
+            mbar_init(barY + 8u * i, 1);
+            if (kSplit) {
+                mbar_init(barStaged + 8u * i, 4);
+                mbar_init(barFree + 8u * i, 1);
+            }
         }
         mbar_init(barB, 1);
-        mbar_init(barY, 1);
-        mbar_init(barY + 8u, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -1113,6 +1441,106 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             __syncwarp();
         }
     } else if (warp >= 2) {
+      if constexpr (kSplit) {
+        const bool finish = warp >= 6;        // finish group (warps 6-9) / convert group (warps 2-5)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int r = row;
+        const int i0 = r % P.b[0];
+        r /= P.b[0];
+        const int i1 = r % P.b[1];
+        r /= P.b[1];
+        const int i2 = r % P.b[2];
+        const int i3 = r / P.b[2];
+        const int eb = (threadIdx.x - 64) & (kGroupThreads - 1);   // thread index within the group
+        EpiArgs E;
+        E.addend = P.addend, E.bias = P.bias, E.part_sum = P.part_sum, E.part_sq = P.part_sq;
+        E.ncols = P.ncols, E.nbias = P.nbias, E.relu = P.relu, E.part_pitch = P.part_pitch;
+        E.debug = P.debug;
+        E.remote_arrive = k2 ? 1 : 0;
+        const uint32_t tmemEmptyBar = k2 ? mapa_shared(barTmemEmpty, 0) : barTmemEmpty;
+        float* statbuf = reinterpret_cast<float*>(smem + statOff);
+        E.bn_y = P.bn_y, E.bn_tab = P.bn_tab, E.bn_relu = P.bn_relu;
+        E.st_acc = statbuf;
+        E.mapY = &mapY, E.ybuf_u32 = base + ybufOff, E.bar_y = barY;
+        E.ynext_u32 = E.ybuf_u32, E.bar_ynext = barY, E.y_early = P.nybuf == 2;
+        E.y_rows = static_cast<uint32_t>(rows);
+        // columns this tile owns: a non-last N tile only owns n_step of its bn_tile computed columns
+        const int width = (n_tile + 1 < P.n_tiles) ? P.n_step : P.bn_tile;
+        auto tile_origin = [&](int it, int& o0, int& o1, int& o2, int& o3) {
+            const int mt = k2 ? 2 * it + static_cast<int>(rank) : it;
+            int m, m3;
+            o0 = fdivmod(mt, P.fd_tl0, m) * P.b[0];
+            o1 = fdivmod(m, P.fd_tl1, m) * P.b[1];
+            o2 = fdivmod(m, P.fd_tl2, m3) * P.b[2];
+            o3 = m3 * P.b[3];
+            return mt;
+        };
+        if (finish) {
+            if (P.bn_y != nullptr || P.part_sum != nullptr)   // running sums of this CTA start at zero
+                for (int i = eb; i < 2 * P.ncols; i += kGroupThreads) statbuf[i] = 0.f;
+            if (P.bn_y != nullptr) {
+                // rows of the y buffer that no box ever writes must not hold NaN bit patterns (0 * NaN in the column pass)
+                uint32_t* yz = reinterpret_cast<uint32_t*>(smem + ybufOff);
+                for (uint32_t i = eb; i < P.nybuf * stagingBytes / 4u; i += kGroupThreads) yz[i] = 0u;
+                fence_proxy_async_smem();
+            }
+            named_bar_sync(1, kGroupThreads);
+            if (P.bn_y != nullptr && eb == 0 && m_first < m_count) {
+                int o0, o1, o2, o3;
+                tile_origin(m_first, o0, o1, o2, o3);
+                load_y_tile(E, E.ybuf_u32, barY, width, n_origin, o0, o1, o2, o3);
+            }
+        }
+        E.next_origin = n_origin;
+        int local = 0;
+        for (int it = m_first; it < m_count; it += m_stride, ++local) {
+            int o0, o1, o2, o3;
+            tile_origin(it, o0, o1, o2, o3);
+            const uint32_t buf = local & 1;
+            // staging buffer of this tile and the parity of this use of it
+            const uint32_t sbi = P.nstg == 2 ? buf : 0u;
+            const uint32_t sb = sbi * stagingBytes;
+            E.bar_staged = barStaged + 8u * sbi, E.bar_free = barFree + 8u * sbi;
+            E.stg_phase = (P.nstg == 2 ? (local >> 1) : local) & 1u;
+            if (!finish) {
+                const bool valid = row < rows && (o0 + i0) < P.O[0] && (o1 + i1) < P.O[1] && (o2 + i2) < P.O[2] &&
+                                   (o3 + i3) < P.O[3];
+                const long long off = (long long)(o0 + i0) * P.os[0] + (long long)(o1 + i1) * P.os[1] +
+                                      (long long)(o2 + i2) * P.os[2] + (long long)(o3 + i3) * P.os[3];
+                E.bar_full = barTmemFull + 8u * buf, E.full_phase = (local >> 1) & 1u;
+                const uint32_t trow = tmem_base + buf * acc_stride + (static_cast<uint32_t>(q * 32) << 16);
+                epilogue_convert(E, smem + stagingOff + sb, trow, tmemEmptyBar + 8u * buf, width, n_origin, valid, off, row,
+                                 lane);
+            } else {
+                E.has_next = it + m_stride < m_count;
+                if (P.bn_y != nullptr) {
+                    if (E.has_next) tile_origin(it + m_stride, E.n0, E.n1, E.n2, E.n3);
+                    if (P.nybuf == 2) {   // y buffers and their barriers alternate with the tiles
+                        E.ybuf_u32 = base + ybufOff + buf * stagingBytes, E.bar_y = barY + 8u * buf, E.y_phase = (local >> 1) & 1u;
+                        E.ynext_u32 = base + ybufOff + (buf ^ 1u) * stagingBytes, E.bar_ynext = barY + 8u * (buf ^ 1u);
+                    } else {
+                        E.y_phase = local & 1u;
+                    }
+                }
+                epilogue_finish(E, &mapOut, base + stagingOff + sb, width, n_origin, o0, o1, o2, o3, eb, lane);
+            }
+        }
+        if (finish) {
+            if (eb == 0) tma_store_wait_all();
+            if (P.bn_y != nullptr) {
+                for (int i = eb; i < 2 * P.ncols; i += kGroupThreads) {   // (the last tile's named barrier ordered the sums)
+                    const int qn = i >= P.ncols ? 1 : 0;
+                    P.bn_partial[((long long)blockIdx.x * 4 + qn) * P.ncols + (i - qn * P.ncols)] = statbuf[i];
+                }
+            } else if (P.part_sum != nullptr) {
+                for (int i = eb; i < 2 * P.ncols; i += kGroupThreads) {
+                    const int qn = i >= P.ncols ? 1 : 0;
+                    (qn ? P.part_sq : P.part_sum)[(long long)blockIdx.x * P.part_pitch + (i - qn * P.ncols)] = statbuf[i];
+                }
+            }
+        }
+      } else {
         const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         const int row = q * 32 + lane;
@@ -1202,6 +1630,8 @@ igemm_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
                 (qn ? P.part_sq : P.part_sum)[(long long)blockIdx.x * P.part_pitch + (i - qn * P.ncols)] = statbuf[i];
             }
         }
+    
+      }
     }
     if (k2) cluster_sync_all();     // neither CTA leaves (or frees TMEM) while the pair still reads its shared memory
     else __syncthreads();
@@ -2335,6 +2765,12 @@ bool igemm_use_pair(int bn_tile, long long m_tiles) {
     const char* e = getenv("ZSV_2CTA");
     return !(e && atoi(e) == 0) && (bn_tile % 16) == 0 && m_tiles >= 2;
 }
+// Tiles of at most 64 output channels with two staging buffers run the split epilogue (convert / finish groups on
+// consecutive tiles); ZSV_EPI_SPLIT=0 keeps the single group everywhere.
+bool epilogue_split(int bn_tile, int nstg) {
+    const char* e = getenv("ZSV_EPI_SPLIT");
+    return !(e && atoi(e) == 0) && bn_tile <= 64 && nstg == 2;
+}
 // grid of the generic kernel (one BatchNorm partial row per CTA)
 int igemm_grid(int bn_tile, long long m_tiles, int n_tiles) {
     if (igemm_use_pair(bn_tile, m_tiles))
@@ -2392,9 +2828,13 @@ int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtenso
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(igemm_kmajor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_err = cudaFuncSetAttribute(igemm_kmajor_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(igemm_kmajor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            attr_err = cudaFuncSetAttribute(igemm_kmajor_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(igemm_kmajor_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(igemm_kmajor_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (attr_err != cudaSuccess)
         return fail(ZSV_ERR_CUDA, "cudaFuncSetAttribute(igemm) failed: %s", cudaGetErrorString(attr_err));
@@ -2417,6 +2857,7 @@ int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtenso
     }
     MapPack pack;
     for (int i = 0; i < kMaxMaps; ++i) pack.m[i] = maps[i];
+    const bool split = epilogue_split(a.bn_tile, a.nstg);
     if (two) {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
@@ -2426,10 +2867,13 @@ int launch_igemm(const CUtensorMap* maps, const CUtensorMap& mapB, const CUtenso
         attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
         pdl_attribute(&attr[1]);
         cfg.attrs = attr, cfg.numAttrs = 2;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_kmajor_kernel<true>, pack, mapB, mapOut, mapY ? *mapY : mapOut, a);
+        cudaError_t e = split ? cudaLaunchKernelEx(&cfg, igemm_kmajor_kernel<true, true>, pack, mapB, mapOut, mapY ? *mapY : mapOut, a)
+                              : cudaLaunchKernelEx(&cfg, igemm_kmajor_kernel<true, false>, pack, mapB, mapOut, mapY ? *mapY : mapOut, a);
         if (e != cudaSuccess) return fail(ZSV_ERR_CUDA, "launch of igemm_kmajor_kernel<pair> failed: %s", cudaGetErrorString(e));
+    } else if (split) {
+        zsv::launch(igemm_kmajor_kernel<false, true>, grid, kIgemmThreads, smem, stream, pack, mapB, mapOut, mapY ? *mapY : mapOut, a);
     } else {
-        zsv::launch(igemm_kmajor_kernel<false>, grid, kIgemmThreads, smem, stream, pack, mapB, mapOut, mapY ? *mapY : mapOut, a);
+        zsv::launch(igemm_kmajor_kernel<false, false>, grid, kIgemmThreads, smem, stream, pack, mapB, mapOut, mapY ? *mapY : mapOut, a);
     }
     ZSV_LAUNCH_CHECK("igemm_kmajor_kernel");
     return ZSV_OK;
@@ -2565,7 +3009,7 @@ HaloPlan plan_halo_impl(int W, int H, int T, int N, int kdim, int cols, int kt, 
         p.bn_tile = bn;
         p.n_step = n_step;
         p.n_tiles = nt;
-        p.smem = fixed + stages * (int)p.a_stage_bytes + 16 * stages + 64;
+        p.smem = fixed + stages * (int)p.a_stage_bytes + 16 * stages + 96;
         p.ok = true;
         return p;
     }
@@ -2691,9 +3135,13 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(igemm_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_err = cudaFuncSetAttribute(igemm_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(igemm_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            attr_err = cudaFuncSetAttribute(igemm_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(igemm_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(igemm_halo_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (attr_err != cudaSuccess)
         return fail(ZSV_ERR_CUDA, "cudaFuncSetAttribute(halo igemm) failed: %s", cudaGetErrorString(attr_err));
@@ -2710,6 +3158,7 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
         a.bn_partial = fuse->partial + (size_t)fuse->rows_used * 4 * a.ncols;
         fuse->rows_used += grid;
     }
+    const bool split = epilogue_split(p.bn_tile, p.nstg);
     if (p.pair) {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
@@ -2719,10 +3168,13 @@ int launch_halo(const HaloPlan& p, const void* act, int actC, int actPitch, cons
         attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
         pdl_attribute(&attr[1]);
         cfg.attrs = attr, cfg.numAttrs = 2;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, igemm_halo_kernel<true>, mA, mAt, mB, mBt, mO, mY, a);
+        cudaError_t e = split ? cudaLaunchKernelEx(&cfg, igemm_halo_kernel<true, true>, mA, mAt, mB, mBt, mO, mY, a)
+                              : cudaLaunchKernelEx(&cfg, igemm_halo_kernel<true, false>, mA, mAt, mB, mBt, mO, mY, a);
         if (e != cudaSuccess) return fail(ZSV_ERR_CUDA, "launch of igemm_halo_kernel<pair> failed: %s", cudaGetErrorString(e));
+    } else if (split) {
+        zsv::launch(igemm_halo_kernel<false, true>, grid, kIgemmThreads, p.smem, st, mA, mAt, mB, mBt, mO, mY, a);
     } else {
-        zsv::launch(igemm_halo_kernel<false>, grid, kIgemmThreads, p.smem, st, mA, mAt, mB, mBt, mO, mY, a);
+        zsv::launch(igemm_halo_kernel<false, false>, grid, kIgemmThreads, p.smem, st, mA, mAt, mB, mBt, mO, mY, a);
     }
     ZSV_LAUNCH_CHECK("igemm_halo_kernel");
     return ZSV_OK;
