@@ -3024,7 +3024,8 @@ HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int k
     const char* e = getenv("ZSV_HALO_2CTA");
     const int mode = e ? atoi(e) : -1;
     if (mode == 0) return one;
-    if (mode < 0 && one.ok && one.stages > (one.wshift ? 1 : 2)) return one;
+    const bool narrow_temporal = one.ok && !one.spatial && cols <= 64 && kdim > 64;
+    if (mode < 0 && one.ok && one.stages > (one.wshift ? 1 : 2) && !narrow_temporal) return one;
     const HaloPlan two = plan_halo_impl(W, H, T, N, kdim, cols, kt, kh, kw, scratch_mode, true);
     if (getenv("ZSV_DEBUG_PLAN"))
         fprintf(stderr, "[zsv] halo plan k=%d cols=%d taps=%dx%dx%d: single ok=%d stages=%d nstg=%d box=%d,%d,%d,%d | pair ok=%d stages=%d nstg=%d\n",
@@ -3032,6 +3033,10 @@ HaloPlan plan_halo(int W, int H, int T, int N, int kdim, int cols, int kt, int k
                 two.stages, two.nstg);
     if (!two.ok) return one;
     if (mode == 1) return two;
+    // narrow temporal convolutions with more than one channel chunk (144->64 fprop): the N = 64 MMAs saturate the
+    // shared-memory port (48 clk each, 43 in a pair: profiles/r02_mma_rate.txt) and, since the split epilogue took the
+    // statistics off the chain, the pair is faster (105.4 -> 97.9 us at batch 22; 45->64 with one chunk is not)
+    if (!one.spatial && one.ok && cols <= 64 && kdim > 64 && two.stages >= 3) return two;
     // measured (profiles/r01_halo_pair_ab.txt): the pair pays off where it reaches a 4-deep ring and the single-CTA
     // plan has at most two stages or does not exist (the generic kernel would run); epilogue-bound temporal
     // convolutions with a 3-stage single-CTA plan are faster as they are
