@@ -406,3 +406,38 @@ def test_halo_w_taps_by_descriptor_offset(case, monkeypatch):
         assert torch.equal(a, b)
     assert torch.allclose(outs["0"][3], outs["1"][3], rtol=1e-6, atol=1e-4)
     assert torch.allclose(outs["0"][4], outs["1"][4], rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("geom", [
+    (3, 8, 24, 24, 45, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0)),     # narrow tiles: split epilogue, single CTA
+    (3, 8, 24, 24, 64, 144, (1, 3, 3), (1, 1, 1), (0, 1, 1)),    # CTA pair; dgrad narrow (split), fprop wide
+    (2, 8, 24, 24, 144, 64, (3, 1, 1), (1, 1, 1), (1, 0, 0)),    # pair chosen for the narrow temporal fprop
+    (4, 4, 14, 14, 128, 288, (1, 3, 3), (1, 1, 1), (0, 1, 1)),   # generic K-major kernel, wide tiles
+], ids=lambda g: f"{g[4]}_{g[5]}")
+def test_passes_are_run_to_run_deterministic(geom):
+    """The warp-specialised kernels hand tiles between roles (TMA producer, MMA issuer, convert / finish epilogue groups)
+    through mbarriers; a protocol bug shows up as run-to-run differences.  Twelve runs of every pass on the same inputs
+    must be bit-identical (tools/stress_determinism.py is the longer version at layer-1 sizes)."""
+    from zeroshotvideoclassification_b200 import ops
+    N, T, H, W, cin, cout, k, s, p = geom
+    op = ops.Conv3d(N, T, H, W, cin, cout, k, s, p)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(N, T, H, W, cpad(cin), device="cuda", generator=g).to(torch.bfloat16)
+    x[..., cin:] = 0
+    w = torch.randn(cout, cin, *k, device="cuda", generator=g) * 0.05
+    wf, wd = op.pack(w)
+    y0, _, _ = op.fprop(x, wf, stats=True)
+    dy = torch.randn(y0.shape, device="cuda", generator=g).to(torch.bfloat16)
+    tab = torch.rand(cpad(cin), 4, device="cuda", generator=g)
+    ref = None
+    for _ in range(12):
+        y, ps, pq = op.fprop(x, wf, stats=True)
+        dz, part, r = op.dgrad_bn_fused(dy, wd, None, x, tab, True)
+        dw, _ = op.wgrad(x, dy)
+        torch.cuda.synchronize()
+        outs = [t.clone() for t in (y, ps.sum(0), pq.sum(0), op.dgrad(dy, wd), dz, part[:r, :2].sum(0), dw)]
+        if ref is None:
+            ref = outs
+        else:
+            for i, (a, b) in enumerate(zip(outs, ref)):
+                assert torch.equal(a, b), f"output {i} differs between runs"
