@@ -728,10 +728,12 @@ __device__ __forceinline__ void epilogue_finish(const EpiArgs& E, const CUtensor
 //   warp 0      : TMA producer -- runs ahead across tile boundaries through a `stages`-deep smem ring
 //   warp 1      : MMA issuer + TMEM owner -- two accumulator buffers in TMEM, so the epilogue of tile i overlaps
 //                 the mainloop of tile i+1
-//   warps 2..   : epilogue, kEpiWarps warps (TMEM lane quadrant = warp % 4; the warps of a quadrant take the 16-column
-//                 chunks round-robin; 16 warps were measured and are not faster than 8): tcgen05.ld -> bias/addend/ReLU -> bf16 -> swizzled staging -> TMA store, plus per-tile
-//                 BatchNorm partial sums.  The epilogue of a small-K tile is a latency chain (TMEM load, fences,
-//                 barriers) that bounds the whole kernel, hence the wide group.
+//   warps 2..9  : epilogue (TMEM lane quadrant = warp % 4): tcgen05.ld -> bias/addend/ReLU -> bf16 -> swizzled staging ->
+//                 TMA store, plus per-tile BatchNorm partial sums or the fused BatchNorm-backward column pass.
+//                 kSplit = false (tiles wider than 64 channels): one group of eight warps, the two warps of a quadrant
+//                 take the 16-column chunks round-robin (the read-out is the long part; 16 warps were measured and are
+//                 not faster than 8).  kSplit = true (tiles of <= 64 channels): a convert group (warps 2-5) and a finish
+//                 group (warps 6-9) work on consecutive tiles at the same time, see "Split epilogue" above.
 // ------------------------------------------------------------------------------------------------
 // k2 = CTA-pair variant (cluster of 2, tcgen05 cta_group::2): the pair computes two M tiles (one per CTA) against the same
 // N tile with M = 256 MMAs issued by the leader; every CTA loads its own A tile and HALF of the B tile (mapB then has a
@@ -1124,7 +1126,8 @@ igemm_kmajor_kernel(const __grid_constant__ MapPack mapsA,
 //     (bit-exact against the copy version, tests/test_gpu_conv.py).  Other box widths load kw W-shifted copies.
 // One staged chunk therefore feeds kw x S x ksteps MMAs: ~420 MAC per ingested byte for the 64->144 conv.
 // Channel tails of 16 / 32 use SWIZZLE_32B / SWIZZLE_64B tiles so they cost 1/4 / 1/2 of a full chunk.
-// Same persistent warp-specialised structure and epilogue as igemm_kmajor_kernel; a CTA keeps one N tile.
+// Same persistent warp-specialised structure and epilogue (single group or kSplit) as igemm_kmajor_kernel; a CTA keeps
+// one N tile.
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxCopies = 8;
 
